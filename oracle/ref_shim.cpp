@@ -1,0 +1,82 @@
+// ref_shim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Thin C ABI over the UNMODIFIED reference class PlmDCA
+// (/root/reference/pydca/plmdca/include/plmdca.h:16-84) so that tests and the
+// CPU-baseline leg of bench.py can call computeSeqsWeight / initFieldsAndCouplings
+// / gradient on caller-supplied buffers.  It is compiled together with the
+// reference's own sources, from where they lie, into oracle/_ref/ by
+// oracle/Makefile; no reference source is copied into this repository.
+//
+// The reference keeps its state private; the shim re-opens the class with the
+// access keyword redefined (layout is unaffected under the Itanium ABI).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
+
+#define private public
+#include "include/plmdca.h"
+#undef private
+
+extern "C" {
+
+void *ref_plm_create(const char *msa_file, unsigned biomolecule, unsigned seqs_len,
+                     unsigned q, float seqid, float lambda_h, float lambda_J,
+                     unsigned num_threads)
+{
+    try {
+        return new PlmDCA(msa_file, biomolecule, seqs_len, q, seqid, lambda_h,
+                          lambda_J, num_threads);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "ref_plm_create: %s\n", e.what());
+        return nullptr;
+    }
+}
+
+void ref_plm_destroy(void *p) { delete static_cast<PlmDCA *>(p); }
+
+unsigned ref_plm_num_seqs(void *p) { return static_cast<PlmDCA *>(p)->num_seqs; }
+
+void ref_plm_get_seqs(void *p, unsigned char *out)
+{
+    auto *o = static_cast<PlmDCA *>(p);
+    size_t k = 0;
+    for (auto const &s : o->seqs_int_form)
+        for (auto v : s) out[k++] = static_cast<unsigned char>(v);
+}
+
+void ref_plm_get_weights(void *p, float *out)
+{
+    auto *o = static_cast<PlmDCA *>(p);
+    std::copy(o->seqs_weight.begin(), o->seqs_weight.end(), out);
+}
+
+float ref_plm_meff(void *p) { return static_cast<PlmDCA *>(p)->Meff; }
+
+void ref_plm_set_threads(void *p, unsigned n) { static_cast<PlmDCA *>(p)->num_threads = n; }
+
+void ref_plm_init(void *p, float *x) { static_cast<PlmDCA *>(p)->initFieldsAndCouplings(x); }
+
+float ref_plm_gradient(void *p, const float *x, float *g)
+{
+    return static_cast<PlmDCA *>(p)->gradient(x, g);
+}
+
+// re-run the reweighting only (timing leg)
+void ref_plm_reweight(void *p, float *out)
+{
+    auto *o = static_cast<PlmDCA *>(p);
+    auto w = o->computeSeqsWeight();
+    if (out) std::copy(w.begin(), w.end(), out);
+}
+
+}  // extern "C"
