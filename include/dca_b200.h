@@ -1,0 +1,132 @@
+/*
+ * dca_b200.h -- C ABI of pydca_b200/_plmdcaBackend_b200.so, the B200-native
+ * replacement for pydca's DCA hot path.  Plain C: pointers and sizes only, no
+ * torch / C++ types.  Every function returns 0 on success (or a non-NULL
+ * pointer); on failure it returns non-zero / NULL and dca_last_error() holds the
+ * reason.  Nothing here throws across the ABI and nothing falls back to the CPU:
+ * without a CUDA device every compute entry point fails.
+ *
+ * Reference interfaces replaced (paths relative to the pydca source tree):
+ *   plmdcaBackend / freeFieldsAndCouplings   pydca/plmdca/plmdcaBackend.cpp:151-223,
+ *                                            bound by ctypes at pydca/plmdca/plmdca.py:79-89
+ *   lbfgs_evaluate_t (objective operator)    pydca/plmdca/lbfgs/include/lbfgs.h:380-419
+ *   PlmDCA::computeSeqsWeight                pydca/plmdca/plmdca_numerics.cpp:611-671
+ *   msa_numerics operator functions          pydca/meanfield_dca/msa_numerics.py:14-342,
+ *                                            called at pydca/meanfield_dca/meanfield_dca.py:371-548
+ *   FN / APC scoring loops                   pydca/plmdca/plmdca.py:437-524,
+ *                                            pydca/meanfield_dca/meanfield_dca.py:902-988
+ */
+#ifndef DCA_B200_H
+#define DCA_B200_H
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- diagnostics -------------------------------------------------------- */
+const char *dca_last_error(void);
+int dca_device_count(void);                 /* CUDA devices visible (0 => compute calls fail) */
+int dca_set_device(int device);
+unsigned long long dca_kernel_launches(void); /* kernels launched by this library so far */
+
+/* ---- the reference's own ABI (drop-in) ------------------------------------
+ * plmdcaBackend.cpp:151-156.  biomolecule: 1 = protein, anything else = RNA.
+ * msa_file: FASTA path.  Returns P = L*q + L(L-1)/2*q*q floats, fields first
+ * (index a + q*i), then J_ij (i<j) blocks in pair order, element a*q + b
+ * (plmdca_numerics.cpp:338-342).  The buffer is host memory owned by the
+ * library; release it with freeFieldsAndCouplings (plmdcaBackend.cpp:204).
+ * num_threads is accepted for signature compatibility and ignored (the work
+ * runs on the GPU).  Returns NULL on error (the reference aborts instead). */
+float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states,
+                     const char *msa_file, unsigned int seqs_len, float seqid,
+                     float lambda_h, float lambda_J, unsigned int max_iteration,
+                     unsigned int num_threads, bool verbose);
+void freeFieldsAndCouplings(void *h_and_J);
+
+/* ---- FASTA ingest (host logic) ----------------------------------------------
+ * plmdca_numerics.cpp:685-767 / fasta_reader.py:122-163: upper-case, encode to
+ * 0..q-1 (gap and every unknown letter = q-1), keep the first occurrence of
+ * each distinct sequence in file order.  *msa_out is malloc'd u8[N][seqs_len];
+ * free with dca_free_host.  Returns N (>0) or a negative error. */
+long dca_read_fasta(const char *msa_file, int biomolecule, int seqs_len, uint8_t **msa_out);
+void dca_free_host(void *p);
+
+/* ---- sequence reweighting ----------------------------------------------------
+ * counts[i] = #{ j : ident(i,j)/L > seqid }, self included (bit-exact integers).
+ * compare_f64 = 0: the C++ float32 compare (plmdca_numerics.cpp:642-643);
+ * compare_f64 = 1: the numba float64 compare (msa_numerics.py:46).
+ * Host buffers in, host buffer out; rows [row_lo,row_hi) only (0,N for all). */
+int dca_weights(const uint8_t *msa, long num_seqs, int seqs_len, double seqid,
+                int compare_f64, long row_lo, long row_hi, uint32_t *counts_out);
+
+/* ---- plmDCA objective / optimiser ------------------------------------------------
+ * A dca_plm handle owns the device-resident MSA, weights and work buffers of one
+ * objective (PlmDCA object of plmdca.h:16).  site_lo/site_hi shard the data term
+ * by sites for multi-GPU use (0, L for the whole objective). */
+typedef struct dca_plm dca_plm;
+dca_plm *dca_plm_create(const uint8_t *msa, const float *weights, long num_seqs,
+                        int seqs_len, int num_site_states, float lambda_h,
+                        float lambda_J, int site_lo, int site_hi);
+void dca_plm_destroy(dca_plm *p);
+long dca_plm_num_params(const dca_plm *p);
+/* carry = 1 (default) reproduces the reference's loop-carried prob_ni
+ * (plmdca_numerics.cpp:492,:499); carry = 0 is textbook plmDCA.  chunk / warm:
+ * chain length and warm-up overlap of the chunked scan (<=0 keeps the default 32/32). */
+int dca_plm_set_carry(dca_plm *p, int carry, int chunk, int warm);
+/* initial point, PlmDCA::initFieldsAndCouplings (plmdca_numerics.cpp:207-249) */
+int dca_plm_init(dca_plm *p, float *x_out_host);
+/* objective + gradient with HOST buffers (x in, g out, *fx out): PlmDCA::gradient
+ * (plmdca_numerics.cpp:436-607).  H2D of x and D2H of g are part of the call. */
+int dca_plm_eval(dca_plm *p, const float *x_host, float *g_host, double *fx_out);
+/* the lbfgs_evaluate_t contract on DEVICE pointers (no copies, no sync):
+ * scalars_out_host may be NULL; otherwise receives {fx, g.dir, g.g, x.x}. */
+int dca_plm_eval_device(dca_plm *p, const float *x_dev, float *g_dev,
+                        const float *dir_dev, double *scalars_out_host);
+/* optional collective for site-sharded objectives: sum g (n floats) and the
+ * n_scalars doubles at scalars_dev over all ranks; both are DEVICE pointers. */
+typedef int (*dca_allreduce_fn)(void *ctx, float *g_dev, long n, double *scalars_dev, int n_scalars);
+typedef struct {
+    int status;          /* libLBFGS code: 0 converged, -997 max iterations, -1001 line-search rounding ... */
+    int iterations;
+    int evaluations;     /* objective/gradient evaluations = 1 + sum of line-search trials */
+    float fx;
+    double device_ms;    /* CUDA-event time of the whole optimisation */
+    double timed_ms;     /* CUDA-event time after `warmup_iterations` iterations */
+    int timed_evaluations;
+} dca_fit_result;
+/* lbfgs() as configured at plmdcaBackend.cpp:68-81, starting from x_inout_host
+ * (host buffer, P floats; overwritten with the result). */
+int dca_plm_fit(dca_plm *p, float *x_inout_host, int max_iterations, int verbose,
+                int warmup_iterations, dca_allreduce_fn allreduce, void *allreduce_ctx,
+                dca_fit_result *result);
+
+/* ---- scoring --------------------------------------------------------------------
+ * Frobenius norm of the double-centred non-gap block of every J_ij, then APC
+ * (plmdca.py:437-524).  fn_out / fn_apc_out: double[L(L-1)/2] in pair order. */
+int dca_plm_fn_apc(const float *x_host, int seqs_len, int num_site_states,
+                   double *fn_out, double *fn_apc_out);
+
+/* ---- mean-field DCA operators (msa_numerics.py) ------------------------------------
+ * weights: float64[N] (1/counts).  fi_out: double[L][q] (gap column kept,
+ * :54-89).  fij_out: double[L(L-1)/2][q-1][q-1] in pair order (:183-229);
+ * may be NULL. */
+int dca_mf_freqs(const uint8_t *msa, const double *weights, long num_seqs, int seqs_len,
+                 int num_site_states, double *fi_out, double *fij_out);
+/* fused: frequencies -> pseudocount (:93-125, :232-267) -> covariance matrix
+ * C (n x n, n = L(q-1), :271-318) written row-major to corr_out. */
+int dca_mf_corr_mat(const uint8_t *msa, const double *weights, long num_seqs, int seqs_len,
+                    int num_site_states, double pseudocount, double *reg_fi_out,
+                    double *corr_out);
+/* couplings = -inv(C), C symmetric positive definite (:322-342). */
+int dca_mf_couplings(const double *corr, int n, double *couplings_out);
+/* FN + APC of the couplings matrix (meanfield_dca.py:902-988). */
+int dca_mf_fn_apc(const double *couplings, int seqs_len, int num_site_states,
+                  double *fn_out, double *fn_apc_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCA_B200_H */

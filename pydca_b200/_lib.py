@@ -1,0 +1,207 @@
+"""ctypes binding of pydca_b200/_plmdcaBackend_b200.so (include/dca_b200.h).
+
+The library is looked up exactly like the reference looks up its own backend
+(``glob('<pkgdir>/_plmdcaBackend*')``, pydca/plmdca/plmdca.py:33-38).  There is
+no CPU fallback: if the shared object is missing, or no CUDA device is visible,
+every compute call raises ``DcaBackendError``.
+"""
+import ctypes
+import glob
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+
+
+class DcaBackendError(RuntimeError):
+    """Raised when the CUDA backend is missing or a backend call fails."""
+
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_f32p = ctypes.POINTER(ctypes.c_float)
+_f64p = ctypes.POINTER(ctypes.c_double)
+
+#: int (*)(void *ctx, float *g_dev, long n, double *scalars_dev, int n_scalars)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long,
+                                ctypes.c_void_p, ctypes.c_int)
+
+
+class FitResult(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_int), ("iterations", ctypes.c_int), ("evaluations", ctypes.c_int),
+                ("fx", ctypes.c_float), ("device_ms", ctypes.c_double), ("timed_ms", ctypes.c_double),
+                ("timed_evaluations", ctypes.c_int)]
+
+
+def library_path():
+    paths = sorted(glob.glob(os.path.join(_PKG, "_plmdcaBackend*")))
+    if not paths:
+        raise DcaBackendError(
+            "pydca_b200 CUDA backend not built: no _plmdcaBackend*.so in %s "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C pydca_b200/csrc`)" % _PKG)
+    return paths[0]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared object with argtypes set (loaded once)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    L = ctypes.CDLL(library_path())
+    L.dca_last_error.restype = ctypes.c_char_p
+    L.dca_device_count.restype = ctypes.c_int
+    L.dca_set_device.argtypes = [ctypes.c_int]
+    L.dca_kernel_launches.restype = ctypes.c_ulonglong
+    # the reference's own ABI, same argtypes/restype as pydca/plmdca/plmdca.py:81-89
+    L.plmdcaBackend.argtypes = (ctypes.c_ushort, ctypes.c_ushort, ctypes.c_char_p, ctypes.c_uint,
+                                ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_uint,
+                                ctypes.c_uint, ctypes.c_bool)
+    L.plmdcaBackend.restype = ctypes.c_void_p
+    L.freeFieldsAndCouplings.argtypes = [ctypes.c_void_p]
+    L.freeFieldsAndCouplings.restype = None
+    L.dca_read_fasta.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_u8p)]
+    L.dca_read_fasta.restype = ctypes.c_long
+    L.dca_free_host.argtypes = [ctypes.c_void_p]
+    L.dca_free_host.restype = None
+    L.dca_weights.argtypes = [_u8p, ctypes.c_long, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                              ctypes.c_long, ctypes.c_long, _u32p]
+    L.dca_plm_create.argtypes = [_u8p, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                 ctypes.c_float, ctypes.c_int, ctypes.c_int]
+    L.dca_plm_create.restype = ctypes.c_void_p
+    L.dca_plm_destroy.argtypes = [ctypes.c_void_p]
+    L.dca_plm_destroy.restype = None
+    L.dca_plm_num_params.argtypes = [ctypes.c_void_p]
+    L.dca_plm_num_params.restype = ctypes.c_long
+    L.dca_plm_set_carry.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.dca_plm_init.argtypes = [ctypes.c_void_p, _f32p]
+    L.dca_plm_eval.argtypes = [ctypes.c_void_p, _f32p, _f32p, _f64p]
+    L.dca_plm_eval_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _f64p]
+    L.dca_plm_fit.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                              ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FitResult)]
+    L.dca_plm_fn_apc.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
+    L.dca_mf_freqs.argtypes = [_u8p, _f64p, ctypes.c_long, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
+    L.dca_mf_corr_mat.argtypes = [_u8p, _f64p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                  _f64p, _f64p]
+    L.dca_mf_couplings.argtypes = [_f64p, ctypes.c_int, _f64p]
+    L.dca_mf_fn_apc.argtypes = [_f64p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
+    _lib = L
+    return L
+
+
+def last_error():
+    return lib().dca_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise DcaBackendError("%s failed: %s" % (what, last_error()))
+
+
+def ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def biomolecule_int(biomolecule):
+    return 1 if biomolecule.strip().upper() == "PROTEIN" else 2
+
+
+# ---- thin array-level wrappers -----------------------------------------------
+def read_fasta(path, biomolecule, seqs_len):
+    """uint8[N, L] unique sequences (states 0..q-1) in first-occurrence order."""
+    out = _u8p()
+    n = lib().dca_read_fasta(os.fsencode(path), biomolecule_int(biomolecule), int(seqs_len), ctypes.byref(out))
+    if n <= 0:
+        raise DcaBackendError("reading %s failed: %s" % (path, last_error()))
+    arr = np.ctypeslib.as_array(out, shape=(n, int(seqs_len))).copy()
+    lib().dca_free_host(out)
+    return arr
+
+
+def sequence_counts(msa, seqid, compare_f64=False, rows=None):
+    """Neighbour counts c_i (uint32[N]); rows=(lo,hi) computes a shard only."""
+    msa = np.ascontiguousarray(msa, dtype=np.uint8)
+    n, l = msa.shape
+    lo, hi = (0, n) if rows is None else rows
+    counts = np.zeros(n, dtype=np.uint32)
+    check(lib().dca_weights(ptr(msa, _u8p), n, l, float(seqid), int(bool(compare_f64)), lo, hi,
+                            ptr(counts, _u32p)), "dca_weights")
+    return counts
+
+
+class PlmObjective:
+    """Device-resident plmDCA objective (the reference's C++ PlmDCA object)."""
+
+    def __init__(self, msa, weights, num_site_states, lambda_h, lambda_J, sites=None):
+        msa = np.ascontiguousarray(msa, dtype=np.uint8)
+        weights = np.ascontiguousarray(weights, dtype=np.float32)
+        n, l = msa.shape
+        lo, hi = (0, l) if sites is None else sites
+        self.N, self.L, self.q = n, l, int(num_site_states)
+        self._h = lib().dca_plm_create(ptr(msa, _u8p), ptr(weights, _f32p), n, l, self.q,
+                                       float(lambda_h), float(lambda_J), int(lo), int(hi))
+        if not self._h:
+            raise DcaBackendError("dca_plm_create failed: %s" % last_error())
+        self.P = int(lib().dca_plm_num_params(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dca_plm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_carry(self, carry=True, chunk=0, warm=-1):
+        check(lib().dca_plm_set_carry(self._h, int(bool(carry)), int(chunk), int(warm)), "dca_plm_set_carry")
+
+    def init(self):
+        x = np.zeros(self.P, dtype=np.float32)
+        check(lib().dca_plm_init(self._h, ptr(x, _f32p)), "dca_plm_init")
+        return x
+
+    def eval(self, x, out=None):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        g = np.empty(self.P, dtype=np.float32) if out is None else out
+        fx = ctypes.c_double()
+        check(lib().dca_plm_eval(self._h, ptr(x, _f32p), ptr(g, _f32p), ctypes.byref(fx)), "dca_plm_eval")
+        return fx.value, g
+
+    def eval_device(self, x_ptr, g_ptr, dir_ptr=None, read_scalars=True):
+        sc = np.zeros(4, dtype=np.float64)
+        check(lib().dca_plm_eval_device(self._h, x_ptr, g_ptr, dir_ptr,
+                                        ptr(sc, _f64p) if read_scalars else None), "dca_plm_eval_device")
+        return sc
+
+    def fit(self, x0, max_iterations, verbose=False, warmup_iterations=0, allreduce=None):
+        x = np.array(x0, dtype=np.float32, copy=True)
+        res = FitResult()
+        cb = ctypes.cast(allreduce, ctypes.c_void_p) if allreduce is not None else None
+        check(lib().dca_plm_fit(self._h, ptr(x, _f32p), int(max_iterations), int(bool(verbose)),
+                                int(warmup_iterations), cb, None, ctypes.byref(res)), "dca_plm_fit")
+        return x, res
+
+
+def plm_fn_apc(x, seqs_len, num_site_states):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    npairs = seqs_len * (seqs_len - 1) // 2
+    fn = np.zeros(npairs, dtype=np.float64)
+    apc = np.zeros(npairs, dtype=np.float64)
+    check(lib().dca_plm_fn_apc(ptr(x, _f32p), int(seqs_len), int(num_site_states), ptr(fn, _f64p),
+                               ptr(apc, _f64p)), "dca_plm_fn_apc")
+    return fn, apc
+
+
+def plmdca_backend(msa_file, biomolecule, seqs_len, num_site_states, seqid, lambda_h, lambda_J,
+                   max_iterations, num_threads=1, verbose=False):
+    """The reference's C entry point, called the way pydca/plmdca/plmdca.py:216-230 calls it."""
+    p = seqs_len * num_site_states + seqs_len * (seqs_len - 1) // 2 * num_site_states ** 2
+    h = lib().plmdcaBackend(biomolecule_int(biomolecule), num_site_states, os.fsencode(msa_file), seqs_len,
+                            seqid, lambda_h, lambda_J, max_iterations, num_threads, verbose)
+    if not h:
+        raise DcaBackendError("plmdcaBackend failed: %s" % last_error())
+    x = np.ctypeslib.as_array(ctypes.cast(h, _f32p), shape=(p,)).copy()
+    lib().freeFieldsAndCouplings(h)
+    return x

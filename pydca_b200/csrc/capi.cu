@@ -1,0 +1,296 @@
+// capi.cu -- the C ABI declared in include/dca_b200.h.
+//
+// Drop-in boundary of the reference: plmdcaBackend / freeFieldsAndCouplings
+// (pydca/plmdca/plmdcaBackend.cpp:151-223) plus array-based entry points for
+// each operator of the hot path.  Nothing throws across this boundary and there
+// is no CPU fallback: without a CUDA device every compute call fails.
+#include "dca_common.cuh"
+#include "dca_internal.h"
+#include "../../include/dca_b200.h"
+
+#include <cstdarg>
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace dca {
+
+unsigned long long g_launches = 0;
+
+static thread_local std::string t_error;
+static std::string g_error;
+static std::mutex g_error_mu;
+
+void set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_error = buf;
+    std::lock_guard<std::mutex> lk(g_error_mu);
+    g_error = buf;
+}
+
+const char *last_error() { return t_error.empty() ? g_error.c_str() : t_error.c_str(); }
+
+int require_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s): pydca_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return -1;
+    }
+    return 0;
+}
+
+int sm_count()
+{
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
+    }
+    return cached;
+}
+
+// mf.cu
+int mf_freqs_host(const uint8_t *msa, const double *w, long N, int L, int q, double *fi, double *fij);
+int mf_corr_mat_host(const uint8_t *msa, const double *w, long N, int L, int q, double pseudocount,
+                     double *reg_fi, double *corr);
+int mf_couplings_host(const double *corr, int n, double *out);
+int mf_fn_apc_host(const double *h_J, int L, int q, double *fn, double *fn_apc);
+
+}  // namespace dca
+
+using namespace dca;
+
+struct dca_plm {
+    PlmProblem *prob;
+    float *d_x, *d_g;
+};
+
+extern "C" {
+
+const char *dca_last_error(void) { return last_error(); }
+
+int dca_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int dca_set_device(int device)
+{
+    DCA_CUDA(cudaSetDevice(device));
+    return 0;
+}
+
+unsigned long long dca_kernel_launches(void) { return g_launches; }
+
+long dca_read_fasta(const char *msa_file, int biomolecule, int seqs_len, uint8_t **msa_out)
+{
+    if (!msa_file || !msa_out || seqs_len <= 0) { set_error("dca_read_fasta: bad arguments"); return -1; }
+    std::vector<uint8_t> buf;
+    const long n = read_fasta_unique(msa_file, biomolecule, seqs_len, buf);
+    if (n <= 0) return n;
+    uint8_t *out = (uint8_t *)malloc(buf.size());
+    if (!out) { set_error("dca_read_fasta: out of memory"); return -1; }
+    memcpy(out, buf.data(), buf.size());
+    *msa_out = out;
+    return n;
+}
+
+void dca_free_host(void *p) { free(p); }
+
+int dca_weights(const uint8_t *msa, long num_seqs, int seqs_len, double seqid, int compare_f64,
+                long row_lo, long row_hi, uint32_t *counts_out)
+{
+    if (require_device() != 0) return -1;
+    if (!msa || !counts_out || num_seqs <= 0 || seqs_len <= 0) { set_error("dca_weights: empty alignment"); return -1; }
+    if (row_lo < 0 || row_hi > num_seqs || row_lo >= row_hi) { set_error("dca_weights: bad row range"); return -1; }
+    if (!(seqid > 0.0) || seqid > 1.0) { set_error("dca_weights: seqid %g not in (0,1]", seqid); return -1; }
+    uint8_t *d_msa = nullptr;
+    unsigned *d_counts = nullptr;
+    DCA_CUDA(cudaMalloc(&d_msa, (size_t)num_seqs * seqs_len));
+    DCA_CUDA(cudaMalloc(&d_counts, sizeof(unsigned) * (size_t)num_seqs));
+    DCA_CUDA(cudaMemcpy(d_msa, msa, (size_t)num_seqs * seqs_len, cudaMemcpyHostToDevice));
+    int rc = reweight_counts_device(d_msa, num_seqs, seqs_len, seqid, compare_f64, row_lo, row_hi, d_counts, 0);
+    if (rc == 0) {
+        cudaError_t e = cudaMemcpy(counts_out + row_lo, d_counts + row_lo, sizeof(unsigned) * (size_t)(row_hi - row_lo),
+                                   cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("dca_weights: D2H failed: %s", cudaGetErrorString(e)); rc = -1; }
+    }
+    cudaFree(d_msa); cudaFree(d_counts);
+    return rc;
+}
+
+dca_plm *dca_plm_create(const uint8_t *msa, const float *weights, long num_seqs, int seqs_len,
+                        int num_site_states, float lambda_h, float lambda_J, int site_lo, int site_hi)
+{
+    if (!msa || !weights) { set_error("dca_plm_create: null input"); return nullptr; }
+    PlmProblem *prob = plm_create(msa, weights, num_seqs, seqs_len, num_site_states, lambda_h, lambda_J,
+                                  site_lo, site_hi);
+    if (!prob) return nullptr;
+    dca_plm *h = new (std::nothrow) dca_plm{prob, nullptr, nullptr};
+    if (!h) { plm_destroy(prob); set_error("out of memory"); return nullptr; }
+    const size_t bytes = sizeof(float) * (size_t)plm_num_params(prob);
+    if (cudaMalloc(&h->d_x, bytes) != cudaSuccess || cudaMalloc(&h->d_g, bytes) != cudaSuccess) {
+        set_error("dca_plm_create: cudaMalloc of x/g (%zu bytes) failed", bytes);
+        dca_plm_destroy(h);
+        return nullptr;
+    }
+    return h;
+}
+
+void dca_plm_destroy(dca_plm *p)
+{
+    if (!p) return;
+    cudaFree(p->d_x); cudaFree(p->d_g);
+    plm_destroy(p->prob);
+    delete p;
+}
+
+long dca_plm_num_params(const dca_plm *p) { return p ? plm_num_params(p->prob) : -1; }
+
+int dca_plm_set_carry(dca_plm *p, int carry, int chunk, int warm)
+{
+    if (!p) { set_error("null handle"); return -1; }
+    plm_set_carry(p->prob, carry, chunk, warm);
+    return 0;
+}
+
+int dca_plm_init(dca_plm *p, float *x_out_host)
+{
+    if (!p || !x_out_host) { set_error("dca_plm_init: null argument"); return -1; }
+    if (plm_init_x_device(p->prob, p->d_x) != 0) return -1;
+    DCA_CUDA(cudaMemcpyAsync(x_out_host, p->d_x, sizeof(float) * (size_t)plm_num_params(p->prob),
+                             cudaMemcpyDeviceToHost, plm_stream(p->prob)));
+    DCA_CUDA(cudaStreamSynchronize(plm_stream(p->prob)));
+    return 0;
+}
+
+int dca_plm_eval(dca_plm *p, const float *x_host, float *g_host, double *fx_out)
+{
+    if (!p || !x_host || !g_host) { set_error("dca_plm_eval: null argument"); return -1; }
+    cudaStream_t st = plm_stream(p->prob);
+    const size_t bytes = sizeof(float) * (size_t)plm_num_params(p->prob);
+    DCA_CUDA(cudaMemcpyAsync(p->d_x, x_host, bytes, cudaMemcpyHostToDevice, st));
+    if (plm_eval_device(p->prob, p->d_x, p->d_g, nullptr) != 0) return -1;
+    DCA_CUDA(cudaMemcpyAsync(g_host, p->d_g, bytes, cudaMemcpyDeviceToHost, st));
+    double h[PS_COUNT];
+    if (plm_read_scalars(p->prob, h) != 0) return -1;
+    if (fx_out) *fx_out = h[PS_FX];
+    return 0;
+}
+
+int dca_plm_eval_device(dca_plm *p, const float *x_dev, float *g_dev, const float *dir_dev,
+                        double *scalars_out_host)
+{
+    if (!p || !x_dev || !g_dev) { set_error("dca_plm_eval_device: null argument"); return -1; }
+    if (plm_eval_device(p->prob, x_dev, g_dev, dir_dev) != 0) return -1;
+    if (scalars_out_host) return plm_read_scalars(p->prob, scalars_out_host);
+    return 0;
+}
+
+int dca_plm_fit(dca_plm *p, float *x_inout_host, int max_iterations, int verbose, int warmup_iterations,
+                dca_allreduce_fn allreduce, void *allreduce_ctx, dca_fit_result *result)
+{
+    if (!p || !x_inout_host) { set_error("dca_plm_fit: null argument"); return -1; }
+    cudaStream_t st = plm_stream(p->prob);
+    const size_t bytes = sizeof(float) * (size_t)plm_num_params(p->prob);
+    DCA_CUDA(cudaMemcpyAsync(p->d_x, x_inout_host, bytes, cudaMemcpyHostToDevice, st));
+    LbfgsResult r{};
+    double timed_ms = 0.0;
+    int timed_evals = 0;
+    if (lbfgs_minimize(p->prob, p->d_x, max_iterations, verbose, (dca::allreduce_fn_t)allreduce,
+                       allreduce_ctx, &r, warmup_iterations, &timed_ms, &timed_evals) != 0)
+        return -1;
+    DCA_CUDA(cudaMemcpyAsync(x_inout_host, p->d_x, bytes, cudaMemcpyDeviceToHost, st));
+    DCA_CUDA(cudaStreamSynchronize(st));
+    if (result) {
+        result->status = r.status; result->iterations = r.iterations; result->evaluations = r.evaluations;
+        result->fx = r.fx; result->device_ms = r.device_ms; result->timed_ms = timed_ms;
+        result->timed_evaluations = timed_evals;
+    }
+    return 0;
+}
+
+int dca_plm_fn_apc(const float *x_host, int seqs_len, int num_site_states, double *fn_out, double *fn_apc_out)
+{
+    if (!x_host || !fn_out) { set_error("dca_plm_fn_apc: null argument"); return -1; }
+    return plm_fn_apc_host(x_host, seqs_len, num_site_states, fn_out, fn_apc_out);
+}
+
+// ---- the reference's own entry point -------------------------------------------
+float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states, const char *msa_file,
+                     unsigned int seqs_len, float seqid, float lambda_h, float lambda_J,
+                     unsigned int max_iteration, unsigned int num_threads, bool verbose)
+{
+    (void)num_threads;   // kept for signature compatibility: the work runs on the GPU
+    if (require_device() != 0) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); return nullptr; }
+    const int q = (int)num_site_states, L = (int)seqs_len;
+    if ((biomolecule == 1 && q != 21) || (biomolecule != 1 && q != 5)) {
+        set_error("plmdcaBackend: num_site_states %d does not match biomolecule %d", q, (int)biomolecule);
+        fprintf(stderr, "plmdcaBackend: %s\n", last_error());
+        return nullptr;
+    }
+    std::vector<uint8_t> msa;
+    const long N = read_fasta_unique(msa_file, biomolecule == 1 ? 1 : 2, L, msa);       // plmdca_numerics.cpp:43
+    if (N <= 0) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); return nullptr; }
+    std::vector<uint32_t> counts((size_t)N);
+    if (dca_weights(msa.data(), N, L, (double)seqid, 0, 0, N, counts.data()) != 0) {    // :45
+        fprintf(stderr, "plmdcaBackend: %s\n", last_error());
+        return nullptr;
+    }
+    std::vector<float> w((size_t)N);
+    for (long n = 0; n < N; ++n) w[n] = 1.f / (float)counts[n];                          // :669
+    dca_plm *h = dca_plm_create(msa.data(), w.data(), N, L, q, lambda_h, lambda_J, 0, L);
+    if (!h) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); return nullptr; }
+    const size_t P = (size_t)dca_plm_num_params(h);
+    float *x = (float *)malloc(sizeof(float) * P);                                       // plmdcaBackend.cpp:61
+    if (!x) { fprintf(stderr, "ERROR: Failed to allocate a memory block for variables.\n"); dca_plm_destroy(h); return nullptr; }
+    dca_fit_result res{};
+    int rc = dca_plm_init(h, x);                                                         // :77
+    if (rc == 0) rc = dca_plm_fit(h, x, (int)max_iteration, verbose ? 1 : 0, 0, nullptr, nullptr, &res);   // :81
+    dca_plm_destroy(h);
+    if (rc != 0) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); free(x); return nullptr; }
+    return x;
+}
+
+void freeFieldsAndCouplings(void *h_and_J) { free(h_and_J); }
+
+// ---- mean-field operators ---------------------------------------------------------
+int dca_mf_freqs(const uint8_t *msa, const double *weights, long num_seqs, int seqs_len,
+                 int num_site_states, double *fi_out, double *fij_out)
+{
+    if (!msa || !weights || !fi_out) { set_error("dca_mf_freqs: null argument"); return -1; }
+    return mf_freqs_host(msa, weights, num_seqs, seqs_len, num_site_states, fi_out, fij_out);
+}
+
+int dca_mf_corr_mat(const uint8_t *msa, const double *weights, long num_seqs, int seqs_len,
+                    int num_site_states, double pseudocount, double *reg_fi_out, double *corr_out)
+{
+    if (!msa || !weights || !corr_out) { set_error("dca_mf_corr_mat: null argument"); return -1; }
+    return mf_corr_mat_host(msa, weights, num_seqs, seqs_len, num_site_states, pseudocount, reg_fi_out, corr_out);
+}
+
+int dca_mf_couplings(const double *corr, int n, double *couplings_out)
+{
+    if (!corr || !couplings_out || n <= 0) { set_error("dca_mf_couplings: bad argument"); return -1; }
+    return mf_couplings_host(corr, n, couplings_out);
+}
+
+int dca_mf_fn_apc(const double *couplings, int seqs_len, int num_site_states, double *fn_out, double *fn_apc_out)
+{
+    if (!couplings || !fn_out) { set_error("dca_mf_fn_apc: null argument"); return -1; }
+    return mf_fn_apc_host(couplings, seqs_len, num_site_states, fn_out, fn_apc_out);
+}
+
+}  // extern "C"

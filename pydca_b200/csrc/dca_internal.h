@@ -1,0 +1,57 @@
+// dca_internal.h -- declarations shared by the translation units of
+// _plmdcaBackend_b200.so (not part of the public C ABI; see include/dca_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+
+namespace dca {
+
+// ---- fasta.cpp -----------------------------------------------------------------
+// FASTA -> u8 [N][L] (states 0..q-1, gap q-1), unique rows in first-occurrence order.
+long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uint8_t> &out);
+int encode_residue(int biomolecule, int c);
+
+// ---- reweight.cu -----------------------------------------------------------------
+int reweight_min_ident(int L, double seqid, int compare_f64);
+int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, int compare_f64,
+                           long row_lo, long row_hi, unsigned *d_counts, cudaStream_t stream);
+
+// ---- plm_eval.cu -------------------------------------------------------------------
+struct PlmProblem;   // device-resident state of one plmDCA objective
+
+// scalars every evaluation leaves on the device (double): see plm_eval.cu
+enum PlmScalar { PS_FX = 0, PS_DG = 1, PS_GG = 2, PS_XX = 3, PS_COUNT = 4 };
+
+PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
+                       float lambda_h, float lambda_J, int site_lo, int site_hi);
+void plm_destroy(PlmProblem *p);
+long plm_num_params(const PlmProblem *p);
+cudaStream_t plm_stream(const PlmProblem *p);
+void plm_set_carry(PlmProblem *p, int carry, int chunk, int warm);
+// objective + gradient at device x -> device g ; scalars (fx, g.d, g.g, x.x) left in
+// p's scalar buffer; d_dir may be null (then PS_DG = 0).  No host sync.
+int plm_eval_device(PlmProblem *p, const float *d_x, float *d_g, const float *d_dir);
+// copy the PS_COUNT scalars to the host (one small D2H + stream sync)
+int plm_read_scalars(PlmProblem *p, double *out);
+// initial point (plmdca_numerics.cpp:207-249) written to device x
+int plm_init_x_device(PlmProblem *p, float *d_x);
+double *plm_scalar_buffer(PlmProblem *p);
+
+// ---- lbfgs.cu --------------------------------------------------------------------------
+struct LbfgsResult {
+    int status;        // libLBFGS status code (lbfgs.h:78-150 numbering)
+    int iterations;
+    int evaluations;   // objective/gradient evaluations (1 + sum of line-search trials)
+    float fx;
+    double device_ms;  // CUDA-event time of the optimisation loop
+};
+typedef int (*allreduce_fn_t)(void *ctx, float *d_buf, long n, double *d_scalars, int n_scalars);
+int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
+                   allreduce_fn_t allreduce, void *allreduce_ctx, LbfgsResult *res,
+                   int warmup_iterations, double *timed_ms, int *timed_evals);
+
+// ---- scoring.cu ---------------------------------------------------------------------------
+int plm_fn_apc_host(const float *h_x, int L, int q, double *fn, double *fn_apc);
+
+}  // namespace dca

@@ -1,0 +1,514 @@
+// lbfgs.cu -- L-BFGS driver with device-resident vectors for the plmDCA objective.
+//
+// Replaces  lbfgs()                     pydca/plmdca/lbfgs/lib/lbfgs.cpp:248-644
+//           line_search_morethuente()   :815-1004
+//           update_trial_interval()     :1128-1295
+//           vector ops                  pydca/plmdca/lbfgs/include/arithmetic_ansi.h:51-133
+//           ObjectiveFunction::run      pydca/plmdca/plmdcaBackend.cpp:47-95 (parameters)
+//
+// Same algorithm and parameters as the reference's call site: m = 5,
+// epsilon = 1e-3, ftol = 1e-4, gtol = 0.9, xtol = 1e-16, max_linesearch = 5,
+// min_step = 1e-20, max_step = 1e20, More-Thuente line search, first step
+// 1/|g|, H0 = (y.s / y.y) I, revert to the previous point when the line search
+// fails.  Scalars are float like the reference's lbfgsfloatval_t (lbfgs.h:50-56
+// forces float).  What differs by construction: the 16 vectors of P floats
+// live in HBM, every vector pass is a fused kernel (the reference makes ~78
+// unfused passes per iteration, we make 2m+3), and dot products are reduced
+// in float64 in a fixed order (the reference's are sequential float32 sums, so
+// its trajectory is not reproducible even against itself, SURVEY finding 3).
+//
+// Host <-> device traffic per objective evaluation: one 32-byte D2H read of
+// {fx, g.d, g.g, x.x}.  The two-loop recursion never touches the host: its
+// scalars (alpha_j, beta, ys_j, ys/yy) stay in a small device buffer.
+#include "dca_common.cuh"
+#include "dca_internal.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace dca {
+
+namespace {
+
+constexpr int VEC_THREADS = 256;
+constexpr int LB_M = 5;
+
+// device scalar block (floats): [0..4] alpha_j, [5..9] ys_j, [10] coef, [11] scale
+enum { SC_ALPHA = 0, SC_YS = 5, SC_COEF = 10, SC_SCALE = 11, SC_FLOATS = 16 };
+
+// x = xp + stp * d with separate multiply and add (arithmetic_ansi.h:71-88:
+// veccpy then vecadd, no fused multiply-add on the reference's x86 target)
+__global__ void __launch_bounds__(VEC_THREADS)
+vec_step_kernel(float *__restrict__ x, const float *__restrict__ xp, const float *__restrict__ d,
+                float stp, long n)
+{
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x)
+        x[k] = __fadd_rn(xp[k], __fmul_rn(stp, d[k]));
+}
+
+// s = x - xp ; y = g - gp ; partial {y.s, y.y}      (lbfgs.cpp:546-557)
+__global__ void __launch_bounds__(VEC_THREADS)
+vec_update_sy_kernel(float *__restrict__ s, float *__restrict__ y, const float *__restrict__ x,
+                     const float *__restrict__ xp, const float *__restrict__ g,
+                     const float *__restrict__ gp, long n, double *__restrict__ partial)
+{
+    __shared__ double scratch[32];
+    double ys = 0.0, yy = 0.0;
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) {
+        const float sv = x[k] - xp[k];
+        const float yv = g[k] - gp[k];
+        s[k] = sv; y[k] = yv;
+        ys += (double)yv * sv;
+        yy += (double)yv * yv;
+    }
+    double r = block_sum(ys, scratch); if (threadIdx.x == 0) partial[2 * blockIdx.x] = r;
+    r = block_sum(yy, scratch);        if (threadIdx.x == 0) partial[2 * blockIdx.x + 1] = r;
+}
+
+// one fused pass of the two-loop recursion (lbfgs.cpp:568-601):
+//   mode 0: d = -g                       (vecncpy :575)
+//   mode 1: d += coef * u                (vecadd  :588 / :599), coef from device
+//   mode 2: d *= scale                   (vecscale :591), scale from device
+// followed, when v != null, by the partial dot v.d of the UPDATED d, which is
+// what the next step of the recursion needs (:585 / :596), or g.d for the
+// line search (:845).
+__global__ void __launch_bounds__(VEC_THREADS)
+vec_twoloop_kernel(float *__restrict__ d, const float *__restrict__ u, const float *__restrict__ v,
+                   const float *__restrict__ sc, int mode, long n, double *__restrict__ partial)
+{
+    __shared__ double scratch[32];
+    const float c = (mode == 1) ? sc[SC_COEF] : ((mode == 2) ? sc[SC_SCALE] : 0.f);
+    double dot = 0.0;
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) {
+        float dv;
+        if (mode == 0) dv = -u[k];
+        else if (mode == 1) dv = __fadd_rn(d[k], __fmul_rn(c, u[k]));
+        else dv = __fmul_rn(d[k], c);
+        d[k] = dv;
+        if (v) dot += (double)v[k] * dv;
+    }
+    if (v) {
+        const double r = block_sum(dot, scratch);
+        if (threadIdx.x == 0) partial[blockIdx.x] = r;
+    }
+}
+
+// plain partial dots {a.b, a.a} (multi-GPU path: g.d and g.g after the all-reduce)
+__global__ void __launch_bounds__(VEC_THREADS)
+vec_dots_kernel(const float *__restrict__ a, const float *__restrict__ b, long n,
+                double *__restrict__ partial)
+{
+    __shared__ double scratch[32];
+    double ab = 0.0, aa = 0.0;
+    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) {
+        const float av = a[k];
+        if (b) ab += (double)av * b[k];
+        aa += (double)av * av;
+    }
+    double r = block_sum(ab, scratch); if (threadIdx.x == 0) partial[2 * blockIdx.x] = r;
+    r = block_sum(aa, scratch);        if (threadIdx.x == 0) partial[2 * blockIdx.x + 1] = r;
+}
+
+// single CTA: reduce the partials in a fixed order and apply the scalar step.
+//   op 0: ys_slot = y.s ; scale = ys / yy                  (:556-558, :591)
+//   op 1: alpha_slot = (s.d) / ys_slot ; coef = -alpha      (:585-588)
+//   op 2: beta = (y.d) / ys_slot ; coef = alpha_slot - beta (:596-599)
+//   op 3: dscal[1] = sum (g.d for the line search)
+//   op 4: dscal[1] = sum0 (g.d), dscal[2] = sum1 (g.g)
+__global__ void __launch_bounds__(256)
+scalar_step_kernel(const double *__restrict__ partial, int nb, int stride, int op, int slot,
+                   float *__restrict__ sc, double *__restrict__ dscal)
+{
+    __shared__ double scratch[32];
+    double s0 = 0.0, s1 = 0.0;
+    for (int b = threadIdx.x; b < nb; b += 256) {
+        s0 += partial[(size_t)stride * b];
+        if (stride == 2) s1 += partial[2 * (size_t)b + 1];
+    }
+    s0 = block_sum(s0, scratch);
+    s1 = block_sum(s1, scratch);
+    if (threadIdx.x != 0) return;
+    if (op == 0) {
+        const float ys = (float)s0, yy = (float)s1;
+        sc[SC_YS + slot] = ys;
+        sc[SC_SCALE] = ys / yy;
+    } else if (op == 1) {
+        const float alpha = (float)s0 / sc[SC_YS + slot];
+        sc[SC_ALPHA + slot] = alpha;
+        sc[SC_COEF] = -alpha;
+    } else if (op == 2) {
+        const float beta = (float)s0 / sc[SC_YS + slot];
+        sc[SC_COEF] = sc[SC_ALPHA + slot] - beta;
+    } else if (op == 3) {
+        dscal[PS_DG] = s0;
+    } else {
+        dscal[PS_DG] = s0;
+        dscal[PS_GG] = s1;
+    }
+}
+
+// libLBFGS status codes (lbfgs.h:78-150; the enum counts up from -1024)
+enum {
+    ST_SUCCESS = 0, ST_STOP = 1, ST_ALREADY_MINIMIZED = 2,
+    ST_UNKNOWN = -1024, ST_LOGIC = -1023, ST_OUTOFMEMORY = -1022, ST_CANCELED = -1021,
+    ST_OUTOFINTERVAL = -1003, ST_INCORRECT_TMINMAX = -1002, ST_ROUNDING = -1001,
+    ST_MINSTEP = -1000, ST_MAXSTEP = -999, ST_MAXLINESEARCH = -998, ST_MAXITER = -997,
+    ST_WIDTHTOOSMALL = -996, ST_INVALIDPARAMS = -995, ST_INCREASEGRADIENT = -994
+};
+
+struct Params {
+    float epsilon = 1e-3f;          // plmdcaBackend.cpp:70
+    int max_linesearch = 5;         // :72
+    float ftol = 1e-4f;             // :73
+    float gtol = 0.9f;              // lbfgs.cpp:119 default
+    float xtol = 1.0e-16f;
+    float min_step = 1e-20f;
+    float max_step = 1e20f;
+};
+
+inline float max3f(float a, float b, float c) { return std::max(std::max(a, b), c); }
+
+// minimiser of the cubic through (u,fu,du),(v,fv,dv)            (lbfgs.cpp:1024-1038)
+inline float cubic_min(float u, float fu, float du, float v, float fv, float dv)
+{
+    const float d = v - u;
+    const float theta = (fu - fv) * 3 / d + du + dv;
+    const float s = max3f(std::fabs(theta), std::fabs(du), std::fabs(dv));
+    const float a = theta / s;
+    float gamma = s * std::sqrt(a * a - (du / s) * (dv / s));
+    if (v < u) gamma = -gamma;
+    const float p = gamma - du + theta;
+    const float q = gamma - du + gamma + dv;
+    return u + (p / q) * d;
+}
+
+// variant used when the derivative keeps its sign and shrinks    (:1052-1072)
+inline float cubic_min_bounded(float u, float fu, float du, float v, float fv, float dv,
+                               float xmin, float xmax)
+{
+    const float d = v - u;
+    const float theta = (fu - fv) * 3 / d + du + dv;
+    const float s = max3f(std::fabs(theta), std::fabs(du), std::fabs(dv));
+    const float a = theta / s;
+    float gamma = s * std::sqrt(std::max(0.f, a * a - (du / s) * (dv / s)));
+    if (u < v) gamma = -gamma;
+    const float p = gamma - dv + theta;
+    const float q = gamma - dv + gamma + du;
+    const float r = p / q;
+    if (r < 0.f && gamma != 0.f) return v - r * d;
+    return (a < 0) ? xmax : xmin;
+}
+
+inline float quad_min(float u, float fu, float du, float v, float fv)
+{   // :1083-1085
+    const float a = v - u;
+    return u + du / ((fu - fv) / a + du) / 2 * a;
+}
+
+inline float secant_min(float u, float du, float v, float dv)
+{   // :1095-1097
+    const float a = u - v;
+    return v + dv / (dv - du) * a;
+}
+
+// More-Thuente safeguarded step + interval update               (:1128-1295)
+int update_interval(float &x, float &fx, float &dx, float &y, float &fy, float &dy,
+                    float &t, float &ft, float &dt, float tmin, float tmax, int &brackt)
+{
+    const bool dsign = (dt * (dx / std::fabs(dx))) < 0.;     // fsigndiff, non-IEEE branch (:64)
+    if (brackt) {
+        if (t <= std::min(x, y) || std::max(x, y) <= t) return ST_OUTOFINTERVAL;
+        if (0. <= dx * (t - x)) return ST_INCREASEGRADIENT;
+        if (tmax < tmin) return ST_INCORRECT_TMINMAX;
+    }
+    bool bound;
+    float newt;
+    if (fx < ft) {                       // higher value: minimum bracketed
+        brackt = 1; bound = true;
+        const float mc = cubic_min(x, fx, dx, t, ft, dt);
+        const float mq = quad_min(x, fx, dx, t, ft);
+        newt = (std::fabs(mc - x) < std::fabs(mq - x)) ? mc : mc + 0.5 * (mq - mc);
+    } else if (dsign) {                  // lower value, derivative changed sign
+        brackt = 1; bound = false;
+        const float mc = cubic_min(x, fx, dx, t, ft, dt);
+        const float mq = secant_min(x, dx, t, dt);
+        newt = (std::fabs(mc - t) > std::fabs(mq - t)) ? mc : mq;
+    } else if (std::fabs(dt) < std::fabs(dx)) {   // lower value, same sign, derivative shrinks
+        bound = true;
+        const float mc = cubic_min_bounded(x, fx, dx, t, ft, dt, tmin, tmax);
+        const float mq = secant_min(x, dx, t, dt);
+        if (brackt) newt = (std::fabs(t - mc) < std::fabs(t - mq)) ? mc : mq;
+        else        newt = (std::fabs(t - mc) > std::fabs(t - mq)) ? mc : mq;
+    } else {                             // lower value, same sign, derivative does not shrink
+        bound = false;
+        if (brackt) newt = cubic_min(t, ft, dt, y, fy, dy);
+        else newt = (x < t) ? tmax : tmin;
+    }
+    if (fx < ft) { y = t; fy = ft; dy = dt; }
+    else {
+        if (dsign) { y = x; fy = fx; dy = dx; }
+        x = t; fx = ft; dx = dt;
+    }
+    if (tmax < newt) newt = tmax;
+    if (newt < tmin) newt = tmin;
+    if (brackt && bound) {
+        const float mq = x + 0.66 * (y - x);
+        if (x < y) { if (mq < newt) newt = mq; }
+        else       { if (newt < mq) newt = mq; }
+    }
+    t = newt;
+    return 0;
+}
+
+struct Driver {
+    PlmProblem *p;
+    long n;
+    cudaStream_t st;
+    int blocks;
+    float *x = nullptr, *xp = nullptr, *g = nullptr, *gp = nullptr, *d = nullptr;
+    float *s[LB_M] = {nullptr}, *y[LB_M] = {nullptr};
+    float *sc = nullptr;
+    double *partial = nullptr;
+    allreduce_fn_t allreduce = nullptr;
+    void *ctx = nullptr;
+    int evals = 0;
+
+    int alloc()
+    {
+        float **v[] = {&xp, &g, &gp, &d};
+        for (auto pp : v) DCA_CUDA(cudaMalloc(pp, sizeof(float) * (size_t)n));
+        for (int i = 0; i < LB_M; ++i) {
+            DCA_CUDA(cudaMalloc(&s[i], sizeof(float) * (size_t)n));
+            DCA_CUDA(cudaMalloc(&y[i], sizeof(float) * (size_t)n));
+        }
+        DCA_CUDA(cudaMalloc(&sc, sizeof(float) * SC_FLOATS));
+        DCA_CUDA(cudaMemsetAsync(sc, 0, sizeof(float) * SC_FLOATS, st));
+        DCA_CUDA(cudaMalloc(&partial, sizeof(double) * 2 * (size_t)blocks));
+        return 0;
+    }
+    void release(float *keep_x)
+    {
+        float *v[] = {x, xp, g, gp, d};
+        for (float *q : v) if (q && q != keep_x) cudaFree(q);
+        for (int i = 0; i < LB_M; ++i) { cudaFree(s[i]); cudaFree(y[i]); }
+        cudaFree(sc); cudaFree(partial);
+    }
+
+    // objective at x -> g ; returns {fx, g.d, g.g, x.x} on the host
+    int evaluate(const float *dir, double *h)
+    {
+        ++evals;
+        if (!allreduce) {
+            if (plm_eval_device(p, x, g, dir) != 0) return -1;
+            return plm_read_scalars(p, h);
+        }
+        if (plm_eval_device(p, x, g, nullptr) != 0) return -1;
+        DCA_CUDA(cudaStreamSynchronize(st));
+        if (allreduce(ctx, g, n, plm_scalar_buffer(p), PS_COUNT) != 0) {
+            set_error("lbfgs: all-reduce callback failed");
+            return -1;
+        }
+        DCA_LAUNCH(vec_dots_kernel, blocks, VEC_THREADS, 0, st, g, dir, n, partial);
+        DCA_LAUNCH(scalar_step_kernel, 1, 256, 0, st, partial, blocks, 2, 4, 0, sc, plm_scalar_buffer(p));
+        return plm_read_scalars(p, h);
+    }
+};
+
+}  // namespace
+
+int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
+                   allreduce_fn_t allreduce, void *allreduce_ctx, LbfgsResult *res,
+                   int warmup_iterations, double *timed_ms, int *timed_evals)
+{
+    const Params prm;
+    Driver D;
+    D.p = p; D.n = plm_num_params(p); D.st = plm_stream(p);
+    D.blocks = std::min<long>(ceil_div<long>(D.n, VEC_THREADS * 4), 8L * sm_count());
+    D.x = d_x; D.allreduce = allreduce; D.ctx = allreduce_ctx;
+    if (D.alloc() != 0) { D.release(d_x); return -1; }
+    cudaStream_t st = D.st;
+    const long n = D.n;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evw = nullptr;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&evw);
+    cudaEventRecord(ev0, st);
+    bool warm_marked = (warmup_iterations <= 0);
+    int evals_at_warm = 0;
+    if (warm_marked) cudaEventRecord(evw, st);
+
+    int ret = ST_UNKNOWN;
+    int k = 1, end = 0, ls = 0;
+    double h[PS_COUNT];
+    float fx = 0.f, xnorm = 0.f, gnorm = 0.f, step = 0.f, dginit = 0.f;
+    int rc = 0;
+
+#define LB_CHECK(expr) do { if ((expr) != 0) { rc = -1; goto done; } } while (0)
+
+    LB_CHECK(D.evaluate(nullptr, h));                                    // lbfgs.cpp:415
+    fx = (float)h[PS_FX];
+    DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.g, (const float *)nullptr, D.sc, 0, n, D.partial);
+    xnorm = (float)std::sqrt(h[PS_XX]);
+    gnorm = (float)std::sqrt(h[PS_GG]);
+    if (xnorm < 1.0f) xnorm = 1.0f;
+    if (gnorm / xnorm <= prm.epsilon) { ret = ST_ALREADY_MINIMIZED; goto done; }   // :450-454
+    step = (float)(1.0 / std::sqrt(h[PS_GG]));                           // :459 (d = -g)
+    dginit = -(float)h[PS_GG];
+
+    for (;;) {
+        if (!warm_marked && k > warmup_iterations) {
+            cudaEventRecord(evw, st); warm_marked = true; evals_at_warm = D.evals;
+        }
+        std::swap(D.x, D.xp);                                            // veccpy(xp,x) :465
+        std::swap(D.g, D.gp);                                            // veccpy(gp,g) :466
+
+        // ---- More-Thuente line search (:815-1004) on phi(t) = f(xp + t d) ----
+        {
+            int count = 0, brackt = 0, stage1 = 1, uinfo = 0;
+            float dg = 0.f, f = fx;
+            float stx = 0.f, fxb = fx, dgx = dginit;
+            float sty = 0.f, fy = fx, dgy = dginit;
+            const float finit = fx;
+            float stmin, stmax;
+            if (step <= 0.f) { ls = ST_INVALIDPARAMS; goto ls_done; }
+            if (0 < dginit) { ls = ST_INCREASEGRADIENT; goto ls_done; }
+            {
+                const float dgtest = prm.ftol * dginit;
+                float width = prm.max_step - prm.min_step;
+                float prev_width = 2.0 * width;
+                for (;;) {
+                    if (brackt) { stmin = std::min(stx, sty); stmax = std::max(stx, sty); }
+                    else { stmin = stx; stmax = step + 4.0 * (step - stx); }
+                    if (step < prm.min_step) step = prm.min_step;
+                    if (prm.max_step < step) step = prm.max_step;
+                    if ((brackt && ((step <= stmin || stmax <= step) || prm.max_linesearch <= count + 1 || uinfo != 0)) ||
+                        (brackt && (stmax - stmin <= prm.xtol * stmax)))
+                        step = stx;
+
+                    DCA_LAUNCH(vec_step_kernel, D.blocks, VEC_THREADS, 0, st, D.x, D.xp, D.d, step, n);
+                    LB_CHECK(D.evaluate(D.d, h));
+                    f = (float)h[PS_FX];
+                    dg = (float)h[PS_DG];
+                    const float ftest1 = finit + step * dgtest;
+                    ++count;
+
+                    if (brackt && ((step <= stmin || stmax <= step) || uinfo != 0)) { ls = ST_ROUNDING; break; }
+                    if (step == prm.max_step && f <= ftest1 && dg <= dgtest) { ls = ST_MAXSTEP; break; }
+                    if (step == prm.min_step && (ftest1 < f || dgtest <= dg)) { ls = ST_MINSTEP; break; }
+                    if (brackt && (stmax - stmin) <= prm.xtol * stmax) { ls = ST_WIDTHTOOSMALL; break; }
+                    if (prm.max_linesearch <= count) { ls = ST_MAXLINESEARCH; break; }
+                    if (f <= ftest1 && std::fabs(dg) <= prm.gtol * (-dginit)) { ls = count; break; }
+
+                    if (stage1 && f <= ftest1 && std::min(prm.ftol, prm.gtol) * dginit <= dg) stage1 = 0;
+                    if (stage1 && ftest1 < f && f <= fxb) {
+                        float fm = f - step * dgtest, fxm = fxb - stx * dgtest, fym = fy - sty * dgtest;
+                        float dgm = dg - dgtest, dgxm = dgx - dgtest, dgym = dgy - dgtest;
+                        uinfo = update_interval(stx, fxm, dgxm, sty, fym, dgym, step, fm, dgm, stmin, stmax, brackt);
+                        fxb = fxm + stx * dgtest; fy = fym + sty * dgtest;
+                        dgx = dgxm + dgtest; dgy = dgym + dgtest;
+                    } else {
+                        uinfo = update_interval(stx, fxb, dgx, sty, fy, dgy, step, f, dg, stmin, stmax, brackt);
+                    }
+                    if (brackt) {
+                        if (0.66 * prev_width <= std::fabs(sty - stx)) step = stx + 0.5 * (sty - stx);
+                        prev_width = width;
+                        width = std::fabs(sty - stx);
+                    }
+                }
+            }
+            fx = f;
+        ls_done:;
+        }
+        if (ls < 0) {                                                    // :478-484
+            std::swap(D.x, D.xp);
+            std::swap(D.g, D.gp);
+            ret = ls;
+            // fx reported by the reference here is the failed trial's value (:622)
+            break;
+        }
+        xnorm = (float)std::sqrt(h[PS_XX]);                              // :487-492
+        gnorm = (float)std::sqrt(h[PS_GG]);
+        if (verbose) {                                                   // plmdcaBackend.cpp:137-146
+            fprintf(stderr, "Iteration %d:\n", k);
+            fprintf(stderr, "fx = %f, xnorm = %f, gnorm = %f, step = %f\n", fx, xnorm, gnorm, step);
+            fprintf(stderr, "\n");
+        }
+        if (xnorm < 1.0f) xnorm = 1.0f;
+        if (gnorm / xnorm <= prm.epsilon) { ret = ST_SUCCESS; break; }   // :506-511
+        if (max_iterations != 0 && max_iterations < k + 1) { ret = ST_MAXITER; break; }   // :535-539
+
+        // ---- history update + two-loop recursion, all on the device (:546-601) ----
+        DCA_LAUNCH(vec_update_sy_kernel, D.blocks, VEC_THREADS, 0, st,
+                   D.s[end], D.y[end], D.x, D.xp, D.g, D.gp, n, D.partial);
+        DCA_LAUNCH(scalar_step_kernel, 1, 256, 0, st, D.partial, D.blocks, 2, 0, end, D.sc, plm_scalar_buffer(p));
+        {
+            const int bound = (LB_M <= k) ? LB_M : k;
+            ++k;
+            end = (end + 1) % LB_M;
+            int j = end;
+            // d = -g fused with the first s_j . d
+            int jn = (j + LB_M - 1) % LB_M;
+            DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.g, D.s[jn], D.sc, 0, n, D.partial);
+            for (int i = 0; i < bound; ++i) {
+                j = (j + LB_M - 1) % LB_M;
+                DCA_LAUNCH(scalar_step_kernel, 1, 256, 0, st, D.partial, D.blocks, 1, 1, j, D.sc, plm_scalar_buffer(p));
+                // d -= alpha_j y_j, then dot with the next s (or nothing on the last level)
+                const float *nextv = (i + 1 < bound) ? D.s[(j + LB_M - 1) % LB_M] : nullptr;
+                DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.y[j], nextv, D.sc, 1, n, D.partial);
+            }
+            // d *= ys/yy, fused with y_j . d of the oldest level
+            DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, (const float *)nullptr, D.y[j], D.sc, 2, n, D.partial);
+            for (int i = 0; i < bound; ++i) {
+                DCA_LAUNCH(scalar_step_kernel, 1, 256, 0, st, D.partial, D.blocks, 1, 2, j, D.sc, plm_scalar_buffer(p));
+                const int jnext = (j + 1) % LB_M;
+                // d += (alpha_j - beta) s_j, then dot with the next y, or with g for the line search
+                const float *nextv = (i + 1 < bound) ? D.y[jnext] : D.g;
+                DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.s[j], nextv, D.sc, 1, n, D.partial);
+                j = jnext;
+            }
+            DCA_LAUNCH(scalar_step_kernel, 1, 256, 0, st, D.partial, D.blocks, 1, 3, 0, D.sc, plm_scalar_buffer(p));
+        }
+        {   // g.d of the new direction (needed by the line search, :845)
+            double hh[PS_COUNT];
+            LB_CHECK(plm_read_scalars(p, hh));
+            dginit = (float)hh[PS_DG];
+        }
+        step = 1.0f;                                                     // :617
+    }
+
+done:
+#undef LB_CHECK
+    cudaEventRecord(ev1, st);
+    cudaStreamSynchronize(st);
+    if (!warm_marked) { cudaEventRecord(evw, st); cudaStreamSynchronize(st); evals_at_warm = D.evals; }
+    float ms_total = 0.f, ms_timed = 0.f;
+    cudaEventElapsedTime(&ms_total, ev0, ev1);
+    cudaEventElapsedTime(&ms_timed, evw, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evw);
+    if (rc == 0 && D.x != d_x) {
+        // the caller's buffer must hold the result: copy, then swap ownership back
+        cudaMemcpyAsync(d_x, D.x, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st);
+        cudaStreamSynchronize(st);
+        if (D.xp == d_x) D.xp = D.x;
+        D.x = d_x;
+    } else if (D.x != d_x) {
+        if (D.xp == d_x) D.xp = D.x;
+        D.x = d_x;
+    }
+    D.release(d_x);
+    if (res) {
+        res->status = ret; res->iterations = k; res->evaluations = D.evals;
+        res->fx = fx; res->device_ms = ms_total;
+    }
+    if (timed_ms) *timed_ms = ms_timed;
+    if (timed_evals) *timed_evals = D.evals - evals_at_warm;
+    if (rc == 0 && verbose) {                                            // plmdcaBackend.cpp:82-91
+        if (ret == ST_ROUNDING) fprintf(stderr, "L-BFGS optimization completed\n");
+        else {
+            fprintf(stderr, "L-BFGS optimization terminated with status code = %d\n", ret);
+            fprintf(stderr, "fx = %f\n", fx);
+        }
+    }
+    return rc;
+}
+
+}  // namespace dca

@@ -1,0 +1,528 @@
+// mf.cu -- mean-field DCA operators on sm_100a.
+//
+// Replaces (pydca/meanfield_dca/msa_numerics.py):
+//   compute_single_site_freqs :54-89     get_reg_single_site_freqs :93-125
+//   compute_pair_site_freqs   :183-229   get_reg_pair_site_freqs   :232-267
+//   construct_corr_mat        :271-318   compute_couplings         :322-342
+//
+// 1. pair frequencies.  F[(j,b)][(i,a)] = sum_n w_n [s_nj==b][s_ni==a] in
+//    float64 -- the same "bucketed gather" as the plmDCA scatter kernel: the
+//    weighted one-hot rows of a 128-sequence chunk are generated in shared
+//    memory from the u8 MSA (never materialised in HBM), one warp per site j
+//    walks the chunk in residue-bucket order and keeps q double2 accumulators
+//    per lane: no atomics, fixed summation order.  The diagonal blocks of F are
+//    the single-site counts (F[(i,a)][(i,a)] = sum_n w_n [s_ni==a]).
+// 2. pseudocount + covariance assembly fused in one pass over F.
+// 3. couplings = -C^{-1}: blocked Gauss-Jordan inversion without pivoting (C is
+//    symmetric positive definite by construction when pseudocount > 0), block
+//    size 128; all O(n^3) work is rank-128 updates done by a float64
+//    tensor-core GEMM kernel (mma.sync.m8n8k4.f64, "DMMA"; tcgen05 has no
+//    FP64).  The reference uses LAPACK getrf/getri through numba; results
+//    agree to O(cond * eps).
+#include "dca_common.cuh"
+#include "dca_internal.h"
+
+#include <algorithm>
+#include <vector>
+
+namespace dca {
+
+// perm records are shared with plm_eval.cu's scatter (same layout)
+constexpr int MF_CH = 128;
+constexpr int MF_TC = 64;          // columns per CTA: 32 lanes x double2
+constexpr int MF_WARPS = 16;
+constexpr int MF_PERM_CNT = 32;
+constexpr int MF_PERM_REC = 224;
+
+template <int Q>
+__global__ void mf_build_perm_kernel(const uint8_t *__restrict__ msa, long N, int L, int nchunk,
+                                     uint8_t *__restrict__ perm)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)L * nchunk) return;
+    const int j = (int)(idx / nchunk);
+    const int c = (int)(idx - (long)j * nchunk);
+    const long n0 = (long)c * MF_CH;
+    const int rows = (int)min((long)MF_CH, N - n0);
+    uint8_t *rec = perm + idx * MF_PERM_REC;
+    int cnt[Q], pos[Q];
+#pragma unroll
+    for (int b = 0; b < Q; ++b) cnt[b] = 0;
+    for (int r = 0; r < rows; ++r) {
+        const int v = msa[(n0 + r) * L + j];
+#pragma unroll
+        for (int b = 0; b < Q; ++b) cnt[b] += (v == b);
+    }
+    int off = 0;
+#pragma unroll
+    for (int b = 0; b < Q; ++b) { rec[b] = (uint8_t)cnt[b]; pos[b] = off; off += (cnt[b] + 3) & ~3; }
+    for (int r = 0; r < rows; ++r) {
+        const int v = msa[(n0 + r) * L + j];
+        int where = 0;
+#pragma unroll
+        for (int b = 0; b < Q; ++b)
+            if (v == b) { where = pos[b]; pos[b] = where + 1; }
+        rec[MF_PERM_CNT + where] = (uint8_t)r;
+    }
+}
+
+template <int Q>
+__global__ void __launch_bounds__(MF_WARPS * 32, 1)
+mf_pairfreq_kernel(const uint8_t *__restrict__ msa, const double *__restrict__ w,
+                   const uint8_t *__restrict__ perm, int nchunk, long N, int L, int ld,
+                   double *__restrict__ F, size_t f_split_stride, int chunks_per_split)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *Rs = reinterpret_cast<double *>(smem_raw);                                   // [2][MF_CH][MF_TC]
+    uint8_t *recs = smem_raw + sizeof(double) * 2 * MF_CH * MF_TC;                       // [2][MF_WARPS][REC]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col0 = blockIdx.x * MF_TC;
+    const int j = blockIdx.y * MF_WARPS + warp;
+    const int c0 = blockIdx.z * chunks_per_split;
+    const int c1 = min(nchunk, c0 + chunks_per_split);
+    const int Lq = L * Q;
+
+    double2 acc[Q];
+#pragma unroll
+    for (int b = 0; b < Q; ++b) acc[b] = make_double2(0.0, 0.0);
+
+    // this thread's two columns are fixed: precompute (site, state)
+    const int cA = col0 + 2 * lane, cB = cA + 1;
+    const int iA = cA / Q, aA = cA - iA * Q, iB = cB / Q, aB = cB - iB * Q;
+    const bool okA = cA < Lq, okB = cB < Lq;
+
+    auto gen = [&](int buf, int c) {
+        double *dst = Rs + (size_t)buf * MF_CH * MF_TC;
+        const long nb = (long)c * MF_CH;
+        const int rows = (int)min((long)MF_CH, N - nb);
+        for (int row = warp; row < rows; row += MF_WARPS) {
+            const long n = nb + row;
+            const double wn = w[n];
+            double2 v;
+            v.x = (okA && msa[n * L + iA] == aA) ? wn : 0.0;
+            v.y = (okB && msa[n * L + iB] == aB) ? wn : 0.0;
+            *reinterpret_cast<double2 *>(dst + row * MF_TC + 2 * lane) = v;
+        }
+        if (j < L && lane < MF_PERM_REC / 16)
+            *reinterpret_cast<uint4 *>(recs + ((size_t)buf * MF_WARPS + warp) * MF_PERM_REC + 16 * lane) =
+                *reinterpret_cast<const uint4 *>(perm + ((size_t)j * nchunk + c) * MF_PERM_REC + 16 * lane);
+    };
+
+    if (c0 < c1) gen(0, c0);
+    __syncthreads();
+    for (int c = c0; c < c1; ++c) {
+        const int buf = (c - c0) & 1;
+        if (c + 1 < c1) gen(buf ^ 1, c + 1);
+        if (j < L) {
+            const uint8_t *rec = recs + ((size_t)buf * MF_WARPS + warp) * MF_PERM_REC;
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(rec + MF_PERM_CNT);
+            const double *Rb = Rs + (size_t)buf * MF_CH * MF_TC + 2 * lane;
+#pragma unroll
+            for (int b = 0; b < Q; ++b) {
+                const int m = rec[b];
+                double2 a = acc[b];
+                for (int k = 0; k < m; k += 4) {
+                    const uint32_t w4 = *pw++;
+                    { const double2 v = *reinterpret_cast<const double2 *>(Rb + (w4 & 0xffu) * MF_TC); a.x += v.x; a.y += v.y; }
+                    if (k + 1 < m) { const double2 v = *reinterpret_cast<const double2 *>(Rb + ((w4 >> 8) & 0xffu) * MF_TC); a.x += v.x; a.y += v.y; }
+                    if (k + 2 < m) { const double2 v = *reinterpret_cast<const double2 *>(Rb + ((w4 >> 16) & 0xffu) * MF_TC); a.x += v.x; a.y += v.y; }
+                    if (k + 3 < m) { const double2 v = *reinterpret_cast<const double2 *>(Rb + (w4 >> 24) * MF_TC); a.x += v.x; a.y += v.y; }
+                }
+                acc[b] = a;
+            }
+        }
+        __syncthreads();
+    }
+    if (j < L) {
+        double *f = F + (size_t)blockIdx.z * f_split_stride + (size_t)j * Q * ld + col0 + 2 * lane;
+#pragma unroll
+        for (int b = 0; b < Q; ++b) *reinterpret_cast<double2 *>(f + (size_t)b * ld) = acc[b];
+    }
+}
+
+// fi[i][a] = F[(i,a)][(i,a)] / Meff  (all q states, gap included), regularised copy
+__global__ void mf_single_kernel(const double *__restrict__ F, size_t f_split_stride, int nsplit,
+                                 int L, int q, int ld, double meff, double pseudocount,
+                                 double *__restrict__ fi, double *__restrict__ reg_fi)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L * q) return;
+    double s = 0.0;
+    for (int z = 0; z < nsplit; ++z) s += F[(size_t)z * f_split_stride + (size_t)idx * ld + idx];
+    const double f = s / meff;
+    if (fi) fi[idx] = f;
+    if (reg_fi) reg_fi[idx] = pseudocount / (double)q + (1.0 - pseudocount) * f;     // msa_numerics.py:120-124
+}
+
+// fij[pair][a][b] for non-gap a,b (msa_numerics.py:183-229 layout)
+__global__ void mf_pack_fij_kernel(const double *__restrict__ F, size_t f_split_stride, int nsplit,
+                                   int L, int q, int ld, double meff, double *__restrict__ fij)
+{
+    const int qm1 = q - 1;
+    const long total = (long)L * (L - 1) / 2 * qm1 * qm1;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long pair = idx / (qm1 * qm1);
+    const int ab = (int)(idx - pair * qm1 * qm1);
+    const int a = ab / qm1, b = ab - a * qm1;
+    int i = 0; long rem = pair;
+    while (rem >= L - 1 - i) { rem -= L - 1 - i; ++i; }
+    const int j = i + 1 + (int)rem;
+    double s = 0.0;
+    for (int z = 0; z < nsplit; ++z)
+        s += F[(size_t)z * f_split_stride + ((size_t)j * q + b) * ld + (size_t)i * q + a];
+    fij[idx] = s / meff;
+}
+
+// covariance matrix (msa_numerics.py:271-318) with the pair pseudocount
+// (:232-267) fused; C is npad x npad, identity on the padding diagonal.
+__global__ void mf_corr_kernel(const double *__restrict__ F, size_t f_split_stride, int nsplit,
+                               const double *__restrict__ reg_fi, int L, int q, int ld, double meff,
+                               double pseudocount, int n, int npad, double *__restrict__ C)
+{
+    const int qm1 = q - 1;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (col >= npad) return;
+    double out;
+    if (row >= n || col >= n) out = (row == col) ? 1.0 : 0.0;
+    else {
+        int i = row / qm1, a = row - i * qm1, j = col / qm1, b = col - j * qm1;
+        if (i == j) {
+            const double fia = reg_fi[i * q + a], fib = reg_fi[i * q + b];
+            out = (a == b) ? fia * (1.0 - fia) : -1.0 * fia * fib;
+        } else {
+            if (i > j) { int t = i; i = j; j = t; t = a; a = b; b = t; }   // canonical i<j source: exact symmetry
+            double s = 0.0;
+            for (int z = 0; z < nsplit; ++z)
+                s += F[(size_t)z * f_split_stride + ((size_t)j * q + b) * ld + (size_t)i * q + a];
+            const double fij = s / meff;
+            const double rfij = pseudocount / (double)(q * q) + (1.0 - pseudocount) * fij;
+            out = rfij - reg_fi[i * q + a] * reg_fi[j * q + b];
+        }
+    }
+    C[(size_t)row * npad + col] = out;
+}
+
+// ------------------------------------------------------------------------------
+// FP64 tensor-core GEMM: C[128x128 tile] = beta*C + alpha * A[128xK] * B[Kx128],
+// K = 128.  grid = (N/128, M/128); CTA row-block `skip_rb` is skipped.
+constexpr int GJ_B = 128;
+constexpr int GM_KC = 16;
+constexpr int GM_AS = 20;      // A smem row stride (doubles): 4 mod 16 -> conflict-free LDS.64
+constexpr int GM_BS = 132;     // B smem row stride (doubles)
+
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 1)
+dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, int lda,
+                const double *__restrict__ B, int ldb, double alpha, double beta, int skip_rb)
+{
+    if ((int)blockIdx.y == skip_rb) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *As = reinterpret_cast<double *>(smem_raw);                 // [2][128][GM_AS]
+    double *Bs = As + 2 * GJ_B * GM_AS;                                // [2][GM_KC][GM_BS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;                           // 4 x 2 warps: 32 x 64 per warp
+    const int g = lane >> 2, t4 = lane & 3;
+    const double *Ab = A + (size_t)blockIdx.y * GJ_B * lda;
+    const double *Bb = B + (size_t)blockIdx.x * GJ_B;
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+
+    auto stage = [&](int buf, int kc) {
+        // A chunk: 128 rows x 16 doubles (8 x 16B per row)
+        for (int t = tid; t < GJ_B * 8; t += 256) {
+            const int row = t >> 3, seg = t & 7;
+            cp_async16(As + ((size_t)buf * GJ_B + row) * GM_AS + seg * 2,
+                       Ab + (size_t)row * lda + kc * GM_KC + seg * 2);
+        }
+        // B chunk: 16 rows x 128 doubles (64 x 16B per row)
+        for (int t = tid; t < GM_KC * 64; t += 256) {
+            const int row = t >> 6, seg = t & 63;
+            cp_async16(Bs + ((size_t)buf * GM_KC + row) * GM_BS + seg * 2,
+                       Bb + (size_t)(kc * GM_KC + row) * ldb + seg * 2);
+        }
+        cp_async_commit();
+    };
+
+    constexpr int NK = GJ_B / GM_KC;
+    stage(0, 0);
+    for (int kc = 0; kc < NK; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < NK) { stage(buf ^ 1, kc + 1); cp_async_wait<1>(); }
+        else             { cp_async_wait<0>(); }
+        __syncthreads();
+        const double *Ap = As + (size_t)buf * GJ_B * GM_AS + (wm * 32 + g) * GM_AS + t4;
+        const double *Bp = Bs + (size_t)buf * GM_KC * GM_BS + t4 * GM_BS + wn * 64 + g;
+#pragma unroll
+        for (int k4 = 0; k4 < GM_KC / 4; ++k4) {
+            double a[4], b[8];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = Ap[mi * 8 * GM_AS + k4 * 4];
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) b[ni] = Bp[k4 * 4 * GM_BS + ni * 8];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+        __syncthreads();
+    }
+    double *Cb = C + (size_t)blockIdx.y * GJ_B * ldc + (size_t)blockIdx.x * GJ_B;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+            double2 *p = reinterpret_cast<double2 *>(Cb + (size_t)(wm * 32 + mi * 8 + g) * ldc + wn * 64 + ni * 8 + 2 * t4);
+            double2 v = make_double2(alpha * acc[mi][ni][0], alpha * acc[mi][ni][1]);
+            if (beta != 0.0) { const double2 c = *p; v.x += beta * c.x; v.y += beta * c.y; }
+            *p = v;
+        }
+}
+
+// in-place inverse of one 128x128 diagonal block (unblocked Gauss-Jordan, no pivoting)
+__global__ void __launch_bounds__(512, 1)
+gj_diag_inv_kernel(const double *__restrict__ A, int ld, int k, double *__restrict__ Dinv, int *__restrict__ info)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *S = reinterpret_cast<double *>(smem_raw);          // [128][129]
+    double *colp = S + GJ_B * (GJ_B + 1);                      // [128]
+    __shared__ double piv_s;
+    const int tid = threadIdx.x;
+    const double *Ak = A + (size_t)k * GJ_B * ld + (size_t)k * GJ_B;
+    for (int t = tid; t < GJ_B * GJ_B; t += 512) {
+        const int r = t >> 7, c = t & 127;
+        S[r * (GJ_B + 1) + c] = Ak[(size_t)r * ld + c];
+    }
+    __syncthreads();
+    for (int p = 0; p < GJ_B; ++p) {
+        if (tid < GJ_B) colp[tid] = S[tid * (GJ_B + 1) + p];
+        if (tid == 0) {
+            const double d = S[p * (GJ_B + 1) + p];
+            if (!(fabs(d) > 0.0) && info) *info = k * GJ_B + p + 1;
+            piv_s = 1.0 / d;
+        }
+        __syncthreads();
+        const double piv = piv_s;
+        if (tid < GJ_B) {                                      // scale pivot row
+            const int c = tid;
+            S[p * (GJ_B + 1) + c] = (c == p) ? piv : S[p * (GJ_B + 1) + c] * piv;
+        }
+        __syncthreads();
+        for (int t = tid; t < GJ_B * GJ_B; t += 512) {
+            const int r = t >> 7, c = t & 127;
+            if (r == p) continue;
+            const double f = colp[r];
+            if (c == p) S[r * (GJ_B + 1) + c] = -f * piv;
+            else S[r * (GJ_B + 1) + c] -= f * S[p * (GJ_B + 1) + c];
+        }
+        __syncthreads();
+    }
+    for (int t = tid; t < GJ_B * GJ_B; t += 512) {
+        const int r = t >> 7, c = t & 127;
+        Dinv[(size_t)r * GJ_B + c] = S[r * (GJ_B + 1) + c];
+    }
+}
+
+// Ck = A[:, kblock] ; A[:, kblock] = 0 except the diagonal block = I
+__global__ void gj_split_col_kernel(double *__restrict__ A, int ld, int npad, int k, double *__restrict__ Ck)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)npad * GJ_B) return;
+    const int r = (int)(idx >> 7), c = (int)(idx & 127);
+    double *p = A + (size_t)r * ld + (size_t)k * GJ_B + c;
+    Ck[idx] = *p;
+    *p = (r == k * GJ_B + c) ? 1.0 : 0.0;
+}
+
+__global__ void negate_copy_kernel(const double *__restrict__ A, int ld, int n, double *__restrict__ out)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n * n) return;
+    const int r = (int)(idx / n), c = (int)(idx - (long)r * n);
+    out[idx] = -1.0 * A[(size_t)r * ld + c];
+}
+
+// d_A: npad x npad (row-major, ld = npad), overwritten by its inverse
+static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
+{
+    const int nb = npad / GJ_B;
+    double *d_Dinv = nullptr, *d_Ck = nullptr, *d_Rk = nullptr;
+    int *d_info = nullptr;
+    DCA_CUDA(cudaMalloc(&d_Dinv, sizeof(double) * GJ_B * GJ_B));
+    DCA_CUDA(cudaMalloc(&d_Ck, sizeof(double) * (size_t)npad * GJ_B));
+    DCA_CUDA(cudaMalloc(&d_Rk, sizeof(double) * (size_t)npad * GJ_B));
+    DCA_CUDA(cudaMalloc(&d_info, sizeof(int)));
+    DCA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+    const size_t smem_gemm = sizeof(double) * (2 * GJ_B * GM_AS + 2 * GM_KC * GM_BS);
+    const size_t smem_diag = sizeof(double) * (GJ_B * (GJ_B + 1) + GJ_B);
+    DCA_CUDA(cudaFuncSetAttribute(dgemm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
+    DCA_CUDA(cudaFuncSetAttribute(gj_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag));
+    for (int k = 0; k < nb; ++k) {
+        DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, st, d_A, npad, k, d_Dinv, d_info);
+        DCA_LAUNCH(gj_split_col_kernel, (unsigned)ceil_div<long>((long)npad * GJ_B, 256), 256, 0, st, d_A, npad, npad, k, d_Ck);
+        // Rk (128 x npad) = Dinv (128x128) * A[kblock rows, :]
+        DCA_LAUNCH(dgemm128_kernel, dim3(nb, 1), 256, smem_gemm, st,
+                   d_Rk, npad, d_Dinv, GJ_B, d_A + (size_t)k * GJ_B * npad, npad, 1.0, 0.0, -1);
+        // A[i,:] -= Ck[i] * Rk for every row block i != k
+        DCA_LAUNCH(dgemm128_kernel, dim3(nb, nb), 256, smem_gemm, st,
+                   d_A, npad, d_Ck, GJ_B, d_Rk, npad, -1.0, 1.0, k);
+        DCA_CUDA(cudaMemcpyAsync(d_A + (size_t)k * GJ_B * npad, d_Rk, sizeof(double) * (size_t)GJ_B * npad,
+                                 cudaMemcpyDeviceToDevice, st));
+    }
+    int info = 0;
+    DCA_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    DCA_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_Dinv); cudaFree(d_Ck); cudaFree(d_Rk); cudaFree(d_info);
+    if (info != 0) { set_error("mf_couplings: zero pivot at row %d: the correlation matrix is singular (increase the pseudocount)", info - 1); return -1; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------
+struct MfWork {
+    uint8_t *d_msa = nullptr, *d_perm = nullptr;
+    double *d_w = nullptr, *d_F = nullptr, *d_fi = nullptr, *d_rfi = nullptr;
+    int ld = 0, nsplit = 1, cps = 0, nchunk = 0;
+    size_t fstride = 0;
+    double meff = 0.0;
+    ~MfWork() { cudaFree(d_msa); cudaFree(d_perm); cudaFree(d_w); cudaFree(d_F); cudaFree(d_fi); cudaFree(d_rfi); }
+};
+
+template <int Q>
+static int mf_pairfreq_t(MfWork &W, long N, int L)
+{
+    const long total = (long)L * W.nchunk;
+    DCA_CUDA(cudaMemset(W.d_perm, 0, (size_t)total * MF_PERM_REC));
+    DCA_LAUNCH((mf_build_perm_kernel<Q>), (unsigned)ceil_div<long>(total, 128), 128, 0, 0, W.d_msa, N, L, W.nchunk, W.d_perm);
+    const size_t smem = sizeof(double) * 2 * MF_CH * MF_TC + 2 * MF_WARPS * MF_PERM_REC;
+    DCA_CUDA(cudaFuncSetAttribute(mf_pairfreq_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(W.ld / MF_TC, ceil_div(L, MF_WARPS), W.nsplit);
+    DCA_LAUNCH((mf_pairfreq_kernel<Q>), grid, MF_WARPS * 32, smem, 0,
+               W.d_msa, W.d_w, W.d_perm, W.nchunk, N, L, W.ld, W.d_F, W.fstride, W.cps);
+    DCA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int mf_prepare(MfWork &W, const uint8_t *msa, const double *w, long N, int L, int q)
+{
+    if (require_device() != 0) return -1;
+    if (q != 21 && q != 5) { set_error("mf: num_site_states must be 21 or 5 (got %d)", q); return -1; }
+    if (N <= 0 || L < 2) { set_error("mf: empty alignment (N=%ld L=%d)", N, L); return -1; }
+    for (long k = 0; k < N * (long)L; ++k)
+        if (msa[k] >= q) { set_error("mf: residue code %d >= q=%d at flat index %ld", msa[k], q, k); return -1; }
+    const int Lq = L * q;
+    W.ld = ceil_div(Lq, MF_TC) * MF_TC;
+    W.nchunk = (int)ceil_div<long>(N, MF_CH);
+    const long tiles = (long)(W.ld / MF_TC) * ceil_div(L, MF_WARPS);
+    int want = (int)ceil_div<long>(3L * sm_count(), std::max(1L, tiles));
+    W.nsplit = std::max(1, std::min(want, std::max(1, W.nchunk / 8)));
+    W.cps = ceil_div(W.nchunk, W.nsplit);
+    W.nsplit = ceil_div(W.nchunk, W.cps);
+    W.fstride = (size_t)Lq * W.ld;
+    double m = 0.0;
+    for (long n = 0; n < N; ++n) m += w[n];
+    W.meff = m;
+    DCA_CUDA(cudaMalloc(&W.d_msa, (size_t)N * L));
+    DCA_CUDA(cudaMalloc(&W.d_w, sizeof(double) * (size_t)N));
+    DCA_CUDA(cudaMalloc(&W.d_perm, (size_t)L * W.nchunk * MF_PERM_REC));
+    DCA_CUDA(cudaMalloc(&W.d_F, sizeof(double) * W.fstride * W.nsplit));
+    DCA_CUDA(cudaMalloc(&W.d_fi, sizeof(double) * (size_t)Lq));
+    DCA_CUDA(cudaMalloc(&W.d_rfi, sizeof(double) * (size_t)Lq));
+    DCA_CUDA(cudaMemcpy(W.d_msa, msa, (size_t)N * L, cudaMemcpyHostToDevice));
+    DCA_CUDA(cudaMemcpy(W.d_w, w, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice));
+    return (q == 21) ? mf_pairfreq_t<21>(W, N, L) : mf_pairfreq_t<5>(W, N, L);
+}
+
+int mf_freqs_host(const uint8_t *msa, const double *w, long N, int L, int q, double *fi, double *fij)
+{
+    MfWork W;
+    if (mf_prepare(W, msa, w, N, L, q) != 0) return -1;
+    const int Lq = L * q;
+    DCA_LAUNCH(mf_single_kernel, ceil_div(Lq, 128), 128, 0, 0, W.d_F, W.fstride, W.nsplit, L, q, W.ld, W.meff, 0.0,
+               W.d_fi, (double *)nullptr);
+    DCA_CUDA(cudaMemcpy(fi, W.d_fi, sizeof(double) * (size_t)Lq, cudaMemcpyDeviceToHost));
+    if (fij) {
+        const long total = (long)L * (L - 1) / 2 * (q - 1) * (q - 1);
+        double *d_fij = nullptr;
+        DCA_CUDA(cudaMalloc(&d_fij, sizeof(double) * (size_t)total));
+        DCA_LAUNCH(mf_pack_fij_kernel, (unsigned)ceil_div<long>(total, 256), 256, 0, 0,
+                   W.d_F, W.fstride, W.nsplit, L, q, W.ld, W.meff, d_fij);
+        cudaError_t e = cudaMemcpy(fij, d_fij, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost);
+        cudaFree(d_fij);
+        if (e != cudaSuccess) { set_error("mf_freqs: D2H failed: %s", cudaGetErrorString(e)); return -1; }
+    }
+    return 0;
+}
+
+// builds C on the device; returns the device pointer (npad x npad) through d_C
+static int mf_corr_device(MfWork &W, int L, int q, double pseudocount, double **d_C, int *npad_out)
+{
+    const int Lq = L * q, n = L * (q - 1);
+    const int npad = ceil_div(n, GJ_B) * GJ_B;
+    DCA_LAUNCH(mf_single_kernel, ceil_div(Lq, 128), 128, 0, 0, W.d_F, W.fstride, W.nsplit, L, q, W.ld, W.meff,
+               pseudocount, W.d_fi, W.d_rfi);
+    DCA_CUDA(cudaMalloc(d_C, sizeof(double) * (size_t)npad * npad));
+    dim3 grid(ceil_div(npad, 256), npad);
+    DCA_LAUNCH(mf_corr_kernel, grid, 256, 0, 0, W.d_F, W.fstride, W.nsplit, W.d_rfi, L, q, W.ld, W.meff,
+               pseudocount, n, npad, *d_C);
+    DCA_CUDA(cudaGetLastError());
+    *npad_out = npad;
+    return 0;
+}
+
+int mf_corr_mat_host(const uint8_t *msa, const double *w, long N, int L, int q, double pseudocount,
+                     double *reg_fi, double *corr)
+{
+    MfWork W;
+    if (mf_prepare(W, msa, w, N, L, q) != 0) return -1;
+    double *d_C = nullptr;
+    int npad = 0;
+    if (mf_corr_device(W, L, q, pseudocount, &d_C, &npad) != 0) { cudaFree(d_C); return -1; }
+    const int n = L * (q - 1);
+    cudaError_t e = cudaMemcpy2D(corr, sizeof(double) * (size_t)n, d_C, sizeof(double) * (size_t)npad,
+                                 sizeof(double) * (size_t)n, (size_t)n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && reg_fi)
+        e = cudaMemcpy(reg_fi, W.d_rfi, sizeof(double) * (size_t)L * q, cudaMemcpyDeviceToHost);
+    cudaFree(d_C);
+    if (e != cudaSuccess) { set_error("mf_corr_mat: D2H failed: %s", cudaGetErrorString(e)); return -1; }
+    return 0;
+}
+
+int mf_couplings_host(const double *corr, int n, double *out)
+{
+    if (require_device() != 0) return -1;
+    const int npad = ceil_div(n, GJ_B) * GJ_B;
+    double *d_A = nullptr, *d_out = nullptr;
+    DCA_CUDA(cudaMalloc(&d_A, sizeof(double) * (size_t)npad * npad));
+    DCA_CUDA(cudaMemset(d_A, 0, sizeof(double) * (size_t)npad * npad));
+    DCA_CUDA(cudaMemcpy2D(d_A, sizeof(double) * (size_t)npad, corr, sizeof(double) * (size_t)n,
+                          sizeof(double) * (size_t)n, (size_t)n, cudaMemcpyHostToDevice));
+    if (npad > n) {   // identity on the padding diagonal
+        std::vector<double> ones((size_t)(npad - n), 1.0);
+        DCA_CUDA(cudaMemcpy2D(d_A + (size_t)n * npad + n, sizeof(double) * (size_t)(npad + 1), ones.data(),
+                              sizeof(double), sizeof(double), (size_t)(npad - n), cudaMemcpyHostToDevice));
+    }
+    int rc = gj_invert_device(d_A, npad, 0);
+    if (rc == 0) {
+        if (cudaMalloc(&d_out, sizeof(double) * (size_t)n * n) != cudaSuccess) { set_error("mf_couplings: out of device memory"); rc = -1; }
+    }
+    if (rc == 0) {
+        DCA_LAUNCH(negate_copy_kernel, (unsigned)ceil_div<long>((long)n * n, 256), 256, 0, 0, d_A, npad, n, d_out);
+        cudaError_t e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("mf_couplings: D2H failed: %s", cudaGetErrorString(e)); rc = -1; }
+    }
+    cudaFree(d_A); cudaFree(d_out);
+    return rc;
+}
+
+}  // namespace dca

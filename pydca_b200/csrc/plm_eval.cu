@@ -1,0 +1,732 @@
+// plm_eval.cu -- plmDCA objective + gradient on sm_100a.
+//
+// Replaces PlmDCA::gradient  (pydca/plmdca/plmdca_numerics.cpp:436-607) and
+// PlmDCA::initFieldsAndCouplings (:207-249).  Same parameter vector layout:
+//   x[a + q*i]                                   fields            (:226, :467)
+//   x[L*q + pair(i,j)*q*q + a*q + b]   i<j       couplings J_ij(a,b) (:338-342)
+//
+// Mathematics (per evaluation, all float32 like the reference):
+//   logit_n(i,a) = carry_{n-1}(i,a) + h_i(a) + sum_{j!=i} J_ij(a, s_nj)     (:499-517)
+//   p_n(i,.)     = softmax(logit_n(i,.))                                    (:519-530)
+//   fx          += -w_n log p_n(i, s_ni)                                    (:536)
+//   r_n(i,a)     = w_n (p_n(i,a) - [a == s_ni])                             (:538-567)
+//   dh_i(a)      = sum_n r_n(i,a)
+//   dJ_ij(a,b)   = sum_n r_n(i,a)[s_nj == b] + sum_n [s_ni == a] r_n(j,b)   (:570-602)
+// "carry" is the reference's quirk: prob_ni is allocated once per site (:492)
+// and only += at :499, so sequence n starts from sequence n-1's probabilities.
+// The chain p_n = softmax(p_{n-1} + S_n) contracts by >= 2x per step (the
+// softmax Jacobian has norm <= 1/2), so a chain restarted `warm` = 32 steps
+// early reproduces the serial chain to < 2^-32: the scan is chunked.
+//
+// Data layout in HBM (one PlmProblem):
+//   msa   u8  [N][L]        row-major           (softmax: residue of (n,i))
+//   msaT  u8  [L][Npad]     site-major          (logits: 16 residues per LDS.128)
+//   W     f32 [L*q][ld]     full symmetric coupling matrix, row (j,b) = j*q+b,
+//                           column (i,a) = i*q+a, zero diagonal blocks;
+//                           rebuilt from x every evaluation (unpack)
+//   S     f32 [Npad][ld]    logits, overwritten in place by the residuals r
+//   G     f32 [nsplit][L*q][ld]   G[(j,b)][(i,a)] = sum_n [s_nj==b] r_n(i,a)
+//   perm  u8  [L][nchunk][224]    per (site, 128-sequence chunk): the chunk's
+//                           local sequence indices bucketed by residue (static
+//                           for an MSA, built once) -> atomics-free scatter
+//
+// Kernels per evaluation and what bounds them (DESIGN.md has the numbers):
+//   unpack   x -> W                          HBM/L2 streaming, 12P bytes
+//   logits   S = h + sum_j W[(j,s_nj), :]    shared-memory gather: 1 LDS word / add
+//   softmax  chunked carry scan, S -> r, fx  latency/L2, 8*N*L*q bytes
+//   scatter  G = sum_n onehot^T r            shared-memory gather: 1 LDS word / add
+//   assemble G (+G^T) + 2*lambda*x -> g, fx, g.d, g.g, x.x   HBM/L2 streaming
+// The gather kernels do N*L*L*q adds each; they are bound by shared-memory
+// bandwidth (128 B/clk/SM = 32 adds/clk/SM), not by HBM.
+#include "dca_common.cuh"
+#include "dca_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace dca {
+
+// ------------------------------------------------------------------------------
+constexpr int LG_TN = 256;        // sequences per logits CTA
+constexpr int LG_TC = 128;        // columns per CTA (32 lanes x float4)
+constexpr int LG_THREADS = 512;
+template <int Q> struct LgCfg { static constexpr int JB = (Q > 8) ? 4 : 16; };   // sites per stage
+
+constexpr int SC_CH = 128;        // sequences per scatter chunk
+constexpr int SC_TC = 128;
+constexpr int SC_WARPS = 16;      // one site per warp
+constexpr int PERM_CNT = 32;      // bytes reserved for bucket counts
+constexpr int PERM_REC = 224;     // bytes per (site, chunk) record (14 x 16 B)
+
+constexpr int AS_JG = 8;          // sites j per assemble / unpack CTA
+
+struct PlmProblem {
+    long N = 0, Npad = 0, P = 0;
+    int L = 0, q = 0, Lq = 0, ld = 0;
+    float lh = 0.f, lJ = 0.f;
+    int site_lo = 0, site_hi = 0;
+    int carry = 1, chunk = 32, warm = 32;
+    cudaStream_t stream = nullptr;
+    uint8_t *d_msa = nullptr, *d_msaT = nullptr, *d_perm = nullptr;
+    float *d_w = nullptr, *d_W = nullptr, *d_G = nullptr, *d_S = nullptr;
+    double *d_fxpart = nullptr, *d_red = nullptr, *d_scal = nullptr, *h_scal = nullptr;
+    float h_meff = 0.f;
+    int nsplit = 1, chunks_per_split = 0, nchunk = 0;
+    long nscan = 0;          // number of scan chunks
+    int red_blocks = 0;
+    int col_tile0 = 0, col_tiles = 0;
+};
+
+// ------------------------------------------------------------------------------
+__global__ void transpose_msa_kernel(const uint8_t *__restrict__ msa, long N, int L, long Npad,
+                                     uint8_t *__restrict__ msaT)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)L * Npad) return;
+    const int j = (int)(idx / Npad);
+    const long n = idx - (long)j * Npad;
+    msaT[idx] = (n < N) ? msa[n * L + j] : (uint8_t)0;
+}
+
+// one thread per (site, chunk): bucket the chunk's local indices by residue
+template <int Q>
+__global__ void build_perm_kernel(const uint8_t *__restrict__ msaT, long N, long Npad, int L,
+                                  int nchunk, uint8_t *__restrict__ perm)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)L * nchunk) return;
+    const int j = (int)(idx / nchunk);
+    const int c = (int)(idx - (long)j * nchunk);
+    const uint8_t *col = msaT + (long)j * Npad + (long)c * SC_CH;
+    const int rows = (int)min((long)SC_CH, N - (long)c * SC_CH);
+    uint8_t *rec = perm + idx * PERM_REC;
+    int cnt[Q], pos[Q];
+#pragma unroll
+    for (int b = 0; b < Q; ++b) cnt[b] = 0;
+    for (int r = 0; r < rows; ++r) {
+        const int v = col[r];
+#pragma unroll
+        for (int b = 0; b < Q; ++b) cnt[b] += (v == b);
+    }
+    int off = 0;
+#pragma unroll
+    for (int b = 0; b < Q; ++b) {
+        rec[b] = (uint8_t)cnt[b];
+        pos[b] = off;
+        off += (cnt[b] + 3) & ~3;
+    }
+    for (int r = 0; r < rows; ++r) {
+        const int v = col[r];
+        int where = 0;
+#pragma unroll
+        for (int b = 0; b < Q; ++b)
+            if (v == b) { where = pos[b]; pos[b] = where + 1; }
+        rec[PERM_CNT + where] = (uint8_t)r;
+    }
+}
+
+// ------------------------------------------------------------------------------
+// unpack: x (upper-triangular blocks) -> full symmetric W
+template <int Q>
+__global__ void __launch_bounds__(256)
+plm_unpack_kernel(const float *__restrict__ x, int L, int ld, float *__restrict__ W)
+{
+    constexpr int QQ = Q * Q;
+    __shared__ float tile[AS_JG][QQ];
+    const int i = blockIdx.y;
+    const int j0 = blockIdx.x * AS_JG;
+    if (j0 + AS_JG - 1 <= i) return;
+    const long Lq = (long)L * Q;
+    for (int jj = 0; jj < AS_JG; ++jj) {
+        const int j = j0 + jj;
+        if (j <= i || j >= L) continue;
+        const float *xb = x + Lq + pair_index(L, i, j) * QQ;
+        for (int t = threadIdx.x; t < QQ; t += 256) {
+            const float v = xb[t];
+            tile[jj][t] = v;
+            const int a = t / Q, b = t - a * Q;
+            W[((long)i * Q + a) * ld + j * Q + b] = v;
+        }
+    }
+    __syncthreads();
+    for (int jj = 0; jj < AS_JG; ++jj) {
+        const int j = j0 + jj;
+        if (j <= i || j >= L) continue;
+        for (int t = threadIdx.x; t < QQ; t += 256) {
+            const int b = t / Q, a = t - b * Q;
+            W[((long)j * Q + b) * ld + i * Q + a] = tile[jj][a * Q + b];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------
+// logits: S[n][col] = h[col] + sum_j W[j*Q + s_nj][col]
+template <int Q>
+__global__ void __launch_bounds__(LG_THREADS, 1)
+plm_logits_kernel(const float *__restrict__ W, int ld, const uint8_t *__restrict__ msaT, long Npad,
+                  long N, int L, const float *__restrict__ x, float *__restrict__ S, int col_tile0)
+{
+    constexpr int JB = LgCfg<Q>::JB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *Wt = reinterpret_cast<float *>(smem_raw);                       // [2][JB*Q][128]
+    uint8_t *Mt = smem_raw + sizeof(float) * 2 * JB * Q * LG_TC;           // [2][JB][256]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col0 = (col_tile0 + blockIdx.x) * LG_TC;
+    const long n0 = (long)blockIdx.y * LG_TN;
+    const int Lq = L * Q;
+
+    float4 acc[16];
+    {
+        const int c = col0 + 4 * lane;
+        float4 h;
+        h.x = (c + 0 < Lq) ? x[c + 0] : 0.f;
+        h.y = (c + 1 < Lq) ? x[c + 1] : 0.f;
+        h.z = (c + 2 < Lq) ? x[c + 2] : 0.f;
+        h.w = (c + 3 < Lq) ? x[c + 3] : 0.f;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc[t] = h;
+    }
+
+    auto stage = [&](int buf, int j0) {
+        const int rows = min(JB, L - j0) * Q;
+        float *dstW = Wt + (size_t)buf * JB * Q * LG_TC;
+        const float *srcW = W + (size_t)j0 * Q * ld + col0;
+        for (int t = tid; t < rows * 32; t += LG_THREADS) {
+            const int row = t >> 5, c4 = t & 31;
+            cp_async16(dstW + row * LG_TC + 4 * c4, srcW + (size_t)row * ld + 4 * c4);
+        }
+        const int nj = min(JB, L - j0);
+        uint8_t *dstM = Mt + (size_t)buf * JB * LG_TN;
+        for (int t = tid; t < nj * 16; t += LG_THREADS) {
+            const int jj = t >> 4, seg = t & 15;
+            cp_async16(dstM + jj * LG_TN + seg * 16, msaT + (size_t)(j0 + jj) * Npad + n0 + seg * 16);
+        }
+        cp_async_commit();
+    };
+
+    const int nstage = (L + JB - 1) / JB;
+    stage(0, 0);
+    for (int st = 0; st < nstage; ++st) {
+        const int buf = st & 1;
+        if (st + 1 < nstage) { stage(buf ^ 1, (st + 1) * JB); cp_async_wait<1>(); }
+        else                 { cp_async_wait<0>(); }
+        __syncthreads();
+        const int nj = min(JB, L - st * JB);
+        const float *Wb = Wt + (size_t)buf * JB * Q * LG_TC + 4 * lane;
+        const uint8_t *Mb = Mt + (size_t)buf * JB * LG_TN + warp * 16;
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+            if (jj < nj) {
+                const uint4 r16 = *reinterpret_cast<const uint4 *>(Mb + jj * LG_TN);
+                const float *Wj = Wb + jj * Q * LG_TC;
+                const unsigned rr[4] = {r16.x, r16.y, r16.z, r16.w};
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const unsigned b = (rr[t >> 2] >> (8 * (t & 3))) & 0xffu;
+                    const float4 v = *reinterpret_cast<const float4 *>(Wj + b * LG_TC);
+                    acc[t].x += v.x; acc[t].y += v.y; acc[t].z += v.z; acc[t].w += v.w;
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const long n = n0 + warp * 16 + t;
+        if (n < N) *reinterpret_cast<float4 *>(S + (size_t)n * ld + col0 + 4 * lane) = acc[t];
+    }
+}
+
+// ------------------------------------------------------------------------------
+// softmax with the reference's carry, chunked with a warm-up overlap.
+// warp = 32 consecutive sites of one chunk; lane = one (site, chunk) chain.
+template <int Q>
+__global__ void __launch_bounds__(128)
+plm_softmax_kernel(float *__restrict__ S, int ld, const uint8_t *__restrict__ msa,
+                   const float *__restrict__ w, long N, int L, int site_lo, int site_hi,
+                   int chunk, int warm, int carry, double *__restrict__ fxpart)
+{
+    __shared__ float sbuf[4][32 * Q];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long k = (long)blockIdx.y * 4 + wib;
+    const long nbeg = k * chunk;
+    if (nbeg >= N) return;
+    const long nend = min(N, nbeg + (long)chunk);
+    const long nstart = carry ? max(0L, nbeg - (long)warm) : nbeg;
+    const int s0 = site_lo + blockIdx.x * 32;
+    const int site = s0 + lane;
+    const bool active = site < site_hi;
+    const int ncols = min(32, site_hi - s0) * Q;
+    float *buf = sbuf[wib];
+    const size_t cbase = (size_t)s0 * Q;
+
+    float p[Q], nxt[Q];
+#pragma unroll
+    for (int a = 0; a < Q; ++a) p[a] = 0.f;
+    double fx = 0.0;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+        const int idx = lane + 32 * t;
+        nxt[t] = (idx < ncols) ? S[(size_t)nstart * ld + cbase + idx] : 0.f;
+    }
+    for (long n = nstart; n < nend; ++n) {
+#pragma unroll
+        for (int t = 0; t < Q; ++t) buf[lane + 32 * t] = nxt[t];
+        if (n + 1 < nend) {
+#pragma unroll
+            for (int t = 0; t < Q; ++t) {
+                const int idx = lane + 32 * t;
+                nxt[t] = (idx < ncols) ? S[(size_t)(n + 1) * ld + cbase + idx] : 0.f;
+            }
+        }
+        __syncwarp();
+        float l[Q];
+#pragma unroll
+        for (int a = 0; a < Q; ++a) l[a] = carry ? (p[a] + buf[lane * Q + a]) : buf[lane * Q + a];
+        float m = l[0];
+#pragma unroll
+        for (int a = 1; a < Q; ++a) m = fmaxf(m, l[a]);
+        float z = 0.f;
+#pragma unroll
+        for (int a = 0; a < Q; ++a) { l[a] = expf(l[a] - m); z += l[a]; }
+        const float zi = 1.f / z;
+#pragma unroll
+        for (int a = 0; a < Q; ++a) p[a] = l[a] * zi;
+
+        if (n >= nbeg) {
+            if (active) {
+                const int r = msa[(size_t)n * L + site];
+                const float wn = w[n];
+                float pr = p[0];
+#pragma unroll
+                for (int a = 1; a < Q; ++a) pr = (a == r) ? p[a] : pr;
+                fx -= (double)(wn * logf(pr));
+#pragma unroll
+                for (int a = 0; a < Q; ++a) buf[lane * Q + a] = wn * p[a] - ((a == r) ? wn : 0.f);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < Q; ++t) {
+                const int idx = lane + 32 * t;
+                if (idx < ncols) S[(size_t)n * ld + cbase + idx] = buf[idx];
+            }
+        }
+        __syncwarp();
+    }
+    if (active) fxpart[k * L + site] = fx;
+}
+
+// ------------------------------------------------------------------------------
+// scatter: G[(j,b)][col] = sum_{n : s_nj == b} r[n][col], warp = one site j,
+// 21 float4 accumulators per lane, residual chunk staged in shared memory,
+// sequences visited in residue-bucket order (perm) -> no atomics, fixed order.
+template <int Q>
+__global__ void __launch_bounds__(SC_WARPS * 32, 1)
+plm_scatter_kernel(const float *__restrict__ R, int ld, const uint8_t *__restrict__ perm, int nchunk,
+                   long N, int L, float *__restrict__ G, size_t g_split_stride,
+                   int chunks_per_split, int col_tile0)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *Rs = reinterpret_cast<float *>(smem_raw);                                    // [2][SC_CH][SC_TC]
+    uint8_t *recs = smem_raw + sizeof(float) * 2 * SC_CH * SC_TC;                       // [2][SC_WARPS][PERM_REC]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col0 = (col_tile0 + blockIdx.x) * SC_TC;
+    const int j = blockIdx.y * SC_WARPS + warp;
+    const int c0 = blockIdx.z * chunks_per_split;
+    const int c1 = min(nchunk, c0 + chunks_per_split);
+
+    float4 acc[Q];
+#pragma unroll
+    for (int b = 0; b < Q; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto stage = [&](int buf, int c) {
+        float *dst = Rs + (size_t)buf * SC_CH * SC_TC;
+        const long nb = (long)c * SC_CH;
+        const int rows = (int)min((long)SC_CH, N - nb);
+        const float *src = R + (size_t)nb * ld + col0;
+        for (int t = tid; t < rows * 32; t += SC_WARPS * 32) {
+            const int row = t >> 5, c4 = t & 31;
+            cp_async16(dst + row * SC_TC + 4 * c4, src + (size_t)row * ld + 4 * c4);
+        }
+        if (j < L && lane < PERM_REC / 16)
+            cp_async16(recs + ((size_t)buf * SC_WARPS + warp) * PERM_REC + 16 * lane,
+                       perm + ((size_t)j * nchunk + c) * PERM_REC + 16 * lane);
+        cp_async_commit();
+    };
+
+    if (c0 < c1) stage(0, c0);
+    for (int c = c0; c < c1; ++c) {
+        const int buf = (c - c0) & 1;
+        if (c + 1 < c1) { stage(buf ^ 1, c + 1); cp_async_wait<1>(); }
+        else            { cp_async_wait<0>(); }
+        __syncthreads();
+        if (j < L) {
+            const uint8_t *rec = recs + ((size_t)buf * SC_WARPS + warp) * PERM_REC;
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(rec + PERM_CNT);
+            const float *Rb = Rs + (size_t)buf * SC_CH * SC_TC + 4 * lane;
+#pragma unroll
+            for (int b = 0; b < Q; ++b) {
+                const int m = rec[b];
+                float4 a = acc[b];
+                for (int k = 0; k < m; k += 4) {
+                    const uint32_t w4 = *pw++;
+                    {
+                        const float4 v = *reinterpret_cast<const float4 *>(Rb + (w4 & 0xffu) * SC_TC);
+                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                    }
+                    if (k + 1 < m) {
+                        const float4 v = *reinterpret_cast<const float4 *>(Rb + ((w4 >> 8) & 0xffu) * SC_TC);
+                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                    }
+                    if (k + 2 < m) {
+                        const float4 v = *reinterpret_cast<const float4 *>(Rb + ((w4 >> 16) & 0xffu) * SC_TC);
+                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                    }
+                    if (k + 3 < m) {
+                        const float4 v = *reinterpret_cast<const float4 *>(Rb + (w4 >> 24) * SC_TC);
+                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                    }
+                }
+                acc[b] = a;
+            }
+        }
+        __syncthreads();
+    }
+    if (j < L) {
+        float *g = G + (size_t)blockIdx.z * g_split_stride + (size_t)j * Q * ld + col0 + 4 * lane;
+#pragma unroll
+        for (int b = 0; b < Q; ++b) *reinterpret_cast<float4 *>(g + (size_t)b * ld) = acc[b];
+    }
+}
+
+// ------------------------------------------------------------------------------
+// assemble: g = 2*lambda*x + G^T-part + G-part in the reference's layout, plus
+// the reductions every L-BFGS step needs, in one pass over x:
+//   red[block] = { lambda*x^2 (owned entries), g.d, g.g, x.x }
+// "owned" (multi-GPU site shards): fields and blocks whose first site i is in
+// [site_lo,site_hi) carry the regulariser; the column-(i,a) data term needs i
+// in the shard, the column-(j,b) term needs j in the shard.
+template <int Q>
+__global__ void __launch_bounds__(256)
+plm_assemble_kernel(const float *__restrict__ x, const float *__restrict__ G, size_t g_split_stride,
+                    int nsplit, int L, int ld, float lh, float lJ, int site_lo, int site_hi,
+                    const float *__restrict__ d, float *__restrict__ g, double *__restrict__ red)
+{
+    constexpr int QQ = Q * Q;
+    __shared__ float tile[AS_JG][QQ];
+    __shared__ double scratch[32];
+    const int i = blockIdx.y;
+    const int j0 = blockIdx.x * AS_JG;
+    const long Lq = (long)L * Q;
+    const bool own_i = (i >= site_lo && i < site_hi);
+    double s_reg = 0.0, s_dg = 0.0, s_gg = 0.0, s_xx = 0.0;
+
+    if (blockIdx.x == 0 && threadIdx.x < Q) {          // fields of site i
+        const int a = threadIdx.x;
+        const long k = (long)i * Q + a;
+        const float h = x[k];
+        float gv = 0.f;
+        if (own_i) {
+            gv = 2.f * lh * h;
+            float col = 0.f;
+            for (int s = 0; s < nsplit; ++s) {
+                const float *Gs = G + (size_t)s * g_split_stride;
+                for (int b = 0; b < Q; ++b) col += Gs[((long)i * Q + b) * ld + i * Q + a];
+            }
+            gv += col;
+            s_reg += (double)lh * h * h;
+            s_xx += (double)h * h;
+        }
+        g[k] = gv;
+        if (d) s_dg += (double)gv * d[k];
+        s_gg += (double)gv * gv;
+    }
+
+    const bool any = (j0 + AS_JG - 1 > i);
+    if (any) {
+        // transposed part U[a][b] = G[(j,b)][(i,a)] : read with a fastest, park in smem
+        for (int jj = 0; jj < AS_JG; ++jj) {
+            const int j = j0 + jj;
+            if (j <= i || j >= L) continue;
+            for (int t = threadIdx.x; t < QQ; t += 256) {
+                const int b = t / Q, a = t - b * Q;
+                float u = 0.f;
+                if (own_i)
+                    for (int s = 0; s < nsplit; ++s)
+                        u += G[(size_t)s * g_split_stride + ((long)j * Q + b) * ld + i * Q + a];
+                tile[jj][a * Q + b] = u;
+            }
+        }
+    }
+    __syncthreads();
+    if (any) {
+        for (int jj = 0; jj < AS_JG; ++jj) {
+            const int j = j0 + jj;
+            if (j <= i || j >= L) continue;
+            const bool own_j = (j >= site_lo && j < site_hi);
+            const long base = Lq + pair_index(L, i, j) * QQ;
+            for (int t = threadIdx.x; t < QQ; t += 256) {
+                const int a = t / Q, b = t - a * Q;
+                const float xv = x[base + t];
+                float gv = own_i ? 2.f * lJ * xv : 0.f;
+                gv += tile[jj][t];
+                if (own_j) {
+                    float v = 0.f;
+                    for (int s = 0; s < nsplit; ++s)
+                        v += G[(size_t)s * g_split_stride + ((long)i * Q + a) * ld + j * Q + b];
+                    gv += v;
+                }
+                g[base + t] = gv;
+                if (own_i) { s_reg += (double)lJ * xv * xv; s_xx += (double)xv * xv; }
+                if (d) s_dg += (double)gv * d[base + t];
+                s_gg += (double)gv * gv;
+            }
+        }
+    }
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    double r;
+    r = block_sum(s_reg, scratch); if (threadIdx.x == 0) red[4 * (size_t)blk + 0] = r;
+    r = block_sum(s_dg, scratch);  if (threadIdx.x == 0) red[4 * (size_t)blk + 1] = r;
+    r = block_sum(s_gg, scratch);  if (threadIdx.x == 0) red[4 * (size_t)blk + 2] = r;
+    r = block_sum(s_xx, scratch);  if (threadIdx.x == 0) red[4 * (size_t)blk + 3] = r;
+}
+
+// single CTA, fixed order: scal = { fx, g.d, g.g, x.x }
+__global__ void __launch_bounds__(256)
+plm_finalize_kernel(const double *__restrict__ red, int nred, const double *__restrict__ fxpart,
+                    long nscan, int L, int site_lo, int site_hi, double *__restrict__ scal)
+{
+    __shared__ double scratch[32];
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < nred; b += 256) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[c] += red[4 * (size_t)b + c];
+    }
+    const int ns = site_hi - site_lo;
+    for (long t = threadIdx.x; t < nscan * ns; t += 256) {
+        const long k = t / ns;
+        const int site = site_lo + (int)(t - k * ns);
+        s[0] += fxpart[k * L + site];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double r = block_sum(s[c], scratch);
+        if (threadIdx.x == 0) scal[c] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------
+// initial point (plmdca_numerics.cpp:51-81, :207-249): one thread per site,
+// sequences accumulated in file order in float32 exactly like the reference.
+template <int Q>
+__global__ void plm_init_fields_kernel(const uint8_t *__restrict__ msaT, const float *__restrict__ w,
+                                       long N, long Npad, int L, float meff, float *__restrict__ x)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L) return;
+    float f[Q];
+#pragma unroll
+    for (int a = 0; a < Q; ++a) f[a] = 0.f;
+    const uint8_t *col = msaT + (size_t)i * Npad;
+    for (long n = 0; n < N; ++n) {
+        const int r = col[n];
+        const float wn = w[n];
+#pragma unroll
+        for (int a = 0; a < Q; ++a) f[a] += (a == r) ? wn : 0.f;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < Q; ++a) {
+        const float fr = __fdiv_rn(f[a], meff);
+        f[a] = logf(__fadd_rn(__fmul_rn(fr, meff), 1.f));
+        s += f[a];
+    }
+    const float av = __fdiv_rn(s, (float)Q);
+#pragma unroll
+    for (int a = 0; a < Q; ++a) x[a + Q * i] = f[a] - av;
+}
+
+// ------------------------------------------------------------------------------
+template <int Q>
+static int plm_setup_t(PlmProblem *p)
+{
+    cudaStream_t st = p->stream;
+    {
+        const long total = (long)p->L * p->Npad;
+        DCA_LAUNCH(transpose_msa_kernel, (unsigned)ceil_div<long>(total, 256), 256, 0, st,
+                   p->d_msa, p->N, p->L, p->Npad, p->d_msaT);
+    }
+    {
+        const long total = (long)p->L * p->nchunk;
+        DCA_CUDA(cudaMemsetAsync(p->d_perm, 0, (size_t)total * PERM_REC, st));
+        DCA_LAUNCH((build_perm_kernel<Q>), (unsigned)ceil_div<long>(total, 128), 128, 0, st,
+                   p->d_msaT, p->N, p->Npad, p->L, p->nchunk, p->d_perm);
+    }
+    const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN;
+    const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC;
+    DCA_CUDA(cudaFuncSetAttribute(plm_logits_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    DCA_CUDA(cudaFuncSetAttribute(plm_scatter_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+    DCA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int Q>
+static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *d_dir)
+{
+    cudaStream_t st = p->stream;
+    const int L = p->L, ld = p->ld;
+    dim3 gridU(ceil_div(L, AS_JG), L);
+    DCA_LAUNCH((plm_unpack_kernel<Q>), gridU, 256, 0, st, d_x, L, ld, p->d_W);
+
+    const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN;
+    dim3 gridA(p->col_tiles, (unsigned)(p->Npad / LG_TN));
+    DCA_LAUNCH((plm_logits_kernel<Q>), gridA, LG_THREADS, smemA, st,
+               p->d_W, ld, p->d_msaT, p->Npad, p->N, L, d_x, p->d_S, p->col_tile0);
+
+    const int nsites = p->site_hi - p->site_lo;
+    dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
+    DCA_LAUNCH((plm_softmax_kernel<Q>), gridB, 128, 0, st,
+               p->d_S, ld, p->d_msa, p->d_w, p->N, L, p->site_lo, p->site_hi,
+               p->chunk, p->warm, p->carry, p->d_fxpart);
+
+    const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC;
+    const size_t gstride = (size_t)p->Lq * ld;
+    dim3 gridC(p->col_tiles, ceil_div(L, SC_WARPS), p->nsplit);
+    DCA_LAUNCH((plm_scatter_kernel<Q>), gridC, SC_WARPS * 32, smemC, st,
+               p->d_S, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride,
+               p->chunks_per_split, p->col_tile0);
+
+    DCA_LAUNCH((plm_assemble_kernel<Q>), gridU, 256, 0, st,
+               d_x, p->d_G, gstride, p->nsplit, L, ld, p->lh, p->lJ, p->site_lo, p->site_hi,
+               d_dir, d_g, p->d_red);
+    DCA_LAUNCH(plm_finalize_kernel, 1, 256, 0, st,
+               p->d_red, p->red_blocks, p->d_fxpart, p->nscan, L, p->site_lo, p->site_hi, p->d_scal);
+    DCA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------
+static void plm_free(PlmProblem *p)
+{
+    if (!p) return;
+    cudaFree(p->d_msa); cudaFree(p->d_msaT); cudaFree(p->d_perm); cudaFree(p->d_w);
+    cudaFree(p->d_W); cudaFree(p->d_G); cudaFree(p->d_S); cudaFree(p->d_fxpart);
+    cudaFree(p->d_red); cudaFree(p->d_scal);
+    if (p->h_scal) cudaFreeHost(p->h_scal);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+static void plm_plan_scan(PlmProblem *p)
+{
+    p->nscan = ceil_div<long>(p->N, p->chunk);
+}
+
+PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
+                       float lambda_h, float lambda_J, int site_lo, int site_hi)
+{
+    if (require_device() != 0) return nullptr;
+    if (q != 21 && q != 5) { set_error("plm: num_site_states must be 21 or 5 (got %d)", q); return nullptr; }
+    if (N <= 0 || L < 2) { set_error("plm: empty alignment (N=%ld L=%d)", N, L); return nullptr; }
+    if (site_lo < 0 || site_hi > L || site_lo >= site_hi) {
+        set_error("plm: bad site shard [%d,%d) for L=%d", site_lo, site_hi, L); return nullptr;
+    }
+    for (long k = 0; k < N * (long)L; ++k)
+        if (h_msa[k] >= q) { set_error("plm: residue code %d >= q=%d at flat index %ld", h_msa[k], q, k); return nullptr; }
+
+    PlmProblem *p = new PlmProblem();
+    p->N = N; p->L = L; p->q = q; p->Lq = L * q;
+    p->Npad = ceil_div<long>(N, LG_TN) * LG_TN;
+    p->ld = ceil_div(p->Lq, LG_TC) * LG_TC;
+    p->P = (long)L * q + (long)L * (L - 1) / 2 * q * q;
+    p->lh = lambda_h; p->lJ = lambda_J;
+    p->site_lo = site_lo; p->site_hi = site_hi;
+    p->nchunk = (int)ceil_div<long>(N, SC_CH);
+    p->col_tile0 = (site_lo * q) / LG_TC;
+    p->col_tiles = ceil_div(site_hi * q, LG_TC) - p->col_tile0;
+    p->red_blocks = ceil_div(L, AS_JG) * L;
+    {   // n-splits of the scatter: enough CTAs for >= ~3 waves, each >= 8 chunks
+        const long tiles = (long)p->col_tiles * ceil_div(L, SC_WARPS);
+        int want = (int)ceil_div<long>(3L * sm_count(), std::max(1L, tiles));
+        int maxs = std::max(1, p->nchunk / 8);
+        p->nsplit = std::max(1, std::min(want, maxs));
+        p->chunks_per_split = ceil_div(p->nchunk, p->nsplit);
+        p->nsplit = ceil_div(p->nchunk, p->chunks_per_split);
+    }
+    float meff = 0.f;
+    for (long n = 0; n < N; ++n) meff += h_w[n];     // plmdca_numerics.cpp:46
+    p->h_meff = meff;
+    plm_plan_scan(p);
+
+#define PLM_TRY(call)                                                                 \
+    do { cudaError_t e__ = (call); if (e__ != cudaSuccess) {                          \
+        set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+        plm_free(p); return nullptr; } } while (0)
+
+    PLM_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    PLM_TRY(cudaMalloc(&p->d_msa, (size_t)N * L));
+    PLM_TRY(cudaMalloc(&p->d_msaT, (size_t)L * p->Npad));
+    PLM_TRY(cudaMalloc(&p->d_perm, (size_t)L * p->nchunk * PERM_REC));
+    PLM_TRY(cudaMalloc(&p->d_w, sizeof(float) * (size_t)N));
+    PLM_TRY(cudaMalloc(&p->d_W, sizeof(float) * (size_t)p->Lq * p->ld));
+    PLM_TRY(cudaMalloc(&p->d_G, sizeof(float) * (size_t)p->nsplit * p->Lq * p->ld));
+    PLM_TRY(cudaMalloc(&p->d_S, sizeof(float) * (size_t)p->Npad * p->ld));
+    PLM_TRY(cudaMalloc(&p->d_fxpart, sizeof(double) * (size_t)(N / 8 + 1) * L));   // chunk >= 8
+    PLM_TRY(cudaMalloc(&p->d_red, sizeof(double) * 4 * (size_t)p->red_blocks));
+    PLM_TRY(cudaMalloc(&p->d_scal, sizeof(double) * 16));
+    PLM_TRY(cudaMallocHost(&p->h_scal, sizeof(double) * 16));
+    PLM_TRY(cudaMemcpyAsync(p->d_msa, h_msa, (size_t)N * L, cudaMemcpyHostToDevice, p->stream));
+    PLM_TRY(cudaMemcpyAsync(p->d_w, h_w, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, p->stream));
+    PLM_TRY(cudaMemsetAsync(p->d_W, 0, sizeof(float) * (size_t)p->Lq * p->ld, p->stream));
+    PLM_TRY(cudaMemsetAsync(p->d_S, 0, sizeof(float) * (size_t)p->Npad * p->ld, p->stream));
+    PLM_TRY(cudaMemsetAsync(p->d_fxpart, 0, sizeof(double) * (size_t)(N / 8 + 1) * L, p->stream));
+    const int rc = (q == 21) ? plm_setup_t<21>(p) : plm_setup_t<5>(p);
+    if (rc != 0) { plm_free(p); return nullptr; }
+    PLM_TRY(cudaStreamSynchronize(p->stream));
+#undef PLM_TRY
+    return p;
+}
+
+void plm_destroy(PlmProblem *p) { plm_free(p); }
+long plm_num_params(const PlmProblem *p) { return p->P; }
+cudaStream_t plm_stream(const PlmProblem *p) { return p->stream; }
+double *plm_scalar_buffer(PlmProblem *p) { return p->d_scal; }
+
+void plm_set_carry(PlmProblem *p, int carry, int chunk, int warm)
+{
+    p->carry = carry ? 1 : 0;
+    if (chunk > 0) p->chunk = std::max(8, chunk);
+    if (warm >= 0) p->warm = warm;
+    plm_plan_scan(p);
+}
+
+int plm_eval_device(PlmProblem *p, const float *d_x, float *d_g, const float *d_dir)
+{
+    return (p->q == 21) ? plm_eval_t<21>(p, d_x, d_g, d_dir) : plm_eval_t<5>(p, d_x, d_g, d_dir);
+}
+
+int plm_read_scalars(PlmProblem *p, double *out)
+{
+    DCA_CUDA(cudaMemcpyAsync(p->h_scal, p->d_scal, sizeof(double) * PS_COUNT, cudaMemcpyDeviceToHost, p->stream));
+    DCA_CUDA(cudaStreamSynchronize(p->stream));
+    for (int k = 0; k < PS_COUNT; ++k) out[k] = p->h_scal[k];
+    return 0;
+}
+
+int plm_init_x_device(PlmProblem *p, float *d_x)
+{
+    DCA_CUDA(cudaMemsetAsync(d_x, 0, sizeof(float) * (size_t)p->P, p->stream));
+    if (p->q == 21)
+        DCA_LAUNCH((plm_init_fields_kernel<21>), ceil_div(p->L, 64), 64, 0, p->stream,
+                   p->d_msaT, p->d_w, p->N, p->Npad, p->L, p->h_meff, d_x);
+    else
+        DCA_LAUNCH((plm_init_fields_kernel<5>), ceil_div(p->L, 64), 64, 0, p->stream,
+                   p->d_msaT, p->d_w, p->N, p->Npad, p->L, p->h_meff, d_x);
+    DCA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace dca

@@ -1,0 +1,211 @@
+// reweight.cu -- all-pairs Hamming sequence reweighting on sm_100a.
+//
+// Replaces  PlmDCA::computeSeqsWeight   pydca/plmdca/plmdca_numerics.cpp:611-671
+//           compute_sequences_weight    pydca/meanfield_dca/msa_numerics.py:14-50
+//                                       pydca/plmdca/msa_numerics.py:13-49
+//
+// c_i = #{ j : ident(i,j)/L > seqid }  (self included, strict >).  The float
+// compare is turned into an INTEGER threshold on the host (the smallest ident
+// for which the reference's float32 / float64 expression is true), so the
+// device works on integers only and the counts are bit-exact.
+//
+// Layout: the u8 MSA is re-packed as rows of 32-bit words (4 residues per
+// word), row stride Lw words (multiple of 4 -> 16-byte cp.async), pad bytes 0
+// in every row (pads always match and add no mismatches).
+//
+// Kernel: CTA = 128 rows (i) x a range of j; 64-row j tiles and 128-byte k
+// chunks are staged into shared memory with 16-byte cp.async (double
+// buffered); each thread owns an 8x4 block of (i,j) pairs.  Per 4 residues:
+//   t = a ^ b ; u = t + 0x1f1f1f1f ; m = u & 0x20202020 ; acc = dp4a(m, 1, acc)
+// residues are < 32, so bit 5 of every byte of u is set iff that byte differs
+// (no carries between bytes); dp4a sums the four flags into a 32-bit counter.
+// Roofline: integer-ALU bound (4 lane-ops per 4 residues), not HBM bound:
+// algorithmic bytes are N*L + 4N, ops N^2*L byte compares.
+#include "dca_common.cuh"
+#include "dca_internal.h"
+
+namespace dca {
+
+constexpr int RW_TI = 128;      // i rows per CTA
+constexpr int RW_TJ = 64;       // j rows per tile
+constexpr int RW_KW = 32;       // words per k chunk (128 residues)
+constexpr int RW_STRIDE = 36;   // smem row stride in words (16B aligned, conflict-free LDS.128)
+
+__global__ void __launch_bounds__(256)
+reweight_kernel(const uint32_t *__restrict__ msa_w, long N, long i_lo, long i_hi, int Lw,
+                long j_per_split, unsigned max_mismatch32, unsigned *__restrict__ counts)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *Is = smem;                                   // [2][RW_TI][RW_STRIDE]
+    uint32_t *Js = smem + 2 * RW_TI * RW_STRIDE;           // [2][RW_TJ][RW_STRIDE]
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long i0 = i_lo + (long)blockIdx.x * RW_TI;
+    const long jbeg = (long)blockIdx.y * j_per_split;
+    const long jend = min(N, jbeg + j_per_split);
+    const int nk = (Lw + RW_KW - 1) / RW_KW;
+
+    unsigned rowcount[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) rowcount[r] = 0;
+
+    auto stage = [&](int buf, long j0, int kc) {
+        // I tile: 128 rows x 8 x 16B ; J tile: 64 rows x 8 x 16B
+        const int kw0 = kc * RW_KW;
+        for (int t = tid; t < RW_TI * 8; t += 256) {
+            const int row = t >> 3, seg = t & 7;
+            uint32_t *dst = Is + ((size_t)buf * RW_TI + row) * RW_STRIDE + seg * 4;
+            const long gi = i0 + row;
+            const int kw = kw0 + seg * 4;
+            if (gi < i_hi && kw < Lw) cp_async16(dst, msa_w + gi * Lw + kw);
+            else *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
+        }
+        for (int t = tid; t < RW_TJ * 8; t += 256) {
+            const int row = t >> 3, seg = t & 7;
+            uint32_t *dst = Js + ((size_t)buf * RW_TJ + row) * RW_STRIDE + seg * 4;
+            const long gj = j0 + row;
+            const int kw = kw0 + seg * 4;
+            if (gj < jend && kw < Lw) cp_async16(dst, msa_w + gj * Lw + kw);
+            else *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
+        }
+        cp_async_commit();
+    };
+
+    for (long j0 = jbeg; j0 < jend; j0 += RW_TJ) {
+        unsigned acc[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) acc[r][s] = 0;
+
+        stage(0, j0, 0);
+        for (int kc = 0; kc < nk; ++kc) {
+            const int buf = kc & 1;
+            if (kc + 1 < nk) { stage(buf ^ 1, j0, kc + 1); cp_async_wait<1>(); }
+            else             { cp_async_wait<0>(); }
+            __syncthreads();
+            const uint32_t *Ib = Is + (size_t)buf * RW_TI * RW_STRIDE;
+            const uint32_t *Jb = Js + (size_t)buf * RW_TJ * RW_STRIDE;
+#pragma unroll 2
+            for (int k4 = 0; k4 < RW_KW / 4; ++k4) {
+                uint4 a[8], b[4];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    a[r] = *reinterpret_cast<const uint4 *>(Ib + (ty + 16 * r) * RW_STRIDE + k4 * 4);
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    b[s] = *reinterpret_cast<const uint4 *>(Jb + (tx + 16 * s) * RW_STRIDE + k4 * 4);
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        unsigned c = acc[r][s];
+                        c = __dp4a(((a[r].x ^ b[s].x) + 0x1f1f1f1fu) & 0x20202020u, 0x01010101u, c);
+                        c = __dp4a(((a[r].y ^ b[s].y) + 0x1f1f1f1fu) & 0x20202020u, 0x01010101u, c);
+                        c = __dp4a(((a[r].z ^ b[s].z) + 0x1f1f1f1fu) & 0x20202020u, 0x01010101u, c);
+                        c = __dp4a(((a[r].w ^ b[s].w) + 0x1f1f1f1fu) & 0x20202020u, 0x01010101u, c);
+                        acc[r][s] = c;
+                    }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            unsigned c = 0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const long gj = j0 + tx + 16 * s;
+                c += (gj < jend && acc[r][s] <= max_mismatch32) ? 1u : 0u;
+            }
+            rowcount[r] += c;
+        }
+    }
+    // reduce the 16 tx lanes that share a row (lanes 0-15 / 16-31 of a warp)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        unsigned c = rowcount[r];
+        c += __shfl_xor_sync(0xffffffffu, c, 8);
+        c += __shfl_xor_sync(0xffffffffu, c, 4);
+        c += __shfl_xor_sync(0xffffffffu, c, 2);
+        c += __shfl_xor_sync(0xffffffffu, c, 1);
+        const long gi = i0 + ty + 16 * r;
+        if (tx == 0 && gi < i_hi) atomicAdd(counts + gi, c);   // integer: order-independent
+    }
+}
+
+// host-side integer threshold: smallest ident for which the reference's
+// compare holds (plmdca_numerics.cpp:642-643 in float32; msa_numerics.py:46 in
+// float64).  Returns L+1 when no ident satisfies it (seqid >= 1).
+int reweight_min_ident(int L, double seqid, int compare_f64)
+{
+    for (int k = 0; k <= L; ++k) {
+        bool hit;
+        if (compare_f64) hit = ((double)k / (double)L) > seqid;
+        else {
+            volatile float sim = (float)k / (float)L;
+            hit = sim > (float)seqid;
+        }
+        if (hit) return k;
+    }
+    return L + 1;
+}
+
+// pack a u8 [N][L] device MSA into zero-padded word rows
+__global__ void pack_rows_kernel(const uint8_t *__restrict__ msa, long N, int L, int Lw,
+                                 uint32_t *__restrict__ out)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * Lw) return;
+    const long n = idx / Lw;
+    const int kw = (int)(idx - n * Lw);
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int s = kw * 4 + b;
+        if (s < L) v |= (uint32_t)msa[n * L + s] << (8 * b);
+    }
+    out[idx] = v;
+}
+
+// counts for rows [row_lo,row_hi) against all N rows (multi-GPU: row shards,
+// SURVEY 8e).  d_msa: u8 [N][L] on device; d_counts: u32 [N] (zeroed here for
+// the shard range only).
+int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, int compare_f64,
+                           long row_lo, long row_hi, unsigned *d_counts, cudaStream_t stream)
+{
+    if (N <= 0 || L <= 0) { set_error("reweight: empty alignment (N=%ld L=%d)", N, L); return -1; }
+    const int Lw = (int)(ceil_div(L, 4) + 3) / 4 * 4;
+    uint32_t *d_words = nullptr;
+    DCA_CUDA(cudaMallocAsync(&d_words, sizeof(uint32_t) * (size_t)N * Lw, stream));
+    {
+        const long total = N * Lw;
+        DCA_LAUNCH(pack_rows_kernel, (unsigned)ceil_div<long>(total, 256), 256, 0, stream,
+                   d_msa, N, L, Lw, d_words);
+    }
+    DCA_CUDA(cudaMemsetAsync(d_counts + row_lo, 0, sizeof(unsigned) * (size_t)(row_hi - row_lo), stream));
+    const int T = reweight_min_ident(L, seqid, compare_f64);
+    if (T <= L) {
+        const unsigned max_mismatch32 = 32u * (unsigned)(L - T);
+        const long rows = row_hi - row_lo;
+        const unsigned gx = (unsigned)ceil_div<long>(rows, RW_TI);
+        // split j so that the grid covers the SMs at least twice
+        int js = (int)ceil_div<long>(2L * sm_count(), gx);
+        long jper = ceil_div<long>(ceil_div<long>(N, js), RW_TJ) * RW_TJ;
+        js = (int)ceil_div<long>(N, jper);
+        const size_t smem = sizeof(uint32_t) * 2 * (RW_TI + RW_TJ) * RW_STRIDE;
+        static bool attr_done = false;
+        if (!attr_done) {
+            DCA_CUDA(cudaFuncSetAttribute(reweight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        dim3 grid(gx, (unsigned)js);
+        DCA_LAUNCH(reweight_kernel, grid, 256, smem, stream,
+                   d_words, N, row_lo, row_hi, Lw, jper, max_mismatch32, d_counts);
+    }
+    DCA_CUDA(cudaGetLastError());
+    DCA_CUDA(cudaFreeAsync(d_words, stream));
+    return 0;
+}
+
+}  // namespace dca

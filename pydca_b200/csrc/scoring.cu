@@ -1,0 +1,123 @@
+// scoring.cu -- Frobenius-norm + average-product-correction scoring.
+//
+// Replaces  PlmDCA.get_couplings_no_gap_state / compute_sorted_FN / _FN_APC
+//                      pydca/plmdca/plmdca.py:246-268, :437-524
+//           MeanFieldDCA.compute_sorted_FN / _FN_APC
+//                      pydca/meanfield_dca/meanfield_dca.py:902-988
+//
+// Per site pair (i<j): take the (q-1)x(q-1) non-gap block of J_ij, subtract row
+// and column means, add the grand mean, Frobenius norm.  One warp per pair, the
+// block parked in shared memory, sums in float64 in a fixed order.  APC
+// s_ij - s_i. s_.j / s_.. needs only L(L-1)/2 numbers and is finished on the
+// host in float64 (the reference's pinned numpy also promotes to float64 there).
+// HBM-bound: 4*q*q (plm, f32) or 8*(q-1)^2 (mf, f64) bytes per pair, read once.
+#include "dca_common.cuh"
+#include "dca_internal.h"
+
+#include <vector>
+
+namespace dca {
+
+constexpr int FN_WARPS = 4;
+
+// SRC = float : block at x[L*q + pair*q*q + a*q + b]          (plm layout)
+// SRC = double: block at J[(i*(q-1)+a)*n + j*(q-1)+b], n=L(q-1) (mf layout)
+template <typename SRC>
+__global__ void __launch_bounds__(FN_WARPS * 32)
+fn_kernel(const SRC *__restrict__ src, int L, int q, int is_matrix, double *__restrict__ fn)
+{
+    extern __shared__ double sm[];
+    const int qm1 = q - 1, nb = qm1 * qm1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *blk = sm + (size_t)warp * (nb + 2 * qm1);
+    double *rmean = blk + nb, *cmean = rmean + qm1;
+    const long npairs = (long)L * (L - 1) / 2;
+    const long pair = (long)blockIdx.x * FN_WARPS + warp;
+    if (pair >= npairs) return;
+    // invert pair -> (i,j)
+    int i = 0;
+    {
+        long rem = pair;
+        while (rem >= L - 1 - i) { rem -= L - 1 - i; ++i; }
+        const int j = i + 1 + (int)rem;
+        const long n = (long)L * qm1;
+        for (int t = lane; t < nb; t += 32) {
+            const int a = t / qm1, b = t - a * qm1;
+            double v;
+            if (is_matrix) v = (double)src[((long)i * qm1 + a) * n + (long)j * qm1 + b];
+            else v = (double)src[(long)L * q + pair * q * q + a * q + b];
+            blk[t] = v;
+        }
+    }
+    __syncwarp();
+    for (int a = lane; a < qm1; a += 32) {
+        double r = 0.0, c = 0.0;
+        for (int b = 0; b < qm1; ++b) { r += blk[a * qm1 + b]; c += blk[b * qm1 + a]; }
+        rmean[a] = r / qm1;
+        cmean[a] = c / qm1;
+    }
+    __syncwarp();
+    double tot = 0.0;
+    for (int a = 0; a < qm1; ++a) tot += rmean[a];
+    const double gmean = tot / qm1;
+    double acc = 0.0;
+    for (int t = lane; t < nb; t += 32) {
+        const int a = t / qm1, b = t - a * qm1;
+        const double z = blk[t] - cmean[b] - rmean[a] + gmean;
+        acc += z * z;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) fn[pair] = sqrt(acc);
+}
+
+// APC on the host: s_ij - mean_i * mean_j / mean_all (plmdca.py:503-519)
+static void apc_host(const double *fn, int L, double *out)
+{
+    std::vector<double> site((size_t)L, 0.0);
+    long k = 0;
+    for (int i = 0; i < L - 1; ++i)
+        for (int j = i + 1; j < L; ++j, ++k) { site[i] += fn[k]; site[j] += fn[k]; }
+    double all = 0.0;
+    for (int i = 0; i < L; ++i) { site[i] /= (double)(L - 1); all += site[i]; }
+    all /= (double)L;
+    k = 0;
+    for (int i = 0; i < L - 1; ++i)
+        for (int j = i + 1; j < L; ++j, ++k) out[k] = fn[k] - site[i] * (site[j] / all);
+}
+
+template <typename SRC>
+static int fn_apc_impl(const SRC *h_src, size_t count, int L, int q, int is_matrix,
+                       double *fn, double *fn_apc)
+{
+    if (require_device() != 0) return -1;
+    if (L < 2 || q < 2) { set_error("fn_apc: bad shape L=%d q=%d", L, q); return -1; }
+    const long npairs = (long)L * (L - 1) / 2;
+    SRC *d_src = nullptr;
+    double *d_fn = nullptr;
+    DCA_CUDA(cudaMalloc(&d_src, sizeof(SRC) * count));
+    DCA_CUDA(cudaMalloc(&d_fn, sizeof(double) * (size_t)npairs));
+    DCA_CUDA(cudaMemcpy(d_src, h_src, sizeof(SRC) * count, cudaMemcpyHostToDevice));
+    const int qm1 = q - 1;
+    const size_t smem = sizeof(double) * FN_WARPS * (size_t)(qm1 * qm1 + 2 * qm1);
+    DCA_LAUNCH((fn_kernel<SRC>), (unsigned)ceil_div<long>(npairs, FN_WARPS), FN_WARPS * 32, smem, 0,
+               d_src, L, q, is_matrix, d_fn);
+    DCA_CUDA(cudaGetLastError());
+    DCA_CUDA(cudaMemcpy(fn, d_fn, sizeof(double) * (size_t)npairs, cudaMemcpyDeviceToHost));
+    cudaFree(d_src); cudaFree(d_fn);
+    if (fn_apc) apc_host(fn, L, fn_apc);
+    return 0;
+}
+
+int plm_fn_apc_host(const float *h_x, int L, int q, double *fn, double *fn_apc)
+{
+    const size_t P = (size_t)L * q + (size_t)L * (L - 1) / 2 * q * q;
+    return fn_apc_impl<float>(h_x, P, L, q, 0, fn, fn_apc);
+}
+
+int mf_fn_apc_host(const double *h_J, int L, int q, double *fn, double *fn_apc)
+{
+    const size_t n = (size_t)L * (q - 1);
+    return fn_apc_impl<double>(h_J, n * n, L, q, 1, fn, fn_apc);
+}
+
+}  // namespace dca
