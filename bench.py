@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- plmDCA gradient-evaluations/second on the BASELINE workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], "C2"): plmdca compute_fn protein on the seeded
+synthetic MSA N=5000, L=150, q=21, seqid 0.8, lambda_h = lambda_J = 0.2(L-1),
+max_iterations = 500.
+
+A STEP is one complete plmDCA fit of that MSA: L-BFGS from the reference's initial
+point until the optimiser stops (as in the reference, the float32 More-Thuente line
+search ends the run long before 500 iterations, SURVEY finding 4).  The metric counts
+every objective/gradient evaluation inside the L-BFGS loop (1 + sum of line-search
+trials); `value` = evaluations of the K timed fits / their CUDA-event time with the MSA,
+weights and work buffers resident in HBM; `e2e` = the same metric through the
+reference's own entry point plmdcaBackend(file, ...) with host buffers: FASTA parse,
+de-duplication, reweighting, H2D, fit and D2H of the result inside the timed region.
+
+At N > 1 GPUs the SAME fit is sharded by sites (one all-reduce of the gradient per
+evaluation over NCCL), i.e. strong scaling.
+
+--impl reference times the reference's own OpenMP implementation (oracle/_ref, built
+from /root/reference unmodified) on the host cores: each step is a bounded sample
+(the first REF_ITERS L-BFGS iterations of the same fit).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SEQ, SEQ_LEN, Q = 5000, 150, 21
+SEQID = 0.8
+MAX_ITER = 500
+REF_ITERS = 3            # L-BFGS iterations per reference-arm step (bounded sample)
+CPU_BASELINE_ITERS = 8   # bounded sample for the cpu_baseline object of our own line
+
+
+def workload(tmpdir):
+    from pydca_b200.synthetic import synthetic_msa, write_fasta
+    msa = synthetic_msa(N_SEQ, SEQ_LEN, Q)
+    path = os.path.join(tmpdir, "c2_N%d_L%d.fa" % (N_SEQ, SEQ_LEN))
+    if not os.path.exists(path):
+        write_fasta(msa, path, Q)
+    lam = 0.2 * (SEQ_LEN - 1)
+    return msa, path, lam
+
+
+def config_dict(n_gpus):
+    return {"workload": "C2: plmdca compute_fn protein, synthetic MSA N=%d L=%d q=%d, seqid %.1f, "
+                        "lambda_h=lambda_J=0.2(L-1), max_iterations=%d; one step = one full fit"
+                        % (N_SEQ, SEQ_LEN, Q, SEQID, MAX_ITER),
+            "N": N_SEQ, "L": SEQ_LEN, "q": Q, "max_iterations": MAX_ITER,
+            "parallelism": "site-shard x%d + all-reduce(g) per evaluation" % n_gpus if n_gpus > 1 else "single GPU",
+            "l2": "working set per evaluation (W 40 MB + S 64 MB + G >= 40 MB + 16 L-BFGS vectors x 20 MB) "
+                  "exceeds the 126 MB L2; no explicit flush"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def cpu_reference_fit(path, lam, iters, threads):
+    """The reference's own lbfgs + PlmDCA::gradient (oracle/_ref) or, if that binary is
+    absent, single gradient calls of the C port.  Returns (evals, seconds, kind, cores)."""
+    import oracle
+    if oracle.have_ref():
+        R = oracle.ref()
+        rp = R.plm(path, "protein", SEQ_LEN, Q, SEQID, lam, lam, threads)   # parse + dedup + reweight (untimed)
+        t0 = time.perf_counter()
+        _, status, evals, fx = rp.fit(iters)
+        dt = time.perf_counter() - t0
+        rp.close()
+        return evals, dt, "reference", threads
+    P = oracle.port()
+    msa = P.read_fasta(path, "protein", SEQ_LEN)
+    w = P.plm_weights(P.reweight_counts(msa, SEQID))
+    x = P.plm_init(msa, w, Q)
+    P.set_num_threads(threads)
+    t0 = time.perf_counter()
+    n = max(1, iters)
+    for _ in range(n):
+        P.plm_gradient(msa, w, Q, lam, lam, x)
+    return n, time.perf_counter() - t0, "port", threads
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    tmp = tempfile.mkdtemp(prefix="dca_bench_")
+    msa, path, lam = workload(tmp)
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_reference_fit(path, lam, REF_ITERS, cores)
+    evals = 0
+    secs = 0.0
+    kind = "reference"
+    for _ in range(args.steps):
+        e, dt, kind, _ = cpu_reference_fit(path, lam, REF_ITERS, cores)
+        evals += e
+        secs += dt
+    value = evals / secs
+    sample = ("each step = first %d L-BFGS iterations of the C2 fit (%s lbfgs + PlmDCA::gradient, %d OpenMP threads); "
+              "parse/dedup/reweight untimed" % (REF_ITERS, "reference" if kind == "reference" else "oracle port", cores))
+    line = {"impl": "reference", "metric": "plmdca_grad_evals_per_sec", "value": value, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def roofline_block(obj, x0, peaks):
+    """CUDA-event time of every kernel of one evaluation (events on the stream the
+    kernels run on), dominant kernel vs the HBM roofline, plus the two on-chip roofs
+    that actually bound it."""
+    reps = 5
+    obj.eval_timed(x0)
+    acc = None
+    for _ in range(reps):
+        t = obj.eval_timed(x0)
+        acc = t if acc is None else {k: acc[k] + t[k] for k in t}
+    ms = {k: v / reps for k, v in acc.items()}
+    g = obj.describe()
+    N, L, q, ld, P, nsplit = g["N"], g["L"], g["q"], g["ld"], g["P"], g["nsplit"]
+    Lq = L * q
+    # algorithmic (compulsory) bytes of each kernel, one launch
+    bytes_k = {
+        "unpack": 4 * P + 4 * Lq * Lq,
+        "logits": 4 * Lq * Lq + N * L + 4 * N * Lq,            # read W once, MSA once; write S
+        "softmax_scan": 8 * N * Lq + N * L + 4 * N,            # read S, write r
+        "scatter": 4 * N * Lq + int(1.75 * N * L) + 4 * Lq * Lq * nsplit,
+        "assemble": 4 * Lq * Lq * nsplit + 8 * P,
+    }
+    adds = N * L * Lq                                          # gather adds of logits == scatter
+    top = max(ms, key=ms.get)
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    achieved = bytes_k[top] / (ms[top] * 1e-3) / 1e9
+    eval_bytes = 8 * P + N * L + 4 * N                          # SURVEY 8(d) per-evaluation figure
+    total_ms = sum(ms.values())
+    sm_clock_ghz = peaks.get("sm_max_mhz", 1965.0) / 1e3
+    lane_peak = 148 * 128 * sm_clock_ghz                       # Gop/s FP32 lanes
+    smem_peak = 148 * 32 * sm_clock_ghz                        # G words/s shared-memory bandwidth
+    out = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+           "frac": achieved / hbm, "traffic": None,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+           "kernel_ms": ms, "kernel_share": {k: v / total_ms for k, v in ms.items()},
+           "algorithmic_bytes": bytes_k,
+           "eval": {"algorithmic_bytes": eval_bytes, "ms": total_ms,
+                    "achieved": eval_bytes / (total_ms * 1e-3) / 1e9, "frac": eval_bytes / (total_ms * 1e-3) / 1e9 / hbm},
+           "on_chip": {"note": "logits/scatter are shared-memory-gather bound (1 LDS word per add), not HBM bound",
+                       "gather_adds_per_kernel": adds,
+                       "logits_gadds_per_s": adds / (ms["logits"] * 1e-3) / 1e9,
+                       "scatter_gadds_per_s": adds / (ms["scatter"] * 1e-3) / 1e9,
+                       "smem_roof_gwords_per_s": smem_peak, "fp32_lane_roof_gops": lane_peak,
+                       "logits_frac_of_smem_roof": adds / (ms["logits"] * 1e-3) / 1e9 / smem_peak,
+                       "scatter_frac_of_smem_roof": adds / (ms["scatter"] * 1e-3) / 1e9 / smem_peak,
+                       "eval_frac_of_fp32_lane_roof": 2 * adds / (total_ms * 1e-3) / 1e9 / lane_peak}}
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    from pydca_b200 import _lib
+    from pydca_b200 import distributed as dd
+    L = _lib.lib()
+    if L.dca_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; pydca_b200 has no CPU fallback")
+    _lib.check(L.dca_set_device(local_rank), "dca_set_device")
+    dist = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    tmp = tempfile.mkdtemp(prefix="dca_bench_")
+    msa, path, lam = workload(tmp)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    # ---- device-resident objective --------------------------------------------------
+    if world > 1:
+        counts = dd.sharded_counts(msa, SEQID, device=torch.device("cuda", local_rank))
+        sites = dd.shard_range(SEQ_LEN, rank, world)
+        cb = dd.make_allreduce_callback()
+    else:
+        counts = _lib.sequence_counts(msa, SEQID)
+        sites, cb = None, None
+    w = (1.0 / counts.astype(np.float32)).astype(np.float32)
+    obj = _lib.PlmObjective(msa, w, Q, lam, lam, sites=sites)
+    x0 = obj.init()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        obj.fit(x0, MAX_ITER, allreduce=cb)
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = L.dca_kernel_launches()
+    evals, dev_ms = 0, 0.0
+    t0 = time.perf_counter()
+    status = iters = 0
+    for _ in range(args.steps):
+        _, res = obj.fit(x0, MAX_ITER, allreduce=cb)       # fit() synchronises its stream before returning
+        evals += res.evaluations
+        dev_ms += res.device_ms
+        status, iters = res.status, res.iterations
+    wall = time.perf_counter() - t0
+    barrier()
+    launches = L.dca_kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([dev_ms, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall = float(t[0]), float(t[1])
+
+    # ---- end to end through the reference's entry point (host buffers, file input) ----
+    e2e = None
+    if world == 1:
+        n_e2e = max(1, min(args.steps, 5))
+        _lib.plmdca_backend(path, "protein", SEQ_LEN, Q, SEQID, lam, lam, MAX_ITER)      # warm (page cache, context)
+        e_evals = 0
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            _lib.plmdca_backend(path, "protein", SEQ_LEN, Q, SEQID, lam, lam, MAX_ITER)
+            e_evals += _lib.last_fit().evaluations
+        e_wall = time.perf_counter() - t0
+        P = obj.P
+        e2e = {"value": e_evals / e_wall, "unit": "evals/s",
+               "h2d_bytes_per_step": 2 * N_SEQ * SEQ_LEN + 4 * N_SEQ + 4 * P,
+               "d2h_bytes_per_step": 4 * N_SEQ + 8 * P,
+               "ms_per_step": 1e3 * e_wall / n_e2e, "steps": n_e2e,
+               "call": "plmdcaBackend(msa_file, ...) -> float*: FASTA parse + dedup + reweight + H2D + fit + D2H"}
+    else:
+        # sharded end-to-end: host MSA -> sharded reweight -> create -> fit -> host x, per rank
+        barrier()
+        t0 = time.perf_counter()
+        c2 = dd.sharded_counts(msa, SEQID, device=torch.device("cuda", local_rank))
+        w2 = (1.0 / c2.astype(np.float32)).astype(np.float32)
+        o2 = _lib.PlmObjective(msa, w2, Q, lam, lam, sites=sites)
+        _, r2 = o2.fit(o2.init(), MAX_ITER, allreduce=cb)
+        barrier()
+        e_wall = time.perf_counter() - t0
+        o2.close()
+        t = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": r2.evaluations / float(t[0]), "unit": "evals/s",
+               "h2d_bytes_per_step": 2 * N_SEQ * SEQ_LEN + 4 * N_SEQ + 4 * obj.P,
+               "d2h_bytes_per_step": 4 * N_SEQ + 8 * obj.P, "ms_per_step": 1e3 * float(t[0]), "steps": 1,
+               "call": "host MSA -> row-sharded reweight + all-reduce -> site-sharded fit -> host x"}
+
+    if rank == 0:
+        line = {"metric": "plmdca_grad_evals_per_sec", "value": evals / (dev_ms * 1e-3), "unit": "evals/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world),
+                "evals_per_step": evals / max(1, args.steps), "lbfgs_status": status, "lbfgs_iterations": iters,
+                "wall_ms_per_step": 1e3 * wall / max(1, args.steps),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+        if world == 1:
+            line["roofline"] = roofline_block(obj, x0, peaks)
+            cores = os.cpu_count() or 1
+            try:
+                ev, dt, kind, cores = cpu_reference_fit(path, lam, CPU_BASELINE_ITERS, cores)
+                line["cpu_baseline"] = {"value": ev / dt, "unit": "evals/s", "cores": cores, "kind": kind,
+                                        "sample": "first %d L-BFGS iterations of the same C2 fit (%d evaluations, %.1f s) with "
+                                                  "the reference's own lbfgs + PlmDCA::gradient built from /root/reference "
+                                                  "(-fopenmp -O3), %d threads" % (CPU_BASELINE_ITERS, ev, dt, cores)}
+            except Exception as exc:
+                line["cpu_baseline"] = {"value": None, "unit": "evals/s", "cores": cores, "kind": "unavailable",
+                                        "sample": repr(exc)}
+        print(json.dumps(line))
+    obj.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -85,6 +85,11 @@ int dca_plm_eval(dca_plm *p, const float *x_host, float *g_host, double *fx_out)
  * scalars_out_host may be NULL; otherwise receives {fx, g.dir, g.g, x.x}. */
 int dca_plm_eval_device(dca_plm *p, const float *x_dev, float *g_dev,
                         const float *dir_dev, double *scalars_out_host);
+/* measurement hooks: one evaluation with CUDA events between its kernels, on the
+ * stream they run on: ms_out[5] = unpack, logits, softmax scan, scatter,
+ * assemble+finalize.  out10 = {N, L, q, ld, P, nsplit, nchunk, col_tiles, Npad, nscan}. */
+int dca_plm_eval_timed(dca_plm *p, const float *x_host, float *ms_out);
+int dca_plm_describe(const dca_plm *p, long *out10);
 /* optional collective for site-sharded objectives: sum g (n floats) and the
  * n_scalars doubles at scalars_dev over all ranks; both are DEVICE pointers. */
 typedef int (*dca_allreduce_fn)(void *ctx, float *g_dev, long n, double *scalars_dev, int n_scalars);
@@ -102,6 +107,9 @@ typedef struct {
 int dca_plm_fit(dca_plm *p, float *x_inout_host, int max_iterations, int verbose,
                 int warmup_iterations, dca_allreduce_fn allreduce, void *allreduce_ctx,
                 dca_fit_result *result);
+/* statistics of this thread's most recent plmdcaBackend() call (the reference's
+ * entry point discards the L-BFGS return code, plmdcaBackend.cpp:197). */
+int dca_last_fit(dca_fit_result *result);
 
 /* ---- scoring --------------------------------------------------------------------
  * Frobenius norm of the double-centred non-gap block of every J_ij, then APC
@@ -125,6 +133,20 @@ int dca_mf_couplings(const double *corr, int n, double *couplings_out);
 /* FN + APC of the couplings matrix (meanfield_dca.py:902-988). */
 int dca_mf_fn_apc(const double *couplings, int seqs_len, int num_site_states,
                   double *fn_out, double *fn_apc_out);
+/* construct_corr_mat on caller-supplied regularised frequencies (:271-318):
+ * reg_fi double[L][q], reg_fij double[L(L-1)/2][q-1][q-1] -> corr_out n x n. */
+int dca_mf_corr_from_freqs(const double *reg_fi, const double *reg_fij, int seqs_len,
+                           int num_site_states, double *corr_out);
+
+/* ---- direct information ------------------------------------------------------------
+ * two-site-model fields (fixed point to 1e-4) + DI per pair:
+ * msa_numerics.py:378-533 (mf: couplings = n x n matrix) and
+ * pydca/plmdca/msa_numerics.py:156-311 (plm: parameter vector x, gap stripped).
+ * di_out double[L(L-1)/2]; fields_out double[L(L-1)/2][2][q] or NULL. */
+int dca_mf_direct_info(const double *couplings, const double *reg_fi, int seqs_len,
+                       int num_site_states, double *di_out, double *fields_out);
+int dca_plm_direct_info(const float *x_host, const double *reg_fi, int seqs_len,
+                        int num_site_states, double *di_out, double *fields_out);
 
 #ifdef __cplusplus
 }

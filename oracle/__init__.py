@@ -188,6 +188,16 @@ class _RefPlm:
         self._lib.ref_plm_reweight(self._h, _ptr(out, _f32p))
         return out
 
+    def fit(self, max_iterations):
+        """Reference lbfgs() on the reference gradient (plmdcaBackend.cpp:61-81
+        parameters); returns (x, status, evaluations, fx)."""
+        x = np.zeros(self.P, dtype=np.float32)
+        evals = ctypes.c_int(0)
+        fx = ctypes.c_float(0)
+        st = self._lib.ref_plm_fit(self._h, _ptr(x, _f32p), int(max_iterations), ctypes.byref(evals),
+                                   ctypes.byref(fx))
+        return x, int(st), int(evals.value), float(fx.value)
+
 
 class _Ref:
     def __init__(self):
@@ -213,6 +223,9 @@ class _Ref:
         L.ref_plm_gradient.argtypes = [ctypes.c_void_p, _f32p, _f32p]
         L.ref_plm_gradient.restype = ctypes.c_float
         L.ref_plm_reweight.argtypes = [ctypes.c_void_p, _f32p]
+        L.ref_plm_fit.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_uint, ctypes.POINTER(ctypes.c_int),
+                                  ctypes.POINTER(ctypes.c_float)]
+        L.ref_plm_fit.restype = ctypes.c_int
         # the reference's public C ABI (plmdcaBackend.cpp:151, :204)
         L.plmdcaBackend.argtypes = (ctypes.c_ushort, ctypes.c_ushort, ctypes.c_char_p, ctypes.c_uint,
                                     ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_uint,

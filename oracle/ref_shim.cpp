@@ -79,4 +79,42 @@ void ref_plm_reweight(void *p, float *out)
     if (out) std::copy(w.begin(), w.end(), out);
 }
 
+// The reference's own lbfgs() (lbfgs/lib/lbfgs.cpp:248) on the reference's own
+// PlmDCA::gradient, parameterised exactly as ObjectiveFunction::run does
+// (plmdcaBackend.cpp:61-81), but counting the objective evaluations, which
+// plmdcaBackend() itself does not report.  x receives the result (P floats).
+struct ShimFitCtx { PlmDCA *obj; int evals; };
+
+static lbfgsfloatval_t shim_evaluate(void *instance, const lbfgsfloatval_t *x, lbfgsfloatval_t *g,
+                                     const int, const lbfgsfloatval_t)
+{
+    auto *c = static_cast<ShimFitCtx *>(instance);
+    ++c->evals;
+    return c->obj->gradient(x, g);
+}
+
+int ref_plm_fit(void *p, float *x, unsigned max_iterations, int *evals_out, float *fx_out)
+{
+    auto *o = static_cast<PlmDCA *>(p);
+    const int n = static_cast<int>(o->num_fields_and_couplings);
+    lbfgsfloatval_t *m_x = lbfgs_malloc(n);
+    if (!m_x) return 1;
+    lbfgs_parameter_t param;
+    lbfgs_parameter_init(&param);
+    param.epsilon = 1E-3;
+    param.max_iterations = static_cast<int>(max_iterations);
+    param.max_linesearch = 5;
+    param.ftol = 1E-4;
+    param.m = 5;
+    o->initFieldsAndCouplings(m_x);
+    ShimFitCtx ctx{o, 0};
+    lbfgsfloatval_t fx = 0;
+    const int ret = lbfgs(n, m_x, &fx, shim_evaluate, nullptr, &ctx, &param);
+    std::copy(m_x, m_x + n, x);
+    lbfgs_free(m_x);
+    if (evals_out) *evals_out = ctx.evals;
+    if (fx_out) *fx_out = fx;
+    return ret;
+}
+
 }  // extern "C"

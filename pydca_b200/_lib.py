@@ -82,12 +82,18 @@ def lib():
     L.dca_plm_eval_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _f64p]
     L.dca_plm_fit.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                               ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FitResult)]
+    L.dca_plm_eval_timed.argtypes = [ctypes.c_void_p, _f32p, _f32p]
+    L.dca_plm_describe.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_long)]
+    L.dca_last_fit.argtypes = [ctypes.POINTER(FitResult)]
     L.dca_plm_fn_apc.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
     L.dca_mf_freqs.argtypes = [_u8p, _f64p, ctypes.c_long, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
     L.dca_mf_corr_mat.argtypes = [_u8p, _f64p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                   _f64p, _f64p]
     L.dca_mf_couplings.argtypes = [_f64p, ctypes.c_int, _f64p]
     L.dca_mf_fn_apc.argtypes = [_f64p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
+    L.dca_mf_corr_from_freqs.argtypes = [_f64p, _f64p, ctypes.c_int, ctypes.c_int, _f64p]
+    L.dca_mf_direct_info.argtypes = [_f64p, _f64p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
+    L.dca_plm_direct_info.argtypes = [_f32p, _f64p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
     _lib = L
     return L
 
@@ -175,6 +181,21 @@ class PlmObjective:
                                         ptr(sc, _f64p) if read_scalars else None), "dca_plm_eval_device")
         return sc
 
+    KERNELS = ("unpack", "logits", "softmax_scan", "scatter", "assemble")
+
+    def eval_timed(self, x):
+        """Per-kernel CUDA-event milliseconds of one evaluation (dict by kernel)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        ms = np.zeros(5, dtype=np.float32)
+        check(lib().dca_plm_eval_timed(self._h, ptr(x, _f32p), ptr(ms, _f32p)), "dca_plm_eval_timed")
+        return dict(zip(self.KERNELS, ms.tolist()))
+
+    def describe(self):
+        out = (ctypes.c_long * 10)()
+        check(lib().dca_plm_describe(self._h, out), "dca_plm_describe")
+        keys = ("N", "L", "q", "ld", "P", "nsplit", "nchunk", "col_tiles", "Npad", "nscan")
+        return dict(zip(keys, [int(v) for v in out]))
+
     def fit(self, x0, max_iterations, verbose=False, warmup_iterations=0, allreduce=None):
         x = np.array(x0, dtype=np.float32, copy=True)
         res = FitResult()
@@ -192,6 +213,13 @@ def plm_fn_apc(x, seqs_len, num_site_states):
     check(lib().dca_plm_fn_apc(ptr(x, _f32p), int(seqs_len), int(num_site_states), ptr(fn, _f64p),
                                ptr(apc, _f64p)), "dca_plm_fn_apc")
     return fn, apc
+
+
+def last_fit():
+    """L-BFGS statistics of this thread's most recent plmdcaBackend() call."""
+    res = FitResult()
+    check(lib().dca_last_fit(ctypes.byref(res)), "dca_last_fit")
+    return res
 
 
 def plmdca_backend(msa_file, biomolecule, seqs_len, num_site_states, seqid, lambda_h, lambda_J,

@@ -65,6 +65,10 @@ int mf_corr_mat_host(const uint8_t *msa, const double *w, long N, int L, int q, 
                      double *reg_fi, double *corr);
 int mf_couplings_host(const double *corr, int n, double *out);
 int mf_fn_apc_host(const double *h_J, int L, int q, double *fn, double *fn_apc);
+int mf_corr_from_freqs_host(const double *reg_fi, const double *reg_fij, int L, int q, double *corr);
+// scoring.cu
+int plm_di_host(const float *h_x, const double *h_reg_fi, int L, int q, double *di, double *fields);
+int mf_di_host(const double *h_J, const double *h_reg_fi, int L, int q, double *di, double *fields);
 
 }  // namespace dca
 
@@ -74,6 +78,8 @@ struct dca_plm {
     PlmProblem *prob;
     float *d_x, *d_g;
 };
+
+static thread_local dca_fit_result t_last_fit = {};
 
 extern "C" {
 
@@ -199,6 +205,22 @@ int dca_plm_eval_device(dca_plm *p, const float *x_dev, float *g_dev, const floa
     return 0;
 }
 
+int dca_plm_eval_timed(dca_plm *p, const float *x_host, float *ms_out)
+{
+    if (!p || !x_host || !ms_out) { set_error("dca_plm_eval_timed: null argument"); return -1; }
+    cudaStream_t st = plm_stream(p->prob);
+    DCA_CUDA(cudaMemcpyAsync(p->d_x, x_host, sizeof(float) * (size_t)plm_num_params(p->prob),
+                             cudaMemcpyHostToDevice, st));
+    return plm_eval_timed(p->prob, p->d_x, p->d_g, ms_out);
+}
+
+int dca_plm_describe(const dca_plm *p, long *out10)
+{
+    if (!p || !out10) { set_error("dca_plm_describe: null argument"); return -1; }
+    plm_describe(p->prob, out10);
+    return 0;
+}
+
 int dca_plm_fit(dca_plm *p, float *x_inout_host, int max_iterations, int verbose, int warmup_iterations,
                 dca_allreduce_fn allreduce, void *allreduce_ctx, dca_fit_result *result)
 {
@@ -261,7 +283,15 @@ float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states,
     if (rc == 0) rc = dca_plm_fit(h, x, (int)max_iteration, verbose ? 1 : 0, 0, nullptr, nullptr, &res);   // :81
     dca_plm_destroy(h);
     if (rc != 0) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); free(x); return nullptr; }
+    t_last_fit = res;
     return x;
+}
+
+int dca_last_fit(dca_fit_result *result)
+{
+    if (!result) { set_error("dca_last_fit: null argument"); return -1; }
+    *result = t_last_fit;
+    return 0;
 }
 
 void freeFieldsAndCouplings(void *h_and_J) { free(h_and_J); }
@@ -291,6 +321,27 @@ int dca_mf_fn_apc(const double *couplings, int seqs_len, int num_site_states, do
 {
     if (!couplings || !fn_out) { set_error("dca_mf_fn_apc: null argument"); return -1; }
     return mf_fn_apc_host(couplings, seqs_len, num_site_states, fn_out, fn_apc_out);
+}
+
+int dca_mf_corr_from_freqs(const double *reg_fi, const double *reg_fij, int seqs_len, int num_site_states,
+                           double *corr_out)
+{
+    if (!reg_fi || !reg_fij || !corr_out) { set_error("dca_mf_corr_from_freqs: null argument"); return -1; }
+    return mf_corr_from_freqs_host(reg_fi, reg_fij, seqs_len, num_site_states, corr_out);
+}
+
+int dca_mf_direct_info(const double *couplings, const double *reg_fi, int seqs_len, int num_site_states,
+                       double *di_out, double *fields_out)
+{
+    if (!couplings || !reg_fi || !di_out) { set_error("dca_mf_direct_info: null argument"); return -1; }
+    return mf_di_host(couplings, reg_fi, seqs_len, num_site_states, di_out, fields_out);
+}
+
+int dca_plm_direct_info(const float *x_host, const double *reg_fi, int seqs_len, int num_site_states,
+                        double *di_out, double *fields_out)
+{
+    if (!x_host || !reg_fi || !di_out) { set_error("dca_plm_direct_info: null argument"); return -1; }
+    return plm_di_host(x_host, reg_fi, seqs_len, num_site_states, di_out, fields_out);
 }
 
 }  // extern "C"

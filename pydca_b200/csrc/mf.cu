@@ -498,6 +498,47 @@ int mf_corr_mat_host(const uint8_t *msa, const double *w, long N, int L, int q, 
     return 0;
 }
 
+// construct_corr_mat as a standalone operator on caller-supplied regularised
+// frequencies (msa_numerics.py:271-318): reg_fi [L][q], reg_fij [pairs][q-1][q-1].
+__global__ void mf_corr_from_freqs_kernel(const double *__restrict__ reg_fi, const double *__restrict__ reg_fij,
+                                          int L, int q, int n, double *__restrict__ C)
+{
+    const int qm1 = q - 1;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (col >= n) return;
+    int i = row / qm1, a = row - i * qm1, j = col / qm1, b = col - j * qm1;
+    double out;
+    if (i == j) {
+        const double fia = reg_fi[i * q + a], fib = reg_fi[i * q + b];
+        out = (a == b) ? fia * (1.0 - fia) : -1.0 * fia * fib;
+    } else {
+        if (i > j) { int t = i; i = j; j = t; t = a; a = b; b = t; }
+        out = reg_fij[(pair_index(L, i, j) * qm1 + a) * qm1 + b] - reg_fi[i * q + a] * reg_fi[j * q + b];
+    }
+    C[(size_t)row * n + col] = out;
+}
+
+int mf_corr_from_freqs_host(const double *reg_fi, const double *reg_fij, int L, int q, double *corr)
+{
+    if (require_device() != 0) return -1;
+    if (L < 2 || q < 2) { set_error("construct_corr_mat: bad shape L=%d q=%d", L, q); return -1; }
+    const int qm1 = q - 1, n = L * qm1;
+    const size_t nfij = (size_t)L * (L - 1) / 2 * qm1 * qm1;
+    double *d_fi = nullptr, *d_fij = nullptr, *d_C = nullptr;
+    DCA_CUDA(cudaMalloc(&d_fi, sizeof(double) * (size_t)L * q));
+    DCA_CUDA(cudaMalloc(&d_fij, sizeof(double) * nfij));
+    DCA_CUDA(cudaMalloc(&d_C, sizeof(double) * (size_t)n * n));
+    DCA_CUDA(cudaMemcpy(d_fi, reg_fi, sizeof(double) * (size_t)L * q, cudaMemcpyHostToDevice));
+    DCA_CUDA(cudaMemcpy(d_fij, reg_fij, sizeof(double) * nfij, cudaMemcpyHostToDevice));
+    dim3 grid(ceil_div(n, 256), n);
+    DCA_LAUNCH(mf_corr_from_freqs_kernel, grid, 256, 0, 0, d_fi, d_fij, L, q, n, d_C);
+    DCA_CUDA(cudaGetLastError());
+    DCA_CUDA(cudaMemcpy(corr, d_C, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
+    cudaFree(d_fi); cudaFree(d_fij); cudaFree(d_C);
+    return 0;
+}
+
 int mf_couplings_host(const double *corr, int n, double *out)
 {
     if (require_device() != 0) return -1;

@@ -574,23 +574,30 @@ static int plm_setup_t(PlmProblem *p)
 }
 
 template <int Q>
-static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *d_dir)
+static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *d_dir,
+                      cudaEvent_t *ev = nullptr)
 {
     cudaStream_t st = p->stream;
     const int L = p->L, ld = p->ld;
+    int evi = 0;
+#define PLM_MARK() do { if (ev) cudaEventRecord(ev[evi++], st); } while (0)
+    PLM_MARK();
     dim3 gridU(ceil_div(L, AS_JG), L);
     DCA_LAUNCH((plm_unpack_kernel<Q>), gridU, 256, 0, st, d_x, L, ld, p->d_W);
+    PLM_MARK();
 
     const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN;
     dim3 gridA(p->col_tiles, (unsigned)(p->Npad / LG_TN));
     DCA_LAUNCH((plm_logits_kernel<Q>), gridA, LG_THREADS, smemA, st,
                p->d_W, ld, p->d_msaT, p->Npad, p->N, L, d_x, p->d_S, p->col_tile0);
+    PLM_MARK();
 
     const int nsites = p->site_hi - p->site_lo;
     dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
     DCA_LAUNCH((plm_softmax_kernel<Q>), gridB, 128, 0, st,
                p->d_S, ld, p->d_msa, p->d_w, p->N, L, p->site_lo, p->site_hi,
                p->chunk, p->warm, p->carry, p->d_fxpart);
+    PLM_MARK();
 
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC;
     const size_t gstride = (size_t)p->Lq * ld;
@@ -598,12 +605,15 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
     DCA_LAUNCH((plm_scatter_kernel<Q>), gridC, SC_WARPS * 32, smemC, st,
                p->d_S, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride,
                p->chunks_per_split, p->col_tile0);
+    PLM_MARK();
 
     DCA_LAUNCH((plm_assemble_kernel<Q>), gridU, 256, 0, st,
                d_x, p->d_G, gstride, p->nsplit, L, ld, p->lh, p->lJ, p->site_lo, p->site_hi,
                d_dir, d_g, p->d_red);
     DCA_LAUNCH(plm_finalize_kernel, 1, 256, 0, st,
                p->d_red, p->red_blocks, p->d_fxpart, p->nscan, L, p->site_lo, p->site_hi, p->d_scal);
+    PLM_MARK();
+#undef PLM_MARK
     DCA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -706,6 +716,26 @@ void plm_set_carry(PlmProblem *p, int carry, int chunk, int warm)
 int plm_eval_device(PlmProblem *p, const float *d_x, float *d_g, const float *d_dir)
 {
     return (p->q == 21) ? plm_eval_t<21>(p, d_x, d_g, d_dir) : plm_eval_t<5>(p, d_x, d_g, d_dir);
+}
+
+// one evaluation with CUDA events between the kernels, on the stream they are
+// launched on: ms[0..4] = unpack, logits, softmax, scatter, assemble+finalize
+int plm_eval_timed(PlmProblem *p, const float *d_x, float *d_g, float *ms)
+{
+    cudaEvent_t ev[PLM_NUM_KERNEL_TIMES + 1];
+    for (auto &e : ev) DCA_CUDA(cudaEventCreate(&e));
+    const int rc = (p->q == 21) ? plm_eval_t<21>(p, d_x, d_g, nullptr, ev) : plm_eval_t<5>(p, d_x, d_g, nullptr, ev);
+    DCA_CUDA(cudaStreamSynchronize(p->stream));
+    for (int k = 0; k < PLM_NUM_KERNEL_TIMES; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+// static launch geometry, for the bench's roofline arithmetic
+void plm_describe(const PlmProblem *p, long *out)
+{
+    out[0] = p->N; out[1] = p->L; out[2] = p->q; out[3] = p->ld; out[4] = p->P;
+    out[5] = p->nsplit; out[6] = p->nchunk; out[7] = p->col_tiles; out[8] = p->Npad; out[9] = p->nscan;
 }
 
 int plm_read_scalars(PlmProblem *p, double *out)

@@ -108,6 +108,123 @@ static int fn_apc_impl(const SRC *h_src, size_t count, int L, int q, int is_matr
     return 0;
 }
 
+// ------------------------------------------------------------------------------
+// Direct information: two-site-model fixed point + DI per pair.
+//   compute_two_site_model_fields  pydca/meanfield_dca/msa_numerics.py:378-442
+//                                  pydca/plmdca/msa_numerics.py:156-220
+//   compute_direct_info            :446-533 / :224-311
+// One warp per pair, lane a owns state a (q <= 32); W = exp(J_ij) with the gap
+// row/column at exp(0) = 1 (slice_couplings zero-fills them, :346-374).
+constexpr int DI_WARPS = 4;
+
+template <typename SRC>
+__global__ void __launch_bounds__(DI_WARPS * 32)
+di_kernel(const SRC *__restrict__ src, const double *__restrict__ reg_fi, int L, int q, int is_matrix,
+          double *__restrict__ di, double *__restrict__ fields)
+{
+    extern __shared__ double sm[];
+    const int qm1 = q - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *Wm = sm + (size_t)warp * (q * q + 2 * q);
+    double *hi_s = Wm + q * q, *hj_s = hi_s + q;
+    const long npairs = (long)L * (L - 1) / 2;
+    const long pair = (long)blockIdx.x * DI_WARPS + warp;
+    if (pair >= npairs) return;
+    int i = 0;
+    long rem = pair;
+    while (rem >= L - 1 - i) { rem -= L - 1 - i; ++i; }
+    const int j = i + 1 + (int)rem;
+    const long n = (long)L * qm1;
+    for (int t = lane; t < q * q; t += 32) {
+        const int a = t / q, b = t - a * q;
+        double v = 0.0;
+        if (a < qm1 && b < qm1) {
+            if (is_matrix) v = (double)src[((long)i * qm1 + a) * n + (long)j * qm1 + b];
+            else v = (double)src[(long)L * q + pair * q * q + a * q + b];
+        }
+        Wm[t] = exp(v);
+    }
+    const bool on = lane < q;
+    const double fi = on ? reg_fi[i * q + lane] : 0.0;
+    const double fj = on ? reg_fi[j * q + lane] : 0.0;
+    double hi = 1.0 / (double)q, hj = 1.0 / (double)q;
+    if (on) { hi_s[lane] = hi; hj_s[lane] = hj; }
+    __syncwarp();
+    double change = 10.0;
+    while (change > 1.0e-4) {                                   // TOLERANCE, :411
+        double xi = 0.0, xj = 0.0;
+        if (on) {
+            for (int b = 0; b < q; ++b) { xi += Wm[lane * q + b] * hj_s[b]; xj += Wm[b * q + lane] * hi_s[b]; }
+        }
+        double ni = on ? fi / xi : 0.0, nj = on ? fj / xj : 0.0;
+        const double si = warp_sum(ni), sj = warp_sum(nj);
+        ni /= si; nj /= sj;
+        double c = on ? fmax(fabs(ni - hi), fabs(nj - hj)) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
+        change = c;
+        hi = ni; hj = nj;
+        __syncwarp();
+        if (on) { hi_s[lane] = hi; hj_s[lane] = hj; }
+        __syncwarp();
+    }
+    if (fields && on) {
+        fields[(pair * 2 + 0) * q + lane] = hi;
+        fields[(pair * 2 + 1) * q + lane] = hj;
+    }
+    // pdir = W * hi hj^T / sum ; DI over residue-residue entries with EPSILON 1e-20 (:499-529)
+    double z = 0.0;
+    if (on) for (int b = 0; b < q; ++b) z += Wm[lane * q + b] * hi * hj_s[b];
+    z = warp_sum(z);
+    double acc = 0.0;
+    if (lane < qm1) {
+        for (int b = 0; b < qm1; ++b) {
+            const double pd = Wm[lane * q + b] * hi * hj_s[b] / z + 1.0e-20;
+            const double ff = fi * reg_fi[j * q + b] + 1.0e-20;
+            acc += pd * log(pd / ff);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) di[pair] = acc;
+}
+
+template <typename SRC>
+static int di_impl(const SRC *h_src, size_t count, const double *h_reg_fi, int L, int q, int is_matrix,
+                   double *di, double *fields)
+{
+    if (require_device() != 0) return -1;
+    if (L < 2 || q < 2 || q > 32) { set_error("direct_info: bad shape L=%d q=%d", L, q); return -1; }
+    const long npairs = (long)L * (L - 1) / 2;
+    SRC *d_src = nullptr;
+    double *d_rfi = nullptr, *d_di = nullptr, *d_fields = nullptr;
+    DCA_CUDA(cudaMalloc(&d_src, sizeof(SRC) * count));
+    DCA_CUDA(cudaMalloc(&d_rfi, sizeof(double) * (size_t)L * q));
+    DCA_CUDA(cudaMalloc(&d_di, sizeof(double) * (size_t)npairs));
+    if (fields) DCA_CUDA(cudaMalloc(&d_fields, sizeof(double) * (size_t)npairs * 2 * q));
+    DCA_CUDA(cudaMemcpy(d_src, h_src, sizeof(SRC) * count, cudaMemcpyHostToDevice));
+    DCA_CUDA(cudaMemcpy(d_rfi, h_reg_fi, sizeof(double) * (size_t)L * q, cudaMemcpyHostToDevice));
+    const size_t smem = sizeof(double) * DI_WARPS * (size_t)(q * q + 2 * q);
+    DCA_LAUNCH((di_kernel<SRC>), (unsigned)ceil_div<long>(npairs, DI_WARPS), DI_WARPS * 32, smem, 0,
+               d_src, d_rfi, L, q, is_matrix, d_di, d_fields);
+    DCA_CUDA(cudaGetLastError());
+    DCA_CUDA(cudaMemcpy(di, d_di, sizeof(double) * (size_t)npairs, cudaMemcpyDeviceToHost));
+    if (fields) DCA_CUDA(cudaMemcpy(fields, d_fields, sizeof(double) * (size_t)npairs * 2 * q, cudaMemcpyDeviceToHost));
+    cudaFree(d_src); cudaFree(d_rfi); cudaFree(d_di); cudaFree(d_fields);
+    return 0;
+}
+
+int plm_di_host(const float *h_x, const double *h_reg_fi, int L, int q, double *di, double *fields)
+{
+    const size_t P = (size_t)L * q + (size_t)L * (L - 1) / 2 * q * q;
+    return di_impl<float>(h_x, P, h_reg_fi, L, q, 0, di, fields);
+}
+
+int mf_di_host(const double *h_J, const double *h_reg_fi, int L, int q, double *di, double *fields)
+{
+    const size_t n = (size_t)L * (q - 1);
+    return di_impl<double>(h_J, n * n, h_reg_fi, L, q, 1, di, fields);
+}
+
 int plm_fn_apc_host(const float *h_x, int L, int q, double *fn, double *fn_apc)
 {
     const size_t P = (size_t)L * q + (size_t)L * (L - 1) / 2 * q * q;

@@ -1,0 +1,295 @@
+"""PlmDCA -- the class surface of pydca/plmdca/plmdca.py:25-790 over the B200 backend.
+
+Constructor keywords, defaults, validation, properties and method names are the
+reference's; the numerics go through the same C entry point the reference binds
+(``plmdcaBackend`` / ``freeFieldsAndCouplings``, plmdca.py:79-89, :216-230), now
+exported by ``_plmdcaBackend_b200.so``.  Post-processing that the reference does
+in Python loops over P parameters (:225-227, :262-267, :461-477, :508) is array
+code here; Frobenius norms, APC and DI run on the device.
+"""
+import ctypes
+import logging
+
+import numpy as np
+
+from . import _lib, fasta_reader, msa_numerics
+
+logger = logging.getLogger(__name__)
+
+
+class PlmDCAException(Exception):
+    """Implements exceptions related to PlmDCA computation"""
+
+
+def _sorted_pairs(scores, seqs_len):
+    """[((i, j), score), ...] sorted like ``sorted(..., reverse=True)``: descending,
+    ties keep (i, j) order (plmdca.py:478)."""
+    iu, ju = np.triu_indices(seqs_len, k=1)
+    items = [((int(i), int(j)), s) for i, j, s in zip(iu, ju, scores.tolist())]
+    return sorted(items, key=lambda k: k[1], reverse=True)
+
+
+def average_product_correction(sorted_scores, seqs_len):
+    """plmdca.py:503-521 / meanfield_dca.py:969-984 on a [((i,j),score)] list."""
+    n = seqs_len
+    site_sum = np.zeros(n, dtype=np.float64)
+    for (i, j), s in sorted_scores:
+        site_sum[i] += s
+        site_sum[j] += s
+    av = site_sum / float(n - 1)
+    av_all = sum(av.tolist()) / float(n)
+    out = [(pair, score - av[pair[0]] * (av[pair[1]] / av_all)) for pair, score in sorted_scores]
+    return sorted(out, key=lambda k: k[1], reverse=True)
+
+
+class PlmDCA:
+    """Pseudolikelihood-maximisation DCA on one B200 (plmdca.py:25)."""
+
+    def __init__(self, msa_file, biomolecule, seqid=None, lambda_h=None, lambda_J=None,
+                 max_iterations=None, num_threads=None, verbose=False):
+        self.__biomolecule = biomolecule.strip().upper()
+        if self.__biomolecule not in ("PROTEIN", "RNA"):
+            logger.error("\n\tInvalid biomolecule type {}".format(self.__biomolecule))
+            raise PlmDCAException
+        self.__msa_file = msa_file
+        self.__biomolecule_int = 1 if self.__biomolecule == "PROTEIN" else 2
+        self.__num_site_states = 21 if self.__biomolecule == "PROTEIN" else 5
+        self.__num_seqs, self.__seqs_len = self._get_num_and_len_of_seqs()
+        self.__seqid = 0.8 if seqid is None else seqid
+        if self.__seqid <= 0 or self.__seqid > 1.0:
+            logger.error("\n\t{} is an invalid value of sequences identity (seqid) parameter".format(self.__seqid))
+            raise PlmDCAException
+        self.__lambda_h = 0.2 * (self.__seqs_len - 1) if lambda_h is None else lambda_h
+        if self.__lambda_h < 0:
+            logger.error("\n\tlambda_h must be a positive number. You passed lambda_h={}".format(self.__lambda_h))
+            raise PlmDCAException
+        self.__lambda_J = 0.2 * (self.__seqs_len - 1) if lambda_J is None else lambda_J
+        if self.__lambda_J < 0:
+            logger.error("\n\tlambda_J must be a positive number. You passed lambda_J={}".format(self.__lambda_J))
+            raise PlmDCAException
+        self.__max_iterations = max_iterations if max_iterations is not None else 100
+        self.__num_threads = 1 if num_threads is None else num_threads
+        self.__verbose = True if verbose else False
+        q, l = self.__num_site_states, self.__seqs_len
+        self.__data_size = l * q + l * (l - 1) // 2 * q * q
+        self.__fields_and_couplings_all = None
+        self.__refseq_mapping_dict = None
+        self.__last_fit = None
+        logger.info("Created plmDCA instance: biomolecule %s, L %d, sequences %d, seqid %s, lambda_h %s, "
+                    "lambda_J %s, iterations %d", self.__biomolecule, l, self.__num_seqs, self.__seqid,
+                    self.__lambda_h, self.__lambda_J, self.__max_iterations)
+
+    # ---- properties (plmdca.py:107-160) -------------------------------------------
+    @property
+    def biomolecule(self):
+        return self.__biomolecule
+
+    @property
+    def sequence_identity(self):
+        return self.__seqid
+
+    @property
+    def lambda_h(self):
+        return self.__lambda_h
+
+    @property
+    def lambda_J(self):
+        return self.__lambda_J
+
+    @property
+    def max_iterations(self):
+        return self.__max_iterations
+
+    @property
+    def sequences_len(self):
+        return self.__seqs_len
+
+    @property
+    def num_sequences(self):
+        return self.__num_seqs
+
+    @property
+    def effective_num_sequences(self):
+        raise NotImplementedError
+
+    @property
+    def last_fit(self):
+        """L-BFGS status / iteration / evaluation counts of the last backend call
+        (the reference discards them, plmdcaBackend.cpp:197)."""
+        return self.__last_fit
+
+    def _get_num_and_len_of_seqs(self):
+        """(records in the file, length of record 0), plmdca.py:163-180."""
+        return fasta_reader.first_record_length(self.__msa_file)
+
+    def map_index_couplings(self, i, j, a, b):
+        """plmdca.py:183-199."""
+        q, l = self.__num_site_states, self.__seqs_len
+        site = ((l * (l - 1)) // 2 - ((l - i) * (l - i - 1)) // 2 + j - i - 1) * q * q
+        return l * q + site + b + a * q
+
+    # ---- backend call (plmdca.py:202-243) -------------------------------------------
+    def get_fields_and_couplings_from_backend(self):
+        """float32[P]: fields then couplings, through the reference's C ABI."""
+        logger.info("\n\tComputing fields and couplings using gradient decent")
+        lib = _lib.lib()
+        h_j_ptr = lib.plmdcaBackend(
+            self.__biomolecule_int, self.__num_site_states, self.__msa_file.encode("utf-8"),
+            self.__seqs_len, self.__seqid, self.__lambda_h, self.__lambda_J, self.__max_iterations,
+            self.__num_threads, self.__verbose)
+        if not h_j_ptr:
+            logger.error("\n\tplmDCA backend failed: %s", _lib.last_error())
+            raise PlmDCAException(_lib.last_error())
+        view = np.ctypeslib.as_array(ctypes.cast(h_j_ptr, ctypes.POINTER(ctypes.c_float)),
+                                     shape=(self.__data_size,))
+        fields_and_couplings = np.array(view, dtype=np.float32, copy=True)
+        lib.freeFieldsAndCouplings(h_j_ptr)
+        self.__last_fit = _lib.last_fit()
+        return fields_and_couplings
+
+    # ---- gap-state stripping (plmdca.py:246-318) -----------------------------------------
+    def get_couplings_no_gap_state(self, fields_and_couplings_all):
+        q, l = self.__num_site_states, self.__seqs_len
+        x = np.asarray(fields_and_couplings_all)
+        blocks = x[l * q:].reshape(l * (l - 1) // 2, q, q)[:, :q - 1, :q - 1]
+        return np.ascontiguousarray(blocks).reshape(-1)
+
+    def get_fields_no_gap_state(self, fields_and_couplings_all):
+        q, l = self.__num_site_states, self.__seqs_len
+        x = np.asarray(fields_and_couplings_all)
+        return x[:l * q].reshape(l, q)[:, :q - 1].reshape(-1).tolist()
+
+    def get_fields_and_couplings_no_gap_state(self, fields_and_couplings_all):
+        return (self.get_fields_no_gap_state(fields_and_couplings_all),
+                self.get_couplings_no_gap_state(fields_and_couplings_all))
+
+    def shift_couplings(self, couplings_ij):
+        """plmdca.py:320-342."""
+        qm1 = self.__num_site_states - 1
+        c = np.reshape(couplings_ij, (qm1, qm1))
+        return c - np.mean(c, axis=1).reshape(qm1, 1) - np.mean(c, axis=0).reshape(1, qm1) + np.mean(c)
+
+    # ---- scores ---------------------------------------------------------------------------
+    def _fit_if_needed(self, refit=True):
+        if refit or self.__fields_and_couplings_all is None:
+            self.__fields_and_couplings_all = self.get_fields_and_couplings_from_backend()
+        return self.__fields_and_couplings_all
+
+    def compute_sorted_FN(self, seqbackmapper=None):
+        """plmdca.py:437-481."""
+        x = self._fit_if_needed()
+        logger.info("\n\tComputing non-APC sorted DCA score")
+        fn, _ = _lib.plm_fn_apc(x, self.__seqs_len, self.__num_site_states)
+        scores = _sorted_pairs(fn, self.__seqs_len)
+        if seqbackmapper is not None:
+            scores = self.get_mapped_site_pairs_dca_scores(scores, seqbackmapper)
+        return scores
+
+    def compute_sorted_FN_APC(self, seqbackmapper=None):
+        """plmdca.py:484-524."""
+        scores_plmdca = self.compute_sorted_FN()
+        logger.info("\n\tPerforming average product correction (APC) of FN  of DCA scores")
+        sorted_fn_apc = average_product_correction(scores_plmdca, self.__seqs_len)
+        if seqbackmapper is not None:
+            sorted_fn_apc = self.get_mapped_site_pairs_dca_scores(sorted_fn_apc, seqbackmapper)
+        return sorted_fn_apc
+
+    def get_mapped_site_pairs_dca_scores(self, sorted_dca_scores, seqbackmapper):
+        """plmdca.py:527-562 (seqbackmapper: any object with map_to_reference_sequence())."""
+        mapping_dict = seqbackmapper.map_to_reference_sequence()
+        self.__refseq_mapping_dict = mapping_dict
+        mapped = [((mapping_dict[p[0]], mapping_dict[p[1]]), s) for p, s in sorted_dca_scores
+                  if p[0] in mapping_dict and p[1] in mapping_dict]
+        mapped = sorted(mapped, key=lambda k: k[1], reverse=True)
+        logger.info("\n\tTotal number of mapped sites: {}".format(len(mapped)))
+        return tuple(mapped)
+
+    # ---- DI path (plmdca.py:565-790) ------------------------------------------------------
+    def _alignment(self):
+        return fasta_reader.get_alignment_zero_based(self.__msa_file, self.__biomolecule)
+
+    def compute_seqs_weight(self):
+        """float64 weights recomputed as the reference does for DI (plmdca.py:565-591)."""
+        counts = _lib.sequence_counts(self._alignment(), self.__seqid, compare_f64=True)
+        seqs_weight = 1.0 / counts.astype(np.float64)
+        self.__seqs_weight = seqs_weight
+        self.__eff_num_seqs = np.sum(seqs_weight)
+        return seqs_weight
+
+    def get_single_site_freqs(self):
+        msa = self._alignment()
+        w = 1.0 / _lib.sequence_counts(msa, self.__seqid, compare_f64=True).astype(np.float64)
+        return msa_numerics.compute_single_site_freqs(alignment_data=msa.astype(np.int64) + 1,
+                                                      num_site_states=self.__num_site_states, seqs_weight=w)
+
+    def get_reg_single_site_freqs(self):
+        """pseudocount 0.5 is hard-coded by the reference for plmDCA DI (plmdca.py:647)."""
+        fi = self.get_single_site_freqs()
+        return msa_numerics.get_reg_single_site_freqs(single_site_freqs=fi, seqs_len=self.__seqs_len,
+                                                      num_site_states=self.__num_site_states, pseudocount=0.5)
+
+    def compute_two_site_model_fields(self, couplings=None):
+        reg_fi = self.get_reg_single_site_freqs()
+        x = self._fit_if_needed(refit=False)
+        return msa_numerics.plm_direct_info(x, reg_fi, self.__seqs_len, self.__num_site_states,
+                                            want_fields=True)[1]
+
+    def compute_direct_info_unsorted_DI(self):
+        """plmdca.py:683-720."""
+        x = self._fit_if_needed()
+        reg_fi = self.get_reg_single_site_freqs()
+        logger.info("\n\tComputing direct information")
+        return msa_numerics.plm_direct_info(x, reg_fi, self.__seqs_len, self.__num_site_states)
+
+    def compute_sorted_DI(self, seqbackmapper=None):
+        di = self.compute_direct_info_unsorted_DI()
+        sorted_di = _sorted_pairs(di, self.__seqs_len)
+        if seqbackmapper is not None:
+            sorted_di = self.get_mapped_site_pairs_dca_scores(sorted_di, seqbackmapper)
+        return sorted_di
+
+    def compute_sorted_DI_APC(self, seqbackmapper=None):
+        sorted_di = self.compute_sorted_DI()
+        logger.info("\n\tPerforming average product correction (APC) of DI scores")
+        out = average_product_correction(sorted_di, self.__seqs_len)
+        if seqbackmapper is not None:
+            out = self.get_mapped_site_pairs_dca_scores(out, seqbackmapper)
+        return out
+
+    # ---- compute_params (plmdca.py:345-434) ----------------------------------------------------
+    def compute_params(self, seqbackmapper=None, ranked_by=None, linear_dist=None, num_site_pairs=None):
+        ranked_by = "FN_APC" if ranked_by is None else ranked_by.strip().upper()
+        linear_dist = 4 if linear_dist is None else linear_dist
+        methods = {"FN": self.compute_sorted_FN, "FN_APC": self.compute_sorted_FN_APC,
+                   "DI": self.compute_sorted_DI, "DI_APC": self.compute_sorted_DI_APC}
+        if ranked_by not in methods:
+            logger.error("\n\tInvalid ranking criterion {}.\nChoose from {}".format(ranked_by, tuple(methods)))
+            raise PlmDCAException
+        dca_scores = methods[ranked_by](seqbackmapper=seqbackmapper)
+        x = self.__fields_and_couplings_all
+        q, l = self.__num_site_states, self.__seqs_len
+        qm1 = q - 1
+        fields = np.asarray(self.get_fields_no_gap_state(x))
+        couplings = self.get_couplings_no_gap_state(x).reshape(-1, qm1 * qm1)
+        if seqbackmapper is not None:
+            mapping = {v: k for k, v in self.__refseq_mapping_dict.items()}
+        else:
+            mapping = {i: i for i in range(l)}
+        if num_site_pairs is None:
+            num_site_pairs = len(seqbackmapper.ref_sequence) if seqbackmapper is not None else len(mapping)
+        fields_mapped = [(i, fields[qm1 * mapping[i]: qm1 * mapping[i] + qm1]) for i in mapping]
+        ranked, count = [], 0
+        for pair, _ in dca_scores:
+            if abs(pair[0] - pair[1]) > linear_dist:
+                count += 1
+                if count > num_site_pairs:
+                    break
+                i, j = mapping[pair[0]], mapping[pair[1]]
+                if i > j:
+                    logger.error("\n\tInvalid site pair. Site pair (i, j) should be ordered in i < j")
+                    raise PlmDCAException
+                k = (l * (l - 1)) // 2 - ((l - i) * (l - i - 1)) // 2 + j - i - 1
+                ranked.append((pair, self.shift_couplings(couplings[k]).reshape(qm1 * qm1)))
+        if count < num_site_pairs:
+            logger.warning("\n\tObtained couplings for only {} ranked site pairs.".format(count))
+        return tuple(fields_mapped), tuple(ranked)

@@ -1,0 +1,84 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in pydca_b200/distributed.py:
+shard arithmetic, the row-sharded reweighting collective, and the site-sharded
+objective decomposition + all-reduce that the NCCL path performs per evaluation.
+The per-shard numbers come from the CPU oracle (no CUDA here)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_range_partitions():
+    from pydca_b200.distributed import shard_range
+    for total in (1, 7, 8, 150, 500, 5000):
+        for world in (1, 2, 3, 4, 8):
+            parts = [shard_range(total, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == total
+            assert all(parts[k][1] == parts[k + 1][0] for k in range(world - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from pydca_b200.distributed import allgather_counts, shard_range
+    from pydca_b200.synthetic import synthetic_msa
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = oracle.port()
+    P.set_num_threads(2)
+    N, L, q = 240, 14, 21
+    msa = synthetic_msa(N, L, q, seed=21)
+
+    # row-sharded reweighting: local rows against all rows, then one collective
+    lo, hi = shard_range(N, rank, world)
+    full = P.reweight_counts(msa, 0.8)
+    local = np.zeros(N, dtype=np.uint32)
+    local[lo:hi] = full[lo:hi]           # what dca_weights(rows=(lo,hi)) returns on the GPU path
+    got = allgather_counts(local, (lo, hi), N)
+    assert (got == full).all()
+
+    # site-sharded objective: each rank's data term, all-reduce, regulariser added once
+    w = P.plm_weights(full)
+    lam = 0.2 * (L - 1)
+    rng = np.random.default_rng(4)
+    x = (P.plm_init(msa, w, q) + rng.normal(0, 0.1, L * q + L * (L - 1) // 2 * q * q)).astype(np.float32)
+    f_reg, g_reg = P.plm_gradient(msa, w, q, lam, lam, x, sites=(0, 0))
+    slo, shi = shard_range(L, rank, world)
+    f_loc, g_loc = P.plm_gradient(msa, w, q, lam, lam, x, sites=(slo, shi))
+    g = torch.from_numpy((g_loc.astype(np.float64) - g_reg).copy())
+    s = torch.tensor([f_loc - f_reg], dtype=torch.float64)
+    dist.all_reduce(g)
+    dist.all_reduce(s)
+    f_full, g_full = P.plm_gradient_f64(msa, w, q, lam, lam, x)
+    g_tot = g.numpy() + g_reg
+    f_tot = float(s[0]) + f_reg
+    assert np.abs(g_tot - g_full).max() <= 1e-5 * np.abs(g_full).max()
+    assert abs(f_tot - f_full) <= 5e-5 * abs(f_full)
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+
+
+def test_gloo_world2_collectives(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()

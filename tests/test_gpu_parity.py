@@ -1,0 +1,343 @@
+"""GPU parity tests (-m gpu): every CUDA entry point, called through the C ABI
+(pydca_b200/_lib.py -> include/dca_b200.h), against the CPU oracle on the same seeded
+inputs, against the golden outputs of the unmodified reference, and -- at the
+BASELINE sizes -- through size-independent properties.
+
+Tolerances (north_star): integer counts and pair indices bit-exact; objective,
+gradient and FN/DI scores within 1e-5 relative.  Gradient error is measured in the
+infinity norm relative to max|g|.  The objective is compared with the
+float64 oracle: the reference accumulates fx in float32 and is itself ~1e-5 off."""
+import numpy as np
+import pytest
+
+from conftest import relmax
+from oracle import mf_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def lib():
+    from pydca_b200 import _lib
+    return _lib
+
+
+# ---- reweighting: bit-exact integers ------------------------------------------------
+@pytest.mark.parametrize("N,L,q,seqid", [(1, 7, 5, 0.8), (2, 3, 21, 0.5), (63, 5, 5, 0.8), (130, 129, 21, 0.8),
+                                         (300, 150, 21, 0.8), (257, 515, 21, 0.7), (1000, 64, 5, 0.9),
+                                         (200, 33, 21, 1.0), (200, 33, 21, 0.01)])
+def test_reweight_counts_exact(port, N, L, q, seqid):
+    from pydca_b200.synthetic import synthetic_msa
+    msa = synthetic_msa(N, L, q, seed=N + L, unique=False)[:N]
+    for f64 in (False, True):
+        got = lib().sequence_counts(msa, seqid, compare_f64=f64)
+        want = port.reweight_counts(msa, seqid, f64=f64)
+        assert got.dtype == np.uint32 and (got == want).all()
+
+
+def test_reweight_threshold_edges(port):
+    """ident/L exactly at the threshold: strict '>' in float32 vs float64 can differ."""
+    rng = np.random.default_rng(5)
+    L = 10
+    base = rng.integers(0, 20, size=L, dtype=np.uint8)
+    rows = [base.copy() for _ in range(12)]
+    for k, r in enumerate(rows):
+        r[:k % (L + 1)] = (r[:k % (L + 1)] + 1) % 20          # k mismatches -> ident = L-k
+    msa = np.stack(rows)
+    for seqid in (0.8, 0.7, 0.3, 0.1, 0.9):
+        for f64 in (False, True):
+            assert (lib().sequence_counts(msa, seqid, compare_f64=f64) ==
+                    port.reweight_counts(msa, seqid, f64=f64)).all()
+
+
+def test_reweight_golden_rf00167(golden):
+    d = golden("rf00167_full.npz")
+    c = lib().sequence_counts(d["msa"], 0.8)
+    assert (c == d["counts"]).all() and int(c.sum()) == 7188
+    assert (1.0 / c.astype(np.float32) == d["w_f32"]).all()
+
+
+def test_reweight_row_shards_compose(port):
+    from pydca_b200.synthetic import synthetic_msa
+    msa = synthetic_msa(700, 60, 21, seed=11)
+    full = lib().sequence_counts(msa, 0.8)
+    a = lib().sequence_counts(msa, 0.8, rows=(0, 301))
+    b = lib().sequence_counts(msa, 0.8, rows=(301, 700))
+    assert (a[:301] == full[:301]).all() and (b[301:] == full[301:]).all()
+    assert (a[301:] == 0).all() and (b[:301] == 0).all()
+
+
+def test_reweight_symmetry_property_large():
+    """Full-size property (BASELINE config 2 shape): sum_i c_i counts every similar
+    ordered pair once, so it is N + 2 * #{i<j similar}: parity of (sum - N) is even;
+    c_i >= 1; duplicate-free input => c is invariant under row permutation."""
+    from pydca_b200.synthetic import synthetic_msa
+    msa = synthetic_msa(5000, 150, 21)
+    c = lib().sequence_counts(msa, 0.8)
+    assert c.min() >= 1 and (int(c.sum()) - 5000) % 2 == 0
+    perm = np.random.default_rng(0).permutation(5000)
+    assert (lib().sequence_counts(msa[perm], 0.8) == c[perm]).all()
+    assert abs(float((1.0 / c).sum()) - 3489.3) < 0.1          # SURVEY 8d calibration
+
+
+# ---- plmDCA objective / gradient -------------------------------------------------------
+@pytest.mark.parametrize("name", ["plm_toy_rna.npz", "plm_toy_protein.npz", "plm_mid_protein.npz"])
+def test_plm_eval_vs_reference_golden(golden, port, name):
+    d = golden(name)
+    msa, q = d["msa"], int(d["q"])
+    lh, lj = float(d["lambda_h"]), float(d["lambda_J"])
+    obj = lib().PlmObjective(msa, d["w"], q, lh, lj)
+    x0 = obj.init()
+    assert np.abs(x0 - d["x0"]).max() <= 1e-6 * max(1.0, np.abs(d["x0"]).max())
+    for tag in ("0", "1"):
+        fx, g = obj.eval(d["x" + tag])
+        f64, g64 = port.plm_gradient_f64(msa, d["w"], q, lh, lj, d["x" + tag])
+        assert abs(fx - f64) <= 1e-5 * abs(f64)
+        assert abs(fx - float(d["fx" + tag])) <= 1e-4 * abs(f64)      # float32-accumulated reference fx
+        assert relmax(g, d["g" + tag]) <= 1e-5                          # vs the reference's C++ gradient
+        assert relmax(g, g64) <= 1e-5
+    obj.close()
+
+
+@pytest.mark.parametrize("N,L,q", [(1, 4, 5), (3, 2, 21), (33, 9, 5), (257, 17, 21), (640, 37, 21), (129, 130, 5)])
+def test_plm_eval_vs_oracle_shapes(port, N, L, q):
+    """Ragged shapes: N not a multiple of the 256/128/32 tiles, L below one site tile,
+    L*q not a multiple of 128, single-sequence alignments."""
+    from pydca_b200.synthetic import synthetic_msa
+    msa = synthetic_msa(N, L, q, seed=3 * N + L)
+    w = port.plm_weights(port.reweight_counts(msa, 0.8))
+    lam = 0.2 * (L - 1)
+    obj = lib().PlmObjective(msa, w, q, lam, lam)
+    rng = np.random.default_rng(N)
+    x = (obj.init() + rng.normal(0, 0.2, obj.P)).astype(np.float32)
+    fx, g = obj.eval(x)
+    fo, go = port.plm_gradient(msa, w, q, lam, lam, x)
+    f64, g64 = port.plm_gradient_f64(msa, w, q, lam, lam, x)
+    assert abs(fx - f64) <= 1e-5 * abs(f64)
+    assert relmax(g, go) <= 1e-5 and relmax(g, g64) <= 1e-5
+    obj.close()
+
+
+def test_plm_eval_carry_modes_and_scan_parameters(golden, port):
+    """carry=False is textbook plmDCA; with carry the result must not depend on how
+    the chain is chunked (chunk/warm-up), i.e. the warm-up really reproduces the
+    reference's serial loop-carried state."""
+    d = golden("plm_mid_protein.npz")
+    msa, q = d["msa"], int(d["q"])
+    lh, lj = float(d["lambda_h"]), float(d["lambda_J"])
+    obj = lib().PlmObjective(msa, d["w"], q, lh, lj)
+    fx_ref, g_ref = obj.eval(d["x1"])
+    for chunk, warm in ((8, 32), (64, 32), (1000, 0), (32, 24)):
+        obj.set_carry(True, chunk, warm)
+        fx, g = obj.eval(d["x1"])
+        assert abs(fx - fx_ref) <= 1e-6 * abs(fx_ref) and relmax(g, g_ref) <= 2e-6
+    obj.set_carry(False)
+    fx, g = obj.eval(d["x1"])
+    fo, go = port.plm_gradient(msa, d["w"], q, lh, lj, d["x1"], carry=False)
+    assert abs(fx - fo) <= 1e-4 * abs(fo) and relmax(g, go) <= 1e-5
+    assert relmax(g, g_ref) > 1e-3            # the quirk is material (SURVEY finding 1)
+    obj.close()
+
+
+def test_plm_eval_site_shards_sum_to_full(port):
+    """Multi-GPU decomposition on one device: two site shards add up to the objective."""
+    from pydca_b200.synthetic import synthetic_msa
+    N, L, q = 400, 26, 21
+    msa = synthetic_msa(N, L, q, seed=9)
+    w = port.plm_weights(port.reweight_counts(msa, 0.8))
+    lam = 5.0
+    rng = np.random.default_rng(1)
+    full = lib().PlmObjective(msa, w, q, lam, lam)
+    x = (full.init() + rng.normal(0, 0.1, full.P)).astype(np.float32)
+    fx, g = full.eval(x)
+    parts = [lib().PlmObjective(msa, w, q, lam, lam, sites=s) for s in ((0, 11), (11, 26))]
+    res = [p.eval(x) for p in parts]
+    assert abs(sum(r[0] for r in res) - fx) <= 1e-6 * abs(fx)
+    assert relmax(sum(r[1].astype(np.float64) for r in res), g) <= 1e-6
+    for p in parts + [full]:
+        p.close()
+
+
+def test_plm_eval_linearity_property_config2():
+    """BASELINE config 2 size (N=5000, L=150, q=21): the data term's gradient rows sum
+    to zero over states (sum_a dh_i(a) = 2*lambda*sum_a h_i(a) since sum_a (p - delta) = 0),
+    and the objective at the initial point equals sum_n w_n * (mean log-loss) > 0."""
+    from pydca_b200.synthetic import synthetic_msa
+    N, L, q = 5000, 150, 21
+    msa = synthetic_msa(N, L, q)
+    c = lib().sequence_counts(msa, 0.8)
+    w = (1.0 / c.astype(np.float32)).astype(np.float32)
+    lam = 0.2 * (L - 1)
+    obj = lib().PlmObjective(msa, w, q, lam, lam)
+    x = obj.init()
+    fx, g = obj.eval(x)
+    gh = g[:L * q].reshape(L, q).astype(np.float64)
+    h = x[:L * q].reshape(L, q).astype(np.float64)
+    assert np.abs(gh.sum(axis=1) - 2 * lam * h.sum(axis=1)).max() <= 1e-3 * np.abs(gh).max()
+    gj = g[L * q:].reshape(-1, q, q).astype(np.float64)
+    # every J block gets two data terms, each summing to zero over one index
+    assert abs(gj.sum()) <= 1e-4 * np.abs(gj).sum()
+    assert np.isfinite(fx) and fx > 0
+    fx2, g2 = obj.eval(x)
+    assert fx2 == fx and (g2 == g).all()          # deterministic: fixed reduction order
+    obj.close()
+
+
+# ---- L-BFGS ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["plm_toy_rna.npz", "plm_toy_protein.npz"])
+def test_plm_fit_matches_reference_fit(golden, port, name):
+    """End to end vs the reference's own lbfgs at num_threads=1: same objective value
+    reached (both stop on the float32 line search, status -1001 or -997) and FN scores
+    inside the reference's own noise band (SURVEY finding 3: up to 3e-2 relative)."""
+    d = golden(name)
+    msa, q = d["msa"], int(d["q"])
+    L = msa.shape[1]
+    lh, lj = float(d["lambda_h"]), float(d["lambda_J"])
+    obj = lib().PlmObjective(msa, d["w"], q, lh, lj)
+    x, res = obj.fit(obj.init(), int(d["fit_iters"]))
+    assert res.status in (0, -997, -1001) and res.evaluations >= res.iterations
+    f_gpu, _ = port.plm_gradient_f64(msa, d["w"], q, lh, lj, x)
+    f_ref, _ = port.plm_gradient_f64(msa, d["w"], q, lh, lj, d["x_fit_nt1"])
+    assert abs(f_gpu - f_ref) <= 2e-3 * abs(f_ref)
+    fn, apc = lib().plm_fn_apc(x, L, q)
+    fn_ref = mf_oracle.plm_fn_scores(d["x_fit_nt1"], L, q)
+    assert relmax(fn, fn_ref) <= 3e-2
+    obj.close()
+
+
+def test_plmdca_backend_drop_in(tmp_path, golden, port):
+    """The reference's own C entry point, bound with the reference's argtypes."""
+    from pydca_b200.synthetic import write_fasta
+    d = golden("plm_toy_protein.npz")
+    msa, q = d["msa"], int(d["q"])
+    L = msa.shape[1]
+    path = write_fasta(msa, str(tmp_path / "toy.fa"), q)
+    x = lib().plmdca_backend(path, "protein", L, q, 0.8, float(d["lambda_h"]), float(d["lambda_J"]), 20)
+    assert x.dtype == np.float32 and x.shape == (L * q + L * (L - 1) // 2 * q * q,)
+    stats = lib().last_fit()
+    assert stats.evaluations > 0 and stats.status in (0, -997, -1001)
+    f_gpu, _ = port.plm_gradient_f64(msa, d["w"], q, float(d["lambda_h"]), float(d["lambda_J"]), x)
+    f_ref, _ = port.plm_gradient_f64(msa, d["w"], q, float(d["lambda_h"]), float(d["lambda_J"]), d["x_fit_nt1"])
+    assert abs(f_gpu - f_ref) <= 2e-3 * abs(f_ref)
+    # error behaviour: unreadable file -> NULL -> exception, not an abort
+    with pytest.raises(lib().DcaBackendError):
+        lib().plmdca_backend(str(tmp_path / "nope.fa"), "protein", L, q, 0.8, 1.0, 1.0, 5)
+
+
+# ---- scoring ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["plm_toy_rna.npz", "plm_toy_protein.npz"])
+def test_plm_scoring_vs_reference(golden, name):
+    from pydca_b200 import msa_numerics
+    d = golden(name)
+    msa, q = d["msa"], int(d["q"])
+    L = msa.shape[1]
+    fn, apc = lib().plm_fn_apc(d["x1"], L, q)
+    assert relmax(fn, d["x1_fn"]) <= 1e-6
+    order = np.argsort(-apc, kind="stable")
+    iu, ju = np.triu_indices(L, k=1)
+    got_pairs = np.stack([iu[order], ju[order]], axis=1)
+    assert (got_pairs == d["x1_fn_apc_sorted_pairs"]).all()                 # bit-exact pair indices
+    assert relmax(apc[order], d["x1_fn_apc_sorted_scores"]) <= 1e-6
+    xs = d["x1"] * np.float32(0.05)
+    di, fields = msa_numerics.plm_direct_info(xs, d["x1s_reg_fi"], L, q, want_fields=True)
+    assert relmax(fields, d["x1s_two_site_fields"]) <= 1e-9
+    assert relmax(di, d["x1s_di"]) <= 1e-9
+
+
+# ---- mean-field DCA --------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,q", [("mf_toy_rna.npz", 5), ("mf_toy_protein.npz", 21)])
+def test_mf_operators_vs_reference(golden, name, q):
+    from pydca_b200 import msa_numerics as mfn
+    d = golden(name)
+    msa = d["msa"]
+    L = msa.shape[1]
+    data = msa.astype(np.int32) + 1
+    w = mfn.compute_sequences_weight(alignment_data=data, seqid=0.8)
+    assert (w == d["w"]).all()
+    fi = mfn.compute_single_site_freqs(alignment_data=data, num_site_states=q, seqs_weight=w)
+    assert relmax(fi, d["fi"]) <= 1e-13
+    fij = mfn.compute_pair_site_freqs(alignment_data=data, num_site_states=q, seqs_weight=w)
+    assert fij.shape == d["fij"].shape and relmax(fij, d["fij"]) <= 1e-13
+    rfi = mfn.get_reg_single_site_freqs(single_site_freqs=fi, seqs_len=L, num_site_states=q, pseudocount=0.5)
+    rfij = mfn.get_reg_pair_site_freqs(pair_site_freqs=fij, seqs_len=L, num_site_states=q, pseudocount=0.5)
+    assert relmax(rfi, d["reg_fi"]) <= 1e-13
+    corr = mfn.construct_corr_mat(reg_fi=rfi, reg_fij=rfij, seqs_len=L, num_site_states=q)
+    assert relmax(corr, d["corr"]) <= 1e-12 and (corr == corr.T).all()
+    rfi2, corr2 = mfn.corr_mat_from_alignment(msa, q, w, 0.5)                # fused path
+    assert relmax(corr2, d["corr"]) <= 1e-12 and relmax(rfi2, d["reg_fi"]) <= 1e-13
+    J = mfn.compute_couplings(corr_mat=corr)
+    assert relmax(J, d["couplings"]) <= 1e-9
+    fn, apc = mfn.frobenius_norm_scores(J, L, q)
+    assert relmax(fn, d["fn"]) <= 1e-9
+    order = np.argsort(-apc, kind="stable")
+    iu, ju = np.triu_indices(L, k=1)
+    assert (np.stack([iu[order], ju[order]], axis=1) == d["fn_apc_sorted_pairs"]).all()
+    assert relmax(apc[order], d["fn_apc_sorted_scores"]) <= 1e-9
+    fields = mfn.compute_two_site_model_fields(couplings=J, reg_fi=rfi, seqs_len=L, num_site_states=q)
+    assert relmax(fields, d["two_site_fields"]) <= 1e-8
+    di = mfn.compute_direct_info(couplings=J, fields_ij=fields, reg_fi=rfi, seqs_len=L, num_site_states=q)
+    assert relmax(di, d["di"]) <= 1e-8
+
+
+def test_mf_class_known_answers(tmp_path, golden):
+    """MeanFieldDCA end to end on the reference's own inputs: notebook top-5 (K1) and
+    the full RF00167 ranking (K5), <= 1e-5 relative and identical order."""
+    from pydca_b200 import MeanFieldDCA
+    from pydca_b200.synthetic import write_fasta
+    from test_oracle_golden import NOTEBOOK_MF
+    d = golden("rf00167_trimmed.npz")
+    path = write_fasta(d["msa"], str(tmp_path / "trim.fa"), 5)
+    inst = MeanFieldDCA(path, "rna", pseudocount=0.5, seqid=0.8)
+    assert inst.num_sequences == 2448 and abs(inst.effective_num_sequences - 461.115584101248) < 1e-9
+    ranked = inst.compute_sorted_FN_APC()
+    for k, (pair, score) in enumerate(NOTEBOOK_MF):
+        assert ranked[k][0] == pair and abs(ranked[k][1] - score) <= 1e-5 * score
+    assert [list(p) for p, _ in ranked] == d["mf_fn_apc_sorted_pairs"].tolist()
+    assert relmax([s for _, s in ranked], d["mf_fn_apc_sorted_scores"]) <= 1e-9
+    full = golden("rf00167_full.npz")
+    inst2 = MeanFieldDCA(write_fasta(full["msa"], str(tmp_path / "full.fa"), 5), "rna")
+    di = inst2.compute_sorted_DI()
+    want = mf_oracle.sorted_pairs(full["mf_di"], 102)
+    assert [p for p, _ in di[:200]] == [p for p, _ in want[:200]]
+    assert relmax([s for _, s in di], [s for _, s in want]) <= 1e-8
+
+
+def test_mf_inverse_property_config3_size():
+    """Dense SPD inverse at a padded, non-multiple-of-128 size: A * inv(A) = I."""
+    from pydca_b200 import msa_numerics as mfn
+    rng = np.random.default_rng(2)
+    n = 1000
+    B = rng.normal(size=(n, n))
+    A = B @ B.T / n + np.eye(n)
+    J = mfn.compute_couplings(corr_mat=A)
+    assert np.abs(A @ (-J) - np.eye(n)).max() <= 1e-10
+    with pytest.raises(lib().DcaBackendError, match="singular"):
+        mfn.compute_couplings(corr_mat=np.zeros((4, 4)))
+
+
+def test_mf_singular_and_ragged_inputs():
+    from pydca_b200 import msa_numerics as mfn
+    with pytest.raises(ValueError):
+        mfn.compute_sequences_weight(alignment_data=np.zeros((0, 5), dtype=np.int32), seqid=0.8)
+    with pytest.raises(ValueError):
+        mfn.compute_single_site_freqs(alignment_data=np.full((3, 4), 22), num_site_states=21,
+                                      seqs_weight=np.ones(3))
+    one = np.ones((1, 6), dtype=np.int32)
+    assert mfn.compute_sequences_weight(alignment_data=one, seqid=0.8).tolist() == [1.0]
+
+
+def test_plm_class_end_to_end(tmp_path, golden):
+    """PlmDCA class through plmdcaBackend: K2 ranking on the notebook input."""
+    from pydca_b200 import PlmDCA
+    from pydca_b200.synthetic import write_fasta
+    from test_oracle_golden import NOTEBOOK_PLM
+    d = golden("rf00167_trimmed.npz")
+    path = write_fasta(d["msa"], str(tmp_path / "trim.fa"), 5)
+    inst = PlmDCA(path, "rna", seqid=0.8, lambda_h=1.0, lambda_J=20.0, max_iterations=500)
+    ranked = inst.compute_sorted_FN_APC()
+    assert [p for p, _ in ranked[:5]] == [p for p, _ in NOTEBOOK_PLM]
+    for k, (pair, score) in enumerate(NOTEBOOK_PLM):
+        assert abs(ranked[k][1] - score) <= 3e-2 * score        # reference self-noise band
+    assert inst.last_fit.evaluations > 0
+    top = [p for p, _ in ranked[:71]]
+    ref_top = [tuple(p) for p in d["plm_fn_apc_sorted_pairs"][:71].tolist()]
+    assert len(set(top) & set(ref_top)) >= 60                     # top-L overlap vs reference nt=1
