@@ -36,94 +36,39 @@ constexpr int LB_M = 5;
 // device scalar block (floats): [0..4] alpha_j, [5..9] ys_j, [10] coef, [11] scale
 enum { SC_ALPHA = 0, SC_YS = 5, SC_COEF = 10, SC_SCALE = 11, SC_FLOATS = 16 };
 
-// x = xp + stp * d with separate multiply and add (arithmetic_ansi.h:71-88:
-// veccpy then vecadd, no fused multiply-add on the reference's x86 target)
-__global__ void __launch_bounds__(VEC_THREADS)
-vec_step_kernel(float *__restrict__ x, const float *__restrict__ xp, const float *__restrict__ d,
-                float stp, long n)
+// Every kernel below streams P floats as float4 (the vectors come from cudaMalloc,
+// 256-byte aligned; the <= 3 trailing elements are handled by one CTA), and the
+// kernels that produce a dot product finish it themselves: each CTA writes its
+// float64 partial, takes a ticket, and the LAST CTA reduces the partials in a
+// fixed order and applies the scalar step of the recursion (no separate
+// reduction launch, no host round trip, deterministic).
+//
+// scalar steps (op):
+//   0: ys_slot = y.s ; scale = ys / yy                  (lbfgs.cpp:556-558, :591)
+//   1: alpha_slot = (s.d) / ys_slot ; coef = -alpha      (:585-588)
+//   2: beta = (y.d) / ys_slot ; coef = alpha_slot - beta (:596-599)
+//   3: dscal[PS_DG] = g.d                                (:845, line search)
+//   4: dscal[PS_DG] = g.d, dscal[PS_GG] = g.g            (multi-GPU, after the all-reduce)
+//  -1: none
+__device__ __forceinline__ void finish_dot(double r0, double r1, double *__restrict__ partial,
+                                           int op, int slot, float *__restrict__ sc,
+                                           double *__restrict__ dscal, unsigned *__restrict__ ticket,
+                                           double *scratch)
 {
-    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x)
-        x[k] = __fadd_rn(xp[k], __fmul_rn(stp, d[k]));
-}
-
-// s = x - xp ; y = g - gp ; partial {y.s, y.y}      (lbfgs.cpp:546-557)
-__global__ void __launch_bounds__(VEC_THREADS)
-vec_update_sy_kernel(float *__restrict__ s, float *__restrict__ y, const float *__restrict__ x,
-                     const float *__restrict__ xp, const float *__restrict__ g,
-                     const float *__restrict__ gp, long n, double *__restrict__ partial)
-{
-    __shared__ double scratch[32];
-    double ys = 0.0, yy = 0.0;
-    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) {
-        const float sv = x[k] - xp[k];
-        const float yv = g[k] - gp[k];
-        s[k] = sv; y[k] = yv;
-        ys += (double)yv * sv;
-        yy += (double)yv * yv;
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = r0;
+        partial[2 * blockIdx.x + 1] = r1;
+        __threadfence();
+        last = (atomicInc(ticket, gridDim.x - 1u) == gridDim.x - 1u);
     }
-    double r = block_sum(ys, scratch); if (threadIdx.x == 0) partial[2 * blockIdx.x] = r;
-    r = block_sum(yy, scratch);        if (threadIdx.x == 0) partial[2 * blockIdx.x + 1] = r;
-}
-
-// one fused pass of the two-loop recursion (lbfgs.cpp:568-601):
-//   mode 0: d = -g                       (vecncpy :575)
-//   mode 1: d += coef * u                (vecadd  :588 / :599), coef from device
-//   mode 2: d *= scale                   (vecscale :591), scale from device
-// followed, when v != null, by the partial dot v.d of the UPDATED d, which is
-// what the next step of the recursion needs (:585 / :596), or g.d for the
-// line search (:845).
-__global__ void __launch_bounds__(VEC_THREADS)
-vec_twoloop_kernel(float *__restrict__ d, const float *__restrict__ u, const float *__restrict__ v,
-                   const float *__restrict__ sc, int mode, long n, double *__restrict__ partial)
-{
-    __shared__ double scratch[32];
-    const float c = (mode == 1) ? sc[SC_COEF] : ((mode == 2) ? sc[SC_SCALE] : 0.f);
-    double dot = 0.0;
-    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) {
-        float dv;
-        if (mode == 0) dv = -u[k];
-        else if (mode == 1) dv = __fadd_rn(d[k], __fmul_rn(c, u[k]));
-        else dv = __fmul_rn(d[k], c);
-        d[k] = dv;
-        if (v) dot += (double)v[k] * dv;
-    }
-    if (v) {
-        const double r = block_sum(dot, scratch);
-        if (threadIdx.x == 0) partial[blockIdx.x] = r;
-    }
-}
-
-// plain partial dots {a.b, a.a} (multi-GPU path: g.d and g.g after the all-reduce)
-__global__ void __launch_bounds__(VEC_THREADS)
-vec_dots_kernel(const float *__restrict__ a, const float *__restrict__ b, long n,
-                double *__restrict__ partial)
-{
-    __shared__ double scratch[32];
-    double ab = 0.0, aa = 0.0;
-    for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long)gridDim.x * blockDim.x) {
-        const float av = a[k];
-        if (b) ab += (double)av * b[k];
-        aa += (double)av * av;
-    }
-    double r = block_sum(ab, scratch); if (threadIdx.x == 0) partial[2 * blockIdx.x] = r;
-    r = block_sum(aa, scratch);        if (threadIdx.x == 0) partial[2 * blockIdx.x + 1] = r;
-}
-
-// single CTA: reduce the partials in a fixed order and apply the scalar step.
-//   op 0: ys_slot = y.s ; scale = ys / yy                  (:556-558, :591)
-//   op 1: alpha_slot = (s.d) / ys_slot ; coef = -alpha      (:585-588)
-//   op 2: beta = (y.d) / ys_slot ; coef = alpha_slot - beta (:596-599)
-//   op 3: dscal[1] = sum (g.d for the line search)
-//   op 4: dscal[1] = sum0 (g.d), dscal[2] = sum1 (g.g)
-__global__ void __launch_bounds__(256)
-scalar_step_kernel(const double *__restrict__ partial, int nb, int stride, int op, int slot,
-                   float *__restrict__ sc, double *__restrict__ dscal)
-{
-    __shared__ double scratch[32];
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
     double s0 = 0.0, s1 = 0.0;
-    for (int b = threadIdx.x; b < nb; b += 256) {
-        s0 += partial[(size_t)stride * b];
-        if (stride == 2) s1 += partial[2 * (size_t)b + 1];
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        s0 += partial[2 * b];
+        s1 += partial[2 * b + 1];
     }
     s0 = block_sum(s0, scratch);
     s1 = block_sum(s1, scratch);
@@ -141,10 +86,133 @@ scalar_step_kernel(const double *__restrict__ partial, int nb, int stride, int o
         sc[SC_COEF] = sc[SC_ALPHA + slot] - beta;
     } else if (op == 3) {
         dscal[PS_DG] = s0;
-    } else {
+    } else if (op == 4) {
         dscal[PS_DG] = s0;
         dscal[PS_GG] = s1;
     }
+}
+
+#define VEC_LOOP4(n)                                                                              \
+    const long n4__ = (n) >> 2;                                                                   \
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < n4__; v += (long)gridDim.x * blockDim.x)
+#define VEC_TAIL(n, k)                                                                            \
+    const long k = ((n) & ~3L) + threadIdx.x;                                                     \
+    if (blockIdx.x == gridDim.x - 1 && k < (n))
+
+// x = xp + stp * d with separate multiply and add (arithmetic_ansi.h:71-88:
+// veccpy then vecadd, no fused multiply-add on the reference's x86 target)
+__global__ void __launch_bounds__(VEC_THREADS)
+vec_step_kernel(float *__restrict__ x, const float *__restrict__ xp, const float *__restrict__ d,
+                float stp, long n)
+{
+    VEC_LOOP4(n) {
+        const float4 a = reinterpret_cast<const float4 *>(xp)[v], b = reinterpret_cast<const float4 *>(d)[v];
+        float4 o;
+        o.x = __fadd_rn(a.x, __fmul_rn(stp, b.x)); o.y = __fadd_rn(a.y, __fmul_rn(stp, b.y));
+        o.z = __fadd_rn(a.z, __fmul_rn(stp, b.z)); o.w = __fadd_rn(a.w, __fmul_rn(stp, b.w));
+        reinterpret_cast<float4 *>(x)[v] = o;
+    }
+    VEC_TAIL(n, k) x[k] = __fadd_rn(xp[k], __fmul_rn(stp, d[k]));
+}
+
+// s = x - xp ; y = g - gp ; {y.s, y.y} -> op 0      (lbfgs.cpp:546-558)
+__global__ void __launch_bounds__(VEC_THREADS)
+vec_update_sy_kernel(float *__restrict__ s, float *__restrict__ y, const float *__restrict__ x,
+                     const float *__restrict__ xp, const float *__restrict__ g,
+                     const float *__restrict__ gp, long n, double *__restrict__ partial, int slot,
+                     float *__restrict__ sc, double *__restrict__ dscal, unsigned *__restrict__ ticket)
+{
+    __shared__ double scratch[32];
+    double ys = 0.0, yy = 0.0;
+    VEC_LOOP4(n) {
+        const float4 a = reinterpret_cast<const float4 *>(x)[v], b = reinterpret_cast<const float4 *>(xp)[v];
+        const float4 c = reinterpret_cast<const float4 *>(g)[v], e = reinterpret_cast<const float4 *>(gp)[v];
+        const float4 sv = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+        const float4 yv = make_float4(c.x - e.x, c.y - e.y, c.z - e.z, c.w - e.w);
+        reinterpret_cast<float4 *>(s)[v] = sv;
+        reinterpret_cast<float4 *>(y)[v] = yv;
+        ys += (double)yv.x * sv.x + (double)yv.y * sv.y + (double)yv.z * sv.z + (double)yv.w * sv.w;
+        yy += (double)yv.x * yv.x + (double)yv.y * yv.y + (double)yv.z * yv.z + (double)yv.w * yv.w;
+    }
+    VEC_TAIL(n, k) {
+        const float sv = x[k] - xp[k], yv = g[k] - gp[k];
+        s[k] = sv; y[k] = yv;
+        ys += (double)yv * sv; yy += (double)yv * yv;
+    }
+    const double r0 = block_sum(ys, scratch), r1 = block_sum(yy, scratch);
+    finish_dot(r0, r1, partial, 0, slot, sc, dscal, ticket, scratch);
+}
+
+// one fused pass of the two-loop recursion (lbfgs.cpp:568-601):
+//   mode 0: d = -u                       (vecncpy :575)
+//   mode 1: d += coef * u                (vecadd  :588 / :599), coef from device
+//   mode 2: d *= scale                   (vecscale :591), scale from device
+// followed, when v != null, by the dot v.d of the UPDATED d -- what the next
+// step of the recursion needs (:585 / :596), or g.d for the line search (:845)
+// -- finished by the last CTA with scalar step `op`.
+__global__ void __launch_bounds__(VEC_THREADS)
+vec_twoloop_kernel(float *__restrict__ d, const float *__restrict__ u, const float *__restrict__ vv,
+                   float *__restrict__ sc, int mode, long n, double *__restrict__ partial,
+                   int op, int slot, double *__restrict__ dscal, unsigned *__restrict__ ticket)
+{
+    __shared__ double scratch[32];
+    const float c = (mode == 1) ? sc[SC_COEF] : ((mode == 2) ? sc[SC_SCALE] : 0.f);
+    double dot = 0.0;
+    VEC_LOOP4(n) {
+        float4 dv;
+        if (mode == 0) {
+            const float4 a = reinterpret_cast<const float4 *>(u)[v];
+            dv = make_float4(-a.x, -a.y, -a.z, -a.w);
+        } else if (mode == 1) {
+            const float4 a = reinterpret_cast<const float4 *>(u)[v], o = reinterpret_cast<const float4 *>(d)[v];
+            dv.x = __fadd_rn(o.x, __fmul_rn(c, a.x)); dv.y = __fadd_rn(o.y, __fmul_rn(c, a.y));
+            dv.z = __fadd_rn(o.z, __fmul_rn(c, a.z)); dv.w = __fadd_rn(o.w, __fmul_rn(c, a.w));
+        } else {
+            const float4 o = reinterpret_cast<const float4 *>(d)[v];
+            dv = make_float4(__fmul_rn(o.x, c), __fmul_rn(o.y, c), __fmul_rn(o.z, c), __fmul_rn(o.w, c));
+        }
+        reinterpret_cast<float4 *>(d)[v] = dv;
+        if (vv) {
+            const float4 w = reinterpret_cast<const float4 *>(vv)[v];
+            dot += (double)w.x * dv.x + (double)w.y * dv.y + (double)w.z * dv.z + (double)w.w * dv.w;
+        }
+    }
+    VEC_TAIL(n, k) {
+        float dv;
+        if (mode == 0) dv = -u[k];
+        else if (mode == 1) dv = __fadd_rn(d[k], __fmul_rn(c, u[k]));
+        else dv = __fmul_rn(d[k], c);
+        d[k] = dv;
+        if (vv) dot += (double)vv[k] * dv;
+    }
+    if (vv) {
+        const double r0 = block_sum(dot, scratch);
+        finish_dot(r0, 0.0, partial, op, slot, sc, dscal, ticket, scratch);
+    }
+}
+
+// {a.b, a.a} -> op 4 (multi-GPU path: g.d and g.g after the all-reduce)
+__global__ void __launch_bounds__(VEC_THREADS)
+vec_dots_kernel(const float *__restrict__ a, const float *__restrict__ b, long n,
+                double *__restrict__ partial, float *__restrict__ sc, double *__restrict__ dscal,
+                unsigned *__restrict__ ticket)
+{
+    __shared__ double scratch[32];
+    double ab = 0.0, aa = 0.0;
+    VEC_LOOP4(n) {
+        const float4 p = reinterpret_cast<const float4 *>(a)[v];
+        aa += (double)p.x * p.x + (double)p.y * p.y + (double)p.z * p.z + (double)p.w * p.w;
+        if (b) {
+            const float4 q = reinterpret_cast<const float4 *>(b)[v];
+            ab += (double)p.x * q.x + (double)p.y * q.y + (double)p.z * q.z + (double)p.w * q.w;
+        }
+    }
+    VEC_TAIL(n, k) {
+        aa += (double)a[k] * a[k];
+        if (b) ab += (double)a[k] * b[k];
+    }
+    const double r0 = block_sum(ab, scratch), r1 = block_sum(aa, scratch);
+    finish_dot(r0, r1, partial, 4, 0, sc, dscal, ticket, scratch);
 }
 
 // libLBFGS status codes (lbfgs.h:78-150; the enum counts up from -1024)
@@ -269,6 +337,7 @@ struct Driver {
     float *s[LB_M] = {nullptr}, *y[LB_M] = {nullptr};
     float *sc = nullptr;
     double *partial = nullptr;
+    unsigned *ticket = nullptr;
     allreduce_fn_t allreduce = nullptr;
     void *ctx = nullptr;
     int evals = 0;
@@ -284,6 +353,8 @@ struct Driver {
         DCA_CUDA(cudaMalloc(&sc, sizeof(float) * SC_FLOATS));
         DCA_CUDA(cudaMemsetAsync(sc, 0, sizeof(float) * SC_FLOATS, st));
         DCA_CUDA(cudaMalloc(&partial, sizeof(double) * 2 * (size_t)blocks));
+        DCA_CUDA(cudaMalloc(&ticket, sizeof(unsigned)));
+        DCA_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
         return 0;
     }
     void release(float *keep_x)
@@ -291,7 +362,7 @@ struct Driver {
         float *v[] = {x, xp, g, gp, d};
         for (float *q : v) if (q && q != keep_x) cudaFree(q);
         for (int i = 0; i < LB_M; ++i) { cudaFree(s[i]); cudaFree(y[i]); }
-        cudaFree(sc); cudaFree(partial);
+        cudaFree(sc); cudaFree(partial); cudaFree(ticket);
     }
 
     // objective at x -> g ; returns {fx, g.d, g.g, x.x} on the host
@@ -308,8 +379,7 @@ struct Driver {
             set_error("lbfgs: all-reduce callback failed");
             return -1;
         }
-        DCA_LAUNCH(vec_dots_kernel, blocks, VEC_THREADS, 0, st, g, dir, n, partial);
-        DCA_LAUNCH(scalar_step_kernel, 1, 256, 0, st, partial, blocks, 2, 4, 0, sc, plm_scalar_buffer(p));
+        DCA_LAUNCH(vec_dots_kernel, blocks, VEC_THREADS, 0, st, g, dir, n, partial, sc, plm_scalar_buffer(p), ticket);
         return plm_read_scalars(p, h);
     }
 };
@@ -328,6 +398,7 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
     if (D.alloc() != 0) { D.release(d_x); return -1; }
     cudaStream_t st = D.st;
     const long n = D.n;
+    double *dsc = plm_scalar_buffer(p);
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evw = nullptr;
     cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&evw);
@@ -346,7 +417,8 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
 
     LB_CHECK(D.evaluate(nullptr, h));                                    // lbfgs.cpp:415
     fx = (float)h[PS_FX];
-    DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.g, (const float *)nullptr, D.sc, 0, n, D.partial);
+    DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.g, (const float *)nullptr, D.sc, 0, n,
+               D.partial, -1, 0, dsc, D.ticket);
     xnorm = (float)std::sqrt(h[PS_XX]);
     gnorm = (float)std::sqrt(h[PS_GG]);
     if (xnorm < 1.0f) xnorm = 1.0f;
@@ -438,34 +510,34 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
 
         // ---- history update + two-loop recursion, all on the device (:546-601) ----
         DCA_LAUNCH(vec_update_sy_kernel, D.blocks, VEC_THREADS, 0, st,
-                   D.s[end], D.y[end], D.x, D.xp, D.g, D.gp, n, D.partial);
-        DCA_LAUNCH(scalar_step_kernel, 1, 256, 0, st, D.partial, D.blocks, 2, 0, end, D.sc, plm_scalar_buffer(p));
+                   D.s[end], D.y[end], D.x, D.xp, D.g, D.gp, n, D.partial, end, D.sc, dsc, D.ticket);
         {
             const int bound = (LB_M <= k) ? LB_M : k;
             ++k;
             end = (end + 1) % LB_M;
-            int j = end;
-            // d = -g fused with the first s_j . d
-            int jn = (j + LB_M - 1) % LB_M;
-            DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.g, D.s[jn], D.sc, 0, n, D.partial);
+            int j = (end + LB_M - 1) % LB_M;
+            // d = -g fused with s_j . d -> alpha_j                       (:575, :585)
+            DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.g, D.s[j], D.sc, 0, n,
+                       D.partial, 1, j, dsc, D.ticket);
             for (int i = 0; i < bound; ++i) {
-                j = (j + LB_M - 1) % LB_M;
-                DCA_LAUNCH(scalar_step_kernel, 1, 256, 0, st, D.partial, D.blocks, 1, 1, j, D.sc, plm_scalar_buffer(p));
-                // d -= alpha_j y_j, then dot with the next s (or nothing on the last level)
-                const float *nextv = (i + 1 < bound) ? D.s[(j + LB_M - 1) % LB_M] : nullptr;
-                DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.y[j], nextv, D.sc, 1, n, D.partial);
+                // d -= alpha_j y_j, fused with the next level's s . d, or nothing on the oldest level
+                const int jn = (j + LB_M - 1) % LB_M;
+                const bool more = (i + 1 < bound);
+                DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.y[j],
+                           more ? D.s[jn] : (const float *)nullptr, D.sc, 1, n, D.partial, 1, jn, dsc, D.ticket);
+                if (more) j = jn;
             }
-            // d *= ys/yy, fused with y_j . d of the oldest level
-            DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, (const float *)nullptr, D.y[j], D.sc, 2, n, D.partial);
+            // d *= ys/yy, fused with y_j . d of the oldest level -> beta    (:591, :596)
+            DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, (const float *)nullptr, D.y[j], D.sc, 2, n,
+                       D.partial, 2, j, dsc, D.ticket);
             for (int i = 0; i < bound; ++i) {
-                DCA_LAUNCH(scalar_step_kernel, 1, 256, 0, st, D.partial, D.blocks, 1, 2, j, D.sc, plm_scalar_buffer(p));
-                const int jnext = (j + 1) % LB_M;
-                // d += (alpha_j - beta) s_j, then dot with the next y, or with g for the line search
-                const float *nextv = (i + 1 < bound) ? D.y[jnext] : D.g;
-                DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.s[j], nextv, D.sc, 1, n, D.partial);
-                j = jnext;
+                // d += (alpha_j - beta) s_j, fused with the next y . d, or with g . d for the line search
+                const int jn = (j + 1) % LB_M;
+                const bool more = (i + 1 < bound);
+                DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.s[j],
+                           more ? D.y[jn] : D.g, D.sc, 1, n, D.partial, more ? 2 : 3, jn, dsc, D.ticket);
+                j = jn;
             }
-            DCA_LAUNCH(scalar_step_kernel, 1, 256, 0, st, D.partial, D.blocks, 1, 3, 0, D.sc, plm_scalar_buffer(p));
         }
         {   // g.d of the new direction (needed by the line search, :845)
             double hh[PS_COUNT];

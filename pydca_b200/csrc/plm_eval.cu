@@ -48,16 +48,22 @@
 namespace dca {
 
 // ------------------------------------------------------------------------------
-constexpr int LG_TN = 256;        // sequences per logits CTA
+constexpr int LG_TN = 128;        // sequences per logits CTA (8 warps x 16)
 constexpr int LG_TC = 128;        // columns per CTA (32 lanes x float4)
-constexpr int LG_THREADS = 512;
+constexpr int LG_THREADS = 256;   // 2 CTAs per SM
 template <int Q> struct LgCfg { static constexpr int JB = (Q > 8) ? 4 : 16; };   // sites per stage
 
 constexpr int SC_CH = 128;        // sequences per scatter chunk
 constexpr int SC_TC = 128;
 constexpr int SC_WARPS = 16;      // one site per warp
-constexpr int PERM_CNT = 32;      // bytes reserved for bucket counts
-constexpr int PERM_REC = 224;     // bytes per (site, chunk) record (14 x 16 B)
+// perm record of one (site, chunk): 32 bytes of bucket sizes (u8[q]) followed by
+// the chunk's rows as u32 BYTE OFFSETS into the staged residual tile
+// (row * SC_TC * 4), grouped by residue; every bucket starts on a 16-byte
+// boundary (padded to a multiple of 4 entries) so that a warp walks the record
+// with one 16-byte broadcast load per 4 rows.
+constexpr int PERM_CNT = 32;
+constexpr int PERM_ENTRIES = SC_CH + 3 * 21 + 9;      // 200: worst-case padding + one prefetched quad
+constexpr int PERM_REC = PERM_CNT + 4 * PERM_ENTRIES; // 832 bytes (52 x 16 B)
 
 constexpr int AS_JG = 8;          // sites j per assemble / unpack CTA
 
@@ -74,7 +80,8 @@ struct PlmProblem {
     float h_meff = 0.f;
     int nsplit = 1, chunks_per_split = 0, nchunk = 0;
     long nscan = 0;          // number of scan chunks
-    int red_blocks = 0;
+    int red_blocks = 0, n_active = 0;
+    unsigned *d_ticket = nullptr;
     int col_tile0 = 0, col_tiles = 0;
 };
 
@@ -122,7 +129,7 @@ __global__ void build_perm_kernel(const uint8_t *__restrict__ msaT, long N, long
 #pragma unroll
         for (int b = 0; b < Q; ++b)
             if (v == b) { where = pos[b]; pos[b] = where + 1; }
-        rec[PERM_CNT + where] = (uint8_t)r;
+        reinterpret_cast<uint32_t *>(rec + PERM_CNT)[where] = (uint32_t)r * (SC_TC * 4);
     }
 }
 
@@ -163,7 +170,7 @@ plm_unpack_kernel(const float *__restrict__ x, int L, int ld, float *__restrict_
 // ------------------------------------------------------------------------------
 // logits: S[n][col] = h[col] + sum_j W[j*Q + s_nj][col]
 template <int Q>
-__global__ void __launch_bounds__(LG_THREADS, 1)
+__global__ void __launch_bounds__(LG_THREADS, 2)
 plm_logits_kernel(const float *__restrict__ W, int ld, const uint8_t *__restrict__ msaT, long Npad,
                   long N, int L, const float *__restrict__ x, float *__restrict__ S, int col_tile0)
 {
@@ -199,8 +206,9 @@ plm_logits_kernel(const float *__restrict__ W, int ld, const uint8_t *__restrict
         }
         const int nj = min(JB, L - j0);
         uint8_t *dstM = Mt + (size_t)buf * JB * LG_TN;
-        for (int t = tid; t < nj * 16; t += LG_THREADS) {
-            const int jj = t >> 4, seg = t & 15;
+        constexpr int SEGS = LG_TN / 16;
+        for (int t = tid; t < nj * SEGS; t += LG_THREADS) {
+            const int jj = t / SEGS, seg = t - jj * SEGS;
             cp_async16(dstM + jj * LG_TN + seg * 16, msaT + (size_t)(j0 + jj) * Npad + n0 + seg * 16);
         }
         cp_async_commit();
@@ -315,7 +323,8 @@ plm_softmax_kernel(float *__restrict__ S, int ld, const uint8_t *__restrict__ ms
         }
         __syncwarp();
     }
-    if (active) fxpart[k * L + site] = fx;
+    fx = warp_sum(active ? fx : 0.0);
+    if (lane == 0) fxpart[k * gridDim.x + blockIdx.x] = fx;
 }
 
 // ------------------------------------------------------------------------------
@@ -351,9 +360,10 @@ plm_scatter_kernel(const float *__restrict__ R, int ld, const uint8_t *__restric
             const int row = t >> 5, c4 = t & 31;
             cp_async16(dst + row * SC_TC + 4 * c4, src + (size_t)row * ld + 4 * c4);
         }
-        if (j < L && lane < PERM_REC / 16)
-            cp_async16(recs + ((size_t)buf * SC_WARPS + warp) * PERM_REC + 16 * lane,
-                       perm + ((size_t)j * nchunk + c) * PERM_REC + 16 * lane);
+        if (j < L)
+            for (int s = lane; s < PERM_REC / 16; s += 32)
+                cp_async16(recs + ((size_t)buf * SC_WARPS + warp) * PERM_REC + 16 * s,
+                           perm + ((size_t)j * nchunk + c) * PERM_REC + 16 * s);
         cp_async_commit();
     };
 
@@ -365,33 +375,42 @@ plm_scatter_kernel(const float *__restrict__ R, int ld, const uint8_t *__restric
         __syncthreads();
         if (j < L) {
             const uint8_t *rec = recs + ((size_t)buf * SC_WARPS + warp) * PERM_REC;
-            const uint32_t *pw = reinterpret_cast<const uint32_t *>(rec + PERM_CNT);
-            const float *Rb = Rs + (size_t)buf * SC_CH * SC_TC + 4 * lane;
+            const uint4 *qp = reinterpret_cast<const uint4 *>(rec + PERM_CNT);
+            const char *Rb = reinterpret_cast<const char *>(Rs + (size_t)buf * SC_CH * SC_TC + 4 * lane);
+            // bucket sizes: 32 bytes, broadcast once per chunk
+            const uint4 h0 = *reinterpret_cast<const uint4 *>(rec);
+            const uint4 h1 = *reinterpret_cast<const uint4 *>(rec + 16);
+            const unsigned hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            uint4 cur = qp[0];               // the quad stream is contiguous across buckets:
+            int pos = 0;                     // always keep the next quad in flight
+#define SC_ROW(off) (*reinterpret_cast<const float4 *>(Rb + (off)))
 #pragma unroll
             for (int b = 0; b < Q; ++b) {
-                const int m = rec[b];
+                const unsigned m = (hw[b >> 2] >> (8 * (b & 3))) & 0xffu;
                 float4 a = acc[b];
-                for (int k = 0; k < m; k += 4) {
-                    const uint32_t w4 = *pw++;
-                    {
-                        const float4 v = *reinterpret_cast<const float4 *>(Rb + (w4 & 0xffu) * SC_TC);
-                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-                    }
-                    if (k + 1 < m) {
-                        const float4 v = *reinterpret_cast<const float4 *>(Rb + ((w4 >> 8) & 0xffu) * SC_TC);
-                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-                    }
-                    if (k + 2 < m) {
-                        const float4 v = *reinterpret_cast<const float4 *>(Rb + ((w4 >> 16) & 0xffu) * SC_TC);
-                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-                    }
-                    if (k + 3 < m) {
-                        const float4 v = *reinterpret_cast<const float4 *>(Rb + (w4 >> 24) * SC_TC);
-                        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-                    }
+                const unsigned nq = (m + 3u) >> 2;
+                for (unsigned t = 1; t < nq; ++t) {            // full quads
+                    const uint4 o = cur;
+                    cur = qp[++pos];
+                    const float4 v0 = SC_ROW(o.x), v1 = SC_ROW(o.y), v2 = SC_ROW(o.z), v3 = SC_ROW(o.w);
+                    a.x += (v0.x + v1.x) + (v2.x + v3.x);
+                    a.y += (v0.y + v1.y) + (v2.y + v3.y);
+                    a.z += (v0.z + v1.z) + (v2.z + v3.z);
+                    a.w += (v0.w + v1.w) + (v2.w + v3.w);
+                }
+                if (m != 0u) {                                  // last quad of the bucket: 1..4 rows
+                    const uint4 o = cur;
+                    cur = qp[++pos];
+                    const unsigned rem = m - 4u * (nq - 1u);
+                    float4 s = SC_ROW(o.x);
+                    if (rem > 1u) { const float4 v = SC_ROW(o.y); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+                    if (rem > 2u) { const float4 v = SC_ROW(o.z); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+                    if (rem > 3u) { const float4 v = SC_ROW(o.w); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+                    a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
                 }
                 acc[b] = a;
             }
+#undef SC_ROW
         }
         __syncthreads();
     }
@@ -404,24 +423,33 @@ plm_scatter_kernel(const float *__restrict__ R, int ld, const uint8_t *__restric
 
 // ------------------------------------------------------------------------------
 // assemble: g = 2*lambda*x + G^T-part + G-part in the reference's layout, plus
-// the reductions every L-BFGS step needs, in one pass over x:
-//   red[block] = { lambda*x^2 (owned entries), g.d, g.g, x.x }
+// the reductions every L-BFGS step needs, in one pass over x, and -- in the
+// last CTA to finish (ticket counter, fixed summation order) -- the final
+//   scal = { fx = reg + sum fxpart, g.d, g.g, x.x }.
 // "owned" (multi-GPU site shards): fields and blocks whose first site i is in
 // [site_lo,site_hi) carry the regulariser; the column-(i,a) data term needs i
 // in the shard, the column-(j,b) term needs j in the shard.
+// red is SoA: red[c * nblk + blk]; slots of CTAs that own no pair stay zero.
 template <int Q>
 __global__ void __launch_bounds__(256)
 plm_assemble_kernel(const float *__restrict__ x, const float *__restrict__ G, size_t g_split_stride,
                     int nsplit, int L, int ld, float lh, float lJ, int site_lo, int site_hi,
-                    const float *__restrict__ d, float *__restrict__ g, double *__restrict__ red)
+                    const float *__restrict__ d, float *__restrict__ g, double *__restrict__ red,
+                    const double *__restrict__ fxpart, int nfx, unsigned *__restrict__ ticket,
+                    unsigned n_active, double *__restrict__ scal)
 {
     constexpr int QQ = Q * Q;
-    __shared__ float tile[AS_JG][QQ];
-    __shared__ double scratch[32];
+    __shared__ float tile[AS_JG * QQ];
+    __shared__ double wsum[8][4];
+    __shared__ bool is_last;
     const int i = blockIdx.y;
     const int j0 = blockIdx.x * AS_JG;
+    const bool any = (j0 + AS_JG - 1 > i);
+    if (!any && blockIdx.x != 0) return;               // owns neither a pair nor the fields
     const long Lq = (long)L * Q;
     const bool own_i = (i >= site_lo && i < site_hi);
+    const int jlo = max(j0, i + 1), jhi = min(j0 + AS_JG, L);      // pairs (i, j), jlo <= j < jhi
+    const int npair = max(0, jhi - jlo);
     double s_reg = 0.0, s_dg = 0.0, s_gg = 0.0, s_xx = 0.0;
 
     if (blockIdx.x == 0 && threadIdx.x < Q) {          // fields of site i
@@ -445,76 +473,85 @@ plm_assemble_kernel(const float *__restrict__ x, const float *__restrict__ G, si
         s_gg += (double)gv * gv;
     }
 
-    const bool any = (j0 + AS_JG - 1 > i);
-    if (any) {
-        // transposed part U[a][b] = G[(j,b)][(i,a)] : read with a fastest, park in smem
-        for (int jj = 0; jj < AS_JG; ++jj) {
-            const int j = j0 + jj;
-            if (j <= i || j >= L) continue;
-            for (int t = threadIdx.x; t < QQ; t += 256) {
-                const int b = t / Q, a = t - b * Q;
-                float u = 0.f;
-                if (own_i)
-                    for (int s = 0; s < nsplit; ++s)
-                        u += G[(size_t)s * g_split_stride + ((long)j * Q + b) * ld + i * Q + a];
-                tile[jj][a * Q + b] = u;
-            }
-        }
+    // transposed part U[a][b] = G[(j,b)][(i,a)]: read with a fastest, park in smem
+    for (int t = threadIdx.x; t < npair * QQ; t += 256) {
+        const int jj = t / QQ, e = t - jj * QQ;
+        const int b = e / Q, a = e - b * Q;
+        const int j = jlo + jj;
+        float u = 0.f;
+        if (own_i)
+            for (int s = 0; s < nsplit; ++s)
+                u += G[(size_t)s * g_split_stride + ((long)j * Q + b) * ld + i * Q + a];
+        tile[jj * QQ + a * Q + b] = u;
     }
     __syncthreads();
-    if (any) {
-        for (int jj = 0; jj < AS_JG; ++jj) {
-            const int j = j0 + jj;
-            if (j <= i || j >= L) continue;
-            const bool own_j = (j >= site_lo && j < site_hi);
-            const long base = Lq + pair_index(L, i, j) * QQ;
-            for (int t = threadIdx.x; t < QQ; t += 256) {
-                const int a = t / Q, b = t - a * Q;
-                const float xv = x[base + t];
-                float gv = own_i ? 2.f * lJ * xv : 0.f;
-                gv += tile[jj][t];
-                if (own_j) {
-                    float v = 0.f;
-                    for (int s = 0; s < nsplit; ++s)
-                        v += G[(size_t)s * g_split_stride + ((long)i * Q + a) * ld + j * Q + b];
-                    gv += v;
-                }
-                g[base + t] = gv;
-                if (own_i) { s_reg += (double)lJ * xv * xv; s_xx += (double)xv * xv; }
-                if (d) s_dg += (double)gv * d[base + t];
-                s_gg += (double)gv * gv;
-            }
+    // pairs (i, jlo..jhi-1) are consecutive blocks of x: one contiguous run
+    const long base = Lq + pair_index(L, i, jlo) * QQ;
+    for (int t = threadIdx.x; t < npair * QQ; t += 256) {
+        const int jj = t / QQ, e = t - jj * QQ;
+        const int a = e / Q, b = e - a * Q;
+        const int j = jlo + jj;
+        const float xv = x[base + t];
+        float gv = own_i ? 2.f * lJ * xv : 0.f;
+        gv += tile[t];
+        if (j >= site_lo && j < site_hi) {
+            float v = 0.f;
+            for (int s = 0; s < nsplit; ++s)
+                v += G[(size_t)s * g_split_stride + ((long)i * Q + a) * ld + j * Q + b];
+            gv += v;
         }
+        g[base + t] = gv;
+        if (own_i) { s_reg += (double)lJ * xv * xv; s_xx += (double)xv * xv; }
+        if (d) s_dg += (double)gv * d[base + t];
+        s_gg += (double)gv * gv;
     }
-    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
-    double r;
-    r = block_sum(s_reg, scratch); if (threadIdx.x == 0) red[4 * (size_t)blk + 0] = r;
-    r = block_sum(s_dg, scratch);  if (threadIdx.x == 0) red[4 * (size_t)blk + 1] = r;
-    r = block_sum(s_gg, scratch);  if (threadIdx.x == 0) red[4 * (size_t)blk + 2] = r;
-    r = block_sum(s_xx, scratch);  if (threadIdx.x == 0) red[4 * (size_t)blk + 3] = r;
-}
 
-// single CTA, fixed order: scal = { fx, g.d, g.g, x.x }
-__global__ void __launch_bounds__(256)
-plm_finalize_kernel(const double *__restrict__ red, int nred, const double *__restrict__ fxpart,
-                    long nscan, int L, int site_lo, int site_hi, double *__restrict__ scal)
-{
-    __shared__ double scratch[32];
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int b = threadIdx.x; b < nred; b += 256) {
+    // one fused block reduction of the four sums
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    s_reg = warp_sum(s_reg); s_dg = warp_sum(s_dg); s_gg = warp_sum(s_gg); s_xx = warp_sum(s_xx);
+    if (lane == 0) { wsum[wid][0] = s_reg; wsum[wid][1] = s_dg; wsum[wid][2] = s_gg; wsum[wid][3] = s_xx; }
+    __syncthreads();
+    const int nblk = gridDim.x * gridDim.y;
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x < 4) {
+        double r = 0.0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) s[c] += red[4 * (size_t)b + c];
+        for (int w = 0; w < 8; ++w) r += wsum[w][threadIdx.x];
+        red[(size_t)threadIdx.x * nblk + blk] = r;
+        __threadfence();
     }
-    const int ns = site_hi - site_lo;
-    for (long t = threadIdx.x; t < nscan * ns; t += 256) {
-        const long k = t / ns;
-        const int site = site_lo + (int)(t - k * ns);
-        s[0] += fxpart[k * L + site];
-    }
-#pragma unroll
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicInc(ticket, n_active - 1u) == n_active - 1u);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last CTA: everything is visible; reduce in a fixed order (4 independent loads in flight)
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int c = 0; c < 4; ++c) {
-        const double r = block_sum(s[c], scratch);
-        if (threadIdx.x == 0) scal[c] = r;
+        const double *rc = red + (size_t)c * nblk;
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        int t = threadIdx.x;
+        for (; t + 768 < nblk; t += 1024) { p0 += rc[t]; p1 += rc[t + 256]; p2 += rc[t + 512]; p3 += rc[t + 768]; }
+        for (; t < nblk; t += 256) p0 += rc[t];
+        acc[c] = (p0 + p1) + (p2 + p3);
+    }
+    {
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        int t = threadIdx.x;
+        for (; t + 768 < nfx; t += 1024) { p0 += fxpart[t]; p1 += fxpart[t + 256]; p2 += fxpart[t + 512]; p3 += fxpart[t + 768]; }
+        for (; t < nfx; t += 256) p0 += fxpart[t];
+        acc[0] += (p0 + p1) + (p2 + p3);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = warp_sum(acc[c]);
+    __syncthreads();
+    if (lane == 0) { wsum[wid][0] = acc[0]; wsum[wid][1] = acc[1]; wsum[wid][2] = acc[2]; wsum[wid][3] = acc[3]; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += wsum[w][threadIdx.x];
+        scal[threadIdx.x] = r;
     }
 }
 
@@ -607,11 +644,10 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
                p->chunks_per_split, p->col_tile0);
     PLM_MARK();
 
+    const int nfx = (int)(gridB.x * p->nscan);
     DCA_LAUNCH((plm_assemble_kernel<Q>), gridU, 256, 0, st,
                d_x, p->d_G, gstride, p->nsplit, L, ld, p->lh, p->lJ, p->site_lo, p->site_hi,
-               d_dir, d_g, p->d_red);
-    DCA_LAUNCH(plm_finalize_kernel, 1, 256, 0, st,
-               p->d_red, p->red_blocks, p->d_fxpart, p->nscan, L, p->site_lo, p->site_hi, p->d_scal);
+               d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket, (unsigned)p->n_active, p->d_scal);
     PLM_MARK();
 #undef PLM_MARK
     DCA_CUDA(cudaGetLastError());
@@ -624,7 +660,7 @@ static void plm_free(PlmProblem *p)
     if (!p) return;
     cudaFree(p->d_msa); cudaFree(p->d_msaT); cudaFree(p->d_perm); cudaFree(p->d_w);
     cudaFree(p->d_W); cudaFree(p->d_G); cudaFree(p->d_S); cudaFree(p->d_fxpart);
-    cudaFree(p->d_red); cudaFree(p->d_scal);
+    cudaFree(p->d_red); cudaFree(p->d_scal); cudaFree(p->d_ticket);
     if (p->h_scal) cudaFreeHost(p->h_scal);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -658,6 +694,10 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     p->col_tile0 = (site_lo * q) / LG_TC;
     p->col_tiles = ceil_div(site_hi * q, LG_TC) - p->col_tile0;
     p->red_blocks = ceil_div(L, AS_JG) * L;
+    p->n_active = 0;                 // assemble CTAs that own a pair or the fields of a site
+    for (int i = 0; i < L; ++i)
+        for (int bx = 0; bx < ceil_div(L, AS_JG); ++bx)
+            p->n_active += (bx == 0 || bx * AS_JG + AS_JG - 1 > i) ? 1 : 0;
     {   // n-splits of the scatter: enough CTAs for >= ~3 waves, each >= 8 chunks
         const long tiles = (long)p->col_tiles * ceil_div(L, SC_WARPS);
         int want = (int)ceil_div<long>(3L * sm_count(), std::max(1L, tiles));
@@ -686,6 +726,9 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     PLM_TRY(cudaMalloc(&p->d_S, sizeof(float) * (size_t)p->Npad * p->ld));
     PLM_TRY(cudaMalloc(&p->d_fxpart, sizeof(double) * (size_t)(N / 8 + 1) * L));   // chunk >= 8
     PLM_TRY(cudaMalloc(&p->d_red, sizeof(double) * 4 * (size_t)p->red_blocks));
+    PLM_TRY(cudaMemsetAsync(p->d_red, 0, sizeof(double) * 4 * (size_t)p->red_blocks, p->stream));
+    PLM_TRY(cudaMalloc(&p->d_ticket, sizeof(unsigned)));
+    PLM_TRY(cudaMemsetAsync(p->d_ticket, 0, sizeof(unsigned), p->stream));
     PLM_TRY(cudaMalloc(&p->d_scal, sizeof(double) * 16));
     PLM_TRY(cudaMallocHost(&p->h_scal, sizeof(double) * 16));
     PLM_TRY(cudaMemcpyAsync(p->d_msa, h_msa, (size_t)N * L, cudaMemcpyHostToDevice, p->stream));
