@@ -79,7 +79,7 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -286,11 +286,15 @@ def run_ours(args, rank, world, local_rank):
         n_e2e = max(1, min(args.steps, 5))
         _lib.plmdca_backend(path, "protein", SEQ_LEN, Q, SEQID, lam, lam, MAX_ITER)      # warm (page cache, context)
         e_evals = 0
+        per_call = []
         t0 = time.perf_counter()
         for _ in range(n_e2e):
+            t1 = time.perf_counter()
             _lib.plmdca_backend(path, "protein", SEQ_LEN, Q, SEQID, lam, lam, MAX_ITER)
             e_evals += _lib.last_fit().evaluations
+            per_call.append(1e3 * (time.perf_counter() - t1))
         e_wall = time.perf_counter() - t0
+        print("e2e per-call ms: " + " ".join("%.1f" % v for v in per_call), file=sys.stderr)
         P = obj.P
         e2e = {"value": e_evals / e_wall, "unit": "evals/s",
                "h2d_bytes_per_step": 2 * N_SEQ * SEQ_LEN + 4 * N_SEQ + 4 * P,

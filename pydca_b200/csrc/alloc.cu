@@ -1,0 +1,144 @@
+// alloc.cu -- caching device allocator for the library's work buffers.
+//
+// A plmDCA fit needs ~0.6 GB of device buffers at the BASELINE config-2 size
+// (W, S, G, perm, 16 L-BFGS vectors).  cudaMalloc / cudaFree cost milliseconds
+// each and cudaFree synchronises the device, which dominated the end-to-end time
+// of repeated plmdcaBackend() calls.  Freed blocks are kept (per device, exact
+// size) and handed back on the next request; the cache is capped and is
+// released when an allocation fails.  Callers free a block only after the
+// stream that used it has been synchronised, so reuse needs no stream tracking.
+#include "dca_common.cuh"
+#include "dca_internal.h"
+
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
+namespace dca {
+
+namespace {
+struct Cache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> free_blocks;
+    std::unordered_map<void *, std::pair<int, size_t>> live;
+    size_t cached = 0;
+    size_t cap = 0;
+};
+Cache &cache()
+{
+    static Cache c;
+    if (c.cap == 0) {
+        const char *e = getenv("DCA_B200_CACHE_MB");
+        c.cap = (e ? (size_t)atol(e) : (size_t)8192) << 20;
+    }
+    return c;
+}
+void release_locked(Cache &c)
+{
+    for (auto &kv : c.free_blocks) cudaFree(kv.second);
+    c.free_blocks.clear();
+    c.cached = 0;
+}
+}  // namespace
+
+void *dev_alloc(size_t bytes)
+{
+    if (bytes == 0) bytes = 1;
+    bytes = (bytes + 511) & ~(size_t)511;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Cache &c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.free_blocks.find({dev, bytes});
+    void *p = nullptr;
+    if (it != c.free_blocks.end()) {
+        p = it->second;
+        c.free_blocks.erase(it);
+        c.cached -= bytes;
+    } else {
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            release_locked(c);
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            return nullptr;
+        }
+    }
+    c.live[p] = {dev, bytes};
+    return p;
+}
+
+void dev_free(void *p)
+{
+    if (!p) return;
+    Cache &c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) { cudaFree(p); return; }
+    const auto key = it->second;
+    c.live.erase(it);
+    if (c.cached + key.second <= c.cap) {
+        c.free_blocks.insert({key, p});
+        c.cached += key.second;
+    } else {
+        cudaFree(p);
+    }
+}
+
+// pinned host buffers (result vectors handed to the caller): same exact-size cache
+namespace {
+struct HostCache {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_blocks;
+    std::unordered_map<void *, size_t> live;
+    size_t cached = 0;
+};
+HostCache &host_cache() { static HostCache c; return c; }
+}  // namespace
+
+void *host_pinned_alloc(size_t bytes)
+{
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    HostCache &c = host_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    void *p = nullptr;
+    auto it = c.free_blocks.find(bytes);
+    if (it != c.free_blocks.end()) {
+        p = it->second;
+        c.free_blocks.erase(it);
+        c.cached -= bytes;
+    } else if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("pinned host allocation of %zu bytes failed", bytes);
+        return nullptr;
+    }
+    c.live[p] = bytes;
+    return p;
+}
+
+// returns false when p was not allocated here (caller falls back to free())
+bool host_pinned_free(void *p)
+{
+    HostCache &c = host_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) return false;
+    const size_t bytes = it->second;
+    c.live.erase(it);
+    if (c.cached + bytes <= ((size_t)2 << 30)) { c.free_blocks.insert({bytes, p}); c.cached += bytes; }
+    else cudaFreeHost(p);
+    return true;
+}
+
+void dev_cache_release()
+{
+    Cache &c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    release_locked(c);
+}
+
+}  // namespace dca

@@ -9,6 +9,7 @@
 #include "../../include/dca_b200.h"
 
 #include <cstdarg>
+#include <ctime>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -124,8 +125,10 @@ int dca_weights(const uint8_t *msa, long num_seqs, int seqs_len, double seqid, i
     if (!(seqid > 0.0) || seqid > 1.0) { set_error("dca_weights: seqid %g not in (0,1]", seqid); return -1; }
     uint8_t *d_msa = nullptr;
     unsigned *d_counts = nullptr;
-    DCA_CUDA(cudaMalloc(&d_msa, (size_t)num_seqs * seqs_len));
-    DCA_CUDA(cudaMalloc(&d_counts, sizeof(unsigned) * (size_t)num_seqs));
+    if (!dev_alloc_t(&d_msa, (size_t)num_seqs * seqs_len) || !dev_alloc_t(&d_counts, (size_t)num_seqs)) {
+        dev_free(d_msa); dev_free(d_counts);
+        return -1;
+    }
     DCA_CUDA(cudaMemcpy(d_msa, msa, (size_t)num_seqs * seqs_len, cudaMemcpyHostToDevice));
     int rc = reweight_counts_device(d_msa, num_seqs, seqs_len, seqid, compare_f64, row_lo, row_hi, d_counts, 0);
     if (rc == 0) {
@@ -133,7 +136,8 @@ int dca_weights(const uint8_t *msa, long num_seqs, int seqs_len, double seqid, i
                                    cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { set_error("dca_weights: D2H failed: %s", cudaGetErrorString(e)); rc = -1; }
     }
-    cudaFree(d_msa); cudaFree(d_counts);
+    cudaDeviceSynchronize();
+    dev_free(d_msa); dev_free(d_counts);
     return rc;
 }
 
@@ -147,18 +151,17 @@ dca_plm *dca_plm_create(const uint8_t *msa, const float *weights, long num_seqs,
     dca_plm *h = new (std::nothrow) dca_plm{prob, nullptr, nullptr};
     if (!h) { plm_destroy(prob); set_error("out of memory"); return nullptr; }
     const size_t bytes = sizeof(float) * (size_t)plm_num_params(prob);
-    if (cudaMalloc(&h->d_x, bytes) != cudaSuccess || cudaMalloc(&h->d_g, bytes) != cudaSuccess) {
-        set_error("dca_plm_create: cudaMalloc of x/g (%zu bytes) failed", bytes);
-        dca_plm_destroy(h);
-        return nullptr;
-    }
+    h->d_x = static_cast<float *>(dev_alloc(bytes));
+    h->d_g = static_cast<float *>(dev_alloc(bytes));
+    if (!h->d_x || !h->d_g) { dca_plm_destroy(h); return nullptr; }
     return h;
 }
 
 void dca_plm_destroy(dca_plm *p)
 {
     if (!p) return;
-    cudaFree(p->d_x); cudaFree(p->d_g);
+    cudaStreamSynchronize(plm_stream(p->prob));
+    dev_free(p->d_x); dev_free(p->d_g);
     plm_destroy(p->prob);
     delete p;
 }
@@ -256,6 +259,15 @@ float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states,
                      unsigned int max_iteration, unsigned int num_threads, bool verbose)
 {
     (void)num_threads;   // kept for signature compatibility: the work runs on the GPU
+    const bool trace = getenv("DCA_B200_TRACE") != nullptr;
+    auto now = []() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+    double t_prev = now();
+    auto mark = [&](const char *what) {
+        if (!trace) return;
+        const double t = now();
+        fprintf(stderr, "[dca trace] %-10s %8.2f ms\n", what, t - t_prev);
+        t_prev = t;
+    };
     if (require_device() != 0) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); return nullptr; }
     const int q = (int)num_site_states, L = (int)seqs_len;
     if ((biomolecule == 1 && q != 21) || (biomolecule != 1 && q != 5)) {
@@ -266,23 +278,41 @@ float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states,
     std::vector<uint8_t> msa;
     const long N = read_fasta_unique(msa_file, biomolecule == 1 ? 1 : 2, L, msa);       // plmdca_numerics.cpp:43
     if (N <= 0) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); return nullptr; }
+    mark("read_fasta");
     std::vector<uint32_t> counts((size_t)N);
     if (dca_weights(msa.data(), N, L, (double)seqid, 0, 0, N, counts.data()) != 0) {    // :45
         fprintf(stderr, "plmdcaBackend: %s\n", last_error());
         return nullptr;
     }
+    mark("reweight");
     std::vector<float> w((size_t)N);
     for (long n = 0; n < N; ++n) w[n] = 1.f / (float)counts[n];                          // :669
     dca_plm *h = dca_plm_create(msa.data(), w.data(), N, L, q, lambda_h, lambda_J, 0, L);
     if (!h) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); return nullptr; }
+    mark("create");
     const size_t P = (size_t)dca_plm_num_params(h);
-    float *x = (float *)malloc(sizeof(float) * P);                                       // plmdcaBackend.cpp:61
+    // result buffer (plmdcaBackend.cpp:61 lbfgs_malloc): pinned so the final D2H runs at
+    // full PCIe rate; released by freeFieldsAndCouplings
+    float *x = (float *)host_pinned_alloc(sizeof(float) * P);
     if (!x) { fprintf(stderr, "ERROR: Failed to allocate a memory block for variables.\n"); dca_plm_destroy(h); return nullptr; }
     dca_fit_result res{};
-    int rc = dca_plm_init(h, x);                                                         // :77
-    if (rc == 0) rc = dca_plm_fit(h, x, (int)max_iteration, verbose ? 1 : 0, 0, nullptr, nullptr, &res);   // :81
+    // initial point (:77) and L-BFGS (:81) without leaving the device
+    cudaStream_t st = plm_stream(h->prob);
+    int rc = plm_init_x_device(h->prob, h->d_x);
+    mark("init");
+    LbfgsResult r{};
+    double timed_ms = 0.0;
+    int timed_evals = 0;
+    if (rc == 0) rc = lbfgs_minimize(h->prob, h->d_x, (int)max_iteration, verbose ? 1 : 0, nullptr, nullptr, &r, 0,
+                                     &timed_ms, &timed_evals);
+    if (rc == 0 && cudaMemcpyAsync(x, h->d_x, sizeof(float) * P, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) rc = -1;
+    res.status = r.status; res.iterations = r.iterations; res.evaluations = r.evaluations; res.fx = r.fx;
+    res.device_ms = r.device_ms; res.timed_ms = timed_ms; res.timed_evaluations = timed_evals;
+    mark("fit+d2h");
     dca_plm_destroy(h);
-    if (rc != 0) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); free(x); return nullptr; }
+    mark("destroy");
+    if (rc != 0) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); host_pinned_free(x); return nullptr; }
     t_last_fit = res;
     return x;
 }
@@ -294,7 +324,10 @@ int dca_last_fit(dca_fit_result *result)
     return 0;
 }
 
-void freeFieldsAndCouplings(void *h_and_J) { free(h_and_J); }
+void freeFieldsAndCouplings(void *h_and_J)
+{
+    if (h_and_J && !host_pinned_free(h_and_J)) free(h_and_J);
+}
 
 // ---- mean-field operators ---------------------------------------------------------
 int dca_mf_freqs(const uint8_t *msa, const double *weights, long num_seqs, int seqs_len,

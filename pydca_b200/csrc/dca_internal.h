@@ -7,6 +7,15 @@
 
 namespace dca {
 
+// ---- alloc.cu ------------------------------------------------------------------
+void *dev_alloc(size_t bytes);          // caching cudaMalloc; nullptr + error on failure
+void dev_free(void *p);                 // only after the using stream was synchronised
+void dev_cache_release();
+void *host_pinned_alloc(size_t bytes);   // cached cudaMallocHost
+bool host_pinned_free(void *p);          // false if p is not ours
+template <typename T>
+static inline bool dev_alloc_t(T **out, size_t count) { *out = static_cast<T *>(dev_alloc(sizeof(T) * count)); return *out != nullptr; }
+
 // ---- fasta.cpp -----------------------------------------------------------------
 // FASTA -> u8 [N][L] (states 0..q-1, gap q-1), unique rows in first-occurrence order.
 long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uint8_t> &out);

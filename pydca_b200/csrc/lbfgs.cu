@@ -345,24 +345,22 @@ struct Driver {
     int alloc()
     {
         float **v[] = {&xp, &g, &gp, &d};
-        for (auto pp : v) DCA_CUDA(cudaMalloc(pp, sizeof(float) * (size_t)n));
+        for (auto pp : v) if (!dev_alloc_t(pp, (size_t)n)) return -1;
         for (int i = 0; i < LB_M; ++i) {
-            DCA_CUDA(cudaMalloc(&s[i], sizeof(float) * (size_t)n));
-            DCA_CUDA(cudaMalloc(&y[i], sizeof(float) * (size_t)n));
+            if (!dev_alloc_t(&s[i], (size_t)n) || !dev_alloc_t(&y[i], (size_t)n)) return -1;
         }
-        DCA_CUDA(cudaMalloc(&sc, sizeof(float) * SC_FLOATS));
+        if (!dev_alloc_t(&sc, (size_t)SC_FLOATS)) return -1;
         DCA_CUDA(cudaMemsetAsync(sc, 0, sizeof(float) * SC_FLOATS, st));
-        DCA_CUDA(cudaMalloc(&partial, sizeof(double) * 2 * (size_t)blocks));
-        DCA_CUDA(cudaMalloc(&ticket, sizeof(unsigned)));
+        if (!dev_alloc_t(&partial, 2 * (size_t)blocks) || !dev_alloc_t(&ticket, (size_t)1)) return -1;
         DCA_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
         return 0;
     }
     void release(float *keep_x)
     {
         float *v[] = {x, xp, g, gp, d};
-        for (float *q : v) if (q && q != keep_x) cudaFree(q);
-        for (int i = 0; i < LB_M; ++i) { cudaFree(s[i]); cudaFree(y[i]); }
-        cudaFree(sc); cudaFree(partial); cudaFree(ticket);
+        for (float *q : v) if (q && q != keep_x) dev_free(q);
+        for (int i = 0; i < LB_M; ++i) { dev_free(s[i]); dev_free(y[i]); }
+        dev_free(sc); dev_free(partial); dev_free(ticket);
     }
 
     // objective at x -> g ; returns {fx, g.d, g.g, x.x} on the host

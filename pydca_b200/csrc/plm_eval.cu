@@ -83,6 +83,7 @@ struct PlmProblem {
     int red_blocks = 0, n_active = 0;
     unsigned *d_ticket = nullptr;
     int col_tile0 = 0, col_tiles = 0;
+    int site_tiles = 0, sites_per_tile = 0;
 };
 
 // ------------------------------------------------------------------------------
@@ -335,7 +336,7 @@ template <int Q>
 __global__ void __launch_bounds__(SC_WARPS * 32, 1)
 plm_scatter_kernel(const float *__restrict__ R, int ld, const uint8_t *__restrict__ perm, int nchunk,
                    long N, int L, float *__restrict__ G, size_t g_split_stride,
-                   int chunks_per_split, int col_tile0)
+                   int chunks_per_split, int col_tile0, int sites_per_tile)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *Rs = reinterpret_cast<float *>(smem_raw);                                    // [2][SC_CH][SC_TC]
@@ -343,7 +344,8 @@ plm_scatter_kernel(const float *__restrict__ R, int ld, const uint8_t *__restric
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = (col_tile0 + blockIdx.x) * SC_TC;
-    const int j = blockIdx.y * SC_WARPS + warp;
+    // site tiles are balanced (e.g. L=150 -> 10 tiles of 15 sites): idle warps get j = L
+    const int j = (warp < sites_per_tile) ? min(L, (int)blockIdx.y * sites_per_tile + warp) : L;
     const int c0 = blockIdx.z * chunks_per_split;
     const int c1 = min(nchunk, c0 + chunks_per_split);
 
@@ -638,10 +640,10 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
 
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC;
     const size_t gstride = (size_t)p->Lq * ld;
-    dim3 gridC(p->col_tiles, ceil_div(L, SC_WARPS), p->nsplit);
+    dim3 gridC(p->col_tiles, p->site_tiles, p->nsplit);
     DCA_LAUNCH((plm_scatter_kernel<Q>), gridC, SC_WARPS * 32, smemC, st,
                p->d_S, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride,
-               p->chunks_per_split, p->col_tile0);
+               p->chunks_per_split, p->col_tile0, p->sites_per_tile);
     PLM_MARK();
 
     const int nfx = (int)(gridB.x * p->nscan);
@@ -658,10 +660,11 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
 static void plm_free(PlmProblem *p)
 {
     if (!p) return;
-    cudaFree(p->d_msa); cudaFree(p->d_msaT); cudaFree(p->d_perm); cudaFree(p->d_w);
-    cudaFree(p->d_W); cudaFree(p->d_G); cudaFree(p->d_S); cudaFree(p->d_fxpart);
-    cudaFree(p->d_red); cudaFree(p->d_scal); cudaFree(p->d_ticket);
-    if (p->h_scal) cudaFreeHost(p->h_scal);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    dev_free(p->d_msa); dev_free(p->d_msaT); dev_free(p->d_perm); dev_free(p->d_w);
+    dev_free(p->d_W); dev_free(p->d_G); dev_free(p->d_S); dev_free(p->d_fxpart);
+    dev_free(p->d_red); dev_free(p->d_scal); dev_free(p->d_ticket);
+    if (p->h_scal) host_pinned_free(p->h_scal);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -698,11 +701,21 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     for (int i = 0; i < L; ++i)
         for (int bx = 0; bx < ceil_div(L, AS_JG); ++bx)
             p->n_active += (bx == 0 || bx * AS_JG + AS_JG - 1 > i) ? 1 : 0;
-    {   // n-splits of the scatter: enough CTAs for >= ~3 waves, each >= 8 chunks
-        const long tiles = (long)p->col_tiles * ceil_div(L, SC_WARPS);
-        int want = (int)ceil_div<long>(3L * sm_count(), std::max(1L, tiles));
-        int maxs = std::max(1, p->nchunk / 8);
-        p->nsplit = std::max(1, std::min(want, maxs));
+    {   // scatter plan: balanced site tiles, and the n-split count that minimises the
+        // makespan ceil(CTAs / SMs) / nsplit of equal-cost CTAs (1 CTA per SM), with a
+        // small penalty per split for the extra G traffic the assemble kernel reads
+        p->site_tiles = ceil_div(L, SC_WARPS);
+        p->sites_per_tile = ceil_div(L, p->site_tiles);
+        const long tiles = (long)p->col_tiles * p->site_tiles;
+        const int sms = sm_count();
+        double best = 1e300;
+        int best_s = 1;
+        for (int s = 1; s <= 8; ++s) {
+            if (s > 1 && p->nchunk / s < 4) break;
+            const double cost = (double)ceil_div<long>(tiles * s, sms) / s * (1.0 + 0.02 * s);
+            if (cost < best - 1e-12) { best = cost; best_s = s; }
+        }
+        p->nsplit = best_s;
         p->chunks_per_split = ceil_div(p->nchunk, p->nsplit);
         p->nsplit = ceil_div(p->nchunk, p->chunks_per_split);
     }
@@ -716,21 +729,26 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
         set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
         plm_free(p); return nullptr; } } while (0)
 
+#define PLM_ALLOC(ptr, bytes)                                                         \
+    do { *reinterpret_cast<void **>(&(ptr)) = dev_alloc(bytes);                       \
+         if (!(ptr)) { plm_free(p); return nullptr; } } while (0)
+
     PLM_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    PLM_TRY(cudaMalloc(&p->d_msa, (size_t)N * L));
-    PLM_TRY(cudaMalloc(&p->d_msaT, (size_t)L * p->Npad));
-    PLM_TRY(cudaMalloc(&p->d_perm, (size_t)L * p->nchunk * PERM_REC));
-    PLM_TRY(cudaMalloc(&p->d_w, sizeof(float) * (size_t)N));
-    PLM_TRY(cudaMalloc(&p->d_W, sizeof(float) * (size_t)p->Lq * p->ld));
-    PLM_TRY(cudaMalloc(&p->d_G, sizeof(float) * (size_t)p->nsplit * p->Lq * p->ld));
-    PLM_TRY(cudaMalloc(&p->d_S, sizeof(float) * (size_t)p->Npad * p->ld));
-    PLM_TRY(cudaMalloc(&p->d_fxpart, sizeof(double) * (size_t)(N / 8 + 1) * L));   // chunk >= 8
-    PLM_TRY(cudaMalloc(&p->d_red, sizeof(double) * 4 * (size_t)p->red_blocks));
+    PLM_ALLOC(p->d_msa, (size_t)N * L);
+    PLM_ALLOC(p->d_msaT, (size_t)L * p->Npad);
+    PLM_ALLOC(p->d_perm, (size_t)L * p->nchunk * PERM_REC);
+    PLM_ALLOC(p->d_w, sizeof(float) * (size_t)N);
+    PLM_ALLOC(p->d_W, sizeof(float) * (size_t)p->Lq * p->ld);
+    PLM_ALLOC(p->d_G, sizeof(float) * (size_t)p->nsplit * p->Lq * p->ld);
+    PLM_ALLOC(p->d_S, sizeof(float) * (size_t)p->Npad * p->ld);
+    PLM_ALLOC(p->d_fxpart, sizeof(double) * (size_t)(N / 8 + 1) * L);   // chunk >= 8
+    PLM_ALLOC(p->d_red, sizeof(double) * 4 * (size_t)p->red_blocks);
     PLM_TRY(cudaMemsetAsync(p->d_red, 0, sizeof(double) * 4 * (size_t)p->red_blocks, p->stream));
-    PLM_TRY(cudaMalloc(&p->d_ticket, sizeof(unsigned)));
+    PLM_ALLOC(p->d_ticket, sizeof(unsigned));
     PLM_TRY(cudaMemsetAsync(p->d_ticket, 0, sizeof(unsigned), p->stream));
-    PLM_TRY(cudaMalloc(&p->d_scal, sizeof(double) * 16));
-    PLM_TRY(cudaMallocHost(&p->h_scal, sizeof(double) * 16));
+    PLM_ALLOC(p->d_scal, sizeof(double) * 16);
+    p->h_scal = static_cast<double *>(host_pinned_alloc(sizeof(double) * 16));
+    if (!p->h_scal) { plm_free(p); return nullptr; }
     PLM_TRY(cudaMemcpyAsync(p->d_msa, h_msa, (size_t)N * L, cudaMemcpyHostToDevice, p->stream));
     PLM_TRY(cudaMemcpyAsync(p->d_w, h_w, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, p->stream));
     PLM_TRY(cudaMemsetAsync(p->d_W, 0, sizeof(float) * (size_t)p->Lq * p->ld, p->stream));
@@ -740,6 +758,7 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     if (rc != 0) { plm_free(p); return nullptr; }
     PLM_TRY(cudaStreamSynchronize(p->stream));
 #undef PLM_TRY
+#undef PLM_ALLOC
     return p;
 }
 

@@ -177,7 +177,7 @@ int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, in
     if (N <= 0 || L <= 0) { set_error("reweight: empty alignment (N=%ld L=%d)", N, L); return -1; }
     const int Lw = (int)(ceil_div(L, 4) + 3) / 4 * 4;
     uint32_t *d_words = nullptr;
-    DCA_CUDA(cudaMallocAsync(&d_words, sizeof(uint32_t) * (size_t)N * Lw, stream));
+    if (!dev_alloc_t(&d_words, (size_t)N * Lw)) return -1;
     {
         const long total = N * Lw;
         DCA_LAUNCH(pack_rows_kernel, (unsigned)ceil_div<long>(total, 256), 256, 0, stream,
@@ -204,7 +204,8 @@ int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, in
                    d_words, N, row_lo, row_hi, Lw, jper, max_mismatch32, d_counts);
     }
     DCA_CUDA(cudaGetLastError());
-    DCA_CUDA(cudaFreeAsync(d_words, stream));
+    DCA_CUDA(cudaStreamSynchronize(stream));
+    dev_free(d_words);
     return 0;
 }
 

@@ -159,3 +159,27 @@ def test_synthetic_generator_is_deterministic():
     b = synthetic_msa(500, 30, 21)
     assert (a == b).all() and a.shape == (500, 30) and a.max() == 20
     assert len({r.tobytes() for r in a}) == 500
+
+
+def test_cli_surface_and_writer_format(tmp_path):
+    """Flags of pydca/plmdca_main.py:265-328 and pydca/mfdca_main.py:316-394 parse, and
+    the score table keeps the reference's row format (dca_utilities.py:255-266)."""
+    from pydca_b200 import dca_utilities, mfdca_main, plmdca_main
+    a = vars(plmdca_main.build_parser().parse_args(
+        ["compute_fn", "protein", "x.fa", "--seqid", "0.7", "--lambda_h", "1.0", "--lambda_J", "20", "--max_iterations",
+         "500", "--num_threads", "10", "--apc", "--verbose", "--output_dir", "o"]))
+    assert a["subcommand_name"] == "compute_fn" and a["max_iterations"] == 500 and a["apc"] and a["lambda_J"] == 20.0
+    a = vars(plmdca_main.build_parser().parse_args(["compute_params", "rna", "x.fa", "--ranked_by", "fn_apc",
+                                                     "--linear_dist", "5", "--num_site_pairs", "10"]))
+    assert a["ranked_by"] == "fn_apc" and a["linear_dist"] == 5
+    for cmd in ("compute_di", "compute_fn", "compute_fi", "compute_fij"):
+        a = vars(mfdca_main.build_parser().parse_args([cmd, "rna", "x.fa", "--pseudocount", "0.5", "--seqid", "0.8", "--apc"]))
+        assert a["subcommand_name"] == cmd and a["pseudocount"] == 0.5
+    out = tmp_path / "scores.txt"
+    dca_utilities.write_sorted_dca_scores(str(out), [((60, 74), 4.030616483327582), ((0, 1), 0.5)],
+                                          metadata=["# meta"], score_type="X")
+    lines = out.read_text().splitlines()
+    assert lines[0] == "#" + "=" * 70 and lines[1] == "# meta"
+    assert lines[-2] == "{0:<7} {1:<14} {2:<35}".format(61, 75, 4.030616483327582)
+    assert dca_utilities.get_dca_output_file_path("d", "/a/b/MSA_RF00167.fa", prefix="MFDCA_apc_fn_scores_",
+                                                  postfix=".txt") == os.path.join("d", "MFDCA_apc_fn_scores_MSA_RF00167.txt")

@@ -341,3 +341,26 @@ def test_plm_class_end_to_end(tmp_path, golden):
     top = [p for p, _ in ranked[:71]]
     ref_top = [tuple(p) for p in d["plm_fn_apc_sorted_pairs"][:71].tolist()]
     assert len(set(top) & set(ref_top)) >= 60                     # top-L overlap vs reference nt=1
+
+
+def test_cli_config1_mfdca_and_plmdca(tmp_path, golden):
+    """BASELINE config 1 through the command line: `mfdca compute_fn rna MSA_RF00167.fa
+    --pseudocount 0.5 --apc` (K5 top pairs in the output file), and a plmdca run."""
+    from pydca_b200 import mfdca_main, plmdca_main
+    from pydca_b200.synthetic import write_fasta
+    full = golden("rf00167_full.npz")
+    msa_path = write_fasta(full["msa"], str(tmp_path / "MSA_RF00167.fa"), 5)
+    out_dir = tmp_path / "out"
+    mfdca_main.run_meanfield_dca(["compute_fn", "rna", msa_path, "--pseudocount", "0.5", "--apc",
+                                  "--output_dir", str(out_dir)])
+    rows = [l.split() for l in (out_dir / "MFDCA_apc_fn_scores_MSA_RF00167.txt").read_text().splitlines()
+            if not l.startswith("#")]
+    assert len(rows) == 102 * 101 // 2
+    assert [(int(r[0]), int(r[1])) for r in rows[:5]] == [(61, 75), (62, 74), (31, 47), (34, 44), (33, 45)]
+    assert abs(float(rows[0][2]) - 4.030616483327582) <= 1e-5 * 4.03
+    toy = golden("plm_toy_rna.npz")
+    toy_path = write_fasta(toy["msa"], str(tmp_path / "toy.fa"), 5)
+    plmdca_main.run_plm_dca(["compute_fn", "rna", toy_path, "--max_iterations", "20", "--lambda_h", "1.0",
+                             "--lambda_J", "2.0", "--output_dir", str(out_dir)])
+    rows = [l for l in (out_dir / "PLMDCA_raw_fn_scores_toy.txt").read_text().splitlines() if not l.startswith("#")]
+    assert len(rows) == 7 * 6 // 2
