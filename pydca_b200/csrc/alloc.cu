@@ -134,6 +134,39 @@ bool host_pinned_free(void *p)
     return true;
 }
 
+// ---- tensor maps for TMA tile loads ---------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is looked up through the runtime
+// so that the library does not link against libcuda.
+int make_tensor_map_2d(void *out, int elem_bytes, const void *base, unsigned long long dim0,
+                       unsigned long long dim1, unsigned long long stride1_bytes, unsigned box0, unsigned box1)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return -1;
+        }
+        encode = reinterpret_cast<encode_fn>(fn);
+    }
+    const cuuint64_t gdim[2] = {dim0, dim1};
+    const cuuint64_t gstride[1] = {stride1_bytes};
+    const cuuint32_t box[2] = {box0, box1};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = (elem_bytes == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    const CUresult r = encode(static_cast<CUtensorMap *>(out), dt, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -1; }
+    return 0;
+}
+
 void dev_cache_release()
 {
     Cache &c = cache();

@@ -16,6 +16,11 @@ bool host_pinned_free(void *p);          // false if p is not ours
 template <typename T>
 static inline bool dev_alloc_t(T **out, size_t count) { *out = static_cast<T *>(dev_alloc(sizeof(T) * count)); return *out != nullptr; }
 
+// row-major 2-D tensor map: inner dimension dim0 (contiguous), dim1 rows of stride1_bytes;
+// elem_bytes 4 (float32) or 1 (uint8); box = box0 x box1 elements.  0 on success.
+int make_tensor_map_2d(void *out_CUtensorMap, int elem_bytes, const void *base, unsigned long long dim0,
+                       unsigned long long dim1, unsigned long long stride1_bytes, unsigned box0, unsigned box1);
+
 // ---- fasta.cpp -----------------------------------------------------------------
 // FASTA -> u8 [N][L] (states 0..q-1, gap q-1), unique rows in first-occurrence order.
 long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uint8_t> &out);

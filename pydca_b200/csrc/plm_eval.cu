@@ -84,6 +84,7 @@ struct PlmProblem {
     unsigned *d_ticket = nullptr;
     int col_tile0 = 0, col_tiles = 0;
     int site_tiles = 0, sites_per_tile = 0;
+    CUtensorMap tmS;         // S as [Npad][ld] f32, box 128 x 128 (scatter tiles)
 };
 
 // ------------------------------------------------------------------------------
@@ -98,9 +99,11 @@ __global__ void transpose_msa_kernel(const uint8_t *__restrict__ msa, long N, in
 }
 
 // one thread per (site, chunk): bucket the chunk's local indices by residue
+// records are laid out [site tile][chunk][site within tile] so that the records of
+// the sites one scatter CTA works on are one contiguous block per chunk (one bulk copy)
 template <int Q>
 __global__ void build_perm_kernel(const uint8_t *__restrict__ msaT, long N, long Npad, int L,
-                                  int nchunk, uint8_t *__restrict__ perm)
+                                  int nchunk, int sites_per_tile, uint8_t *__restrict__ perm)
 {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)L * nchunk) return;
@@ -108,7 +111,8 @@ __global__ void build_perm_kernel(const uint8_t *__restrict__ msaT, long N, long
     const int c = (int)(idx - (long)j * nchunk);
     const uint8_t *col = msaT + (long)j * Npad + (long)c * SC_CH;
     const int rows = (int)min((long)SC_CH, N - (long)c * SC_CH);
-    uint8_t *rec = perm + idx * PERM_REC;
+    const int tile = j / sites_per_tile, slot = j - tile * sites_per_tile;
+    uint8_t *rec = perm + (((size_t)tile * nchunk + c) * sites_per_tile + slot) * PERM_REC;
     int cnt[Q], pos[Q];
 #pragma unroll
     for (int b = 0; b < Q; ++b) cnt[b] = 0;
@@ -330,52 +334,69 @@ plm_softmax_kernel(float *__restrict__ S, int ld, const uint8_t *__restrict__ ms
 
 // ------------------------------------------------------------------------------
 // scatter: G[(j,b)][col] = sum_{n : s_nj == b} r[n][col], warp = one site j,
-// 21 float4 accumulators per lane, residual chunk staged in shared memory,
-// sequences visited in residue-bucket order (perm) -> no atomics, fixed order.
+// 21 float4 accumulators per lane, sequences visited in residue-bucket order
+// (perm) -> no atomics, fixed order.
+// Staging: the 128 x 128 f32 residual tile and the warps' perm records are
+// fetched by the TMA engine (cp.async.bulk, one 512-byte row per copy) into a
+// two-deep ring guarded by mbarriers: full[b] (transaction bytes) / empty[b]
+// (one arrival per active warp).  There is no block-wide barrier in the loop:
+// a warp that finishes chunk c moves on to c+1 at once, and the warp whose turn
+// it is ((k+2) mod active warps) waits for empty[b] and re-arms the buffer with
+// chunk c+2.
 template <int Q>
 __global__ void __launch_bounds__(SC_WARPS * 32, 1)
-plm_scatter_kernel(const float *__restrict__ R, int ld, const uint8_t *__restrict__ perm, int nchunk,
+plm_scatter_kernel(const __grid_constant__ CUtensorMap tmS, int ld, const uint8_t *__restrict__ perm, int nchunk,
                    long N, int L, float *__restrict__ G, size_t g_split_stride,
                    int chunks_per_split, int col_tile0, int sites_per_tile)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     float *Rs = reinterpret_cast<float *>(smem_raw);                                    // [2][SC_CH][SC_TC]
     uint8_t *recs = smem_raw + sizeof(float) * 2 * SC_CH * SC_TC;                       // [2][SC_WARPS][PERM_REC]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(recs + 2 * SC_WARPS * PERM_REC);      // full[2], empty[2]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = (col_tile0 + blockIdx.x) * SC_TC;
-    // site tiles are balanced (e.g. L=150 -> 10 tiles of 15 sites): idle warps get j = L
-    const int j = (warp < sites_per_tile) ? min(L, (int)blockIdx.y * sites_per_tile + warp) : L;
+    // site tiles are balanced (e.g. L=150 -> 10 tiles of 15 sites); active warps are a prefix
+    const int jbase = (int)blockIdx.y * sites_per_tile;
+    const int nactive = max(0, min(sites_per_tile, L - jbase));
+    const int j = jbase + warp;
     const int c0 = blockIdx.z * chunks_per_split;
     const int c1 = min(nchunk, c0 + chunks_per_split);
+    const int nloc = max(0, c1 - c0);
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], nactive); mbar_init(&bars[3], nactive);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp >= nactive) return;                         // idle warps: nothing to stage, nothing to sum
 
     float4 acc[Q];
 #pragma unroll
     for (int b = 0; b < Q; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    auto stage = [&](int buf, int c) {
-        float *dst = Rs + (size_t)buf * SC_CH * SC_TC;
-        const long nb = (long)c * SC_CH;
-        const int rows = (int)min((long)SC_CH, N - nb);
-        const float *src = R + (size_t)nb * ld + col0;
-        for (int t = tid; t < rows * 32; t += SC_WARPS * 32) {
-            const int row = t >> 5, c4 = t & 31;
-            cp_async16(dst + row * SC_TC + 4 * c4, src + (size_t)row * ld + 4 * c4);
+    // one lane arms buffer `buf` with chunk c: expect the bytes, then two TMA operations:
+    // the 128 x 128 residual tile (2-D tensor map over S) and this tile's perm records
+    auto issue = [&](int buf, int c) {
+        if (lane == 0) {
+            mbar_expect_tx(&bars[buf], (unsigned)(SC_CH * SC_TC * 4 + nactive * PERM_REC));
+            tma_load_2d(Rs + (size_t)buf * SC_CH * SC_TC, &tmS, col0, c * SC_CH, &bars[buf]);
+            tma_bulk_g2s(recs + (size_t)buf * SC_WARPS * PERM_REC,
+                         perm + (((size_t)blockIdx.y * nchunk + c) * sites_per_tile) * PERM_REC,
+                         (unsigned)(nactive * PERM_REC), &bars[buf]);
         }
-        if (j < L)
-            for (int s = lane; s < PERM_REC / 16; s += 32)
-                cp_async16(recs + ((size_t)buf * SC_WARPS + warp) * PERM_REC + 16 * s,
-                           perm + ((size_t)j * nchunk + c) * PERM_REC + 16 * s);
-        cp_async_commit();
+        __syncwarp();
     };
 
-    if (c0 < c1) stage(0, c0);
-    for (int c = c0; c < c1; ++c) {
-        const int buf = (c - c0) & 1;
-        if (c + 1 < c1) { stage(buf ^ 1, c + 1); cp_async_wait<1>(); }
-        else            { cp_async_wait<0>(); }
-        __syncthreads();
-        if (j < L) {
+    if (warp == 0 && nloc > 0) issue(0, c0);
+    if (warp == (1 % nactive) && nloc > 1) issue(1, c0 + 1);
+
+    for (int k = 0; k < nloc; ++k) {
+        const int buf = k & 1;
+        const unsigned parity = (unsigned)(k >> 1) & 1u;
+        mbar_wait(&bars[buf], parity);                   // TMA bytes of chunk c0+k have landed
+        {
             const uint8_t *rec = recs + ((size_t)buf * SC_WARPS + warp) * PERM_REC;
             const uint4 *qp = reinterpret_cast<const uint4 *>(rec + PERM_CNT);
             const char *Rb = reinterpret_cast<const char *>(Rs + (size_t)buf * SC_CH * SC_TC + 4 * lane);
@@ -391,32 +412,37 @@ plm_scatter_kernel(const float *__restrict__ R, int ld, const uint8_t *__restric
                 const unsigned m = (hw[b >> 2] >> (8 * (b & 3))) & 0xffu;
                 float4 a = acc[b];
                 const unsigned nq = (m + 3u) >> 2;
-                for (unsigned t = 1; t < nq; ++t) {            // full quads
+                // One compact loop per bucket (rows beyond the bucket's size are predicated
+                // off, warp-uniformly).  Deliberately not unrolled: the 21 bucket copies must
+                // stay inside the 32 KB instruction cache -- ncu showed "no instruction" stalls
+                // ~1 per issued instruction when the kernel was 64 KB of SASS.
+#pragma unroll 1
+                for (unsigned t = 0; t < nq; ++t) {
                     const uint4 o = cur;
                     cur = qp[++pos];
-                    const float4 v0 = SC_ROW(o.x), v1 = SC_ROW(o.y), v2 = SC_ROW(o.z), v3 = SC_ROW(o.w);
+                    const unsigned rem = m - 4u * t;                 // rows left in this bucket (>= 1)
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 v0 = SC_ROW(o.x);
+                    const float4 v1 = (rem > 1u) ? SC_ROW(o.y) : z4;
+                    const float4 v2 = (rem > 2u) ? SC_ROW(o.z) : z4;
+                    const float4 v3 = (rem > 3u) ? SC_ROW(o.w) : z4;
                     a.x += (v0.x + v1.x) + (v2.x + v3.x);
                     a.y += (v0.y + v1.y) + (v2.y + v3.y);
                     a.z += (v0.z + v1.z) + (v2.z + v3.z);
                     a.w += (v0.w + v1.w) + (v2.w + v3.w);
                 }
-                if (m != 0u) {                                  // last quad of the bucket: 1..4 rows
-                    const uint4 o = cur;
-                    cur = qp[++pos];
-                    const unsigned rem = m - 4u * (nq - 1u);
-                    float4 s = SC_ROW(o.x);
-                    if (rem > 1u) { const float4 v = SC_ROW(o.y); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
-                    if (rem > 2u) { const float4 v = SC_ROW(o.z); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
-                    if (rem > 3u) { const float4 v = SC_ROW(o.w); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
-                    a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
-                }
                 acc[b] = a;
             }
 #undef SC_ROW
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[2 + buf]);      // this warp is done with buffer `buf`
+        if (k + 2 < nloc && warp == (k + 2) % nactive) {
+            mbar_wait(&bars[2 + buf], parity);           // every active warp released it
+            issue(buf, c0 + k + 2);
+        }
     }
-    if (j < L) {
+    {
         float *g = G + (size_t)blockIdx.z * g_split_stride + (size_t)j * Q * ld + col0 + 4 * lane;
 #pragma unroll
         for (int b = 0; b < Q; ++b) *reinterpret_cast<float4 *>(g + (size_t)b * ld) = acc[b];
@@ -600,12 +626,12 @@ static int plm_setup_t(PlmProblem *p)
     }
     {
         const long total = (long)p->L * p->nchunk;
-        DCA_CUDA(cudaMemsetAsync(p->d_perm, 0, (size_t)total * PERM_REC, st));
+        DCA_CUDA(cudaMemsetAsync(p->d_perm, 0, (size_t)p->site_tiles * p->sites_per_tile * p->nchunk * PERM_REC, st));
         DCA_LAUNCH((build_perm_kernel<Q>), (unsigned)ceil_div<long>(total, 128), 128, 0, st,
-                   p->d_msaT, p->N, p->Npad, p->L, p->nchunk, p->d_perm);
+                   p->d_msaT, p->N, p->Npad, p->L, p->nchunk, p->sites_per_tile, p->d_perm);
     }
     const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN;
-    const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC;
+    const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
     DCA_CUDA(cudaFuncSetAttribute(plm_logits_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     DCA_CUDA(cudaFuncSetAttribute(plm_scatter_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
     DCA_CUDA(cudaGetLastError());
@@ -638,11 +664,11 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
                p->chunk, p->warm, p->carry, p->d_fxpart);
     PLM_MARK();
 
-    const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC;
+    const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
     const size_t gstride = (size_t)p->Lq * ld;
     dim3 gridC(p->col_tiles, p->site_tiles, p->nsplit);
     DCA_LAUNCH((plm_scatter_kernel<Q>), gridC, SC_WARPS * 32, smemC, st,
-               p->d_S, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride,
+               p->tmS, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride,
                p->chunks_per_split, p->col_tile0, p->sites_per_tile);
     PLM_MARK();
 
@@ -736,7 +762,7 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     PLM_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     PLM_ALLOC(p->d_msa, (size_t)N * L);
     PLM_ALLOC(p->d_msaT, (size_t)L * p->Npad);
-    PLM_ALLOC(p->d_perm, (size_t)L * p->nchunk * PERM_REC);
+    PLM_ALLOC(p->d_perm, (size_t)p->site_tiles * p->sites_per_tile * p->nchunk * PERM_REC);
     PLM_ALLOC(p->d_w, sizeof(float) * (size_t)N);
     PLM_ALLOC(p->d_W, sizeof(float) * (size_t)p->Lq * p->ld);
     PLM_ALLOC(p->d_G, sizeof(float) * (size_t)p->nsplit * p->Lq * p->ld);
@@ -754,6 +780,8 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     PLM_TRY(cudaMemsetAsync(p->d_W, 0, sizeof(float) * (size_t)p->Lq * p->ld, p->stream));
     PLM_TRY(cudaMemsetAsync(p->d_S, 0, sizeof(float) * (size_t)p->Npad * p->ld, p->stream));
     PLM_TRY(cudaMemsetAsync(p->d_fxpart, 0, sizeof(double) * (size_t)(N / 8 + 1) * L, p->stream));
+    if (make_tensor_map_2d(&p->tmS, 4, p->d_S, (unsigned long long)p->ld, (unsigned long long)p->Npad,
+                           sizeof(float) * (unsigned long long)p->ld, SC_TC, SC_CH) != 0) { plm_free(p); return nullptr; }
     const int rc = (q == 21) ? plm_setup_t<21>(p) : plm_setup_t<5>(p);
     if (rc != 0) { plm_free(p); return nullptr; }
     PLM_TRY(cudaStreamSynchronize(p->stream));
