@@ -133,6 +133,15 @@ int dca_mf_couplings(const double *corr, int n, double *couplings_out);
 /* FN + APC of the couplings matrix (meanfield_dca.py:902-988). */
 int dca_mf_fn_apc(const double *couplings, int seqs_len, int num_site_states,
                   double *fn_out, double *fn_apc_out);
+/* the whole pipeline of MeanFieldDCA.compute_sorted_FN / _DI (meanfield_dca.py:793-988)
+ * with every intermediate resident in HBM: frequencies -> pseudocount -> covariance ->
+ * -inverse -> FN (+APC) and optionally DI.  reg_fi_out [L][q], couplings_out [n][n],
+ * fn_apc_out, di_out and stage_ms_out may be NULL.  stage_ms_out[5] = CUDA-event ms of
+ * {pair frequencies (incl. H2D), covariance, inverse, FN, DI}. */
+int dca_mf_scores(const uint8_t *msa, const double *weights, long num_seqs, int seqs_len,
+                  int num_site_states, double pseudocount, double *reg_fi_out,
+                  double *couplings_out, double *fn_out, double *fn_apc_out, double *di_out,
+                  float *stage_ms_out);
 /* construct_corr_mat on caller-supplied regularised frequencies (:271-318):
  * reg_fi double[L][q], reg_fij double[L(L-1)/2][q-1][q-1] -> corr_out n x n. */
 int dca_mf_corr_from_freqs(const double *reg_fi, const double *reg_fij, int seqs_len,

@@ -91,6 +91,8 @@ def lib():
                                   _f64p, _f64p]
     L.dca_mf_couplings.argtypes = [_f64p, ctypes.c_int, _f64p]
     L.dca_mf_fn_apc.argtypes = [_f64p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
+    L.dca_mf_scores.argtypes = [_u8p, _f64p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                _f64p, _f64p, _f64p, _f64p, _f64p, _f32p]
     L.dca_mf_corr_from_freqs.argtypes = [_f64p, _f64p, ctypes.c_int, ctypes.c_int, _f64p]
     L.dca_mf_direct_info.argtypes = [_f64p, _f64p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
     L.dca_plm_direct_info.argtypes = [_f32p, _f64p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]

@@ -67,6 +67,8 @@ int mf_corr_mat_host(const uint8_t *msa, const double *w, long N, int L, int q, 
 int mf_couplings_host(const double *corr, int n, double *out);
 int mf_fn_apc_host(const double *h_J, int L, int q, double *fn, double *fn_apc);
 int mf_corr_from_freqs_host(const double *reg_fi, const double *reg_fij, int L, int q, double *corr);
+int mf_scores_host(const uint8_t *msa, const double *w, long N, int L, int q, double pseudocount,
+                   double *reg_fi, double *couplings, double *fn, double *fn_apc, double *di, float *stage_ms);
 // scoring.cu
 int plm_di_host(const float *h_x, const double *h_reg_fi, int L, int q, double *di, double *fields);
 int mf_di_host(const double *h_J, const double *h_reg_fi, int L, int q, double *di, double *fields);
@@ -354,6 +356,15 @@ int dca_mf_fn_apc(const double *couplings, int seqs_len, int num_site_states, do
 {
     if (!couplings || !fn_out) { set_error("dca_mf_fn_apc: null argument"); return -1; }
     return mf_fn_apc_host(couplings, seqs_len, num_site_states, fn_out, fn_apc_out);
+}
+
+int dca_mf_scores(const uint8_t *msa, const double *weights, long num_seqs, int seqs_len, int num_site_states,
+                  double pseudocount, double *reg_fi_out, double *couplings_out, double *fn_out,
+                  double *fn_apc_out, double *di_out, float *stage_ms_out)
+{
+    if (!msa || !weights || !fn_out) { set_error("dca_mf_scores: null argument"); return -1; }
+    return mf_scores_host(msa, weights, num_seqs, seqs_len, num_site_states, pseudocount, reg_fi_out,
+                          couplings_out, fn_out, fn_apc_out, di_out, stage_ms_out);
 }
 
 int dca_mf_corr_from_freqs(const double *reg_fi, const double *reg_fij, int seqs_len, int num_site_states,

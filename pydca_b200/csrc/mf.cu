@@ -118,16 +118,26 @@ mf_pairfreq_kernel(const uint8_t *__restrict__ msa, const double *__restrict__ w
             const uint8_t *rec = recs + ((size_t)buf * MF_WARPS + warp) * MF_PERM_REC;
             const uint32_t *pw = reinterpret_cast<const uint32_t *>(rec + MF_PERM_CNT);
             const double *Rb = Rs + (size_t)buf * MF_CH * MF_TC + 2 * lane;
+            uint32_t cur = pw[0];
+            int pos = 0;
 #pragma unroll
             for (int b = 0; b < Q; ++b) {
-                const int m = rec[b];
+                const unsigned m = rec[b];
                 double2 a = acc[b];
-                for (int k = 0; k < m; k += 4) {
-                    const uint32_t w4 = *pw++;
-                    { const double2 v = *reinterpret_cast<const double2 *>(Rb + (w4 & 0xffu) * MF_TC); a.x += v.x; a.y += v.y; }
-                    if (k + 1 < m) { const double2 v = *reinterpret_cast<const double2 *>(Rb + ((w4 >> 8) & 0xffu) * MF_TC); a.x += v.x; a.y += v.y; }
-                    if (k + 2 < m) { const double2 v = *reinterpret_cast<const double2 *>(Rb + ((w4 >> 16) & 0xffu) * MF_TC); a.x += v.x; a.y += v.y; }
-                    if (k + 3 < m) { const double2 v = *reinterpret_cast<const double2 *>(Rb + (w4 >> 24) * MF_TC); a.x += v.x; a.y += v.y; }
+                const unsigned nq = (m + 3u) >> 2;
+                // compact, not unrolled: 21 copies must fit the instruction cache (see plm_scatter_kernel)
+#pragma unroll 1
+                for (unsigned t = 0; t < nq; ++t) {
+                    const uint32_t w4 = cur;
+                    cur = pw[++pos];
+                    const unsigned rem = m - 4u * t;
+                    const double2 z2 = make_double2(0.0, 0.0);
+                    const double2 v0 = *reinterpret_cast<const double2 *>(Rb + (w4 & 0xffu) * MF_TC);
+                    const double2 v1 = (rem > 1u) ? *reinterpret_cast<const double2 *>(Rb + ((w4 >> 8) & 0xffu) * MF_TC) : z2;
+                    const double2 v2 = (rem > 2u) ? *reinterpret_cast<const double2 *>(Rb + ((w4 >> 16) & 0xffu) * MF_TC) : z2;
+                    const double2 v3 = (rem > 3u) ? *reinterpret_cast<const double2 *>(Rb + (w4 >> 24) * MF_TC) : z2;
+                    a.x += (v0.x + v1.x) + (v2.x + v3.x);
+                    a.y += (v0.y + v1.y) + (v2.y + v3.y);
                 }
                 acc[b] = a;
             }
@@ -221,9 +231,11 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 
 __global__ void __launch_bounds__(256, 1)
 dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, int lda,
-                const double *__restrict__ B, int ldb, double alpha, double beta, int skip_rb)
+                const double *__restrict__ B, int ldb, double alpha, double beta, int skip_rb,
+                int skip_tr, int skip_tc)
 {
     if ((int)blockIdx.y == skip_rb) return;
+    if ((int)blockIdx.y == skip_tr && (int)blockIdx.x == skip_tc) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *As = reinterpret_cast<double *>(smem_raw);                 // [2][128][GM_AS]
     double *Bs = As + 2 * GJ_B * GM_AS;                                // [2][GM_KC][GM_BS]
@@ -354,36 +366,64 @@ __global__ void negate_copy_kernel(const double *__restrict__ A, int ld, int n, 
 }
 
 // d_A: npad x npad (row-major, ld = npad), overwritten by its inverse
+// Look-ahead schedule: the 128x128 diagonal inverse is a single-CTA, latency-bound kernel
+// (~0.33 ms); step k therefore updates tile (k+1,k+1) first, and a second stream inverts it
+// while the main stream finishes the rank-128 update of step k.
 static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
 {
     const int nb = npad / GJ_B;
-    double *d_Dinv = nullptr, *d_Ck = nullptr, *d_Rk = nullptr;
+    double *d_Dinv[2] = {nullptr, nullptr}, *d_Ck = nullptr, *d_Rk = nullptr;
     int *d_info = nullptr;
-    DCA_CUDA(cudaMalloc(&d_Dinv, sizeof(double) * GJ_B * GJ_B));
-    DCA_CUDA(cudaMalloc(&d_Ck, sizeof(double) * (size_t)npad * GJ_B));
-    DCA_CUDA(cudaMalloc(&d_Rk, sizeof(double) * (size_t)npad * GJ_B));
-    DCA_CUDA(cudaMalloc(&d_info, sizeof(int)));
+    if (!dev_alloc_t(&d_Dinv[0], (size_t)GJ_B * GJ_B) || !dev_alloc_t(&d_Dinv[1], (size_t)GJ_B * GJ_B) ||
+        !dev_alloc_t(&d_Ck, (size_t)npad * GJ_B) || !dev_alloc_t(&d_Rk, (size_t)npad * GJ_B) ||
+        !dev_alloc_t(&d_info, (size_t)1))
+        return -1;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_tile = nullptr, ev_diag = nullptr;
+    {   // highest priority: its single CTA must get an SM while the big update is still queued
+        int prio_lo = 0, prio_hi = 0;
+        DCA_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        DCA_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
+    }
+    DCA_CUDA(cudaEventCreateWithFlags(&ev_tile, cudaEventDisableTiming));
+    DCA_CUDA(cudaEventCreateWithFlags(&ev_diag, cudaEventDisableTiming));
     DCA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
     const size_t smem_gemm = sizeof(double) * (2 * GJ_B * GM_AS + 2 * GM_KC * GM_BS);
     const size_t smem_diag = sizeof(double) * (GJ_B * (GJ_B + 1) + GJ_B);
     DCA_CUDA(cudaFuncSetAttribute(dgemm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
     DCA_CUDA(cudaFuncSetAttribute(gj_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag));
+    DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, st, d_A, npad, 0, d_Dinv[0], d_info);
     for (int k = 0; k < nb; ++k) {
-        DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, st, d_A, npad, k, d_Dinv, d_info);
+        double *Dk = d_Dinv[k & 1];
+        if (k > 0) DCA_CUDA(cudaStreamWaitEvent(st, ev_diag, 0));          // Dinv_k from the side stream
         DCA_LAUNCH(gj_split_col_kernel, (unsigned)ceil_div<long>((long)npad * GJ_B, 256), 256, 0, st, d_A, npad, npad, k, d_Ck);
         // Rk (128 x npad) = Dinv (128x128) * A[kblock rows, :]
         DCA_LAUNCH(dgemm128_kernel, dim3(nb, 1), 256, smem_gemm, st,
-                   d_Rk, npad, d_Dinv, GJ_B, d_A + (size_t)k * GJ_B * npad, npad, 1.0, 0.0, -1);
-        // A[i,:] -= Ck[i] * Rk for every row block i != k
+                   d_Rk, npad, Dk, GJ_B, d_A + (size_t)k * GJ_B * npad, npad, 1.0, 0.0, -1, -1, -1);
+        int skr = -1;
+        if (k + 1 < nb) {
+            // tile (k+1,k+1) first, then its inverse on the side stream
+            skr = k + 1;
+            const size_t off = (size_t)(k + 1) * GJ_B;
+            DCA_LAUNCH(dgemm128_kernel, dim3(1, 1), 256, smem_gemm, st,
+                       d_A + off * npad + off, npad, d_Ck + off * GJ_B, GJ_B, d_Rk + off, npad, -1.0, 1.0, -1, -1, -1);
+            DCA_CUDA(cudaEventRecord(ev_tile, st));
+            DCA_CUDA(cudaStreamWaitEvent(side, ev_tile, 0));
+            DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, side, d_A, npad, k + 1, d_Dinv[(k + 1) & 1], d_info);
+            DCA_CUDA(cudaEventRecord(ev_diag, side));
+        }
+        // A[i,:] -= Ck[i] * Rk for every row block i != k (tile (k+1,k+1) already done)
         DCA_LAUNCH(dgemm128_kernel, dim3(nb, nb), 256, smem_gemm, st,
-                   d_A, npad, d_Ck, GJ_B, d_Rk, npad, -1.0, 1.0, k);
+                   d_A, npad, d_Ck, GJ_B, d_Rk, npad, -1.0, 1.0, k, skr, skr);
         DCA_CUDA(cudaMemcpyAsync(d_A + (size_t)k * GJ_B * npad, d_Rk, sizeof(double) * (size_t)GJ_B * npad,
                                  cudaMemcpyDeviceToDevice, st));
     }
     int info = 0;
     DCA_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
     DCA_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_Dinv); cudaFree(d_Ck); cudaFree(d_Rk); cudaFree(d_info);
+    DCA_CUDA(cudaStreamSynchronize(side));
+    cudaStreamDestroy(side); cudaEventDestroy(ev_tile); cudaEventDestroy(ev_diag);
+    dev_free(d_Dinv[0]); dev_free(d_Dinv[1]); dev_free(d_Ck); dev_free(d_Rk); dev_free(d_info);
     if (info != 0) { set_error("mf_couplings: zero pivot at row %d: the correlation matrix is singular (increase the pseudocount)", info - 1); return -1; }
     return 0;
 }
@@ -395,7 +435,7 @@ struct MfWork {
     int ld = 0, nsplit = 1, cps = 0, nchunk = 0;
     size_t fstride = 0;
     double meff = 0.0;
-    ~MfWork() { cudaFree(d_msa); cudaFree(d_perm); cudaFree(d_w); cudaFree(d_F); cudaFree(d_fi); cudaFree(d_rfi); }
+    ~MfWork() { cudaDeviceSynchronize(); dev_free(d_msa); dev_free(d_perm); dev_free(d_w); dev_free(d_F); dev_free(d_fi); dev_free(d_rfi); }
 };
 
 template <int Q>
@@ -404,7 +444,7 @@ static int mf_pairfreq_t(MfWork &W, long N, int L)
     const long total = (long)L * W.nchunk;
     DCA_CUDA(cudaMemset(W.d_perm, 0, (size_t)total * MF_PERM_REC));
     DCA_LAUNCH((mf_build_perm_kernel<Q>), (unsigned)ceil_div<long>(total, 128), 128, 0, 0, W.d_msa, N, L, W.nchunk, W.d_perm);
-    const size_t smem = sizeof(double) * 2 * MF_CH * MF_TC + 2 * MF_WARPS * MF_PERM_REC;
+    const size_t smem = sizeof(double) * 2 * MF_CH * MF_TC + 2 * MF_WARPS * MF_PERM_REC + 16;   // +16: prefetched word
     DCA_CUDA(cudaFuncSetAttribute(mf_pairfreq_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(W.ld / MF_TC, ceil_div(L, MF_WARPS), W.nsplit);
     DCA_LAUNCH((mf_pairfreq_kernel<Q>), grid, MF_WARPS * 32, smem, 0,
@@ -432,12 +472,11 @@ static int mf_prepare(MfWork &W, const uint8_t *msa, const double *w, long N, in
     double m = 0.0;
     for (long n = 0; n < N; ++n) m += w[n];
     W.meff = m;
-    DCA_CUDA(cudaMalloc(&W.d_msa, (size_t)N * L));
-    DCA_CUDA(cudaMalloc(&W.d_w, sizeof(double) * (size_t)N));
-    DCA_CUDA(cudaMalloc(&W.d_perm, (size_t)L * W.nchunk * MF_PERM_REC));
-    DCA_CUDA(cudaMalloc(&W.d_F, sizeof(double) * W.fstride * W.nsplit));
-    DCA_CUDA(cudaMalloc(&W.d_fi, sizeof(double) * (size_t)Lq));
-    DCA_CUDA(cudaMalloc(&W.d_rfi, sizeof(double) * (size_t)Lq));
+    if (!dev_alloc_t(&W.d_msa, (size_t)N * L) || !dev_alloc_t(&W.d_w, (size_t)N) ||
+        !dev_alloc_t(&W.d_perm, (size_t)L * W.nchunk * MF_PERM_REC) ||
+        !dev_alloc_t(&W.d_F, W.fstride * W.nsplit) || !dev_alloc_t(&W.d_fi, (size_t)Lq) ||
+        !dev_alloc_t(&W.d_rfi, (size_t)Lq))
+        return -1;
     DCA_CUDA(cudaMemcpy(W.d_msa, msa, (size_t)N * L, cudaMemcpyHostToDevice));
     DCA_CUDA(cudaMemcpy(W.d_w, w, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice));
     return (q == 21) ? mf_pairfreq_t<21>(W, N, L) : mf_pairfreq_t<5>(W, N, L);
@@ -471,7 +510,7 @@ static int mf_corr_device(MfWork &W, int L, int q, double pseudocount, double **
     const int npad = ceil_div(n, GJ_B) * GJ_B;
     DCA_LAUNCH(mf_single_kernel, ceil_div(Lq, 128), 128, 0, 0, W.d_F, W.fstride, W.nsplit, L, q, W.ld, W.meff,
                pseudocount, W.d_fi, W.d_rfi);
-    DCA_CUDA(cudaMalloc(d_C, sizeof(double) * (size_t)npad * npad));
+    if (!dev_alloc_t(d_C, (size_t)npad * npad)) return -1;
     dim3 grid(ceil_div(npad, 256), npad);
     DCA_LAUNCH(mf_corr_kernel, grid, 256, 0, 0, W.d_F, W.fstride, W.nsplit, W.d_rfi, L, q, W.ld, W.meff,
                pseudocount, n, npad, *d_C);
@@ -487,13 +526,13 @@ int mf_corr_mat_host(const uint8_t *msa, const double *w, long N, int L, int q, 
     if (mf_prepare(W, msa, w, N, L, q) != 0) return -1;
     double *d_C = nullptr;
     int npad = 0;
-    if (mf_corr_device(W, L, q, pseudocount, &d_C, &npad) != 0) { cudaFree(d_C); return -1; }
+    if (mf_corr_device(W, L, q, pseudocount, &d_C, &npad) != 0) { dev_free(d_C); return -1; }
     const int n = L * (q - 1);
     cudaError_t e = cudaMemcpy2D(corr, sizeof(double) * (size_t)n, d_C, sizeof(double) * (size_t)npad,
                                  sizeof(double) * (size_t)n, (size_t)n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && reg_fi)
         e = cudaMemcpy(reg_fi, W.d_rfi, sizeof(double) * (size_t)L * q, cudaMemcpyDeviceToHost);
-    cudaFree(d_C);
+    dev_free(d_C);
     if (e != cudaSuccess) { set_error("mf_corr_mat: D2H failed: %s", cudaGetErrorString(e)); return -1; }
     return 0;
 }
@@ -537,6 +576,70 @@ int mf_corr_from_freqs_host(const double *reg_fi, const double *reg_fij, int L, 
     DCA_CUDA(cudaMemcpy(corr, d_C, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
     cudaFree(d_fi); cudaFree(d_fij); cudaFree(d_C);
     return 0;
+}
+
+// scoring.cu
+int fn_matrix_device(const double *d_J, long ldm, int L, int q, double *d_fn, cudaStream_t st);
+int di_matrix_device(const double *d_J, long ldm, const double *d_rfi, int L, int q, double *d_di, cudaStream_t st);
+void apc_host(const double *fn, int L, double *out);
+
+__global__ void negate_inplace_kernel(double *__restrict__ A, long count)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < count) A[idx] = -1.0 * A[idx];
+}
+
+// The whole mean-field pipeline with every intermediate resident in HBM
+// (meanfield_dca.py:902-988 end to end): MSA + weights in, scores out.  Optional
+// outputs: reg_fi [L][q], couplings [n][n], di [pairs]; stage_ms[5] = pair
+// frequencies, covariance assembly, inverse, FN, DI (CUDA events).
+int mf_scores_host(const uint8_t *msa, const double *w, long N, int L, int q, double pseudocount,
+                   double *reg_fi, double *couplings, double *fn, double *fn_apc, double *di, float *stage_ms)
+{
+    cudaEvent_t ev[6];
+    for (auto &e : ev) DCA_CUDA(cudaEventCreate(&e));
+    MfWork W;
+    DCA_CUDA(cudaEventRecord(ev[0], 0));
+    if (mf_prepare(W, msa, w, N, L, q) != 0) return -1;
+    DCA_CUDA(cudaEventRecord(ev[1], 0));
+    double *d_C = nullptr, *d_fn = nullptr, *d_di = nullptr;
+    int npad = 0;
+    int rc = mf_corr_device(W, L, q, pseudocount, &d_C, &npad);
+    DCA_CUDA(cudaEventRecord(ev[2], 0));
+    if (rc == 0) rc = gj_invert_device(d_C, npad, 0);
+    const int n = L * (q - 1);
+    const long npairs = (long)L * (L - 1) / 2;
+    if (rc == 0) {
+        DCA_LAUNCH(negate_inplace_kernel, (unsigned)ceil_div<long>((long)npad * npad, 256), 256, 0, 0, d_C, (long)npad * npad);
+        DCA_CUDA(cudaEventRecord(ev[3], 0));
+        if (!dev_alloc_t(&d_fn, (size_t)npairs)) rc = -1;
+    }
+    if (rc == 0) rc = fn_matrix_device(d_C, npad, L, q, d_fn, 0);
+    if (rc == 0) {
+        DCA_CUDA(cudaEventRecord(ev[4], 0));
+        if (di) {
+            if (!dev_alloc_t(&d_di, (size_t)npairs)) rc = -1;
+            if (rc == 0) rc = di_matrix_device(d_C, npad, W.d_rfi, L, q, d_di, 0);
+        }
+    }
+    if (rc == 0) {
+        DCA_CUDA(cudaEventRecord(ev[5], 0));
+        cudaError_t e = cudaMemcpy(fn, d_fn, sizeof(double) * (size_t)npairs, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && di) e = cudaMemcpy(di, d_di, sizeof(double) * (size_t)npairs, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && reg_fi) e = cudaMemcpy(reg_fi, W.d_rfi, sizeof(double) * (size_t)L * q, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && couplings)
+            e = cudaMemcpy2D(couplings, sizeof(double) * (size_t)n, d_C, sizeof(double) * (size_t)npad,
+                             sizeof(double) * (size_t)n, (size_t)n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error("mf_scores: D2H failed: %s", cudaGetErrorString(e)); rc = -1; }
+    }
+    if (rc == 0) {
+        if (fn_apc) apc_host(fn, L, fn_apc);
+        if (stage_ms) for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&stage_ms[k], ev[k], ev[k + 1]);
+    }
+    cudaDeviceSynchronize();
+    dev_free(d_C); dev_free(d_fn); dev_free(d_di);
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
 }
 
 int mf_couplings_host(const double *corr, int n, double *out)

@@ -85,6 +85,8 @@ struct PlmProblem {
     int col_tile0 = 0, col_tiles = 0;
     int site_tiles = 0, sites_per_tile = 0;
     CUtensorMap tmS;         // S as [Npad][ld] f32, box 128 x 128 (scatter tiles)
+    CUtensorMap tmW;         // W as [Lq][ld] f32, box 128 x JB*q (logits stage)
+    CUtensorMap tmM;         // msaT as [L][Npad] u8, box 128 x JB (logits stage)
 };
 
 // ------------------------------------------------------------------------------
@@ -174,20 +176,38 @@ plm_unpack_kernel(const float *__restrict__ x, int L, int ld, float *__restrict_
 
 // ------------------------------------------------------------------------------
 // logits: S[n][col] = h[col] + sum_j W[j*Q + s_nj][col]
+// CTA = 128 columns x 128 sequences (8 warps x 16 sequences, lane = 4 columns), two
+// CTAs per SM.  Per stage the TMA engine fetches two 2-D tiles through tensor maps --
+// the W rows of JB sites (JB*Q x 128 f32) and their residues (JB x 128 u8) -- into a
+// two-deep ring guarded by mbarriers (full: transaction bytes, empty: one arrival per
+// warp); warps are decoupled, there is no block-wide barrier in the loop.  Rows beyond
+// L (last stage) are zero-filled by the hardware: residue 0 then selects a zero row.
+// Inner loop: one 16-byte load brings a warp's 16 residues, then one conflict-free
+// LDS.128 (a 512-byte row segment per warp) per 4 adds.
 template <int Q>
 __global__ void __launch_bounds__(LG_THREADS, 2)
-plm_logits_kernel(const float *__restrict__ W, int ld, const uint8_t *__restrict__ msaT, long Npad,
-                  long N, int L, const float *__restrict__ x, float *__restrict__ S, int col_tile0)
+plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmM,
+                  int ld, long N, int L, const float *__restrict__ x, float *__restrict__ S, int col_tile0)
 {
     constexpr int JB = LgCfg<Q>::JB;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NWARP = LG_THREADS / 32;
+    constexpr unsigned STAGE_BYTES = JB * Q * LG_TC * 4 + JB * LG_TN;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     float *Wt = reinterpret_cast<float *>(smem_raw);                       // [2][JB*Q][128]
-    uint8_t *Mt = smem_raw + sizeof(float) * 2 * JB * Q * LG_TC;           // [2][JB][256]
+    uint8_t *Mt = smem_raw + sizeof(float) * 2 * JB * Q * LG_TC;           // [2][JB][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Mt + 2 * JB * LG_TN);    // full[2], empty[2]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = (col_tile0 + blockIdx.x) * LG_TC;
     const long n0 = (long)blockIdx.y * LG_TN;
     const int Lq = L * Q;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], NWARP); mbar_init(&bars[3], NWARP);
+        mbar_fence_init();
+    }
+    __syncthreads();
 
     float4 acc[16];
     {
@@ -201,49 +221,43 @@ plm_logits_kernel(const float *__restrict__ W, int ld, const uint8_t *__restrict
         for (int t = 0; t < 16; ++t) acc[t] = h;
     }
 
-    auto stage = [&](int buf, int j0) {
-        const int rows = min(JB, L - j0) * Q;
-        float *dstW = Wt + (size_t)buf * JB * Q * LG_TC;
-        const float *srcW = W + (size_t)j0 * Q * ld + col0;
-        for (int t = tid; t < rows * 32; t += LG_THREADS) {
-            const int row = t >> 5, c4 = t & 31;
-            cp_async16(dstW + row * LG_TC + 4 * c4, srcW + (size_t)row * ld + 4 * c4);
+    auto issue = [&](int buf, int st) {
+        if (lane == 0) {
+            mbar_expect_tx(&bars[buf], STAGE_BYTES);
+            tma_load_2d(Wt + (size_t)buf * JB * Q * LG_TC, &tmW, col0, st * JB * Q, &bars[buf]);
+            tma_load_2d(Mt + (size_t)buf * JB * LG_TN, &tmM, (int)n0, st * JB, &bars[buf]);
         }
-        const int nj = min(JB, L - j0);
-        uint8_t *dstM = Mt + (size_t)buf * JB * LG_TN;
-        constexpr int SEGS = LG_TN / 16;
-        for (int t = tid; t < nj * SEGS; t += LG_THREADS) {
-            const int jj = t / SEGS, seg = t - jj * SEGS;
-            cp_async16(dstM + jj * LG_TN + seg * 16, msaT + (size_t)(j0 + jj) * Npad + n0 + seg * 16);
-        }
-        cp_async_commit();
+        __syncwarp();
     };
 
     const int nstage = (L + JB - 1) / JB;
-    stage(0, 0);
+    if (warp == 0) issue(0, 0);
+    if (warp == 1 && nstage > 1) issue(1, 1);
+
     for (int st = 0; st < nstage; ++st) {
         const int buf = st & 1;
-        if (st + 1 < nstage) { stage(buf ^ 1, (st + 1) * JB); cp_async_wait<1>(); }
-        else                 { cp_async_wait<0>(); }
-        __syncthreads();
-        const int nj = min(JB, L - st * JB);
+        const unsigned parity = (unsigned)(st >> 1) & 1u;
+        mbar_wait(&bars[buf], parity);
         const float *Wb = Wt + (size_t)buf * JB * Q * LG_TC + 4 * lane;
         const uint8_t *Mb = Mt + (size_t)buf * JB * LG_TN + warp * 16;
 #pragma unroll
         for (int jj = 0; jj < JB; ++jj) {
-            if (jj < nj) {
-                const uint4 r16 = *reinterpret_cast<const uint4 *>(Mb + jj * LG_TN);
-                const float *Wj = Wb + jj * Q * LG_TC;
-                const unsigned rr[4] = {r16.x, r16.y, r16.z, r16.w};
+            const uint4 r16 = *reinterpret_cast<const uint4 *>(Mb + jj * LG_TN);
+            const float *Wj = Wb + jj * Q * LG_TC;
+            const unsigned rr[4] = {r16.x, r16.y, r16.z, r16.w};
 #pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    const unsigned b = (rr[t >> 2] >> (8 * (t & 3))) & 0xffu;
-                    const float4 v = *reinterpret_cast<const float4 *>(Wj + b * LG_TC);
-                    acc[t].x += v.x; acc[t].y += v.y; acc[t].z += v.z; acc[t].w += v.w;
-                }
+            for (int t = 0; t < 16; ++t) {
+                const unsigned b = (rr[t >> 2] >> (8 * (t & 3))) & 0xffu;
+                const float4 v = *reinterpret_cast<const float4 *>(Wj + b * LG_TC);
+                acc[t].x += v.x; acc[t].y += v.y; acc[t].z += v.z; acc[t].w += v.w;
             }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[2 + buf]);
+        if (st + 2 < nstage && warp == (st + 2) % NWARP) {
+            mbar_wait(&bars[2 + buf], parity);
+            issue(buf, st + 2);
+        }
     }
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
@@ -630,7 +644,7 @@ static int plm_setup_t(PlmProblem *p)
         DCA_LAUNCH((build_perm_kernel<Q>), (unsigned)ceil_div<long>(total, 128), 128, 0, st,
                    p->d_msaT, p->N, p->Npad, p->L, p->nchunk, p->sites_per_tile, p->d_perm);
     }
-    const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN;
+    const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN + 64 + 1024;
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
     DCA_CUDA(cudaFuncSetAttribute(plm_logits_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     DCA_CUDA(cudaFuncSetAttribute(plm_scatter_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
@@ -651,10 +665,10 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
     DCA_LAUNCH((plm_unpack_kernel<Q>), gridU, 256, 0, st, d_x, L, ld, p->d_W);
     PLM_MARK();
 
-    const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN;
+    const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN + 64 + 1024;
     dim3 gridA(p->col_tiles, (unsigned)(p->Npad / LG_TN));
     DCA_LAUNCH((plm_logits_kernel<Q>), gridA, LG_THREADS, smemA, st,
-               p->d_W, ld, p->d_msaT, p->Npad, p->N, L, d_x, p->d_S, p->col_tile0);
+               p->tmW, p->tmM, ld, p->N, L, d_x, p->d_S, p->col_tile0);
     PLM_MARK();
 
     const int nsites = p->site_hi - p->site_lo;
@@ -748,6 +762,8 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     float meff = 0.f;
     for (long n = 0; n < N; ++n) meff += h_w[n];     // plmdca_numerics.cpp:46
     p->h_meff = meff;
+    // the carry scan is latency bound on small problems: shorter chains = more of them
+    if ((long)L * (N / 32) < 50000) p->chunk = 16;
     plm_plan_scan(p);
 
 #define PLM_TRY(call)                                                                 \
@@ -782,6 +798,13 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     PLM_TRY(cudaMemsetAsync(p->d_fxpart, 0, sizeof(double) * (size_t)(N / 8 + 1) * L, p->stream));
     if (make_tensor_map_2d(&p->tmS, 4, p->d_S, (unsigned long long)p->ld, (unsigned long long)p->Npad,
                            sizeof(float) * (unsigned long long)p->ld, SC_TC, SC_CH) != 0) { plm_free(p); return nullptr; }
+    {
+        const unsigned jb = (q > 8) ? 4 : 16;         // LgCfg<Q>::JB
+        if (make_tensor_map_2d(&p->tmW, 4, p->d_W, (unsigned long long)p->ld, (unsigned long long)p->Lq,
+                               sizeof(float) * (unsigned long long)p->ld, LG_TC, jb * (unsigned)q) != 0 ||
+            make_tensor_map_2d(&p->tmM, 1, p->d_msaT, (unsigned long long)p->Npad, (unsigned long long)L,
+                               (unsigned long long)p->Npad, LG_TN, jb) != 0) { plm_free(p); return nullptr; }
+    }
     const int rc = (q == 21) ? plm_setup_t<21>(p) : plm_setup_t<5>(p);
     if (rc != 0) { plm_free(p); return nullptr; }
     PLM_TRY(cudaStreamSynchronize(p->stream));

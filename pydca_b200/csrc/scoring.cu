@@ -24,7 +24,7 @@ constexpr int FN_WARPS = 4;
 // SRC = double: block at J[(i*(q-1)+a)*n + j*(q-1)+b], n=L(q-1) (mf layout)
 template <typename SRC>
 __global__ void __launch_bounds__(FN_WARPS * 32)
-fn_kernel(const SRC *__restrict__ src, int L, int q, int is_matrix, double *__restrict__ fn)
+fn_kernel(const SRC *__restrict__ src, int L, int q, int is_matrix, long ldm, double *__restrict__ fn)
 {
     extern __shared__ double sm[];
     const int qm1 = q - 1, nb = qm1 * qm1;
@@ -40,11 +40,10 @@ fn_kernel(const SRC *__restrict__ src, int L, int q, int is_matrix, double *__re
         long rem = pair;
         while (rem >= L - 1 - i) { rem -= L - 1 - i; ++i; }
         const int j = i + 1 + (int)rem;
-        const long n = (long)L * qm1;
         for (int t = lane; t < nb; t += 32) {
             const int a = t / qm1, b = t - a * qm1;
             double v;
-            if (is_matrix) v = (double)src[((long)i * qm1 + a) * n + (long)j * qm1 + b];
+            if (is_matrix) v = (double)src[((long)i * qm1 + a) * ldm + (long)j * qm1 + b];
             else v = (double)src[(long)L * q + pair * q * q + a * q + b];
             blk[t] = v;
         }
@@ -71,7 +70,7 @@ fn_kernel(const SRC *__restrict__ src, int L, int q, int is_matrix, double *__re
 }
 
 // APC on the host: s_ij - mean_i * mean_j / mean_all (plmdca.py:503-519)
-static void apc_host(const double *fn, int L, double *out)
+void apc_host(const double *fn, int L, double *out)
 {
     std::vector<double> site((size_t)L, 0.0);
     long k = 0;
@@ -100,7 +99,7 @@ static int fn_apc_impl(const SRC *h_src, size_t count, int L, int q, int is_matr
     const int qm1 = q - 1;
     const size_t smem = sizeof(double) * FN_WARPS * (size_t)(qm1 * qm1 + 2 * qm1);
     DCA_LAUNCH((fn_kernel<SRC>), (unsigned)ceil_div<long>(npairs, FN_WARPS), FN_WARPS * 32, smem, 0,
-               d_src, L, q, is_matrix, d_fn);
+               d_src, L, q, is_matrix, (long)L * (q - 1), d_fn);
     DCA_CUDA(cudaGetLastError());
     DCA_CUDA(cudaMemcpy(fn, d_fn, sizeof(double) * (size_t)npairs, cudaMemcpyDeviceToHost));
     cudaFree(d_src); cudaFree(d_fn);
@@ -119,7 +118,7 @@ constexpr int DI_WARPS = 4;
 
 template <typename SRC>
 __global__ void __launch_bounds__(DI_WARPS * 32)
-di_kernel(const SRC *__restrict__ src, const double *__restrict__ reg_fi, int L, int q, int is_matrix,
+di_kernel(const SRC *__restrict__ src, const double *__restrict__ reg_fi, int L, int q, int is_matrix, long ldm,
           double *__restrict__ di, double *__restrict__ fields)
 {
     extern __shared__ double sm[];
@@ -134,12 +133,11 @@ di_kernel(const SRC *__restrict__ src, const double *__restrict__ reg_fi, int L,
     long rem = pair;
     while (rem >= L - 1 - i) { rem -= L - 1 - i; ++i; }
     const int j = i + 1 + (int)rem;
-    const long n = (long)L * qm1;
     for (int t = lane; t < q * q; t += 32) {
         const int a = t / q, b = t - a * q;
         double v = 0.0;
         if (a < qm1 && b < qm1) {
-            if (is_matrix) v = (double)src[((long)i * qm1 + a) * n + (long)j * qm1 + b];
+            if (is_matrix) v = (double)src[((long)i * qm1 + a) * ldm + (long)j * qm1 + b];
             else v = (double)src[(long)L * q + pair * q * q + a * q + b];
         }
         Wm[t] = exp(v);
@@ -205,7 +203,7 @@ static int di_impl(const SRC *h_src, size_t count, const double *h_reg_fi, int L
     DCA_CUDA(cudaMemcpy(d_rfi, h_reg_fi, sizeof(double) * (size_t)L * q, cudaMemcpyHostToDevice));
     const size_t smem = sizeof(double) * DI_WARPS * (size_t)(q * q + 2 * q);
     DCA_LAUNCH((di_kernel<SRC>), (unsigned)ceil_div<long>(npairs, DI_WARPS), DI_WARPS * 32, smem, 0,
-               d_src, d_rfi, L, q, is_matrix, d_di, d_fields);
+               d_src, d_rfi, L, q, is_matrix, (long)L * (q - 1), d_di, d_fields);
     DCA_CUDA(cudaGetLastError());
     DCA_CUDA(cudaMemcpy(di, d_di, sizeof(double) * (size_t)npairs, cudaMemcpyDeviceToHost));
     if (fields) DCA_CUDA(cudaMemcpy(fields, d_fields, sizeof(double) * (size_t)npairs * 2 * q, cudaMemcpyDeviceToHost));
@@ -223,6 +221,29 @@ int mf_di_host(const double *h_J, const double *h_reg_fi, int L, int q, double *
 {
     const size_t n = (size_t)L * (q - 1);
     return di_impl<double>(h_J, n * n, h_reg_fi, L, q, 1, di, fields);
+}
+
+// device-resident variants used by the fused mean-field pipeline (mf.cu): J is a
+// row-major matrix with leading dimension ldm on the device
+int fn_matrix_device(const double *d_J, long ldm, int L, int q, double *d_fn, cudaStream_t st)
+{
+    const long npairs = (long)L * (L - 1) / 2;
+    const int qm1 = q - 1;
+    const size_t smem = sizeof(double) * FN_WARPS * (size_t)(qm1 * qm1 + 2 * qm1);
+    DCA_LAUNCH((fn_kernel<double>), (unsigned)ceil_div<long>(npairs, FN_WARPS), FN_WARPS * 32, smem, st,
+               d_J, L, q, 1, ldm, d_fn);
+    DCA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int di_matrix_device(const double *d_J, long ldm, const double *d_rfi, int L, int q, double *d_di, cudaStream_t st)
+{
+    const long npairs = (long)L * (L - 1) / 2;
+    const size_t smem = sizeof(double) * DI_WARPS * (size_t)(q * q + 2 * q);
+    DCA_LAUNCH((di_kernel<double>), (unsigned)ceil_div<long>(npairs, DI_WARPS), DI_WARPS * 32, smem, st,
+               d_J, d_rfi, L, q, 1, ldm, d_di, (double *)nullptr);
+    DCA_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int plm_fn_apc_host(const float *h_x, int L, int q, double *fn, double *fn_apc)

@@ -63,6 +63,10 @@ class MeanFieldDCA:
         self.__effective_num_sequences = np.sum(self.__sequences_weight)
         self.__couplings = None
         self.__refseq_mapping_dict = None
+        #: keep the n x n couplings matrix on the host after scoring (needed by compute_params;
+        #: set False to skip the 8 n^2-byte D2H when only scores are wanted)
+        self.keep_couplings = True
+        self.last_stage_ms = None
         logger.info("Created a MeanFieldDCA object: %s, q %d, pseudocount %s, seqid %s, L %d, N %d, Meff %s",
                     biomolecule, self.__num_site_states, self.__pseudocount, self.__seqid,
                     self.__sequences_len, self.__num_sequences, self.__effective_num_sequences)
@@ -209,11 +213,11 @@ class MeanFieldDCA:
 
     def get_site_pair_di_score(self):
         """meanfield_dca.py:793-830 -> {(i, j): DI}."""
-        reg_fi, couplings = self._reg_fi_and_couplings()
         logger.info("\n\tComputing direct information")
-        di = msa_numerics.compute_direct_info(couplings=couplings, fields_ij=None, reg_fi=reg_fi,
-                                              seqs_len=self.__sequences_len,
-                                              num_site_states=self.__num_site_states)
+        res = msa_numerics.mean_field_scores(self.__msa0, self.__num_site_states, self.__sequences_weight,
+                                             self.__pseudocount, want_couplings=True, want_di=True)
+        self.__couplings = res["couplings"]
+        di = res["di"]
         iu, ju = np.triu_indices(self.__sequences_len, k=1)
         return {(int(i), int(j)): s for i, j, s in zip(iu, ju, di.tolist())}
 
@@ -234,9 +238,12 @@ class MeanFieldDCA:
 
     def compute_sorted_FN(self, seqbackmapper=None):
         """meanfield_dca.py:902-943."""
-        _, couplings = self._reg_fi_and_couplings()
         logger.info("\n\tComputing Frobenius norm of couplings")
-        fn, _ = msa_numerics.frobenius_norm_scores(couplings, self.__sequences_len, self.__num_site_states)
+        res = msa_numerics.mean_field_scores(self.__msa0, self.__num_site_states, self.__sequences_weight,
+                                             self.__pseudocount, want_couplings=self.keep_couplings)
+        self.__couplings = res.get("couplings")
+        self.last_stage_ms = res["stage_ms"]
+        fn = res["fn"]
         fn_sorted = _sorted_pairs(fn, self.__sequences_len)
         if seqbackmapper is not None:
             fn_sorted = self.get_mapped_site_pairs_dca_scores(fn_sorted, seqbackmapper)

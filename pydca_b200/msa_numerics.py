@@ -17,7 +17,7 @@ from ._lib import _f32p, _f64p, _u8p, check, lib, ptr
 __all__ = ["compute_sequences_weight", "compute_single_site_freqs", "get_reg_single_site_freqs",
            "compute_pair_site_freqs", "get_reg_pair_site_freqs", "construct_corr_mat",
            "compute_couplings", "compute_two_site_model_fields", "compute_direct_info",
-           "corr_mat_from_alignment", "frobenius_norm_scores"]
+           "corr_mat_from_alignment", "frobenius_norm_scores", "mean_field_scores"]
 
 
 def _zero_based(alignment_data, num_site_states=None):
@@ -137,6 +137,31 @@ def corr_mat_from_alignment(msa_zero_based, num_site_states, seqs_weight, pseudo
     check(lib().dca_mf_corr_mat(ptr(msa, _u8p), ptr(w, _f64p), n, l, q, float(pseudocount),
                                 ptr(rfi, _f64p), ptr(corr, _f64p)), "dca_mf_corr_mat")
     return rfi, corr
+
+
+def mean_field_scores(msa_zero_based, num_site_states, seqs_weight, pseudocount, want_couplings=False,
+                      want_di=False):
+    """The whole pipeline in one device-resident pass (dca_mf_scores).  Returns a dict with
+    reg_fi, fn, fn_apc, stage_ms and, on request, couplings and di."""
+    msa = np.ascontiguousarray(msa_zero_based, dtype=np.uint8)
+    n, l = msa.shape
+    q = int(num_site_states)
+    w = np.ascontiguousarray(seqs_weight, dtype=np.float64)
+    npairs = l * (l - 1) // 2
+    dim = l * (q - 1)
+    out = {"reg_fi": np.zeros((l, q)), "fn": np.zeros(npairs), "fn_apc": np.zeros(npairs),
+           "stage_ms": np.zeros(5, dtype=np.float32)}
+    if want_couplings:
+        out["couplings"] = np.zeros((dim, dim))
+    if want_di:
+        out["di"] = np.zeros(npairs)
+    check(lib().dca_mf_scores(ptr(msa, _u8p), ptr(w, _f64p), n, l, q, float(pseudocount),
+                              ptr(out["reg_fi"], _f64p),
+                              ptr(out["couplings"], _f64p) if want_couplings else None,
+                              ptr(out["fn"], _f64p), ptr(out["fn_apc"], _f64p),
+                              ptr(out["di"], _f64p) if want_di else None,
+                              ptr(out["stage_ms"], _f32p)), "dca_mf_scores")
+    return out
 
 
 def frobenius_norm_scores(couplings, seqs_len, num_site_states):

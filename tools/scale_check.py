@@ -30,6 +30,13 @@ def mf_c3(N=20000, L=300, q=21):
         t = tic(); fn, apc = mfn.frobenius_norm_scores(J, L, q); t_f = tic() - t
         print("[mf C3 N=%d L=%d] rep %d weights %.3fs corr(+D2H %d MB) %.3fs inverse(+H2D/D2H) %.3fs fn %.3fs  total %.3fs"
               % (N, L, rep, t_w, corr.nbytes >> 20, t_c, t_i, t_f, t_w + t_c + t_i + t_f))
+    for rep in range(3):
+        t = tic()
+        res = mfn.mean_field_scores(msa, q, w, 0.5, want_couplings=False, want_di=(rep == 2))
+        dt = tic() - t
+        print("[mf C3 fused] rep %d wall %.3fs  stage ms {pairfreq+H2D, corr, inverse, fn, di} = %s  => %.0f site-pairs/s"
+              % (rep, dt, np.round(res["stage_ms"], 2).tolist(), L * (L - 1) / 2 / dt))
+    print("   fused FN == staged FN: max rel diff %.2e" % (np.abs(res["fn"] - fn).max() / fn.max()))
     n = corr.shape[0]
     rng = np.random.default_rng(0)
     v = rng.normal(size=(n, 4))
