@@ -243,12 +243,14 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         counts = dd.sharded_counts(msa, SEQID, device=torch.device("cuda", local_rank))
         sites = dd.shard_range(SEQ_LEN, rank, world)
-        cb = dd.make_allreduce_callback()
+        cb = None  # set after the objective exists
     else:
         counts = _lib.sequence_counts(msa, SEQID)
         sites, cb = None, None
     w = (1.0 / counts.astype(np.float32)).astype(np.float32)
     obj = _lib.PlmObjective(msa, w, Q, lam, lam, sites=sites)
+    if world > 1:
+        cb = dd.make_allreduce_callback(obj.cuda_stream())
     x0 = obj.init()
 
     def barrier():
@@ -308,7 +310,8 @@ def run_ours(args, rank, world, local_rank):
         c2 = dd.sharded_counts(msa, SEQID, device=torch.device("cuda", local_rank))
         w2 = (1.0 / c2.astype(np.float32)).astype(np.float32)
         o2 = _lib.PlmObjective(msa, w2, Q, lam, lam, sites=sites)
-        _, r2 = o2.fit(o2.init(), MAX_ITER, allreduce=cb)
+        cb2 = dd.make_allreduce_callback(o2.cuda_stream())
+        _, r2 = o2.fit(o2.init(), MAX_ITER, allreduce=cb2)
         barrier()
         e_wall = time.perf_counter() - t0
         o2.close()

@@ -90,8 +90,13 @@ int dca_plm_eval_device(dca_plm *p, const float *x_dev, float *g_dev,
  * assemble+finalize.  out10 = {N, L, q, ld, P, nsplit, nchunk, col_tiles, Npad, nscan}. */
 int dca_plm_eval_timed(dca_plm *p, const float *x_host, float *ms_out);
 int dca_plm_describe(const dca_plm *p, long *out10);
+/* the cudaStream_t every kernel of this handle is launched on */
+void *dca_plm_cuda_stream(const dca_plm *p);
 /* optional collective for site-sharded objectives: sum g (n floats) and the
- * n_scalars doubles at scalars_dev over all ranks; both are DEVICE pointers. */
+ * n_scalars doubles at scalars_dev over all ranks; both are DEVICE pointers.  The
+ * callback must ENQUEUE the reduction in stream order on dca_plm_cuda_stream(p) (it is
+ * called right after the evaluation kernels were launched there, without a host
+ * synchronisation) and may return before it has completed. */
 typedef int (*dca_allreduce_fn)(void *ctx, float *g_dev, long n, double *scalars_dev, int n_scalars);
 typedef struct {
     int status;          /* libLBFGS code: 0 converged, -997 max iterations, -1001 line-search rounding ... */

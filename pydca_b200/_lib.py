@@ -83,6 +83,8 @@ def lib():
     L.dca_plm_fit.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                               ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FitResult)]
     L.dca_plm_eval_timed.argtypes = [ctypes.c_void_p, _f32p, _f32p]
+    L.dca_plm_cuda_stream.argtypes = [ctypes.c_void_p]
+    L.dca_plm_cuda_stream.restype = ctypes.c_void_p
     L.dca_plm_describe.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_long)]
     L.dca_last_fit.argtypes = [ctypes.POINTER(FitResult)]
     L.dca_plm_fn_apc.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
@@ -191,6 +193,10 @@ class PlmObjective:
         ms = np.zeros(5, dtype=np.float32)
         check(lib().dca_plm_eval_timed(self._h, ptr(x, _f32p), ptr(ms, _f32p)), "dca_plm_eval_timed")
         return dict(zip(self.KERNELS, ms.tolist()))
+
+    def cuda_stream(self):
+        """Raw cudaStream_t (int) the handle's kernels run on."""
+        return int(lib().dca_plm_cuda_stream(self._h) or 0)
 
     def describe(self):
         out = (ctypes.c_long * 10)()

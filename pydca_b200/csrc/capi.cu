@@ -219,6 +219,8 @@ int dca_plm_eval_timed(dca_plm *p, const float *x_host, float *ms_out)
     return plm_eval_timed(p->prob, p->d_x, p->d_g, ms_out);
 }
 
+void *dca_plm_cuda_stream(const dca_plm *p) { return p ? (void *)plm_stream(p->prob) : nullptr; }
+
 int dca_plm_describe(const dca_plm *p, long *out10)
 {
     if (!p || !out10) { set_error("dca_plm_describe: null argument"); return -1; }

@@ -115,34 +115,6 @@ vec_step_kernel(float *__restrict__ x, const float *__restrict__ xp, const float
     VEC_TAIL(n, k) x[k] = __fadd_rn(xp[k], __fmul_rn(stp, d[k]));
 }
 
-// s = x - xp ; y = g - gp ; {y.s, y.y} -> op 0      (lbfgs.cpp:546-558)
-__global__ void __launch_bounds__(VEC_THREADS)
-vec_update_sy_kernel(float *__restrict__ s, float *__restrict__ y, const float *__restrict__ x,
-                     const float *__restrict__ xp, const float *__restrict__ g,
-                     const float *__restrict__ gp, long n, double *__restrict__ partial, int slot,
-                     float *__restrict__ sc, double *__restrict__ dscal, unsigned *__restrict__ ticket)
-{
-    __shared__ double scratch[32];
-    double ys = 0.0, yy = 0.0;
-    VEC_LOOP4(n) {
-        const float4 a = reinterpret_cast<const float4 *>(x)[v], b = reinterpret_cast<const float4 *>(xp)[v];
-        const float4 c = reinterpret_cast<const float4 *>(g)[v], e = reinterpret_cast<const float4 *>(gp)[v];
-        const float4 sv = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
-        const float4 yv = make_float4(c.x - e.x, c.y - e.y, c.z - e.z, c.w - e.w);
-        reinterpret_cast<float4 *>(s)[v] = sv;
-        reinterpret_cast<float4 *>(y)[v] = yv;
-        ys += (double)yv.x * sv.x + (double)yv.y * sv.y + (double)yv.z * sv.z + (double)yv.w * sv.w;
-        yy += (double)yv.x * yv.x + (double)yv.y * yv.y + (double)yv.z * yv.z + (double)yv.w * yv.w;
-    }
-    VEC_TAIL(n, k) {
-        const float sv = x[k] - xp[k], yv = g[k] - gp[k];
-        s[k] = sv; y[k] = yv;
-        ys += (double)yv * sv; yy += (double)yv * yv;
-    }
-    const double r0 = block_sum(ys, scratch), r1 = block_sum(yy, scratch);
-    finish_dot(r0, r1, partial, 0, slot, sc, dscal, ticket, scratch);
-}
-
 // one fused pass of the two-loop recursion (lbfgs.cpp:568-601):
 //   mode 0: d = -u                       (vecncpy :575)
 //   mode 1: d += coef * u                (vecadd  :588 / :599), coef from device
@@ -213,6 +185,198 @@ vec_dots_kernel(const float *__restrict__ a, const float *__restrict__ b, long n
     }
     const double r0 = block_sum(ab, scratch), r1 = block_sum(aa, scratch);
     finish_dot(r0, r1, partial, 4, 0, sc, dscal, ticket, scratch);
+}
+
+// ---- compact two-loop recursion ---------------------------------------------------
+// The recursion of lbfgs.cpp:568-601 only ever needs inner products between the
+// vectors {s_k, y_k, g}.  With the Gram entries SY[i][k] = s_i.y_k, YY[i][k] = y_i.y_k,
+// sg[k] = s_k.g, yg[k] = y_k.g, gg = g.g every alpha_j, beta_j follows from scalar
+// recurrences (exactly the quantities the reference computes on the updated vector):
+//   s_j.q_t = -sg[j] - sum_{u<t} alpha_u SY[j][u]
+//   y_j.r_t = gamma (-yg[j] - sum_u alpha_u YY[j][u]) + sum_{v older than t} c_v SY[v][j]
+// and the direction is ONE linear combination
+//   d = -gamma g - gamma sum_u alpha_u y_u + sum_v (alpha_v - beta_v) s_v,
+// g.d (needed by the line search, :845) included.  Per iteration that is two passes
+// over HBM -- (A) s,y update + the 5 new inner products per stored pair, (B) the
+// combination -- instead of 2m+3 = 13 dependent passes: 28 vs 50 vector reads/writes of
+// P floats at m = 5.  The scalar recursion runs in the last CTA of pass A (float64).
+struct HistPtrs {
+    const float *s[LB_M];
+    const float *y[LB_M];
+    int slot[LB_M];         // ring slot of entry t, t = 0 newest (the pair being written) ... bound-1 oldest
+    int bound;
+};
+
+constexpr int GR_SY = 0;                       // [LB_M][LB_M]
+constexpr int GR_YY = LB_M * LB_M;             // [LB_M][LB_M]
+constexpr int GR_SG = 2 * LB_M * LB_M;         // [LB_M]
+constexpr int GR_YG = GR_SG + LB_M;            // [LB_M]
+constexpr int GR_GG = GR_YG + LB_M;
+constexpr int GR_DOUBLES = GR_GG + 1;
+constexpr int GR_NPART = 5 * LB_M;             // partial sums per CTA
+// float coefficients for pass B: [0] g, [1..m] y by entry t, [1+m..2m] s by entry t
+constexpr int CF_FLOATS = 1 + 2 * LB_M;
+
+__global__ void __launch_bounds__(VEC_THREADS)
+vec_update_gram_kernel(float *__restrict__ s_new, float *__restrict__ y_new, const float *__restrict__ x,
+                       const float *__restrict__ xp, const float *__restrict__ g, const float *__restrict__ gp,
+                       HistPtrs H, long n, double *__restrict__ partial, double *__restrict__ gram,
+                       float *__restrict__ coef, double *__restrict__ dscal, unsigned *__restrict__ ticket)
+{
+    __shared__ double red[VEC_THREADS / 32][GR_NPART];
+    __shared__ bool last;
+    double acc[GR_NPART];
+#pragma unroll
+    for (int k = 0; k < GR_NPART; ++k) acc[k] = 0.0;
+    const int nh = H.bound - 1;                // stored pairs other than the new one
+
+    // one element: the five products with g / the new pair, then five per stored pair
+    auto elem = [&](float sv, float yv, float gv) {
+        acc[0] += (double)yv * sv; acc[1] += (double)yv * yv; acc[2] += (double)sv * gv;
+        acc[3] += (double)yv * gv; acc[4] += (double)gv * gv;
+    };
+    auto elem_h = [&](int h, float sv, float yv, float gv, float hs, float hy) {
+        acc[5 + 5 * h + 0] += (double)sv * hy;      // s_new . y_h
+        acc[5 + 5 * h + 1] += (double)hs * yv;      // s_h . y_new
+        acc[5 + 5 * h + 2] += (double)yv * hy;      // y_new . y_h
+        acc[5 + 5 * h + 3] += (double)hs * gv;      // s_h . g
+        acc[5 + 5 * h + 4] += (double)hy * gv;      // y_h . g
+    };
+    VEC_LOOP4(n) {
+        const float4 X = reinterpret_cast<const float4 *>(x)[v], XP = reinterpret_cast<const float4 *>(xp)[v];
+        const float4 G = reinterpret_cast<const float4 *>(g)[v], GP = reinterpret_cast<const float4 *>(gp)[v];
+        const float4 S = make_float4(X.x - XP.x, X.y - XP.y, X.z - XP.z, X.w - XP.w);
+        const float4 Y = make_float4(G.x - GP.x, G.y - GP.y, G.z - GP.z, G.w - GP.w);
+        reinterpret_cast<float4 *>(s_new)[v] = S;
+        reinterpret_cast<float4 *>(y_new)[v] = Y;
+        elem(S.x, Y.x, G.x); elem(S.y, Y.y, G.y); elem(S.z, Y.z, G.z); elem(S.w, Y.w, G.w);
+#pragma unroll
+        for (int h = 0; h < LB_M - 1; ++h) {
+            if (h < nh) {
+                const float4 HS = reinterpret_cast<const float4 *>(H.s[h + 1])[v];
+                const float4 HY = reinterpret_cast<const float4 *>(H.y[h + 1])[v];
+                elem_h(h, S.x, Y.x, G.x, HS.x, HY.x); elem_h(h, S.y, Y.y, G.y, HS.y, HY.y);
+                elem_h(h, S.z, Y.z, G.z, HS.z, HY.z); elem_h(h, S.w, Y.w, G.w, HS.w, HY.w);
+            }
+        }
+    }
+    VEC_TAIL(n, k) {
+        const float sv = x[k] - xp[k], yv = g[k] - gp[k], gv = g[k];
+        s_new[k] = sv; y_new[k] = yv;
+        elem(sv, yv, gv);
+#pragma unroll
+        for (int h = 0; h < LB_M - 1; ++h)
+            if (h < nh) elem_h(h, sv, yv, gv, H.s[h + 1][k], H.y[h + 1][k]);
+    }
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < GR_NPART; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) red[wid][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < GR_NPART) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < VEC_THREADS / 32; ++w) v += red[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * GR_NPART + threadIdx.x] = v;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicInc(ticket, gridDim.x - 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // last CTA: fixed-order reduction of the partials (thread k owns sum k) ...
+    if (threadIdx.x < GR_NPART) {
+        double v = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += partial[(size_t)b * GR_NPART + threadIdx.x];
+        red[0][threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    // ... then the Gram update and the scalar recursion
+    const double *t = red[0];
+    const int e = H.slot[0];
+    gram[GR_SY + e * LB_M + e] = t[0];
+    gram[GR_YY + e * LB_M + e] = t[1];
+    gram[GR_SG + e] = t[2];
+    gram[GR_YG + e] = t[3];
+    gram[GR_GG] = t[4];
+    for (int h = 0; h < nh; ++h) {
+        const int kk = H.slot[h + 1];
+        gram[GR_SY + e * LB_M + kk] = t[5 + 5 * h + 0];
+        gram[GR_SY + kk * LB_M + e] = t[5 + 5 * h + 1];
+        gram[GR_YY + e * LB_M + kk] = t[5 + 5 * h + 2];
+        gram[GR_YY + kk * LB_M + e] = t[5 + 5 * h + 2];
+        gram[GR_SG + kk] = t[5 + 5 * h + 3];
+        gram[GR_YG + kk] = t[5 + 5 * h + 4];
+    }
+    const int bound = H.bound;
+    const double gamma = (double)((float)t[0] / (float)t[1]);          // ys / yy in float (:591)
+    double alpha[LB_M], c[LB_M];
+    for (int tt = 0; tt < bound; ++tt) {                                // newest -> oldest (:581-589)
+        const int j = H.slot[tt];
+        double num = -gram[GR_SG + j];
+        for (int u = 0; u < tt; ++u) num -= alpha[u] * gram[GR_SY + j * LB_M + H.slot[u]];
+        alpha[tt] = num / gram[GR_SY + j * LB_M + j];
+    }
+    for (int tt = bound - 1; tt >= 0; --tt) {                           // oldest -> newest (:593-601)
+        const int j = H.slot[tt];
+        double num = -gram[GR_YG + j];
+        for (int u = 0; u < bound; ++u) num -= alpha[u] * gram[GR_YY + j * LB_M + H.slot[u]];
+        num *= gamma;
+        for (int v = bound - 1; v > tt; --v) num += c[v] * gram[GR_SY + H.slot[v] * LB_M + j];
+        const double beta = num / gram[GR_SY + j * LB_M + j];
+        c[tt] = alpha[tt] - beta;
+    }
+    double dg = -gamma * gram[GR_GG];
+    coef[0] = (float)(-gamma);
+    for (int tt = 0; tt < bound; ++tt) {
+        const int j = H.slot[tt];
+        coef[1 + tt] = (float)(-gamma * alpha[tt]);
+        coef[1 + LB_M + tt] = (float)c[tt];
+        dg += -gamma * alpha[tt] * gram[GR_YG + j] + c[tt] * gram[GR_SG + j];
+    }
+    dscal[PS_DG] = dg;
+}
+
+// pass B: d = coef_g g + sum_t (coef_y[t] y_t + coef_s[t] s_t)
+__global__ void __launch_bounds__(VEC_THREADS)
+vec_direction_kernel(float *__restrict__ d, const float *__restrict__ g, HistPtrs H,
+                     const float *__restrict__ coef, long n)
+{
+    float cy[LB_M], cs[LB_M];
+    const float cg = coef[0];
+#pragma unroll
+    for (int t = 0; t < LB_M; ++t) { cy[t] = coef[1 + t]; cs[t] = coef[1 + LB_M + t]; }
+    const int bound = H.bound;
+    VEC_LOOP4(n) {
+        const float4 gv = reinterpret_cast<const float4 *>(g)[v];
+        float4 o = make_float4(cg * gv.x, cg * gv.y, cg * gv.z, cg * gv.w);
+#pragma unroll
+        for (int t = 0; t < LB_M; ++t) {
+            if (t < bound) {
+                const float4 yv = reinterpret_cast<const float4 *>(H.y[t])[v];
+                o.x += cy[t] * yv.x; o.y += cy[t] * yv.y; o.z += cy[t] * yv.z; o.w += cy[t] * yv.w;
+            }
+        }
+#pragma unroll
+        for (int t = LB_M - 1; t >= 0; --t) {
+            if (t < bound) {
+                const float4 sv = reinterpret_cast<const float4 *>(H.s[t])[v];
+                o.x += cs[t] * sv.x; o.y += cs[t] * sv.y; o.z += cs[t] * sv.z; o.w += cs[t] * sv.w;
+            }
+        }
+        reinterpret_cast<float4 *>(d)[v] = o;
+    }
+    VEC_TAIL(n, k) {
+        float o = cg * g[k];
+        for (int t = 0; t < bound; ++t) o += cy[t] * H.y[t][k];
+        for (int t = bound - 1; t >= 0; --t) o += cs[t] * H.s[t][k];
+        d[k] = o;
+    }
 }
 
 // libLBFGS status codes (lbfgs.h:78-150; the enum counts up from -1024)
@@ -335,8 +499,8 @@ struct Driver {
     int blocks;
     float *x = nullptr, *xp = nullptr, *g = nullptr, *gp = nullptr, *d = nullptr;
     float *s[LB_M] = {nullptr}, *y[LB_M] = {nullptr};
-    float *sc = nullptr;
-    double *partial = nullptr;
+    float *sc = nullptr, *coef = nullptr;
+    double *partial = nullptr, *gram = nullptr;
     unsigned *ticket = nullptr;
     allreduce_fn_t allreduce = nullptr;
     void *ctx = nullptr;
@@ -351,7 +515,9 @@ struct Driver {
         }
         if (!dev_alloc_t(&sc, (size_t)SC_FLOATS)) return -1;
         DCA_CUDA(cudaMemsetAsync(sc, 0, sizeof(float) * SC_FLOATS, st));
-        if (!dev_alloc_t(&partial, 2 * (size_t)blocks) || !dev_alloc_t(&ticket, (size_t)1)) return -1;
+        if (!dev_alloc_t(&partial, (size_t)GR_NPART * blocks) || !dev_alloc_t(&ticket, (size_t)1) ||
+            !dev_alloc_t(&gram, (size_t)GR_DOUBLES) || !dev_alloc_t(&coef, (size_t)CF_FLOATS + 3)) return -1;
+        DCA_CUDA(cudaMemsetAsync(gram, 0, sizeof(double) * GR_DOUBLES, st));
         DCA_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
         return 0;
     }
@@ -360,7 +526,7 @@ struct Driver {
         float *v[] = {x, xp, g, gp, d};
         for (float *q : v) if (q && q != keep_x) dev_free(q);
         for (int i = 0; i < LB_M; ++i) { dev_free(s[i]); dev_free(y[i]); }
-        dev_free(sc); dev_free(partial); dev_free(ticket);
+        dev_free(sc); dev_free(partial); dev_free(ticket); dev_free(gram); dev_free(coef);
     }
 
     // objective at x -> g ; returns {fx, g.d, g.g, x.x} on the host
@@ -372,7 +538,8 @@ struct Driver {
             return plm_read_scalars(p, h);
         }
         if (plm_eval_device(p, x, g, nullptr) != 0) return -1;
-        DCA_CUDA(cudaStreamSynchronize(st));
+        // the callback enqueues the collective in stream order behind the evaluation on the
+        // library's stream (dca_plm_cuda_stream): no host synchronisation here
         if (allreduce(ctx, g, n, plm_scalar_buffer(p), PS_COUNT) != 0) {
             set_error("lbfgs: all-reduce callback failed");
             return -1;
@@ -507,35 +674,22 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
         if (max_iterations != 0 && max_iterations < k + 1) { ret = ST_MAXITER; break; }   // :535-539
 
         // ---- history update + two-loop recursion, all on the device (:546-601) ----
-        DCA_LAUNCH(vec_update_sy_kernel, D.blocks, VEC_THREADS, 0, st,
-                   D.s[end], D.y[end], D.x, D.xp, D.g, D.gp, n, D.partial, end, D.sc, dsc, D.ticket);
         {
             const int bound = (LB_M <= k) ? LB_M : k;
+            HistPtrs H;
+            H.bound = bound;
+            for (int t = 0; t < LB_M; ++t) {
+                const int slot = (end + LB_M - t) % LB_M;      // t = 0: the pair written now
+                H.slot[t] = slot; H.s[t] = D.s[slot]; H.y[t] = D.y[slot];
+            }
+            // pass A: s = x - xp, y = g - gp, the new inner products, Gram update and the scalar
+            // recursion (alpha, beta, gamma -> coefficients, g.d) in the last CTA
+            DCA_LAUNCH(vec_update_gram_kernel, D.blocks, VEC_THREADS, 0, st,
+                       D.s[end], D.y[end], D.x, D.xp, D.g, D.gp, H, n, D.partial, D.gram, D.coef, dsc, D.ticket);
+            // pass B: the direction as one linear combination
+            DCA_LAUNCH(vec_direction_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.g, H, D.coef, n);
             ++k;
             end = (end + 1) % LB_M;
-            int j = (end + LB_M - 1) % LB_M;
-            // d = -g fused with s_j . d -> alpha_j                       (:575, :585)
-            DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.g, D.s[j], D.sc, 0, n,
-                       D.partial, 1, j, dsc, D.ticket);
-            for (int i = 0; i < bound; ++i) {
-                // d -= alpha_j y_j, fused with the next level's s . d, or nothing on the oldest level
-                const int jn = (j + LB_M - 1) % LB_M;
-                const bool more = (i + 1 < bound);
-                DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.y[j],
-                           more ? D.s[jn] : (const float *)nullptr, D.sc, 1, n, D.partial, 1, jn, dsc, D.ticket);
-                if (more) j = jn;
-            }
-            // d *= ys/yy, fused with y_j . d of the oldest level -> beta    (:591, :596)
-            DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, (const float *)nullptr, D.y[j], D.sc, 2, n,
-                       D.partial, 2, j, dsc, D.ticket);
-            for (int i = 0; i < bound; ++i) {
-                // d += (alpha_j - beta) s_j, fused with the next y . d, or with g . d for the line search
-                const int jn = (j + 1) % LB_M;
-                const bool more = (i + 1 < bound);
-                DCA_LAUNCH(vec_twoloop_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.s[j],
-                           more ? D.y[jn] : D.g, D.sc, 1, n, D.partial, more ? 2 : 3, jn, dsc, D.ticket);
-                j = jn;
-            }
         }
         {   // g.d of the new direction (needed by the line search, :845)
             double hh[PS_COUNT];

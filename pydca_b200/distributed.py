@@ -33,24 +33,32 @@ class _CudaView:
                                          "data": (int(ptr), False), "version": 2}
 
 
-def make_allreduce_callback(group=None, device=None):
+def make_allreduce_callback(stream_ptr, group=None, device=None):
     """ctypes callback of type dca_allreduce_fn (include/dca_b200.h): sums the gradient
     buffer and the scalar block over all ranks with NCCL.  Both arguments are DEVICE
-    pointers owned by the C library; the C side has synchronised its stream before
-    calling, and this callback synchronises torch's stream before returning."""
+    pointers owned by the C library.  The collectives are enqueued in stream order on the
+    library's own stream (``stream_ptr`` = PlmObjective.cuda_stream(), wrapped as a
+    torch ExternalStream): no host synchronisation on either side of the call."""
     import torch
     import torch.distributed as dist
     from ._lib import ALLREDUCE_FN
 
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    ext = torch.cuda.ExternalStream(int(stream_ptr), device=dev)
+    views = {}
+
+    def view(ptr, count, typestr):
+        key = (ptr, count, typestr)
+        t = views.get(key)
+        if t is None:
+            t = views[key] = torch.as_tensor(_CudaView(ptr, count, typestr), device=dev)
+        return t
 
     def _cb(_ctx, g_ptr, n, s_ptr, ns):
         try:
-            g = torch.as_tensor(_CudaView(g_ptr, n, "<f4"), device=dev)
-            s = torch.as_tensor(_CudaView(s_ptr, ns, "<f8"), device=dev)
-            dist.all_reduce(g, group=group)
-            dist.all_reduce(s, group=group)
-            torch.cuda.current_stream(dev).synchronize()
+            with torch.cuda.stream(ext):
+                dist.all_reduce(view(s_ptr, ns, "<f8"), group=group)
+                dist.all_reduce(view(g_ptr, n, "<f4"), group=group)
             return 0
         except Exception as exc:          # never let an exception cross the C ABI
             print("dca all-reduce callback failed: %r" % (exc,))
