@@ -199,8 +199,19 @@ def roofline_block(obj, x0, peaks):
     sm_clock_ghz = peaks.get("sm_max_mhz", 1965.0) / 1e3
     lane_peak = 148 * 128 * sm_clock_ghz                       # Gop/s FP32 lanes
     smem_peak = 148 * 32 * sm_clock_ghz                        # G words/s shared-memory bandwidth
+    # DRAM traffic per launch of the same kernel from the committed `ncu --set full` capture
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ncu_name = {"unpack": "plm_unpack_kernel<21>", "logits": "plm_logits_kernel<21>",
+                    "softmax_scan": "plm_softmax_kernel<21>", "scatter": "plm_scatter_kernel<21>",
+                    "assemble": "plm_assemble_kernel<21>"}[top]
+        traffic = tj["kernels"][ncu_name]["dram_bytes"]
+        traffic_src = tj["source"]
+    except Exception:
+        pass
     out = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-           "frac": achieved / hbm, "traffic": None,
+           "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src,
            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
            "kernel_ms": ms, "kernel_share": {k: v / total_ms for k, v in ms.items()},
            "algorithmic_bytes": bytes_k,

@@ -288,11 +288,22 @@ vec_update_gram_kernel(float *__restrict__ s_new, float *__restrict__ y_new, con
     __syncthreads();
     if (!last) return;
     __threadfence();
-    // last CTA: fixed-order reduction of the partials (thread k owns sum k) ...
-    if (threadIdx.x < GR_NPART) {
-        double v = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) v += partial[(size_t)b * GR_NPART + threadIdx.x];
-        red[0][threadIdx.x] = v;
+    // last CTA: fixed-order reduction of the partials, 10 row groups x 25 sums in parallel ...
+    {
+        __shared__ double red2[10][GR_NPART];
+        const int col = threadIdx.x % GR_NPART, grp = threadIdx.x / GR_NPART;
+        if (grp < 10) {
+            double v = 0.0;
+            for (unsigned b = grp; b < gridDim.x; b += 10) v += partial[(size_t)b * GR_NPART + col];
+            red2[grp][col] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < GR_NPART) {
+            double v = 0.0;
+#pragma unroll
+            for (int r = 0; r < 10; ++r) v += red2[r][threadIdx.x];
+            red[0][threadIdx.x] = v;
+        }
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
