@@ -10,16 +10,20 @@
 // epsilon = 1e-3, ftol = 1e-4, gtol = 0.9, xtol = 1e-16, max_linesearch = 5,
 // min_step = 1e-20, max_step = 1e20, More-Thuente line search, first step
 // 1/|g|, H0 = (y.s / y.y) I, revert to the previous point when the line search
-// fails.  Scalars are float like the reference's lbfgsfloatval_t (lbfgs.h:50-56
-// forces float).  What differs by construction: the 16 vectors of P floats
-// live in HBM, every vector pass is a fused kernel (the reference makes ~78
-// unfused passes per iteration, we make 2m+3), and dot products are reduced
-// in float64 in a fixed order (the reference's are sequential float32 sums, so
-// its trajectory is not reproducible even against itself, SURVEY finding 3).
+// fails.  Line-search scalars are float like the reference's lbfgsfloatval_t
+// (lbfgs.h:50-56 forces float).  What differs by construction:
+//   * the 16 vectors of P floats live in HBM; x/xp and g/gp are pointer-swapped
+//     instead of copied;
+//   * the two-loop recursion is evaluated in its compact form: two HBM passes per
+//     iteration (history update + the new inner products; one linear combination)
+//     instead of the reference's ~78 unfused vector passes -- see
+//     vec_update_gram_kernel;
+//   * inner products are reduced in float64 in a fixed order (the reference's are
+//     sequential float32 sums, so its trajectory is not reproducible even against
+//     itself, SURVEY finding 3).
 //
 // Host <-> device traffic per objective evaluation: one 32-byte D2H read of
-// {fx, g.d, g.g, x.x}.  The two-loop recursion never touches the host: its
-// scalars (alpha_j, beta, ys_j, ys/yy) stay in a small device buffer.
+// {fx, g.d, g.g, x.x}; per iteration one more for g.d of the new direction.
 #include "dca_common.cuh"
 #include "dca_internal.h"
 
@@ -33,7 +37,7 @@ namespace {
 constexpr int VEC_THREADS = 256;
 constexpr int LB_M = 5;
 
-// device scalar block (floats): [0..4] alpha_j, [5..9] ys_j, [10] coef, [11] scale
+// small device scalar block kept for the single-vector kernels below
 enum { SC_ALPHA = 0, SC_YS = 5, SC_COEF = 10, SC_SCALE = 11, SC_FLOATS = 16 };
 
 // Every kernel below streams P floats as float4 (the vectors come from cudaMalloc,

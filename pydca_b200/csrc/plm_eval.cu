@@ -26,16 +26,20 @@
 //                           rebuilt from x every evaluation (unpack)
 //   S     f32 [Npad][ld]    logits, overwritten in place by the residuals r
 //   G     f32 [nsplit][L*q][ld]   G[(j,b)][(i,a)] = sum_n [s_nj==b] r_n(i,a)
-//   perm  u8  [L][nchunk][224]    per (site, 128-sequence chunk): the chunk's
-//                           local sequence indices bucketed by residue (static
-//                           for an MSA, built once) -> atomics-free scatter
+//   perm  [site tile][nchunk][site][832 B]  per (site, 128-sequence chunk): bucket
+//                           sizes + the chunk's rows as byte offsets grouped by
+//                           residue (static for an MSA, built once) -> atomics-free
+//                           scatter; one contiguous block per (CTA, chunk)
 //
 // Kernels per evaluation and what bounds them (DESIGN.md has the numbers):
 //   unpack   x -> W                          HBM/L2 streaming, 12P bytes
-//   logits   S = h + sum_j W[(j,s_nj), :]    shared-memory gather: 1 LDS word / add
+//   logits   S = h + sum_j W[(j,s_nj), :]    shared-memory gather: 1 LDS word / add;
+//                                            TMA tensor-map tiles + mbarrier ring
 //   softmax  chunked carry scan, S -> r, fx  latency/L2, 8*N*L*q bytes
-//   scatter  G = sum_n onehot^T r            shared-memory gather: 1 LDS word / add
-//   assemble G (+G^T) + 2*lambda*x -> g, fx, g.d, g.g, x.x   HBM/L2 streaming
+//   scatter  G = sum_n onehot^T r            shared-memory gather: 1 LDS word / add;
+//                                            TMA tensor-map tiles + mbarrier ring
+//   assemble G (+G^T) + 2*lambda*x -> g, and {fx, g.d, g.g, x.x} finished by the
+//            last CTA                        HBM/L2 streaming
 // The gather kernels do N*L*L*q adds each; they are bound by shared-memory
 // bandwidth (128 B/clk/SM = 32 adds/clk/SM), not by HBM.
 #include "dca_common.cuh"
