@@ -225,6 +225,26 @@ def roofline_block(obj, x0, peaks):
                        "logits_frac_of_smem_roof": adds / (ms["logits"] * 1e-3) / 1e9 / smem_peak,
                        "scatter_frac_of_smem_roof": adds / (ms["scatter"] * 1e-3) / 1e9 / smem_peak,
                        "eval_frac_of_fp32_lane_roof": 2 * adds / (total_ms * 1e-3) / 1e9 / lane_peak}}
+    # the HBM-bound part of the path: the two L-BFGS vector passes of one iteration (m = 5)
+    try:
+        from pydca_b200 import _lib as _l
+        vm = _l.lbfgs_vector_bench(P, 5, 20)
+        gram_bytes = 4 * P * (4 + 8 + 2)          # x, xp, g, gp + 4 stored s/y pairs read; s, y written
+        dir_bytes = 4 * P * (1 + 10 + 1)          # g + 5 s + 5 y read; d written
+        step_bytes = 4 * P * 3
+        out["hbm_bound_kernels"] = {
+            "note": "L-BFGS vector algebra: algorithmic bytes / CUDA-event time vs the measured HBM peak",
+            "vec_update_gram": {"ms": vm["update_gram"], "bytes": gram_bytes,
+                                "achieved_gbs": gram_bytes / (vm["update_gram"] * 1e-3) / 1e9,
+                                "frac": gram_bytes / (vm["update_gram"] * 1e-3) / 1e9 / hbm},
+            "vec_direction": {"ms": vm["direction"], "bytes": dir_bytes,
+                              "achieved_gbs": dir_bytes / (vm["direction"] * 1e-3) / 1e9,
+                              "frac": dir_bytes / (vm["direction"] * 1e-3) / 1e9 / hbm},
+            "vec_step": {"ms": vm["step"], "bytes": step_bytes,
+                         "achieved_gbs": step_bytes / (vm["step"] * 1e-3) / 1e9,
+                         "frac": step_bytes / (vm["step"] * 1e-3) / 1e9 / hbm}}
+    except Exception as exc:
+        out["hbm_bound_kernels"] = {"error": repr(exc)}
     return out
 
 

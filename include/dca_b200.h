@@ -90,6 +90,10 @@ int dca_plm_eval_device(dca_plm *p, const float *x_dev, float *g_dev,
  * assemble+finalize.  out10 = {N, L, q, ld, P, nsplit, nchunk, col_tiles, Npad, nscan}. */
 int dca_plm_eval_timed(dca_plm *p, const float *x_host, float *ms_out);
 int dca_plm_describe(const dca_plm *p, long *out10);
+/* measurement hook for the HBM-bound part of the path: CUDA-event ms of the two L-BFGS
+ * passes of one iteration and of the trial-step kernel on n floats with `stored_pairs`
+ * (1..5) history pairs: ms_out3 = {history update + inner products, direction, step}. */
+int dca_lbfgs_vector_bench(long n, int stored_pairs, int reps, float *ms_out3);
 /* the cudaStream_t every kernel of this handle is launched on */
 void *dca_plm_cuda_stream(const dca_plm *p);
 /* optional collective for site-sharded objectives: sum g (n floats) and the

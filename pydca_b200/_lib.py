@@ -83,6 +83,7 @@ def lib():
     L.dca_plm_fit.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                               ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FitResult)]
     L.dca_plm_eval_timed.argtypes = [ctypes.c_void_p, _f32p, _f32p]
+    L.dca_lbfgs_vector_bench.argtypes = [ctypes.c_long, ctypes.c_int, ctypes.c_int, _f32p]
     L.dca_plm_cuda_stream.argtypes = [ctypes.c_void_p]
     L.dca_plm_cuda_stream.restype = ctypes.c_void_p
     L.dca_plm_describe.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_long)]
@@ -221,6 +222,13 @@ def plm_fn_apc(x, seqs_len, num_site_states):
     check(lib().dca_plm_fn_apc(ptr(x, _f32p), int(seqs_len), int(num_site_states), ptr(fn, _f64p),
                                ptr(apc, _f64p)), "dca_plm_fn_apc")
     return fn, apc
+
+
+def lbfgs_vector_bench(n, stored_pairs=5, reps=20):
+    """CUDA-event ms of {history+inner products, direction, step} passes on n floats."""
+    ms = np.zeros(3, dtype=np.float32)
+    check(lib().dca_lbfgs_vector_bench(int(n), int(stored_pairs), int(reps), ptr(ms, _f32p)), "dca_lbfgs_vector_bench")
+    return dict(zip(("update_gram", "direction", "step"), ms.tolist()))
 
 
 def last_fit():

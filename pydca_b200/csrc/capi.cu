@@ -219,6 +219,12 @@ int dca_plm_eval_timed(dca_plm *p, const float *x_host, float *ms_out)
     return plm_eval_timed(p->prob, p->d_x, p->d_g, ms_out);
 }
 
+int dca_lbfgs_vector_bench(long n, int stored_pairs, int reps, float *ms_out3)
+{
+    if (!ms_out3) { set_error("dca_lbfgs_vector_bench: null argument"); return -1; }
+    return lbfgs_vector_bench(n, stored_pairs, reps, ms_out3);
+}
+
 void *dca_plm_cuda_stream(const dca_plm *p) { return p ? (void *)plm_stream(p->prob) : nullptr; }
 
 int dca_plm_describe(const dca_plm *p, long *out10)

@@ -68,6 +68,8 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
                    allreduce_fn_t allreduce, void *allreduce_ctx, LbfgsResult *res,
                    int warmup_iterations, double *timed_ms, int *timed_evals);
 
+int lbfgs_vector_bench(long n, int bound, int reps, float *ms_out);
+
 // ---- scoring.cu ---------------------------------------------------------------------------
 int plm_fn_apc_host(const float *h_x, int L, int q, double *fn, double *fn_apc);
 

@@ -247,21 +247,33 @@ vec_update_gram_kernel(float *__restrict__ s_new, float *__restrict__ y_new, con
         acc[5 + 5 * h + 4] += (double)hy * gv;      // y_h . g
     };
     VEC_LOOP4(n) {
+        // issue every load of this iteration first (predicated, one basic block): with the
+        // loads behind per-pair branches only ~6 of the 12 streams were in flight per thread
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 X = reinterpret_cast<const float4 *>(x)[v], XP = reinterpret_cast<const float4 *>(xp)[v];
         const float4 G = reinterpret_cast<const float4 *>(g)[v], GP = reinterpret_cast<const float4 *>(gp)[v];
+        float4 HS[LB_M - 1], HY[LB_M - 1];
+#pragma unroll
+        for (int h = 0; h < LB_M - 1; ++h) {
+            HS[h] = (h < nh) ? reinterpret_cast<const float4 *>(H.s[h + 1])[v] : z4;
+            HY[h] = (h < nh) ? reinterpret_cast<const float4 *>(H.y[h + 1])[v] : z4;
+        }
         const float4 S = make_float4(X.x - XP.x, X.y - XP.y, X.z - XP.z, X.w - XP.w);
         const float4 Y = make_float4(G.x - GP.x, G.y - GP.y, G.z - GP.z, G.w - GP.w);
         reinterpret_cast<float4 *>(s_new)[v] = S;
         reinterpret_cast<float4 *>(y_new)[v] = Y;
-        elem(S.x, Y.x, G.x); elem(S.y, Y.y, G.y); elem(S.z, Y.z, G.z); elem(S.w, Y.w, G.w);
+        // 4-element partial products in float (FMA), accumulated in float64: a quarter of the
+        // FP64 work, and still far tighter than the reference's sequential float32 sums
+        auto dot4 = [](const float4 &a, const float4 &b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; };
+        acc[0] += (double)dot4(Y, S); acc[1] += (double)dot4(Y, Y); acc[2] += (double)dot4(S, G);
+        acc[3] += (double)dot4(Y, G); acc[4] += (double)dot4(G, G);
 #pragma unroll
-        for (int h = 0; h < LB_M - 1; ++h) {
-            if (h < nh) {
-                const float4 HS = reinterpret_cast<const float4 *>(H.s[h + 1])[v];
-                const float4 HY = reinterpret_cast<const float4 *>(H.y[h + 1])[v];
-                elem_h(h, S.x, Y.x, G.x, HS.x, HY.x); elem_h(h, S.y, Y.y, G.y, HS.y, HY.y);
-                elem_h(h, S.z, Y.z, G.z, HS.z, HY.z); elem_h(h, S.w, Y.w, G.w, HS.w, HY.w);
-            }
+        for (int h = 0; h < LB_M - 1; ++h) {       // pairs beyond nh contribute exact zeros
+            acc[5 + 5 * h + 0] += (double)dot4(S, HY[h]);
+            acc[5 + 5 * h + 1] += (double)dot4(HS[h], Y);
+            acc[5 + 5 * h + 2] += (double)dot4(Y, HY[h]);
+            acc[5 + 5 * h + 3] += (double)dot4(HS[h], G);
+            acc[5 + 5 * h + 4] += (double)dot4(HY[h], G);
         }
     }
     VEC_TAIL(n, k) {
@@ -310,51 +322,60 @@ vec_update_gram_kernel(float *__restrict__ s_new, float *__restrict__ y_new, con
         }
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    // ... then the Gram update and the scalar recursion
-    const double *t = red[0];
-    const int e = H.slot[0];
-    gram[GR_SY + e * LB_M + e] = t[0];
-    gram[GR_YY + e * LB_M + e] = t[1];
-    gram[GR_SG + e] = t[2];
-    gram[GR_YG + e] = t[3];
-    gram[GR_GG] = t[4];
-    for (int h = 0; h < nh; ++h) {
-        const int kk = H.slot[h + 1];
-        gram[GR_SY + e * LB_M + kk] = t[5 + 5 * h + 0];
-        gram[GR_SY + kk * LB_M + e] = t[5 + 5 * h + 1];
-        gram[GR_YY + e * LB_M + kk] = t[5 + 5 * h + 2];
-        gram[GR_YY + kk * LB_M + e] = t[5 + 5 * h + 2];
-        gram[GR_SG + kk] = t[5 + 5 * h + 3];
-        gram[GR_YG + kk] = t[5 + 5 * h + 4];
+    // ... then the Gram update and the scalar recursion, on a shared-memory copy of the
+    // 56-double Gram block (the recursion is ~100 dependent loads: from global memory it
+    // was a 30 us serial tail)
+    __shared__ double gs[GR_DOUBLES];
+    for (int i = threadIdx.x; i < GR_DOUBLES; i += VEC_THREADS) gs[i] = gram[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double *t = red[0];
+        const int e = H.slot[0];
+        gs[GR_SY + e * LB_M + e] = t[0];
+        gs[GR_YY + e * LB_M + e] = t[1];
+        gs[GR_SG + e] = t[2];
+        gs[GR_YG + e] = t[3];
+        gs[GR_GG] = t[4];
+        for (int h = 0; h < nh; ++h) {
+            const int kk = H.slot[h + 1];
+            gs[GR_SY + e * LB_M + kk] = t[5 + 5 * h + 0];
+            gs[GR_SY + kk * LB_M + e] = t[5 + 5 * h + 1];
+            gs[GR_YY + e * LB_M + kk] = t[5 + 5 * h + 2];
+            gs[GR_YY + kk * LB_M + e] = t[5 + 5 * h + 2];
+            gs[GR_SG + kk] = t[5 + 5 * h + 3];
+            gs[GR_YG + kk] = t[5 + 5 * h + 4];
+        }
+        const int bound = H.bound;
+        const double gamma = (double)((float)t[0] / (float)t[1]);          // ys / yy in float (:591)
+        double alpha[LB_M], c[LB_M];
+        for (int tt = 0; tt < bound; ++tt) {                                // newest -> oldest (:581-589)
+            const int j = H.slot[tt];
+            double num = -gs[GR_SG + j];
+            for (int u = 0; u < tt; ++u) num -= alpha[u] * gs[GR_SY + j * LB_M + H.slot[u]];
+            alpha[tt] = num / gs[GR_SY + j * LB_M + j];
+        }
+        for (int tt = bound - 1; tt >= 0; --tt) {                           // oldest -> newest (:593-601)
+            const int j = H.slot[tt];
+            double num = -gs[GR_YG + j];
+            for (int u = 0; u < bound; ++u) num -= alpha[u] * gs[GR_YY + j * LB_M + H.slot[u]];
+            num *= gamma;
+            for (int v = bound - 1; v > tt; --v) num += c[v] * gs[GR_SY + H.slot[v] * LB_M + j];
+            const double beta = num / gs[GR_SY + j * LB_M + j];
+            c[tt] = alpha[tt] - beta;
+        }
+        double dg = -gamma * gs[GR_GG];
+        coef[0] = (float)(-gamma);
+        for (int tt = bound; tt < LB_M; ++tt) { coef[1 + tt] = 0.f; coef[1 + LB_M + tt] = 0.f; }
+        for (int tt = 0; tt < bound; ++tt) {
+            const int j = H.slot[tt];
+            coef[1 + tt] = (float)(-gamma * alpha[tt]);
+            coef[1 + LB_M + tt] = (float)c[tt];
+            dg += -gamma * alpha[tt] * gs[GR_YG + j] + c[tt] * gs[GR_SG + j];
+        }
+        dscal[PS_DG] = dg;
     }
-    const int bound = H.bound;
-    const double gamma = (double)((float)t[0] / (float)t[1]);          // ys / yy in float (:591)
-    double alpha[LB_M], c[LB_M];
-    for (int tt = 0; tt < bound; ++tt) {                                // newest -> oldest (:581-589)
-        const int j = H.slot[tt];
-        double num = -gram[GR_SG + j];
-        for (int u = 0; u < tt; ++u) num -= alpha[u] * gram[GR_SY + j * LB_M + H.slot[u]];
-        alpha[tt] = num / gram[GR_SY + j * LB_M + j];
-    }
-    for (int tt = bound - 1; tt >= 0; --tt) {                           // oldest -> newest (:593-601)
-        const int j = H.slot[tt];
-        double num = -gram[GR_YG + j];
-        for (int u = 0; u < bound; ++u) num -= alpha[u] * gram[GR_YY + j * LB_M + H.slot[u]];
-        num *= gamma;
-        for (int v = bound - 1; v > tt; --v) num += c[v] * gram[GR_SY + H.slot[v] * LB_M + j];
-        const double beta = num / gram[GR_SY + j * LB_M + j];
-        c[tt] = alpha[tt] - beta;
-    }
-    double dg = -gamma * gram[GR_GG];
-    coef[0] = (float)(-gamma);
-    for (int tt = 0; tt < bound; ++tt) {
-        const int j = H.slot[tt];
-        coef[1 + tt] = (float)(-gamma * alpha[tt]);
-        coef[1 + LB_M + tt] = (float)c[tt];
-        dg += -gamma * alpha[tt] * gram[GR_YG + j] + c[tt] * gram[GR_SG + j];
-    }
-    dscal[PS_DG] = dg;
+    __syncthreads();
+    for (int i = threadIdx.x; i < GR_DOUBLES; i += VEC_THREADS) gram[i] = gs[i];
 }
 
 // pass B: d = coef_g g + sum_t (coef_y[t] y_t + coef_s[t] s_t)
@@ -368,21 +389,22 @@ vec_direction_kernel(float *__restrict__ d, const float *__restrict__ g, HistPtr
     for (int t = 0; t < LB_M; ++t) { cy[t] = coef[1 + t]; cs[t] = coef[1 + LB_M + t]; }
     const int bound = H.bound;
     VEC_LOOP4(n) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 gv = reinterpret_cast<const float4 *>(g)[v];
+        float4 yv[LB_M], sv[LB_M];
+#pragma unroll
+        for (int t = 0; t < LB_M; ++t) {           // all loads first, predicated
+            yv[t] = (t < bound) ? reinterpret_cast<const float4 *>(H.y[t])[v] : z4;
+            sv[t] = (t < bound) ? reinterpret_cast<const float4 *>(H.s[t])[v] : z4;
+        }
         float4 o = make_float4(cg * gv.x, cg * gv.y, cg * gv.z, cg * gv.w);
 #pragma unroll
         for (int t = 0; t < LB_M; ++t) {
-            if (t < bound) {
-                const float4 yv = reinterpret_cast<const float4 *>(H.y[t])[v];
-                o.x += cy[t] * yv.x; o.y += cy[t] * yv.y; o.z += cy[t] * yv.z; o.w += cy[t] * yv.w;
-            }
+            o.x += cy[t] * yv[t].x; o.y += cy[t] * yv[t].y; o.z += cy[t] * yv[t].z; o.w += cy[t] * yv[t].w;
         }
 #pragma unroll
         for (int t = LB_M - 1; t >= 0; --t) {
-            if (t < bound) {
-                const float4 sv = reinterpret_cast<const float4 *>(H.s[t])[v];
-                o.x += cs[t] * sv.x; o.y += cs[t] * sv.y; o.z += cs[t] * sv.z; o.w += cs[t] * sv.w;
-            }
+            o.x += cs[t] * sv[t].x; o.y += cs[t] * sv[t].y; o.z += cs[t] * sv[t].z; o.w += cs[t] * sv[t].w;
         }
         reinterpret_cast<float4 *>(d)[v] = o;
     }
@@ -565,6 +587,60 @@ struct Driver {
 };
 
 }  // namespace
+
+// Measurement hook: the two HBM-bound passes of one L-BFGS iteration (and the trial-step
+// kernel) on n floats with `bound` stored pairs, CUDA events on the launching stream.
+// ms_out[3] = {vec_update_gram, vec_direction, vec_step} averaged over reps.
+int lbfgs_vector_bench(long n, int bound, int reps, float *ms_out)
+{
+    if (require_device() != 0) return -1;
+    if (bound < 1 || bound > LB_M || n <= 0 || reps <= 0) { set_error("lbfgs_vector_bench: bad arguments"); return -1; }
+    cudaStream_t st;
+    DCA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    float *v[5 + 2 * LB_M] = {nullptr};
+    float *coef = nullptr;
+    double *partial = nullptr, *gram = nullptr, *dscal = nullptr;
+    unsigned *ticket = nullptr;
+    const int blocks = (int)std::min<long>(ceil_div<long>(n, VEC_THREADS * 4), 8L * sm_count());
+    bool ok = true;
+    for (auto &q : v) ok = ok && dev_alloc_t(&q, (size_t)n);
+    ok = ok && dev_alloc_t(&coef, (size_t)CF_FLOATS + 3) && dev_alloc_t(&partial, (size_t)GR_NPART * blocks) &&
+         dev_alloc_t(&gram, (size_t)GR_DOUBLES) && dev_alloc_t(&dscal, (size_t)16) && dev_alloc_t(&ticket, (size_t)1);
+    int rc = ok ? 0 : -1;
+    if (ok) {
+        for (auto q : v) cudaMemsetAsync(q, 0, sizeof(float) * (size_t)n, st);
+        cudaMemsetAsync(coef, 0, sizeof(float) * (CF_FLOATS + 3), st);
+        cudaMemsetAsync(gram, 0, sizeof(double) * GR_DOUBLES, st);
+        cudaMemsetAsync(ticket, 0, sizeof(unsigned), st);
+        HistPtrs H;
+        H.bound = bound;
+        for (int t = 0; t < LB_M; ++t) { H.slot[t] = t; H.s[t] = v[5 + t]; H.y[t] = v[5 + LB_M + t]; }
+        cudaEvent_t e[4];
+        for (auto &x : e) cudaEventCreate(&x);
+        float acc[3] = {0.f, 0.f, 0.f};
+        for (int r = -2; r < reps; ++r) {          // two warm-up rounds
+            cudaEventRecord(e[0], st);
+            DCA_LAUNCH(vec_update_gram_kernel, blocks, VEC_THREADS, 0, st, v[5], v[5 + LB_M], v[0], v[1], v[2], v[3], H, n,
+                       partial, gram, coef, dscal, ticket);
+            cudaEventRecord(e[1], st);
+            DCA_LAUNCH(vec_direction_kernel, blocks, VEC_THREADS, 0, st, v[4], v[2], H, coef, n);
+            cudaEventRecord(e[2], st);
+            DCA_LAUNCH(vec_step_kernel, blocks, VEC_THREADS, 0, st, v[0], v[1], v[4], 1.0f, n);
+            cudaEventRecord(e[3], st);
+            cudaStreamSynchronize(st);
+            if (r >= 0)
+                for (int k = 0; k < 3; ++k) { float ms = 0.f; cudaEventElapsedTime(&ms, e[k], e[k + 1]); acc[k] += ms; }
+        }
+        for (int k = 0; k < 3; ++k) ms_out[k] = acc[k] / reps;
+        for (auto &x : e) cudaEventDestroy(x);
+        if (cudaGetLastError() != cudaSuccess) { set_error("lbfgs_vector_bench: kernel failure"); rc = -1; }
+    }
+    cudaStreamSynchronize(st);
+    for (auto q : v) dev_free(q);
+    dev_free(coef); dev_free(partial); dev_free(gram); dev_free(dscal); dev_free(ticket);
+    cudaStreamDestroy(st);
+    return rc;
+}
 
 int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
                    allreduce_fn_t allreduce, void *allreduce_ctx, LbfgsResult *res,
