@@ -301,6 +301,29 @@ def test_mf_class_known_answers(tmp_path, golden):
     assert relmax([s for _, s in di], [s for _, s in want]) <= 1e-8
 
 
+def test_mf_path_and_alignment_object_inputs_agree(tmp_path, golden):
+    """K3 (tests/test_meanfield_dca.py of the reference builds the instance both from a
+    file path and from an in-memory alignment): the two routes give identical rankings."""
+    from pydca_b200 import MeanFieldDCA
+    from pydca_b200.synthetic import write_fasta
+    d = golden("mf_toy_rna.npz")
+    path = write_fasta(d["msa"], str(tmp_path / "toy.fa"), 5)
+    seqs = [l.strip() for l in open(path) if not l.startswith(">")]
+    from_path = MeanFieldDCA(path, "rna", pseudocount=0.5, seqid=0.8)
+    from_obj = MeanFieldDCA(seqs, "RNA", pseudocount=0.5, seqid=0.8)
+    assert from_path.num_sequences == from_obj.num_sequences
+    a, b = from_path.compute_sorted_FN_APC(), from_obj.compute_sorted_FN_APC()
+    assert a == b
+    assert from_path.compute_sorted_DI() == from_obj.compute_sorted_DI()
+    assert from_path.last_stage_ms is not None and all(v >= 0 for v in from_path.last_stage_ms.values())
+
+
+def test_lbfgs_vector_pass_timing_hook():
+    """bench.py's HBM roofline block relies on this hook: three positive per-pass times."""
+    ms = lib().lbfgs_vector_bench(100_003, 3)
+    assert len(ms) == 3 and all(v > 0 for v in ms.values())
+
+
 def test_mf_inverse_property_config3_size():
     """Dense SPD inverse at a padded, non-multiple-of-128 size: A * inv(A) = I."""
     from pydca_b200 import msa_numerics as mfn
