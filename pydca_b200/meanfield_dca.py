@@ -201,6 +201,12 @@ class MeanFieldDCA:
         c = np.reshape(couplings_ij, (qm1, qm1))
         return c - np.mean(c, axis=1).reshape(qm1, 1) - np.mean(c, axis=0).reshape(1, qm1) + np.mean(c)
 
+    @staticmethod
+    def _stage_dict(stage_ms):
+        """CUDA-event milliseconds of the device pipeline stages of the last scoring call."""
+        names = ("pair_freqs_and_h2d", "covariance", "inverse", "frobenius_norm", "direct_info")
+        return {k: float(v) for k, v in zip(names, stage_ms)}
+
     def get_mapped_site_pairs_dca_scores(self, sorted_dca_scores, seqbackmapper):
         """meanfield_dca.py:755-790."""
         mapping_dict = seqbackmapper.map_to_reference_sequence()
@@ -217,6 +223,7 @@ class MeanFieldDCA:
         res = msa_numerics.mean_field_scores(self.__msa0, self.__num_site_states, self.__sequences_weight,
                                              self.__pseudocount, want_couplings=True, want_di=True)
         self.__couplings = res["couplings"]
+        self.last_stage_ms = self._stage_dict(res["stage_ms"])
         di = res["di"]
         iu, ju = np.triu_indices(self.__sequences_len, k=1)
         return {(int(i), int(j)): s for i, j, s in zip(iu, ju, di.tolist())}
@@ -242,7 +249,7 @@ class MeanFieldDCA:
         res = msa_numerics.mean_field_scores(self.__msa0, self.__num_site_states, self.__sequences_weight,
                                              self.__pseudocount, want_couplings=self.keep_couplings)
         self.__couplings = res.get("couplings")
-        self.last_stage_ms = res["stage_ms"]
+        self.last_stage_ms = self._stage_dict(res["stage_ms"])
         fn = res["fn"]
         fn_sorted = _sorted_pairs(fn, self.__sequences_len)
         if seqbackmapper is not None:
