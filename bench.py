@@ -18,8 +18,12 @@ weights and work buffers resident in HBM; `e2e` = the same metric through the
 reference's own entry point plmdcaBackend(file, ...) with host buffers: FASTA parse,
 de-duplication, reweighting, H2D, fit and D2H of the result inside the timed region.
 
-At N > 1 GPUs the SAME fit is sharded by sites (one all-reduce of the gradient per
-evaluation over NCCL), i.e. strong scaling.
+At N > 1 GPUs the SAME fit is owner-sharded by sites (pydca_b200.distributed.ShardedPlm):
+every rank owns a site range, the matching slice of the parameter vector and of the L-BFGS
+vectors; per evaluation only the cross blocks move, by P2P stores over NVLink fused into
+the unpack / export kernels, i.e. strong scaling.  DCA_B200_EXCHANGE=allreduce selects the
+older replicated-x path (one NCCL all-reduce of the gradient per evaluation); it is also
+the fallback if the peer arenas cannot be mapped.
 
 --impl reference times the reference's own OpenMP implementation (oracle/_ref, built
 from /root/reference unmodified) on the host cores: each step is a bounded sample
@@ -55,12 +59,18 @@ def workload(tmpdir):
     return msa, path, lam
 
 
-def config_dict(n_gpus):
+def config_dict(n_gpus, exchange=None):
+    par = "single GPU"
+    if n_gpus > 1 and exchange == "peer":
+        par = ("owner-sharded sites x%d: P2P stores of the cross blocks (fused unpack/export kernels) + "
+               "flag barriers + rank-ordered float64 scalar sums over peer memory; no NCCL in the loop" % n_gpus)
+    elif n_gpus > 1:
+        par = "site-shard x%d + NCCL all-reduce(g) per evaluation" % n_gpus
     return {"workload": "C2: plmdca compute_fn protein, synthetic MSA N=%d L=%d q=%d, seqid %.1f, "
                         "lambda_h=lambda_J=0.2(L-1), max_iterations=%d; one step = one full fit"
                         % (N_SEQ, SEQ_LEN, Q, SEQID, MAX_ITER),
             "N": N_SEQ, "L": SEQ_LEN, "q": Q, "max_iterations": MAX_ITER,
-            "parallelism": "site-shard x%d + all-reduce(g) per evaluation" % n_gpus if n_gpus > 1 else "single GPU",
+            "parallelism": par,
             "l2": "working set per evaluation (W 40 MB + S 64 MB + G >= 40 MB + 16 L-BFGS vectors x 20 MB) "
                   "exceeds the 126 MB L2; no explicit flush"}
 
@@ -271,17 +281,26 @@ def run_ours(args, rank, world, local_rank):
         pass
 
     # ---- device-resident objective --------------------------------------------------
+    sp, obj, cb, exchange = None, None, None, None
     if world > 1:
-        counts = dd.sharded_counts(msa, SEQID, device=torch.device("cuda", local_rank))
-        sites = dd.shard_range(SEQ_LEN, rank, world)
-        cb = None  # set after the objective exists
+        dev = torch.device("cuda", local_rank)
+        counts = dd.sharded_counts(msa, SEQID, device=dev)
+        w = (1.0 / counts.astype(np.float32)).astype(np.float32)
+        if os.environ.get("DCA_B200_EXCHANGE", "peer") == "peer":
+            try:
+                sp = dd.ShardedPlm(msa, w, Q, lam, lam)
+                obj, exchange = sp.obj, "peer"
+            except Exception as exc:          # every rank raises together (ShardedPlm agrees on failure)
+                print("bench.py: peer-memory exchange unavailable (%r); using NCCL all-reduce" % (exc,), file=sys.stderr)
+                sp = None
+        if sp is None:
+            obj = _lib.PlmObjective(msa, w, Q, lam, lam, sites=dd.shard_range(SEQ_LEN, rank, world))
+            cb = dd.make_allreduce_callback(obj.cuda_stream())
+            exchange = "allreduce"
     else:
         counts = _lib.sequence_counts(msa, SEQID)
-        sites, cb = None, None
-    w = (1.0 / counts.astype(np.float32)).astype(np.float32)
-    obj = _lib.PlmObjective(msa, w, Q, lam, lam, sites=sites)
-    if world > 1:
-        cb = dd.make_allreduce_callback(obj.cuda_stream())
+        w = (1.0 / counts.astype(np.float32)).astype(np.float32)
+        obj = _lib.PlmObjective(msa, w, Q, lam, lam)
     x0 = obj.init()
 
     def barrier():
@@ -335,29 +354,38 @@ def run_ours(args, rank, world, local_rank):
                "ms_per_step": 1e3 * e_wall / n_e2e, "steps": n_e2e,
                "call": "plmdcaBackend(msa_file, ...) -> float*: FASTA parse + dedup + reweight + H2D + fit + D2H"}
     else:
-        # sharded end-to-end: host MSA -> sharded reweight -> create -> fit -> host x, per rank
+        # sharded end-to-end: host MSA -> row-sharded reweight -> create + wire -> fit -> full x on the host
         barrier()
         t0 = time.perf_counter()
-        c2 = dd.sharded_counts(msa, SEQID, device=torch.device("cuda", local_rank))
+        dev = torch.device("cuda", local_rank)
+        c2 = dd.sharded_counts(msa, SEQID, device=dev)
         w2 = (1.0 / c2.astype(np.float32)).astype(np.float32)
-        o2 = _lib.PlmObjective(msa, w2, Q, lam, lam, sites=sites)
-        cb2 = dd.make_allreduce_callback(o2.cuda_stream())
-        _, r2 = o2.fit(o2.init(), MAX_ITER, allreduce=cb2)
+        if exchange == "peer":
+            sp2 = dd.ShardedPlm(msa, w2, Q, lam, lam)
+            _, r2 = sp2.fit(MAX_ITER)
+            x_full = sp2.gather()
+            sp2.close()
+        else:
+            o2 = _lib.PlmObjective(msa, w2, Q, lam, lam, sites=dd.shard_range(SEQ_LEN, rank, world))
+            cb2 = dd.make_allreduce_callback(o2.cuda_stream())
+            x_full, r2 = o2.fit(o2.init(), MAX_ITER, allreduce=cb2)
+            o2.close()
+        assert x_full.size == obj.P
         barrier()
         e_wall = time.perf_counter() - t0
-        o2.close()
         t = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": r2.evaluations / float(t[0]), "unit": "evals/s",
-               "h2d_bytes_per_step": 2 * N_SEQ * SEQ_LEN + 4 * N_SEQ + 4 * obj.P,
-               "d2h_bytes_per_step": 4 * N_SEQ + 8 * obj.P, "ms_per_step": 1e3 * float(t[0]), "steps": 1,
-               "call": "host MSA -> row-sharded reweight + all-reduce -> site-sharded fit -> host x"}
+               "h2d_bytes_per_step": 2 * N_SEQ * SEQ_LEN + 4 * N_SEQ,
+               "d2h_bytes_per_step": 4 * N_SEQ + 4 * obj.P, "ms_per_step": 1e3 * float(t[0]), "steps": 1,
+               "call": "host MSA -> row-sharded reweight + all-reduce(counts) -> sharded create -> fit -> "
+                       "all-gather -> full x on the host, per rank"}
 
     if rank == 0:
         line = {"metric": "plmdca_grad_evals_per_sec", "value": evals / (dev_ms * 1e-3), "unit": "evals/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world, exchange),
                 "evals_per_step": evals / max(1, args.steps), "lbfgs_status": status, "lbfgs_iterations": iters,
                 "wall_ms_per_step": 1e3 * wall / max(1, args.steps),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
@@ -374,7 +402,10 @@ def run_ours(args, rank, world, local_rank):
                 line["cpu_baseline"] = {"value": None, "unit": "evals/s", "cores": cores, "kind": "unavailable",
                                         "sample": repr(exc)}
         print(json.dumps(line))
-    obj.close()
+    if sp is not None:
+        sp.close()
+    else:
+        obj.close()
     if dist is not None:
         dist.destroy_process_group()
 

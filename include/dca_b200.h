@@ -116,6 +116,38 @@ typedef struct {
 int dca_plm_fit(dca_plm *p, float *x_inout_host, int max_iterations, int verbose,
                 int warmup_iterations, dca_allreduce_fn allreduce, void *allreduce_ctx,
                 dca_fit_result *result);
+/* ---- owner-sharded plmDCA for 2..16 GPUs of one node (one process per GPU) -----------------
+ * The reference parallelises PlmDCA::gradient over sites with OpenMP
+ * (plmdca_numerics.cpp:488); here rank r of `world` OWNS the sites
+ * [bounds[r], bounds[r+1]) (bounds[0] = 0, bounds[world] = L, every rank at least one site)
+ * and the slice of the parameter vector made of those sites' fields and of the blocks J_ij
+ * whose first site i it owns -- two contiguous runs of the reference's vector
+ * (dca_plm_local_layout).  On a sharded handle dca_plm_init / dca_plm_eval / dca_plm_fit
+ * take and return that LOCAL slice (dca_plm_local_params floats); the optimiser's vectors are
+ * sharded the same way.  Per evaluation the ranks exchange only the cross blocks, by P2P
+ * stores over NVLink into each other's arena (fused into the unpack / export kernels), and
+ * a few float64 scalars, summed in rank order so that every rank takes the same decisions.
+ * Every rank must make the same sequence of eval / fit calls (they are collective).
+ * Wiring: exchange dca_plm_ipc_handle() bytes between the processes (e.g. torch.distributed
+ * all_gather) and pass all of them to dca_plm_connect_ipc; ranks living in one process pass
+ * raw dca_plm_arena() pointers to dca_plm_connect_ptrs instead.  Call dca_plm_disconnect on
+ * every rank (then synchronise the ranks) before any rank destroys its handle. */
+dca_plm *dca_plm_create_sharded(const uint8_t *msa, const float *weights, long num_seqs,
+                                int seqs_len, int num_site_states, float lambda_h,
+                                float lambda_J, int rank, int world, const int *bounds);
+long dca_plm_local_params(const dca_plm *p);
+/* out4 = {first field, number of fields, first coupling element, number of coupling elements}
+ * of the local slice inside the reference's vector (plmdca_numerics.cpp:226, :338-342) */
+int dca_plm_local_layout(const dca_plm *p, long *out4);
+/* the same arithmetic without a handle or a GPU (host only) */
+int dca_shard_layout(int seqs_len, int num_site_states, int site_lo, int site_hi, long *out4);
+void *dca_plm_arena(const dca_plm *p);                   /* device pointer, NULL unless sharded */
+void *dca_plm_x_device(dca_plm *p);                      /* device buffer holding the last init / fit result */
+int dca_plm_ipc_handle(const dca_plm *p, unsigned char *out64);
+int dca_plm_connect_ipc(dca_plm *p, const unsigned char *handles /* world x 64 bytes, by rank */, int world);
+int dca_plm_connect_ptrs(dca_plm *p, void *const *arena_ptrs /* world entries, by rank */);
+int dca_plm_disconnect(dca_plm *p);
+
 /* statistics of this thread's most recent plmdcaBackend() call (the reference's
  * entry point discards the L-BFGS return code, plmdcaBackend.cpp:197). */
 int dca_last_fit(dca_fit_result *result);

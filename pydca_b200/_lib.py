@@ -72,6 +72,21 @@ def lib():
     L.dca_plm_create.argtypes = [_u8p, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                  ctypes.c_float, ctypes.c_int, ctypes.c_int]
     L.dca_plm_create.restype = ctypes.c_void_p
+    L.dca_plm_create_sharded.argtypes = [_u8p, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                         ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.dca_plm_create_sharded.restype = ctypes.c_void_p
+    L.dca_plm_local_params.argtypes = [ctypes.c_void_p]
+    L.dca_plm_local_params.restype = ctypes.c_long
+    L.dca_plm_local_layout.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_long)]
+    L.dca_shard_layout.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_long)]
+    L.dca_plm_arena.argtypes = [ctypes.c_void_p]
+    L.dca_plm_arena.restype = ctypes.c_void_p
+    L.dca_plm_x_device.argtypes = [ctypes.c_void_p]
+    L.dca_plm_x_device.restype = ctypes.c_void_p
+    L.dca_plm_ipc_handle.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    L.dca_plm_connect_ipc.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+    L.dca_plm_connect_ptrs.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+    L.dca_plm_disconnect.argtypes = [ctypes.c_void_p]
     L.dca_plm_destroy.argtypes = [ctypes.c_void_p]
     L.dca_plm_destroy.restype = None
     L.dca_plm_num_params.argtypes = [ctypes.c_void_p]
@@ -143,20 +158,76 @@ def sequence_counts(msa, seqid, compare_f64=False, rows=None):
     return counts
 
 
-class PlmObjective:
-    """Device-resident plmDCA objective (the reference's C++ PlmDCA object)."""
+def shard_layout(seqs_len, num_site_states, site_lo, site_hi):
+    """(field offset, field count, coupling offset, coupling count) of the parameter slice owned
+    by the sites [site_lo, site_hi) inside the reference's vector (host arithmetic only)."""
+    out = (ctypes.c_long * 4)()
+    check(lib().dca_shard_layout(int(seqs_len), int(num_site_states), int(site_lo), int(site_hi), out),
+          "dca_shard_layout")
+    return tuple(int(v) for v in out)
 
-    def __init__(self, msa, weights, num_site_states, lambda_h, lambda_J, sites=None):
+
+class PlmObjective:
+    """Device-resident plmDCA objective (the reference's C++ PlmDCA object).
+
+    ``sites=(lo, hi)``: data term of those sites only over the whole (replicated) vector.
+    ``shard=(rank, world, bounds)``: owner-sharded multi-GPU objective (include/dca_b200.h);
+    init / eval / fit then work on the LOCAL slice of ``Ploc`` floats and are collective."""
+
+    def __init__(self, msa, weights, num_site_states, lambda_h, lambda_J, sites=None, shard=None):
         msa = np.ascontiguousarray(msa, dtype=np.uint8)
         weights = np.ascontiguousarray(weights, dtype=np.float32)
         n, l = msa.shape
-        lo, hi = (0, l) if sites is None else sites
         self.N, self.L, self.q = n, l, int(num_site_states)
-        self._h = lib().dca_plm_create(ptr(msa, _u8p), ptr(weights, _f32p), n, l, self.q,
-                                       float(lambda_h), float(lambda_J), int(lo), int(hi))
+        self.shard = None
+        if shard is not None:
+            rank, world, bounds = shard
+            b = (ctypes.c_int * (int(world) + 1))(*[int(v) for v in bounds])
+            self.shard = (int(rank), int(world), tuple(int(v) for v in bounds))
+            self._h = lib().dca_plm_create_sharded(ptr(msa, _u8p), ptr(weights, _f32p), n, l, self.q,
+                                                   float(lambda_h), float(lambda_J), int(rank), int(world), b)
+        else:
+            lo, hi = (0, l) if sites is None else sites
+            self._h = lib().dca_plm_create(ptr(msa, _u8p), ptr(weights, _f32p), n, l, self.q,
+                                           float(lambda_h), float(lambda_J), int(lo), int(hi))
         if not self._h:
             raise DcaBackendError("dca_plm_create failed: %s" % last_error())
         self.P = int(lib().dca_plm_num_params(self._h))
+        self.Ploc = int(lib().dca_plm_local_params(self._h))
+
+    # ---- owner-sharded wiring -----------------------------------------------------------
+    def local_layout(self):
+        out = (ctypes.c_long * 4)()
+        check(lib().dca_plm_local_layout(self._h, out), "dca_plm_local_layout")
+        return tuple(int(v) for v in out)
+
+    def local_slice(self, x_full):
+        """The part of a full parameter vector this rank owns."""
+        fo, fc, co, cc = self.local_layout()
+        return np.concatenate([x_full[fo:fo + fc], x_full[co:co + cc]]).astype(np.float32)
+
+    def arena(self):
+        return int(lib().dca_plm_arena(self._h) or 0)
+
+    def x_device(self):
+        return int(lib().dca_plm_x_device(self._h) or 0)
+
+    def ipc_handle(self):
+        buf = ctypes.create_string_buffer(64)
+        check(lib().dca_plm_ipc_handle(self._h, buf), "dca_plm_ipc_handle")
+        return buf.raw
+
+    def connect_ipc(self, handles):
+        blob = b"".join(handles)
+        check(lib().dca_plm_connect_ipc(self._h, blob, len(handles)), "dca_plm_connect_ipc")
+
+    def connect_ptrs(self, arena_ptrs):
+        arr = (ctypes.c_void_p * len(arena_ptrs))(*[int(v) for v in arena_ptrs])
+        check(lib().dca_plm_connect_ptrs(self._h, arr), "dca_plm_connect_ptrs")
+
+    def disconnect(self):
+        if getattr(self, "_h", None):
+            check(lib().dca_plm_disconnect(self._h), "dca_plm_disconnect")
 
     def close(self):
         if getattr(self, "_h", None):
@@ -169,13 +240,13 @@ class PlmObjective:
         check(lib().dca_plm_set_carry(self._h, int(bool(carry)), int(chunk), int(warm)), "dca_plm_set_carry")
 
     def init(self):
-        x = np.zeros(self.P, dtype=np.float32)
+        x = np.zeros(self.Ploc, dtype=np.float32)
         check(lib().dca_plm_init(self._h, ptr(x, _f32p)), "dca_plm_init")
         return x
 
     def eval(self, x, out=None):
         x = np.ascontiguousarray(x, dtype=np.float32)
-        g = np.empty(self.P, dtype=np.float32) if out is None else out
+        g = np.empty(self.Ploc, dtype=np.float32) if out is None else out
         fx = ctypes.c_double()
         check(lib().dca_plm_eval(self._h, ptr(x, _f32p), ptr(g, _f32p), ctypes.byref(fx)), "dca_plm_eval")
         return fx.value, g

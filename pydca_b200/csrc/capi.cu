@@ -79,10 +79,24 @@ using namespace dca;
 
 struct dca_plm {
     PlmProblem *prob;
-    float *d_x, *d_g;
+    float *d_x, *d_g;                       // whole vector, or the local slice of a sharded objective
+    void *ipc_opened[XR_MAX_RANKS];         // peer arenas this process opened through CUDA IPC
 };
 
 static thread_local dca_fit_result t_last_fit = {};
+
+extern "C" void dca_plm_destroy(dca_plm *p);
+
+static dca_plm *wrap_problem(PlmProblem *prob)
+{
+    dca_plm *h = new (std::nothrow) dca_plm{prob, nullptr, nullptr, {nullptr}};
+    if (!h) { plm_destroy(prob); set_error("out of memory"); return nullptr; }
+    const size_t bytes = sizeof(float) * (size_t)plm_local_params(prob);
+    h->d_x = static_cast<float *>(dev_alloc(bytes));
+    h->d_g = static_cast<float *>(dev_alloc(bytes));
+    if (!h->d_x || !h->d_g) { dca_plm_destroy(h); return nullptr; }
+    return h;
+}
 
 extern "C" {
 
@@ -150,19 +164,97 @@ dca_plm *dca_plm_create(const uint8_t *msa, const float *weights, long num_seqs,
     PlmProblem *prob = plm_create(msa, weights, num_seqs, seqs_len, num_site_states, lambda_h, lambda_J,
                                   site_lo, site_hi);
     if (!prob) return nullptr;
-    dca_plm *h = new (std::nothrow) dca_plm{prob, nullptr, nullptr};
-    if (!h) { plm_destroy(prob); set_error("out of memory"); return nullptr; }
-    const size_t bytes = sizeof(float) * (size_t)plm_num_params(prob);
-    h->d_x = static_cast<float *>(dev_alloc(bytes));
-    h->d_g = static_cast<float *>(dev_alloc(bytes));
-    if (!h->d_x || !h->d_g) { dca_plm_destroy(h); return nullptr; }
-    return h;
+    return wrap_problem(prob);
+}
+
+dca_plm *dca_plm_create_sharded(const uint8_t *msa, const float *weights, long num_seqs, int seqs_len,
+                                int num_site_states, float lambda_h, float lambda_J, int rank, int world,
+                                const int *bounds)
+{
+    if (!msa || !weights || !bounds) { set_error("dca_plm_create_sharded: null input"); return nullptr; }
+    PlmProblem *prob = plm_create_sharded(msa, weights, num_seqs, seqs_len, num_site_states, lambda_h, lambda_J,
+                                          rank, world, bounds);
+    if (!prob) return nullptr;
+    return wrap_problem(prob);
+}
+
+long dca_plm_local_params(const dca_plm *p) { return p ? plm_local_params(p->prob) : -1; }
+
+int dca_plm_local_layout(const dca_plm *p, long *out4)
+{
+    if (!p || !out4) { set_error("dca_plm_local_layout: null argument"); return -1; }
+    plm_local_layout(p->prob, out4);
+    return 0;
+}
+
+int dca_shard_layout(int seqs_len, int num_site_states, int site_lo, int site_hi, long *out4)
+{
+    const long L = seqs_len, q = num_site_states;
+    if (!out4 || L < 2 || q < 2 || site_lo < 0 || site_hi > L || site_lo >= site_hi) {
+        set_error("dca_shard_layout: bad arguments"); return -1;
+    }
+    out4[0] = site_lo * q;
+    out4[1] = (site_hi - site_lo) * q;
+    out4[2] = L * q + pair_index(L, site_lo, site_lo + 1) * q * q;
+    out4[3] = (pair_index(L, site_hi, site_hi + 1) - pair_index(L, site_lo, site_lo + 1)) * q * q;
+    return 0;
+}
+
+void *dca_plm_arena(const dca_plm *p) { return p ? plm_arena(p->prob) : nullptr; }
+void *dca_plm_x_device(dca_plm *p) { return p ? (void *)p->d_x : nullptr; }
+
+int dca_plm_ipc_handle(const dca_plm *p, unsigned char *out64)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (!p || !out64 || !plm_arena(p->prob)) { set_error("dca_plm_ipc_handle: not a sharded objective"); return -1; }
+    cudaIpcMemHandle_t h;
+    DCA_CUDA(cudaIpcGetMemHandle(&h, plm_arena(p->prob)));
+    memcpy(out64, &h, 64);
+    return 0;
+}
+
+int dca_plm_connect_ptrs(dca_plm *p, void *const *arena_ptrs)
+{
+    if (!p || !arena_ptrs) { set_error("dca_plm_connect_ptrs: null argument"); return -1; }
+    return plm_connect(p->prob, arena_ptrs, true);
+}
+
+int dca_plm_connect_ipc(dca_plm *p, const unsigned char *handles, int world)
+{
+    if (!p || !handles || world < 1 || world > XR_MAX_RANKS) { set_error("dca_plm_connect_ipc: bad arguments"); return -1; }
+    void *ptrs[XR_MAX_RANKS] = {nullptr};
+    void *own = plm_arena(p->prob);
+    cudaIpcMemHandle_t mine;
+    DCA_CUDA(cudaIpcGetMemHandle(&mine, own));
+    for (int r = 0; r < world; ++r) {
+        if (memcmp(handles + 64 * r, &mine, 64) == 0) { ptrs[r] = own; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * r, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&ptrs[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
+            for (int k = 0; k < r; ++k) if (p->ipc_opened[k]) { cudaIpcCloseMemHandle(p->ipc_opened[k]); p->ipc_opened[k] = nullptr; }
+            return -1;
+        }
+        p->ipc_opened[r] = ptrs[r];
+    }
+    return plm_connect(p->prob, ptrs, false);
+}
+
+int dca_plm_disconnect(dca_plm *p)
+{
+    if (!p) { set_error("null handle"); return -1; }
+    plm_disconnect(p->prob);
+    for (int r = 0; r < XR_MAX_RANKS; ++r)
+        if (p->ipc_opened[r]) { cudaIpcCloseMemHandle(p->ipc_opened[r]); p->ipc_opened[r] = nullptr; }
+    return 0;
 }
 
 void dca_plm_destroy(dca_plm *p)
 {
     if (!p) return;
     cudaStreamSynchronize(plm_stream(p->prob));
+    dca_plm_disconnect(p);
     dev_free(p->d_x); dev_free(p->d_g);
     plm_destroy(p->prob);
     delete p;
@@ -181,7 +273,7 @@ int dca_plm_init(dca_plm *p, float *x_out_host)
 {
     if (!p || !x_out_host) { set_error("dca_plm_init: null argument"); return -1; }
     if (plm_init_x_device(p->prob, p->d_x) != 0) return -1;
-    DCA_CUDA(cudaMemcpyAsync(x_out_host, p->d_x, sizeof(float) * (size_t)plm_num_params(p->prob),
+    DCA_CUDA(cudaMemcpyAsync(x_out_host, p->d_x, sizeof(float) * (size_t)plm_local_params(p->prob),
                              cudaMemcpyDeviceToHost, plm_stream(p->prob)));
     DCA_CUDA(cudaStreamSynchronize(plm_stream(p->prob)));
     return 0;
@@ -191,12 +283,16 @@ int dca_plm_eval(dca_plm *p, const float *x_host, float *g_host, double *fx_out)
 {
     if (!p || !x_host || !g_host) { set_error("dca_plm_eval: null argument"); return -1; }
     cudaStream_t st = plm_stream(p->prob);
-    const size_t bytes = sizeof(float) * (size_t)plm_num_params(p->prob);
+    const size_t bytes = sizeof(float) * (size_t)plm_local_params(p->prob);
     DCA_CUDA(cudaMemcpyAsync(p->d_x, x_host, bytes, cudaMemcpyHostToDevice, st));
     if (plm_eval_device(p->prob, p->d_x, p->d_g, nullptr) != 0) return -1;
-    DCA_CUDA(cudaMemcpyAsync(g_host, p->d_g, bytes, cudaMemcpyDeviceToHost, st));
+    // scalars first (pinned buffer + stream sync), then the gradient on an idle stream: a copy
+    // to pageable memory waits inside the driver, and when several sharded ranks live in one
+    // process that wait must not sit in front of a peer's kernel launches
     double h[PS_COUNT];
     if (plm_read_scalars(p->prob, h) != 0) return -1;
+    DCA_CUDA(cudaMemcpyAsync(g_host, p->d_g, bytes, cudaMemcpyDeviceToHost, st));
+    DCA_CUDA(cudaStreamSynchronize(st));
     if (fx_out) *fx_out = h[PS_FX];
     return 0;
 }
@@ -214,7 +310,7 @@ int dca_plm_eval_timed(dca_plm *p, const float *x_host, float *ms_out)
 {
     if (!p || !x_host || !ms_out) { set_error("dca_plm_eval_timed: null argument"); return -1; }
     cudaStream_t st = plm_stream(p->prob);
-    DCA_CUDA(cudaMemcpyAsync(p->d_x, x_host, sizeof(float) * (size_t)plm_num_params(p->prob),
+    DCA_CUDA(cudaMemcpyAsync(p->d_x, x_host, sizeof(float) * (size_t)plm_local_params(p->prob),
                              cudaMemcpyHostToDevice, st));
     return plm_eval_timed(p->prob, p->d_x, p->d_g, ms_out);
 }
@@ -239,7 +335,7 @@ int dca_plm_fit(dca_plm *p, float *x_inout_host, int max_iterations, int verbose
 {
     if (!p || !x_inout_host) { set_error("dca_plm_fit: null argument"); return -1; }
     cudaStream_t st = plm_stream(p->prob);
-    const size_t bytes = sizeof(float) * (size_t)plm_num_params(p->prob);
+    const size_t bytes = sizeof(float) * (size_t)plm_local_params(p->prob);
     DCA_CUDA(cudaMemcpyAsync(p->d_x, x_inout_host, bytes, cudaMemcpyHostToDevice, st));
     LbfgsResult r{};
     double timed_ms = 0.0;

@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <vector>
 
+#include "xrank.cuh"
+
 namespace dca {
 
 // ---- alloc.cu ------------------------------------------------------------------
@@ -39,6 +41,20 @@ enum PlmScalar { PS_FX = 0, PS_DG = 1, PS_GG = 2, PS_XX = 3, PS_COUNT = 4 };
 
 PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
                        float lambda_h, float lambda_J, int site_lo, int site_hi);
+// owner-sharded objective for multi-GPU runs (xrank.cuh): rank r of `world` owns the sites
+// [bounds[r], bounds[r+1]); x, g and the optimiser's vectors hold the local slice only
+PlmProblem *plm_create_sharded(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
+                               float lambda_h, float lambda_J, int rank, int world, const int *bounds);
+int plm_connect(PlmProblem *p, void *const *arenas, bool shared_process);    // device pointers of every rank's arena
+void plm_disconnect(PlmProblem *p);
+void *plm_arena(const PlmProblem *p);
+size_t plm_arena_bytes(const PlmProblem *p);
+bool plm_is_sharded(const PlmProblem *p);
+long plm_local_params(const PlmProblem *p);             // == plm_num_params unless sharded
+void plm_local_layout(const PlmProblem *p, long *out4);  // {field off, count, coupling off, count} in the full vector
+struct XrCall { XrPeers P; XrLayout lay; unsigned epoch, seq; unsigned *err; };
+XrCall plm_xr_next(PlmProblem *p);
+int plm_xr_barrier(PlmProblem *p);                       // flag barrier on the stream (no-op unless sharded)                       // arguments of the next cross-rank reduction
 void plm_destroy(PlmProblem *p);
 long plm_num_params(const PlmProblem *p);
 cudaStream_t plm_stream(const PlmProblem *p);
@@ -69,6 +85,7 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
                    int warmup_iterations, double *timed_ms, int *timed_evals);
 
 int lbfgs_vector_bench(long n, int bound, int reps, float *ms_out);
+int lbfgs_preload_kernels();   // force-load the optimiser's kernels (see plm_setup_t)
 
 // ---- scoring.cu ---------------------------------------------------------------------------
 int plm_fn_apc_host(const float *h_x, int L, int q, double *fn, double *fn_apc);

@@ -221,12 +221,74 @@ constexpr int GR_NPART = 5 * LB_M;             // partial sums per CTA
 // float coefficients for pass B: [0] g, [1..m] y by entry t, [1+m..2m] s by entry t
 constexpr int CF_FLOATS = 1 + 2 * LB_M;
 
+// Gram update + scalar two-loop recursion from the 25 freshly reduced inner products t[]
+// (t may live in shared memory).  Whole CTA participates; thread 0 runs the recursion on a
+// shared-memory copy of the 56-double Gram block (the recursion is ~100 dependent loads:
+// from global memory it was a 30 us serial tail).
+__device__ __forceinline__ void gram_recursion(const double *t, const HistPtrs &H, double *__restrict__ gram,
+                                               float *__restrict__ coef, double *__restrict__ dscal)
+{
+    const int nh = H.bound - 1;
+    __shared__ double gs[GR_DOUBLES];
+    for (int i = threadIdx.x; i < GR_DOUBLES; i += blockDim.x) gs[i] = gram[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int e = H.slot[0];
+        gs[GR_SY + e * LB_M + e] = t[0];
+        gs[GR_YY + e * LB_M + e] = t[1];
+        gs[GR_SG + e] = t[2];
+        gs[GR_YG + e] = t[3];
+        gs[GR_GG] = t[4];
+        for (int h = 0; h < nh; ++h) {
+            const int kk = H.slot[h + 1];
+            gs[GR_SY + e * LB_M + kk] = t[5 + 5 * h + 0];
+            gs[GR_SY + kk * LB_M + e] = t[5 + 5 * h + 1];
+            gs[GR_YY + e * LB_M + kk] = t[5 + 5 * h + 2];
+            gs[GR_YY + kk * LB_M + e] = t[5 + 5 * h + 2];
+            gs[GR_SG + kk] = t[5 + 5 * h + 3];
+            gs[GR_YG + kk] = t[5 + 5 * h + 4];
+        }
+        const int bound = H.bound;
+        const double gamma = (double)((float)t[0] / (float)t[1]);          // ys / yy in float (:591)
+        double alpha[LB_M], c[LB_M];
+        for (int tt = 0; tt < bound; ++tt) {                                // newest -> oldest (:581-589)
+            const int j = H.slot[tt];
+            double num = -gs[GR_SG + j];
+            for (int u = 0; u < tt; ++u) num -= alpha[u] * gs[GR_SY + j * LB_M + H.slot[u]];
+            alpha[tt] = num / gs[GR_SY + j * LB_M + j];
+        }
+        for (int tt = bound - 1; tt >= 0; --tt) {                           // oldest -> newest (:593-601)
+            const int j = H.slot[tt];
+            double num = -gs[GR_YG + j];
+            for (int u = 0; u < bound; ++u) num -= alpha[u] * gs[GR_YY + j * LB_M + H.slot[u]];
+            num *= gamma;
+            for (int v = bound - 1; v > tt; --v) num += c[v] * gs[GR_SY + H.slot[v] * LB_M + j];
+            const double beta = num / gs[GR_SY + j * LB_M + j];
+            c[tt] = alpha[tt] - beta;
+        }
+        double dg = -gamma * gs[GR_GG];
+        coef[0] = (float)(-gamma);
+        for (int tt = bound; tt < LB_M; ++tt) { coef[1 + tt] = 0.f; coef[1 + LB_M + tt] = 0.f; }
+        for (int tt = 0; tt < bound; ++tt) {
+            const int j = H.slot[tt];
+            coef[1 + tt] = (float)(-gamma * alpha[tt]);
+            coef[1 + LB_M + tt] = (float)c[tt];
+            dg += -gamma * alpha[tt] * gs[GR_YG + j] + c[tt] * gs[GR_SG + j];
+        }
+        dscal[PS_DG] = dg;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < GR_DOUBLES; i += blockDim.x) gram[i] = gs[i];
+}
+
 __global__ void __launch_bounds__(VEC_THREADS)
 vec_update_gram_kernel(float *__restrict__ s_new, float *__restrict__ y_new, const float *__restrict__ x,
                        const float *__restrict__ xp, const float *__restrict__ g, const float *__restrict__ gp,
                        HistPtrs H, long n, double *__restrict__ partial, double *__restrict__ gram,
-                       float *__restrict__ coef, double *__restrict__ dscal, unsigned *__restrict__ ticket)
-{
+                       float *__restrict__ coef, double *__restrict__ dscal, unsigned *__restrict__ ticket,
+                       double *__restrict__ gram_loc)
+{   // gram_loc != null (owner-sharded multi-GPU): the last CTA only leaves this rank's 25 partial
+    // inner products there; xr_gram_kernel sums them over the ranks and runs the recursion
     __shared__ double red[VEC_THREADS / 32][GR_NPART];
     __shared__ bool last;
     double acc[GR_NPART];
@@ -322,60 +384,24 @@ vec_update_gram_kernel(float *__restrict__ s_new, float *__restrict__ y_new, con
         }
     }
     __syncthreads();
-    // ... then the Gram update and the scalar recursion, on a shared-memory copy of the
-    // 56-double Gram block (the recursion is ~100 dependent loads: from global memory it
-    // was a 30 us serial tail)
-    __shared__ double gs[GR_DOUBLES];
-    for (int i = threadIdx.x; i < GR_DOUBLES; i += VEC_THREADS) gs[i] = gram[i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const double *t = red[0];
-        const int e = H.slot[0];
-        gs[GR_SY + e * LB_M + e] = t[0];
-        gs[GR_YY + e * LB_M + e] = t[1];
-        gs[GR_SG + e] = t[2];
-        gs[GR_YG + e] = t[3];
-        gs[GR_GG] = t[4];
-        for (int h = 0; h < nh; ++h) {
-            const int kk = H.slot[h + 1];
-            gs[GR_SY + e * LB_M + kk] = t[5 + 5 * h + 0];
-            gs[GR_SY + kk * LB_M + e] = t[5 + 5 * h + 1];
-            gs[GR_YY + e * LB_M + kk] = t[5 + 5 * h + 2];
-            gs[GR_YY + kk * LB_M + e] = t[5 + 5 * h + 2];
-            gs[GR_SG + kk] = t[5 + 5 * h + 3];
-            gs[GR_YG + kk] = t[5 + 5 * h + 4];
-        }
-        const int bound = H.bound;
-        const double gamma = (double)((float)t[0] / (float)t[1]);          // ys / yy in float (:591)
-        double alpha[LB_M], c[LB_M];
-        for (int tt = 0; tt < bound; ++tt) {                                // newest -> oldest (:581-589)
-            const int j = H.slot[tt];
-            double num = -gs[GR_SG + j];
-            for (int u = 0; u < tt; ++u) num -= alpha[u] * gs[GR_SY + j * LB_M + H.slot[u]];
-            alpha[tt] = num / gs[GR_SY + j * LB_M + j];
-        }
-        for (int tt = bound - 1; tt >= 0; --tt) {                           // oldest -> newest (:593-601)
-            const int j = H.slot[tt];
-            double num = -gs[GR_YG + j];
-            for (int u = 0; u < bound; ++u) num -= alpha[u] * gs[GR_YY + j * LB_M + H.slot[u]];
-            num *= gamma;
-            for (int v = bound - 1; v > tt; --v) num += c[v] * gs[GR_SY + H.slot[v] * LB_M + j];
-            const double beta = num / gs[GR_SY + j * LB_M + j];
-            c[tt] = alpha[tt] - beta;
-        }
-        double dg = -gamma * gs[GR_GG];
-        coef[0] = (float)(-gamma);
-        for (int tt = bound; tt < LB_M; ++tt) { coef[1 + tt] = 0.f; coef[1 + LB_M + tt] = 0.f; }
-        for (int tt = 0; tt < bound; ++tt) {
-            const int j = H.slot[tt];
-            coef[1 + tt] = (float)(-gamma * alpha[tt]);
-            coef[1 + LB_M + tt] = (float)c[tt];
-            dg += -gamma * alpha[tt] * gs[GR_YG + j] + c[tt] * gs[GR_SG + j];
-        }
-        dscal[PS_DG] = dg;
+    if (gram_loc) {
+        if (threadIdx.x < GR_NPART) gram_loc[threadIdx.x] = red[0][threadIdx.x];
+        return;
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < GR_DOUBLES; i += VEC_THREADS) gram[i] = gs[i];
+    gram_recursion(red[0], H, gram, coef, dscal);
+}
+
+// cross-rank version of the tail above: sum the 25 inner products over all ranks (rank order,
+// so every rank gets the same bits), then the same Gram update + scalar recursion, redundantly
+// on every rank
+__global__ void __launch_bounds__(128)
+xr_gram_kernel(XrPeers P, XrLayout lay, unsigned epoch, unsigned seq, const double *__restrict__ gram_loc,
+               HistPtrs H, double *__restrict__ gram, float *__restrict__ coef, double *__restrict__ dscal,
+               unsigned *err)
+{
+    __shared__ double t[GR_NPART];
+    xr_reduce_body(P, lay, epoch, seq, gram_loc, GR_NPART, t, err);
+    gram_recursion(t, H, gram, coef, dscal);
 }
 
 // pass B: d = coef_g g + sum_t (coef_y[t] y_t + coef_s[t] s_t)
@@ -537,8 +563,9 @@ struct Driver {
     float *x = nullptr, *xp = nullptr, *g = nullptr, *gp = nullptr, *d = nullptr;
     float *s[LB_M] = {nullptr}, *y[LB_M] = {nullptr};
     float *sc = nullptr, *coef = nullptr;
-    double *partial = nullptr, *gram = nullptr;
+    double *partial = nullptr, *gram = nullptr, *gram_loc = nullptr;
     unsigned *ticket = nullptr;
+    bool sharded = false;          // owner-sharded multi-GPU: n = local slice, scalars summed over peer memory
     allreduce_fn_t allreduce = nullptr;
     void *ctx = nullptr;
     int evals = 0;
@@ -553,7 +580,8 @@ struct Driver {
         if (!dev_alloc_t(&sc, (size_t)SC_FLOATS)) return -1;
         DCA_CUDA(cudaMemsetAsync(sc, 0, sizeof(float) * SC_FLOATS, st));
         if (!dev_alloc_t(&partial, (size_t)GR_NPART * blocks) || !dev_alloc_t(&ticket, (size_t)1) ||
-            !dev_alloc_t(&gram, (size_t)GR_DOUBLES) || !dev_alloc_t(&coef, (size_t)CF_FLOATS + 3)) return -1;
+            !dev_alloc_t(&gram, (size_t)GR_DOUBLES) || !dev_alloc_t(&coef, (size_t)CF_FLOATS + 3) ||
+            !dev_alloc_t(&gram_loc, (size_t)XR_SLOT)) return -1;
         DCA_CUDA(cudaMemsetAsync(gram, 0, sizeof(double) * GR_DOUBLES, st));
         DCA_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
         return 0;
@@ -563,7 +591,7 @@ struct Driver {
         float *v[] = {x, xp, g, gp, d};
         for (float *q : v) if (q && q != keep_x) dev_free(q);
         for (int i = 0; i < LB_M; ++i) { dev_free(s[i]); dev_free(y[i]); }
-        dev_free(sc); dev_free(partial); dev_free(ticket); dev_free(gram); dev_free(coef);
+        dev_free(sc); dev_free(partial); dev_free(ticket); dev_free(gram); dev_free(coef); dev_free(gram_loc);
     }
 
     // objective at x -> g ; returns {fx, g.d, g.g, x.x} on the host
@@ -587,6 +615,18 @@ struct Driver {
 };
 
 }  // namespace
+
+int lbfgs_preload_kernels()
+{
+    cudaFuncAttributes fa;
+    DCA_CUDA(cudaFuncGetAttributes(&fa, vec_step_kernel));
+    DCA_CUDA(cudaFuncGetAttributes(&fa, vec_twoloop_kernel));
+    DCA_CUDA(cudaFuncGetAttributes(&fa, vec_dots_kernel));
+    DCA_CUDA(cudaFuncGetAttributes(&fa, vec_update_gram_kernel));
+    DCA_CUDA(cudaFuncGetAttributes(&fa, vec_direction_kernel));
+    DCA_CUDA(cudaFuncGetAttributes(&fa, xr_gram_kernel));
+    return 0;
+}
 
 // Measurement hook: the two HBM-bound passes of one L-BFGS iteration (and the trial-step
 // kernel) on n floats with `bound` stored pairs, CUDA events on the launching stream.
@@ -621,7 +661,7 @@ int lbfgs_vector_bench(long n, int bound, int reps, float *ms_out)
         for (int r = -2; r < reps; ++r) {          // two warm-up rounds
             cudaEventRecord(e[0], st);
             DCA_LAUNCH(vec_update_gram_kernel, blocks, VEC_THREADS, 0, st, v[5], v[5 + LB_M], v[0], v[1], v[2], v[3], H, n,
-                       partial, gram, coef, dscal, ticket);
+                       partial, gram, coef, dscal, ticket, (double *)nullptr);
             cudaEventRecord(e[1], st);
             DCA_LAUNCH(vec_direction_kernel, blocks, VEC_THREADS, 0, st, v[4], v[2], H, coef, n);
             cudaEventRecord(e[2], st);
@@ -648,7 +688,9 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
 {
     const Params prm;
     Driver D;
-    D.p = p; D.n = plm_num_params(p); D.st = plm_stream(p);
+    D.p = p; D.n = plm_local_params(p); D.st = plm_stream(p);
+    D.sharded = plm_is_sharded(p);
+    if (D.sharded && allreduce) { set_error("lbfgs: an owner-sharded objective exchanges over peer memory; no all-reduce callback"); return -1; }
     D.blocks = std::min<long>(ceil_div<long>(D.n, VEC_THREADS * 4), 8L * sm_count());
     D.x = d_x; D.allreduce = allreduce; D.ctx = allreduce_ctx;
     if (D.alloc() != 0) { D.release(d_x); return -1; }
@@ -658,6 +700,9 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evw = nullptr;
     cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&evw);
+    // sharded: start the clock on every rank at the same moment (the ranks reach this point
+    // with a skew of their unequal H2D copies; without it the fastest rank's time includes it)
+    if (plm_xr_barrier(p) != 0) { D.release(d_x); return -1; }
     cudaEventRecord(ev0, st);
     bool warm_marked = (warmup_iterations <= 0);
     int evals_at_warm = 0;
@@ -776,7 +821,13 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
             // pass A: s = x - xp, y = g - gp, the new inner products, Gram update and the scalar
             // recursion (alpha, beta, gamma -> coefficients, g.d) in the last CTA
             DCA_LAUNCH(vec_update_gram_kernel, D.blocks, VEC_THREADS, 0, st,
-                       D.s[end], D.y[end], D.x, D.xp, D.g, D.gp, H, n, D.partial, D.gram, D.coef, dsc, D.ticket);
+                       D.s[end], D.y[end], D.x, D.xp, D.g, D.gp, H, n, D.partial, D.gram, D.coef, dsc, D.ticket,
+                       D.sharded ? D.gram_loc : (double *)nullptr);
+            if (D.sharded) {
+                const XrCall c = plm_xr_next(p);
+                DCA_LAUNCH(xr_gram_kernel, 1, 128, 0, st, c.P, c.lay, c.epoch, c.seq, D.gram_loc, H, D.gram, D.coef,
+                           dsc, c.err);
+            }
             // pass B: the direction as one linear combination
             DCA_LAUNCH(vec_direction_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.g, H, D.coef, n);
             ++k;

@@ -44,6 +44,7 @@
 // bandwidth (128 B/clk/SM = 32 adds/clk/SM), not by HBM.
 #include "dca_common.cuh"
 #include "dca_internal.h"
+#include "xrank.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -91,6 +92,23 @@ struct PlmProblem {
     CUtensorMap tmS;         // S as [Npad][ld] f32, box 128 x 128 (scatter tiles)
     CUtensorMap tmW;         // W as [Lq][ld] f32, box 128 x JB*q (logits stage)
     CUtensorMap tmM;         // msaT as [L][Npad] u8, box 128 x JB (logits stage)
+    // ---- owner-sharded multi-GPU mode (xrank.cuh): x, g and every L-BFGS vector hold only
+    // the LOCAL slice [fields of my sites | my coupling blocks]; W lives in the peer arena
+    bool sharded = false, connected = false;
+    bool shared_process = false;   // peers are threads of this process (tests): see plm_read_scalars
+    long Ploc = 0;           // local parameters = nq_loc + ncpl_loc
+    long nq_loc = 0;         // (site_hi - site_lo) * q fields
+    long pair0 = 0;          // pair index of my first block = pair(site_lo, site_lo + 1)
+    long ncpl_loc = 0;       // floats in my coupling blocks
+    int max_sites = 0;       // largest shard (rows of every rank's R buffer / q)
+    unsigned char *arena = nullptr;
+    XrLayout lay{};
+    XrPeers peers{};
+    float *d_R = nullptr;    // arena + off_R
+    unsigned epoch = 0, red_seq = 0;
+    unsigned *d_err = nullptr;
+    double *d_scal_loc = nullptr;
+    int n_active_own = 0;
 };
 
 // ------------------------------------------------------------------------------
@@ -191,8 +209,9 @@ plm_unpack_kernel(const float *__restrict__ x, int L, int ld, float *__restrict_
 template <int Q>
 __global__ void __launch_bounds__(LG_THREADS, 2)
 plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmM,
-                  int ld, long N, int L, const float *__restrict__ x, float *__restrict__ S, int col_tile0)
-{
+                  int ld, long N, int L, const float *__restrict__ xf, int col_lo, int col_hi,
+                  float *__restrict__ S, int col_tile0)
+{   // xf[c - col_lo] = field of column c for col_lo <= c < col_hi (the columns this GPU owns)
     constexpr int JB = LgCfg<Q>::JB;
     constexpr int NWARP = LG_THREADS / 32;
     constexpr unsigned STAGE_BYTES = JB * Q * LG_TC * 4 + JB * LG_TN;
@@ -204,7 +223,6 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col0 = (col_tile0 + blockIdx.x) * LG_TC;
     const long n0 = (long)blockIdx.y * LG_TN;
-    const int Lq = L * Q;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
@@ -217,10 +235,10 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     {
         const int c = col0 + 4 * lane;
         float4 h;
-        h.x = (c + 0 < Lq) ? x[c + 0] : 0.f;
-        h.y = (c + 1 < Lq) ? x[c + 1] : 0.f;
-        h.z = (c + 2 < Lq) ? x[c + 2] : 0.f;
-        h.w = (c + 3 < Lq) ? x[c + 3] : 0.f;
+        h.x = (c + 0 >= col_lo && c + 0 < col_hi) ? xf[c + 0 - col_lo] : 0.f;
+        h.y = (c + 1 >= col_lo && c + 1 < col_hi) ? xf[c + 1 - col_lo] : 0.f;
+        h.z = (c + 2 >= col_lo && c + 2 < col_hi) ? xf[c + 2 - col_lo] : 0.f;
+        h.w = (c + 3 >= col_lo && c + 3 < col_hi) ? xf[c + 3 - col_lo] : 0.f;
 #pragma unroll
         for (int t = 0; t < 16; ++t) acc[t] = h;
     }
@@ -468,6 +486,66 @@ plm_scatter_kernel(const __grid_constant__ CUtensorMap tmS, int ld, const uint8_
 }
 
 // ------------------------------------------------------------------------------
+// tail shared by the assemble kernels: one fused block reduction of the four sums, the
+// CTA's partials to `red` (SoA: red[c * nblk + blk]; slots of CTAs that own no pair stay
+// zero), a ticket, and -- in the last CTA to finish -- the fixed-order reduction
+//   scal = { fx = reg + sum fxpart, g.d, g.g, x.x }.
+__device__ __forceinline__ void assemble_finish(double s_reg, double s_dg, double s_gg, double s_xx,
+                                                double *__restrict__ red, const double *__restrict__ fxpart,
+                                                int nfx, unsigned *__restrict__ ticket, unsigned n_active,
+                                                double *__restrict__ scal)
+{
+    __shared__ double wsum[8][4];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    s_reg = warp_sum(s_reg); s_dg = warp_sum(s_dg); s_gg = warp_sum(s_gg); s_xx = warp_sum(s_xx);
+    if (lane == 0) { wsum[wid][0] = s_reg; wsum[wid][1] = s_dg; wsum[wid][2] = s_gg; wsum[wid][3] = s_xx; }
+    __syncthreads();
+    const int nblk = gridDim.x * gridDim.y;
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x < 4) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += wsum[w][threadIdx.x];
+        red[(size_t)threadIdx.x * nblk + blk] = r;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicInc(ticket, n_active - 1u) == n_active - 1u);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last CTA: everything is visible; reduce in a fixed order (4 independent loads in flight)
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = 0; c < 4; ++c) {
+        const double *rc = red + (size_t)c * nblk;
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        int t = threadIdx.x;
+        for (; t + 768 < nblk; t += 1024) { p0 += rc[t]; p1 += rc[t + 256]; p2 += rc[t + 512]; p3 += rc[t + 768]; }
+        for (; t < nblk; t += 256) p0 += rc[t];
+        acc[c] = (p0 + p1) + (p2 + p3);
+    }
+    {
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        int t = threadIdx.x;
+        for (; t + 768 < nfx; t += 1024) { p0 += fxpart[t]; p1 += fxpart[t + 256]; p2 += fxpart[t + 512]; p3 += fxpart[t + 768]; }
+        for (; t < nfx; t += 256) p0 += fxpart[t];
+        acc[0] += (p0 + p1) + (p2 + p3);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = warp_sum(acc[c]);
+    __syncthreads();
+    if (lane == 0) { wsum[wid][0] = acc[0]; wsum[wid][1] = acc[1]; wsum[wid][2] = acc[2]; wsum[wid][3] = acc[3]; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += wsum[w][threadIdx.x];
+        scal[threadIdx.x] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------
 // assemble: g = 2*lambda*x + G^T-part + G-part in the reference's layout, plus
 // the reductions every L-BFGS step needs, in one pass over x, and -- in the
 // last CTA to finish (ticket counter, fixed summation order) -- the final
@@ -486,8 +564,6 @@ plm_assemble_kernel(const float *__restrict__ x, const float *__restrict__ G, si
 {
     constexpr int QQ = Q * Q;
     __shared__ float tile[AS_JG * QQ];
-    __shared__ double wsum[8][4];
-    __shared__ bool is_last;
     const int i = blockIdx.y;
     const int j0 = blockIdx.x * AS_JG;
     const bool any = (j0 + AS_JG - 1 > i);
@@ -552,53 +628,158 @@ plm_assemble_kernel(const float *__restrict__ x, const float *__restrict__ G, si
         s_gg += (double)gv * gv;
     }
 
-    // one fused block reduction of the four sums
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    s_reg = warp_sum(s_reg); s_dg = warp_sum(s_dg); s_gg = warp_sum(s_gg); s_xx = warp_sum(s_xx);
-    if (lane == 0) { wsum[wid][0] = s_reg; wsum[wid][1] = s_dg; wsum[wid][2] = s_gg; wsum[wid][3] = s_xx; }
+    assemble_finish(s_reg, s_dg, s_gg, s_xx, red, fxpart, nfx, ticket, n_active, scal);
+}
+
+// ==============================================================================
+// Owner-sharded multi-GPU mode (xrank.cuh).  Rank r owns the
+// sites [lo, hi) and the LOCAL parameter slice
+//   xl[(i - lo)*Q + a]                               fields,    lo <= i < hi
+//   xl[nq + (pair(i,j) - pair0)*QQ + a*Q + b]        couplings, lo <= i < hi, j > i
+// (a contiguous run of the reference's vector: x[lo*Q .. hi*Q) and
+//  x[Lq + pair0*QQ .. Lq + pair(hi,hi+1)*QQ)).  Per evaluation two exchanges over
+// peer memory, both fused into the kernel that produces the data:
+//   unpack_push   J_ij of my blocks -> my W (columns of site i) and, by P2P stores,
+//                 the W of owner(j) (columns of site j)
+//   export        my G rows (i,a), i < lo  (site-j conditional's half of dJ_ij, j mine)
+//                 summed over the n-splits -> R of owner(i)
+// each followed by a flag barrier (xr_barrier_kernel); the 4 objective scalars are
+// summed across ranks in rank order by xr_reduce_kernel (identical bits on all ranks).
+
+template <int Q>
+__global__ void __launch_bounds__(256)
+plm_unpack_push_kernel(const float *__restrict__ xl, long nq, long pair0, int L, int ld, int lo,
+                       XrPeers P, size_t off_W)
+{
+    constexpr int QQ = Q * Q;
+    __shared__ float tile[AS_JG * QQ];
+    const int i = lo + blockIdx.y;
+    const int j0 = blockIdx.x * AS_JG;
+    const int jlo = max(j0, i + 1), jhi = min(j0 + AS_JG, L);
+    const int npair = jhi - jlo;
+    if (npair <= 0) return;
+    const float *xb = xl + nq + (pair_index(L, i, jlo) - pair0) * QQ;    // npair consecutive blocks
+    for (int t = threadIdx.x; t < npair * QQ; t += 256) tile[t] = xb[t];
     __syncthreads();
-    const int nblk = gridDim.x * gridDim.y;
-    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
-    if (threadIdx.x < 4) {
-        double r = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) r += wsum[w][threadIdx.x];
-        red[(size_t)threadIdx.x * nblk + blk] = r;
-        __threadfence();
+    // my columns (i,a), rows (j,b):  W_me[(j,b)][(i,a)] = J_ij(a,b)
+    float *Wme = reinterpret_cast<float *>(P.arena[P.rank] + off_W);
+    for (int t = threadIdx.x; t < npair * QQ; t += 256) {
+        const int jj = t / QQ, e = t - jj * QQ;
+        const int b = e / Q, a = e - b * Q;
+        Wme[((long)(jlo + jj) * Q + b) * ld + i * Q + a] = tile[jj * QQ + a * Q + b];
+    }
+    // columns (j,b) belong to owner(j):  W_owner[(i,a)][(j,b)] = J_ij(a,b);
+    // npair*Q contiguous floats per row (i,a), stored over NVLink when owner(j) != me
+    const int run = npair * Q;
+    for (int t = threadIdx.x; t < Q * run; t += 256) {
+        const int a = t / run, c = t - a * run;
+        const int jj = c / Q, b = c - jj * Q;
+        float *Wo = reinterpret_cast<float *>(P.arena[xr_owner(P, jlo + jj)] + off_W);
+        Wo[((long)i * Q + a) * ld + jlo * Q + c] = tile[jj * QQ + a * Q + b];
+    }
+}
+
+// one CTA per G row (i,a) with i < lo: those rows are the site-j conditional's contribution
+// to blocks (i, j) owned by a lower rank.  Sum the n-split partials, store into the owner's R.
+template <int Q>
+__global__ void __launch_bounds__(128)
+plm_export_kernel(const float *__restrict__ G, size_t g_split_stride, int nsplit, int ld, int lo, int hi,
+                  XrPeers P, size_t off_R)
+{
+    const int row = blockIdx.x;
+    const int o = xr_owner(P, row / Q);
+    float *R = reinterpret_cast<float *>(P.arena[o] + off_R) + (size_t)(row - P.bounds[o] * Q) * ld;
+    const float *g = G + (size_t)row * ld;
+    for (int c = lo * Q + threadIdx.x; c < hi * Q; c += 128) {
+        float v = 0.f;
+        for (int s = 0; s < nsplit; ++s) v += g[(size_t)s * g_split_stride + c];
+        R[c] = v;
+    }
+}
+
+// gradient of my slice: 2*lambda*x + G[(j,b)][(i,a)] (my conditional, transposed through
+// smem) + the site-j conditional's half, from my own G when I own j, else from R.
+template <int Q>
+__global__ void __launch_bounds__(256)
+plm_assemble_owner_kernel(const float *__restrict__ xl, long nq, long pair0, const float *__restrict__ G,
+                          size_t g_split_stride, int nsplit, const float *__restrict__ R, int L, int ld,
+                          float lh, float lJ, int lo, int hi, const float *__restrict__ dl,
+                          float *__restrict__ gl, double *__restrict__ red, const double *__restrict__ fxpart,
+                          int nfx, unsigned *__restrict__ ticket, unsigned n_active, double *__restrict__ scal)
+{
+    constexpr int QQ = Q * Q;
+    __shared__ float tile[AS_JG * QQ];
+    const int i = lo + blockIdx.y;
+    const int j0 = blockIdx.x * AS_JG;
+    const bool any = (j0 + AS_JG - 1 > i);
+    if (!any && blockIdx.x != 0) return;
+    const int jlo = max(j0, i + 1), jhi = min(j0 + AS_JG, L);
+    const int npair = max(0, jhi - jlo);
+    double s_reg = 0.0, s_dg = 0.0, s_gg = 0.0, s_xx = 0.0;
+
+    if (blockIdx.x == 0 && threadIdx.x < Q) {
+        const int a = threadIdx.x;
+        const long k = (long)(i - lo) * Q + a;
+        const float h = xl[k];
+        float gv = 2.f * lh * h;
+        float col = 0.f;
+        for (int s = 0; s < nsplit; ++s) {
+            const float *Gs = G + (size_t)s * g_split_stride;
+            for (int b = 0; b < Q; ++b) col += Gs[((long)i * Q + b) * ld + i * Q + a];
+        }
+        gv += col;
+        s_reg += (double)lh * h * h;
+        s_xx += (double)h * h;
+        gl[k] = gv;
+        if (dl) s_dg += (double)gv * dl[k];
+        s_gg += (double)gv * gv;
+    }
+    for (int t = threadIdx.x; t < npair * QQ; t += 256) {
+        const int jj = t / QQ, e = t - jj * QQ;
+        const int b = e / Q, a = e - b * Q;
+        const int j = jlo + jj;
+        float u = 0.f;
+        for (int s = 0; s < nsplit; ++s)
+            u += G[(size_t)s * g_split_stride + ((long)j * Q + b) * ld + i * Q + a];
+        tile[jj * QQ + a * Q + b] = u;
     }
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicInc(ticket, n_active - 1u) == n_active - 1u);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // last CTA: everything is visible; reduce in a fixed order (4 independent loads in flight)
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c = 0; c < 4; ++c) {
-        const double *rc = red + (size_t)c * nblk;
-        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-        int t = threadIdx.x;
-        for (; t + 768 < nblk; t += 1024) { p0 += rc[t]; p1 += rc[t + 256]; p2 += rc[t + 512]; p3 += rc[t + 768]; }
-        for (; t < nblk; t += 256) p0 += rc[t];
-        acc[c] = (p0 + p1) + (p2 + p3);
+    const long base = nq + (pair_index(L, i, jlo) - pair0) * QQ;
+    for (int t = threadIdx.x; t < npair * QQ; t += 256) {
+        const int jj = t / QQ, e = t - jj * QQ;
+        const int a = e / Q, b = e - a * Q;
+        const int j = jlo + jj;
+        const float xv = xl[base + t];
+        float gv = 2.f * lJ * xv;
+        gv += tile[t];
+        float v = 0.f;
+        if (j < hi) {
+            for (int s = 0; s < nsplit; ++s)
+                v += G[(size_t)s * g_split_stride + ((long)i * Q + a) * ld + j * Q + b];
+        } else {
+            v = R[((long)(i - lo) * Q + a) * ld + j * Q + b];
+        }
+        gv += v;
+        gl[base + t] = gv;
+        s_reg += (double)lJ * xv * xv; s_xx += (double)xv * xv;
+        if (dl) s_dg += (double)gv * dl[base + t];
+        s_gg += (double)gv * gv;
     }
-    {
-        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-        int t = threadIdx.x;
-        for (; t + 768 < nfx; t += 1024) { p0 += fxpart[t]; p1 += fxpart[t + 256]; p2 += fxpart[t + 512]; p3 += fxpart[t + 768]; }
-        for (; t < nfx; t += 256) p0 += fxpart[t];
-        acc[0] += (p0 + p1) + (p2 + p3);
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[c] = warp_sum(acc[c]);
-    __syncthreads();
-    if (lane == 0) { wsum[wid][0] = acc[0]; wsum[wid][1] = acc[1]; wsum[wid][2] = acc[2]; wsum[wid][3] = acc[3]; }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        double r = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) r += wsum[w][threadIdx.x];
-        scal[threadIdx.x] = r;
-    }
+    assemble_finish(s_reg, s_dg, s_gg, s_xx, red, fxpart, nfx, ticket, n_active, scal);
+}
+
+__global__ void xr_barrier_kernel(XrPeers P, size_t off_flags, unsigned epoch, unsigned *err)
+{
+    if ((int)threadIdx.x < P.world) xr_signal_and_wait(P, off_flags, epoch, threadIdx.x, err);
+}
+
+// out[k] = sum over ranks (in rank order) of local[k], k < n <= XR_SLOT: every rank stores
+// its values into every rank's slot block, signals, waits for all, sums.
+__global__ void __launch_bounds__(128)
+xr_reduce_kernel(XrPeers P, XrLayout lay, unsigned epoch, unsigned seq, const double *__restrict__ local,
+                 int n, double *__restrict__ out, unsigned *err)
+{
+    xr_reduce_body(P, lay, epoch, seq, local, n, out, err);
 }
 
 // ------------------------------------------------------------------------------
@@ -606,10 +787,11 @@ plm_assemble_kernel(const float *__restrict__ x, const float *__restrict__ G, si
 // sequences accumulated in file order in float32 exactly like the reference.
 template <int Q>
 __global__ void plm_init_fields_kernel(const uint8_t *__restrict__ msaT, const float *__restrict__ w,
-                                       long N, long Npad, int L, float meff, float *__restrict__ x)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L) return;
+                                       long N, long Npad, int site_lo, int site_hi, float meff,
+                                       float *__restrict__ x)
+{   // x[a + Q*(i - site_lo)]: the whole vector (site_lo = 0) or an owner's local slice
+    const int i = site_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= site_hi) return;
     float f[Q];
 #pragma unroll
     for (int a = 0; a < Q; ++a) f[a] = 0.f;
@@ -629,7 +811,7 @@ __global__ void plm_init_fields_kernel(const uint8_t *__restrict__ msaT, const f
     }
     const float av = __fdiv_rn(s, (float)Q);
 #pragma unroll
-    for (int a = 0; a < Q; ++a) x[a + Q * i] = f[a] - av;
+    for (int a = 0; a < Q; ++a) x[a + Q * (i - site_lo)] = f[a] - av;
 }
 
 // ------------------------------------------------------------------------------
@@ -652,6 +834,22 @@ static int plm_setup_t(PlmProblem *p)
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
     DCA_CUDA(cudaFuncSetAttribute(plm_logits_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     DCA_CUDA(cudaFuncSetAttribute(plm_scatter_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+    if (p->sharded) {
+        // CUDA loads kernels lazily, and loading one synchronises the context: a rank that
+        // first-launches a kernel while a peer thread of the same process spins in a barrier
+        // would dead-lock.  Load everything the collective path launches up front.
+        cudaFuncAttributes fa;
+        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_unpack_push_kernel<Q>));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_export_kernel<Q>));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_assemble_owner_kernel<Q>));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_logits_kernel<Q>));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_softmax_kernel<Q>));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_scatter_kernel<Q>));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_init_fields_kernel<Q>));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, xr_barrier_kernel));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, xr_reduce_kernel));
+        if (lbfgs_preload_kernels() != 0) return -1;
+    }
     DCA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -662,23 +860,33 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
 {
     cudaStream_t st = p->stream;
     const int L = p->L, ld = p->ld;
+    const int lo = p->site_lo, hi = p->site_hi, nsites = hi - lo;
     int evi = 0;
 #define PLM_MARK() do { if (ev) cudaEventRecord(ev[evi++], st); } while (0)
+    if (p->sharded && !p->connected) { set_error("plm: sharded objective used before its peers were connected"); return -1; }
     PLM_MARK();
-    dim3 gridU(ceil_div(L, AS_JG), L);
-    DCA_LAUNCH((plm_unpack_kernel<Q>), gridU, 256, 0, st, d_x, L, ld, p->d_W);
+    dim3 gridU(ceil_div(L, AS_JG), p->sharded ? nsites : L);
+    if (p->sharded) {
+        // fused unpack + exchange: my blocks go to my W and, by P2P stores, to the W of owner(j)
+        DCA_LAUNCH((plm_unpack_push_kernel<Q>), gridU, 256, 0, st, d_x, p->nq_loc, p->pair0, L, ld, lo,
+                   p->peers, p->lay.off_W);
+        DCA_LAUNCH(xr_barrier_kernel, 1, 32, 0, st, p->peers, p->lay.off_flags, ++p->epoch, p->d_err);
+    } else {
+        DCA_LAUNCH((plm_unpack_kernel<Q>), gridU, 256, 0, st, d_x, L, ld, p->d_W);
+    }
     PLM_MARK();
 
     const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN + 64 + 1024;
     dim3 gridA(p->col_tiles, (unsigned)(p->Npad / LG_TN));
+    // fields: the head of the local slice (sharded) or of the whole vector
+    const int col_lo = p->sharded ? lo * Q : 0, col_hi = p->sharded ? hi * Q : L * Q;
     DCA_LAUNCH((plm_logits_kernel<Q>), gridA, LG_THREADS, smemA, st,
-               p->tmW, p->tmM, ld, p->N, L, d_x, p->d_S, p->col_tile0);
+               p->tmW, p->tmM, ld, p->N, L, d_x, col_lo, col_hi, p->d_S, p->col_tile0);
     PLM_MARK();
 
-    const int nsites = p->site_hi - p->site_lo;
     dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
     DCA_LAUNCH((plm_softmax_kernel<Q>), gridB, 128, 0, st,
-               p->d_S, ld, p->d_msa, p->d_w, p->N, L, p->site_lo, p->site_hi,
+               p->d_S, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
                p->chunk, p->warm, p->carry, p->d_fxpart);
     PLM_MARK();
 
@@ -691,9 +899,21 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
     PLM_MARK();
 
     const int nfx = (int)(gridB.x * p->nscan);
-    DCA_LAUNCH((plm_assemble_kernel<Q>), gridU, 256, 0, st,
-               d_x, p->d_G, gstride, p->nsplit, L, ld, p->lh, p->lJ, p->site_lo, p->site_hi,
-               d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket, (unsigned)p->n_active, p->d_scal);
+    if (p->sharded) {
+        if (lo > 0)
+            DCA_LAUNCH((plm_export_kernel<Q>), lo * Q, 128, 0, st, p->d_G, gstride, p->nsplit, ld, lo, hi,
+                       p->peers, p->lay.off_R);
+        DCA_LAUNCH(xr_barrier_kernel, 1, 32, 0, st, p->peers, p->lay.off_flags, ++p->epoch, p->d_err);
+        DCA_LAUNCH((plm_assemble_owner_kernel<Q>), gridU, 256, 0, st,
+                   d_x, p->nq_loc, p->pair0, p->d_G, gstride, p->nsplit, p->d_R, L, ld, p->lh, p->lJ, lo, hi,
+                   d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket, (unsigned)p->n_active_own, p->d_scal_loc);
+        DCA_LAUNCH(xr_reduce_kernel, 1, 128, 0, st, p->peers, p->lay, ++p->epoch, p->red_seq++,
+                   p->d_scal_loc, (int)PS_COUNT, p->d_scal, p->d_err);
+    } else {
+        DCA_LAUNCH((plm_assemble_kernel<Q>), gridU, 256, 0, st,
+                   d_x, p->d_G, gstride, p->nsplit, L, ld, p->lh, p->lJ, lo, hi,
+                   d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket, (unsigned)p->n_active, p->d_scal);
+    }
     PLM_MARK();
 #undef PLM_MARK
     DCA_CUDA(cudaGetLastError());
@@ -706,8 +926,10 @@ static void plm_free(PlmProblem *p)
     if (!p) return;
     if (p->stream) cudaStreamSynchronize(p->stream);
     dev_free(p->d_msa); dev_free(p->d_msaT); dev_free(p->d_perm); dev_free(p->d_w);
-    dev_free(p->d_W); dev_free(p->d_G); dev_free(p->d_S); dev_free(p->d_fxpart);
-    dev_free(p->d_red); dev_free(p->d_scal); dev_free(p->d_ticket);
+    if (!p->sharded) dev_free(p->d_W);
+    dev_free(p->d_G); dev_free(p->d_S); dev_free(p->d_fxpart);
+    dev_free(p->d_red); dev_free(p->d_scal); dev_free(p->d_ticket); dev_free(p->d_scal_loc);
+    if (p->arena) cudaFree(p->arena);        // peers must have disconnected first (plm_disconnect)
     if (p->h_scal) host_pinned_free(p->h_scal);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -718,12 +940,37 @@ static void plm_plan_scan(PlmProblem *p)
     p->nscan = ceil_div<long>(p->N, p->chunk);
 }
 
-PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
-                       float lambda_h, float lambda_J, int site_lo, int site_hi)
+// byte offsets of the peer arena; identical on every rank (depends on L, q, the padded
+// row length and the largest shard only)
+static XrLayout xr_layout(int Lq, int ld, int max_sites, int q)
+{
+    auto up = [](size_t v) { return (v + 4095) & ~(size_t)4095; };
+    XrLayout l;
+    l.off_flags = 0;
+    l.off_slots = 1024;
+    l.off_W = up(l.off_slots + sizeof(double) * 2 * XR_MAX_RANKS * XR_SLOT);
+    l.off_R = up(l.off_W + sizeof(float) * (size_t)Lq * ld);
+    l.bytes = up(l.off_R + sizeof(float) * (size_t)max_sites * q * ld);
+    return l;
+}
+
+static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
+                                   float lambda_h, float lambda_J, int site_lo, int site_hi,
+                                   int rank, int world, const int *bounds)
 {
     if (require_device() != 0) return nullptr;
     if (q != 21 && q != 5) { set_error("plm: num_site_states must be 21 or 5 (got %d)", q); return nullptr; }
     if (N <= 0 || L < 2) { set_error("plm: empty alignment (N=%ld L=%d)", N, L); return nullptr; }
+    const bool sharded = (bounds != nullptr);
+    if (sharded) {
+        if (world < 1 || world > XR_MAX_RANKS || rank < 0 || rank >= world) {
+            set_error("plm: bad rank %d / world %d (at most %d ranks)", rank, world, XR_MAX_RANKS); return nullptr;
+        }
+        if (bounds[0] != 0 || bounds[world] != L) { set_error("plm: shard bounds must run from 0 to L"); return nullptr; }
+        for (int r = 0; r < world; ++r)
+            if (bounds[r + 1] <= bounds[r]) { set_error("plm: every rank must own at least one site (rank %d owns none)", r); return nullptr; }
+        site_lo = bounds[rank]; site_hi = bounds[rank + 1];
+    }
     if (site_lo < 0 || site_hi > L || site_lo >= site_hi) {
         set_error("plm: bad site shard [%d,%d) for L=%d", site_lo, site_hi, L); return nullptr;
     }
@@ -742,9 +989,26 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     p->col_tiles = ceil_div(site_hi * q, LG_TC) - p->col_tile0;
     p->red_blocks = ceil_div(L, AS_JG) * L;
     p->n_active = 0;                 // assemble CTAs that own a pair or the fields of a site
+    p->n_active_own = 0;             // ... of my sites only (owner-sharded mode)
     for (int i = 0; i < L; ++i)
-        for (int bx = 0; bx < ceil_div(L, AS_JG); ++bx)
-            p->n_active += (bx == 0 || bx * AS_JG + AS_JG - 1 > i) ? 1 : 0;
+        for (int bx = 0; bx < ceil_div(L, AS_JG); ++bx) {
+            const int act = (bx == 0 || bx * AS_JG + AS_JG - 1 > i) ? 1 : 0;
+            p->n_active += act;
+            if (i >= site_lo && i < site_hi) p->n_active_own += act;
+        }
+    p->Ploc = p->P;
+    if (sharded) {
+        p->sharded = true;
+        p->peers.rank = rank; p->peers.world = world;
+        p->max_sites = 0;
+        for (int r = 0; r <= XR_MAX_RANKS; ++r) p->peers.bounds[r] = (r <= world) ? bounds[r] : L;
+        for (int r = 0; r < world; ++r) p->max_sites = std::max(p->max_sites, bounds[r + 1] - bounds[r]);
+        p->nq_loc = (long)(site_hi - site_lo) * q;
+        p->pair0 = pair_index(L, site_lo, site_lo + 1);
+        p->ncpl_loc = (pair_index(L, site_hi, site_hi + 1) - p->pair0) * q * q;
+        p->Ploc = p->nq_loc + p->ncpl_loc;
+        p->lay = xr_layout(p->Lq, p->ld, p->max_sites, q);
+    }
     {   // scatter plan: balanced site tiles, and the n-split count that minimises the
         // makespan ceil(CTAs / SMs) / nsplit of equal-cost CTAs (1 CTA per SM), with a
         // small penalty per split for the extra G traffic the assemble kernel reads
@@ -754,7 +1018,7 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
         const int sms = sm_count();
         double best = 1e300;
         int best_s = 1;
-        for (int s = 1; s <= 8; ++s) {
+        for (int s = 1; s <= (sharded ? 16 : 8); ++s) {
             if (s > 1 && p->nchunk / s < 4) break;
             const double cost = (double)ceil_div<long>(tiles * s, sms) / s * (1.0 + 0.02 * s);
             if (cost < best - 1e-12) { best = cost; best_s = s; }
@@ -767,7 +1031,7 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     for (long n = 0; n < N; ++n) meff += h_w[n];     // plmdca_numerics.cpp:46
     p->h_meff = meff;
     // the carry scan is latency bound on small problems: shorter chains = more of them
-    if ((long)L * (N / 32) < 50000) p->chunk = 16;
+    if ((long)(site_hi - site_lo) * (N / 32) < 50000) p->chunk = 16;
     plm_plan_scan(p);
 
 #define PLM_TRY(call)                                                                 \
@@ -784,7 +1048,21 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     PLM_ALLOC(p->d_msaT, (size_t)L * p->Npad);
     PLM_ALLOC(p->d_perm, (size_t)p->site_tiles * p->sites_per_tile * p->nchunk * PERM_REC);
     PLM_ALLOC(p->d_w, sizeof(float) * (size_t)N);
-    PLM_ALLOC(p->d_W, sizeof(float) * (size_t)p->Lq * p->ld);
+    if (sharded) {
+        // the peer arena is exported through CUDA IPC: a plain cudaMalloc of its own, never
+        // a sub-allocation of the caching allocator
+        PLM_TRY(cudaMalloc(reinterpret_cast<void **>(&p->arena), p->lay.bytes));
+        PLM_TRY(cudaMemsetAsync(p->arena, 0, p->lay.bytes, p->stream));
+        p->d_W = reinterpret_cast<float *>(p->arena + p->lay.off_W);
+        p->d_R = reinterpret_cast<float *>(p->arena + p->lay.off_R);
+        for (int r = 0; r < XR_MAX_RANKS; ++r) p->peers.arena[r] = nullptr;
+        p->peers.arena[rank] = p->arena;
+        p->connected = (world == 1);
+        PLM_ALLOC(p->d_scal_loc, sizeof(double) * 8);
+    } else {
+        PLM_ALLOC(p->d_W, sizeof(float) * (size_t)p->Lq * p->ld);
+        PLM_TRY(cudaMemsetAsync(p->d_W, 0, sizeof(float) * (size_t)p->Lq * p->ld, p->stream));
+    }
     PLM_ALLOC(p->d_G, sizeof(float) * (size_t)p->nsplit * p->Lq * p->ld);
     PLM_ALLOC(p->d_S, sizeof(float) * (size_t)p->Npad * p->ld);
     PLM_ALLOC(p->d_fxpart, sizeof(double) * (size_t)(N / 8 + 1) * L);   // chunk >= 8
@@ -793,11 +1071,12 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
     PLM_ALLOC(p->d_ticket, sizeof(unsigned));
     PLM_TRY(cudaMemsetAsync(p->d_ticket, 0, sizeof(unsigned), p->stream));
     PLM_ALLOC(p->d_scal, sizeof(double) * 16);
+    PLM_TRY(cudaMemsetAsync(p->d_scal, 0, sizeof(double) * 16, p->stream));
+    p->d_err = reinterpret_cast<unsigned *>(p->d_scal + PS_COUNT);       // read back with the scalars
     p->h_scal = static_cast<double *>(host_pinned_alloc(sizeof(double) * 16));
     if (!p->h_scal) { plm_free(p); return nullptr; }
     PLM_TRY(cudaMemcpyAsync(p->d_msa, h_msa, (size_t)N * L, cudaMemcpyHostToDevice, p->stream));
     PLM_TRY(cudaMemcpyAsync(p->d_w, h_w, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, p->stream));
-    PLM_TRY(cudaMemsetAsync(p->d_W, 0, sizeof(float) * (size_t)p->Lq * p->ld, p->stream));
     PLM_TRY(cudaMemsetAsync(p->d_S, 0, sizeof(float) * (size_t)p->Npad * p->ld, p->stream));
     PLM_TRY(cudaMemsetAsync(p->d_fxpart, 0, sizeof(double) * (size_t)(N / 8 + 1) * L, p->stream));
     if (make_tensor_map_2d(&p->tmS, 4, p->d_S, (unsigned long long)p->ld, (unsigned long long)p->Npad,
@@ -815,6 +1094,74 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
 #undef PLM_TRY
 #undef PLM_ALLOC
     return p;
+}
+
+PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
+                       float lambda_h, float lambda_J, int site_lo, int site_hi)
+{
+    return plm_create_impl(h_msa, h_w, N, L, q, lambda_h, lambda_J, site_lo, site_hi, 0, 1, nullptr);
+}
+
+PlmProblem *plm_create_sharded(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
+                               float lambda_h, float lambda_J, int rank, int world, const int *bounds)
+{
+    if (!bounds) { set_error("plm: shard bounds missing"); return nullptr; }
+    return plm_create_impl(h_msa, h_w, N, L, q, lambda_h, lambda_J, 0, 0, rank, world, bounds);
+}
+
+// peers: device pointers of every rank's arena valid in THIS process (IPC-opened, or raw
+// when the ranks share a process); the own entry is ignored
+int plm_connect(PlmProblem *p, void *const *arenas, bool shared_process)
+{
+    p->shared_process = shared_process;
+    if (!p->sharded) { set_error("plm_connect: not a sharded objective"); return -1; }
+    for (int r = 0; r < p->peers.world; ++r) {
+        if (r == p->peers.rank) continue;
+        if (!arenas[r]) { set_error("plm_connect: arena of rank %d missing", r); return -1; }
+        p->peers.arena[r] = static_cast<unsigned char *>(arenas[r]);
+    }
+    p->connected = true;
+    return 0;
+}
+
+void plm_disconnect(PlmProblem *p)
+{
+    if (!p->sharded) return;
+    cudaStreamSynchronize(p->stream);
+    for (int r = 0; r < p->peers.world; ++r)
+        if (r != p->peers.rank) p->peers.arena[r] = nullptr;
+    p->connected = (p->peers.world == 1);
+}
+
+void *plm_arena(const PlmProblem *p) { return p->arena; }
+size_t plm_arena_bytes(const PlmProblem *p) { return p->sharded ? p->lay.bytes : 0; }
+bool plm_is_sharded(const PlmProblem *p) { return p->sharded; }
+long plm_local_params(const PlmProblem *p) { return p->Ploc; }
+
+// where the local slice sits in the reference's parameter vector:
+// out = {field offset, field count, coupling offset, coupling count}
+void plm_local_layout(const PlmProblem *p, long *out)
+{
+    if (!p->sharded) { out[0] = 0; out[1] = p->Lq; out[2] = p->Lq; out[3] = p->P - p->Lq; return; }
+    out[0] = (long)p->site_lo * p->q; out[1] = p->nq_loc;
+    out[2] = (long)p->Lq + p->pair0 * p->q * p->q; out[3] = p->ncpl_loc;
+}
+
+// align the ranks (flag barrier on the stream); no-op unless sharded
+int plm_xr_barrier(PlmProblem *p)
+{
+    if (!p->sharded) return 0;
+    if (!p->connected) { set_error("plm: sharded objective used before its peers were connected"); return -1; }
+    DCA_LAUNCH(xr_barrier_kernel, 1, 32, 0, p->stream, p->peers, p->lay.off_flags, ++p->epoch, p->d_err);
+    DCA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+XrCall plm_xr_next(PlmProblem *p)
+{
+    XrCall c;
+    c.P = p->peers; c.lay = p->lay; c.epoch = ++p->epoch; c.seq = p->red_seq++; c.err = p->d_err;
+    return c;
 }
 
 void plm_destroy(PlmProblem *p) { plm_free(p); }
@@ -836,7 +1183,7 @@ int plm_eval_device(PlmProblem *p, const float *d_x, float *d_g, const float *d_
 }
 
 // one evaluation with CUDA events between the kernels, on the stream they are
-// launched on: ms[0..4] = unpack, logits, softmax, scatter, assemble+finalize
+// launched on: ms[0..4] = unpack (+exchange), logits, softmax, scatter, (export +) assemble+finalize
 int plm_eval_timed(PlmProblem *p, const float *d_x, float *d_g, float *ms)
 {
     cudaEvent_t ev[PLM_NUM_KERNEL_TIMES + 1];
@@ -855,23 +1202,35 @@ void plm_describe(const PlmProblem *p, long *out)
     out[5] = p->nsplit; out[6] = p->nchunk; out[7] = p->col_tiles; out[8] = p->Npad; out[9] = p->nscan;
 }
 
+// the PS_COUNT scalars plus the peer-timeout flag behind them: one small D2H + stream sync
 int plm_read_scalars(PlmProblem *p, double *out)
 {
-    DCA_CUDA(cudaMemcpyAsync(p->h_scal, p->d_scal, sizeof(double) * PS_COUNT, cudaMemcpyDeviceToHost, p->stream));
+    // Ranks sharing one process (and one GPU) share its copy-engine queues: a D2H copy parked
+    // behind my spinning barrier kernel would block the peer's H2D copies, i.e. the very work
+    // the barrier waits for.  Drain the stream first in that (test-only) configuration.
+    if (p->shared_process) DCA_CUDA(cudaStreamSynchronize(p->stream));
+    DCA_CUDA(cudaMemcpyAsync(p->h_scal, p->d_scal, sizeof(double) * (PS_COUNT + 1), cudaMemcpyDeviceToHost, p->stream));
     DCA_CUDA(cudaStreamSynchronize(p->stream));
     for (int k = 0; k < PS_COUNT; ++k) out[k] = p->h_scal[k];
+    if (*reinterpret_cast<const unsigned *>(p->h_scal + PS_COUNT) != 0u) {
+        set_error("plm: a peer GPU did not reach the exchange within %.0f s (rank %d of %d)",
+                  XR_TIMEOUT_NS * 1e-9, p->peers.rank, p->peers.world);
+        return -1;
+    }
     return 0;
 }
 
+// initial point of the whole vector, or of the local slice of a sharded objective
 int plm_init_x_device(PlmProblem *p, float *d_x)
 {
-    DCA_CUDA(cudaMemsetAsync(d_x, 0, sizeof(float) * (size_t)p->P, p->stream));
+    DCA_CUDA(cudaMemsetAsync(d_x, 0, sizeof(float) * (size_t)p->Ploc, p->stream));
+    const int lo = p->sharded ? p->site_lo : 0, hi = p->sharded ? p->site_hi : p->L;
     if (p->q == 21)
-        DCA_LAUNCH((plm_init_fields_kernel<21>), ceil_div(p->L, 64), 64, 0, p->stream,
-                   p->d_msaT, p->d_w, p->N, p->Npad, p->L, p->h_meff, d_x);
+        DCA_LAUNCH((plm_init_fields_kernel<21>), ceil_div(hi - lo, 64), 64, 0, p->stream,
+                   p->d_msaT, p->d_w, p->N, p->Npad, lo, hi, p->h_meff, d_x);
     else
-        DCA_LAUNCH((plm_init_fields_kernel<5>), ceil_div(p->L, 64), 64, 0, p->stream,
-                   p->d_msaT, p->d_w, p->N, p->Npad, p->L, p->h_meff, d_x);
+        DCA_LAUNCH((plm_init_fields_kernel<5>), ceil_div(hi - lo, 64), 64, 0, p->stream,
+                   p->d_msaT, p->d_w, p->N, p->Npad, lo, hi, p->h_meff, d_x);
     DCA_CUDA(cudaGetLastError());
     return 0;
 }

@@ -6,10 +6,15 @@ How the hot path shards:
 * reweighting  -- rows are independent: rank r computes c_i for its row range against
   the replicated MSA; one all-gather of N uint32 counts.
 * plmDCA       -- the loop-carried softmax chain is per site, so SITES are sharded,
-  never sequences.  Rank r evaluates the data term of its site range [lo, hi); the
-  parameter vector x is replicated and the gradient needs one exchange per
-  evaluation: an all-reduce (sum) of g (P floats) plus the 4 objective scalars.
-  The L-BFGS vector algebra is replicated (identical on every rank, deterministic).
+  never sequences.  Default (``ShardedPlm``): rank r OWNS a contiguous site range and
+  the slice of the parameter vector whose blocks J_ij start in it; the optimiser's
+  vectors are sharded the same way.  Per evaluation only the cross blocks move, by
+  P2P stores over NVLink fused into the unpack / export kernels (csrc/xrank.cuh),
+  plus a few float64 scalars summed in rank order.  torch.distributed carries the
+  64-byte CUDA IPC handles at start-up and the one NCCL all-gather of the final
+  parameters; nothing else.
+  Legacy (``make_allreduce_callback``): x replicated, one NCCL all-reduce of g (P floats)
+  per evaluation -- kept as the fallback when peer memory cannot be mapped.
 * mfDCA        -- replicas only at the named sizes: the 6000^2 FP64 inverse is
   tens of milliseconds on one GPU.
 """
@@ -87,3 +92,111 @@ def sharded_counts(msa, seqid, compare_f64=False, group=None, device=None):
     lo, hi = shard_range(msa.shape[0], rank, world)
     local = _lib.sequence_counts(msa, seqid, compare_f64=compare_f64, rows=(lo, hi))
     return allgather_counts(local, (lo, hi), msa.shape[0], group=group, device=device)
+
+
+# ---- owner-sharded plmDCA (peer-memory exchange) ------------------------------------------
+def balanced_site_bounds(seqs_len, world, rho=0.5):
+    """Contiguous site ranges, bounds[r] .. bounds[r+1], that balance the per-rank cost.
+    Site i costs 1 (its column of the gather / scatter kernels) + rho * (L-1-i)/(L-1) (the
+    L-1-i coupling blocks it owns: unpack, assemble and every L-BFGS vector pass), so low
+    ranks get slightly fewer sites.  Every rank owns at least one site."""
+    L, world = int(seqs_len), int(world)
+    if world > L:
+        raise ValueError("more ranks (%d) than sites (%d)" % (world, L))
+    cost = np.array([1.0 + rho * (L - 1 - i) / max(1, L - 1) for i in range(L)])
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    bounds = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        k = int(np.searchsorted(cum, target))
+        if k > 0 and abs(cum[k - 1] - target) <= abs(cum[k] - target):
+            k -= 1
+        k = max(k, bounds[-1] + 1)
+        k = min(k, L - (world - r))
+        bounds.append(k)
+    bounds.append(L)
+    return bounds
+
+
+def scatter_full_vector(slices, layouts, num_params):
+    """Inverse of PlmObjective.local_slice over all ranks: slices[r] (fields then couplings
+    of rank r) placed at layouts[r] = (field off, count, coupling off, count)."""
+    x = np.zeros(int(num_params), dtype=np.float32)
+    for sl, (fo, fc, co, cc) in zip(slices, layouts):
+        x[fo:fo + fc] = sl[:fc]
+        x[co:co + cc] = sl[fc:fc + cc]
+    return x
+
+
+class ShardedPlm:
+    """One rank of an owner-sharded plmDCA objective: create, wire the peers, fit, gather.
+
+        sp = ShardedPlm(msa, w, q, lam_h, lam_J)        # inside an initialised process group
+        x_local, res = sp.fit(max_iterations)
+        x = sp.gather(x_local)                           # NCCL all-gather -> full vector on every rank
+        sp.close()
+    """
+
+    def __init__(self, msa, weights, num_site_states, lambda_h, lambda_J, group=None, bounds=None):
+        import torch.distributed as dist
+        from . import _lib
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        L = msa.shape[1]
+        self.bounds = list(bounds) if bounds is not None else balanced_site_bounds(L, self.world)
+        self.obj = _lib.PlmObjective(msa, weights, num_site_states, lambda_h, lambda_J,
+                                     shard=(self.rank, self.world, self.bounds))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.obj.ipc_handle(), group=group)
+        err = None
+        try:
+            self.obj.connect_ipc(handles)
+        except Exception as exc:                 # e.g. no P2P between two devices
+            err = repr(exc)
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err, group=group)       # all ranks succeed or all give up
+        if any(e is not None for e in errs):
+            self.obj.disconnect()
+            dist.barrier(group=group)
+            self.obj.close()
+            self.obj = None
+            raise RuntimeError("peer-memory wiring failed: %s" % [e for e in errs if e is not None][0])
+        self.layouts = [_lib.shard_layout(L, num_site_states, self.bounds[r], self.bounds[r + 1])
+                        for r in range(self.world)]
+        dist.barrier(group=group)               # every arena is mapped everywhere before the first push
+
+    def init(self):
+        return self.obj.init()
+
+    def fit(self, max_iterations, x0_local=None, verbose=False):
+        x0 = self.obj.init() if x0_local is None else x0_local
+        return self.obj.fit(x0, max_iterations, verbose=verbose)
+
+    def gather(self, x_local=None, device=None):
+        """All ranks' slices -> the full parameter vector (reference layout) on every rank:
+        ONE NCCL all-gather of the padded device slices (north_star: a single all-gather of
+        the final J blocks before FN + APC)."""
+        import torch
+        import torch.distributed as dist
+        nmax = max(fc + cc for _, fc, _, cc in self.layouts)
+        backend = dist.get_backend(self.group)
+        if backend == "nccl":
+            dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+            mine = torch.zeros(nmax, dtype=torch.float32, device=dev)
+            src = torch.as_tensor(_CudaView(self.obj.x_device(), self.obj.Ploc, "<f4"), device=dev)
+            mine[:self.obj.Ploc].copy_(src)
+        else:
+            mine = torch.zeros(nmax, dtype=torch.float32)
+            mine[:self.obj.Ploc] = torch.from_numpy(np.ascontiguousarray(x_local, dtype=np.float32))
+        out = torch.empty(self.world * nmax, dtype=torch.float32, device=mine.device)
+        dist.all_gather_into_tensor(out, mine, group=self.group)
+        allx = out.cpu().numpy().reshape(self.world, nmax)
+        return scatter_full_vector([allx[r] for r in range(self.world)], self.layouts, self.obj.P)
+
+    def close(self):
+        import torch.distributed as dist
+        if self.obj is not None:
+            self.obj.disconnect()
+            dist.barrier(group=self.group)       # nobody frees an arena a peer still maps
+            self.obj.close()
+            self.obj = None

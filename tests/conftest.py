@@ -1,6 +1,11 @@
 import os
 import sys
 
+# The sharded tests run several ranks as threads of this process; a kernel that is lazily
+# loaded while a peer thread spins in a barrier kernel would dead-lock the context.  The
+# library force-loads its kernels too (plm_setup_t); this makes the whole process eager.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import numpy as np
 import pytest
 

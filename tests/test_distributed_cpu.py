@@ -23,6 +23,55 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_balanced_site_bounds_cover_and_order():
+    from pydca_b200.distributed import balanced_site_bounds
+    for L in (2, 3, 9, 150, 500):
+        for world in (1, 2, 3, 4, 8):
+            if world > L:
+                with pytest.raises(ValueError):
+                    balanced_site_bounds(L, world)
+                continue
+            for rho in (0.0, 0.5, 2.0):
+                b = balanced_site_bounds(L, world, rho)
+                assert len(b) == world + 1 and b[0] == 0 and b[-1] == L
+                assert all(b[k + 1] > b[k] for k in range(world))
+    # rho = 0 is the plain balanced split; rho > 0 gives low ranks (which own more blocks) fewer sites
+    sizes = np.diff(balanced_site_bounds(150, 8, 0.0))
+    assert sizes.max() - sizes.min() <= 1
+    b = balanced_site_bounds(150, 8, 0.5)
+    assert b[1] - b[0] < b[8] - b[7]
+
+
+def test_shard_layout_partitions_the_parameter_vector():
+    """dca_shard_layout (C, host-only) against the reference's index arithmetic
+    (plmdca_numerics.cpp:226, :338-342): the owners' slices tile the vector exactly, and
+    scatter_full_vector inverts local_slice."""
+    from pydca_b200 import _lib
+    from pydca_b200.distributed import balanced_site_bounds, scatter_full_vector
+    for L, q in ((7, 5), (150, 21), (33, 21)):
+        P = L * q + L * (L - 1) // 2 * q * q
+        pair = lambda i, j: L * (L - 1) // 2 - (L - i) * (L - i - 1) // 2 + j - i - 1
+        for world in (1, 2, 3, min(8, L)):
+            b = balanced_site_bounds(L, world)
+            lay = [_lib.shard_layout(L, q, b[r], b[r + 1]) for r in range(world)]
+            assert lay[0][0] == 0 and lay[0][2] == L * q
+            for r in range(world):
+                fo, fc, co, cc = lay[r]
+                assert fo == b[r] * q and fc == (b[r + 1] - b[r]) * q
+                if b[r] + 1 < L:
+                    assert co == L * q + pair(b[r], b[r] + 1) * q * q
+                nblocks = sum(L - 1 - i for i in range(b[r], b[r + 1]))
+                assert cc == nblocks * q * q
+                if r + 1 < world:
+                    assert fo + fc == lay[r + 1][0] and co + cc == lay[r + 1][2]
+            assert lay[-1][0] + lay[-1][1] == L * q and lay[-1][2] + lay[-1][3] == P
+            x = np.arange(P, dtype=np.float32)
+            slices = [np.concatenate([x[fo:fo + fc], x[co:co + cc]]) for fo, fc, co, cc in lay]
+            assert (scatter_full_vector(slices, lay, P) == x).all()
+    with pytest.raises(_lib.DcaBackendError):
+        _lib.shard_layout(10, 21, 4, 4)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -72,6 +121,22 @@ def _worker(rank, world, port, out_dir):
     f_tot = float(s[0]) + f_reg
     assert np.abs(g_tot - g_full).max() <= 1e-5 * np.abs(g_full).max()
     assert abs(f_tot - f_full) <= 5e-5 * abs(f_full)
+    # owner-sharded parameters: every rank holds its slice; ShardedPlm.gather() rebuilds the
+    # full vector with one all_gather_into_tensor (the GPU path does the same over NCCL)
+    from pydca_b200 import _lib
+    from pydca_b200.distributed import ShardedPlm, balanced_site_bounds
+    bounds = balanced_site_bounds(L, world)
+    sp = ShardedPlm.__new__(ShardedPlm)
+    sp.group, sp.rank, sp.world, sp.bounds = None, rank, world, bounds
+    sp.layouts = [_lib.shard_layout(L, q, bounds[r], bounds[r + 1]) for r in range(world)]
+
+    class _Obj:
+        P = x.size
+        Ploc = sp.layouts[rank][1] + sp.layouts[rank][3]
+    sp.obj = _Obj()
+    fo, fc, co, cc = sp.layouts[rank]
+    mine = np.concatenate([x[fo:fo + fc], x[co:co + cc]])
+    assert (sp.gather(mine) == x).all()
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
