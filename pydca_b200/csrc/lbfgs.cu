@@ -286,9 +286,10 @@ vec_update_gram_kernel(float *__restrict__ s_new, float *__restrict__ y_new, con
                        const float *__restrict__ xp, const float *__restrict__ g, const float *__restrict__ gp,
                        HistPtrs H, long n, double *__restrict__ partial, double *__restrict__ gram,
                        float *__restrict__ coef, double *__restrict__ dscal, unsigned *__restrict__ ticket,
-                       double *__restrict__ gram_loc)
-{   // gram_loc != null (owner-sharded multi-GPU): the last CTA only leaves this rank's 25 partial
-    // inner products there; xr_gram_kernel sums them over the ranks and runs the recursion
+                       double *__restrict__ gram_loc, XrCall xc)
+{   // gram_loc != null (owner-sharded multi-GPU): the last CTA first sums this rank's 25 partial
+    // inner products over all ranks through peer memory (rank order: same bits everywhere),
+    // then every rank runs the same recursion
     __shared__ double red[VEC_THREADS / 32][GR_NPART];
     __shared__ bool last;
     double acc[GR_NPART];
@@ -386,22 +387,10 @@ vec_update_gram_kernel(float *__restrict__ s_new, float *__restrict__ y_new, con
     __syncthreads();
     if (gram_loc) {
         if (threadIdx.x < GR_NPART) gram_loc[threadIdx.x] = red[0][threadIdx.x];
-        return;
+        __syncthreads();
+        xr_reduce_body(xc.P, xc.lay, xc.epoch, xc.seq, gram_loc, GR_NPART, red[0], xc.err);
     }
     gram_recursion(red[0], H, gram, coef, dscal);
-}
-
-// cross-rank version of the tail above: sum the 25 inner products over all ranks (rank order,
-// so every rank gets the same bits), then the same Gram update + scalar recursion, redundantly
-// on every rank
-__global__ void __launch_bounds__(128)
-xr_gram_kernel(XrPeers P, XrLayout lay, unsigned epoch, unsigned seq, const double *__restrict__ gram_loc,
-               HistPtrs H, double *__restrict__ gram, float *__restrict__ coef, double *__restrict__ dscal,
-               unsigned *err)
-{
-    __shared__ double t[GR_NPART];
-    xr_reduce_body(P, lay, epoch, seq, gram_loc, GR_NPART, t, err);
-    gram_recursion(t, H, gram, coef, dscal);
 }
 
 // pass B: d = coef_g g + sum_t (coef_y[t] y_t + coef_s[t] s_t)
@@ -624,7 +613,6 @@ int lbfgs_preload_kernels()
     DCA_CUDA(cudaFuncGetAttributes(&fa, vec_dots_kernel));
     DCA_CUDA(cudaFuncGetAttributes(&fa, vec_update_gram_kernel));
     DCA_CUDA(cudaFuncGetAttributes(&fa, vec_direction_kernel));
-    DCA_CUDA(cudaFuncGetAttributes(&fa, xr_gram_kernel));
     return 0;
 }
 
@@ -661,7 +649,7 @@ int lbfgs_vector_bench(long n, int bound, int reps, float *ms_out)
         for (int r = -2; r < reps; ++r) {          // two warm-up rounds
             cudaEventRecord(e[0], st);
             DCA_LAUNCH(vec_update_gram_kernel, blocks, VEC_THREADS, 0, st, v[5], v[5 + LB_M], v[0], v[1], v[2], v[3], H, n,
-                       partial, gram, coef, dscal, ticket, (double *)nullptr);
+                       partial, gram, coef, dscal, ticket, (double *)nullptr, XrCall{});
             cudaEventRecord(e[1], st);
             DCA_LAUNCH(vec_direction_kernel, blocks, VEC_THREADS, 0, st, v[4], v[2], H, coef, n);
             cudaEventRecord(e[2], st);
@@ -822,12 +810,7 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
             // recursion (alpha, beta, gamma -> coefficients, g.d) in the last CTA
             DCA_LAUNCH(vec_update_gram_kernel, D.blocks, VEC_THREADS, 0, st,
                        D.s[end], D.y[end], D.x, D.xp, D.g, D.gp, H, n, D.partial, D.gram, D.coef, dsc, D.ticket,
-                       D.sharded ? D.gram_loc : (double *)nullptr);
-            if (D.sharded) {
-                const XrCall c = plm_xr_next(p);
-                DCA_LAUNCH(xr_gram_kernel, 1, 128, 0, st, c.P, c.lay, c.epoch, c.seq, D.gram_loc, H, D.gram, D.coef,
-                           dsc, c.err);
-            }
+                       D.sharded ? D.gram_loc : (double *)nullptr, D.sharded ? plm_xr_next(p) : XrCall{});
             // pass B: the direction as one linear combination
             DCA_LAUNCH(vec_direction_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.g, H, D.coef, n);
             ++k;

@@ -87,10 +87,11 @@ struct PlmProblem {
     long nscan = 0;          // number of scan chunks
     int red_blocks = 0, n_active = 0;
     unsigned *d_ticket = nullptr;
-    int col_tile0 = 0, col_tiles = 0;
+    int col_tile0 = 0, col_tiles = 0;     // scatter: 128-column tiles covering my sites' columns
+    int lg_tc = LG_TC, lg_tile0 = 0, lg_tiles = 0;   // logits: lg_tc-column tiles (128, or 64 for small grids)
     int site_tiles = 0, sites_per_tile = 0;
     CUtensorMap tmS;         // S as [Npad][ld] f32, box 128 x 128 (scatter tiles)
-    CUtensorMap tmW;         // W as [Lq][ld] f32, box 128 x JB*q (logits stage)
+    CUtensorMap tmW;         // W as [Lq][ld] f32, box lg_tc x JB*q (logits stage)
     CUtensorMap tmM;         // msaT as [L][Npad] u8, box 128 x JB (logits stage)
     // ---- owner-sharded multi-GPU mode (xrank.cuh): x, g and every L-BFGS vector hold only
     // the LOCAL slice [fields of my sites | my coupling blocks]; W lives in the peer arena
@@ -110,6 +111,8 @@ struct PlmProblem {
     double *d_scal_loc = nullptr;
     int n_active_own = 0;
 };
+
+XrCall plm_xr_next(PlmProblem *p);
 
 // ------------------------------------------------------------------------------
 __global__ void transpose_msa_kernel(const uint8_t *__restrict__ msa, long N, int L, long Npad,
@@ -206,22 +209,27 @@ plm_unpack_kernel(const float *__restrict__ x, int L, int ld, float *__restrict_
 // L (last stage) are zero-filled by the hardware: residue 0 then selects a zero row.
 // Inner loop: one 16-byte load brings a warp's 16 residues, then one conflict-free
 // LDS.128 (a 512-byte row segment per warp) per 4 adds.
-template <int Q>
-__global__ void __launch_bounds__(LG_THREADS, 2)
+template <int Q, int TC>
+__global__ void __launch_bounds__(LG_THREADS, (TC == 128) ? 2 : 3)
 plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmM,
                   int ld, long N, int L, const float *__restrict__ xf, int col_lo, int col_hi,
-                  float *__restrict__ S, int col_tile0)
-{   // xf[c - col_lo] = field of column c for col_lo <= c < col_hi (the columns this GPU owns)
+                  float *__restrict__ S, int col_tile0, XrWait wt)
+{   // wt: owner-sharded mode only -- wait until every rank's unpack_push has signalled (W complete)
+    // xf[c - col_lo] = field of column c for col_lo <= c < col_hi (the columns this GPU owns)
+    // TC = columns per CTA: 128 (lane = float4) or 64 (lane = float2).  The narrow variant moves
+    // the same shared-memory bytes per add; it exists for small grids (multi-GPU shards), where
+    // 128-column CTAs quantise badly over the 148 SMs.
     constexpr int JB = LgCfg<Q>::JB;
     constexpr int NWARP = LG_THREADS / 32;
-    constexpr unsigned STAGE_BYTES = JB * Q * LG_TC * 4 + JB * LG_TN;
+    constexpr int VEC = TC / 32;
+    constexpr unsigned STAGE_BYTES = JB * Q * TC * 4 + JB * LG_TN;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    float *Wt = reinterpret_cast<float *>(smem_raw);                       // [2][JB*Q][128]
-    uint8_t *Mt = smem_raw + sizeof(float) * 2 * JB * Q * LG_TC;           // [2][JB][128]
+    float *Wt = reinterpret_cast<float *>(smem_raw);                       // [2][JB*Q][TC]
+    uint8_t *Mt = smem_raw + sizeof(float) * 2 * JB * Q * TC;              // [2][JB][128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(Mt + 2 * JB * LG_TN);    // full[2], empty[2]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int col0 = (col_tile0 + blockIdx.x) * LG_TC;
+    const int col0 = (col_tile0 + blockIdx.x) * TC;
     const long n0 = (long)blockIdx.y * LG_TN;
 
     if (tid == 0) {
@@ -230,23 +238,23 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         mbar_fence_init();
     }
     __syncthreads();
+    xr_wait_all(wt);
 
-    float4 acc[16];
+    float acc[16][VEC];
     {
-        const int c = col0 + 4 * lane;
-        float4 h;
-        h.x = (c + 0 >= col_lo && c + 0 < col_hi) ? xf[c + 0 - col_lo] : 0.f;
-        h.y = (c + 1 >= col_lo && c + 1 < col_hi) ? xf[c + 1 - col_lo] : 0.f;
-        h.z = (c + 2 >= col_lo && c + 2 < col_hi) ? xf[c + 2 - col_lo] : 0.f;
-        h.w = (c + 3 >= col_lo && c + 3 < col_hi) ? xf[c + 3 - col_lo] : 0.f;
+        const int c = col0 + VEC * lane;
 #pragma unroll
-        for (int t = 0; t < 16; ++t) acc[t] = h;
+        for (int v = 0; v < VEC; ++v) {
+            const float h = (c + v >= col_lo && c + v < col_hi) ? xf[c + v - col_lo] : 0.f;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) acc[t][v] = h;
+        }
     }
 
     auto issue = [&](int buf, int st) {
         if (lane == 0) {
             mbar_expect_tx(&bars[buf], STAGE_BYTES);
-            tma_load_2d(Wt + (size_t)buf * JB * Q * LG_TC, &tmW, col0, st * JB * Q, &bars[buf]);
+            tma_load_2d(Wt + (size_t)buf * JB * Q * TC, &tmW, col0, st * JB * Q, &bars[buf]);
             tma_load_2d(Mt + (size_t)buf * JB * LG_TN, &tmM, (int)n0, st * JB, &bars[buf]);
         }
         __syncwarp();
@@ -260,18 +268,23 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int buf = st & 1;
         const unsigned parity = (unsigned)(st >> 1) & 1u;
         mbar_wait(&bars[buf], parity);
-        const float *Wb = Wt + (size_t)buf * JB * Q * LG_TC + 4 * lane;
+        const float *Wb = Wt + (size_t)buf * JB * Q * TC + VEC * lane;
         const uint8_t *Mb = Mt + (size_t)buf * JB * LG_TN + warp * 16;
 #pragma unroll
         for (int jj = 0; jj < JB; ++jj) {
             const uint4 r16 = *reinterpret_cast<const uint4 *>(Mb + jj * LG_TN);
-            const float *Wj = Wb + jj * Q * LG_TC;
+            const float *Wj = Wb + jj * Q * TC;
             const unsigned rr[4] = {r16.x, r16.y, r16.z, r16.w};
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
                 const unsigned b = (rr[t >> 2] >> (8 * (t & 3))) & 0xffu;
-                const float4 v = *reinterpret_cast<const float4 *>(Wj + b * LG_TC);
-                acc[t].x += v.x; acc[t].y += v.y; acc[t].z += v.z; acc[t].w += v.w;
+                if constexpr (VEC == 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(Wj + b * TC);
+                    acc[t][0] += v.x; acc[t][1] += v.y; acc[t][2] += v.z; acc[t][3] += v.w;
+                } else {
+                    const float2 v = *reinterpret_cast<const float2 *>(Wj + b * TC);
+                    acc[t][0] += v.x; acc[t][1] += v.y;
+                }
             }
         }
         __syncwarp();
@@ -284,7 +297,11 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
         const long n = n0 + warp * 16 + t;
-        if (n < N) *reinterpret_cast<float4 *>(S + (size_t)n * ld + col0 + 4 * lane) = acc[t];
+        if (n < N) {
+            float *dst = S + (size_t)n * ld + col0 + VEC * lane;
+            if constexpr (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+            else *reinterpret_cast<float2 *>(dst) = make_float2(acc[t][0], acc[t][1]);
+        }
     }
 }
 
@@ -447,25 +464,37 @@ plm_scatter_kernel(const __grid_constant__ CUtensorMap tmS, int ld, const uint8_
             for (int b = 0; b < Q; ++b) {
                 const unsigned m = (hw[b >> 2] >> (8 * (b & 3))) & 0xffu;
                 float4 a = acc[b];
-                const unsigned nq = (m + 3u) >> 2;
-                // One compact loop per bucket (rows beyond the bucket's size are predicated
-                // off, warp-uniformly).  Deliberately not unrolled: the 21 bucket copies must
-                // stay inside the 32 KB instruction cache -- ncu showed "no instruction" stalls
-                // ~1 per issued instruction when the kernel was 64 KB of SASS.
+                const unsigned nfull = m >> 2, tail = m & 3u;
+                // Full quads: four unconditional LDS.128 + 16 adds, nothing else.  Deliberately not
+                // unrolled: the 21 bucket copies must stay inside the 32 KB instruction cache
+                // (ncu: "no instruction" stalls ~1 per issued instruction at 64 KB of SASS).
 #pragma unroll 1
-                for (unsigned t = 0; t < nq; ++t) {
+                for (unsigned t = 0; t < nfull; ++t) {
                     const uint4 o = cur;
                     cur = qp[++pos];
-                    const unsigned rem = m - 4u * t;                 // rows left in this bucket (>= 1)
-                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 v0 = SC_ROW(o.x);
-                    const float4 v1 = (rem > 1u) ? SC_ROW(o.y) : z4;
-                    const float4 v2 = (rem > 2u) ? SC_ROW(o.z) : z4;
-                    const float4 v3 = (rem > 3u) ? SC_ROW(o.w) : z4;
+                    const float4 v0 = SC_ROW(o.x), v1 = SC_ROW(o.y), v2 = SC_ROW(o.z), v3 = SC_ROW(o.w);
                     a.x += (v0.x + v1.x) + (v2.x + v3.x);
                     a.y += (v0.y + v1.y) + (v2.y + v3.y);
                     a.z += (v0.z + v1.z) + (v2.z + v3.z);
                     a.w += (v0.w + v1.w) + (v2.w + v3.w);
+                }
+                // Ragged tail (1..3 rows of the bucket's last, padded quad): warp-uniform branches.
+                // The earlier version predicated every row of every quad against the bucket size
+                // (select-with-zero): 51 issued instructions per quad for 21 useful ones, and ncu
+                // showed the kernel issue-bound (71 % issue-active) below the shared-memory roof.
+                if (tail != 0u) {
+                    const uint4 o = cur;
+                    cur = qp[++pos];
+                    const float4 v0 = SC_ROW(o.x);
+                    a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+                    if (tail > 1u) {
+                        const float4 v1 = SC_ROW(o.y);
+                        a.x += v1.x; a.y += v1.y; a.z += v1.z; a.w += v1.w;
+                        if (tail > 2u) {
+                            const float4 v2 = SC_ROW(o.z);
+                            a.x += v2.x; a.y += v2.y; a.z += v2.z; a.w += v2.w;
+                        }
+                    }
                 }
                 acc[b] = a;
             }
@@ -488,9 +517,9 @@ plm_scatter_kernel(const __grid_constant__ CUtensorMap tmS, int ld, const uint8_
 // ------------------------------------------------------------------------------
 // tail shared by the assemble kernels: one fused block reduction of the four sums, the
 // CTA's partials to `red` (SoA: red[c * nblk + blk]; slots of CTAs that own no pair stay
-// zero), a ticket, and -- in the last CTA to finish -- the fixed-order reduction
-//   scal = { fx = reg + sum fxpart, g.d, g.g, x.x }.
-__device__ __forceinline__ void assemble_finish(double s_reg, double s_dg, double s_gg, double s_xx,
+// zero), a ticket, and -- in the last CTA to finish, the only one that gets `true` back --
+// the fixed-order reduction  scal = { fx = reg + sum fxpart, g.d, g.g, x.x }.
+__device__ __forceinline__ bool assemble_finish(double s_reg, double s_dg, double s_gg, double s_xx,
                                                 double *__restrict__ red, const double *__restrict__ fxpart,
                                                 int nfx, unsigned *__restrict__ ticket, unsigned n_active,
                                                 double *__restrict__ scal)
@@ -513,7 +542,7 @@ __device__ __forceinline__ void assemble_finish(double s_reg, double s_dg, doubl
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicInc(ticket, n_active - 1u) == n_active - 1u);
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) return false;
     __threadfence();
     // last CTA: everything is visible; reduce in a fixed order (4 independent loads in flight)
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -543,6 +572,8 @@ __device__ __forceinline__ void assemble_finish(double s_reg, double s_dg, doubl
         for (int w = 0; w < 8; ++w) r += wsum[w][threadIdx.x];
         scal[threadIdx.x] = r;
     }
+    __syncthreads();
+    return true;               // only in the last CTA, with scal[] written and visible to the CTA
 }
 
 // ------------------------------------------------------------------------------
@@ -649,7 +680,7 @@ plm_assemble_kernel(const float *__restrict__ x, const float *__restrict__ G, si
 template <int Q>
 __global__ void __launch_bounds__(256)
 plm_unpack_push_kernel(const float *__restrict__ xl, long nq, long pair0, int L, int ld, int lo,
-                       XrPeers P, size_t off_W)
+                       XrPeers P, size_t off_W, size_t off_flags, unsigned *__restrict__ ticket, unsigned epoch)
 {
     constexpr int QQ = Q * Q;
     __shared__ float tile[AS_JG * QQ];
@@ -657,7 +688,7 @@ plm_unpack_push_kernel(const float *__restrict__ xl, long nq, long pair0, int L,
     const int j0 = blockIdx.x * AS_JG;
     const int jlo = max(j0, i + 1), jhi = min(j0 + AS_JG, L);
     const int npair = jhi - jlo;
-    if (npair <= 0) return;
+    if (npair > 0) {
     const float *xb = xl + nq + (pair_index(L, i, jlo) - pair0) * QQ;    // npair consecutive blocks
     for (int t = threadIdx.x; t < npair * QQ; t += 256) tile[t] = xb[t];
     __syncthreads();
@@ -677,6 +708,10 @@ plm_unpack_push_kernel(const float *__restrict__ xl, long nq, long pair0, int L,
         float *Wo = reinterpret_cast<float *>(P.arena[xr_owner(P, jlo + jj)] + off_W);
         Wo[((long)i * Q + a) * ld + jlo * Q + c] = tile[jj * QQ + a * Q + b];
     }
+    }
+    // the barrier is part of this kernel: the last CTA tells every rank that my pushes are done
+    // (plm_logits_kernel waits for all ranks' signals before it touches W)
+    xr_grid_signal(ticket, P, off_flags, epoch);
 }
 
 // one CTA per G row (i,a) with i < lo: those rows are the site-j conditional's contribution
@@ -684,17 +719,20 @@ plm_unpack_push_kernel(const float *__restrict__ xl, long nq, long pair0, int L,
 template <int Q>
 __global__ void __launch_bounds__(128)
 plm_export_kernel(const float *__restrict__ G, size_t g_split_stride, int nsplit, int ld, int lo, int hi,
-                  XrPeers P, size_t off_R)
+                  XrPeers P, size_t off_R, size_t off_flags, unsigned *__restrict__ ticket, unsigned epoch)
 {
     const int row = blockIdx.x;
-    const int o = xr_owner(P, row / Q);
-    float *R = reinterpret_cast<float *>(P.arena[o] + off_R) + (size_t)(row - P.bounds[o] * Q) * ld;
-    const float *g = G + (size_t)row * ld;
-    for (int c = lo * Q + threadIdx.x; c < hi * Q; c += 128) {
-        float v = 0.f;
-        for (int s = 0; s < nsplit; ++s) v += g[(size_t)s * g_split_stride + c];
-        R[c] = v;
+    if (row < lo * Q) {                 // rank 0 exports nothing: its single CTA only signals
+        const int o = xr_owner(P, row / Q);
+        float *R = reinterpret_cast<float *>(P.arena[o] + off_R) + (size_t)(row - P.bounds[o] * Q) * ld;
+        const float *g = G + (size_t)row * ld;
+        for (int c = lo * Q + threadIdx.x; c < hi * Q; c += 128) {
+            float v = 0.f;
+            for (int s = 0; s < nsplit; ++s) v += g[(size_t)s * g_split_stride + c];
+            R[c] = v;
+        }
     }
+    xr_grid_signal(ticket, P, off_flags, epoch);      // plm_assemble_owner_kernel waits for all ranks
 }
 
 // gradient of my slice: 2*lambda*x + G[(j,b)][(i,a)] (my conditional, transposed through
@@ -705,10 +743,12 @@ plm_assemble_owner_kernel(const float *__restrict__ xl, long nq, long pair0, con
                           size_t g_split_stride, int nsplit, const float *__restrict__ R, int L, int ld,
                           float lh, float lJ, int lo, int hi, const float *__restrict__ dl,
                           float *__restrict__ gl, double *__restrict__ red, const double *__restrict__ fxpart,
-                          int nfx, unsigned *__restrict__ ticket, unsigned n_active, double *__restrict__ scal)
+                          int nfx, unsigned *__restrict__ ticket, unsigned n_active, double *__restrict__ scal_loc,
+                          XrWait wt, XrCall xc, double *__restrict__ scal)
 {
     constexpr int QQ = Q * Q;
     __shared__ float tile[AS_JG * QQ];
+    xr_wait_all(wt);                     // every rank's export has landed in my R
     const int i = lo + blockIdx.y;
     const int j0 = blockIdx.x * AS_JG;
     const bool any = (j0 + AS_JG - 1 > i);
@@ -765,21 +805,14 @@ plm_assemble_owner_kernel(const float *__restrict__ xl, long nq, long pair0, con
         if (dl) s_dg += (double)gv * dl[base + t];
         s_gg += (double)gv * gv;
     }
-    assemble_finish(s_reg, s_dg, s_gg, s_xx, red, fxpart, nfx, ticket, n_active, scal);
+    // the last CTA holds this rank's four partial scalars: sum them over the ranks right here
+    if (assemble_finish(s_reg, s_dg, s_gg, s_xx, red, fxpart, nfx, ticket, n_active, scal_loc))
+        xr_reduce_body(xc.P, xc.lay, xc.epoch, xc.seq, scal_loc, (int)PS_COUNT, scal, xc.err);
 }
 
 __global__ void xr_barrier_kernel(XrPeers P, size_t off_flags, unsigned epoch, unsigned *err)
 {
     if ((int)threadIdx.x < P.world) xr_signal_and_wait(P, off_flags, epoch, threadIdx.x, err);
-}
-
-// out[k] = sum over ranks (in rank order) of local[k], k < n <= XR_SLOT: every rank stores
-// its values into every rank's slot block, signals, waits for all, sums.
-__global__ void __launch_bounds__(128)
-xr_reduce_kernel(XrPeers P, XrLayout lay, unsigned epoch, unsigned seq, const double *__restrict__ local,
-                 int n, double *__restrict__ out, unsigned *err)
-{
-    xr_reduce_body(P, lay, epoch, seq, local, n, out, err);
 }
 
 // ------------------------------------------------------------------------------
@@ -832,7 +865,8 @@ static int plm_setup_t(PlmProblem *p)
     }
     const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN + 64 + 1024;
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
-    DCA_CUDA(cudaFuncSetAttribute(plm_logits_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    DCA_CUDA(cudaFuncSetAttribute((plm_logits_kernel<Q, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    DCA_CUDA(cudaFuncSetAttribute((plm_logits_kernel<Q, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     DCA_CUDA(cudaFuncSetAttribute(plm_scatter_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
     if (p->sharded) {
         // CUDA loads kernels lazily, and loading one synchronises the context: a rank that
@@ -842,12 +876,12 @@ static int plm_setup_t(PlmProblem *p)
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_unpack_push_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_export_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_assemble_owner_kernel<Q>));
-        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_logits_kernel<Q>));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_logits_kernel<Q, 128>)));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_logits_kernel<Q, 64>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_softmax_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_scatter_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_init_fields_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, xr_barrier_kernel));
-        DCA_CUDA(cudaFuncGetAttributes(&fa, xr_reduce_kernel));
         if (lbfgs_preload_kernels() != 0) return -1;
     }
     DCA_CUDA(cudaGetLastError());
@@ -869,19 +903,25 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
     if (p->sharded) {
         // fused unpack + exchange: my blocks go to my W and, by P2P stores, to the W of owner(j)
         DCA_LAUNCH((plm_unpack_push_kernel<Q>), gridU, 256, 0, st, d_x, p->nq_loc, p->pair0, L, ld, lo,
-                   p->peers, p->lay.off_W);
-        DCA_LAUNCH(xr_barrier_kernel, 1, 32, 0, st, p->peers, p->lay.off_flags, ++p->epoch, p->d_err);
+                   p->peers, p->lay.off_W, p->lay.off_flags, p->d_ticket + 1, ++p->epoch);
     } else {
         DCA_LAUNCH((plm_unpack_kernel<Q>), gridU, 256, 0, st, d_x, L, ld, p->d_W);
     }
     PLM_MARK();
 
-    const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN + 64 + 1024;
-    dim3 gridA(p->col_tiles, (unsigned)(p->Npad / LG_TN));
+    const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * p->lg_tc + 2 * LgCfg<Q>::JB * LG_TN + 64 + 1024;
+    dim3 gridA(p->lg_tiles, (unsigned)(p->Npad / LG_TN));
     // fields: the head of the local slice (sharded) or of the whole vector
     const int col_lo = p->sharded ? lo * Q : 0, col_hi = p->sharded ? hi * Q : L * Q;
-    DCA_LAUNCH((plm_logits_kernel<Q>), gridA, LG_THREADS, smemA, st,
-               p->tmW, p->tmM, ld, p->N, L, d_x, col_lo, col_hi, p->d_S, p->col_tile0);
+    XrWait wt{nullptr, nullptr, 0, 0u};
+    if (p->sharded && p->peers.world > 1)
+        wt = XrWait{reinterpret_cast<const unsigned *>(p->arena + p->lay.off_flags), p->d_err, p->peers.world, p->epoch};
+    if (p->lg_tc == 128)
+        DCA_LAUNCH((plm_logits_kernel<Q, 128>), gridA, LG_THREADS, smemA, st,
+                   p->tmW, p->tmM, ld, p->N, L, d_x, col_lo, col_hi, p->d_S, p->lg_tile0, wt);
+    else
+        DCA_LAUNCH((plm_logits_kernel<Q, 64>), gridA, LG_THREADS, smemA, st,
+                   p->tmW, p->tmM, ld, p->N, L, d_x, col_lo, col_hi, p->d_S, p->lg_tile0, wt);
     PLM_MARK();
 
     dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
@@ -900,15 +940,15 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
 
     const int nfx = (int)(gridB.x * p->nscan);
     if (p->sharded) {
-        if (lo > 0)
-            DCA_LAUNCH((plm_export_kernel<Q>), lo * Q, 128, 0, st, p->d_G, gstride, p->nsplit, ld, lo, hi,
-                       p->peers, p->lay.off_R);
-        DCA_LAUNCH(xr_barrier_kernel, 1, 32, 0, st, p->peers, p->lay.off_flags, ++p->epoch, p->d_err);
+        // export (+ signal) -> assemble (waits; its last CTA sums the scalars over the ranks)
+        DCA_LAUNCH((plm_export_kernel<Q>), std::max(1, lo * Q), 128, 0, st, p->d_G, gstride, p->nsplit, ld, lo, hi,
+                   p->peers, p->lay.off_R, p->lay.off_flags, p->d_ticket + 2, ++p->epoch);
+        wt.epoch = p->epoch;
+        const XrCall xc = plm_xr_next(p);
         DCA_LAUNCH((plm_assemble_owner_kernel<Q>), gridU, 256, 0, st,
                    d_x, p->nq_loc, p->pair0, p->d_G, gstride, p->nsplit, p->d_R, L, ld, p->lh, p->lJ, lo, hi,
-                   d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket, (unsigned)p->n_active_own, p->d_scal_loc);
-        DCA_LAUNCH(xr_reduce_kernel, 1, 128, 0, st, p->peers, p->lay, ++p->epoch, p->red_seq++,
-                   p->d_scal_loc, (int)PS_COUNT, p->d_scal, p->d_err);
+                   d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket, (unsigned)p->n_active_own, p->d_scal_loc,
+                   wt, xc, p->d_scal);
     } else {
         DCA_LAUNCH((plm_assemble_kernel<Q>), gridU, 256, 0, st,
                    d_x, p->d_G, gstride, p->nsplit, L, ld, p->lh, p->lJ, lo, hi,
@@ -985,8 +1025,25 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     p->lh = lambda_h; p->lJ = lambda_J;
     p->site_lo = site_lo; p->site_hi = site_hi;
     p->nchunk = (int)ceil_div<long>(N, SC_CH);
-    p->col_tile0 = (site_lo * q) / LG_TC;
-    p->col_tiles = ceil_div(site_hi * q, LG_TC) - p->col_tile0;
+    p->col_tile0 = (site_lo * q) / SC_TC;
+    p->col_tiles = ceil_div(site_hi * q, SC_TC) - p->col_tile0;
+    {   // logits tiling: every SM streams (CTAs it hosts) x (columns per CTA) through shared memory;
+        // take the narrow 64-column CTAs only when they shorten that makespan (small grids)
+        const long seq_tiles = p->Npad / LG_TN;
+        const int sms = sm_count();
+        long best = -1;
+        for (int tc : {128, 64}) {
+            const int t0 = (site_lo * q) / tc, nt = ceil_div(site_hi * q, tc) - t0;
+            const long cost = ceil_div<long>((long)nt * seq_tiles, sms) * tc;
+            if (best < 0 || cost < best) { best = cost; p->lg_tc = tc; p->lg_tile0 = t0; p->lg_tiles = nt; }
+        }
+        if (const char *e = getenv("DCA_B200_LOGITS_TC")) {        // measurement override
+            const int tc = atoi(e);
+            if (tc == 64 || tc == 128) {
+                p->lg_tc = tc; p->lg_tile0 = (site_lo * q) / tc; p->lg_tiles = ceil_div(site_hi * q, tc) - p->lg_tile0;
+            }
+        }
+    }
     p->red_blocks = ceil_div(L, AS_JG) * L;
     p->n_active = 0;                 // assemble CTAs that own a pair or the fields of a site
     p->n_active_own = 0;             // ... of my sites only (owner-sharded mode)
@@ -1068,8 +1125,8 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     PLM_ALLOC(p->d_fxpart, sizeof(double) * (size_t)(N / 8 + 1) * L);   // chunk >= 8
     PLM_ALLOC(p->d_red, sizeof(double) * 4 * (size_t)p->red_blocks);
     PLM_TRY(cudaMemsetAsync(p->d_red, 0, sizeof(double) * 4 * (size_t)p->red_blocks, p->stream));
-    PLM_ALLOC(p->d_ticket, sizeof(unsigned));
-    PLM_TRY(cudaMemsetAsync(p->d_ticket, 0, sizeof(unsigned), p->stream));
+    PLM_ALLOC(p->d_ticket, sizeof(unsigned) * 4);      // [0] assemble, [1] unpack_push, [2] export
+    PLM_TRY(cudaMemsetAsync(p->d_ticket, 0, sizeof(unsigned) * 4, p->stream));
     PLM_ALLOC(p->d_scal, sizeof(double) * 16);
     PLM_TRY(cudaMemsetAsync(p->d_scal, 0, sizeof(double) * 16, p->stream));
     p->d_err = reinterpret_cast<unsigned *>(p->d_scal + PS_COUNT);       // read back with the scalars
@@ -1084,7 +1141,7 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     {
         const unsigned jb = (q > 8) ? 4 : 16;         // LgCfg<Q>::JB
         if (make_tensor_map_2d(&p->tmW, 4, p->d_W, (unsigned long long)p->ld, (unsigned long long)p->Lq,
-                               sizeof(float) * (unsigned long long)p->ld, LG_TC, jb * (unsigned)q) != 0 ||
+                               sizeof(float) * (unsigned long long)p->ld, (unsigned)p->lg_tc, jb * (unsigned)q) != 0 ||
             make_tensor_map_2d(&p->tmM, 1, p->d_msaT, (unsigned long long)p->Npad, (unsigned long long)L,
                                (unsigned long long)p->Npad, LG_TN, jb) != 0) { plm_free(p); return nullptr; }
     }

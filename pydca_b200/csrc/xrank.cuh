@@ -39,6 +39,8 @@ struct XrLayout {                                         // byte offsets inside
     size_t off_flags, off_slots, off_W, off_R, bytes;
 };
 
+struct XrWait { const unsigned *flags; unsigned *err; int world; unsigned epoch; };   // see xr_wait_all
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void xr_st_release_sys(unsigned *p, unsigned v)
 {
@@ -79,6 +81,43 @@ __device__ __forceinline__ void xr_signal_and_wait(const XrPeers &P, size_t off_
         if (xr_now_ns() - t0 > XR_TIMEOUT_NS) { atomicExch(err, 1u); break; }
         __nanosleep(64);
     }
+}
+
+// ---- barriers fused into the producing / consuming kernels -----------------------------
+// Producer side: every thread calls this after its (possibly remote) stores; the last CTA of
+// the grid to arrive tells every rank that this rank reached `epoch`.  `ticket` must be a
+// zero-initialised counter used by this kernel only (atomicInc wraps it back to zero).
+__device__ __forceinline__ void xr_grid_signal(unsigned *ticket, const XrPeers &P, size_t off_flags, unsigned epoch)
+{
+    __shared__ bool xr_last;
+    __threadfence_system();                       // my stores are performed before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned n = gridDim.x * gridDim.y * gridDim.z;
+        xr_last = (atomicInc(ticket, n - 1u) == n - 1u);
+    }
+    __syncthreads();
+    if (xr_last && (int)threadIdx.x < P.world) {
+        __threadfence_system();                   // cumulative: every CTA's stores precede the flag
+        xr_st_release_sys(reinterpret_cast<unsigned *>(P.arena[threadIdx.x] + off_flags) + P.rank, epoch);
+    }
+}
+
+// Consumer side: every CTA of the consuming kernel waits (on this rank's OWN flags) until all
+// ranks have signalled `epoch`; world == 0 disables the wait.  Ends with a block barrier and a
+// proxy fence, so that TMA (async proxy) loads issued afterwards see the peers' stores.
+__device__ __forceinline__ void xr_wait_all(const XrWait &w)
+{
+    if (w.world == 0) return;
+    if ((int)threadIdx.x < w.world) {
+        const unsigned long long t0 = xr_now_ns();
+        while ((int)(xr_ld_acquire_sys(w.flags + threadIdx.x) - w.epoch) < 0) {
+            if (xr_now_ns() - t0 > XR_TIMEOUT_NS) { atomicExch(w.err, 1u); break; }
+            __nanosleep(32);
+        }
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async.global;\n" ::: "memory");
 }
 
 // Sum n (<= XR_SLOT) doubles over all ranks, in rank order (bit-identical result everywhere).
