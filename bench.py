@@ -198,6 +198,7 @@ def roofline_block(obj, x0, peaks):
         "logits": 4 * Lq * Lq + N * L + 4 * N * Lq,            # read W once, MSA once; write S
         "softmax_scan": 8 * N * Lq + N * L + 4 * N,            # read S, write r
         "scatter": 4 * N * Lq + int(1.75 * N * L) + 4 * Lq * Lq * nsplit,
+        "export": 0,
         "assemble": 4 * Lq * Lq * nsplit + 8 * P,
     }
     adds = N * L * Lq                                          # gather adds of logits == scatter

@@ -86,8 +86,8 @@ int dca_plm_eval(dca_plm *p, const float *x_host, float *g_host, double *fx_out)
 int dca_plm_eval_device(dca_plm *p, const float *x_dev, float *g_dev,
                         const float *dir_dev, double *scalars_out_host);
 /* measurement hooks: one evaluation with CUDA events between its kernels, on the
- * stream they run on: ms_out[5] = unpack, logits, softmax scan, scatter,
- * assemble+finalize.  out10 = {N, L, q, ld, P, nsplit, nchunk, col_tiles, Npad, nscan}. */
+ * stream they run on: ms_out[6] = unpack, logits, softmax scan, scatter, export
+ * (owner-sharded handles only, else 0), assemble+finalize.  out10 = {N, L, q, ld, P, nsplit, nchunk, col_tiles, Npad, nscan}. */
 int dca_plm_eval_timed(dca_plm *p, const float *x_host, float *ms_out);
 int dca_plm_describe(const dca_plm *p, long *out10);
 /* measurement hook for the HBM-bound part of the path: CUDA-event ms of the two L-BFGS

@@ -257,12 +257,12 @@ class PlmObjective:
                                         ptr(sc, _f64p) if read_scalars else None), "dca_plm_eval_device")
         return sc
 
-    KERNELS = ("unpack", "logits", "softmax_scan", "scatter", "assemble")
+    KERNELS = ("unpack", "logits", "softmax_scan", "scatter", "export", "assemble")
 
     def eval_timed(self, x):
         """Per-kernel CUDA-event milliseconds of one evaluation (dict by kernel)."""
         x = np.ascontiguousarray(x, dtype=np.float32)
-        ms = np.zeros(5, dtype=np.float32)
+        ms = np.zeros(6, dtype=np.float32)
         check(lib().dca_plm_eval_timed(self._h, ptr(x, _f32p), ptr(ms, _f32p)), "dca_plm_eval_timed")
         return dict(zip(self.KERNELS, ms.tolist()))
 

@@ -67,7 +67,7 @@ int plm_read_scalars(PlmProblem *p, double *out);
 // initial point (plmdca_numerics.cpp:207-249) written to device x
 int plm_init_x_device(PlmProblem *p, float *d_x);
 double *plm_scalar_buffer(PlmProblem *p);
-constexpr int PLM_NUM_KERNEL_TIMES = 5;   // unpack, logits, softmax, scatter, assemble+finalize
+constexpr int PLM_NUM_KERNEL_TIMES = 6;   // unpack, logits, softmax, scatter, export (sharded), assemble+finalize
 int plm_eval_timed(PlmProblem *p, const float *d_x, float *d_g, float *ms);
 void plm_describe(const PlmProblem *p, long *out);
 

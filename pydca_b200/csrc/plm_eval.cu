@@ -110,6 +110,7 @@ struct PlmProblem {
     unsigned *d_err = nullptr;
     double *d_scal_loc = nullptr;
     int n_active_own = 0;
+    int own_jg = AS_JG;      // sites j per CTA of the owner kernels: 8, or 2 when the shard is small
 };
 
 XrCall plm_xr_next(PlmProblem *p);
@@ -677,16 +678,16 @@ plm_assemble_kernel(const float *__restrict__ x, const float *__restrict__ G, si
 // each followed by a flag barrier (xr_barrier_kernel); the 4 objective scalars are
 // summed across ranks in rank order by xr_reduce_kernel (identical bits on all ranks).
 
-template <int Q>
+template <int Q, int JG>
 __global__ void __launch_bounds__(256)
 plm_unpack_push_kernel(const float *__restrict__ xl, long nq, long pair0, int L, int ld, int lo,
                        XrPeers P, size_t off_W, size_t off_flags, unsigned *__restrict__ ticket, unsigned epoch)
 {
     constexpr int QQ = Q * Q;
-    __shared__ float tile[AS_JG * QQ];
+    __shared__ float tile[JG * QQ];
     const int i = lo + blockIdx.y;
-    const int j0 = blockIdx.x * AS_JG;
-    const int jlo = max(j0, i + 1), jhi = min(j0 + AS_JG, L);
+    const int j0 = blockIdx.x * JG;
+    const int jlo = max(j0, i + 1), jhi = min(j0 + JG, L);
     const int npair = jhi - jlo;
     if (npair > 0) {
     const float *xb = xl + nq + (pair_index(L, i, jlo) - pair0) * QQ;    // npair consecutive blocks
@@ -737,7 +738,7 @@ plm_export_kernel(const float *__restrict__ G, size_t g_split_stride, int nsplit
 
 // gradient of my slice: 2*lambda*x + G[(j,b)][(i,a)] (my conditional, transposed through
 // smem) + the site-j conditional's half, from my own G when I own j, else from R.
-template <int Q>
+template <int Q, int JG>
 __global__ void __launch_bounds__(256)
 plm_assemble_owner_kernel(const float *__restrict__ xl, long nq, long pair0, const float *__restrict__ G,
                           size_t g_split_stride, int nsplit, const float *__restrict__ R, int L, int ld,
@@ -747,13 +748,13 @@ plm_assemble_owner_kernel(const float *__restrict__ xl, long nq, long pair0, con
                           XrWait wt, XrCall xc, double *__restrict__ scal)
 {
     constexpr int QQ = Q * Q;
-    __shared__ float tile[AS_JG * QQ];
+    __shared__ float tile[JG * QQ];
     xr_wait_all(wt);                     // every rank's export has landed in my R
     const int i = lo + blockIdx.y;
-    const int j0 = blockIdx.x * AS_JG;
-    const bool any = (j0 + AS_JG - 1 > i);
+    const int j0 = blockIdx.x * JG;
+    const bool any = (j0 + JG - 1 > i);
     if (!any && blockIdx.x != 0) return;
-    const int jlo = max(j0, i + 1), jhi = min(j0 + AS_JG, L);
+    const int jlo = max(j0, i + 1), jhi = min(j0 + JG, L);
     const int npair = max(0, jhi - jlo);
     double s_reg = 0.0, s_dg = 0.0, s_gg = 0.0, s_xx = 0.0;
 
@@ -873,9 +874,11 @@ static int plm_setup_t(PlmProblem *p)
         // first-launches a kernel while a peer thread of the same process spins in a barrier
         // would dead-lock.  Load everything the collective path launches up front.
         cudaFuncAttributes fa;
-        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_unpack_push_kernel<Q>));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_unpack_push_kernel<Q, 8>)));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_unpack_push_kernel<Q, 2>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_export_kernel<Q>));
-        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_assemble_owner_kernel<Q>));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_assemble_owner_kernel<Q, 8>)));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_assemble_owner_kernel<Q, 2>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_logits_kernel<Q, 128>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_logits_kernel<Q, 64>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_softmax_kernel<Q>));
@@ -899,11 +902,15 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
 #define PLM_MARK() do { if (ev) cudaEventRecord(ev[evi++], st); } while (0)
     if (p->sharded && !p->connected) { set_error("plm: sharded objective used before its peers were connected"); return -1; }
     PLM_MARK();
-    dim3 gridU(ceil_div(L, AS_JG), p->sharded ? nsites : L);
+    dim3 gridU(ceil_div(L, p->sharded ? p->own_jg : AS_JG), p->sharded ? nsites : L);
     if (p->sharded) {
         // fused unpack + exchange: my blocks go to my W and, by P2P stores, to the W of owner(j)
-        DCA_LAUNCH((plm_unpack_push_kernel<Q>), gridU, 256, 0, st, d_x, p->nq_loc, p->pair0, L, ld, lo,
-                   p->peers, p->lay.off_W, p->lay.off_flags, p->d_ticket + 1, ++p->epoch);
+        if (p->own_jg == 8)
+            DCA_LAUNCH((plm_unpack_push_kernel<Q, 8>), gridU, 256, 0, st, d_x, p->nq_loc, p->pair0, L, ld, lo,
+                       p->peers, p->lay.off_W, p->lay.off_flags, p->d_ticket + 1, ++p->epoch);
+        else
+            DCA_LAUNCH((plm_unpack_push_kernel<Q, 2>), gridU, 256, 0, st, d_x, p->nq_loc, p->pair0, L, ld, lo,
+                       p->peers, p->lay.off_W, p->lay.off_flags, p->d_ticket + 1, ++p->epoch);
     } else {
         DCA_LAUNCH((plm_unpack_kernel<Q>), gridU, 256, 0, st, d_x, L, ld, p->d_W);
     }
@@ -943,13 +950,21 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
         // export (+ signal) -> assemble (waits; its last CTA sums the scalars over the ranks)
         DCA_LAUNCH((plm_export_kernel<Q>), std::max(1, lo * Q), 128, 0, st, p->d_G, gstride, p->nsplit, ld, lo, hi,
                    p->peers, p->lay.off_R, p->lay.off_flags, p->d_ticket + 2, ++p->epoch);
+        PLM_MARK();
         wt.epoch = p->epoch;
         const XrCall xc = plm_xr_next(p);
-        DCA_LAUNCH((plm_assemble_owner_kernel<Q>), gridU, 256, 0, st,
-                   d_x, p->nq_loc, p->pair0, p->d_G, gstride, p->nsplit, p->d_R, L, ld, p->lh, p->lJ, lo, hi,
-                   d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket, (unsigned)p->n_active_own, p->d_scal_loc,
-                   wt, xc, p->d_scal);
+        if (p->own_jg == 8)
+            DCA_LAUNCH((plm_assemble_owner_kernel<Q, 8>), gridU, 256, 0, st,
+                       d_x, p->nq_loc, p->pair0, p->d_G, gstride, p->nsplit, p->d_R, L, ld, p->lh, p->lJ, lo, hi,
+                       d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket, (unsigned)p->n_active_own, p->d_scal_loc,
+                       wt, xc, p->d_scal);
+        else
+            DCA_LAUNCH((plm_assemble_owner_kernel<Q, 2>), gridU, 256, 0, st,
+                       d_x, p->nq_loc, p->pair0, p->d_G, gstride, p->nsplit, p->d_R, L, ld, p->lh, p->lJ, lo, hi,
+                       d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket, (unsigned)p->n_active_own, p->d_scal_loc,
+                       wt, xc, p->d_scal);
     } else {
+        PLM_MARK();
         DCA_LAUNCH((plm_assemble_kernel<Q>), gridU, 256, 0, st,
                    d_x, p->d_G, gstride, p->nsplit, L, ld, p->lh, p->lJ, lo, hi,
                    d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket, (unsigned)p->n_active, p->d_scal);
@@ -1046,13 +1061,21 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     }
     p->red_blocks = ceil_div(L, AS_JG) * L;
     p->n_active = 0;                 // assemble CTAs that own a pair or the fields of a site
-    p->n_active_own = 0;             // ... of my sites only (owner-sharded mode)
     for (int i = 0; i < L; ++i)
-        for (int bx = 0; bx < ceil_div(L, AS_JG); ++bx) {
-            const int act = (bx == 0 || bx * AS_JG + AS_JG - 1 > i) ? 1 : 0;
-            p->n_active += act;
-            if (i >= site_lo && i < site_hi) p->n_active_own += act;
-        }
+        for (int bx = 0; bx < ceil_div(L, AS_JG); ++bx)
+            p->n_active += (bx == 0 || bx * AS_JG + AS_JG - 1 > i) ? 1 : 0;
+    // owner kernels (sharded): 8 sites j per CTA unless that leaves the GPU short of CTAs
+    const int forced_jg = getenv("DCA_B200_OWN_JG") ? atoi(getenv("DCA_B200_OWN_JG")) : 0;    // tests / measurements
+    for (int jg : {8, 2}) {
+        if (forced_jg == 2 && jg == 8) continue;
+        p->own_jg = jg;
+        p->n_active_own = 0;
+        for (int i = site_lo; i < site_hi; ++i)
+            for (int bx = 0; bx < ceil_div(L, jg); ++bx)
+                p->n_active_own += (bx == 0 || bx * jg + jg - 1 > i) ? 1 : 0;
+        if (p->n_active_own >= 4 * sm_count() || forced_jg == 8) break;
+    }
+    p->red_blocks = std::max(p->red_blocks, ceil_div(L, 2) * (site_hi - site_lo));
     p->Ploc = p->P;
     if (sharded) {
         p->sharded = true;
@@ -1240,7 +1263,8 @@ int plm_eval_device(PlmProblem *p, const float *d_x, float *d_g, const float *d_
 }
 
 // one evaluation with CUDA events between the kernels, on the stream they are
-// launched on: ms[0..4] = unpack (+exchange), logits, softmax, scatter, (export +) assemble+finalize
+// launched on: ms[0..5] = unpack (+push), logits (waits for the peers' pushes), softmax, scatter,
+// export (sharded only), assemble + finalize (waits for the peers' exports; cross-rank scalar sum)
 int plm_eval_timed(PlmProblem *p, const float *d_x, float *d_g, float *ms)
 {
     cudaEvent_t ev[PLM_NUM_KERNEL_TIMES + 1];

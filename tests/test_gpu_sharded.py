@@ -128,6 +128,29 @@ def test_sharded_fit_follows_single_gpu_fit(port):
     _close(objs)
 
 
+def test_sharded_eval_wide_owner_tiles(port, monkeypatch):
+    """The owner kernels come in two tile widths (8 or 2 sites j per CTA, picked by grid size);
+    small test problems take the narrow one, so force the wide one here."""
+    from pydca_b200 import _lib
+    from pydca_b200.distributed import scatter_full_vector
+    from pydca_b200.synthetic import synthetic_msa
+    monkeypatch.setenv("DCA_B200_OWN_JG", "8")
+    N, L, q, bounds = 300, 21, 21, [0, 5, 13, 21]
+    msa = synthetic_msa(N, L, q, seed=9)
+    w = port.plm_weights(port.reweight_counts(msa, 0.8))
+    lam = 0.2 * (L - 1)
+    objs = _make_ranks(msa, w, q, lam, bounds)
+    monkeypatch.delenv("DCA_B200_OWN_JG")
+    ref = _lib.PlmObjective(msa, w, q, lam, lam)
+    x = (ref.init() + np.random.default_rng(3).normal(0, 0.2, ref.P)).astype(np.float32)
+    fx1, g1 = ref.eval(x)
+    ref.close()
+    outs = _run_ranks(3, lambda r: objs[r].eval(objs[r].local_slice(x)))
+    g = scatter_full_vector([o[1] for o in outs], [o.local_layout() for o in objs], objs[0].P)
+    assert abs(outs[0][0] - fx1) <= 1e-9 * abs(fx1) and relmax(g, g1) <= 2e-6
+    _close(objs)
+
+
 def test_sharded_world1_is_the_plain_objective(port):
     from pydca_b200 import _lib
     from pydca_b200.synthetic import synthetic_msa

@@ -66,7 +66,7 @@ def main():
                   (fx, f1, abs(fx - f1) / abs(f1), np.abs(g - g1).max() / np.abs(g1).max()), flush=True)
         # per-kernel times (collective call), max over ranks
         sp.obj.eval_timed(xl)
-        acc = np.zeros(5)
+        acc = np.zeros(6)
         for _ in range(5):
             t = sp.obj.eval_timed(xl)
             acc += np.array([t[k] for k in sp.obj.KERNELS])
@@ -76,7 +76,7 @@ def main():
         alls = [torch.zeros_like(tt) for _ in range(world)]
         dist.all_gather(alls, tt)
         if rank == 0:
-            print("kernel ms (max over ranks) unpack+xchg %.3f logits %.3f softmax %.3f scatter %.3f export+assemble+reduce %.3f  sum %.3f"
+            print("kernel ms (max over ranks) unpack+push %.3f logits %.3f softmax %.3f scatter %.3f export %.3f assemble+reduce %.3f  sum %.3f"
                   % (*tmax.tolist(), float(tmax.sum())))
             for r, a in enumerate(alls):
                 print("   rank %d sites %d: %s  describe %s" % (r, bounds[r + 1] - bounds[r],
