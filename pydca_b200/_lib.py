@@ -8,6 +8,7 @@ every compute call raises ``DcaBackendError``.
 import ctypes
 import glob
 import os
+import weakref
 
 import numpy as np
 
@@ -310,13 +311,23 @@ def last_fit():
 
 
 def plmdca_backend(msa_file, biomolecule, seqs_len, num_site_states, seqid, lambda_h, lambda_J,
-                   max_iterations, num_threads=1, verbose=False):
-    """The reference's C entry point, called the way pydca/plmdca/plmdca.py:216-230 calls it."""
+                   max_iterations, num_threads=1, verbose=False, copy=False):
+    """The reference's C entry point, called the way pydca/plmdca/plmdca.py:216-230 calls it.
+
+    The reference copies the returned buffer element by element and then calls
+    freeFieldsAndCouplings (:225-230).  Here the float32[P] result is a zero-copy view of the
+    library's host buffer; freeFieldsAndCouplings runs when the array (and every view of it) is
+    garbage collected.  ``copy=True`` gives the reference's copy-then-free behaviour."""
     p = seqs_len * num_site_states + seqs_len * (seqs_len - 1) // 2 * num_site_states ** 2
-    h = lib().plmdcaBackend(biomolecule_int(biomolecule), num_site_states, os.fsencode(msa_file), seqs_len,
-                            seqid, lambda_h, lambda_J, max_iterations, num_threads, verbose)
+    L = lib()
+    h = L.plmdcaBackend(biomolecule_int(biomolecule), num_site_states, os.fsencode(msa_file), seqs_len,
+                        seqid, lambda_h, lambda_J, max_iterations, num_threads, verbose)
     if not h:
         raise DcaBackendError("plmdcaBackend failed: %s" % last_error())
-    x = np.ctypeslib.as_array(ctypes.cast(h, _f32p), shape=(p,)).copy()
-    lib().freeFieldsAndCouplings(h)
+    x = np.ctypeslib.as_array(ctypes.cast(h, _f32p), shape=(p,))
+    if copy:
+        x = x.copy()
+        L.freeFieldsAndCouplings(h)
+        return x
+    weakref.finalize(x, L.freeFieldsAndCouplings, h)
     return x

@@ -1100,10 +1100,17 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
         int best_s = 1;
         for (int s = 1; s <= (sharded ? 16 : 8); ++s) {
             if (s > 1 && p->nchunk / s < 4) break;
-            const double cost = (double)ceil_div<long>(tiles * s, sms) / s * (1.0 + 0.02 * s);
+            // every extra split is one more copy of G for export / assemble to sum; on the small
+            // grids of a multi-GPU shard that costs more than a slightly longer scatter (measured
+            // at 8 GPUs: 3 splits 2756 evaluations/s, 7 splits 2700)
+            const double cost = (double)ceil_div<long>(tiles * s, sms) / s * (1.0 + (sharded ? 0.06 : 0.02) * s);
             if (cost < best - 1e-12) { best = cost; best_s = s; }
         }
         p->nsplit = best_s;
+        if (const char *e = getenv("DCA_B200_NSPLIT")) {            // measurement override
+            const int v = atoi(e);
+            if (v >= 1 && v <= 16 && v <= p->nchunk) p->nsplit = v;
+        }
         p->chunks_per_split = ceil_div(p->nchunk, p->nsplit);
         p->nsplit = ceil_div(p->nchunk, p->chunks_per_split);
     }

@@ -25,7 +25,8 @@ def main():
 
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
     L = int(sys.argv[2]) if len(sys.argv) > 2 else 150
-    rhos = [float(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0.5]
+    rhos = [float(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0.0]
+    nsplits = [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]
     q = 21
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     _lib.check(_lib.lib().dca_set_device(local), "set_device")
@@ -35,7 +36,9 @@ def main():
     counts = dd.sharded_counts(msa, 0.8, device=torch.device("cuda", local))
     w = (1.0 / counts.astype(np.float32)).astype(np.float32)
     lam = 0.2 * (L - 1)
-    for rho in rhos:
+    for rho, ns in [(r, n) for r in rhos for n in nsplits]:
+        if ns > 0:
+            os.environ["DCA_B200_NSPLIT"] = str(ns)       # read by the scatter planner at create time
         bounds = dd.balanced_site_bounds(L, world, rho)
         sp = dd.ShardedPlm(msa, w, q, lam, lam, bounds=bounds)
         P = sp.obj.P
@@ -61,7 +64,7 @@ def main():
             ref = _lib.PlmObjective(msa, w, q, lam, lam)
             f1, g1 = ref.eval(xfull)
             ref.close()
-            print("rho %.2f bounds %s" % (rho, bounds))
+            print("rho %.2f nsplit override %d bounds %s" % (rho, ns, bounds))
             print("parity: fx %.9g vs %.9g (rel %.2e)  g relmax %.2e" %
                   (fx, f1, abs(fx - f1) / abs(f1), np.abs(g - g1).max() / np.abs(g1).max()), flush=True)
         # per-kernel times (collective call), max over ranks
