@@ -189,6 +189,7 @@ def roofline_block(obj, x0, peaks):
         t = obj.eval_timed(x0)
         acc = t if acc is None else {k: acc[k] + t[k] for k in t}
     ms = {k: v / reps for k, v in acc.items()}
+    ms.pop("export", None)                 # owner-sharded runs only (no kernel here: an empty event gap)
     g = obj.describe()
     N, L, q, ld, P, nsplit = g["N"], g["L"], g["q"], g["ld"], g["P"], g["nsplit"]
     Lq = L * q
@@ -198,7 +199,6 @@ def roofline_block(obj, x0, peaks):
         "logits": 4 * Lq * Lq + N * L + 4 * N * Lq,            # read W once, MSA once; write S
         "softmax_scan": 8 * N * Lq + N * L + 4 * N,            # read S, write r
         "scatter": 4 * N * Lq + int(1.75 * N * L) + 4 * Lq * Lq * nsplit,
-        "export": 0,
         "assemble": 4 * Lq * Lq * nsplit + 8 * P,
     }
     adds = N * L * Lq                                          # gather adds of logits == scatter
@@ -214,7 +214,7 @@ def roofline_block(obj, x0, peaks):
     traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        ncu_name = {"unpack": "plm_unpack_kernel<21>", "logits": "plm_logits_kernel<21>",
+        ncu_name = {"unpack": "plm_unpack_kernel<21>", "logits": "plm_logits_kernel<21, 128>",
                     "softmax_scan": "plm_softmax_kernel<21>", "scatter": "plm_scatter_kernel<21>",
                     "assemble": "plm_assemble_kernel<21>"}[top]
         traffic = tj["kernels"][ncu_name]["dram_bytes"]
