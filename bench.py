@@ -268,7 +268,13 @@ def run_ours(args, rank, world, local_rank):
     _lib.check(L.dca_set_device(local_rank), "dca_set_device")
     dist = None
     torch = None
+    saved_stdout = None
     if world > 1:
+        # stdout must carry exactly ONE line (the JSON): NCCL prints its version banner there when
+        # NCCL_DEBUG asks for it, so everything up to the final print goes to stderr instead
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -361,11 +367,19 @@ def run_ours(args, rank, world, local_rank):
         dev = torch.device("cuda", local_rank)
         c2 = dd.sharded_counts(msa, SEQID, device=dev)
         w2 = (1.0 / c2.astype(np.float32)).astype(np.float32)
+        t_rw = time.perf_counter()
         if exchange == "peer":
             sp2 = dd.ShardedPlm(msa, w2, Q, lam, lam)
+            t_mk = time.perf_counter()
             _, r2 = sp2.fit(MAX_ITER)
+            t_fit = time.perf_counter()
             x_full = sp2.gather()
+            t_ga = time.perf_counter()
             sp2.close()
+            if rank == 0:
+                print("e2e stages ms: reweight %.1f setup %.1f %s fit %.1f gather %.1f close %.1f"
+                      % (1e3 * (t_rw - t0), 1e3 * (t_mk - t_rw), {k: round(v, 1) for k, v in sp2.trace.items()},
+                         1e3 * (t_fit - t_mk), 1e3 * (t_ga - t_fit), 1e3 * (time.perf_counter() - t_ga)), file=sys.stderr)
         else:
             o2 = _lib.PlmObjective(msa, w2, Q, lam, lam, sites=dd.shard_range(SEQ_LEN, rank, world))
             cb2 = dd.make_allreduce_callback(o2.cuda_stream())
@@ -402,7 +416,12 @@ def run_ours(args, rank, world, local_rank):
             except Exception as exc:
                 line["cpu_baseline"] = {"value": None, "unit": "evals/s", "cores": cores, "kind": "unavailable",
                                         "sample": repr(exc)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        if saved_stdout is not None:
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        if saved_stdout is not None:
+            os.dup2(2, 1)
     if sp is not None:
         sp.close()
     else:

@@ -116,6 +116,10 @@ typedef struct {
 int dca_plm_fit(dca_plm *p, float *x_inout_host, int max_iterations, int verbose,
                 int warmup_iterations, dca_allreduce_fn allreduce, void *allreduce_ctx,
                 dca_fit_result *result);
+/* the same from the reference's initial point (plmdcaBackend.cpp:77) built on the device; the result
+ * stays in the handle's device buffer (dca_plm_x_device): no host copy of the parameters at all.
+ * On a sharded handle: collective, local slice. */
+int dca_plm_fit_from_init(dca_plm *p, int max_iterations, int verbose, dca_fit_result *result);
 /* ---- owner-sharded plmDCA for 2..16 GPUs of one node (one process per GPU) -----------------
  * The reference parallelises PlmDCA::gradient over sites with OpenMP
  * (plmdca_numerics.cpp:488); here rank r of `world` OWNS the sites

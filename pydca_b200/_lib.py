@@ -98,6 +98,7 @@ def lib():
     L.dca_plm_eval_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _f64p]
     L.dca_plm_fit.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                               ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FitResult)]
+    L.dca_plm_fit_from_init.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(FitResult)]
     L.dca_plm_eval_timed.argtypes = [ctypes.c_void_p, _f32p, _f32p]
     L.dca_lbfgs_vector_bench.argtypes = [ctypes.c_long, ctypes.c_int, ctypes.c_int, _f32p]
     L.dca_plm_cuda_stream.argtypes = [ctypes.c_void_p]
@@ -284,6 +285,18 @@ class PlmObjective:
         check(lib().dca_plm_fit(self._h, ptr(x, _f32p), int(max_iterations), int(bool(verbose)),
                                 int(warmup_iterations), cb, None, ctypes.byref(res)), "dca_plm_fit")
         return x, res
+
+
+def _fit_from_init(self, max_iterations, verbose=False):
+    """Initial point built on the device, L-BFGS, result left in the handle's device buffer
+    (x_device()): no host copy of the parameters in either direction."""
+    res = FitResult()
+    check(lib().dca_plm_fit_from_init(self._h, int(max_iterations), int(bool(verbose)), ctypes.byref(res)),
+          "dca_plm_fit_from_init")
+    return res
+
+
+PlmObjective.fit_from_init = _fit_from_init
 
 
 def plm_fn_apc(x, seqs_len, num_site_states):

@@ -353,6 +353,23 @@ int dca_plm_fit(dca_plm *p, float *x_inout_host, int max_iterations, int verbose
     return 0;
 }
 
+int dca_plm_fit_from_init(dca_plm *p, int max_iterations, int verbose, dca_fit_result *result)
+{
+    if (!p) { set_error("dca_plm_fit_from_init: null handle"); return -1; }
+    if (plm_init_x_device(p->prob, p->d_x) != 0) return -1;
+    LbfgsResult r{};
+    double timed_ms = 0.0;
+    int timed_evals = 0;
+    if (lbfgs_minimize(p->prob, p->d_x, max_iterations, verbose, nullptr, nullptr, &r, 0, &timed_ms, &timed_evals) != 0)
+        return -1;
+    if (result) {
+        result->status = r.status; result->iterations = r.iterations; result->evaluations = r.evaluations;
+        result->fx = r.fx; result->device_ms = r.device_ms; result->timed_ms = timed_ms;
+        result->timed_evaluations = timed_evals;
+    }
+    return 0;
+}
+
 int dca_plm_fn_apc(const float *x_host, int seqs_len, int num_site_states, double *fn_out, double *fn_apc_out)
 {
     if (!x_host || !fn_out) { set_error("dca_plm_fn_apc: null argument"); return -1; }

@@ -24,7 +24,8 @@
 //   W     f32 [L*q][ld]     full symmetric coupling matrix, row (j,b) = j*q+b,
 //                           column (i,a) = i*q+a, zero diagonal blocks;
 //                           rebuilt from x every evaluation (unpack)
-//   S     f32 [Npad][ld]    logits, overwritten in place by the residuals r
+//   S     f32 [Npad][ld]    logits
+//   Rz    f32 [Npad][ld]    residuals r (separate buffer: see plm_softmax_kernel)
 //   G     f32 [nsplit][L*q][ld]   G[(j,b)][(i,a)] = sum_n [s_nj==b] r_n(i,a)
 //   perm  [site tile][nchunk][site][832 B]  per (site, 128-sequence chunk): bucket
 //                           sizes + the chunk's rows as byte offsets grouped by
@@ -80,7 +81,7 @@ struct PlmProblem {
     int carry = 1, chunk = 32, warm = 32;
     cudaStream_t stream = nullptr;
     uint8_t *d_msa = nullptr, *d_msaT = nullptr, *d_perm = nullptr;
-    float *d_w = nullptr, *d_W = nullptr, *d_G = nullptr, *d_S = nullptr;
+    float *d_w = nullptr, *d_W = nullptr, *d_G = nullptr, *d_S = nullptr, *d_Rz = nullptr;
     double *d_fxpart = nullptr, *d_red = nullptr, *d_scal = nullptr, *h_scal = nullptr;
     float h_meff = 0.f;
     int nsplit = 1, chunks_per_split = 0, nchunk = 0;
@@ -90,7 +91,7 @@ struct PlmProblem {
     int col_tile0 = 0, col_tiles = 0;     // scatter: 128-column tiles covering my sites' columns
     int lg_tc = LG_TC, lg_tile0 = 0, lg_tiles = 0;   // logits: lg_tc-column tiles (128, or 64 for small grids)
     int site_tiles = 0, sites_per_tile = 0;
-    CUtensorMap tmS;         // S as [Npad][ld] f32, box 128 x 128 (scatter tiles)
+    CUtensorMap tmS;         // Rz (residuals) as [Npad][ld] f32, box 128 x 128 (scatter tiles)
     CUtensorMap tmW;         // W as [Lq][ld] f32, box lg_tc x JB*q (logits stage)
     CUtensorMap tmM;         // msaT as [L][Npad] u8, box 128 x JB (logits stage)
     // ---- owner-sharded multi-GPU mode (xrank.cuh): x, g and every L-BFGS vector hold only
@@ -309,9 +310,12 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 // ------------------------------------------------------------------------------
 // softmax with the reference's carry, chunked with a warm-up overlap.
 // warp = 32 consecutive sites of one chunk; lane = one (site, chunk) chain.
-template <int Q>
+// Logits are read from S, residuals written to a SEPARATE buffer Rz: a chain's warm-up rows are
+// the rows other chains emit, so writing the residuals in place (the first version did) is a race
+// that only co-residency of all CTAs hid -- grids of more than one wave read residuals as logits.
+template <int Q, int SM_PF>
 __global__ void __launch_bounds__(128)
-plm_softmax_kernel(float *__restrict__ S, int ld, const uint8_t *__restrict__ msa,
+plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, const uint8_t *__restrict__ msa,
                    const float *__restrict__ w, long N, int L, int site_lo, int site_hi,
                    int chunk, int warm, int carry, double *__restrict__ fxpart)
 {
@@ -329,58 +333,72 @@ plm_softmax_kernel(float *__restrict__ S, int ld, const uint8_t *__restrict__ ms
     float *buf = sbuf[wib];
     const size_t cbase = (size_t)s0 * Q;
 
-    float p[Q], nxt[Q];
+    // The chain is serial in n and every step needs one row segment of S from L2/HBM.  SM_PF rows
+    // are kept in flight (register ring, statically indexed by unrolling the step loop SM_PF
+    // times).  Large grids are issue-bound and want occupancy: SM_PF = 1 (96 registers).  Small
+    // grids (multi-GPU shards) are bound by the memory round trip per step (~0.9 us x 48 steps
+    // was the whole 45 us kernel): SM_PF = 4 (201 registers) hides it.
+    float p[Q], nxt[SM_PF][Q];
 #pragma unroll
     for (int a = 0; a < Q; ++a) p[a] = 0.f;
     double fx = 0.0;
 #pragma unroll
-    for (int t = 0; t < Q; ++t) {
-        const int idx = lane + 32 * t;
-        nxt[t] = (idx < ncols) ? S[(size_t)nstart * ld + cbase + idx] : 0.f;
-    }
-    for (long n = nstart; n < nend; ++n) {
+    for (int u = 0; u < SM_PF; ++u) {
+        const long nn = nstart + u;
 #pragma unroll
-        for (int t = 0; t < Q; ++t) buf[lane + 32 * t] = nxt[t];
-        if (n + 1 < nend) {
-#pragma unroll
-            for (int t = 0; t < Q; ++t) {
-                const int idx = lane + 32 * t;
-                nxt[t] = (idx < ncols) ? S[(size_t)(n + 1) * ld + cbase + idx] : 0.f;
-            }
+        for (int t = 0; t < Q; ++t) {
+            const int idx = lane + 32 * t;
+            nxt[u][t] = (nn < nend && idx < ncols) ? S[(size_t)nn * ld + cbase + idx] : 0.f;
         }
-        __syncwarp();
-        float l[Q];
+    }
+    for (long n0 = nstart; n0 < nend; n0 += SM_PF) {
 #pragma unroll
-        for (int a = 0; a < Q; ++a) l[a] = carry ? (p[a] + buf[lane * Q + a]) : buf[lane * Q + a];
-        float m = l[0];
+        for (int u = 0; u < SM_PF; ++u) {
+            const long n = n0 + u;
+            if (n >= nend) break;                          // warp-uniform
 #pragma unroll
-        for (int a = 1; a < Q; ++a) m = fmaxf(m, l[a]);
-        float z = 0.f;
+            for (int t = 0; t < Q; ++t) buf[lane + 32 * t] = nxt[u][t];
+            if (n + SM_PF < nend) {
 #pragma unroll
-        for (int a = 0; a < Q; ++a) { l[a] = expf(l[a] - m); z += l[a]; }
-        const float zi = 1.f / z;
-#pragma unroll
-        for (int a = 0; a < Q; ++a) p[a] = l[a] * zi;
-
-        if (n >= nbeg) {
-            if (active) {
-                const int r = msa[(size_t)n * L + site];
-                const float wn = w[n];
-                float pr = p[0];
-#pragma unroll
-                for (int a = 1; a < Q; ++a) pr = (a == r) ? p[a] : pr;
-                fx -= (double)(wn * logf(pr));
-#pragma unroll
-                for (int a = 0; a < Q; ++a) buf[lane * Q + a] = wn * p[a] - ((a == r) ? wn : 0.f);
+                for (int t = 0; t < Q; ++t) {
+                    const int idx = lane + 32 * t;
+                    nxt[u][t] = (idx < ncols) ? S[(size_t)(n + SM_PF) * ld + cbase + idx] : 0.f;
+                }
             }
             __syncwarp();
+            float l[Q];
 #pragma unroll
-            for (int t = 0; t < Q; ++t) {
-                const int idx = lane + 32 * t;
-                if (idx < ncols) S[(size_t)n * ld + cbase + idx] = buf[idx];
+            for (int a = 0; a < Q; ++a) l[a] = carry ? (p[a] + buf[lane * Q + a]) : buf[lane * Q + a];
+            float m = l[0];
+#pragma unroll
+            for (int a = 1; a < Q; ++a) m = fmaxf(m, l[a]);
+            float z = 0.f;
+#pragma unroll
+            for (int a = 0; a < Q; ++a) { l[a] = expf(l[a] - m); z += l[a]; }
+            const float zi = 1.f / z;
+#pragma unroll
+            for (int a = 0; a < Q; ++a) p[a] = l[a] * zi;
+
+            if (n >= nbeg) {
+                if (active) {
+                    const int r = msa[(size_t)n * L + site];
+                    const float wn = w[n];
+                    float pr = p[0];
+#pragma unroll
+                    for (int a = 1; a < Q; ++a) pr = (a == r) ? p[a] : pr;
+                    fx -= (double)(wn * logf(pr));
+#pragma unroll
+                    for (int a = 0; a < Q; ++a) buf[lane * Q + a] = wn * p[a] - ((a == r) ? wn : 0.f);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < Q; ++t) {
+                    const int idx = lane + 32 * t;
+                    if (idx < ncols) Rz[(size_t)n * ld + cbase + idx] = buf[idx];
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
     fx = warp_sum(active ? fx : 0.0);
     if (lane == 0) fxpart[k * gridDim.x + blockIdx.x] = fx;
@@ -881,7 +899,8 @@ static int plm_setup_t(PlmProblem *p)
         DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_assemble_owner_kernel<Q, 2>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_logits_kernel<Q, 128>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_logits_kernel<Q, 64>)));
-        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_softmax_kernel<Q>));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_softmax_kernel<Q, 1>)));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_softmax_kernel<Q, 4>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_scatter_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_init_fields_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, xr_barrier_kernel));
@@ -932,9 +951,14 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
     PLM_MARK();
 
     dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
-    DCA_LAUNCH((plm_softmax_kernel<Q>), gridB, 128, 0, st,
-               p->d_S, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-               p->chunk, p->warm, p->carry, p->d_fxpart);
+    if ((long)gridB.x * gridB.y > 2L * sm_count())
+        DCA_LAUNCH((plm_softmax_kernel<Q, 1>), gridB, 128, 0, st,
+                   p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
+                   p->chunk, p->warm, p->carry, p->d_fxpart);
+    else
+        DCA_LAUNCH((plm_softmax_kernel<Q, 4>), gridB, 128, 0, st,
+                   p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
+                   p->chunk, p->warm, p->carry, p->d_fxpart);
     PLM_MARK();
 
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
@@ -982,7 +1006,7 @@ static void plm_free(PlmProblem *p)
     if (p->stream) cudaStreamSynchronize(p->stream);
     dev_free(p->d_msa); dev_free(p->d_msaT); dev_free(p->d_perm); dev_free(p->d_w);
     if (!p->sharded) dev_free(p->d_W);
-    dev_free(p->d_G); dev_free(p->d_S); dev_free(p->d_fxpart);
+    dev_free(p->d_G); dev_free(p->d_S); dev_free(p->d_Rz); dev_free(p->d_fxpart);
     dev_free(p->d_red); dev_free(p->d_scal); dev_free(p->d_ticket); dev_free(p->d_scal_loc);
     if (p->arena) cudaFree(p->arena);        // peers must have disconnected first (plm_disconnect)
     if (p->h_scal) host_pinned_free(p->h_scal);
@@ -1152,6 +1176,7 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     }
     PLM_ALLOC(p->d_G, sizeof(float) * (size_t)p->nsplit * p->Lq * p->ld);
     PLM_ALLOC(p->d_S, sizeof(float) * (size_t)p->Npad * p->ld);
+    PLM_ALLOC(p->d_Rz, sizeof(float) * (size_t)p->Npad * p->ld);
     PLM_ALLOC(p->d_fxpart, sizeof(double) * (size_t)(N / 8 + 1) * L);   // chunk >= 8
     PLM_ALLOC(p->d_red, sizeof(double) * 4 * (size_t)p->red_blocks);
     PLM_TRY(cudaMemsetAsync(p->d_red, 0, sizeof(double) * 4 * (size_t)p->red_blocks, p->stream));
@@ -1165,8 +1190,9 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     PLM_TRY(cudaMemcpyAsync(p->d_msa, h_msa, (size_t)N * L, cudaMemcpyHostToDevice, p->stream));
     PLM_TRY(cudaMemcpyAsync(p->d_w, h_w, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, p->stream));
     PLM_TRY(cudaMemsetAsync(p->d_S, 0, sizeof(float) * (size_t)p->Npad * p->ld, p->stream));
+    PLM_TRY(cudaMemsetAsync(p->d_Rz, 0, sizeof(float) * (size_t)p->Npad * p->ld, p->stream));
     PLM_TRY(cudaMemsetAsync(p->d_fxpart, 0, sizeof(double) * (size_t)(N / 8 + 1) * L, p->stream));
-    if (make_tensor_map_2d(&p->tmS, 4, p->d_S, (unsigned long long)p->ld, (unsigned long long)p->Npad,
+    if (make_tensor_map_2d(&p->tmS, 4, p->d_Rz, (unsigned long long)p->ld, (unsigned long long)p->Npad,
                            sizeof(float) * (unsigned long long)p->ld, SC_TC, SC_CH) != 0) { plm_free(p); return nullptr; }
     {
         const unsigned jb = (q > 8) ? 4 : 16;         // LgCfg<Q>::JB

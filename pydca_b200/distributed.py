@@ -84,22 +84,34 @@ def allgather_counts(local_counts, rows, num_seqs, group=None, device=None):
     return t.cpu().numpy().astype(np.uint32)
 
 
-def sharded_counts(msa, seqid, compare_f64=False, group=None, device=None):
-    """c_i over all ranks: row shard on this rank's GPU + one collective."""
+#: below this many residue compares (N * N * L) every rank simply computes all counts itself:
+#: the whole reweighting is then under ~10 ms on one B200 and a collective would cost more
+REPLICATE_REWEIGHT_BELOW = 1.0e11
+
+
+def sharded_counts(msa, seqid, compare_f64=False, group=None, device=None, force_shard=False):
+    """c_i on every rank.  Deep alignments: row shard on this rank's GPU + one collective
+    (disjoint rows, so the sum is a gather).  Shallow ones: computed redundantly, no collective."""
     import torch.distributed as dist
     from . import _lib
+    n, l = msa.shape
+    if not force_shard and float(n) * n * l < REPLICATE_REWEIGHT_BELOW:
+        return _lib.sequence_counts(msa, seqid, compare_f64=compare_f64)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    lo, hi = shard_range(msa.shape[0], rank, world)
+    lo, hi = shard_range(n, rank, world)
     local = _lib.sequence_counts(msa, seqid, compare_f64=compare_f64, rows=(lo, hi))
-    return allgather_counts(local, (lo, hi), msa.shape[0], group=group, device=device)
+    return allgather_counts(local, (lo, hi), n, group=group, device=device)
 
 
 # ---- owner-sharded plmDCA (peer-memory exchange) ------------------------------------------
-def balanced_site_bounds(seqs_len, world, rho=0.5):
+def balanced_site_bounds(seqs_len, world, rho=0.0):
     """Contiguous site ranges, bounds[r] .. bounds[r+1], that balance the per-rank cost.
     Site i costs 1 (its column of the gather / scatter kernels) + rho * (L-1-i)/(L-1) (the
-    L-1-i coupling blocks it owns: unpack, assemble and every L-BFGS vector pass), so low
-    ranks get slightly fewer sites.  Every rank owns at least one site."""
+    L-1-i coupling blocks it owns: unpack, assemble and every L-BFGS vector pass), so rho > 0
+    gives low ranks fewer sites.  Measured at the bench workload the gather / scatter kernels and
+    their 128-column tile quantisation dominate: the plain balanced split (rho = 0, the default)
+    was fastest at 2 and 8 GPUs (2756 vs 2590 evaluations/s at rho = 0.15 on 8).  Every rank owns
+    at least one site."""
     L, world = int(seqs_len), int(world)
     if world > L:
         raise ValueError("more ranks (%d) than sites (%d)" % (world, L))
@@ -138,23 +150,36 @@ class ShardedPlm:
     """
 
     def __init__(self, msa, weights, num_site_states, lambda_h, lambda_J, group=None, bounds=None):
+        import time
         import torch.distributed as dist
         from . import _lib
+        t0 = time.perf_counter()
+        self.trace = {}                          # wall-clock ms of the set-up stages (diagnostics)
+
+        def mark(name):
+            nonlocal t0
+            t1 = time.perf_counter()
+            self.trace[name] = self.trace.get(name, 0.0) + 1e3 * (t1 - t0)
+            t0 = t1
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         L = msa.shape[1]
         self.bounds = list(bounds) if bounds is not None else balanced_site_bounds(L, self.world)
         self.obj = _lib.PlmObjective(msa, weights, num_site_states, lambda_h, lambda_J,
                                      shard=(self.rank, self.world, self.bounds))
+        mark("create")
         handles = [None] * self.world
         dist.all_gather_object(handles, self.obj.ipc_handle(), group=group)
+        mark("exchange_handles")
         err = None
         try:
             self.obj.connect_ipc(handles)
         except Exception as exc:                 # e.g. no P2P between two devices
             err = repr(exc)
+        mark("ipc_open")
         errs = [None] * self.world
         dist.all_gather_object(errs, err, group=group)       # all ranks succeed or all give up
+        mark("agree")
         if any(e is not None for e in errs):
             self.obj.disconnect()
             dist.barrier(group=group)
@@ -164,13 +189,17 @@ class ShardedPlm:
         self.layouts = [_lib.shard_layout(L, num_site_states, self.bounds[r], self.bounds[r + 1])
                         for r in range(self.world)]
         dist.barrier(group=group)               # every arena is mapped everywhere before the first push
+        mark("barrier")
 
     def init(self):
         return self.obj.init()
 
     def fit(self, max_iterations, x0_local=None, verbose=False):
-        x0 = self.obj.init() if x0_local is None else x0_local
-        return self.obj.fit(x0, max_iterations, verbose=verbose)
+        """L-BFGS on the local slices (collective).  Without ``x0_local`` the reference's initial
+        point is built on the device and the result stays there for gather(): no host copies."""
+        if x0_local is None:
+            return None, self.obj.fit_from_init(max_iterations, verbose=verbose)
+        return self.obj.fit(x0_local, max_iterations, verbose=verbose)
 
     def gather(self, x_local=None, device=None):
         """All ranks' slices -> the full parameter vector (reference layout) on every rank:
@@ -190,7 +219,12 @@ class ShardedPlm:
             mine[:self.obj.Ploc] = torch.from_numpy(np.ascontiguousarray(x_local, dtype=np.float32))
         out = torch.empty(self.world * nmax, dtype=torch.float32, device=mine.device)
         dist.all_gather_into_tensor(out, mine, group=self.group)
-        allx = out.cpu().numpy().reshape(self.world, nmax)
+        if out.is_cuda:
+            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream(out.device).synchronize()
+            out = host
+        allx = out.numpy().reshape(self.world, nmax)
         return scatter_full_vector([allx[r] for r in range(self.world)], self.layouts, self.obj.P)
 
     def close(self):

@@ -40,6 +40,7 @@ def test_balanced_site_bounds_cover_and_order():
     assert sizes.max() - sizes.min() <= 1
     b = balanced_site_bounds(150, 8, 0.5)
     assert b[1] - b[0] < b[8] - b[7]
+    assert balanced_site_bounds(150, 8) == balanced_site_bounds(150, 8, 0.0)
 
 
 def test_shard_layout_partitions_the_parameter_vector():

@@ -117,6 +117,40 @@ def test_plm_eval_vs_oracle_shapes(port, N, L, q):
     obj.close()
 
 
+def test_fit_from_device_init_equals_fit_from_host_init(golden):
+    """dca_plm_fit_from_init (no host copies) takes the same optimisation path as
+    dca_plm_init -> host -> dca_plm_fit: deterministic kernels, identical scalars."""
+    d = golden("plm_mid_protein.npz")
+    obj = lib().PlmObjective(d["msa"], d["w"], int(d["q"]), float(d["lambda_h"]), float(d["lambda_J"]))
+    _, r1 = obj.fit(obj.init(), 15)
+    r2 = obj.fit_from_init(15)
+    assert (r1.status, r1.iterations, r1.evaluations, r1.fx) == (r2.status, r2.iterations, r2.evaluations, r2.fx)
+    obj.close()
+
+
+def test_plm_eval_multi_wave_scan_matches_oracle(port):
+    """Deep alignment: the chunked carry scan needs more CTAs than fit on the GPU at once, so
+    chains start long after the chains that own their warm-up rows have finished.  (Residuals
+    used to be written over the logits in place; only co-residency of all CTAs hid that race.)
+    Checked against the serial float32 oracle and for independence of the scan parameters."""
+    N, L, q = 60000, 33, 21
+    rng = np.random.default_rng(12)
+    msa = rng.integers(0, q, size=(N, L), dtype=np.uint8)
+    w = rng.uniform(0.05, 1.0, N).astype(np.float32)
+    lam = 0.2 * (L - 1)
+    obj = lib().PlmObjective(msa, w, q, lam, lam)
+    x = (obj.init() + rng.normal(0, 0.3, obj.P)).astype(np.float32)
+    fx, g = obj.eval(x)
+    port.set_num_threads(8)
+    fo, go = port.plm_gradient(msa, w, q, lam, lam, x)
+    assert relmax(g, go) <= 1e-5
+    assert abs(fx - fo) <= 2e-4 * abs(fo)                       # oracle fx is float32-accumulated
+    obj.set_carry(True, chunk=64, warm=32)
+    fx2, g2 = obj.eval(x)
+    assert relmax(g2, g) <= 2e-6 and abs(fx2 - fx) <= 1e-7 * abs(fx)
+    obj.close()
+
+
 def test_plm_eval_carry_modes_and_scan_parameters(golden, port):
     """carry=False is textbook plmDCA; with carry the result must not depend on how
     the chain is chunked (chunk/warm-up), i.e. the warm-up really reproduces the
