@@ -361,40 +361,51 @@ def run_ours(args, rank, world, local_rank):
                "ms_per_step": 1e3 * e_wall / n_e2e, "steps": n_e2e,
                "call": "plmdcaBackend(msa_file, ...) -> float*: FASTA parse + dedup + reweight + H2D + fit + D2H"}
     else:
-        # sharded end-to-end: host MSA -> row-sharded reweight -> create + wire -> fit -> full x on the host
+        # sharded end-to-end, host buffers in and out on every rank: MSA -> reweight -> sharded create +
+        # peer wiring -> fit -> NCCL all-gather -> full parameter vector on the host
+        dev = torch.device("cuda", local_rank)
+
+        def e2e_call(report):
+            ta = time.perf_counter()
+            c2 = dd.sharded_counts(msa, SEQID, device=dev)
+            w2 = (1.0 / c2.astype(np.float32)).astype(np.float32)
+            t_rw = time.perf_counter()
+            if exchange == "peer":
+                sp2 = dd.ShardedPlm(msa, w2, Q, lam, lam)
+                t_mk = time.perf_counter()
+                _, r2 = sp2.fit(MAX_ITER)
+                t_fit = time.perf_counter()
+                x_full = sp2.gather()
+                t_ga = time.perf_counter()
+                sp2.close()
+                if report and rank == 0:
+                    print("e2e stages ms: reweight %.1f setup %.1f %s fit %.1f gather %.1f close %.1f"
+                          % (1e3 * (t_rw - ta), 1e3 * (t_mk - t_rw), {k: round(v, 1) for k, v in sp2.trace.items()},
+                             1e3 * (t_fit - t_mk), 1e3 * (t_ga - t_fit), 1e3 * (time.perf_counter() - t_ga)), file=sys.stderr)
+            else:
+                o2 = _lib.PlmObjective(msa, w2, Q, lam, lam, sites=dd.shard_range(SEQ_LEN, rank, world))
+                cb2 = dd.make_allreduce_callback(o2.cuda_stream())
+                x_full, r2 = o2.fit(o2.init(), MAX_ITER, allreduce=cb2)
+                o2.close()
+            assert x_full.size == obj.P
+            return r2.evaluations
+
+        e2e_call(False)                      # warm: pinned staging buffers, NCCL channels for these sizes
+        n_e2e = max(1, min(args.steps, 3))
         barrier()
         t0 = time.perf_counter()
-        dev = torch.device("cuda", local_rank)
-        c2 = dd.sharded_counts(msa, SEQID, device=dev)
-        w2 = (1.0 / c2.astype(np.float32)).astype(np.float32)
-        t_rw = time.perf_counter()
-        if exchange == "peer":
-            sp2 = dd.ShardedPlm(msa, w2, Q, lam, lam)
-            t_mk = time.perf_counter()
-            _, r2 = sp2.fit(MAX_ITER)
-            t_fit = time.perf_counter()
-            x_full = sp2.gather()
-            t_ga = time.perf_counter()
-            sp2.close()
-            if rank == 0:
-                print("e2e stages ms: reweight %.1f setup %.1f %s fit %.1f gather %.1f close %.1f"
-                      % (1e3 * (t_rw - t0), 1e3 * (t_mk - t_rw), {k: round(v, 1) for k, v in sp2.trace.items()},
-                         1e3 * (t_fit - t_mk), 1e3 * (t_ga - t_fit), 1e3 * (time.perf_counter() - t_ga)), file=sys.stderr)
-        else:
-            o2 = _lib.PlmObjective(msa, w2, Q, lam, lam, sites=dd.shard_range(SEQ_LEN, rank, world))
-            cb2 = dd.make_allreduce_callback(o2.cuda_stream())
-            x_full, r2 = o2.fit(o2.init(), MAX_ITER, allreduce=cb2)
-            o2.close()
-        assert x_full.size == obj.P
+        e_evals = 0
+        for k in range(n_e2e):
+            e_evals += e2e_call(k == n_e2e - 1)
         barrier()
         e_wall = time.perf_counter() - t0
         t = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": r2.evaluations / float(t[0]), "unit": "evals/s",
+        e2e = {"value": e_evals / float(t[0]), "unit": "evals/s",
                "h2d_bytes_per_step": 2 * N_SEQ * SEQ_LEN + 4 * N_SEQ,
-               "d2h_bytes_per_step": 4 * N_SEQ + 4 * obj.P, "ms_per_step": 1e3 * float(t[0]), "steps": 1,
-               "call": "host MSA -> row-sharded reweight + all-reduce(counts) -> sharded create -> fit -> "
-                       "all-gather -> full x on the host, per rank"}
+               "d2h_bytes_per_step": 4 * N_SEQ + 4 * obj.P, "ms_per_step": 1e3 * float(t[0]) / n_e2e, "steps": n_e2e,
+               "call": "per rank: host MSA -> reweight (replicated below 1e11 compares, else row-sharded + "
+                       "all-reduce) -> sharded create + CUDA IPC wiring -> fit -> NCCL all-gather -> full x on the host"}
 
     if rank == 0:
         line = {"metric": "plmdca_grad_evals_per_sec", "value": evals / (dev_ms * 1e-3), "unit": "evals/s",

@@ -38,6 +38,8 @@ struct PlmProblem;   // device-resident state of one plmDCA objective
 
 // scalars every evaluation leaves on the device (double): see plm_eval.cu
 enum PlmScalar { PS_FX = 0, PS_DG = 1, PS_GG = 2, PS_XX = 3, PS_COUNT = 4 };
+// slot PS_COUNT holds the peer-timeout flag; slot PS_DGINIT the g.d of the direction the optimiser built last
+constexpr int PS_DGINIT = PS_COUNT + 1;
 
 PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
                        float lambda_h, float lambda_J, int site_lo, int site_hi);
@@ -63,7 +65,7 @@ void plm_set_carry(PlmProblem *p, int carry, int chunk, int warm);
 // p's scalar buffer; d_dir may be null (then PS_DG = 0).  No host sync.
 int plm_eval_device(PlmProblem *p, const float *d_x, float *d_g, const float *d_dir);
 // copy the PS_COUNT scalars to the host (one small D2H + stream sync)
-int plm_read_scalars(PlmProblem *p, double *out);
+int plm_read_scalars(PlmProblem *p, double *out, double *dginit = nullptr);
 // initial point (plmdca_numerics.cpp:207-249) written to device x
 int plm_init_x_device(PlmProblem *p, float *d_x);
 double *plm_scalar_buffer(PlmProblem *p);

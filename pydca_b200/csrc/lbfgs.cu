@@ -276,6 +276,7 @@ __device__ __forceinline__ void gram_recursion(const double *t, const HistPtrs &
             dg += -gamma * alpha[tt] * gs[GR_YG + j] + c[tt] * gs[GR_SG + j];
         }
         dscal[PS_DG] = dg;
+        dscal[PS_DGINIT] = dg;      // survives the next evaluation, which overwrites PS_DG
     }
     __syncthreads();
     for (int i = threadIdx.x; i < GR_DOUBLES; i += blockDim.x) gram[i] = gs[i];
@@ -584,12 +585,12 @@ struct Driver {
     }
 
     // objective at x -> g ; returns {fx, g.d, g.g, x.x} on the host
-    int evaluate(const float *dir, double *h)
+    int evaluate(const float *dir, double *h, double *dginit = nullptr)
     {
         ++evals;
         if (!allreduce) {
             if (plm_eval_device(p, x, g, dir) != 0) return -1;
-            return plm_read_scalars(p, h);
+            return plm_read_scalars(p, h, dginit);
         }
         if (plm_eval_device(p, x, g, nullptr) != 0) return -1;
         // the callback enqueues the collective in stream order behind the evaluation on the
@@ -599,7 +600,7 @@ struct Driver {
             return -1;
         }
         DCA_LAUNCH(vec_dots_kernel, blocks, VEC_THREADS, 0, st, g, dir, n, partial, sc, plm_scalar_buffer(p), ticket);
-        return plm_read_scalars(p, h);
+        return plm_read_scalars(p, h, dginit);
     }
 };
 
@@ -686,11 +687,11 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
     const long n = D.n;
     double *dsc = plm_scalar_buffer(p);
 
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evw = nullptr;
-    cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&evw);
     // sharded: start the clock on every rank at the same moment (the ranks reach this point
     // with a skew of their unequal H2D copies; without it the fastest rank's time includes it)
     if (plm_xr_barrier(p) != 0) { D.release(d_x); return -1; }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evw = nullptr;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&evw);
     cudaEventRecord(ev0, st);
     bool warm_marked = (warmup_iterations <= 0);
     int evals_at_warm = 0;
@@ -700,6 +701,7 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
     int k = 1, end = 0, ls = 0;
     double h[PS_COUNT];
     float fx = 0.f, xnorm = 0.f, gnorm = 0.f, step = 0.f, dginit = 0.f;
+    bool dginit_deferred = false;
     int rc = 0;
 
 #define LB_CHECK(expr) do { if ((expr) != 0) { rc = -1; goto done; } } while (0)
@@ -723,6 +725,10 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
         std::swap(D.g, D.gp);                                            // veccpy(gp,g) :466
 
         // ---- More-Thuente line search (:815-1004) on phi(t) = f(xp + t d) ----
+        // dginit (g.d of the direction just built on the device) is not read back before the first
+        // trial: nothing needs it until that trial's scalars are in, so it rides along in the same
+        // 48-byte D2H -- one host round trip per iteration less.  Should it turn out positive
+        // (:833-836 would have returned before evaluating) the trial is discarded and not counted.
         {
             int count = 0, brackt = 0, stage1 = 1, uinfo = 0;
             float dg = 0.f, f = fx;
@@ -730,10 +736,11 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
             float sty = 0.f, fy = fx, dgy = dginit;
             const float finit = fx;
             float stmin, stmax;
+            bool accepted = false;
             if (step <= 0.f) { ls = ST_INVALIDPARAMS; goto ls_done; }
-            if (0 < dginit) { ls = ST_INCREASEGRADIENT; goto ls_done; }
+            if (!dginit_deferred && 0 < dginit) { ls = ST_INCREASEGRADIENT; goto ls_done; }
             {
-                const float dgtest = prm.ftol * dginit;
+                float dgtest = prm.ftol * dginit;
                 float width = prm.max_step - prm.min_step;
                 float prev_width = 2.0 * width;
                 for (;;) {
@@ -746,18 +753,28 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
                         step = stx;
 
                     DCA_LAUNCH(vec_step_kernel, D.blocks, VEC_THREADS, 0, st, D.x, D.xp, D.d, step, n);
-                    LB_CHECK(D.evaluate(D.d, h));
+                    if (dginit_deferred) {
+                        double dgi = 0.0;
+                        LB_CHECK(D.evaluate(D.d, h, &dgi));
+                        dginit_deferred = false;
+                        dginit = (float)dgi;
+                        dgx = dginit; dgy = dginit;
+                        dgtest = prm.ftol * dginit;
+                        if (0 < dginit) { --D.evals; ls = ST_INCREASEGRADIENT; break; }
+                    } else {
+                        LB_CHECK(D.evaluate(D.d, h));
+                    }
                     f = (float)h[PS_FX];
                     dg = (float)h[PS_DG];
                     const float ftest1 = finit + step * dgtest;
                     ++count;
 
-                    if (brackt && ((step <= stmin || stmax <= step) || uinfo != 0)) { ls = ST_ROUNDING; break; }
-                    if (step == prm.max_step && f <= ftest1 && dg <= dgtest) { ls = ST_MAXSTEP; break; }
-                    if (step == prm.min_step && (ftest1 < f || dgtest <= dg)) { ls = ST_MINSTEP; break; }
-                    if (brackt && (stmax - stmin) <= prm.xtol * stmax) { ls = ST_WIDTHTOOSMALL; break; }
-                    if (prm.max_linesearch <= count) { ls = ST_MAXLINESEARCH; break; }
-                    if (f <= ftest1 && std::fabs(dg) <= prm.gtol * (-dginit)) { ls = count; break; }
+                    if (brackt && ((step <= stmin || stmax <= step) || uinfo != 0)) { ls = ST_ROUNDING; accepted = true; break; }
+                    if (step == prm.max_step && f <= ftest1 && dg <= dgtest) { ls = ST_MAXSTEP; accepted = true; break; }
+                    if (step == prm.min_step && (ftest1 < f || dgtest <= dg)) { ls = ST_MINSTEP; accepted = true; break; }
+                    if (brackt && (stmax - stmin) <= prm.xtol * stmax) { ls = ST_WIDTHTOOSMALL; accepted = true; break; }
+                    if (prm.max_linesearch <= count) { ls = ST_MAXLINESEARCH; accepted = true; break; }
+                    if (f <= ftest1 && std::fabs(dg) <= prm.gtol * (-dginit)) { ls = count; accepted = true; break; }
 
                     if (stage1 && f <= ftest1 && std::min(prm.ftol, prm.gtol) * dginit <= dg) stage1 = 0;
                     if (stage1 && ftest1 < f && f <= fxb) {
@@ -776,7 +793,7 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
                     }
                 }
             }
-            fx = f;
+            if (accepted) fx = f;        // every exit after an evaluation reports that trial's value (:622)
         ls_done:;
         }
         if (ls < 0) {                                                    // :478-484
@@ -816,11 +833,8 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
             ++k;
             end = (end + 1) % LB_M;
         }
-        {   // g.d of the new direction (needed by the line search, :845)
-            double hh[PS_COUNT];
-            LB_CHECK(plm_read_scalars(p, hh));
-            dginit = (float)hh[PS_DG];
-        }
+        dginit_deferred = true;      // g.d of the new direction (:845) is read with the first trial's scalars
+        dginit = 0.f;
         step = 1.0f;                                                     // :617
     }
 

@@ -1317,15 +1317,16 @@ void plm_describe(const PlmProblem *p, long *out)
 }
 
 // the PS_COUNT scalars plus the peer-timeout flag behind them: one small D2H + stream sync
-int plm_read_scalars(PlmProblem *p, double *out)
+int plm_read_scalars(PlmProblem *p, double *out, double *dginit)
 {
     // Ranks sharing one process (and one GPU) share its copy-engine queues: a D2H copy parked
     // behind my spinning barrier kernel would block the peer's H2D copies, i.e. the very work
     // the barrier waits for.  Drain the stream first in that (test-only) configuration.
     if (p->shared_process) DCA_CUDA(cudaStreamSynchronize(p->stream));
-    DCA_CUDA(cudaMemcpyAsync(p->h_scal, p->d_scal, sizeof(double) * (PS_COUNT + 1), cudaMemcpyDeviceToHost, p->stream));
+    DCA_CUDA(cudaMemcpyAsync(p->h_scal, p->d_scal, sizeof(double) * (PS_DGINIT + 1), cudaMemcpyDeviceToHost, p->stream));
     DCA_CUDA(cudaStreamSynchronize(p->stream));
     for (int k = 0; k < PS_COUNT; ++k) out[k] = p->h_scal[k];
+    if (dginit) *dginit = p->h_scal[PS_DGINIT];
     if (*reinterpret_cast<const unsigned *>(p->h_scal + PS_COUNT) != 0u) {
         set_error("plm: a peer GPU did not reach the exchange within %.0f s (rank %d of %d)",
                   XR_TIMEOUT_NS * 1e-9, p->peers.rank, p->peers.world);
