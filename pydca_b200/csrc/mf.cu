@@ -6,12 +6,10 @@
 //   construct_corr_mat        :271-318   compute_couplings         :322-342
 //
 // 1. pair frequencies.  F[(j,b)][(i,a)] = sum_n w_n [s_nj==b][s_ni==a] in
-//    float64 -- the same "bucketed gather" as the plmDCA scatter kernel: the
-//    weighted one-hot rows of a 128-sequence chunk are generated in shared
-//    memory from the u8 MSA (never materialised in HBM), one warp per site j
-//    walks the chunk in residue-bucket order and keeps q double2 accumulators
-//    per lane: no atomics, fixed summation order.  The diagonal blocks of F are
-//    the single-site counts (F[(i,a)][(i,a)] = sum_n w_n [s_ni==a]).
+//    float64 as weighted histograms over per-site residue buckets (see
+//    mf_pairhist_kernel): N*L*L/32 warp steps instead of the N*L*L*q adds of a
+//    dense one-hot product; no atomics, sequential summation order.  The
+//    diagonal of F holds the single-site counts (F[(i,a)][(i,a)] = sum_n w_n [s_ni==a]).
 // 2. pseudocount + covariance assembly fused in one pass over F.
 // 3. couplings = -C^{-1}: blocked Gauss-Jordan inversion without pivoting (C is
 //    symmetric positive definite by construction when pseudocount > 0), block
@@ -27,127 +25,105 @@
 
 namespace dca {
 
-// perm records are shared with plm_eval.cu's scatter (same layout)
-constexpr int MF_CH = 128;
-constexpr int MF_TC = 64;          // columns per CTA: 32 lanes x double2
-constexpr int MF_WARPS = 16;
-constexpr int MF_PERM_CNT = 32;
-constexpr int MF_PERM_REC = 224;
+constexpr int MF_TC = 64;          // F row padding (columns)
+constexpr int MF_HW = 8;           // warps per CTA of the histogram kernel
 
+// Per site: the row indices of the alignment grouped by residue, ascending n inside a group
+// (stable counting sort), plus the q+1 group offsets.  One warp per site.
 template <int Q>
-__global__ void mf_build_perm_kernel(const uint8_t *__restrict__ msa, long N, int L, int nchunk,
-                                     uint8_t *__restrict__ perm)
+__global__ void __launch_bounds__(128)
+mf_site_buckets_kernel(const uint8_t *__restrict__ msa, long N, int L, unsigned *__restrict__ rows,
+                       unsigned *__restrict__ off)
 {
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long)L * nchunk) return;
-    const int j = (int)(idx / nchunk);
-    const int c = (int)(idx - (long)j * nchunk);
-    const long n0 = (long)c * MF_CH;
-    const int rows = (int)min((long)MF_CH, N - n0);
-    uint8_t *rec = perm + idx * MF_PERM_REC;
-    int cnt[Q], pos[Q];
-#pragma unroll
-    for (int b = 0; b < Q; ++b) cnt[b] = 0;
-    for (int r = 0; r < rows; ++r) {
-        const int v = msa[(n0 + r) * L + j];
-#pragma unroll
-        for (int b = 0; b < Q; ++b) cnt[b] += (v == b);
+    __shared__ unsigned cnt[4][Q + 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * 4 + wib;
+    if (i >= L) return;
+    if (lane <= Q) cnt[wib][lane] = 0;
+    __syncwarp();
+    for (long n = lane; n < N; n += 32) atomicAdd(&cnt[wib][msa[n * L + i]], 1u);
+    __syncwarp();
+    if (lane == 0) {
+        unsigned run = 0;
+        for (int b = 0; b < Q; ++b) { const unsigned c = cnt[wib][b]; cnt[wib][b] = run; off[(size_t)i * (Q + 1) + b] = run; run += c; }
+        off[(size_t)i * (Q + 1) + Q] = run;
     }
-    int off = 0;
-#pragma unroll
-    for (int b = 0; b < Q; ++b) { rec[b] = (uint8_t)cnt[b]; pos[b] = off; off += (cnt[b] + 3) & ~3; }
-    for (int r = 0; r < rows; ++r) {
-        const int v = msa[(n0 + r) * L + j];
-        int where = 0;
-#pragma unroll
-        for (int b = 0; b < Q; ++b)
-            if (v == b) { where = pos[b]; pos[b] = where + 1; }
-        rec[MF_PERM_CNT + where] = (uint8_t)r;
+    __syncwarp();
+    const unsigned lt = (1u << lane) - 1u;
+    for (long n0 = 0; n0 < N; n0 += 32) {
+        const long n = n0 + lane;
+        const bool valid = n < N;
+        const unsigned r = valid ? msa[n * L + i] : (unsigned)Q;
+        const unsigned peers = __match_any_sync(0xffffffffu, r);
+        const unsigned base = cnt[wib][r];
+        __syncwarp();
+        if (valid) {
+            rows[(size_t)i * N + base + __popc(peers & lt)] = (unsigned)n;
+            if ((peers & lt) == 0u) cnt[wib][r] = base + __popc(peers);     // lowest lane of the group
+        }
+        __syncwarp();
     }
 }
 
+// Pair counts as weighted histograms.  F[(j,b)][(i,a)] = sum_n w_n [s_ni = a][s_nj = b] has only
+// N non-zero terms per (i,j) -- one per sequence -- so instead of multiplying dense one-hot
+// rows (N*L*L*q adds: 3.8e10 at N = 20000, L = 300; the first version, 18 ms) a warp takes
+// (site i, residue a, 32 consecutive sites j), walks the rows of bucket (i,a) in ascending n and
+// adds w_n into bins[s_nj][lane]: N*L*L/32 warp steps (6e7), every step one coalesced 32-byte
+// read of the MSA row.  The bins live in shared memory ([q][32] doubles per warp, lane-interleaved:
+// conflict-free for any residues); each bin is owned by one lane: no atomics, and the order of the
+// additions is the sequential order of the reference's loop (msa_numerics.py:54-89, :183-229).
+// Only tiles holding some j >= i are computed (the consumers read the canonical i <= j entries).
 template <int Q>
-__global__ void __launch_bounds__(MF_WARPS * 32, 1)
-mf_pairfreq_kernel(const uint8_t *__restrict__ msa, const double *__restrict__ w,
-                   const uint8_t *__restrict__ perm, int nchunk, long N, int L, int ld,
-                   double *__restrict__ F, size_t f_split_stride, int chunks_per_split)
+__global__ void __launch_bounds__(MF_HW * 32)
+mf_pairhist_kernel(const uint8_t *__restrict__ msa, const double *__restrict__ w,
+                   const unsigned *__restrict__ rows, const unsigned *__restrict__ off,
+                   long N, int L, int ld, double *__restrict__ F)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *Rs = reinterpret_cast<double *>(smem_raw);                                   // [2][MF_CH][MF_TC]
-    uint8_t *recs = smem_raw + sizeof(double) * 2 * MF_CH * MF_TC;                       // [2][MF_WARPS][REC]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int col0 = blockIdx.x * MF_TC;
-    const int j = blockIdx.y * MF_WARPS + warp;
-    const int c0 = blockIdx.z * chunks_per_split;
-    const int c1 = min(nchunk, c0 + chunks_per_split);
-    const int Lq = L * Q;
-
-    double2 acc[Q];
+    __shared__ double bins[MF_HW][Q][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.y;
+    const int njt = (L + 31) / 32;
+    const int item = blockIdx.x * MF_HW + wib;
+    if (item >= Q * njt) return;
+    const int a = item / njt, jt = item - a * njt;
+    const int j0 = jt * 32;
+    if (j0 + 31 < i) return;
+    const int j = j0 + lane;
+    const bool jok = j < L;
 #pragma unroll
-    for (int b = 0; b < Q; ++b) acc[b] = make_double2(0.0, 0.0);
-
-    // this thread's two columns are fixed: precompute (site, state)
-    const int cA = col0 + 2 * lane, cB = cA + 1;
-    const int iA = cA / Q, aA = cA - iA * Q, iB = cB / Q, aB = cB - iB * Q;
-    const bool okA = cA < Lq, okB = cB < Lq;
-
-    auto gen = [&](int buf, int c) {
-        double *dst = Rs + (size_t)buf * MF_CH * MF_TC;
-        const long nb = (long)c * MF_CH;
-        const int rows = (int)min((long)MF_CH, N - nb);
-        for (int row = warp; row < rows; row += MF_WARPS) {
-            const long n = nb + row;
-            const double wn = w[n];
-            double2 v;
-            v.x = (okA && msa[n * L + iA] == aA) ? wn : 0.0;
-            v.y = (okB && msa[n * L + iB] == aB) ? wn : 0.0;
-            *reinterpret_cast<double2 *>(dst + row * MF_TC + 2 * lane) = v;
-        }
-        if (j < L && lane < MF_PERM_REC / 16)
-            *reinterpret_cast<uint4 *>(recs + ((size_t)buf * MF_WARPS + warp) * MF_PERM_REC + 16 * lane) =
-                *reinterpret_cast<const uint4 *>(perm + ((size_t)j * nchunk + c) * MF_PERM_REC + 16 * lane);
-    };
-
-    if (c0 < c1) gen(0, c0);
-    __syncthreads();
-    for (int c = c0; c < c1; ++c) {
-        const int buf = (c - c0) & 1;
-        if (c + 1 < c1) gen(buf ^ 1, c + 1);
-        if (j < L) {
-            const uint8_t *rec = recs + ((size_t)buf * MF_WARPS + warp) * MF_PERM_REC;
-            const uint32_t *pw = reinterpret_cast<const uint32_t *>(rec + MF_PERM_CNT);
-            const double *Rb = Rs + (size_t)buf * MF_CH * MF_TC + 2 * lane;
-            uint32_t cur = pw[0];
-            int pos = 0;
+    for (int b = 0; b < Q; ++b) bins[wib][b][lane] = 0.0;
+    const unsigned beg = off[(size_t)i * (Q + 1) + a], end = off[(size_t)i * (Q + 1) + a + 1];
+    const unsigned *ri = rows + (size_t)i * N;
+    for (unsigned k = beg; k < end; k += 32) {
+        const unsigned cntk = min(32u, end - k);
+        unsigned nk = 0;
+        double wk = 0.0;
+        if (lane < cntk) { nk = ri[k + lane]; wk = w[nk]; }
+        unsigned t = 0;
+        for (; t + 4 <= cntk; t += 4) {            // four MSA reads in flight, then the four updates
+            unsigned n4[4], b4[4];
+            double w4[4];
 #pragma unroll
-            for (int b = 0; b < Q; ++b) {
-                const unsigned m = rec[b];
-                double2 a = acc[b];
-                const unsigned nq = (m + 3u) >> 2;
-                // compact, not unrolled: 21 copies must fit the instruction cache (see plm_scatter_kernel)
-#pragma unroll 1
-                for (unsigned t = 0; t < nq; ++t) {
-                    const uint32_t w4 = cur;
-                    cur = pw[++pos];
-                    const unsigned rem = m - 4u * t;
-                    const double2 z2 = make_double2(0.0, 0.0);
-                    const double2 v0 = *reinterpret_cast<const double2 *>(Rb + (w4 & 0xffu) * MF_TC);
-                    const double2 v1 = (rem > 1u) ? *reinterpret_cast<const double2 *>(Rb + ((w4 >> 8) & 0xffu) * MF_TC) : z2;
-                    const double2 v2 = (rem > 2u) ? *reinterpret_cast<const double2 *>(Rb + ((w4 >> 16) & 0xffu) * MF_TC) : z2;
-                    const double2 v3 = (rem > 3u) ? *reinterpret_cast<const double2 *>(Rb + (w4 >> 24) * MF_TC) : z2;
-                    a.x += (v0.x + v1.x) + (v2.x + v3.x);
-                    a.y += (v0.y + v1.y) + (v2.y + v3.y);
-                }
-                acc[b] = a;
+            for (int u = 0; u < 4; ++u) {
+                n4[u] = __shfl_sync(0xffffffffu, nk, t + u);
+                w4[u] = __shfl_sync(0xffffffffu, wk, t + u);
+                b4[u] = jok ? msa[(size_t)n4[u] * L + j] : 0u;
             }
-        }
-        __syncthreads();
-    }
-    if (j < L) {
-        double *f = F + (size_t)blockIdx.z * f_split_stride + (size_t)j * Q * ld + col0 + 2 * lane;
 #pragma unroll
-        for (int b = 0; b < Q; ++b) *reinterpret_cast<double2 *>(f + (size_t)b * ld) = acc[b];
+            for (int u = 0; u < 4; ++u) bins[wib][b4[u]][lane] += w4[u];
+        }
+        for (; t < cntk; ++t) {
+            const unsigned n = __shfl_sync(0xffffffffu, nk, t);
+            const double wv = __shfl_sync(0xffffffffu, wk, t);
+            const unsigned b = jok ? msa[(size_t)n * L + j] : 0u;
+            bins[wib][b][lane] += wv;
+        }
+    }
+    if (jok) {
+        double *f = F + ((size_t)j * Q) * ld + (size_t)i * Q + a;
+#pragma unroll
+        for (int b = 0; b < Q; ++b) f[(size_t)b * ld] = bins[wib][b][lane];
     }
 }
 
@@ -430,25 +406,22 @@ static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
 
 // ------------------------------------------------------------------------------
 struct MfWork {
-    uint8_t *d_msa = nullptr, *d_perm = nullptr;
+    uint8_t *d_msa = nullptr;
+    unsigned *d_rows = nullptr, *d_off = nullptr;     // per site: rows grouped by residue, group offsets
     double *d_w = nullptr, *d_F = nullptr, *d_fi = nullptr, *d_rfi = nullptr;
-    int ld = 0, nsplit = 1, cps = 0, nchunk = 0;
+    int ld = 0, nsplit = 1;                           // one copy of F (the consumers' nsplit argument)
     size_t fstride = 0;
     double meff = 0.0;
-    ~MfWork() { cudaDeviceSynchronize(); dev_free(d_msa); dev_free(d_perm); dev_free(d_w); dev_free(d_F); dev_free(d_fi); dev_free(d_rfi); }
+    ~MfWork() { cudaDeviceSynchronize(); dev_free(d_msa); dev_free(d_rows); dev_free(d_off); dev_free(d_w); dev_free(d_F); dev_free(d_fi); dev_free(d_rfi); }
 };
 
 template <int Q>
 static int mf_pairfreq_t(MfWork &W, long N, int L)
 {
-    const long total = (long)L * W.nchunk;
-    DCA_CUDA(cudaMemset(W.d_perm, 0, (size_t)total * MF_PERM_REC));
-    DCA_LAUNCH((mf_build_perm_kernel<Q>), (unsigned)ceil_div<long>(total, 128), 128, 0, 0, W.d_msa, N, L, W.nchunk, W.d_perm);
-    const size_t smem = sizeof(double) * 2 * MF_CH * MF_TC + 2 * MF_WARPS * MF_PERM_REC + 16;   // +16: prefetched word
-    DCA_CUDA(cudaFuncSetAttribute(mf_pairfreq_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(W.ld / MF_TC, ceil_div(L, MF_WARPS), W.nsplit);
-    DCA_LAUNCH((mf_pairfreq_kernel<Q>), grid, MF_WARPS * 32, smem, 0,
-               W.d_msa, W.d_w, W.d_perm, W.nchunk, N, L, W.ld, W.d_F, W.fstride, W.cps);
+    DCA_LAUNCH((mf_site_buckets_kernel<Q>), ceil_div(L, 4), 128, 0, 0, W.d_msa, N, L, W.d_rows, W.d_off);
+    const int njt = ceil_div(L, 32);
+    dim3 grid(ceil_div(Q * njt, MF_HW), L);
+    DCA_LAUNCH((mf_pairhist_kernel<Q>), grid, MF_HW * 32, 0, 0, W.d_msa, W.d_w, W.d_rows, W.d_off, N, L, W.ld, W.d_F);
     DCA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -462,18 +435,13 @@ static int mf_prepare(MfWork &W, const uint8_t *msa, const double *w, long N, in
         if (msa[k] >= q) { set_error("mf: residue code %d >= q=%d at flat index %ld", msa[k], q, k); return -1; }
     const int Lq = L * q;
     W.ld = ceil_div(Lq, MF_TC) * MF_TC;
-    W.nchunk = (int)ceil_div<long>(N, MF_CH);
-    const long tiles = (long)(W.ld / MF_TC) * ceil_div(L, MF_WARPS);
-    int want = (int)ceil_div<long>(3L * sm_count(), std::max(1L, tiles));
-    W.nsplit = std::max(1, std::min(want, std::max(1, W.nchunk / 8)));
-    W.cps = ceil_div(W.nchunk, W.nsplit);
-    W.nsplit = ceil_div(W.nchunk, W.cps);
+    W.nsplit = 1;
     W.fstride = (size_t)Lq * W.ld;
     double m = 0.0;
     for (long n = 0; n < N; ++n) m += w[n];
     W.meff = m;
     if (!dev_alloc_t(&W.d_msa, (size_t)N * L) || !dev_alloc_t(&W.d_w, (size_t)N) ||
-        !dev_alloc_t(&W.d_perm, (size_t)L * W.nchunk * MF_PERM_REC) ||
+        !dev_alloc_t(&W.d_rows, (size_t)L * N) || !dev_alloc_t(&W.d_off, (size_t)L * (q + 1)) ||
         !dev_alloc_t(&W.d_F, W.fstride * W.nsplit) || !dev_alloc_t(&W.d_fi, (size_t)Lq) ||
         !dev_alloc_t(&W.d_rfi, (size_t)Lq))
         return -1;

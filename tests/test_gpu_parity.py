@@ -191,6 +191,25 @@ def test_plm_eval_site_shards_sum_to_full(port):
         p.close()
 
 
+def test_plm_eval_config2_full_size_vs_oracle(port):
+    """BASELINE config 2 at full size (N=5000, L=150, q=21, P = 4.9 M): the bench workload itself,
+    every gradient entry against the serial float32 oracle and fx against the float64 one."""
+    from pydca_b200.synthetic import synthetic_msa
+    N, L, q = 5000, 150, 21
+    msa = synthetic_msa(N, L, q)
+    w = (1.0 / lib().sequence_counts(msa, 0.8).astype(np.float32)).astype(np.float32)
+    lam = 0.2 * (L - 1)
+    obj = lib().PlmObjective(msa, w, q, lam, lam)
+    x = (obj.init() + np.random.default_rng(2).normal(0, 0.05, obj.P)).astype(np.float32)
+    fx, g = obj.eval(x)
+    port.set_num_threads(8)
+    fo, go = port.plm_gradient(msa, w, q, lam, lam, x)
+    f64, g64 = port.plm_gradient_f64(msa, w, q, lam, lam, x)
+    assert relmax(g, go) <= 1e-5 and relmax(g, g64) <= 1e-5
+    assert abs(fx - f64) <= 1e-5 * abs(f64)
+    obj.close()
+
+
 def test_plm_eval_linearity_property_config2():
     """BASELINE config 2 size (N=5000, L=150, q=21): the data term's gradient rows sum
     to zero over states (sum_a dh_i(a) = 2*lambda*sum_a h_i(a) since sum_a (p - delta) = 0),
