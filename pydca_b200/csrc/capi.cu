@@ -80,16 +80,20 @@ using namespace dca;
 struct dca_plm {
     PlmProblem *prob;
     float *d_x, *d_g;                       // whole vector, or the local slice of a sharded objective
-    void *ipc_opened[XR_MAX_RANKS];         // peer arenas this process opened through CUDA IPC
 };
 
 static thread_local dca_fit_result t_last_fit = {};
+
+// peer arenas opened through CUDA IPC stay mapped for the life of the process, keyed by handle:
+// the owners recycle their arenas (plm_eval.cu), and re-opening costs ~1.5 ms per peer
+static std::mutex g_ipc_mu;
+static std::vector<std::pair<std::string, void *>> g_ipc_open;
 
 extern "C" void dca_plm_destroy(dca_plm *p);
 
 static dca_plm *wrap_problem(PlmProblem *prob)
 {
-    dca_plm *h = new (std::nothrow) dca_plm{prob, nullptr, nullptr, {nullptr}};
+    dca_plm *h = new (std::nothrow) dca_plm{prob, nullptr, nullptr};
     if (!h) { plm_destroy(prob); set_error("out of memory"); return nullptr; }
     const size_t bytes = sizeof(float) * (size_t)plm_local_params(prob);
     h->d_x = static_cast<float *>(dev_alloc(bytes));
@@ -228,15 +232,22 @@ int dca_plm_connect_ipc(dca_plm *p, const unsigned char *handles, int world)
     DCA_CUDA(cudaIpcGetMemHandle(&mine, own));
     for (int r = 0; r < world; ++r) {
         if (memcmp(handles + 64 * r, &mine, 64) == 0) { ptrs[r] = own; continue; }
+        const std::string key(reinterpret_cast<const char *>(handles + 64 * r), 64);
+        {
+            std::lock_guard<std::mutex> lk(g_ipc_mu);
+            for (auto &kv : g_ipc_open) if (kv.first == key) ptrs[r] = kv.second;
+        }
+        if (ptrs[r]) continue;
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + 64 * r, 64);
         cudaError_t e = cudaIpcOpenMemHandle(&ptrs[r], h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             set_error("cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
-            for (int k = 0; k < r; ++k) if (p->ipc_opened[k]) { cudaIpcCloseMemHandle(p->ipc_opened[k]); p->ipc_opened[k] = nullptr; }
+            cudaGetLastError();
             return -1;
         }
-        p->ipc_opened[r] = ptrs[r];
+        std::lock_guard<std::mutex> lk(g_ipc_mu);
+        g_ipc_open.emplace_back(key, ptrs[r]);
     }
     return plm_connect(p->prob, ptrs, false);
 }
@@ -244,9 +255,7 @@ int dca_plm_connect_ipc(dca_plm *p, const unsigned char *handles, int world)
 int dca_plm_disconnect(dca_plm *p)
 {
     if (!p) { set_error("null handle"); return -1; }
-    plm_disconnect(p->prob);
-    for (int r = 0; r < XR_MAX_RANKS; ++r)
-        if (p->ipc_opened[r]) { cudaIpcCloseMemHandle(p->ipc_opened[r]); p->ipc_opened[r] = nullptr; }
+    plm_disconnect(p->prob);          // forget the peers; their mappings stay cached (see g_ipc_open)
     return 0;
 }
 
