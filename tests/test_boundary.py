@@ -105,6 +105,32 @@ def test_fasta_reader_semantics(tmp_path, port):
     assert rna.tolist() == [[0, 1, 2, 3, 4, 4, 4]]
 
 
+def test_fasta_reader_line_endings_whitespace_and_many_duplicates(tmp_path, port):
+    """The single-pass reader (csrc/fasta.cpp): CRLF files, blanks/tabs inside a line, no
+    trailing newline, residues beyond seqs_len ignored, a headerless file is one record, and
+    hash-then-verify dedup keeps first occurrences in file order on a duplicate-heavy file."""
+    from pydca_b200 import _lib
+    p = tmp_path / "crlf.fa"
+    p.write_bytes(b">a\r\nAC DE\tF\r\n>b\r\nACDEFGG\r\n>c\r\nWWWWW")        # b: 2 extra residues; c: no newline
+    msa = _lib.read_fasta(str(p), "protein", 5)
+    assert msa.tolist() == [[0, 1, 2, 3, 4], [18, 18, 18, 18, 18]]           # b duplicates a after truncation
+    h = tmp_path / "headerless.fa"
+    h.write_text("ACD\nEF\n")
+    assert _lib.read_fasta(str(h), "protein", 5).tolist() == [[0, 1, 2, 3, 4]]
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 21, size=(40, 17), dtype=np.uint8)
+    order = rng.integers(0, 40, size=3000)
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY-", dtype=np.uint8)
+    d = tmp_path / "dups.fa"
+    with open(d, "wb") as f:
+        for k, r in enumerate(order):
+            f.write(b">s%d\n" % k + letters[base[r]].tobytes() + b"\n")
+    got = _lib.read_fasta(str(d), "protein", 17)
+    first = list(dict.fromkeys(order.tolist()))
+    assert got.shape == (len(first), 17) and (got == base[first]).all()
+    assert (got == port.read_fasta(str(d), "protein", 17)).all()
+
+
 def test_fasta_reader_errors(tmp_path):
     from pydca_b200 import _lib
     with pytest.raises(_lib.DcaBackendError, match="Unable to open"):

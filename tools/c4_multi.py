@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""BASELINE config 4 (plmdca N=50k, L=500, q=21) site-sharded over the GPUs of one box.
+"""BASELINE config 4 (plmdca N=50k, L=500, q=21) owner-sharded over the GPUs of one box
+(DCA_B200_EXCHANGE=allreduce: the older replicated-x + NCCL all-reduce path).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 \
         --master-port 29533 tools/c4_multi.py [N L iters]
@@ -40,18 +41,32 @@ def main():
     dist.barrier()
     t_rw = time.perf_counter() - t
     w = (1.0 / counts.astype(np.float32)).astype(np.float32)
-    sites = dd.shard_range(L, rank, world)
     lam = 0.2 * (L - 1)
-    obj = _lib.PlmObjective(msa, w, q, lam, lam, sites=sites)
-    x0 = obj.init()
-    ms = obj.eval_timed(x0)
-    ms = obj.eval_timed(x0)
-    cb = dd.make_allreduce_callback(obj.cuda_stream())
-    dist.barrier()
-    t = time.perf_counter()
-    x, res = obj.fit(x0, iters, allreduce=cb)
-    dist.barrier()
-    dt = time.perf_counter() - t
+    peer = os.environ.get("DCA_B200_EXCHANGE", "peer") == "peer"
+    if peer:
+        sp = dd.ShardedPlm(msa, w, q, lam, lam)
+        obj, sites = sp.obj, (sp.bounds[rank], sp.bounds[rank + 1])
+        x0 = obj.init()
+        ms = obj.eval_timed(x0)
+        ms = obj.eval_timed(x0)
+        dist.barrier()
+        t = time.perf_counter()
+        _, res = sp.fit(iters)
+        dist.barrier()
+        dt = time.perf_counter() - t
+        x = sp.gather()
+    else:
+        sites = dd.shard_range(L, rank, world)
+        obj = _lib.PlmObjective(msa, w, q, lam, lam, sites=sites)
+        x0 = obj.init()
+        ms = obj.eval_timed(x0)
+        ms = obj.eval_timed(x0)
+        cb = dd.make_allreduce_callback(obj.cuda_stream())
+        dist.barrier()
+        t = time.perf_counter()
+        x, res = obj.fit(x0, iters, allreduce=cb)
+        dist.barrier()
+        dt = time.perf_counter() - t
     tt = torch.tensor([res.device_ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     if rank == 0:
@@ -63,7 +78,10 @@ def main():
         order = np.argsort(-apc, kind="stable")[:5]
         iu, ju = np.triu_indices(L, k=1)
         print("   FN-APC top5:", [(int(iu[k]), int(ju[k]), round(float(apc[k]), 5)) for k in order], "finite:", bool(np.isfinite(x).all()))
-    obj.close()
+    if peer:
+        sp.close()
+    else:
+        obj.close()
     dist.destroy_process_group()
 
 
