@@ -208,9 +208,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 __global__ void __launch_bounds__(256, 1)
 dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, int lda,
                 const double *__restrict__ B, int ldb, double alpha, double beta, int skip_rb,
-                int skip_tr, int skip_tc)
+                int skip_tr, int skip_tc, int lower_only)
 {
     if ((int)blockIdx.y == skip_rb) return;
+    if (lower_only && blockIdx.x > blockIdx.y) return;          // symmetric sweep: tiles (i, j <= i) only
     if ((int)blockIdx.y == skip_tr && (int)blockIdx.x == skip_tc) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *As = reinterpret_cast<double *>(smem_raw);                 // [2][128][GM_AS]
@@ -278,59 +279,124 @@ dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, i
         }
 }
 
-// in-place inverse of one 128x128 diagonal block (unblocked Gauss-Jordan, no pivoting)
+// inverse of one 128x128 diagonal block (unblocked Gauss-Jordan, no pivoting), one CTA.
+// The block lives in REGISTERS: thread (tr, tc) = (warp, lane) owns the 8 x 4 patch rows tr*8.., cols
+// tc*4..; per pivot the owners publish the old pivot row and column through two small shared arrays
+// (double-buffered: one barrier per pivot) and every thread updates its patch from 4 + 8 values.
+// The first version kept the block in shared memory and moved 2 x 128 KB through it per pivot
+// (0.33 ms per block); with the symmetric update halving the GEMM time that single-CTA kernel had
+// become the critical path of the whole inverse.
 __global__ void __launch_bounds__(512, 1)
 gj_diag_inv_kernel(const double *__restrict__ A, int ld, int k, double *__restrict__ Dinv, int *__restrict__ info)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *S = reinterpret_cast<double *>(smem_raw);          // [128][129]
-    double *colp = S + GJ_B * (GJ_B + 1);                      // [128]
-    __shared__ double piv_s;
-    const int tid = threadIdx.x;
+    __shared__ double prow[2][GJ_B], pcol[2][GJ_B];
+    const int tid = threadIdx.x, tr = tid >> 5, tc = tid & 31;
     const double *Ak = A + (size_t)k * GJ_B * ld + (size_t)k * GJ_B;
-    for (int t = tid; t < GJ_B * GJ_B; t += 512) {
-        const int r = t >> 7, c = t & 127;
-        S[r * (GJ_B + 1) + c] = Ak[(size_t)r * ld + c];
+    double a[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double2 lo = *reinterpret_cast<const double2 *>(Ak + (size_t)(tr * 8 + i) * ld + tc * 4);
+        const double2 hi = *reinterpret_cast<const double2 *>(Ak + (size_t)(tr * 8 + i) * ld + tc * 4 + 2);
+        a[i][0] = lo.x; a[i][1] = lo.y; a[i][2] = hi.x; a[i][3] = hi.y;
     }
-    __syncthreads();
     for (int p = 0; p < GJ_B; ++p) {
-        if (tid < GJ_B) colp[tid] = S[tid * (GJ_B + 1) + p];
-        if (tid == 0) {
-            const double d = S[p * (GJ_B + 1) + p];
-            if (!(fabs(d) > 0.0) && info) *info = k * GJ_B + p + 1;
-            piv_s = 1.0 / d;
+        const int buf = p & 1;
+        if (tr == (p >> 3)) {                          // my warp owns pivot row p (register row p & 7)
+            const int i0 = p & 7;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double v = a[0][j];
+#pragma unroll
+                for (int i = 1; i < 8; ++i) v = (i0 == i) ? a[i][j] : v;
+                prow[buf][tc * 4 + j] = v;
+            }
+        }
+        if (tc == (p >> 2)) {                          // my lane owns pivot column p (register column p & 3)
+            const int j0 = p & 3;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double v = a[i][0];
+#pragma unroll
+                for (int j = 1; j < 4; ++j) v = (j0 == j) ? a[i][j] : v;
+                pcol[buf][tr * 8 + i] = v;
+            }
         }
         __syncthreads();
-        const double piv = piv_s;
-        if (tid < GJ_B) {                                      // scale pivot row
-            const int c = tid;
-            S[p * (GJ_B + 1) + c] = (c == p) ? piv : S[p * (GJ_B + 1) + c] * piv;
+        const double d = prow[buf][p];
+        if (tid == 0 && !(fabs(d) > 0.0) && info) *info = k * GJ_B + p + 1;
+        const double piv = 1.0 / d;
+        double rowv[4], colv[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rowv[j] = prow[buf][tc * 4 + j] * piv;      // scaled pivot row
+#pragma unroll
+        for (int i = 0; i < 8; ++i) colv[i] = pcol[buf][tr * 8 + i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool rp = (tr * 8 + i == p);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool cp = (tc * 4 + j == p);
+                double v;
+                if (rp) v = cp ? piv : rowv[j];
+                else v = cp ? (-colv[i] * piv) : (a[i][j] - colv[i] * rowv[j]);
+                a[i][j] = v;
+            }
         }
-        __syncthreads();
-        for (int t = tid; t < GJ_B * GJ_B; t += 512) {
-            const int r = t >> 7, c = t & 127;
-            if (r == p) continue;
-            const double f = colp[r];
-            if (c == p) S[r * (GJ_B + 1) + c] = -f * piv;
-            else S[r * (GJ_B + 1) + c] -= f * S[p * (GJ_B + 1) + c];
-        }
-        __syncthreads();
     }
-    for (int t = tid; t < GJ_B * GJ_B; t += 512) {
-        const int r = t >> 7, c = t & 127;
-        Dinv[(size_t)r * GJ_B + c] = S[r * (GJ_B + 1) + c];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double *o = Dinv + (size_t)(tr * 8 + i) * GJ_B + tc * 4;
+        *reinterpret_cast<double2 *>(o) = make_double2(a[i][0], a[i][1]);
+        *reinterpret_cast<double2 *>(o + 2) = make_double2(a[i][2], a[i][3]);
     }
 }
 
-// Ck = A[:, kblock] ; A[:, kblock] = 0 except the diagonal block = I
-__global__ void gj_split_col_kernel(double *__restrict__ A, int ld, int npad, int k, double *__restrict__ Ck)
+// Symmetric Gauss-Jordan keeps only the tiles (i, j <= i).  For an SPD matrix the intermediates
+// obey, with K the pivoted and U the unpivoted block indices,  B_KK and B_UU symmetric and
+// B_KU = -B_UK^T, so every tile above the diagonal is (+/-) the transpose of one below it.
+// This kernel assembles what step k needs from the lower tiles:
+//   Ck   [npad][128]  = column block k:   rows i >= k direct, rows i < k = -tile(k,i)^T
+//   Arow [128][npad]  = row block k:      cols j < k direct, j = k the identity, j > k = tile(j,k)^T
+// and then resets the lower part of column block k to the unit columns, as the unsymmetric
+// algorithm does.  Every element it overwrites is read by the overwriting thread only.
+__global__ void gj_gather_kernel(double *__restrict__ A, int ld, int npad, int k, double *__restrict__ Ck,
+                                 double *__restrict__ Arow)
 {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)npad * GJ_B) return;
     const int r = (int)(idx >> 7), c = (int)(idx & 127);
-    double *p = A + (size_t)r * ld + (size_t)k * GJ_B + c;
-    Ck[idx] = *p;
-    *p = (r == k * GJ_B + c) ? 1.0 : 0.0;
+    const int kb = k * GJ_B;
+    if (r >= kb) {
+        double *p = A + (size_t)r * ld + kb + c;
+        const double v = *p;
+        Ck[idx] = v;
+        const bool diag_tile = r < kb + GJ_B;
+        Arow[(size_t)c * npad + r] = diag_tile ? ((r == kb + c) ? 1.0 : 0.0) : v;
+        *p = (r == kb + c) ? 1.0 : 0.0;
+    } else {
+        const double v = A[(size_t)(kb + c) * ld + r];
+        Ck[idx] = -v;
+        Arow[(size_t)c * npad + r] = v;
+    }
+}
+
+// after the last step every index is pivoted and the matrix is symmetric: fill the upper tiles
+__global__ void gj_mirror_kernel(double *__restrict__ A, int ld, int npad)
+{
+    __shared__ double t[32][33];
+    const int bx = blockIdx.x, by = blockIdx.y;              // 32 x 32 element tiles
+    if (bx <= by) {
+        if (bx < by) return;
+        // diagonal 32-tile: mirror inside the tile
+    }
+    const int x = threadIdx.x, y = threadIdx.y;              // 32 x 8 threads
+    // source tile (row block bx, col block by) lies below the diagonal (bx > by), or is the diagonal one
+    for (int yy = y; yy < 32; yy += 8) t[yy][x] = A[(size_t)(bx * 32 + yy) * ld + by * 32 + x];
+    __syncthreads();
+    for (int yy = y; yy < 32; yy += 8) {
+        const int row = by * 32 + yy, col = bx * 32 + x;     // transposed destination
+        if (col > row) A[(size_t)row * ld + col] = t[x][yy];
+    }
 }
 
 __global__ void negate_copy_kernel(const double *__restrict__ A, int ld, int n, double *__restrict__ out)
@@ -341,18 +407,19 @@ __global__ void negate_copy_kernel(const double *__restrict__ A, int ld, int n, 
     out[idx] = -1.0 * A[(size_t)r * ld + c];
 }
 
-// d_A: npad x npad (row-major, ld = npad), overwritten by its inverse
+// d_A: npad x npad (row-major, ld = npad), SYMMETRIC positive definite, overwritten by its inverse.
+// Only the tiles on and below the diagonal are read and updated (see gj_gather_kernel).
 // Look-ahead schedule: the 128x128 diagonal inverse is a single-CTA, latency-bound kernel
 // (~0.33 ms); step k therefore updates tile (k+1,k+1) first, and a second stream inverts it
 // while the main stream finishes the rank-128 update of step k.
 static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
 {
     const int nb = npad / GJ_B;
-    double *d_Dinv[2] = {nullptr, nullptr}, *d_Ck = nullptr, *d_Rk = nullptr;
+    double *d_Dinv[2] = {nullptr, nullptr}, *d_Ck = nullptr, *d_Rk = nullptr, *d_Arow = nullptr;
     int *d_info = nullptr;
     if (!dev_alloc_t(&d_Dinv[0], (size_t)GJ_B * GJ_B) || !dev_alloc_t(&d_Dinv[1], (size_t)GJ_B * GJ_B) ||
         !dev_alloc_t(&d_Ck, (size_t)npad * GJ_B) || !dev_alloc_t(&d_Rk, (size_t)npad * GJ_B) ||
-        !dev_alloc_t(&d_info, (size_t)1))
+        !dev_alloc_t(&d_Arow, (size_t)npad * GJ_B) || !dev_alloc_t(&d_info, (size_t)1))
         return -1;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_tile = nullptr, ev_diag = nullptr;
@@ -365,41 +432,46 @@ static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
     DCA_CUDA(cudaEventCreateWithFlags(&ev_diag, cudaEventDisableTiming));
     DCA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
     const size_t smem_gemm = sizeof(double) * (2 * GJ_B * GM_AS + 2 * GM_KC * GM_BS);
-    const size_t smem_diag = sizeof(double) * (GJ_B * (GJ_B + 1) + GJ_B);
+    const size_t smem_diag = 0;          // the diagonal-block kernel keeps the block in registers
     DCA_CUDA(cudaFuncSetAttribute(dgemm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
-    DCA_CUDA(cudaFuncSetAttribute(gj_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag));
     DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, st, d_A, npad, 0, d_Dinv[0], d_info);
     for (int k = 0; k < nb; ++k) {
         double *Dk = d_Dinv[k & 1];
         if (k > 0) DCA_CUDA(cudaStreamWaitEvent(st, ev_diag, 0));          // Dinv_k from the side stream
-        DCA_LAUNCH(gj_split_col_kernel, (unsigned)ceil_div<long>((long)npad * GJ_B, 256), 256, 0, st, d_A, npad, npad, k, d_Ck);
+        // column block k and row block k rebuilt from the lower tiles; column block k reset to unit columns
+        DCA_LAUNCH(gj_gather_kernel, (unsigned)ceil_div<long>((long)npad * GJ_B, 256), 256, 0, st, d_A, npad, npad, k,
+                   d_Ck, d_Arow);
         // Rk (128 x npad) = Dinv (128x128) * A[kblock rows, :]
         DCA_LAUNCH(dgemm128_kernel, dim3(nb, 1), 256, smem_gemm, st,
-                   d_Rk, npad, Dk, GJ_B, d_A + (size_t)k * GJ_B * npad, npad, 1.0, 0.0, -1, -1, -1);
+                   d_Rk, npad, Dk, GJ_B, d_Arow, npad, 1.0, 0.0, -1, -1, -1, 0);
         int skr = -1;
         if (k + 1 < nb) {
             // tile (k+1,k+1) first, then its inverse on the side stream
             skr = k + 1;
             const size_t off = (size_t)(k + 1) * GJ_B;
             DCA_LAUNCH(dgemm128_kernel, dim3(1, 1), 256, smem_gemm, st,
-                       d_A + off * npad + off, npad, d_Ck + off * GJ_B, GJ_B, d_Rk + off, npad, -1.0, 1.0, -1, -1, -1);
+                       d_A + off * npad + off, npad, d_Ck + off * GJ_B, GJ_B, d_Rk + off, npad, -1.0, 1.0, -1, -1, -1, 0);
             DCA_CUDA(cudaEventRecord(ev_tile, st));
             DCA_CUDA(cudaStreamWaitEvent(side, ev_tile, 0));
             DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, side, d_A, npad, k + 1, d_Dinv[(k + 1) & 1], d_info);
             DCA_CUDA(cudaEventRecord(ev_diag, side));
         }
-        // A[i,:] -= Ck[i] * Rk for every row block i != k (tile (k+1,k+1) already done)
+        // A[i,j] -= Ck[i] * Rk[j] for the tiles j <= i of every row block i != k (tile (k+1,k+1) already done):
+        // half the rank-128 updates of the unsymmetric algorithm (n^3 instead of 2 n^3 flops)
         DCA_LAUNCH(dgemm128_kernel, dim3(nb, nb), 256, smem_gemm, st,
-                   d_A, npad, d_Ck, GJ_B, d_Rk, npad, -1.0, 1.0, k, skr, skr);
-        DCA_CUDA(cudaMemcpyAsync(d_A + (size_t)k * GJ_B * npad, d_Rk, sizeof(double) * (size_t)GJ_B * npad,
-                                 cudaMemcpyDeviceToDevice, st));
+                   d_A, npad, d_Ck, GJ_B, d_Rk, npad, -1.0, 1.0, k, skr, skr, 1);
+        // row block k, columns 0 .. (k+1)*128: the part below / on the diagonal
+        DCA_CUDA(cudaMemcpy2DAsync(d_A + (size_t)k * GJ_B * npad, sizeof(double) * (size_t)npad, d_Rk,
+                                   sizeof(double) * (size_t)npad, sizeof(double) * (size_t)(k + 1) * GJ_B, GJ_B,
+                                   cudaMemcpyDeviceToDevice, st));
     }
+    DCA_LAUNCH(gj_mirror_kernel, dim3(npad / 32, npad / 32), dim3(32, 8), 0, st, d_A, npad, npad);
     int info = 0;
     DCA_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
     DCA_CUDA(cudaStreamSynchronize(st));
     DCA_CUDA(cudaStreamSynchronize(side));
     cudaStreamDestroy(side); cudaEventDestroy(ev_tile); cudaEventDestroy(ev_diag);
-    dev_free(d_Dinv[0]); dev_free(d_Dinv[1]); dev_free(d_Ck); dev_free(d_Rk); dev_free(d_info);
+    dev_free(d_Dinv[0]); dev_free(d_Dinv[1]); dev_free(d_Ck); dev_free(d_Rk); dev_free(d_Arow); dev_free(d_info);
     if (info != 0) { set_error("mf_couplings: zero pivot at row %d: the correlation matrix is singular (increase the pseudocount)", info - 1); return -1; }
     return 0;
 }
