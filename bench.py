@@ -190,14 +190,18 @@ def find_hbm_peak(peaks):
                 walk(v, (prefix + "." + str(k)) if prefix else str(k))
         elif isinstance(node, (int, float)) and not isinstance(node, bool):
             key = prefix.lower()
-            if any(t in key for t in ("hbm", "copy", "dram", "mem_bw", "bandwidth")) and "tf" not in key:
-                found.append((prefix, float(node)))
+            if any(t in key for t in ("nvlink", "pcie", "l2", "smem", "shared", "h2d", "d2h", "tf", "flop")):
+                return
+            for rank, tag in enumerate(("hbm", "dram", "copy", "mem_bw", "membw")):
+                if tag in key:
+                    found.append((prefix, float(node), rank))
+                    break
     walk(peaks, "")
-    found = [(k, v if v < 1e5 else v / 1e9) for k, v in found if v > 0]       # bytes/s -> GB/s
-    found = [(k, v) for k, v in found if 500.0 < v < 20000.0]
+    found = [(k, v if v < 1e5 else v / 1e9, r) for k, v, r in found if v > 0]       # bytes/s -> GB/s
+    found = [(k, v, r) for k, v, r in found if 1000.0 < v < 20000.0]
     if not found:
         return 6650.0, "fallback 6650 GB/s (no MEASURED_PEAKS.json HBM entry)"
-    found.sort(key=lambda kv: (0 if "burst" in kv[0].lower() else 1 if "sustain" not in kv[0].lower() else 2))
+    found.sort(key=lambda kv: (kv[2], 0 if "burst" in kv[0].lower() else 1 if "sustain" not in kv[0].lower() else 2))
     return found[0][1], "MEASURED_PEAKS.json %s" % found[0][0]
 
 
