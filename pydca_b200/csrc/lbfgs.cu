@@ -22,8 +22,9 @@
 //     sequential float32 sums, so its trajectory is not reproducible even against
 //     itself, SURVEY finding 3).
 //
-// Host <-> device traffic per objective evaluation: one 32-byte D2H read of
-// {fx, g.d, g.g, x.x}; per iteration one more for g.d of the new direction.
+// Host <-> device traffic per objective evaluation: one 48-byte D2H read of
+// {fx, g.d, g.g, x.x}, the peer-timeout flag and the g.d of the direction built last
+// (read together with the first trial's scalars: no round trip of its own).
 #include "dca_common.cuh"
 #include "dca_internal.h"
 
