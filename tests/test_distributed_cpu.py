@@ -105,6 +105,27 @@ def _worker(rank, world, port, out_dir):
     got = allgather_counts(local, (lo, hi), N)
     assert (got == full).all()
 
+    # sharded_counts(): shallow alignments are computed redundantly (no collective), deep ones are
+    # row-sharded + summed; the device kernel is replaced by the oracle here (no CUDA on this box)
+    from pydca_b200 import _lib, distributed as dd
+    calls = []
+
+    def fake_counts(m, seqid, compare_f64=False, rows=None):
+        calls.append(rows)
+        c = P.reweight_counts(m, seqid, f64=compare_f64)
+        if rows is None:
+            return c
+        out = np.zeros_like(c)
+        out[rows[0]:rows[1]] = c[rows[0]:rows[1]]
+        return out
+    real = _lib.sequence_counts
+    _lib.sequence_counts = fake_counts
+    try:
+        assert (dd.sharded_counts(msa, 0.8) == full).all() and calls == [None]
+        assert (dd.sharded_counts(msa, 0.8, force_shard=True) == full).all() and calls[-1] == (lo, hi)
+    finally:
+        _lib.sequence_counts = real
+
     # site-sharded objective: each rank's data term, all-reduce, regulariser added once
     w = P.plm_weights(full)
     lam = 0.2 * (L - 1)
