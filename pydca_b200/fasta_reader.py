@@ -12,7 +12,8 @@ import numpy as np
 from . import _lib
 
 __all__ = ["get_alignment_from_fasta_file", "get_alignment_int_form", "alignment_letter2int",
-           "first_record_length", "get_alignment_zero_based", "alignment_zero_based"]
+           "first_record_length", "get_alignment_zero_based", "alignment_zero_based",
+           "res_to_char", "get_alignment_char_form", "sequences_to_char_form"]
 
 RES_TO_INT_ALL = {
     "PROTEIN": {c: i + 1 for i, c in enumerate("ACDEFGHIKLMNPQRSTVWY")},
@@ -116,3 +117,22 @@ def get_alignment_int_form(file_name, biomolecule="protein"):
 def alignment_letter2int(alignment, biomolecule="protein"):
     """fasta_reader.py:122-163."""
     return (alignment_zero_based(alignment, biomolecule).astype(np.int64) + 1).tolist()
+
+
+def res_to_char(biomolecule):
+    """{state (1..q): letter}, the inverse of the residue table with '-' as the one gap
+    symbol (fasta_reader.py:53-76)."""
+    table = RES_TO_INT_ALL[biomolecule.strip().upper()]
+    return {val: key for key, val in table.items() if key not in (".", "~")}
+
+
+def sequences_to_char_form(seqs_lst, biomolecule):
+    """Integer sequences (states 1..q) -> strings (fasta_reader.py:227-249)."""
+    to_char = res_to_char(biomolecule)
+    return ["".join(to_char[int(res)] for res in seq) for seq in seqs_lst]
+
+
+def get_alignment_char_form(file_name, biomolecule="PROTEIN"):
+    """The unique sequences of a FASTA file as strings over the standard alphabet: unknown
+    letters and all gap aliases come back as '-' (fasta_reader.py:191-224)."""
+    return sequences_to_char_form(get_alignment_int_form(file_name, biomolecule=biomolecule), biomolecule)

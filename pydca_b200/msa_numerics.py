@@ -17,7 +17,8 @@ from ._lib import _f32p, _f64p, _u8p, check, lib, ptr
 __all__ = ["compute_sequences_weight", "compute_single_site_freqs", "get_reg_single_site_freqs",
            "compute_pair_site_freqs", "get_reg_pair_site_freqs", "construct_corr_mat",
            "compute_couplings", "compute_two_site_model_fields", "compute_direct_info",
-           "corr_mat_from_alignment", "frobenius_norm_scores", "mean_field_scores"]
+           "corr_mat_from_alignment", "frobenius_norm_scores", "mean_field_scores",
+           "compute_pair_site_freqs_serial", "slice_couplings"]
 
 
 def _zero_based(alignment_data, num_site_states=None):
@@ -67,6 +68,23 @@ def get_reg_single_site_freqs(single_site_freqs=None, seqs_len=None, num_site_st
 def compute_pair_site_freqs(alignment_data=None, num_site_states=None, seqs_weight=None):
     """msa_numerics.py:183-229 -> float64[L(L-1)/2, q-1, q-1] in pair(i,j) order."""
     return _freqs(_zero_based(alignment_data, num_site_states), num_site_states, seqs_weight, True)[1]
+
+
+def compute_pair_site_freqs_serial(alignment_data=None, num_site_states=None, seqs_weight=None):
+    """msa_numerics.py:130-179, the reference's serial twin of compute_pair_site_freqs: same
+    result, same device kernel here."""
+    return compute_pair_site_freqs(alignment_data=alignment_data, num_site_states=num_site_states,
+                                   seqs_weight=seqs_weight)
+
+
+def slice_couplings(couplings=None, site_pair=None, num_site_states=None):
+    """msa_numerics.py:346-375 -> float64[q, q]: the (q-1) x (q-1) block of the pair, gap row and
+    column zero."""
+    q = int(num_site_states)
+    i, j = int(site_pair[0]), int(site_pair[1])
+    out = np.zeros((q, q), dtype=np.float64)
+    out[:q - 1, :q - 1] = np.asarray(couplings)[i * (q - 1):(i + 1) * (q - 1), j * (q - 1):(j + 1) * (q - 1)]
+    return out
 
 
 def get_reg_pair_site_freqs(pair_site_freqs=None, seqs_len=None, num_site_states=None, pseudocount=None):

@@ -131,6 +131,26 @@ def test_fasta_reader_line_endings_whitespace_and_many_duplicates(tmp_path, port
     assert (got == port.read_fasta(str(d), "protein", 17)).all()
 
 
+def test_char_form_helpers_and_slice_couplings(tmp_path):
+    """Host helpers of the reference surface: fasta_reader.res_to_char / sequences_to_char_form /
+    get_alignment_char_form (fasta_reader.py:53-76, :191-249) and msa_numerics.slice_couplings
+    (meanfield_dca/msa_numerics.py:346-375)."""
+    from pydca_b200 import fasta_reader, msa_numerics
+    assert fasta_reader.res_to_char("rna") == {1: "A", 2: "C", 3: "G", 4: "U", 5: "-"}
+    prot = fasta_reader.res_to_char("protein")
+    assert len(prot) == 21 and prot[1] == "A" and prot[20] == "Y" and prot[21] == "-"
+    assert fasta_reader.sequences_to_char_form([[1, 2, 21, 20], [5, 5, 5, 5]], "PROTEIN") == ["AC-Y", "FFFF"]
+    p = tmp_path / "t.fa"
+    p.write_text(FASTA)
+    assert fasta_reader.get_alignment_char_form(str(p), "protein") == [
+        "ACDEFGHIKL", "AC-EF-HI-L", "ACDEFGHIK-", "------ACDE"]
+    q, L = 5, 3
+    J = np.arange((L * (q - 1)) ** 2, dtype=np.float64).reshape(L * (q - 1), L * (q - 1))
+    blk = msa_numerics.slice_couplings(couplings=J, site_pair=(0, 2), num_site_states=q)
+    assert blk.shape == (q, q) and (blk[q - 1] == 0).all() and (blk[:, q - 1] == 0).all()
+    assert (blk[:q - 1, :q - 1] == J[0:4, 8:12]).all()
+
+
 def test_fasta_reader_errors(tmp_path):
     from pydca_b200 import _lib
     with pytest.raises(_lib.DcaBackendError, match="Unable to open"):
