@@ -1,6 +1,8 @@
-"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in pydca_b200/distributed.py:
-shard arithmetic, the row-sharded reweighting collective, and the site-sharded
-objective decomposition + all-reduce that the NCCL path performs per evaluation.
+"""world_size-2 and -3 gloo tests (CPU) of the multi-GPU host logic in pydca_b200/distributed.py:
+shard arithmetic and parameter-slice layout, both branches of the reweighting counts logic,
+the gather of the parameter slices, the replicated-x decomposition + all-reduce of the
+fallback path, and the OWNER-SHARDED decomposition (which conditional's half of which block
+goes to which rank) with a point-to-point exchange standing in for the peer-memory stores.
 The per-shard numbers come from the CPU oracle (no CUDA here)."""
 import os
 import socket
@@ -159,13 +161,54 @@ def _worker(rank, world, port, out_dir):
     fo, fc, co, cc = sp.layouts[rank]
     mine = np.concatenate([x[fo:fo + fc], x[co:co + cc]])
     assert (sp.gather(mine) == x).all()
+    # owner-sharded evaluation, decomposition only (the CUDA kernels do this over peer memory):
+    # rank r evaluates the conditionals of its sites; what they contribute to blocks J_ij owned by
+    # another rank (i outside my range, j inside) is "exported" to owner(i); every owner adds what
+    # it receives to its own part and the regulariser of its slice -> its slice of the full gradient
+    nq = L * q
+    qq = q * q
+
+    def block_range(i_lo, i_hi):          # coupling elements of the blocks (i, j > i), i in [i_lo, i_hi)
+        pair = lambda i: L * (L - 1) // 2 - (L - i) * (L - i - 1) // 2
+        return nq + pair(i_lo) * qq, nq + pair(i_hi) * qq
+    slo, shi = bounds[rank], bounds[rank + 1]
+    f_mine, g_mine = P.plm_gradient(msa, w, q, lam, lam, x, sites=(slo, shi))
+    data = g_mine.astype(np.float64) - g_reg                  # data term of my sites' conditionals
+    sends = []
+    for r in range(world):
+        c0, c1 = block_range(bounds[r], bounds[r + 1])
+        part = data[c0:c1].copy()
+        if r == rank:
+            part[:] = 0.0                                     # my own blocks stay here
+        sends.append(torch.from_numpy(part))
+    recvs = [torch.zeros(block_range(slo, shi)[1] - block_range(slo, shi)[0], dtype=torch.float64)
+             for _ in range(world)]
+    # all-to-all by point-to-point exchanges (gloo has no all_to_all for uneven CPU tensors everywhere)
+    for r in range(world):
+        if r == rank:
+            continue
+        if rank < r:
+            dist.send(sends[r], dst=r); dist.recv(recvs[r], src=r)
+        else:
+            dist.recv(recvs[r], src=r); dist.send(sends[r], dst=r)
+    c0, c1 = block_range(slo, shi)
+    own_c = data[c0:c1] + sum(t.numpy() for t in recvs) + g_reg[c0:c1]
+    own_f = data[slo * q:shi * q] + g_reg[slo * q:shi * q]
+    lay = sp.layouts[rank]
+    assert (lay[0], lay[1], lay[2], lay[3]) == (slo * q, (shi - slo) * q, c0, c1 - c0)
+    want = np.concatenate([g_full[slo * q:shi * q], g_full[c0:c1]])
+    got_slice = np.concatenate([own_f, own_c])
+    assert np.abs(got_slice - want).max() <= 1e-5 * np.abs(g_full).max()
+    # the fields of my sites never leave the rank; blocks below my range got nothing from me twice
+    assert all(float(t.abs().sum()) == 0.0 for r, t in enumerate(recvs) if r < rank)
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
 
 
-def test_gloo_world2_collectives(tmp_path):
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_collectives_and_owner_sharding(tmp_path, world):
     import torch.multiprocessing as mp
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
