@@ -242,7 +242,7 @@ def roofline_block(obj, x0, peaks):
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         ncu_name = {"unpack": "plm_unpack_kernel<21>", "logits": "plm_logits_kernel<21, 128>",
-                    "softmax_scan": "plm_softmax_kernel<21>", "scatter": "plm_scatter_kernel<21>",
+                    "softmax_scan": "plm_softmax_kernel<21, 1>", "scatter": "plm_scatter_kernel<21>",
                     "assemble": "plm_assemble_kernel<21>"}[top]
         traffic = tj["kernels"][ncu_name]["dram_bytes"]
         traffic_src = tj["source"]
