@@ -43,8 +43,6 @@ def main():
         sp = dd.ShardedPlm(msa, w, q, lam, lam, bounds=bounds)
         P = sp.obj.P
         rng = np.random.default_rng(1)
-        x = np.zeros(P, dtype=np.float32)
-        x0 = dd.scatter_full_vector([None] * 0, [], P)
         xl0 = sp.init()
         # parity at a perturbed point
         pert = rng.normal(0, 0.05, P).astype(np.float32)
@@ -82,8 +80,7 @@ def main():
             print("kernel ms (max over ranks) unpack+push %.3f logits %.3f softmax %.3f scatter %.3f export %.3f assemble+reduce %.3f  sum %.3f"
                   % (*tmax.tolist(), float(tmax.sum())))
             for r, a in enumerate(alls):
-                print("   rank %d sites %d: %s  describe %s" % (r, bounds[r + 1] - bounds[r],
-                      " ".join("%.3f" % v for v in a.tolist()), ""))
+                print("   rank %d sites %d: %s" % (r, bounds[r + 1] - bounds[r], " ".join("%.3f" % v for v in a.tolist())))
         d = sp.obj.describe()
         print("   rank %d nsplit %d col_tiles %d nscan %d Ploc %d" % (rank, d["nsplit"], d["col_tiles"], d["nscan"], sp.obj.Ploc), flush=True)
         # fit rate
