@@ -230,3 +230,66 @@ def mf_pipeline(msa, q, counts, pseudocount=0.5):
     fn = mf_fn_scores(J, L, q)
     return dict(w=w, meff=w.sum(), fi=fi, reg_fi=rfi, fij=fij, reg_fij=rfij, corr=C,
                 couplings=J, fn=fn, fn_apc=apc(fn, L))
+
+
+# ---- model of the device inverse (csrc/mf.cu) -------------------------------------------
+def symmetric_block_gauss_jordan(a, block):
+    """Numpy model of gj_invert_device (pydca_b200/csrc/mf.cu): blocked Gauss-Jordan on a
+    symmetric positive definite matrix that only ever reads and updates the tiles on and below
+    the diagonal.  With K the pivoted and U the unpivoted block indices the intermediates
+    satisfy  B_KK, B_UU symmetric and  B_KU = -B_UK^T,  so column block k and row block k are
+    rebuilt from lower tiles with signed transposes (gj_gather_kernel) and the rank-`block`
+    update touches the tiles j <= i only.  The upper tiles are poisoned with NaN here: a model
+    that passed would have failed loudly had it read one.  Returns inv(a), like
+    numpy.linalg.inv (msa_numerics.py:340 of the reference negates it afterwards).
+    Test infrastructure only."""
+    a = np.array(a, dtype=np.float64, copy=True)
+    n = a.shape[0]
+    if n % block:
+        raise ValueError("the model wants n to be a multiple of the block size")
+    nb = n // block
+
+    def tile(i, j):
+        return a[i * block:(i + 1) * block, j * block:(j + 1) * block]
+
+    for i in range(nb):
+        for j in range(i + 1, nb):
+            tile(i, j)[:] = np.nan
+    eye = np.eye(block)
+    for k in range(nb):
+        dinv = unblocked_gauss_jordan(tile(k, k))
+        ck = np.empty((n, block))
+        arow = np.empty((block, n))
+        for i in range(nb):
+            ck[i * block:(i + 1) * block] = tile(i, k) if i >= k else -tile(k, i).T
+        for j in range(nb):
+            arow[:, j * block:(j + 1) * block] = tile(k, j) if j < k else (eye if j == k else tile(j, k).T)
+        for i in range(k, nb):
+            tile(i, k)[:] = eye if i == k else 0.0
+        rk = dinv @ arow
+        for i in range(nb):
+            if i == k:
+                continue
+            for j in range(i + 1):
+                tile(i, j)[:] -= ck[i * block:(i + 1) * block] @ rk[:, j * block:(j + 1) * block]
+        for j in range(k + 1):
+            tile(k, j)[:] = rk[:, j * block:(j + 1) * block]
+    # gj_mirror_kernel: every element above the diagonal is copied from below it
+    return np.tril(a) + np.tril(a, -1).T
+
+
+def unblocked_gauss_jordan(a):
+    """Numpy model of gj_diag_inv_kernel: in-place Gauss-Jordan without pivoting, every pivot
+    step computed from the OLD pivot row and column (what the register-resident kernel
+    publishes through shared memory)."""
+    a = np.array(a, dtype=np.float64, copy=True)
+    for p in range(a.shape[0]):
+        prow, pcol = a[p, :].copy(), a[:, p].copy()
+        piv = 1.0 / prow[p]
+        rowv = prow * piv
+        new = a - np.outer(pcol, rowv)
+        new[p, :] = rowv
+        new[:, p] = -pcol * piv
+        new[p, p] = piv
+        a = new
+    return a
