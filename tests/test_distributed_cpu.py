@@ -75,6 +75,67 @@ def test_shard_layout_partitions_the_parameter_vector():
         _lib.shard_layout(10, 21, 4, 4)
 
 
+def test_owner_sharded_index_model():
+    """Index arithmetic of the fused exchange kernels (csrc/plm_eval.cu: plm_unpack_push_kernel,
+    plm_export_kernel, plm_assemble_owner_kernel) restated in numpy for several shard layouts:
+    after the pushes every rank's W holds exactly the columns of the full symmetric coupling
+    matrix it needs, and after the exports every owner assembles
+    dJ_ij(a,b) = G[(j,b)][(i,a)] + G[(i,a)][(j,b)] for its blocks from its own G and its R buffer."""
+    from pydca_b200 import _lib
+    rng = np.random.default_rng(5)
+    for L, q, bounds in ((7, 5, [0, 3, 7]), (9, 3, [0, 1, 8, 9]), (12, 4, [0, 3, 6, 9, 12]), (6, 5, [0, 6])):
+        Lq, qq = L * q, q * q
+        world = len(bounds) - 1
+        pair = lambda i, j: L * (L - 1) // 2 - (L - i) * (L - i - 1) // 2 + j - i - 1
+        owner = lambda s: max(r for r in range(world) if bounds[r] <= s)
+        P = Lq + L * (L - 1) // 2 * qq
+        x = rng.normal(size=P)
+        Jfull = np.zeros((Lq, Lq))                                   # [(i,a)][(j,b)] = J_ij(a,b), symmetric
+        for i in range(L):
+            for j in range(i + 1, L):
+                blk = x[Lq + pair(i, j) * qq: Lq + (pair(i, j) + 1) * qq].reshape(q, q)
+                Jfull[i * q:(i + 1) * q, j * q:(j + 1) * q] = blk
+                Jfull[j * q:(j + 1) * q, i * q:(i + 1) * q] = blk.T
+        # --- unpack + push: every rank walks its LOCAL slice
+        W = [np.full((Lq, Lq), np.nan) for _ in range(world)]
+        for r in range(world):
+            lo, hi = bounds[r], bounds[r + 1]
+            fo, fc, co, cc = _lib.shard_layout(L, q, lo, hi)
+            xl = np.concatenate([x[fo:fo + fc], x[co:co + cc]])
+            nq, pair0 = (hi - lo) * q, pair(lo, lo + 1) if lo + 1 < L else L * (L - 1) // 2
+            for i in range(lo, hi):
+                for j in range(i + 1, L):
+                    blk = xl[nq + (pair(i, j) - pair0) * qq: nq + (pair(i, j) - pair0 + 1) * qq].reshape(q, q)
+                    W[r][j * q:(j + 1) * q, i * q:(i + 1) * q] = blk.T             # my columns (i,a), rows (j,b)
+                    W[owner(j)][i * q:(i + 1) * q, j * q:(j + 1) * q] = blk        # owner(j)'s columns (j,b), rows (i,a)
+        for r in range(world):
+            lo, hi = bounds[r], bounds[r + 1]
+            for i in range(lo, hi):
+                cols = slice(i * q, (i + 1) * q)
+                rows = np.r_[0:i * q, (i + 1) * q:Lq]                               # every j != i
+                assert np.array_equal(W[r][rows, cols], Jfull[rows, cols])
+        # --- export + assemble: G[(j,b)][(i,a)] is produced by owner(i) (columns of site i)
+        G = rng.normal(size=(Lq, Lq))
+        max_sites = max(bounds[r + 1] - bounds[r] for r in range(world))
+        R = [np.full((max_sites * q, Lq), np.nan) for _ in range(world)]
+        for r in range(world):
+            lo, hi = bounds[r], bounds[r + 1]
+            for row in range(lo * q):                                               # rows (i,a) with i below my range
+                o = owner(row // q)
+                R[o][row - bounds[o] * q, lo * q:hi * q] = G[row, lo * q:hi * q]
+        for r in range(world):
+            lo, hi = bounds[r], bounds[r + 1]
+            for i in range(lo, hi):
+                for j in range(i + 1, L):
+                    u = G[j * q:(j + 1) * q, i * q:(i + 1) * q].T                   # my conditional: G[(j,b)][(i,a)]
+                    if j < hi:
+                        v = G[i * q:(i + 1) * q, j * q:(j + 1) * q]
+                    else:
+                        v = R[r][(i - lo) * q:(i - lo + 1) * q, j * q:(j + 1) * q]
+                    want = G[j * q:(j + 1) * q, i * q:(i + 1) * q].T + G[i * q:(i + 1) * q, j * q:(j + 1) * q]
+                    assert np.array_equal(u + v, want)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
