@@ -76,6 +76,25 @@ long dca_plm_num_params(const dca_plm *p);
  * (plmdca_numerics.cpp:492,:499); carry = 0 is textbook plmDCA.  chunk / warm:
  * chain length and warm-up overlap of the chunked scan (<=0 keeps the default 32/32). */
 int dca_plm_set_carry(dca_plm *p, int carry, int chunk, int warm);
+/* Arithmetic of the optimiser's inner products and of the L2 term of fx.
+ *   mode 1 ("reference"): the reference's own -- SEQUENTIAL float32 sums over all P
+ *     parameters (vecdot, arithmetic_ansi.h:114-121; fx += lambda*v*v,
+ *     plmdca_numerics.cpp:463-486; fx += fxi in site order, :572), reproduced bit for bit
+ *     by an exact block-parallel kernel (csrc/seqsum.cu) together with the reference's own
+ *     sequence of two-loop passes (lbfgs.cpp:568-601).  Those sums carry a deterministic
+ *     rounding bias (1.8 % of |g|^2 at N=5000, L=150) that steers the reference's L-BFGS
+ *     trajectory; with it the fit reproduces the reference's to ~1e-6 on FN scores.
+ *   mode 0 ("accurate"): float64 fixed-order reductions and the compact two-pass
+ *     recursion -- faster, but a different (better conditioned) trajectory: FN scores differ
+ *     from the reference's by a few 1e-4, exactly as the reference's own would with
+ *     float64 sums.
+ * Single-GPU handles only.  plmdcaBackend() picks the mode from DCA_B200_ARITHMETIC
+ * (reference | accurate; default reference). */
+int dca_plm_set_fidelity(dca_plm *p, int mode);
+/* test / measurement hook of that kernel on HOST buffers: *out = the sequential float32
+ * dot product of x and y (y != NULL), or the sequential L2 accumulation of x with lambda0 on
+ * the first n0 entries and lambda1 on the rest (y == NULL). */
+int dca_seq_sum(const float *x, const float *y, long n, long n0, float lambda0, float lambda1, float *out);
 /* initial point, PlmDCA::initFieldsAndCouplings (plmdca_numerics.cpp:207-249) */
 int dca_plm_init(dca_plm *p, float *x_out_host);
 /* objective + gradient with HOST buffers (x in, g out, *fx out): PlmDCA::gradient

@@ -12,7 +12,7 @@ Two checkers live here:
 * ``ref``   -- the UNMODIFIED reference C++ compiled from /root/reference into
   ``oracle/_ref/libpydca_ref.so`` (see Makefile), reached through ``ref_shim.cpp``.
 
-Parity status: pinned (tests/test_oracle_vs_ref.py, tests/golden/).
+Parity status: pinned (tests/test_oracle_golden.py, tests/golden/).
 """
 import ctypes
 import os
@@ -198,6 +198,18 @@ class _RefPlm:
                                    ctypes.byref(fx))
         return x, int(st), int(evals.value), float(fx.value)
 
+    def fit_trace(self, max_iterations, max_trace=512):
+        """fit() with the reference's progress callback recorded: returns (x, status,
+        evaluations, fx, trace[iterations, 6] = fx, xnorm, gnorm, step, ls, evaluations so far)."""
+        x = np.zeros(self.P, dtype=np.float32)
+        evals = ctypes.c_int(0)
+        iters = ctypes.c_int(0)
+        fx = ctypes.c_float(0)
+        trace = np.zeros((max_trace, 6), dtype=np.float32)
+        st = self._lib.ref_plm_fit_trace(self._h, _ptr(x, _f32p), int(max_iterations), ctypes.byref(evals),
+                                         ctypes.byref(fx), _ptr(trace, _f32p), int(max_trace), ctypes.byref(iters))
+        return x, int(st), int(evals.value), float(fx.value), trace[:min(max_trace, int(iters.value))].copy()
+
 
 class _Ref:
     def __init__(self):
@@ -226,6 +238,10 @@ class _Ref:
         L.ref_plm_fit.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_uint, ctypes.POINTER(ctypes.c_int),
                                   ctypes.POINTER(ctypes.c_float)]
         L.ref_plm_fit.restype = ctypes.c_int
+        L.ref_plm_fit_trace.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_uint, ctypes.POINTER(ctypes.c_int),
+                                        ctypes.POINTER(ctypes.c_float), _f32p, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_int)]
+        L.ref_plm_fit_trace.restype = ctypes.c_int
         # the reference's public C ABI (plmdcaBackend.cpp:151, :204)
         L.plmdcaBackend.argtypes = (ctypes.c_ushort, ctypes.c_ushort, ctypes.c_char_p, ctypes.c_uint,
                                     ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_uint,

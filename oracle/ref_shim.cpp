@@ -117,4 +117,56 @@ int ref_plm_fit(void *p, float *x, unsigned max_iterations, int *evals_out, floa
     return ret;
 }
 
+// The same with the reference's progress callback hooked (lbfgs.cpp:496): per iteration
+// trace[6*k .. 6*k+5] = {fx, xnorm, gnorm, step, line-search evaluations, evaluations so far}
+// for the first max_trace iterations; *iters_out = iterations reported.
+struct ShimTraceCtx { PlmDCA *obj; int evals; float *trace; int max_trace; int iters; };
+
+static lbfgsfloatval_t shim_evaluate_t(void *instance, const lbfgsfloatval_t *x, lbfgsfloatval_t *g,
+                                       const int, const lbfgsfloatval_t)
+{
+    auto *c = static_cast<ShimTraceCtx *>(instance);
+    ++c->evals;
+    return c->obj->gradient(x, g);
+}
+
+static int shim_progress_t(void *instance, const lbfgsfloatval_t *, const lbfgsfloatval_t *,
+                           const lbfgsfloatval_t fx, const lbfgsfloatval_t xnorm, const lbfgsfloatval_t gnorm,
+                           const lbfgsfloatval_t step, int, int k, int ls)
+{
+    auto *c = static_cast<ShimTraceCtx *>(instance);
+    if (c->trace && k >= 1 && k <= c->max_trace) {
+        float *t = c->trace + 6 * (k - 1);
+        t[0] = fx; t[1] = xnorm; t[2] = gnorm; t[3] = step; t[4] = (float)ls; t[5] = (float)c->evals;
+    }
+    c->iters = k;
+    return 0;
+}
+
+int ref_plm_fit_trace(void *p, float *x, unsigned max_iterations, int *evals_out, float *fx_out,
+                      float *trace, int max_trace, int *iters_out)
+{
+    auto *o = static_cast<PlmDCA *>(p);
+    const int n = static_cast<int>(o->num_fields_and_couplings);
+    lbfgsfloatval_t *m_x = lbfgs_malloc(n);
+    if (!m_x) return 1;
+    lbfgs_parameter_t param;
+    lbfgs_parameter_init(&param);
+    param.epsilon = 1E-3;
+    param.max_iterations = static_cast<int>(max_iterations);
+    param.max_linesearch = 5;
+    param.ftol = 1E-4;
+    param.m = 5;
+    o->initFieldsAndCouplings(m_x);
+    ShimTraceCtx ctx{o, 0, trace, max_trace, 0};
+    lbfgsfloatval_t fx = 0;
+    const int ret = lbfgs(n, m_x, &fx, shim_evaluate_t, shim_progress_t, &ctx, &param);
+    std::copy(m_x, m_x + n, x);
+    lbfgs_free(m_x);
+    if (evals_out) *evals_out = ctx.evals;
+    if (fx_out) *fx_out = fx;
+    if (iters_out) *iters_out = ctx.iters;
+    return ret;
+}
+
 }  // extern "C"

@@ -93,6 +93,8 @@ def lib():
     L.dca_plm_num_params.argtypes = [ctypes.c_void_p]
     L.dca_plm_num_params.restype = ctypes.c_long
     L.dca_plm_set_carry.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.dca_plm_set_fidelity.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.dca_seq_sum.argtypes = [_f32p, _f32p, ctypes.c_long, ctypes.c_long, ctypes.c_float, ctypes.c_float, _f32p]
     L.dca_plm_init.argtypes = [ctypes.c_void_p, _f32p]
     L.dca_plm_eval.argtypes = [ctypes.c_void_p, _f32p, _f32p, _f64p]
     L.dca_plm_eval_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _f64p]
@@ -241,6 +243,14 @@ class PlmObjective:
     def set_carry(self, carry=True, chunk=0, warm=-1):
         check(lib().dca_plm_set_carry(self._h, int(bool(carry)), int(chunk), int(warm)), "dca_plm_set_carry")
 
+    def set_arithmetic(self, mode):
+        """'reference': the reference's sequential float32 sums, bit for bit (its L-BFGS
+        trajectory); 'accurate': float64 fixed-order reductions (faster, FN differs ~1e-4)."""
+        modes = {"reference": 1, "accurate": 0}
+        if mode not in modes:
+            raise ValueError("arithmetic mode must be 'reference' or 'accurate', got %r" % (mode,))
+        check(lib().dca_plm_set_fidelity(self._h, modes[mode]), "dca_plm_set_fidelity")
+
     def init(self):
         x = np.zeros(self.Ploc, dtype=np.float32)
         check(lib().dca_plm_init(self._h, ptr(x, _f32p)), "dca_plm_init")
@@ -307,6 +317,24 @@ def plm_fn_apc(x, seqs_len, num_site_states):
     check(lib().dca_plm_fn_apc(ptr(x, _f32p), int(seqs_len), int(num_site_states), ptr(fn, _f64p),
                                ptr(apc, _f64p)), "dca_plm_fn_apc")
     return fn, apc
+
+
+def seq_dot(x, y):
+    """Sequential float32 dot product (arithmetic_ansi.h:114-121) evaluated exactly on the GPU."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    out = ctypes.c_float()
+    check(lib().dca_seq_sum(ptr(x, _f32p), ptr(y, _f32p), x.size, 0, 0.0, 0.0, ctypes.byref(out)), "dca_seq_sum")
+    return np.float32(out.value)
+
+
+def seq_reg(x, n0, lambda0, lambda1):
+    """Sequential float32 L2 accumulation (plmdca_numerics.cpp:463-486) evaluated exactly on the GPU."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = ctypes.c_float()
+    check(lib().dca_seq_sum(ptr(x, _f32p), None, x.size, int(n0), float(lambda0), float(lambda1),
+                            ctypes.byref(out)), "dca_seq_sum")
+    return np.float32(out.value)
 
 
 def lbfgs_vector_bench(n, stored_pairs=5, reps=20):

@@ -8,15 +8,20 @@
 #include "dca_internal.h"
 #include "../../include/dca_b200.h"
 
+#include <atomic>
 #include <cstdarg>
 #include <ctime>
 #include <mutex>
 #include <new>
 #include <vector>
 
+#ifndef DCA_DEFAULT_ARITHMETIC
+#define DCA_DEFAULT_ARITHMETIC 1      /* 1 = reference, 0 = accurate */
+#endif
+
 namespace dca {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 static thread_local std::string t_error;
 static std::string g_error;
@@ -51,13 +56,16 @@ int require_device()
 
 int sm_count()
 {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
+    // cached per device ordinal: one process may drive several GPUs (plmdcaBackend with DCA_B200_GPUS)
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cached[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev].store(v, std::memory_order_relaxed);
     }
-    return cached;
+    return v;
 }
 
 // mf.cu
@@ -91,6 +99,16 @@ static std::vector<std::pair<std::string, void *>> g_ipc_open;
 
 extern "C" void dca_plm_destroy(dca_plm *p);
 
+// arithmetic of plmdcaBackend(): DCA_B200_ARITHMETIC = reference (the reference's sequential
+// float32 sums: its trajectory, FN within ~1e-6) | accurate (float64 reductions, faster)
+static int backend_arithmetic()
+{
+    const char *e = getenv("DCA_B200_ARITHMETIC");
+    if (e && (strcmp(e, "accurate") == 0 || strcmp(e, "0") == 0)) return 0;
+    if (e && (strcmp(e, "reference") == 0 || strcmp(e, "1") == 0)) return 1;
+    return DCA_DEFAULT_ARITHMETIC;
+}
+
 static dca_plm *wrap_problem(PlmProblem *prob)
 {
     dca_plm *h = new (std::nothrow) dca_plm{prob, nullptr, nullptr};
@@ -119,7 +137,7 @@ int dca_set_device(int device)
     return 0;
 }
 
-unsigned long long dca_kernel_launches(void) { return g_launches; }
+unsigned long long dca_kernel_launches(void) { return g_launches.load(); }
 
 long dca_read_fasta(const char *msa_file, int biomolecule, int seqs_len, uint8_t **msa_out)
 {
@@ -143,22 +161,14 @@ int dca_weights(const uint8_t *msa, long num_seqs, int seqs_len, double seqid, i
     if (!msa || !counts_out || num_seqs <= 0 || seqs_len <= 0) { set_error("dca_weights: empty alignment"); return -1; }
     if (row_lo < 0 || row_hi > num_seqs || row_lo >= row_hi) { set_error("dca_weights: bad row range"); return -1; }
     if (!(seqid > 0.0) || seqid > 1.0) { set_error("dca_weights: seqid %g not in (0,1]", seqid); return -1; }
-    uint8_t *d_msa = nullptr;
-    unsigned *d_counts = nullptr;
-    if (!dev_alloc_t(&d_msa, (size_t)num_seqs * seqs_len) || !dev_alloc_t(&d_counts, (size_t)num_seqs)) {
-        dev_free(d_msa); dev_free(d_counts);
-        return -1;
-    }
+    DevBuf<uint8_t> d_msa;               // released on every return path
+    DevBuf<unsigned> d_counts;
+    if (!d_msa.alloc((size_t)num_seqs * seqs_len) || !d_counts.alloc((size_t)num_seqs)) return -1;
     DCA_CUDA(cudaMemcpy(d_msa, msa, (size_t)num_seqs * seqs_len, cudaMemcpyHostToDevice));
-    int rc = reweight_counts_device(d_msa, num_seqs, seqs_len, seqid, compare_f64, row_lo, row_hi, d_counts, 0);
-    if (rc == 0) {
-        cudaError_t e = cudaMemcpy(counts_out + row_lo, d_counts + row_lo, sizeof(unsigned) * (size_t)(row_hi - row_lo),
-                                   cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) { set_error("dca_weights: D2H failed: %s", cudaGetErrorString(e)); rc = -1; }
-    }
-    cudaDeviceSynchronize();
-    dev_free(d_msa); dev_free(d_counts);
-    return rc;
+    if (reweight_counts_device(d_msa, num_seqs, seqs_len, seqid, compare_f64, row_lo, row_hi, d_counts, 0) != 0) return -1;
+    DCA_CUDA(cudaMemcpy(counts_out + row_lo, d_counts.p + row_lo, sizeof(unsigned) * (size_t)(row_hi - row_lo),
+                        cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 dca_plm *dca_plm_create(const uint8_t *msa, const float *weights, long num_seqs, int seqs_len,
@@ -276,6 +286,17 @@ int dca_plm_set_carry(dca_plm *p, int carry, int chunk, int warm)
     if (!p) { set_error("null handle"); return -1; }
     plm_set_carry(p->prob, carry, chunk, warm);
     return 0;
+}
+
+int dca_plm_set_fidelity(dca_plm *p, int mode)
+{
+    if (!p) { set_error("null handle"); return -1; }
+    return plm_set_fidelity(p->prob, mode);
+}
+
+int dca_seq_sum(const float *x, const float *y, long n, long n0, float lambda0, float lambda1, float *out)
+{
+    return seqsum_host(x, y, n, n0, lambda0, lambda1, out);
 }
 
 int dca_plm_init(dca_plm *p, float *x_out_host)
@@ -430,7 +451,8 @@ float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states,
     dca_fit_result res{};
     // initial point (:77) and L-BFGS (:81) without leaving the device
     cudaStream_t st = plm_stream(h->prob);
-    int rc = plm_init_x_device(h->prob, h->d_x);
+    int rc = plm_set_fidelity(h->prob, backend_arithmetic());
+    if (rc == 0) rc = plm_init_x_device(h->prob, h->d_x);
     mark("init");
     LbfgsResult r{};
     double timed_ms = 0.0;

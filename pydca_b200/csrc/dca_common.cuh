@@ -1,6 +1,7 @@
 // dca_common.cuh -- shared helpers for the sm_100a DCA kernels.
 #pragma once
 #include <cuda.h>
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -44,11 +45,11 @@ int sm_count();
 
 // launch counter: every kernel launch of ours goes through DCA_LAUNCH so that
 // bench.py can report gpu_launches honestly
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;   // threads driving different GPUs launch concurrently
 #define DCA_LAUNCH(kernel, grid, block, smem, stream, ...)                      \
     do {                                                                        \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);             \
-        ++dca::g_launches;                                                      \
+        dca::g_launches.fetch_add(1, std::memory_order_relaxed);                                                    \
     } while (0)
 
 template <typename T>

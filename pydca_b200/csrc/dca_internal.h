@@ -18,6 +18,18 @@ bool host_pinned_free(void *p);          // false if p is not ours
 template <typename T>
 static inline bool dev_alloc_t(T **out, size_t count) { *out = static_cast<T *>(dev_alloc(sizeof(T) * count)); return *out != nullptr; }
 
+// scope guard for a cached device block: released on every return path
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { dev_free(p); }
+    bool alloc(size_t count) { p = static_cast<T *>(dev_alloc(sizeof(T) * count)); return p != nullptr; }
+    operator T *() const { return p; }
+};
+
 // row-major 2-D tensor map: inner dimension dim0 (contiguous), dim1 rows of stride1_bytes;
 // elem_bytes 4 (float32) or 1 (uint8); box = box0 x box1 elements.  0 on success.
 int make_tensor_map_2d(void *out_CUtensorMap, int elem_bytes, const void *base, unsigned long long dim0,
@@ -61,6 +73,9 @@ void plm_destroy(PlmProblem *p);
 long plm_num_params(const PlmProblem *p);
 cudaStream_t plm_stream(const PlmProblem *p);
 void plm_set_carry(PlmProblem *p, int carry, int chunk, int warm);
+int plm_set_fidelity(PlmProblem *p, int on);             // 1 = reference arithmetic (sequential float32 sums), single GPU
+int plm_fidelity(const PlmProblem *p);
+void plm_fx_layout(const PlmProblem *p, const double **fxsite, long *nscan, int *L, int *q, float *lh, float *lJ);
 // objective + gradient at device x -> device g ; scalars (fx, g.d, g.g, x.x) left in
 // p's scalar buffer; d_dir may be null (then PS_DG = 0).  No host sync.
 int plm_eval_device(PlmProblem *p, const float *d_x, float *d_g, const float *d_dir);
@@ -88,6 +103,26 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
 
 int lbfgs_vector_bench(long n, int bound, int reps, float *ms_out);
 int lbfgs_preload_kernels();   // force-load the optimiser's kernels (see plm_setup_t)
+
+// ---- seqsum.cu -----------------------------------------------------------------------
+// exact sequential float32 sums (the reference's vecdot / L2 accumulation), one CTA per job
+enum { SEQ_DOT = 0, SEQ_REG = 1 };
+constexpr int SEQ_MAX_JOBS = 4;
+struct SeqJob {
+    const float *x;
+    const float *y;          // SEQ_DOT: t_k = fl(x_k * y_k)
+    long n;
+    int kind;
+    long n0;                 // SEQ_REG: t_k = fl(fl(lam * x_k) * x_k), lam = lam0 for k < n0, else lam1
+    float lam0, lam1;
+    int out;                 // result slot in the float block handed to seqsum_launch
+    const double *fxsite;    // SEQ_REG epilogue (may be null): s += (float) sum_k fxsite[k*L + i], i = 0..L-1
+    long nscan;
+    int L;
+};
+int seqsum_prepare();        // once per device before the first launch (dynamic shared memory attribute)
+int seqsum_launch(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st);
+int seqsum_host(const float *x, const float *y, long n, long n0, float lam0, float lam1, float *out);
 
 // ---- scoring.cu ---------------------------------------------------------------------------
 int plm_fn_apc_host(const float *h_x, int L, int q, double *fn, double *fn_apc);

@@ -433,6 +433,61 @@ vec_direction_kernel(float *__restrict__ d, const float *__restrict__ g, HistPtr
     }
 }
 
+// ---- reference-arithmetic mode ("fidelity"): the reference's own sequence of vector passes ----
+// Inner products come from seqsum.cu (bit-exact sequential float32 sums) as floats in the
+// device block fd[]; the element-wise passes below read the scalars they need from it, so
+// the two-loop recursion (lbfgs.cpp:568-601) runs without a host round trip.
+enum { FD_FX = 0, FD_DG = 1, FD_GG = 2, FD_XX = 3, FD_DOT = 4, FD_YS = 5, FD_ALPHA = 10, FD_YY = 15,
+       FD_DGINIT = 16, FD_FLOATS = 20 };
+
+// s = x - xp, y = g - gp (vecdiff, :548-549) and d = -g (vecncpy, :575)
+__global__ void __launch_bounds__(VEC_THREADS)
+fid_diff_kernel(float *__restrict__ s_new, float *__restrict__ y_new, float *__restrict__ d,
+                const float *__restrict__ x, const float *__restrict__ xp, const float *__restrict__ g,
+                const float *__restrict__ gp, long n)
+{
+    VEC_LOOP4(n) {
+        const float4 X = reinterpret_cast<const float4 *>(x)[v], XP = reinterpret_cast<const float4 *>(xp)[v];
+        const float4 G = reinterpret_cast<const float4 *>(g)[v], GP = reinterpret_cast<const float4 *>(gp)[v];
+        reinterpret_cast<float4 *>(s_new)[v] = make_float4(X.x - XP.x, X.y - XP.y, X.z - XP.z, X.w - XP.w);
+        reinterpret_cast<float4 *>(y_new)[v] = make_float4(G.x - GP.x, G.y - GP.y, G.z - GP.z, G.w - GP.w);
+        reinterpret_cast<float4 *>(d)[v] = make_float4(-G.x, -G.y, -G.z, -G.w);
+    }
+    VEC_TAIL(n, k) { s_new[k] = x[k] - xp[k]; y_new[k] = g[k] - gp[k]; d[k] = -g[k]; }
+}
+
+// one vecadd / vecscale of the recursion with its scalar taken from fd[]:
+//   mode 0: alpha_j = fd[DOT] / ys_j ; d += (-alpha_j) * u      (u = y_j, :585-588)
+//   mode 1: d *= ys_new / yy                                      (:591)
+//   mode 2: beta = fd[DOT] / ys_j ; d += (alpha_j - beta) * u    (u = s_j, :596-599)
+__global__ void __launch_bounds__(VEC_THREADS)
+fid_axpy_kernel(float *__restrict__ d, const float *__restrict__ u, float *__restrict__ fd, int mode, int j, long n)
+{
+    float c;
+    if (mode == 0) {
+        const float alpha = __fdiv_rn(fd[FD_DOT], fd[FD_YS + j]);
+        // stored for mode 2; FD_ALPHA is not read by this launch and FD_DOT not written by it
+        if (blockIdx.x == 0 && threadIdx.x == 0) fd[FD_ALPHA + j] = alpha;
+        c = -alpha;
+    } else if (mode == 1) {
+        c = __fdiv_rn(fd[FD_YS + j], fd[FD_YY]);
+    } else {
+        c = __fsub_rn(fd[FD_ALPHA + j], __fdiv_rn(fd[FD_DOT], fd[FD_YS + j]));
+    }
+    VEC_LOOP4(n) {
+        float4 o = reinterpret_cast<const float4 *>(d)[v];
+        if (mode == 1) {
+            o = make_float4(__fmul_rn(o.x, c), __fmul_rn(o.y, c), __fmul_rn(o.z, c), __fmul_rn(o.w, c));
+        } else {
+            const float4 a = reinterpret_cast<const float4 *>(u)[v];
+            o.x = __fadd_rn(o.x, __fmul_rn(c, a.x)); o.y = __fadd_rn(o.y, __fmul_rn(c, a.y));
+            o.z = __fadd_rn(o.z, __fmul_rn(c, a.z)); o.w = __fadd_rn(o.w, __fmul_rn(c, a.w));
+        }
+        reinterpret_cast<float4 *>(d)[v] = o;
+    }
+    VEC_TAIL(n, k) d[k] = (mode == 1) ? __fmul_rn(d[k], c) : __fadd_rn(d[k], __fmul_rn(c, u[k]));
+}
+
 // libLBFGS status codes (lbfgs.h:78-150; the enum counts up from -1024)
 enum {
     ST_SUCCESS = 0, ST_STOP = 1, ST_ALREADY_MINIMIZED = 2,
@@ -560,9 +615,18 @@ struct Driver {
     allreduce_fn_t allreduce = nullptr;
     void *ctx = nullptr;
     int evals = 0;
+    bool fidelity = false;         // reference arithmetic: sequential float32 sums (seqsum.cu)
+    float *fd = nullptr, *h_fd = nullptr;
 
     int alloc()
     {
+        if (fidelity) {
+            if (!dev_alloc_t(&fd, (size_t)FD_FLOATS)) return -1;
+            DCA_CUDA(cudaMemsetAsync(fd, 0, sizeof(float) * FD_FLOATS, st));
+            h_fd = static_cast<float *>(host_pinned_alloc(sizeof(float) * FD_FLOATS));
+            if (!h_fd) return -1;
+            if (seqsum_prepare() != 0) return -1;
+        }
         float **v[] = {&xp, &g, &gp, &d};
         for (auto pp : v) if (!dev_alloc_t(pp, (size_t)n)) return -1;
         for (int i = 0; i < LB_M; ++i) {
@@ -583,12 +647,72 @@ struct Driver {
         for (float *q : v) if (q && q != keep_x) dev_free(q);
         for (int i = 0; i < LB_M; ++i) { dev_free(s[i]); dev_free(y[i]); }
         dev_free(sc); dev_free(partial); dev_free(ticket); dev_free(gram); dev_free(coef); dev_free(gram_loc);
+        dev_free(fd);
+        if (h_fd) host_pinned_free(h_fd);
     }
 
     // objective at x -> g ; returns {fx, g.d, g.g, x.x} on the host
+    SeqJob dot_job(const float *a, const float *b, int out) const
+    {
+        SeqJob j{};
+        j.x = a; j.y = b; j.n = n; j.kind = SEQ_DOT; j.out = out;
+        return j;
+    }
+
+    // reference arithmetic: fx = sequential L2 sum + per-site terms in site order
+    // (plmdca_numerics.cpp:463-486, :572), g.d / g.g / x.x as the reference's vecdot
+    int evaluate_fidelity(const float *dir, double *h, double *dginit)
+    {
+        if (plm_eval_device(p, x, g, nullptr) != 0) return -1;
+        SeqJob jobs[4];
+        int nj = 0;
+        {
+            SeqJob r{};
+            const double *fxsite; long nscan; int L, q; float lh, lJ;
+            plm_fx_layout(p, &fxsite, &nscan, &L, &q, &lh, &lJ);
+            r.x = x; r.y = nullptr; r.n = n; r.kind = SEQ_REG; r.n0 = (long)L * q; r.lam0 = lh; r.lam1 = lJ;
+            r.out = FD_FX; r.fxsite = fxsite; r.nscan = nscan; r.L = L;
+            jobs[nj++] = r;
+        }
+        if (dir) jobs[nj++] = dot_job(g, dir, FD_DG);
+        jobs[nj++] = dot_job(g, g, FD_GG);
+        jobs[nj++] = dot_job(x, x, FD_XX);
+        if (seqsum_launch(jobs, nj, fd, st) != 0) return -1;
+        DCA_CUDA(cudaMemcpyAsync(h_fd, fd, sizeof(float) * FD_FLOATS, cudaMemcpyDeviceToHost, st));
+        DCA_CUDA(cudaStreamSynchronize(st));
+        h[PS_FX] = h_fd[FD_FX]; h[PS_DG] = dir ? h_fd[FD_DG] : 0.0; h[PS_GG] = h_fd[FD_GG]; h[PS_XX] = h_fd[FD_XX];
+        if (dginit) *dginit = h_fd[FD_DGINIT];
+        return 0;
+    }
+
+    // history update + two-loop recursion exactly as lbfgs.cpp:546-601, nothing read back
+    int direction_fidelity(int end, int bound)
+    {
+        DCA_LAUNCH(fid_diff_kernel, blocks, VEC_THREADS, 0, st, s[end], y[end], d, x, xp, g, gp, n);
+        SeqJob two[2] = {dot_job(y[end], s[end], FD_YS + end), dot_job(y[end], y[end], FD_YY)};
+        if (seqsum_launch(two, 2, fd, st) != 0) return -1;
+        int j = (end + 1) % LB_M;
+        for (int i = 0; i < bound; ++i) {
+            j = (j + LB_M - 1) % LB_M;
+            SeqJob a = dot_job(s[j], d, FD_DOT);
+            if (seqsum_launch(&a, 1, fd, st) != 0) return -1;
+            DCA_LAUNCH(fid_axpy_kernel, blocks, VEC_THREADS, 0, st, d, y[j], fd, 0, j, n);
+        }
+        DCA_LAUNCH(fid_axpy_kernel, blocks, VEC_THREADS, 0, st, d, (const float *)nullptr, fd, 1, end, n);
+        for (int i = 0; i < bound; ++i) {
+            SeqJob b = dot_job(y[j], d, FD_DOT);
+            if (seqsum_launch(&b, 1, fd, st) != 0) return -1;
+            DCA_LAUNCH(fid_axpy_kernel, blocks, VEC_THREADS, 0, st, d, s[j], fd, 2, j, n);
+            j = (j + 1) % LB_M;
+        }
+        SeqJob dg = dot_job(g, d, FD_DGINIT);             // vecdot(&dginit, g, s, n), lbfgs.cpp:830
+        return seqsum_launch(&dg, 1, fd, st);
+    }
+
     int evaluate(const float *dir, double *h, double *dginit = nullptr)
     {
         ++evals;
+        if (fidelity) return evaluate_fidelity(dir, h, dginit);
         if (!allreduce) {
             if (plm_eval_device(p, x, g, dir) != 0) return -1;
             return plm_read_scalars(p, h, dginit);
@@ -615,6 +739,8 @@ int lbfgs_preload_kernels()
     DCA_CUDA(cudaFuncGetAttributes(&fa, vec_dots_kernel));
     DCA_CUDA(cudaFuncGetAttributes(&fa, vec_update_gram_kernel));
     DCA_CUDA(cudaFuncGetAttributes(&fa, vec_direction_kernel));
+    DCA_CUDA(cudaFuncGetAttributes(&fa, fid_diff_kernel));
+    DCA_CUDA(cudaFuncGetAttributes(&fa, fid_axpy_kernel));
     return 0;
 }
 
@@ -680,6 +806,8 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
     Driver D;
     D.p = p; D.n = plm_local_params(p); D.st = plm_stream(p);
     D.sharded = plm_is_sharded(p);
+    D.fidelity = plm_fidelity(p) != 0;
+    if (D.fidelity && (D.sharded || allreduce)) { set_error("lbfgs: the reference-arithmetic mode runs on one GPU"); return -1; }
     if (D.sharded && allreduce) { set_error("lbfgs: an owner-sharded objective exchanges over peer memory; no all-reduce callback"); return -1; }
     D.blocks = std::min<long>(ceil_div<long>(D.n, VEC_THREADS * 4), 8L * sm_count());
     D.x = d_x; D.allreduce = allreduce; D.ctx = allreduce_ctx;
@@ -715,7 +843,7 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
     gnorm = (float)std::sqrt(h[PS_GG]);
     if (xnorm < 1.0f) xnorm = 1.0f;
     if (gnorm / xnorm <= prm.epsilon) { ret = ST_ALREADY_MINIMIZED; goto done; }   // :450-454
-    step = (float)(1.0 / std::sqrt(h[PS_GG]));                           // :459 (d = -g)
+    step = (float)(1.0 / (double)gnorm);                                 // :459 vec2norminv (d = -g): 1 / the float norm
     dginit = -(float)h[PS_GG];
 
     for (;;) {
@@ -824,6 +952,9 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
                 const int slot = (end + LB_M - t) % LB_M;      // t = 0: the pair written now
                 H.slot[t] = slot; H.s[t] = D.s[slot]; H.y[t] = D.y[slot];
             }
+            if (D.fidelity) {
+                LB_CHECK(D.direction_fidelity(end, bound));
+            } else {
             // pass A: s = x - xp, y = g - gp, the new inner products, Gram update and the scalar
             // recursion (alpha, beta, gamma -> coefficients, g.d) in the last CTA
             DCA_LAUNCH(vec_update_gram_kernel, D.blocks, VEC_THREADS, 0, st,
@@ -831,6 +962,7 @@ int lbfgs_minimize(PlmProblem *p, float *d_x, int max_iterations, int verbose,
                        D.sharded ? D.gram_loc : (double *)nullptr, D.sharded ? plm_xr_next(p) : XrCall{});
             // pass B: the direction as one linear combination
             DCA_LAUNCH(vec_direction_kernel, D.blocks, VEC_THREADS, 0, st, D.d, D.g, H, D.coef, n);
+            }
             ++k;
             end = (end + 1) % LB_M;
         }

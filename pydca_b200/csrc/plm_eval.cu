@@ -81,6 +81,8 @@ struct PlmProblem {
     float lh = 0.f, lJ = 0.f;
     int site_lo = 0, site_hi = 0;
     int carry = 1, chunk = 32, warm = 32;
+    int fidelity = 0;        // 1: keep per-(scan chunk, site) fx partials for the reference-arithmetic optimiser (seqsum.cu)
+    double *d_fxsite = nullptr;
     cudaStream_t stream = nullptr;
     uint8_t *d_msa = nullptr, *d_msaT = nullptr, *d_perm = nullptr;
     float *d_w = nullptr, *d_W = nullptr, *d_G = nullptr, *d_S = nullptr, *d_Rz = nullptr;
@@ -319,8 +321,8 @@ template <int Q, int SM_PF>
 __global__ void __launch_bounds__(128)
 plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, const uint8_t *__restrict__ msa,
                    const float *__restrict__ w, long N, int L, int site_lo, int site_hi,
-                   int chunk, int warm, int carry, double *__restrict__ fxpart)
-{
+                   int chunk, int warm, int carry, double *__restrict__ fxpart, double *__restrict__ fxsite)
+{   // fxsite (may be null): [scan chunk][L] per-site partials of fx, for the reference-order sum of seqsum.cu
     __shared__ float sbuf[4][32 * Q];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long k = (long)blockIdx.y * 4 + wib;
@@ -402,6 +404,7 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
             __syncwarp();
         }
     }
+    if (fxsite && active) fxsite[k * L + site] = fx;
     fx = warp_sum(active ? fx : 0.0);
     if (lane == 0) fxpart[k * gridDim.x + blockIdx.x] = fx;
 }
@@ -956,11 +959,11 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
     if ((long)gridB.x * gridB.y > 2L * sm_count())
         DCA_LAUNCH((plm_softmax_kernel<Q, 1>), gridB, 128, 0, st,
                    p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart);
+                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr);
     else
         DCA_LAUNCH((plm_softmax_kernel<Q, 4>), gridB, 128, 0, st,
                    p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart);
+                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr);
     PLM_MARK();
 
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
@@ -1007,14 +1010,21 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
 // 8 GPUs (measured: the whole end-to-end call is ~30 ms).  A recycled arena keeps its address, so
 // its IPC handle and every peer's mapping of it stay valid (capi.cu caches those by handle).
 static std::mutex g_arena_mu;
-static std::vector<std::pair<unsigned char *, size_t>> g_arena_pool;
+static std::vector<std::pair<unsigned char *, size_t>> g_arena_pool;   // .second = bytes ^ (device << 56)
+
+static size_t arena_key(size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return bytes ^ ((size_t)dev << 56);
+}
 
 static unsigned char *arena_acquire(size_t bytes)
 {
     {
         std::lock_guard<std::mutex> lk(g_arena_mu);
         for (size_t k = 0; k < g_arena_pool.size(); ++k)
-            if (g_arena_pool[k].second == bytes) {
+            if (g_arena_pool[k].second == arena_key(bytes)) {
                 unsigned char *ptr = g_arena_pool[k].first;
                 g_arena_pool.erase(g_arena_pool.begin() + (long)k);
                 return ptr;
@@ -1031,7 +1041,7 @@ static unsigned char *arena_acquire(size_t bytes)
 static void arena_release(unsigned char *ptr, size_t bytes)
 {
     std::lock_guard<std::mutex> lk(g_arena_mu);
-    g_arena_pool.emplace_back(ptr, bytes);
+    g_arena_pool.emplace_back(ptr, arena_key(bytes));
 }
 
 static void plm_free(PlmProblem *p)
@@ -1041,7 +1051,7 @@ static void plm_free(PlmProblem *p)
     dev_free(p->d_msa); dev_free(p->d_msaT); dev_free(p->d_perm); dev_free(p->d_w);
     if (!p->sharded) dev_free(p->d_W);
     dev_free(p->d_G); dev_free(p->d_S); dev_free(p->d_Rz); dev_free(p->d_fxpart);
-    dev_free(p->d_red); dev_free(p->d_scal); dev_free(p->d_ticket); dev_free(p->d_scal_loc);
+    dev_free(p->d_fxsite); dev_free(p->d_red); dev_free(p->d_scal); dev_free(p->d_ticket); dev_free(p->d_scal_loc);
     if (p->arena) arena_release(p->arena, p->lay.bytes);   // no peer pushes any more: every rank synchronised before destroy
     if (p->h_scal) host_pinned_free(p->h_scal);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -1323,6 +1333,25 @@ void plm_set_carry(PlmProblem *p, int carry, int chunk, int warm)
     if (chunk > 0) p->chunk = std::max(8, chunk);
     if (warm >= 0) p->warm = warm;
     plm_plan_scan(p);
+}
+
+// reference-arithmetic mode: the softmax kernel also keeps the per-site
+// partials of fx, which seqsum.cu adds in the reference's order
+int plm_set_fidelity(PlmProblem *p, int on)
+{
+    if (on && p->sharded) { set_error("plm: the reference-arithmetic mode runs on one GPU (sequential sums span the whole vector)"); return -1; }
+    if (on && !p->d_fxsite) {
+        const size_t count = (size_t)(p->N / 8 + 1) * p->L;          // chunk >= 8
+        if (!dev_alloc_t(&p->d_fxsite, count)) return -1;
+        DCA_CUDA(cudaMemsetAsync(p->d_fxsite, 0, sizeof(double) * count, p->stream));
+    }
+    p->fidelity = on ? 1 : 0;
+    return 0;
+}
+int plm_fidelity(const PlmProblem *p) { return p->fidelity; }
+void plm_fx_layout(const PlmProblem *p, const double **fxsite, long *nscan, int *L, int *q, float *lh, float *lJ)
+{
+    *fxsite = p->d_fxsite; *nscan = p->nscan; *L = p->L; *q = p->q; *lh = p->lh; *lJ = p->lJ;
 }
 
 int plm_eval_device(PlmProblem *p, const float *d_x, float *d_g, const float *d_dir)

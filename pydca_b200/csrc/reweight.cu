@@ -153,8 +153,9 @@ int reweight_min_ident(int L, double seqid, int compare_f64)
 
 // pack a u8 [N][L] device MSA into zero-padded word rows
 __global__ void pack_rows_kernel(const uint8_t *__restrict__ msa, long N, int L, int Lw,
-                                 uint32_t *__restrict__ out)
-{
+                                 uint32_t *__restrict__ out, unsigned *__restrict__ bad)
+{   // *bad is raised for residue codes >= 32: the mismatch test of reweight_kernel (bit 5 of
+    // (a ^ b) + 0x1f per byte) is exact only for 5-bit codes
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * Lw) return;
     const long n = idx / Lw;
@@ -163,7 +164,11 @@ __global__ void pack_rows_kernel(const uint8_t *__restrict__ msa, long N, int L,
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
         const int s = kw * 4 + b;
-        if (s < L) v |= (uint32_t)msa[n * L + s] << (8 * b);
+        if (s < L) {
+            const uint32_t c = msa[n * L + s];
+            if (c >= 32u) atomicOr(bad, 1u);
+            v |= c << (8 * b);
+        }
     }
     out[idx] = v;
 }
@@ -176,12 +181,14 @@ int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, in
 {
     if (N <= 0 || L <= 0) { set_error("reweight: empty alignment (N=%ld L=%d)", N, L); return -1; }
     const int Lw = (int)(ceil_div(L, 4) + 3) / 4 * 4;
-    uint32_t *d_words = nullptr;
-    if (!dev_alloc_t(&d_words, (size_t)N * Lw)) return -1;
+    DevBuf<uint32_t> d_words;            // released on every return path
+    DevBuf<unsigned> d_bad;
+    if (!d_words.alloc((size_t)N * Lw) || !d_bad.alloc(1)) return -1;
+    DCA_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), stream));
     {
         const long total = N * Lw;
         DCA_LAUNCH(pack_rows_kernel, (unsigned)ceil_div<long>(total, 256), 256, 0, stream,
-                   d_msa, N, L, Lw, d_words);
+                   d_msa, N, L, Lw, d_words, d_bad);
     }
     DCA_CUDA(cudaMemsetAsync(d_counts + row_lo, 0, sizeof(unsigned) * (size_t)(row_hi - row_lo), stream));
     const int T = reweight_min_ident(L, seqid, compare_f64);
@@ -194,18 +201,17 @@ int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, in
         long jper = ceil_div<long>(ceil_div<long>(N, js), RW_TJ) * RW_TJ;
         js = (int)ceil_div<long>(N, jper);
         const size_t smem = sizeof(uint32_t) * 2 * (RW_TI + RW_TJ) * RW_STRIDE;
-        static bool attr_done = false;
-        if (!attr_done) {
-            DCA_CUDA(cudaFuncSetAttribute(reweight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
-        }
+        // per-device attribute (a process may drive several GPUs): set on every call, it is cheap
+        DCA_CUDA(cudaFuncSetAttribute(reweight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(gx, (unsigned)js);
         DCA_LAUNCH(reweight_kernel, grid, 256, smem, stream,
                    d_words, N, row_lo, row_hi, Lw, jper, max_mismatch32, d_counts);
     }
     DCA_CUDA(cudaGetLastError());
+    unsigned h_bad = 0;
+    DCA_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
     DCA_CUDA(cudaStreamSynchronize(stream));
-    dev_free(d_words);
+    if (h_bad) { set_error("reweight: residue code >= 32 in the alignment (states must be 0..q-1, q <= 32)"); return -1; }
     return 0;
 }
 

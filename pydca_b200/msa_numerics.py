@@ -29,6 +29,8 @@ def _zero_based(alignment_data, num_site_states=None):
         raise ValueError("alignment_data must use states 1..q (gap = q)")
     if num_site_states is not None and a.max() > num_site_states:
         raise ValueError("alignment_data contains state %d > num_site_states %d" % (a.max(), num_site_states))
+    if a.max() > 32:        # the uint8 cast below would wrap; the reweighting kernel packs 5-bit codes
+        raise ValueError("alignment_data contains state %d; at most 32 states are supported" % a.max())
     return np.ascontiguousarray(a - 1, dtype=np.uint8)
 
 
