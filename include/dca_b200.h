@@ -62,6 +62,17 @@ void dca_free_host(void *p);
 int dca_weights(const uint8_t *msa, long num_seqs, int seqs_len, double seqid,
                 int compare_f64, long row_lo, long row_hi, uint32_t *counts_out);
 
+/* Symmetric variant for deep alignments and for several GPUs: ident(i,j) = ident(j,i), so only
+ * the tiles on and above the diagonal are compared and a hit counts for both rows (half the
+ * compares of dca_weights on a row range).  128-row tiles are dealt to `nparts` parts cyclically;
+ * partial_counts_out[N] receives part `part`'s contribution to EVERY row -- the element-wise
+ * sum over the parts (one all-reduce of N integers across GPUs) is counts[].  nparts = 1 gives
+ * the counts directly (dca_weights on the whole alignment takes this path).  device_ms_out
+ * (may be NULL): CUDA-event time of pack + compare kernels, H2D / D2H excluded. */
+int dca_weights_part(const uint8_t *msa, long num_seqs, int seqs_len, double seqid,
+                     int compare_f64, int part, int nparts, uint32_t *partial_counts_out,
+                     float *device_ms_out);
+
 /* ---- plmDCA objective / optimiser ------------------------------------------------
  * A dca_plm handle owns the device-resident MSA, weights and work buffers of one
  * objective (PlmDCA object of plmdca.h:16).  site_lo/site_hi shard the data term
@@ -206,6 +217,10 @@ int dca_mf_scores(const uint8_t *msa, const double *weights, long num_seqs, int 
                   int num_site_states, double pseudocount, double *reg_fi_out,
                   double *couplings_out, double *fn_out, double *fn_apc_out, double *di_out,
                   float *stage_ms_out);
+/* measurement hook: best-of-reps TFLOP/s of a register-only mma.sync.m8n8k4.f64 stream on
+ * every SM -- the measured FP64 tensor-pipe peak the inverse is reported against
+ * ("the builder micro-benchmarks it before reporting the inverse"). */
+int dca_fp64_mma_peak(int reps, double *tflops_out);
 /* construct_corr_mat on caller-supplied regularised frequencies (:271-318):
  * reg_fi double[L][q], reg_fij double[L(L-1)/2][q-1][q-1] -> corr_out n x n. */
 int dca_mf_corr_from_freqs(const double *reg_fi, const double *reg_fij, int seqs_len,

@@ -51,6 +51,8 @@ class _Port:
         L.orc_read_fasta.restype = ctypes.c_long
         L.orc_free.argtypes = [ctypes.c_void_p]
         L.orc_reweight_counts.argtypes = [_u8p, ctypes.c_long, ctypes.c_int, ctypes.c_double, ctypes.c_int, _u32p]
+        L.orc_reweight_counts_rows.argtypes = [_u8p, ctypes.c_long, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                               ctypes.POINTER(ctypes.c_long), ctypes.c_long, _u32p]
         L.orc_plm_weights.argtypes = [_u32p, ctypes.c_long, _f32p]
         L.orc_plm_meff.argtypes = [_f32p, ctypes.c_long]
         L.orc_plm_meff.restype = ctypes.c_float
@@ -84,6 +86,16 @@ class _Port:
         n, l = msa.shape
         c = np.zeros(n, dtype=np.uint32)
         self.L.orc_reweight_counts(_ptr(msa, _u8p), n, l, float(seqid), int(bool(f64)), _ptr(c, _u32p))
+        return c
+
+    def reweight_counts_rows(self, msa, seqid, rows, f64=False):
+        """c_i for the given rows only (each against all N rows): spot checks at full size."""
+        msa = np.ascontiguousarray(msa, dtype=np.uint8)
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        n, l = msa.shape
+        c = np.zeros(rows.size, dtype=np.uint32)
+        self.L.orc_reweight_counts_rows(_ptr(msa, _u8p), n, l, float(seqid), int(bool(f64)),
+                                        rows.ctypes.data_as(ctypes.POINTER(ctypes.c_long)), rows.size, _ptr(c, _u32p))
         return c
 
     def plm_weights(self, counts):

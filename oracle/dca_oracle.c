@@ -126,6 +126,31 @@ void orc_reweight_counts(const uint8_t *msa, long N, int L, double seqid,
     }
 }
 
+/* the same loop for a caller-chosen subset of rows i (full-size spot checks of deep
+ * alignments: work is linear in the number of rows): counts[k] = c_{rows[k]}          */
+void orc_reweight_counts_rows(const uint8_t *msa, long N, int L, double seqid, int f64,
+                              const long *rows, long nrows, uint32_t *counts)
+{
+    const float seqid_f = (float)seqid;
+#pragma omp parallel for schedule(static)
+    for (long k = 0; k < nrows; ++k) {
+        const uint8_t *si = msa + rows[k] * (long)L;
+        uint32_t c = 0;
+        for (long j = 0; j < N; ++j) {
+            const uint8_t *sj = msa + j * (long)L;
+            unsigned ident = 0;
+            for (int s = 0; s < L; ++s) ident += (si[s] == sj[s]);
+            if (f64) {
+                if ((double)ident / (double)L > seqid) ++c;
+            } else {
+                float sim = (float)ident / (float)L;
+                if (sim > seqid_f) ++c;
+            }
+        }
+        counts[k] = c;
+    }
+}
+
 /* plmdca_numerics.cpp:669  w = 1.f / count (count held as float there). */
 void orc_plm_weights(const uint32_t *counts, long N, float *w)
 {

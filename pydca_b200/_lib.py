@@ -70,6 +70,8 @@ def lib():
     L.dca_free_host.restype = None
     L.dca_weights.argtypes = [_u8p, ctypes.c_long, ctypes.c_int, ctypes.c_double, ctypes.c_int,
                               ctypes.c_long, ctypes.c_long, _u32p]
+    L.dca_weights_part.argtypes = [_u8p, ctypes.c_long, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_int, _u32p, _f32p]
     L.dca_plm_create.argtypes = [_u8p, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                  ctypes.c_float, ctypes.c_int, ctypes.c_int]
     L.dca_plm_create.restype = ctypes.c_void_p
@@ -116,6 +118,7 @@ def lib():
     L.dca_mf_scores.argtypes = [_u8p, _f64p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                 _f64p, _f64p, _f64p, _f64p, _f64p, _f32p]
     L.dca_mf_corr_from_freqs.argtypes = [_f64p, _f64p, ctypes.c_int, ctypes.c_int, _f64p]
+    L.dca_fp64_mma_peak.argtypes = [ctypes.c_int, _f64p]
     L.dca_mf_direct_info.argtypes = [_f64p, _f64p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
     L.dca_plm_direct_info.argtypes = [_f32p, _f64p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
     _lib = L
@@ -160,6 +163,18 @@ def sequence_counts(msa, seqid, compare_f64=False, rows=None):
     check(lib().dca_weights(ptr(msa, _u8p), n, l, float(seqid), int(bool(compare_f64)), lo, hi,
                             ptr(counts, _u32p)), "dca_weights")
     return counts
+
+
+def sequence_counts_part(msa, seqid, part, nparts, compare_f64=False, want_ms=False):
+    """Part `part` of `nparts` of the symmetric all-pairs comparison: partial neighbour counts of
+    ALL rows (uint32[N]); summing the parts gives sequence_counts(msa, seqid)."""
+    msa = np.ascontiguousarray(msa, dtype=np.uint8)
+    n, l = msa.shape
+    counts = np.zeros(n, dtype=np.uint32)
+    ms = ctypes.c_float()
+    check(lib().dca_weights_part(ptr(msa, _u8p), n, l, float(seqid), int(bool(compare_f64)), int(part),
+                                 int(nparts), ptr(counts, _u32p), ctypes.byref(ms)), "dca_weights_part")
+    return (counts, ms.value) if want_ms else counts
 
 
 def shard_layout(seqs_len, num_site_states, site_lo, site_hi):
@@ -342,6 +357,13 @@ def lbfgs_vector_bench(n, stored_pairs=5, reps=20):
     ms = np.zeros(3, dtype=np.float32)
     check(lib().dca_lbfgs_vector_bench(int(n), int(stored_pairs), int(reps), ptr(ms, _f32p)), "dca_lbfgs_vector_bench")
     return dict(zip(("update_gram", "direction", "step"), ms.tolist()))
+
+
+def fp64_mma_peak(reps=5):
+    """Measured FP64 tensor-pipe peak (TFLOP/s): a register-only DMMA stream on every SM."""
+    out = ctypes.c_double()
+    check(lib().dca_fp64_mma_peak(int(reps), ctypes.byref(out)), "dca_fp64_mma_peak")
+    return out.value
 
 
 def last_fit():

@@ -77,6 +77,7 @@ int mf_fn_apc_host(const double *h_J, int L, int q, double *fn, double *fn_apc);
 int mf_corr_from_freqs_host(const double *reg_fi, const double *reg_fij, int L, int q, double *corr);
 int mf_scores_host(const uint8_t *msa, const double *w, long N, int L, int q, double pseudocount,
                    double *reg_fi, double *couplings, double *fn, double *fn_apc, double *di, float *stage_ms);
+int fp64_mma_peak(int reps, double *tflops_out);
 // scoring.cu
 int plm_di_host(const float *h_x, const double *h_reg_fi, int L, int q, double *di, double *fields);
 int mf_di_host(const double *h_J, const double *h_reg_fi, int L, int q, double *di, double *fields);
@@ -165,9 +166,38 @@ int dca_weights(const uint8_t *msa, long num_seqs, int seqs_len, double seqid, i
     DevBuf<unsigned> d_counts;
     if (!d_msa.alloc((size_t)num_seqs * seqs_len) || !d_counts.alloc((size_t)num_seqs)) return -1;
     DCA_CUDA(cudaMemcpy(d_msa, msa, (size_t)num_seqs * seqs_len, cudaMemcpyHostToDevice));
-    if (reweight_counts_device(d_msa, num_seqs, seqs_len, seqid, compare_f64, row_lo, row_hi, d_counts, 0) != 0) return -1;
+    // the whole alignment: symmetric tiles (half the compares); a row shard: those rows against all
+    const bool whole = (row_lo == 0 && row_hi == num_seqs);
+    if (reweight_counts_device(d_msa, num_seqs, seqs_len, seqid, compare_f64, row_lo, row_hi, d_counts, 0,
+                               whole ? 0 : -1, 1) != 0) return -1;
     DCA_CUDA(cudaMemcpy(counts_out + row_lo, d_counts.p + row_lo, sizeof(unsigned) * (size_t)(row_hi - row_lo),
                         cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dca_weights_part(const uint8_t *msa, long num_seqs, int seqs_len, double seqid, int compare_f64,
+                     int part, int nparts, uint32_t *partial_counts_out, float *device_ms_out)
+{
+    if (require_device() != 0) return -1;
+    if (!msa || !partial_counts_out || num_seqs <= 0 || seqs_len <= 0) { set_error("dca_weights_part: empty alignment"); return -1; }
+    if (nparts < 1 || part < 0 || part >= nparts) { set_error("dca_weights_part: bad part %d of %d", part, nparts); return -1; }
+    if (!(seqid > 0.0) || seqid > 1.0) { set_error("dca_weights_part: seqid %g not in (0,1]", seqid); return -1; }
+    DevBuf<uint8_t> d_msa;
+    DevBuf<unsigned> d_counts;
+    if (!d_msa.alloc((size_t)num_seqs * seqs_len) || !d_counts.alloc((size_t)num_seqs)) return -1;
+    DCA_CUDA(cudaMemcpy(d_msa, msa, (size_t)num_seqs * seqs_len, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    DCA_CUDA(cudaEventCreate(&e0)); DCA_CUDA(cudaEventCreate(&e1));
+    cudaEventRecord(e0, 0);
+    const int rc = reweight_counts_device(d_msa, num_seqs, seqs_len, seqid, compare_f64, 0, num_seqs, d_counts, 0, part, nparts);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != 0) return -1;
+    if (device_ms_out) *device_ms_out = ms;
+    DCA_CUDA(cudaMemcpy(partial_counts_out, d_counts.p, sizeof(unsigned) * (size_t)num_seqs, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -518,6 +548,8 @@ int dca_mf_scores(const uint8_t *msa, const double *weights, long num_seqs, int 
     return mf_scores_host(msa, weights, num_seqs, seqs_len, num_site_states, pseudocount, reg_fi_out,
                           couplings_out, fn_out, fn_apc_out, di_out, stage_ms_out);
 }
+
+int dca_fp64_mma_peak(int reps, double *tflops_out) { return fp64_mma_peak(reps, tflops_out); }
 
 int dca_mf_corr_from_freqs(const double *reg_fi, const double *reg_fij, int seqs_len, int num_site_states,
                            double *corr_out)

@@ -42,8 +42,11 @@ int encode_residue(int biomolecule, int c);
 
 // ---- reweight.cu -----------------------------------------------------------------
 int reweight_min_ident(int L, double seqid, int compare_f64);
+// part >= 0: symmetric tiles, part `part` of `nparts` (partial counts of all N rows);
+// part < 0: rows [row_lo,row_hi) against all rows
 int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, int compare_f64,
-                           long row_lo, long row_hi, unsigned *d_counts, cudaStream_t stream);
+                           long row_lo, long row_hi, unsigned *d_counts, cudaStream_t stream,
+                           int part = -1, int nparts = 1);
 
 // ---- plm_eval.cu -------------------------------------------------------------------
 struct PlmProblem;   // device-resident state of one plmDCA objective

@@ -682,6 +682,57 @@ int mf_scores_host(const uint8_t *msa, const double *w, long N, int L, int q, do
     return rc;
 }
 
+// ---- measured FP64 tensor-pipe peak (the roofline denominator of the inverse) --------------
+// Register-only DMMA stream: every warp keeps 16 independent m8n8k4 accumulator pairs in
+// flight (no memory traffic), 8 warps per CTA, enough CTAs to fill every SM several times.
+__global__ void __launch_bounds__(256)
+fp64_mma_peak_kernel(double *__restrict__ sink, int iters)
+{
+    double acc[16][2];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dmma_m8n8k4(acc[k][0], acc[k][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += acc[k][0] + acc[k][1];
+    if (s == -1.0) sink[0] = s;          // never true: keeps the loop alive
+}
+
+// best-of-reps TFLOP/s of mma.sync.m8n8k4.f64 (2*8*8*4 flops per warp instruction)
+int fp64_mma_peak(int reps, double *tflops_out)
+{
+    if (require_device() != 0) return -1;
+    if (reps < 1 || !tflops_out) { set_error("fp64_mma_peak: bad arguments"); return -1; }
+    cudaStream_t st;
+    DCA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    DevBuf<double> sink;
+    if (!sink.alloc(8)) { cudaStreamDestroy(st); return -1; }
+    const int iters = 4096, ctas = sm_count() * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int r = -1; r < reps; ++r) {
+        cudaEventRecord(e0, st);
+        DCA_LAUNCH(fp64_mma_peak_kernel, ctas, 256, 0, st, sink.p, iters);
+        cudaEventRecord(e1, st);
+        cudaStreamSynchronize(st);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 512.0 * 16.0 * iters * 8.0 * ctas;
+        if (r >= 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaError_t e = cudaGetLastError();
+    cudaStreamDestroy(st);
+    if (e != cudaSuccess) { set_error("fp64_mma_peak: %s", cudaGetErrorString(e)); return -1; }
+    *tflops_out = best;
+    return 0;
+}
+
 int mf_couplings_host(const double *corr, int n, double *out)
 {
     if (require_device() != 0) return -1;

@@ -19,10 +19,16 @@
 //   t = a ^ b ; u = t + 0x1f1f1f1f ; m = u & 0x20202020 ; acc = dp4a(m, 1, acc)
 // residues are < 32, so bit 5 of every byte of u is set iff that byte differs
 // (no carries between bytes); dp4a sums the four flags into a 32-bit counter.
+// Symmetric mode (sym = 1): ident(i,j) = ident(j,i), so only the tiles on and above the
+// diagonal are compared (row tile I against j >= 128*I) and a hit outside the diagonal block
+// counts for BOTH rows: half the compares.  Row tiles are dealt to `nparts` parts cyclically
+// (multi-GPU: part = rank; the partial count vectors add up to the full counts).
 // Roofline: integer-ALU bound (4 lane-ops per 4 residues), not HBM bound:
 // algorithmic bytes are N*L + 4N, ops N^2*L byte compares.
 #include "dca_common.cuh"
 #include "dca_internal.h"
+
+#include <algorithm>
 
 namespace dca {
 
@@ -33,17 +39,31 @@ constexpr int RW_STRIDE = 36;   // smem row stride in words (16B aligned, confli
 
 __global__ void __launch_bounds__(256)
 reweight_kernel(const uint32_t *__restrict__ msa_w, long N, long i_lo, long i_hi, int Lw,
-                long j_per_split, unsigned max_mismatch32, unsigned *__restrict__ counts)
+                long j_per_split, unsigned max_mismatch32, unsigned *__restrict__ counts,
+                int sym, int part, int nparts)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *Is = smem;                                   // [2][RW_TI][RW_STRIDE]
     uint32_t *Js = smem + 2 * RW_TI * RW_STRIDE;           // [2][RW_TJ][RW_STRIDE]
+    __shared__ unsigned jc[RW_TJ];                         // symmetric mode: hits per j row of the current tile
 
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
-    const long i0 = i_lo + (long)blockIdx.x * RW_TI;
-    const long jbeg = (long)blockIdx.y * j_per_split;
-    const long jend = min(N, jbeg + j_per_split);
+    long i0, jbeg, jend;
+    if (sym) {
+        // row tile `part + blockIdx.x * nparts` against j in [i0, N), that span cut into gridDim.y pieces
+        i0 = ((long)part + (long)blockIdx.x * nparts) * RW_TI;
+        i_lo = 0; i_hi = N;
+        const long span = N - i0;
+        const long per = ((span + gridDim.y - 1) / gridDim.y + RW_TJ - 1) / RW_TJ * RW_TJ;
+        jbeg = i0 + (long)blockIdx.y * per;
+        jend = min(N, jbeg + per);
+        if (tid < RW_TJ) jc[tid] = 0;
+    } else {
+        i0 = i_lo + (long)blockIdx.x * RW_TI;
+        jbeg = (long)blockIdx.y * j_per_split;
+        jend = min(N, jbeg + j_per_split);
+    }
     const int nk = (Lw + RW_KW - 1) / RW_KW;
 
     unsigned rowcount[8];
@@ -110,15 +130,35 @@ reweight_kernel(const uint32_t *__restrict__ msa_w, long N, long i_lo, long i_hi
             }
             __syncthreads();
         }
+        const bool mirror = sym && (j0 >= i0 + RW_TI);     // off the diagonal block: the hit counts for row j too
+        unsigned colhit[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             unsigned c = 0;
+            const bool vi = (i0 + ty + 16 * r) < i_hi;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const long gj = j0 + tx + 16 * s;
-                c += (gj < jend && acc[r][s] <= max_mismatch32) ? 1u : 0u;
+                const unsigned hit = (gj < jend && acc[r][s] <= max_mismatch32) ? 1u : 0u;
+                c += hit;
+                colhit[s] += vi ? hit : 0u;
             }
             rowcount[r] += c;
+        }
+        if (mirror) {                                      // block-uniform
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                unsigned c = colhit[s];
+                c += __shfl_xor_sync(0xffffffffu, c, 16);  // the two ty rows of this warp
+                if ((tid & 31) < 16 && c) atomicAdd(&jc[tx + 16 * s], c);
+            }
+            __syncthreads();
+            if (tid < RW_TJ) {
+                const unsigned c = jc[tid];
+                if (c) atomicAdd(counts + j0 + tid, c);    // j0 + tid < jend whenever c != 0
+                jc[tid] = 0;
+            }
+            __syncthreads();
         }
     }
     // reduce the 16 tx lanes that share a row (lanes 0-15 / 16-31 of a warp)
@@ -176,10 +216,19 @@ __global__ void pack_rows_kernel(const uint8_t *__restrict__ msa, long N, int L,
 // counts for rows [row_lo,row_hi) against all N rows (multi-GPU: row shards,
 // SURVEY 8e).  d_msa: u8 [N][L] on device; d_counts: u32 [N] (zeroed here for
 // the shard range only).
+// part >= 0: symmetric mode -- part `part` of `nparts` of the upper-triangular tile pairs;
+// d_counts [N] receives this part's PARTIAL counts of every row (nparts = 1: the counts).
+// part < 0: rows [row_lo, row_hi) against all N rows (full compares, counts of those rows only).
 int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, int compare_f64,
-                           long row_lo, long row_hi, unsigned *d_counts, cudaStream_t stream)
+                           long row_lo, long row_hi, unsigned *d_counts, cudaStream_t stream,
+                           int part, int nparts)
 {
     if (N <= 0 || L <= 0) { set_error("reweight: empty alignment (N=%ld L=%d)", N, L); return -1; }
+    const bool sym = part >= 0;
+    if (sym) {
+        if (nparts < 1 || part >= nparts) { set_error("reweight: bad part %d of %d", part, nparts); return -1; }
+        row_lo = 0; row_hi = N;
+    }
     const int Lw = (int)(ceil_div(L, 4) + 3) / 4 * 4;
     DevBuf<uint32_t> d_words;            // released on every return path
     DevBuf<unsigned> d_bad;
@@ -195,17 +244,24 @@ int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, in
     if (T <= L) {
         const unsigned max_mismatch32 = 32u * (unsigned)(L - T);
         const long rows = row_hi - row_lo;
-        const unsigned gx = (unsigned)ceil_div<long>(rows, RW_TI);
-        // split j so that the grid covers the SMs at least twice
-        int js = (int)ceil_div<long>(2L * sm_count(), gx);
+        unsigned gx = (unsigned)ceil_div<long>(rows, RW_TI);
+        if (sym) {
+            const long ntile = ceil_div<long>(N, RW_TI);
+            gx = (unsigned)((ntile - part + nparts - 1) / nparts);      // row tiles part, part + nparts, ...
+        }
+        // split j so that the grid covers the SMs at least twice (symmetric mode: row tile I has
+        // (N - 128 I) rows of j, so CTA costs fall off linearly; more, smaller CTAs balance that)
+        int js = (int)ceil_div<long>((sym ? 6L : 2L) * sm_count(), std::max(1u, gx));
         long jper = ceil_div<long>(ceil_div<long>(N, js), RW_TJ) * RW_TJ;
         js = (int)ceil_div<long>(N, jper);
         const size_t smem = sizeof(uint32_t) * 2 * (RW_TI + RW_TJ) * RW_STRIDE;
         // per-device attribute (a process may drive several GPUs): set on every call, it is cheap
         DCA_CUDA(cudaFuncSetAttribute(reweight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(gx, (unsigned)js);
-        DCA_LAUNCH(reweight_kernel, grid, 256, smem, stream,
-                   d_words, N, row_lo, row_hi, Lw, jper, max_mismatch32, d_counts);
+        if (gx > 0)
+            DCA_LAUNCH(reweight_kernel, grid, 256, smem, stream,
+                       d_words, N, row_lo, row_hi, Lw, jper, max_mismatch32, d_counts,
+                       sym ? 1 : 0, sym ? part : 0, sym ? nparts : 1);
     }
     DCA_CUDA(cudaGetLastError());
     unsigned h_bad = 0;

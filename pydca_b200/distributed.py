@@ -3,8 +3,9 @@ the collectives, nothing else from torch.
 
 How the hot path shards:
 
-* reweighting  -- rows are independent: rank r computes c_i for its row range against
-  the replicated MSA; one all-gather of N uint32 counts.
+* reweighting  -- the all-pairs comparison is symmetric: rank r takes every world-th 128-row
+  tile of the upper-triangular tile pairs against the replicated MSA (half the compares of
+  the reference's row decomposition); one all-reduce of N integer counts.
 * plmDCA       -- the loop-carried softmax chain is per site, so SITES are sharded,
   never sequences.  Default (``ShardedPlm``): rank r OWNS a contiguous site range and
   the slice of the parameter vector whose blocks J_ij start in it; the optimiser's
@@ -72,16 +73,21 @@ def make_allreduce_callback(stream_ptr, group=None, device=None):
     return ALLREDUCE_FN(_cb)
 
 
-def allgather_counts(local_counts, rows, num_seqs, group=None, device=None):
-    """Row-sharded reweighting: every rank passes its counts array (zeros outside its
-    rows); returns the complete uint32[N].  Works on CPU tensors (gloo) and CUDA (nccl)."""
+def allreduce_counts(partial_counts, group=None, device=None):
+    """Sum the ranks' partial neighbour counts (symmetric tile parts, or disjoint row shards)
+    into the complete uint32[N] on every rank.  Works on CPU tensors (gloo) and CUDA (nccl)."""
     import torch
     import torch.distributed as dist
-    t = torch.from_numpy(np.ascontiguousarray(local_counts, dtype=np.int64).copy())
+    t = torch.from_numpy(np.ascontiguousarray(partial_counts, dtype=np.int64).copy())
     if device is not None:
         t = t.to(device)
-    dist.all_reduce(t, group=group)           # disjoint row ranges: sum == gather
+    dist.all_reduce(t, group=group)
     return t.cpu().numpy().astype(np.uint32)
+
+
+def allgather_counts(local_counts, rows, num_seqs, group=None, device=None):
+    """Row-sharded variant: counts are zero outside this rank's rows, so the sum is a gather."""
+    return allreduce_counts(local_counts, group=group, device=device)
 
 
 #: below this many residue compares (N * N * L) every rank simply computes all counts itself:
@@ -89,15 +95,23 @@ def allgather_counts(local_counts, rows, num_seqs, group=None, device=None):
 REPLICATE_REWEIGHT_BELOW = 1.0e11
 
 
-def sharded_counts(msa, seqid, compare_f64=False, group=None, device=None, force_shard=False):
-    """c_i on every rank.  Deep alignments: row shard on this rank's GPU + one collective
-    (disjoint rows, so the sum is a gather).  Shallow ones: computed redundantly, no collective."""
+def sharded_counts(msa, seqid, compare_f64=False, group=None, device=None, force_shard=False,
+                   symmetric=True):
+    """c_i on every rank.  Deep alignments: this rank's share of the all-pairs comparison on its
+    GPU + one all-reduce of N integers.  symmetric=True (default): rank r takes the row tiles
+    r, r + world, ... of the UPPER-triangular tile pairs and every hit counts for both rows
+    (half the compares, balanced by the cyclic deal); symmetric=False: the reference's
+    decomposition, rows [rN/G, (r+1)N/G) against all rows (plmdca_numerics.cpp:633).
+    Shallow alignments: computed redundantly, no collective."""
     import torch.distributed as dist
     from . import _lib
     n, l = msa.shape
     if not force_shard and float(n) * n * l < REPLICATE_REWEIGHT_BELOW:
         return _lib.sequence_counts(msa, seqid, compare_f64=compare_f64)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if symmetric:
+        local = _lib.sequence_counts_part(msa, seqid, rank, world, compare_f64=compare_f64)
+        return allreduce_counts(local, group=group, device=device)
     lo, hi = shard_range(n, rank, world)
     local = _lib.sequence_counts(msa, seqid, compare_f64=compare_f64, rows=(lo, hi))
     return allgather_counts(local, (lo, hi), n, group=group, device=device)

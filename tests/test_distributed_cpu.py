@@ -181,13 +181,31 @@ def _worker(rank, world, port, out_dir):
         out = np.zeros_like(c)
         out[rows[0]:rows[1]] = c[rows[0]:rows[1]]
         return out
-    real = _lib.sequence_counts
-    _lib.sequence_counts = fake_counts
+    def fake_part(m, seqid, part, nparts, compare_f64=False, want_ms=False):
+        """numpy model of the symmetric kernel (csrc/reweight.cu, sym = 1): 128-row tiles dealt
+        cyclically; the diagonal block counts rows only, tiles right of it count both rows."""
+        calls.append(("part", part, nparts))
+        n, l = m.shape
+        thr = [k for k in range(l + 1) if np.float32(k) / np.float32(l) > np.float32(seqid)]
+        tmin = thr[0] if thr else l + 1
+        out = np.zeros(n, dtype=np.uint32)
+        for i0 in range(128 * part, n, 128 * nparts):
+            rows = m[i0:i0 + 128]
+            ident = (rows[:, None, :] == m[None, i0:, :]).sum(axis=2)        # j >= i0 only
+            hit = ident >= tmin
+            out[i0:i0 + rows.shape[0]] += hit.sum(axis=1).astype(np.uint32)
+            out[i0 + 128:] += hit[:, 128:].sum(axis=0).astype(np.uint32)     # mirrored counts
+        return out
+    real, real_part = _lib.sequence_counts, _lib.sequence_counts_part
+    _lib.sequence_counts, _lib.sequence_counts_part = fake_counts, fake_part
     try:
         assert (dd.sharded_counts(msa, 0.8) == full).all() and calls == [None]
-        assert (dd.sharded_counts(msa, 0.8, force_shard=True) == full).all() and calls[-1] == (lo, hi)
+        assert (dd.sharded_counts(msa, 0.8, force_shard=True, symmetric=False) == full).all() and calls[-1] == (lo, hi)
+        assert (dd.sharded_counts(msa, 0.8, force_shard=True) == full).all() and calls[-1] == ("part", rank, world)
+        big = synthetic_msa(700, 9, q, seed=5)                               # 6 row tiles over `world` parts
+        assert (dd.sharded_counts(big, 0.8, force_shard=True) == P.reweight_counts(big, 0.8)).all()
     finally:
-        _lib.sequence_counts = real
+        _lib.sequence_counts, _lib.sequence_counts_part = real, real_part
 
     # site-sharded objective: each rank's data term, all-reduce, regulariser added once
     w = P.plm_weights(full)
