@@ -1,11 +1,12 @@
 #!/usr/bin/env python
-"""bench.py -- plmDCA gradient-evaluations/second on the BASELINE workload.
+"""bench.py -- plmDCA gradient-evaluations/second on the BASELINE workload, plus the other
+half of BASELINE's metric (mfDCA end to end) and the large configurations as extra blocks.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1], "C2"): plmdca compute_fn protein on the seeded
+Headline workload (BASELINE.json configs[1], "C2"): plmdca compute_fn protein on the seeded
 synthetic MSA N=5000, L=150, q=21, seqid 0.8, lambda_h = lambda_J = 0.2(L-1),
 max_iterations = 500.
 
@@ -18,12 +19,21 @@ weights and work buffers resident in HBM; `e2e` = the same metric through the
 reference's own entry point plmdcaBackend(file, ...) with host buffers: FASTA parse,
 de-duplication, reweighting, H2D, fit and D2H of the result inside the timed region.
 
-At N > 1 GPUs the SAME fit is owner-sharded by sites (pydca_b200.distributed.ShardedPlm):
+Extra blocks of the N=1 line (each measured live in this run; --no-extras skips them):
+  parity    the fit against the frozen reference fit (tests/golden/plm_c2_fit.npz) in both
+            arithmetic modes: evaluation count, max-rel FN deviation, top-L overlap, next to the
+            reference's own nt=1 vs nt=all-cores band
+  mfdca     BASELINE configs[2] (N=20000, L=300): MeanFieldDCA(file).compute_sorted_FN_APC() end
+            to end incl. FASTA ingest and reweighting, site-pairs/s, per-stage CUDA-event ms, the
+            inverse against the MEASURED FP64 tensor-pipe peak, a CPU baseline of the same stages
+  reweight  BASELINE configs[4]'s all-pairs Hamming reweighting (N=200000, L=250) on one GPU
+  c4        BASELINE configs[3] (N=50000, L=500): a 10-iteration fit on one GPU
+
+At N > 1 GPUs the SAME C2 fit is owner-sharded by sites (pydca_b200.distributed.ShardedPlm):
 every rank owns a site range, the matching slice of the parameter vector and of the L-BFGS
 vectors; per evaluation only the cross blocks move, by P2P stores over NVLink fused into
-the unpack / export kernels, i.e. strong scaling.  DCA_B200_EXCHANGE=allreduce selects the
-older replicated-x path (one NCCL all-reduce of the gradient per evaluation); it is also
-the fallback if the peer arenas cannot be mapped.
+the unpack / export kernels, i.e. strong scaling.  The gathered result is compared with a
+single-GPU fit of the same input in the same run (`multi_gpu_check`).
 
 --impl reference times the reference's own OpenMP implementation (oracle/_ref, built
 from /root/reference unmodified) on the host cores: each step is a bounded sample
@@ -59,18 +69,22 @@ def workload(tmpdir):
     return msa, path, lam
 
 
-def config_dict(n_gpus, exchange=None):
-    par = "single GPU"
+def parallelism(n_gpus, exchange=None):
     if n_gpus > 1 and exchange == "peer":
-        par = ("owner-sharded sites x%d: P2P stores of the cross blocks (fused unpack/export kernels) + "
-               "flag barriers + rank-ordered float64 scalar sums over peer memory; no NCCL in the loop" % n_gpus)
-    elif n_gpus > 1:
-        par = "site-shard x%d + NCCL all-reduce(g) per evaluation" % n_gpus
+        return ("owner-sharded sites x%d: P2P stores of the cross blocks (fused unpack/export kernels) + "
+                "flag barriers + rank-ordered float64 scalar sums over peer memory; no NCCL in the loop" % n_gpus)
+    if n_gpus > 1:
+        return "site-shard x%d + NCCL all-reduce(g) per evaluation" % n_gpus
+    return "single GPU"
+
+
+def config_dict():
+    """The workload only (identical at every GPU count; how it is parallelised is reported
+    next to it as `parallelism`)."""
     return {"workload": "C2: plmdca compute_fn protein, synthetic MSA N=%d L=%d q=%d, seqid %.1f, "
                         "lambda_h=lambda_J=0.2(L-1), max_iterations=%d; one step = one full fit"
                         % (N_SEQ, SEQ_LEN, Q, SEQID, MAX_ITER),
             "N": N_SEQ, "L": SEQ_LEN, "q": Q, "max_iterations": MAX_ITER,
-            "parallelism": par,
             "l2": "working set per evaluation (W 40 MB + S 64 MB + G >= 40 MB + 16 L-BFGS vectors x 20 MB) "
                   "exceeds the 126 MB L2; no explicit flush"}
 
@@ -171,7 +185,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "plmdca_grad_evals_per_sec", "value": value, "unit": "evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(),
+            "parallelism": "host cores (OpenMP)",
             "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -231,7 +246,6 @@ def roofline_block(obj, x0, peaks):
     adds = N * L * Lq                                          # gather adds of logits == scatter
     top = max(ms, key=ms.get)
     hbm, hbm_source = find_hbm_peak(peaks)
-    achieved = bytes_k[top] / (ms[top] * 1e-3) / 1e9
     eval_bytes = 8 * P + N * L + 4 * N                          # SURVEY 8(d) per-evaluation figure
     total_ms = sum(ms.values())
     sm_clock_ghz = 1965.0 / 1e3                                # clocks.max.sm of the B200 (bench records the live clock too)
@@ -248,20 +262,30 @@ def roofline_block(obj, x0, peaks):
         traffic_src = tj["source"]
     except Exception:
         pass
-    out = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-           "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src,
-           "peak_source": hbm_source,
+    # What binds the dominant kernel (ncu, profiles/): the shared-memory pipe -- every add of the
+    # gather / scatter kernels needs one 4-byte operand selected by a residue, one LDS word.
+    gadds = {"logits": adds / (ms["logits"] * 1e-3) / 1e9, "scatter": adds / (ms["scatter"] * 1e-3) / 1e9}
+    top_gather = top if top in gadds else max(gadds, key=lambda k: ms[k])
+    out = {"bound": "smem", "kernel": top_gather,
+           "achieved": gadds[top_gather], "peak": smem_peak, "unit": "Gword/s (shared-memory operand words = adds)",
+           "frac": gadds[top_gather] / smem_peak,
+           "traffic": traffic, "traffic_source": traffic_src,
+           "peak_source": "148 SMs x 32 LDS words/clk x %.3f GHz (clocks.max.sm)" % sm_clock_ghz,
+           "fp32_lane": {"note": "same kernel against the FP32-lane roof (148 x 128 lanes)",
+                         "achieved_gops": gadds[top_gather], "peak_gops": lane_peak, "frac": gadds[top_gather] / lane_peak},
+           "hbm": {"note": "secondary: SURVEY 8(d) algorithmic bytes of one evaluation (8P + N*L + 4N) over the "
+                           "CUDA-event time of its kernels vs the measured HBM peak; small by construction "
+                           "(intensity ~117 adds/byte vs a ridge of ~6)",
+                   "algorithmic_bytes": eval_bytes, "ms": total_ms,
+                   "achieved": eval_bytes / (total_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                   "frac": eval_bytes / (total_ms * 1e-3) / 1e9 / hbm, "peak_source": hbm_source},
            "kernel_ms": ms, "kernel_share": {k: v / total_ms for k, v in ms.items()},
-           "algorithmic_bytes": bytes_k,
-           "eval": {"algorithmic_bytes": eval_bytes, "ms": total_ms,
-                    "achieved": eval_bytes / (total_ms * 1e-3) / 1e9, "frac": eval_bytes / (total_ms * 1e-3) / 1e9 / hbm},
-           "on_chip": {"note": "logits/scatter are shared-memory-gather bound (1 LDS word per add), not HBM bound",
-                       "gather_adds_per_kernel": adds,
-                       "logits_gadds_per_s": adds / (ms["logits"] * 1e-3) / 1e9,
-                       "scatter_gadds_per_s": adds / (ms["scatter"] * 1e-3) / 1e9,
+           "kernel_algorithmic_bytes": bytes_k,
+           "on_chip": {"gather_adds_per_kernel": adds,
+                       "logits_gadds_per_s": gadds["logits"], "scatter_gadds_per_s": gadds["scatter"],
                        "smem_roof_gwords_per_s": smem_peak, "fp32_lane_roof_gops": lane_peak,
-                       "logits_frac_of_smem_roof": adds / (ms["logits"] * 1e-3) / 1e9 / smem_peak,
-                       "scatter_frac_of_smem_roof": adds / (ms["scatter"] * 1e-3) / 1e9 / smem_peak,
+                       "logits_frac_of_smem_roof": gadds["logits"] / smem_peak,
+                       "scatter_frac_of_smem_roof": gadds["scatter"] / smem_peak,
                        "eval_frac_of_fp32_lane_roof": 2 * adds / (total_ms * 1e-3) / 1e9 / lane_peak}}
     # the HBM-bound part of the path: the two L-BFGS vector passes of one iteration (m = 5)
     try:
@@ -284,6 +308,182 @@ def roofline_block(obj, x0, peaks):
     except Exception as exc:
         out["hbm_bound_kernels"] = {"error": repr(exc)}
     return out
+
+
+def fn_scores(x, L, q):
+    from pydca_b200 import _lib
+    return _lib.plm_fn_apc(x, L, q)[0]
+
+
+def parity_block(msa, w, lam):
+    """The C2 fit in both arithmetic modes against the frozen reference fit
+    (tests/golden/plm_c2_fit.npz: the unmodified reference's lbfgs() + PlmDCA::gradient at
+    num_threads = 1 and = all cores, written by tests/golden/make_c2_fit.py)."""
+    from pydca_b200 import _lib
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "plm_c2_fit.npz"))
+    ref = gold["nt1_fn"].astype(np.float64)
+    refN = gold["ntN_fn"].astype(np.float64)
+    top = np.argsort(-ref, kind="stable")[:SEQ_LEN]
+    out = {"golden": "tests/golden/plm_c2_fit.npz (reference at num_threads=1)",
+           "reference": {"evaluations": int(gold["nt1_evaluations"]), "status": int(gold["nt1_status"]),
+                         "fx": float(gold["nt1_fx"]),
+                         "self_band_fn_max_rel": float(np.max(np.abs(refN - ref) / ref)),
+                         "self_band_note": "reference num_threads=1 vs num_threads=%d" % int(gold["ntN_threads"])},
+           "tolerance": "north_star: 1e-5 relative on FN scores"}
+    obj = _lib.PlmObjective(msa, w, Q, lam, lam)
+    try:
+        for mode in ("reference", "accurate"):
+            obj.set_arithmetic(mode)
+            x0 = obj.init()
+            obj.fit(x0, MAX_ITER)                                   # warm
+            x, res = obj.fit(x0, MAX_ITER)
+            fn = fn_scores(x, SEQ_LEN, Q)
+            out["arithmetic_" + mode] = {
+                "evaluations": res.evaluations, "iterations": res.iterations, "status": res.status, "fx": res.fx,
+                "fn_max_rel_dev": float(np.max(np.abs(fn - ref) / ref)),
+                "topL_overlap": int(len(set(top.tolist()) & set(np.argsort(-fn, kind="stable")[:SEQ_LEN].tolist()))),
+                "topL": SEQ_LEN, "evals_per_s": res.evaluations / (res.device_ms * 1e-3), "fit_ms": res.device_ms}
+    finally:
+        obj.close()
+    out["explanation"] = ("the reference sums its inner products and the L2 term sequentially in float32 over all P; "
+                          "that bias (1.8 % of |g|^2 here) steers its L-BFGS trajectory. arithmetic=reference "
+                          "reproduces those sums bit for bit (csrc/seqsum.cu); arithmetic=accurate (default, the "
+                          "headline) uses float64 reductions and lands where the reference itself lands when "
+                          "built with float64 sums (DESIGN.md section 6)")
+    return out
+
+
+def mfdca_block(tmp, peaks):
+    """BASELINE configs[2]: mfdca compute_fn protein, N=20000 L=300 (n = 6000), pseudocount 0.5,
+    through the class a user calls, FASTA file in, sorted FN-APC list out."""
+    from pydca_b200 import _lib, msa_numerics
+    from pydca_b200.meanfield_dca import MeanFieldDCA
+    from pydca_b200.synthetic import synthetic_msa, write_fasta
+    N, L, pc = 20000, 300, 0.5
+    n = L * (Q - 1)
+    npairs = L * (L - 1) // 2
+    msa = synthetic_msa(N, L, Q)
+    path = write_fasta(msa, os.path.join(tmp, "c3_N%d_L%d.fa" % (N, L)), Q)
+    MeanFieldDCA(path, "protein", pseudocount=pc, seqid=SEQID).compute_sorted_FN_APC()      # warm
+    reps, walls, stages, t_ctor = 3, [], None, []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        inst = MeanFieldDCA(path, "protein", pseudocount=pc, seqid=SEQID)
+        t1 = time.perf_counter()
+        scores = inst.compute_sorted_FN_APC()
+        walls.append(time.perf_counter() - t0)
+        t_ctor.append(t1 - t0)
+        stages = inst.last_stage_ms
+    assert len(scores) == npairs
+    wall = float(np.median(walls))
+    # device-resident part alone (MSA + weights already on the host as arrays)
+    counts = _lib.sequence_counts(msa, SEQID, compare_f64=True)
+    w = 1.0 / counts.astype(np.float64)
+    res = msa_numerics.mean_field_scores(msa, Q, w, pc)
+    res = msa_numerics.mean_field_scores(msa, Q, w, pc)
+    st = {k: float(v) for k, v in zip(("pair_freqs_and_h2d", "covariance", "inverse", "frobenius_norm", "direct_info"),
+                                      res["stage_ms"])}
+    dev_s = 1e-3 * sum(st.values())
+    peak = _lib.fp64_mma_peak(5)
+    inv_tflops = float(n) ** 3 / (st["inverse"] * 1e-3) / 1e12
+    hbm, hbm_src = find_hbm_peak(peaks)
+    hist_bytes = N * L + 8 * N + 8 * n * n
+    out = {"workload": "C3: mfdca compute_fn protein, synthetic MSA N=%d L=%d q=%d, pseudocount %.1f, seqid %.1f "
+                       "(n = %d covariance)" % (N, L, Q, pc, SEQID, n),
+           "e2e_seconds": wall, "pairs_per_s": npairs / wall, "site_pairs": npairs,
+           "e2e_call": "MeanFieldDCA(msa_file, 'protein', pseudocount, seqid).compute_sorted_FN_APC(): FASTA parse + "
+                       "dedup + reweighting + H2D + frequencies + covariance + inverse + FN + D2H (couplings kept, "
+                       "as compute_params needs them) + APC + sort",
+           "constructor_seconds": float(np.median(t_ctor)), "stage_ms_in_call": stages,
+           "device_resident": {"seconds": dev_s, "pairs_per_s": npairs / dev_s, "stage_ms": st,
+                               "call": "dca_mf_scores on host arrays (weights given), scores only"},
+           "inverse": {"flops": float(n) ** 3, "note": "symmetric blocked Gauss-Jordan: n^3 flops (Cholesky+potri count)",
+                       "achieved_tflops": inv_tflops, "peak_tflops": peak,
+                       "peak_source": "measured in this run: register-only mma.sync.m8n8k4.f64 stream on all SMs "
+                                      "(dca_fp64_mma_peak)", "frac": inv_tflops / peak},
+           "pair_histogram": {"algorithmic_bytes": hist_bytes, "ms": st["pair_freqs_and_h2d"],
+                              "achieved_gbs": hist_bytes / (st["pair_freqs_and_h2d"] * 1e-3) / 1e9, "peak_gbs": hbm,
+                              "frac": hist_bytes / (st["pair_freqs_and_h2d"] * 1e-3) / 1e9 / hbm,
+                              "note": "SURVEY 8(d): N*L + 8N + 8n^2 bytes; stage time includes the H2D of the MSA"}}
+    # CPU baseline of the same stages: numpy restatement of the reference's numba functions
+    # (oracle/mf_oracle.py) on a row subsample for the O(N) stages, the full 6000^2 inverse
+    try:
+        from oracle import mf_oracle
+        import oracle
+        nsub = 2000
+        t0 = time.perf_counter()
+        c_sub = oracle.port().reweight_counts_rows(msa, SEQID, np.arange(nsub, dtype=np.int64), f64=True)
+        t_rw = (time.perf_counter() - t0) * (N / nsub)
+        wsub = 1.0 / c_sub.astype(np.float64)
+        t0 = time.perf_counter()
+        fi = mf_oracle.reg_single_site_freqs(mf_oracle.single_site_freqs(msa[:nsub], Q, wsub), Q, pc)
+        fij = mf_oracle.reg_pair_site_freqs(mf_oracle.pair_site_freqs(msa[:nsub], Q, wsub), Q, pc)
+        t_freq = (time.perf_counter() - t0) * (N / nsub)
+        t0 = time.perf_counter()
+        C = mf_oracle.construct_corr_mat(fi, fij, L, Q)
+        t_corr = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        np.linalg.inv(C)
+        t_inv = time.perf_counter() - t0
+        total = t_rw + t_freq + t_corr + t_inv
+        out["cpu_baseline"] = {"value": total, "unit": "s", "cores": os.cpu_count() or 1, "kind": "port",
+                               "pairs_per_s": npairs / total,
+                               "stage_s": {"reweight": t_rw, "frequencies": t_freq, "covariance": t_corr, "inverse": t_inv},
+                               "sample": "oracle (numpy / C restatement of meanfield_dca/msa_numerics.py): reweighting and "
+                                         "frequencies on the first %d of %d sequences, extrapolated linearly in N (the "
+                                         "work is exactly linear in rows); covariance assembly and numpy.linalg.inv at "
+                                         "full size" % (nsub, N)}
+    except Exception as exc:
+        out["cpu_baseline"] = {"value": None, "kind": "unavailable", "sample": repr(exc)}
+    return out
+
+
+def reweight_block():
+    """All-pairs Hamming reweighting at BASELINE configs[4]'s size on one GPU (symmetric tiles)."""
+    from pydca_b200 import _lib
+    from pydca_b200.synthetic import synthetic_msa
+    out = {}
+    for tag, N, L in (("c2", N_SEQ, SEQ_LEN), ("c5", 200000, 250)):
+        msa = synthetic_msa(N, L, Q)
+        _lib.sequence_counts_part(msa, SEQID, 0, 1)
+        ms = min(_lib.sequence_counts_part(msa, SEQID, 0, 1, want_ms=True)[1] for _ in range(3))
+        compares = float(N) * N * L
+        lane_ops = compares / 4.0
+        sm_clock_ghz = 1.965
+        floor_ms = lane_ops / (148 * 128 * sm_clock_ghz * 1e9) * 1e3
+        out[tag] = {"N": N, "L": L, "device_ms": ms, "byte_compares_per_s": compares / (ms * 1e-3),
+                    "packed_lane_floor_ms": floor_ms, "frac_of_packed_lane_floor": floor_ms / ms,
+                    "note": "floor = N^2 L / 4 packed lane-ops at 148 x 128 lanes x 1.965 GHz (SURVEY 8d); the kernel "
+                            "spends 4 integer ops per 4 residues (xor, add, and, dp4a) on HALF the pairs (symmetric tiles)"}
+    return out
+
+
+def c4_block():
+    """BASELINE configs[3] on ONE GPU: N=50000, L=500 (P = 55 M): a 10-iteration fit."""
+    from pydca_b200 import _lib
+    from pydca_b200.synthetic import synthetic_msa
+    N, L = 50000, 500
+    lam = 0.2 * (L - 1)
+    msa = synthetic_msa(N, L, Q)
+    counts = _lib.sequence_counts(msa, SEQID)
+    w = (1.0 / counts.astype(np.float32)).astype(np.float32)
+    obj = _lib.PlmObjective(msa, w, Q, lam, lam)
+    try:
+        x0 = obj.init()
+        obj.fit(x0, 2)
+        _, res = obj.fit(x0, 10)
+        ms = obj.eval_timed(x0)
+        ms = obj.eval_timed(x0)
+        ms.pop("export", None)
+        adds = float(N) * L * L * Q
+        smem_peak = 148 * 32 * 1.965
+        return {"workload": "C4 on one GPU: plmdca N=%d L=%d q=%d, first 10 L-BFGS iterations" % (N, L, Q),
+                "evals_per_s": res.evaluations / (res.device_ms * 1e-3), "evaluations": res.evaluations,
+                "fit_ms": res.device_ms, "kernel_ms": ms,
+                "logits_frac_of_smem_roof": adds / (ms["logits"] * 1e-3) / 1e9 / smem_peak,
+                "scatter_frac_of_smem_roof": adds / (ms["scatter"] * 1e-3) / 1e9 / smem_peak}
+    finally:
+        obj.close()
 
 
 def run_ours(args, rank, world, local_rank):
@@ -392,6 +592,8 @@ def run_ours(args, rank, world, local_rank):
         # peer wiring -> fit -> NCCL all-gather -> full parameter vector on the host
         dev = torch.device("cuda", local_rank)
 
+        last_x = [None]
+
         def e2e_call(report):
             ta = time.perf_counter()
             c2 = dd.sharded_counts(msa, SEQID, device=dev)
@@ -415,6 +617,7 @@ def run_ours(args, rank, world, local_rank):
                 x_full, r2 = o2.fit(o2.init(), MAX_ITER, allreduce=cb2)
                 o2.close()
             assert x_full.size == obj.P
+            last_x[0] = x_full
             return r2.evaluations
 
         e2e_call(False)                      # warm: pinned staging buffers, NCCL channels for these sizes
@@ -434,16 +637,46 @@ def run_ours(args, rank, world, local_rank):
                "call": "per rank: host MSA -> reweight (replicated below 1e11 compares, else row-sharded + "
                        "all-reduce) -> sharded create + CUDA IPC wiring -> fit -> NCCL all-gather -> full x on the host"}
 
+    # ---- numerical check of the real multi-GPU run: the gathered parameters of the sharded fit
+    # against a single-GPU fit of the same input on rank 0's GPU, in this run
+    multi_check = None
+    if world > 1:
+        if rank == 0:
+            try:
+                solo = _lib.PlmObjective(msa, w, Q, lam, lam)
+                xs, rs = solo.fit(solo.init(), MAX_ITER)
+                solo.close()
+                fn_m, fn_s = fn_scores(last_x[0], SEQ_LEN, Q), fn_scores(xs, SEQ_LEN, Q)
+                multi_check = {"evaluations_single_gpu": rs.evaluations, "evaluations_multi_gpu": int(e_evals // n_e2e),
+                               "fn_max_rel_dev_vs_single_gpu": float(np.max(np.abs(fn_m - fn_s) / np.abs(fn_s))),
+                               "x_max_abs_dev": float(np.max(np.abs(last_x[0] - xs))),
+                               "x_max_abs": float(np.max(np.abs(xs))),
+                               "note": "gathered x of the %d-GPU owner-sharded fit vs a 1-GPU fit of the same MSA "
+                                       "(same decisions, different reduction grouping across ranks)" % world}
+            except Exception as exc:
+                multi_check = {"error": repr(exc)}
+        barrier()
+
     if rank == 0:
         line = {"metric": "plmdca_grad_evals_per_sec", "value": evals / (dev_ms * 1e-3), "unit": "evals/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world, exchange),
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(),
+                "parallelism": parallelism(world, exchange), "arithmetic": "accurate (float64 fixed-order reductions); see parity",
                 "evals_per_step": evals / max(1, args.steps), "lbfgs_status": status, "lbfgs_iterations": iters,
                 "wall_ms_per_step": 1e3 * wall / max(1, args.steps),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
+        if multi_check is not None:
+            line["multi_gpu_check"] = multi_check
         if world == 1:
             line["roofline"] = roofline_block(obj, x0, peaks)
+            if not args.no_extras:
+                for name, fn in (("parity", lambda: parity_block(msa, w, lam)), ("mfdca", lambda: mfdca_block(tmp, peaks)),
+                                 ("reweight", reweight_block), ("c4", c4_block)):
+                    try:
+                        line[name] = fn()
+                    except Exception as exc:          # an extra block never takes the headline down
+                        line[name] = {"error": repr(exc)}
             cores = os.cpu_count() or 1
             try:
                 ev, dt, kind, cores = cpu_reference_fit(path, lam, CPU_BASELINE_ITERS, cores)
@@ -474,6 +707,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the parity / mfdca / reweight / c4 blocks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -100,8 +100,11 @@ int dca_plm_set_carry(dca_plm *p, int carry, int chunk, int warm);
  *     from the reference's by a few 1e-4, exactly as the reference's own would with
  *     float64 sums.
  * Single-GPU handles only.  plmdcaBackend() picks the mode from DCA_B200_ARITHMETIC
- * (reference | accurate; default reference). */
+ * (accurate | reference; default accurate). */
 int dca_plm_set_fidelity(dca_plm *p, int mode);
+/* process-wide choice for plmdcaBackend(): 0 accurate, 1 reference, -1 back to the environment
+ * variable.  (The reference's entry point has no room for an extra argument.) */
+int dca_set_arithmetic(int mode);
 /* test / measurement hook of that kernel on HOST buffers: *out = the sequential float32
  * dot product of x and y (y != NULL), or the sequential L2 accumulation of x with lambda0 on
  * the first n0 entries and lambda1 on the rest (y == NULL). */

@@ -96,6 +96,7 @@ def lib():
     L.dca_plm_num_params.restype = ctypes.c_long
     L.dca_plm_set_carry.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.dca_plm_set_fidelity.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.dca_set_arithmetic.argtypes = [ctypes.c_int]
     L.dca_seq_sum.argtypes = [_f32p, _f32p, ctypes.c_long, ctypes.c_long, ctypes.c_float, ctypes.c_float, _f32p]
     L.dca_plm_init.argtypes = [ctypes.c_void_p, _f32p]
     L.dca_plm_eval.argtypes = [ctypes.c_void_p, _f32p, _f32p, _f64p]
@@ -332,6 +333,17 @@ def plm_fn_apc(x, seqs_len, num_site_states):
     check(lib().dca_plm_fn_apc(ptr(x, _f32p), int(seqs_len), int(num_site_states), ptr(fn, _f64p),
                                ptr(apc, _f64p)), "dca_plm_fn_apc")
     return fn, apc
+
+
+ARITHMETIC_MODES = {"accurate": 0, "reference": 1, None: -1}
+
+
+def set_backend_arithmetic(mode):
+    """Arithmetic of plmdcaBackend() for this process: 'accurate', 'reference' or None (follow
+    the DCA_B200_ARITHMETIC environment variable; default accurate)."""
+    if mode not in ARITHMETIC_MODES:
+        raise ValueError("arithmetic must be 'accurate', 'reference' or None, got %r" % (mode,))
+    check(lib().dca_set_arithmetic(ARITHMETIC_MODES[mode]), "dca_set_arithmetic")
 
 
 def seq_dot(x, y):

@@ -16,7 +16,7 @@
 #include <vector>
 
 #ifndef DCA_DEFAULT_ARITHMETIC
-#define DCA_DEFAULT_ARITHMETIC 1      /* 1 = reference, 0 = accurate */
+#define DCA_DEFAULT_ARITHMETIC 0      /* 1 = reference, 0 = accurate */
 #endif
 
 namespace dca {
@@ -100,10 +100,15 @@ static std::vector<std::pair<std::string, void *>> g_ipc_open;
 
 extern "C" void dca_plm_destroy(dca_plm *p);
 
-// arithmetic of plmdcaBackend(): DCA_B200_ARITHMETIC = reference (the reference's sequential
-// float32 sums: its trajectory, FN within ~1e-6) | accurate (float64 reductions, faster)
+// arithmetic of plmdcaBackend(): DCA_B200_ARITHMETIC = accurate (default: float64 reductions,
+// fastest; FN a few 1e-4 from the reference's, like the reference's own with float64 sums) |
+// reference (the reference's sequential float32 sums bit for bit: its trajectory, FN ~1e-6)
+static std::atomic<int> g_arithmetic{-1};      // dca_set_arithmetic(): overrides the environment
+
 static int backend_arithmetic()
 {
+    const int forced = g_arithmetic.load();
+    if (forced == 0 || forced == 1) return forced;
     const char *e = getenv("DCA_B200_ARITHMETIC");
     if (e && (strcmp(e, "accurate") == 0 || strcmp(e, "0") == 0)) return 0;
     if (e && (strcmp(e, "reference") == 0 || strcmp(e, "1") == 0)) return 1;
@@ -315,6 +320,13 @@ int dca_plm_set_carry(dca_plm *p, int carry, int chunk, int warm)
 {
     if (!p) { set_error("null handle"); return -1; }
     plm_set_carry(p->prob, carry, chunk, warm);
+    return 0;
+}
+
+int dca_set_arithmetic(int mode)
+{
+    if (mode < -1 || mode > 1) { set_error("dca_set_arithmetic: mode must be -1 (environment), 0 (accurate) or 1 (reference)"); return -1; }
+    g_arithmetic.store(mode);
     return 0;
 }
 

@@ -46,7 +46,14 @@ class PlmDCA:
     """Pseudolikelihood-maximisation DCA on one B200 (plmdca.py:25)."""
 
     def __init__(self, msa_file, biomolecule, seqid=None, lambda_h=None, lambda_J=None,
-                 max_iterations=None, num_threads=None, verbose=False):
+                 max_iterations=None, num_threads=None, verbose=False, arithmetic=None):
+        # arithmetic (not in the reference): 'accurate' (float64 reductions, fastest), 'reference' (the
+        # reference's sequential float32 sums bit for bit -> its L-BFGS trajectory, FN within ~1e-6;
+        # one GPU) or None = the DCA_B200_ARITHMETIC environment variable (default accurate)
+        if arithmetic not in _lib.ARITHMETIC_MODES:
+            logger.error("\n\tInvalid arithmetic mode {}".format(arithmetic))
+            raise PlmDCAException
+        self.__arithmetic = arithmetic
         self.__biomolecule = biomolecule.strip().upper()
         if self.__biomolecule not in ("PROTEIN", "RNA"):
             logger.error("\n\tInvalid biomolecule type {}".format(self.__biomolecule))
@@ -133,6 +140,7 @@ class PlmDCA:
         """float32[P]: fields then couplings, through the reference's C ABI."""
         logger.info("\n\tComputing fields and couplings using gradient decent")
         lib = _lib.lib()
+        _lib.set_backend_arithmetic(self.__arithmetic)
         h_j_ptr = lib.plmdcaBackend(
             self.__biomolecule_int, self.__num_site_states, self.__msa_file.encode("utf-8"),
             self.__seqs_len, self.__seqid, self.__lambda_h, self.__lambda_J, self.__max_iterations,

@@ -34,13 +34,13 @@ def _reject_refseq(refseq_file):
 def execute_from_command_line(biomolecule, msa_file, the_command=None, refseq_file=None, seqid=None,
                               lambda_h=None, lambda_J=None, max_iterations=None, apc=False, verbose=False,
                               output_dir=None, num_threads=None, ranked_by=None, linear_dist=None,
-                              num_site_pairs=None):
+                              num_site_pairs=None, arithmetic=None):
     """pydca/plmdca_main.py:136-256."""
     if verbose:
         configure_logging()
     _reject_refseq(refseq_file)
     inst = PlmDCA(msa_file, biomolecule, seqid=seqid, lambda_h=lambda_h, lambda_J=lambda_J,
-                  max_iterations=max_iterations, num_threads=num_threads, verbose=verbose)
+                  max_iterations=max_iterations, num_threads=num_threads, verbose=verbose, arithmetic=arithmetic)
     if the_command not in DCA_COMPUTATION_SUBCOMMANDS:
         return None
     meta = dca_utilities.plmdca_param_metadata(inst)
@@ -100,6 +100,9 @@ def build_parser():
         p.add_argument("--refseq_file", help="FASTA file containing a reference sequence")
         p.add_argument("--verbose", action="store_true", help="Show logging information on the terminal")
         p.add_argument("--output_dir", help="Directory path to which output results are written")
+        p.add_argument("--arithmetic", choices=("accurate", "reference"),
+                       help="accurate: float64 reductions (default, fastest); reference: the reference's sequential "
+                            "float32 sums bit for bit, i.e. its own L-BFGS trajectory (not a flag of the reference)")
         if name != "compute_params":
             p.add_argument("--apc", action="store_true", help="Compute the average product corrected (APC) scores")
         else:
@@ -120,7 +123,7 @@ def run_plm_dca(argv=None):
                               max_iterations=args.get("max_iterations"), num_threads=args.get("num_threads"),
                               apc=args.get("apc"), output_dir=args.get("output_dir"), verbose=args.get("verbose"),
                               ranked_by=args.get("ranked_by"), linear_dist=args.get("linear_dist"),
-                              num_site_pairs=args.get("num_site_pairs"))
+                              num_site_pairs=args.get("num_site_pairs"), arithmetic=args.get("arithmetic"))
     return None
 
 
