@@ -496,6 +496,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     torch = None
     saved_stdout = None
+    cpu_group = None
     if world > 1:
         # stdout must carry exactly ONE line (the JSON): NCCL prints its version banner there when
         # NCCL_DEBUG asks for it, so everything up to the final print goes to stderr instead
@@ -506,6 +507,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")     # host-side barriers: no kernel parked on idle GPUs
     tmp = tempfile.mkdtemp(prefix="dca_bench_")
     msa, path, lam = workload(tmp)
     peaks = {}
@@ -541,6 +543,11 @@ def run_ours(args, rank, world, local_rank):
         if dist is not None:
             dist.barrier()
 
+    def cpu_barrier():
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)
+
     for _ in range(args.warmup):
         obj.fit(x0, MAX_ITER, allreduce=cb)
 
@@ -570,6 +577,7 @@ def run_ours(args, rank, world, local_rank):
     e2e = None
     if world == 1:
         n_e2e = max(1, min(args.steps, 5))
+        _lib.set_backend_gpus(1)              # the box may show more GPUs than this run is about
         _lib.plmdca_backend(path, "protein", SEQ_LEN, Q, SEQID, lam, lam, MAX_ITER)      # warm (page cache, context)
         e_evals = 0
         per_call = []
@@ -588,54 +596,33 @@ def run_ours(args, rank, world, local_rank):
                "ms_per_step": 1e3 * e_wall / n_e2e, "steps": n_e2e,
                "call": "plmdcaBackend(msa_file, ...) -> float*: FASTA parse + dedup + reweight + H2D + fit + D2H"}
     else:
-        # sharded end-to-end, host buffers in and out on every rank: MSA -> reweight -> sharded create +
-        # peer wiring -> fit -> NCCL all-gather -> full parameter vector on the host
-        dev = torch.device("cuda", local_rank)
-
+        # end to end at N GPUs through the SAME entry point: rank 0 calls plmdcaBackend(file, ...) with
+        # DCA_B200_GPUS = N (one host thread per GPU inside the call, peer-memory exchange, every GPU
+        # copying its slice into the returned host vector); the other ranks' processes stay idle
         last_x = [None]
-
-        def e2e_call(report):
-            ta = time.perf_counter()
-            c2 = dd.sharded_counts(msa, SEQID, device=dev)
-            w2 = (1.0 / c2.astype(np.float32)).astype(np.float32)
-            t_rw = time.perf_counter()
-            if exchange == "peer":
-                sp2 = dd.ShardedPlm(msa, w2, Q, lam, lam)
-                t_mk = time.perf_counter()
-                _, r2 = sp2.fit(MAX_ITER)
-                t_fit = time.perf_counter()
-                x_full = sp2.gather()
-                t_ga = time.perf_counter()
-                sp2.close()
-                if report and rank == 0:
-                    print("e2e stages ms: reweight %.1f setup %.1f %s fit %.1f gather %.1f close %.1f"
-                          % (1e3 * (t_rw - ta), 1e3 * (t_mk - t_rw), {k: round(v, 1) for k, v in sp2.trace.items()},
-                             1e3 * (t_fit - t_mk), 1e3 * (t_ga - t_fit), 1e3 * (time.perf_counter() - t_ga)), file=sys.stderr)
-            else:
-                o2 = _lib.PlmObjective(msa, w2, Q, lam, lam, sites=dd.shard_range(SEQ_LEN, rank, world))
-                cb2 = dd.make_allreduce_callback(o2.cuda_stream())
-                x_full, r2 = o2.fit(o2.init(), MAX_ITER, allreduce=cb2)
-                o2.close()
-            assert x_full.size == obj.P
-            last_x[0] = x_full
-            return r2.evaluations
-
-        e2e_call(False)                      # warm: pinned staging buffers, NCCL channels for these sizes
         n_e2e = max(1, min(args.steps, 3))
-        barrier()
-        t0 = time.perf_counter()
-        e_evals = 0
-        for k in range(n_e2e):
-            e_evals += e2e_call(k == n_e2e - 1)
-        barrier()
-        e_wall = time.perf_counter() - t0
-        t = torch.tensor([e_wall], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": e_evals / float(t[0]), "unit": "evals/s",
-               "h2d_bytes_per_step": 2 * N_SEQ * SEQ_LEN + 4 * N_SEQ,
-               "d2h_bytes_per_step": 4 * N_SEQ + 4 * obj.P, "ms_per_step": 1e3 * float(t[0]) / n_e2e, "steps": n_e2e,
-               "call": "per rank: host MSA -> reweight (replicated below 1e11 compares, else row-sharded + "
-                       "all-reduce) -> sharded create + CUDA IPC wiring -> fit -> NCCL all-gather -> full x on the host"}
+        e_evals, e_wall = 0, 0.0
+        cpu_barrier()
+        if rank == 0:
+            _lib.set_backend_gpus(world)
+            _lib.plmdca_backend(path, "protein", SEQ_LEN, Q, SEQID, lam, lam, MAX_ITER)      # warm: contexts, arenas
+            per_call = []
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                t1 = time.perf_counter()
+                last_x[0] = _lib.plmdca_backend(path, "protein", SEQ_LEN, Q, SEQID, lam, lam, MAX_ITER)
+                e_evals += _lib.last_fit().evaluations
+                per_call.append(1e3 * (time.perf_counter() - t1))
+            e_wall = time.perf_counter() - t0
+            print("e2e per-call ms (%d GPUs): " % world + " ".join("%.1f" % v for v in per_call), file=sys.stderr)
+        cpu_barrier()
+        if rank == 0:
+            e2e = {"value": e_evals / e_wall, "unit": "evals/s",
+                   "h2d_bytes_per_step": world * (2 * N_SEQ * SEQ_LEN + 4 * N_SEQ),
+                   "d2h_bytes_per_step": 4 * N_SEQ + 4 * obj.P, "ms_per_step": 1e3 * e_wall / n_e2e, "steps": n_e2e,
+                   "call": "plmdcaBackend(msa_file, ...) -> float* with DCA_B200_GPUS=%d: FASTA parse + dedup + reweight + "
+                           "per-GPU H2D + owner-sharded fit (one host thread per GPU, peer-memory exchange) + per-GPU "
+                           "D2H of its slice into the returned host vector" % world}
 
     # ---- numerical check of the real multi-GPU run: the gathered parameters of the sharded fit
     # against a single-GPU fit of the same input on rank 0's GPU, in this run
@@ -655,7 +642,7 @@ def run_ours(args, rank, world, local_rank):
                                        "(same decisions, different reduction grouping across ranks)" % world}
             except Exception as exc:
                 multi_check = {"error": repr(exc)}
-        barrier()
+        cpu_barrier()
 
     if rank == 0:
         line = {"metric": "plmdca_grad_evals_per_sec", "value": evals / (dev_ms * 1e-3), "unit": "evals/s",

@@ -39,12 +39,18 @@ unsigned long long dca_kernel_launches(void); /* kernels launched by this librar
  * (plmdca_numerics.cpp:338-342).  The buffer is host memory owned by the
  * library; release it with freeFieldsAndCouplings (plmdcaBackend.cpp:204).
  * num_threads is accepted for signature compatibility and ignored (the work
- * runs on the GPU).  Returns NULL on error (the reference aborts instead). */
+ * runs on the GPU).  Returns NULL on error (the reference aborts instead).
+ * GPUs: the call drives DCA_B200_GPUS GPUs of this node (default: all visible; dca_set_gpus
+ * overrides) -- one host thread per GPU inside this one call, owner-sharded sites, peer-memory
+ * exchange, every GPU copying its slice of the result into the returned vector.  Falls back to
+ * one GPU when peer access is unavailable. */
 float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states,
                      const char *msa_file, unsigned int seqs_len, float seqid,
                      float lambda_h, float lambda_J, unsigned int max_iteration,
                      unsigned int num_threads, bool verbose);
 void freeFieldsAndCouplings(void *h_and_J);
+/* process-wide GPU count for plmdcaBackend(): n >= 1, or 0 = DCA_B200_GPUS / all visible */
+int dca_set_gpus(int n);
 
 /* ---- FASTA ingest (host logic) ----------------------------------------------
  * plmdca_numerics.cpp:685-767 / fasta_reader.py:122-163: upper-case, encode to

@@ -97,6 +97,7 @@ def lib():
     L.dca_plm_set_carry.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.dca_plm_set_fidelity.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.dca_set_arithmetic.argtypes = [ctypes.c_int]
+    L.dca_set_gpus.argtypes = [ctypes.c_int]
     L.dca_seq_sum.argtypes = [_f32p, _f32p, ctypes.c_long, ctypes.c_long, ctypes.c_float, ctypes.c_float, _f32p]
     L.dca_plm_init.argtypes = [ctypes.c_void_p, _f32p]
     L.dca_plm_eval.argtypes = [ctypes.c_void_p, _f32p, _f32p, _f64p]
@@ -344,6 +345,11 @@ def set_backend_arithmetic(mode):
     if mode not in ARITHMETIC_MODES:
         raise ValueError("arithmetic must be 'accurate', 'reference' or None, got %r" % (mode,))
     check(lib().dca_set_arithmetic(ARITHMETIC_MODES[mode]), "dca_set_arithmetic")
+
+
+def set_backend_gpus(n):
+    """GPUs plmdcaBackend() drives in this process (0 = DCA_B200_GPUS, default all visible)."""
+    check(lib().dca_set_gpus(int(n)), "dca_set_gpus")
 
 
 def seq_dot(x, y):

@@ -8,11 +8,14 @@
 #include "dca_internal.h"
 #include "../../include/dca_b200.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <ctime>
+#include <condition_variable>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #ifndef DCA_DEFAULT_ARITHMETIC
@@ -104,6 +107,18 @@ extern "C" void dca_plm_destroy(dca_plm *p);
 // fastest; FN a few 1e-4 from the reference's, like the reference's own with float64 sums) |
 // reference (the reference's sequential float32 sums bit for bit: its trajectory, FN ~1e-6)
 static std::atomic<int> g_arithmetic{-1};      // dca_set_arithmetic(): overrides the environment
+static std::atomic<int> g_gpus{0};             // dca_set_gpus(): overrides DCA_B200_GPUS (0 = environment)
+
+// how many GPUs plmdcaBackend() drives: dca_set_gpus() > DCA_B200_GPUS > all visible
+static int backend_gpus(int L)
+{
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess) { cudaGetLastError(); visible = 1; }
+    int want = g_gpus.load();
+    if (want <= 0) { const char *e = getenv("DCA_B200_GPUS"); want = e ? atoi(e) : visible; }
+    if (want <= 0) want = visible;
+    return std::max(1, std::min(std::min(want, visible), std::min(L, (int)XR_MAX_RANKS)));
+}
 
 static int backend_arithmetic()
 {
@@ -330,6 +345,13 @@ int dca_set_arithmetic(int mode)
     return 0;
 }
 
+int dca_set_gpus(int n)
+{
+    if (n < 0) { set_error("dca_set_gpus: n must be >= 0 (0 = DCA_B200_GPUS / all visible)"); return -1; }
+    g_gpus.store(n);
+    return 0;
+}
+
 int dca_plm_set_fidelity(dca_plm *p, int mode)
 {
     if (!p) { set_error("null handle"); return -1; }
@@ -448,6 +470,191 @@ int dca_plm_fn_apc(const float *x_host, int seqs_len, int num_site_states, doubl
     return plm_fn_apc_host(x_host, seqs_len, num_site_states, fn_out, fn_apc_out);
 }
 
+// ---- several GPUs behind the reference's entry point -------------------------------------
+// plmdcaBackend() is what stock pydca calls (plmdcaBackend.cpp:151); it is one synchronous call
+// in one process.  With G > 1 GPUs it starts one host thread per GPU: each creates its
+// owner-sharded objective (sites [bounds[r], bounds[r+1])), enables peer access, hands its
+// arena pointer to the others (same address space: no IPC), runs the same collective L-BFGS
+// as the one-process-per-GPU path, and copies ITS slice of the result straight into the
+// caller's host vector over its own PCIe link -- no gather collective at all.
+namespace {
+
+class ThreadBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n, waiting = 0;
+    unsigned long gen = 0;
+public:
+    explicit ThreadBarrier(int count) : n(count) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned long g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+struct MgShared {
+    int G = 1;
+    const uint8_t *msa = nullptr;
+    long N = 0;
+    int L = 0, q = 0;
+    float lh = 0.f, lJ = 0.f;
+    double seqid = 0.8;
+    int max_it = 0, verbose = 0;
+    bool deep_reweight = false;
+    std::vector<int> bounds;
+    std::vector<std::vector<uint32_t>> partial;     // symmetric reweighting parts (deep alignments)
+    std::vector<float> w;
+    void *arenas[XR_MAX_RANKS] = {nullptr};
+    float *x_host = nullptr;
+    std::atomic<int> err{0};
+    ThreadBarrier *bar = nullptr;
+    LbfgsResult res0{};
+    double timed_ms = 0.0;
+    int timed_evals = 0;
+    double stage_ms[4] = {0, 0, 0, 0};              // rank 0: reweight, create+wire, fit, d2h
+};
+
+static double wall_ms()
+{
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+}
+
+static void mg_worker(MgShared *S, int r)
+{
+    PlmProblem *prob = nullptr;
+    float *d_x = nullptr;
+    auto fail = [&](const char *what) {
+        S->err.store(1);
+        fprintf(stderr, "plmdcaBackend: GPU %d: %s: %s\n", r, what, last_error());
+    };
+    double t0 = wall_ms();
+    if (cudaSetDevice(r) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", r); fail("device"); }
+    for (int p = 0; p < S->G && !S->err.load(); ++p) {
+        if (p == r) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, r, p);
+        if (!can) { set_error("GPU %d cannot access GPU %d's memory (no P2P)", r, p); fail("peer access"); break; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(p, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+            set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", r, p, cudaGetErrorString(e)); fail("peer access"); break;
+        }
+        cudaGetLastError();
+    }
+    // ---- reweighting: deep alignments split the symmetric tile pairs over the GPUs -------------
+    if (S->deep_reweight && !S->err.load()) {
+        DevBuf<uint8_t> d_msa;
+        DevBuf<unsigned> d_counts;
+        S->partial[r].assign((size_t)S->N, 0u);
+        if (!d_msa.alloc((size_t)S->N * S->L) || !d_counts.alloc((size_t)S->N) ||
+            cudaMemcpy(d_msa, S->msa, (size_t)S->N * S->L, cudaMemcpyHostToDevice) != cudaSuccess ||
+            reweight_counts_device(d_msa, S->N, S->L, S->seqid, 0, 0, S->N, d_counts, 0, r, S->G) != 0 ||
+            cudaMemcpy(S->partial[r].data(), d_counts.p, sizeof(unsigned) * (size_t)S->N, cudaMemcpyDeviceToHost) != cudaSuccess)
+            fail("reweighting");
+    }
+    S->bar->wait();
+    if (S->deep_reweight && r == 0 && !S->err.load()) {
+        for (long n = 0; n < S->N; ++n) {
+            unsigned c = 0;
+            for (int p = 0; p < S->G; ++p) c += S->partial[p][(size_t)n];
+            S->w[(size_t)n] = 1.f / (float)c;                                    // plmdca_numerics.cpp:669
+        }
+    }
+    S->bar->wait();
+    if (r == 0) { S->stage_ms[0] = wall_ms() - t0; t0 = wall_ms(); }
+    // ---- owner-sharded objective + peer wiring -------------------------------------------------------
+    if (!S->err.load()) {
+        prob = plm_create_sharded(S->msa, S->w.data(), S->N, S->L, S->q, S->lh, S->lJ, r, S->G, S->bounds.data());
+        if (!prob) fail("create");
+        else S->arenas[r] = plm_arena(prob);
+    }
+    S->bar->wait();
+    if (!S->err.load() && plm_connect(prob, S->arenas, true) != 0) fail("connect");
+    if (!S->err.load()) {
+        d_x = static_cast<float *>(dev_alloc(sizeof(float) * (size_t)plm_local_params(prob)));
+        if (!d_x) fail("allocation");
+    }
+    S->bar->wait();                       // every arena is known everywhere before the first push
+    if (r == 0) { S->stage_ms[1] = wall_ms() - t0; t0 = wall_ms(); }
+    // ---- collective fit; on an error every rank still reaches the barriers below (a dead peer
+    // shows up as the 4 s flag time-out inside the kernels, not as a hang)
+    if (!S->err.load()) {
+        LbfgsResult res{};
+        double tms = 0.0;
+        int tev = 0;
+        if (plm_init_x_device(prob, d_x) != 0 ||
+            lbfgs_minimize(prob, d_x, S->max_it, (r == 0) ? S->verbose : 0, nullptr, nullptr, &res, 0, &tms, &tev) != 0)
+            fail("fit");
+        else if (r == 0) { S->res0 = res; S->timed_ms = tms; S->timed_evals = tev; }
+    }
+    if (r == 0) { S->stage_ms[2] = wall_ms() - t0; t0 = wall_ms(); }
+    if (!S->err.load()) {
+        long lay[4];
+        plm_local_layout(prob, lay);
+        cudaStream_t st = plm_stream(prob);
+        if (cudaMemcpyAsync(S->x_host + lay[0], d_x, sizeof(float) * (size_t)lay[1], cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(S->x_host + lay[2], d_x + lay[1], sizeof(float) * (size_t)lay[3], cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            set_error("D2H of the slice of GPU %d failed: %s", r, cudaGetErrorString(cudaGetLastError()));
+            fail("d2h");
+        }
+    }
+    S->bar->wait();                       // nobody releases an arena a peer may still push into
+    if (r == 0) S->stage_ms[3] = wall_ms() - t0;
+    if (prob) { cudaStreamSynchronize(plm_stream(prob)); plm_disconnect(prob); }
+    dev_free(d_x);
+    if (prob) plm_destroy(prob);
+}
+
+// contiguous, balanced site ranges (distributed.py: shard_range)
+static std::vector<int> even_bounds(int L, int G)
+{
+    std::vector<int> b((size_t)G + 1, 0);
+    const int base = L / G, extra = L % G;
+    for (int r = 0; r < G; ++r) b[(size_t)r + 1] = b[(size_t)r] + base + (r < extra ? 1 : 0);
+    return b;
+}
+
+// returns 0 and fills x_host / res on success; -1 when the multi-GPU path could not run
+static int backend_multi_gpu(int G, const std::vector<uint8_t> &msa, std::vector<float> &w, bool have_w, long N, int L,
+                             int q, double seqid, float lh, float lJ, int max_it, int verbose, float *x_host,
+                             dca_fit_result *res, bool trace)
+{
+    int saved = 0;
+    cudaGetDevice(&saved);
+    MgShared S;
+    S.G = G; S.msa = msa.data(); S.N = N; S.L = L; S.q = q; S.lh = lh; S.lJ = lJ; S.seqid = seqid;
+    S.max_it = max_it; S.verbose = verbose;
+    S.deep_reweight = !have_w;
+    S.bounds = even_bounds(L, G);
+    S.partial.resize((size_t)G);
+    S.w.swap(w);
+    if (!have_w) S.w.assign((size_t)N, 0.f);
+    S.x_host = x_host;
+    ThreadBarrier bar(G);
+    S.bar = &bar;
+    std::vector<std::thread> th;
+    for (int r = 1; r < G; ++r) th.emplace_back(mg_worker, &S, r);
+    mg_worker(&S, 0);
+    for (auto &t : th) t.join();
+    cudaSetDevice(saved);
+    w.swap(S.w);
+    if (trace)
+        fprintf(stderr, "[dca trace] %d GPUs: reweight %.2f ms, create+wire %.2f ms, fit %.2f ms, d2h %.2f ms\n",
+                G, S.stage_ms[0], S.stage_ms[1], S.stage_ms[2], S.stage_ms[3]);
+    if (S.err.load()) return -1;
+    res->status = S.res0.status; res->iterations = S.res0.iterations; res->evaluations = S.res0.evaluations;
+    res->fx = S.res0.fx; res->device_ms = S.res0.device_ms; res->timed_ms = S.timed_ms;
+    res->timed_evaluations = S.timed_evals;
+    return 0;
+}
+
+}  // namespace
+
 // ---- the reference's own entry point -------------------------------------------
 float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states, const char *msa_file,
                      unsigned int seqs_len, float seqid, float lambda_h, float lambda_J,
@@ -474,14 +681,46 @@ float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states,
     const long N = read_fasta_unique(msa_file, biomolecule == 1 ? 1 : 2, L, msa);       // plmdca_numerics.cpp:43
     if (N <= 0) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); return nullptr; }
     mark("read_fasta");
-    std::vector<uint32_t> counts((size_t)N);
-    if (dca_weights(msa.data(), N, L, (double)seqid, 0, 0, N, counts.data()) != 0) {    // :45
-        fprintf(stderr, "plmdcaBackend: %s\n", last_error());
-        return nullptr;
+    // GPUs: DCA_B200_GPUS / dca_set_gpus(), default all visible; the reference-arithmetic mode is
+    // single-GPU (its sequential sums span the whole vector)
+    int G = backend_gpus(L);
+    if (G > 1 && backend_arithmetic() == 1) {
+        if (verbose) fprintf(stderr, "plmdcaBackend: arithmetic=reference runs on one GPU\n");
+        G = 1;
     }
-    mark("reweight");
+    const bool deep = (double)N * (double)N * (double)L >= 1.0e11;    // reweighting worth splitting over the GPUs
     std::vector<float> w((size_t)N);
-    for (long n = 0; n < N; ++n) w[n] = 1.f / (float)counts[n];                          // :669
+    if (!(G > 1 && deep)) {
+        std::vector<uint32_t> counts((size_t)N);
+        if (dca_weights(msa.data(), N, L, (double)seqid, 0, 0, N, counts.data()) != 0) {    // :45
+            fprintf(stderr, "plmdcaBackend: %s\n", last_error());
+            return nullptr;
+        }
+        for (long n = 0; n < N; ++n) w[n] = 1.f / (float)counts[n];                          // :669
+        mark("reweight");
+    }
+    if (G > 1) {
+        const size_t Pm = (size_t)L * q + (size_t)L * (L - 1) / 2 * q * q;
+        float *xm = (float *)host_pinned_alloc(sizeof(float) * Pm);
+        if (!xm) { fprintf(stderr, "ERROR: Failed to allocate a memory block for variables.\n"); return nullptr; }
+        dca_fit_result resm{};
+        if (backend_multi_gpu(G, msa, w, !deep, N, L, q, (double)seqid, lambda_h, lambda_J, (int)max_iteration,
+                              verbose ? 1 : 0, xm, &resm, trace) == 0) {
+            mark("multi-gpu");
+            t_last_fit = resm;
+            return xm;
+        }
+        host_pinned_free(xm);
+        fprintf(stderr, "plmdcaBackend: the %d-GPU path failed (%s); using one GPU\n", G, last_error());
+        if (deep) {     // weights were to be computed by the workers
+            std::vector<uint32_t> counts((size_t)N);
+            if (dca_weights(msa.data(), N, L, (double)seqid, 0, 0, N, counts.data()) != 0) {
+                fprintf(stderr, "plmdcaBackend: %s\n", last_error());
+                return nullptr;
+            }
+            for (long n = 0; n < N; ++n) w[n] = 1.f / (float)counts[n];
+        }
+    }
     dca_plm *h = dca_plm_create(msa.data(), w.data(), N, L, q, lambda_h, lambda_J, 0, L);
     if (!h) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); return nullptr; }
     mark("create");

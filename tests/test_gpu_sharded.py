@@ -179,3 +179,33 @@ def test_unconnected_shard_fails_loudly(port):
     o.close()
     with pytest.raises(_lib.DcaBackendError):
         _lib.PlmObjective(msa, w, 5, 1.0, 1.0, shard=(0, 2, [0, 6, 6]))      # a rank without sites
+
+
+def test_plmdca_backend_drives_several_gpus(tmp_path):
+    """The reference's own entry point with DCA_B200_GPUS > 1 (plmdcaBackend.cpp:151: one synchronous
+    call; here one host thread per GPU inside it, peer-memory exchange over NVLink, every GPU
+    copying its slice into the returned vector).  Needs >= 2 devices: skipped on a 1-GPU box."""
+    from pydca_b200 import _lib
+    from pydca_b200.synthetic import synthetic_msa, write_fasta
+    ngpu = _lib.lib().dca_device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    N, L, q = 1500, 41, 21
+    lam = 0.2 * (L - 1)
+    msa = synthetic_msa(N, L, q, seed=123)
+    path = write_fasta(msa, str(tmp_path / "multi.fa"), q)
+    try:
+        _lib.set_backend_gpus(1)
+        x1 = _lib.plmdca_backend(path, "protein", L, q, 0.8, lam, lam, 40, copy=True)
+        r1 = _lib.last_fit()
+        for g in sorted({2, min(ngpu, 4), ngpu}):
+            _lib.set_backend_gpus(g)
+            xg = _lib.plmdca_backend(path, "protein", L, q, 0.8, lam, lam, 40, copy=True)
+            rg = _lib.last_fit()
+            assert (rg.status, rg.iterations, rg.evaluations) == (r1.status, r1.iterations, r1.evaluations), g
+            fn1, _ = _lib.plm_fn_apc(x1, L, q)
+            fng, _ = _lib.plm_fn_apc(xg, L, q)
+            assert relmax(fng, fn1) <= 5e-6, g
+            assert relmax(xg, x1) <= 5e-5, g
+    finally:
+        _lib.set_backend_gpus(0)
