@@ -4,7 +4,7 @@
 // (W, S, G, perm, 16 L-BFGS vectors).  cudaMalloc / cudaFree cost milliseconds
 // each and cudaFree synchronises the device, which dominated the end-to-end time
 // of repeated plmdcaBackend() calls.  Freed blocks are kept (per device, exact
-// size) and handed back on the next request; the cache is capped and is
+// size) and handed back on the next request; the cache is capped per device and is
 // released when an allocation fails.  Callers free a block only after the
 // stream that used it has been synchronised, so reuse needs no stream tracking.
 #include "dca_common.cuh"
@@ -17,19 +17,21 @@
 namespace dca {
 
 namespace {
+constexpr int MAX_DEV = 64;
 struct Cache {
     std::mutex mu;
     std::multimap<std::pair<int, size_t>, void *> free_blocks;
     std::unordered_map<void *, std::pair<int, size_t>> live;
-    size_t cached = 0;
-    size_t cap = 0;
+    size_t cached[MAX_DEV] = {0};      // per device: a process may drive several GPUs
+    size_t cap = 0;                    // per device
 };
 Cache &cache()
 {
     static Cache c;
     if (c.cap == 0) {
         const char *e = getenv("DCA_B200_CACHE_MB");
-        c.cap = (e ? (size_t)atol(e) : (size_t)8192) << 20;
+        // config 4 (N=50000, L=500) needs ~11 GB of work buffers on one B200 (180 GB of HBM)
+        c.cap = (e ? (size_t)atol(e) : (size_t)24576) << 20;
     }
     return c;
 }
@@ -37,7 +39,7 @@ void release_locked(Cache &c)
 {
     for (auto &kv : c.free_blocks) cudaFree(kv.second);
     c.free_blocks.clear();
-    c.cached = 0;
+    for (auto &v : c.cached) v = 0;
 }
 }  // namespace
 
@@ -54,7 +56,7 @@ void *dev_alloc(size_t bytes)
     if (it != c.free_blocks.end()) {
         p = it->second;
         c.free_blocks.erase(it);
-        c.cached -= bytes;
+        c.cached[dev & (MAX_DEV - 1)] -= bytes;
     } else {
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess) {
@@ -81,9 +83,10 @@ void dev_free(void *p)
     if (it == c.live.end()) { cudaFree(p); return; }
     const auto key = it->second;
     c.live.erase(it);
-    if (c.cached + key.second <= c.cap) {
+    size_t &cached = c.cached[key.first & (MAX_DEV - 1)];
+    if (cached + key.second <= c.cap) {
         c.free_blocks.insert({key, p});
-        c.cached += key.second;
+        cached += key.second;
     } else {
         cudaFree(p);
     }

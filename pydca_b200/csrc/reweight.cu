@@ -251,7 +251,9 @@ int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, in
         }
         // split j so that the grid covers the SMs at least twice (symmetric mode: row tile I has
         // (N - 128 I) rows of j, so CTA costs fall off linearly; more, smaller CTAs balance that)
-        int js = (int)ceil_div<long>((sym ? 6L : 2L) * sm_count(), std::max(1u, gx));
+        // (4 CTAs are resident per SM; symmetric CTAs get ~12 waves of work, at least 4 j tiles each)
+        int js = (int)ceil_div<long>((sym ? 48L : 2L) * sm_count(), std::max(1u, gx));
+        if (sym) js = (int)std::max<long>(1, std::min<long>(js, N / (4 * RW_TJ)));
         long jper = ceil_div<long>(ceil_div<long>(N, js), RW_TJ) * RW_TJ;
         js = (int)ceil_div<long>(N, jper);
         const size_t smem = sizeof(uint32_t) * 2 * (RW_TI + RW_TJ) * RW_STRIDE;

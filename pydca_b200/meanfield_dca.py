@@ -63,9 +63,10 @@ class MeanFieldDCA:
         self.__effective_num_sequences = np.sum(self.__sequences_weight)
         self.__couplings = None
         self.__refseq_mapping_dict = None
-        #: keep the n x n couplings matrix on the host after scoring (needed by compute_params;
-        #: set False to skip the 8 n^2-byte D2H when only scores are wanted)
-        self.keep_couplings = True
+        #: copy the n x n couplings matrix to the host when scoring (8 n^2 bytes: 288 MB at L=300).
+        #: The scoring methods do not need it; compute_params (the only consumer, meanfield_dca.py:
+        #: 661-752) switches it on for its own call
+        self.keep_couplings = False
         self.last_stage_ms = None
         logger.info("Created a MeanFieldDCA object: %s, q %d, pseudocount %s, seqid %s, L %d, N %d, Meff %s",
                     biomolecule, self.__num_site_states, self.__pseudocount, self.__seqid,
@@ -124,9 +125,11 @@ class MeanFieldDCA:
         return self.__msa0.astype(np.int32) + 1
 
     def compute_sequences_weight(self):
-        """meanfield_dca.py:350-375."""
+        """meanfield_dca.py:350-375 (float64 compare, msa_numerics.py:46); the zero-based uint8
+        alignment goes to the device as it is."""
         logger.info("\n\tComputing sequences weights")
-        return msa_numerics.compute_sequences_weight(alignment_data=self._alignment_data(), seqid=self.__seqid)
+        counts = _lib.sequence_counts(self.__msa0, self.__seqid, compare_f64=True)
+        return 1.0 / counts.astype(np.float64)
 
     def get_single_site_freqs(self):
         logger.info("\n\tComputing single site frequencies")
@@ -221,8 +224,8 @@ class MeanFieldDCA:
         """meanfield_dca.py:793-830 -> {(i, j): DI}."""
         logger.info("\n\tComputing direct information")
         res = msa_numerics.mean_field_scores(self.__msa0, self.__num_site_states, self.__sequences_weight,
-                                             self.__pseudocount, want_couplings=True, want_di=True)
-        self.__couplings = res["couplings"]
+                                             self.__pseudocount, want_couplings=self.keep_couplings, want_di=True)
+        self.__couplings = res.get("couplings")
         self.last_stage_ms = self._stage_dict(res["stage_ms"])
         di = res["di"]
         iu, ju = np.triu_indices(self.__sequences_len, k=1)
@@ -274,7 +277,11 @@ class MeanFieldDCA:
         if ranked_by not in methods:
             logger.error("\n\tInvalid ranking criterion {}.\nChoose from {}".format(ranked_by, tuple(methods)))
             raise MeanFieldDCAException
-        dca_scores = methods[ranked_by](seqbackmapper=seqbackmapper)
+        keep, self.keep_couplings = self.keep_couplings, True
+        try:
+            dca_scores = methods[ranked_by](seqbackmapper=seqbackmapper)
+        finally:
+            self.keep_couplings = keep
         fields = self.compute_fields(couplings=self.__couplings)
         qm1 = self.__num_site_states - 1
         if seqbackmapper is not None:

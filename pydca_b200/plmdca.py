@@ -24,22 +24,30 @@ class PlmDCAException(Exception):
 def _sorted_pairs(scores, seqs_len):
     """[((i, j), score), ...] sorted like ``sorted(..., reverse=True)``: descending,
     ties keep (i, j) order (plmdca.py:478)."""
+    scores = np.asarray(scores)
     iu, ju = np.triu_indices(seqs_len, k=1)
-    items = [((int(i), int(j)), s) for i, j, s in zip(iu, ju, scores.tolist())]
-    return sorted(items, key=lambda k: k[1], reverse=True)
+    order = np.argsort(-scores, kind="stable")
+    return list(zip(zip(iu[order].tolist(), ju[order].tolist()), scores[order].tolist()))
 
 
 def average_product_correction(sorted_scores, seqs_len):
-    """plmdca.py:503-521 / meanfield_dca.py:969-984 on a [((i,j),score)] list."""
+    """plmdca.py:503-521 / meanfield_dca.py:969-984 on a [((i,j),score)] list.  The reference sums,
+    for every site, the scores of the pairs containing it in the order of the sorted list; the
+    unbuffered np.add.at below adds in exactly that order, with plain float64 additions as
+    sum() did on the Pythons the reference ran on (3.12's sum() is compensated: <= 1 ulp apart)."""
     n = seqs_len
+    pairs = np.array([p for p, _ in sorted_scores], dtype=np.int64).reshape(-1, 2)
+    vals = np.array([s for _, s in sorted_scores], dtype=np.float64)
     site_sum = np.zeros(n, dtype=np.float64)
-    for (i, j), s in sorted_scores:
-        site_sum[i] += s
-        site_sum[j] += s
+    np.add.at(site_sum, pairs.ravel(), np.repeat(vals, 2))
     av = site_sum / float(n - 1)
-    av_all = sum(av.tolist()) / float(n)
-    out = [(pair, score - av[pair[0]] * (av[pair[1]] / av_all)) for pair, score in sorted_scores]
-    return sorted(out, key=lambda k: k[1], reverse=True)
+    tot = 0.0
+    for v in av.tolist():          # plain left-to-right float sum (the reference's Python 3.5-3.7 sum())
+        tot += v
+    av_all = tot / float(n)
+    corrected = vals - av[pairs[:, 0]] * (av[pairs[:, 1]] / av_all)
+    order = np.argsort(-corrected, kind="stable")
+    return [(sorted_scores[k][0], v) for k, v in zip(order.tolist(), corrected[order].tolist())]
 
 
 class PlmDCA:
