@@ -110,6 +110,9 @@ static std::atomic<int> g_arithmetic{-1};      // dca_set_arithmetic(): override
 static std::atomic<int> g_gpus{0};             // dca_set_gpus(): overrides DCA_B200_GPUS (0 = environment)
 
 // how many GPUs plmdcaBackend() drives: dca_set_gpus() > DCA_B200_GPUS > all visible
+static int backend_gpus(int L);
+int dca::backend_gpu_count(int limit) { return backend_gpus(limit); }
+
 static int backend_gpus(int L)
 {
     int visible = 0;

@@ -35,6 +35,10 @@ struct DevBuf {
 int make_tensor_map_2d(void *out_CUtensorMap, int elem_bytes, const void *base, unsigned long long dim0,
                        unsigned long long dim1, unsigned long long stride1_bytes, unsigned box0, unsigned box1);
 
+// ---- capi.cu ------------------------------------------------------------------
+// GPUs one call may drive: dca_set_gpus() > DCA_B200_GPUS > all visible, capped by `limit`
+int backend_gpu_count(int limit);
+
 // ---- fasta.cpp -----------------------------------------------------------------
 // FASTA -> u8 [N][L] (states 0..q-1, gap q-1), unique rows in first-occurrence order.
 long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uint8_t> &out);

@@ -21,6 +21,8 @@
 #include "dca_internal.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 namespace dca {
@@ -33,12 +35,12 @@ constexpr int MF_HW = 8;           // warps per CTA of the histogram kernel
 template <int Q>
 __global__ void __launch_bounds__(128)
 mf_site_buckets_kernel(const uint8_t *__restrict__ msa, long N, int L, unsigned *__restrict__ rows,
-                       unsigned *__restrict__ off)
-{
+                       unsigned *__restrict__ off, int site_lo, int site_hi)
+{   // sites [site_lo, site_hi) only (multi-GPU: every GPU buckets the sites it histograms)
     __shared__ unsigned cnt[4][Q + 1];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = blockIdx.x * 4 + wib;
-    if (i >= L) return;
+    const int i = site_lo + blockIdx.x * 4 + wib;
+    if (i >= site_hi) return;
     if (lane <= Q) cnt[wib][lane] = 0;
     __syncwarp();
     for (long n = lane; n < N; n += 32) atomicAdd(&cnt[wib][msa[n * L + i]], 1u);
@@ -78,11 +80,12 @@ template <int Q>
 __global__ void __launch_bounds__(MF_HW * 32)
 mf_pairhist_kernel(const uint8_t *__restrict__ msa, const double *__restrict__ w,
                    const unsigned *__restrict__ rows, const unsigned *__restrict__ off,
-                   long N, int L, int ld, double *__restrict__ F)
-{
+                   long N, int L, int ld, double *__restrict__ F, int site_lo)
+{   // F may live on ANOTHER GPU (multi-GPU mfDCA: every GPU stores the columns of its sites
+    // straight into the solver GPU's matrix over NVLink)
     __shared__ double bins[MF_HW][Q][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = blockIdx.y;
+    const int i = site_lo + blockIdx.y;
     const int njt = (L + 31) / 32;
     const int item = blockIdx.x * MF_HW + wib;
     if (item >= Q * njt) return;
@@ -482,20 +485,76 @@ struct MfWork {
     unsigned *d_rows = nullptr, *d_off = nullptr;     // per site: rows grouped by residue, group offsets
     double *d_w = nullptr, *d_F = nullptr, *d_fi = nullptr, *d_rfi = nullptr;
     int ld = 0, nsplit = 1;                           // one copy of F (the consumers' nsplit argument)
+    int gpus = 1;                                     // GPUs that computed the pair histograms
     size_t fstride = 0;
     double meff = 0.0;
     ~MfWork() { cudaDeviceSynchronize(); dev_free(d_msa); dev_free(d_rows); dev_free(d_off); dev_free(d_w); dev_free(d_F); dev_free(d_fi); dev_free(d_rfi); }
 };
 
 template <int Q>
-static int mf_pairfreq_t(MfWork &W, long N, int L)
+static int mf_pairfreq_range_t(const uint8_t *d_msa, const double *d_w, unsigned *d_rows, unsigned *d_off, long N, int L,
+                               int ld, double *d_F, int site_lo, int site_hi)
 {
-    DCA_LAUNCH((mf_site_buckets_kernel<Q>), ceil_div(L, 4), 128, 0, 0, W.d_msa, N, L, W.d_rows, W.d_off);
+    if (site_hi <= site_lo) return 0;
+    DCA_LAUNCH((mf_site_buckets_kernel<Q>), ceil_div(site_hi - site_lo, 4), 128, 0, 0, d_msa, N, L, d_rows, d_off,
+               site_lo, site_hi);
     const int njt = ceil_div(L, 32);
-    dim3 grid(ceil_div(Q * njt, MF_HW), L);
-    DCA_LAUNCH((mf_pairhist_kernel<Q>), grid, MF_HW * 32, 0, 0, W.d_msa, W.d_w, W.d_rows, W.d_off, N, L, W.ld, W.d_F);
+    dim3 grid(ceil_div(Q * njt, MF_HW), site_hi - site_lo);
+    DCA_LAUNCH((mf_pairhist_kernel<Q>), grid, MF_HW * 32, 0, 0, d_msa, d_w, d_rows, d_off, N, L, ld, d_F, site_lo);
     DCA_CUDA(cudaGetLastError());
     return 0;
+}
+
+static int mf_pairfreq_range(int q, const uint8_t *d_msa, const double *d_w, unsigned *d_rows, unsigned *d_off, long N,
+                             int L, int ld, double *d_F, int site_lo, int site_hi)
+{
+    return (q == 21) ? mf_pairfreq_range_t<21>(d_msa, d_w, d_rows, d_off, N, L, ld, d_F, site_lo, site_hi)
+                     : mf_pairfreq_range_t<5>(d_msa, d_w, d_rows, d_off, N, L, ld, d_F, site_lo, site_hi);
+}
+
+// Contiguous site ranges of equal histogram cost: site i costs the 32-site tiles holding some
+// j >= i, i.e. njt - i/32 (the kernel skips the tiles left of the diagonal).
+static std::vector<int> mf_site_bounds(int L, int G)
+{
+    const int njt = ceil_div(L, 32);
+    std::vector<double> cum((size_t)L + 1, 0.0);
+    for (int i = 0; i < L; ++i) cum[(size_t)i + 1] = cum[(size_t)i] + (double)(njt - i / 32);
+    std::vector<int> b((size_t)G + 1, L);
+    b[0] = 0;
+    for (int r = 1; r < G; ++r) {
+        const double target = cum[(size_t)L] * r / G;
+        int k = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+        b[(size_t)r] = std::min(L, std::max(k, b[(size_t)r - 1]));
+    }
+    return b;
+}
+
+// the pair histograms are independent per (site i, tile of j), so GPU r takes
+// the sites [bounds[r], bounds[r+1]) -- MSA and weights replicated -- and stores its columns of F
+// directly into the solver GPU's matrix (peer stores from the kernel; no gather step).  Ranks
+// are host threads of this call; GPU `home` (the caller's) owns F and does the rest of the pipeline.
+static void mf_pairfreq_worker(int dev, int home, const uint8_t *h_msa, const double *h_w, long N, int L, int q, int ld,
+                               double *d_F_home, int site_lo, int site_hi, std::atomic<int> *err)
+{
+    if (cudaSetDevice(dev) != cudaSuccess) { err->store(1); return; }
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, dev, home);
+    if (!can) { set_error("mf: GPU %d cannot access GPU %d's memory", dev, home); err->store(1); return; }
+    const cudaError_t pe = cudaDeviceEnablePeerAccess(home, 0);
+    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { set_error("mf: enabling peer access failed"); err->store(1); return; }
+    cudaGetLastError();
+    DevBuf<uint8_t> d_msa;
+    DevBuf<double> d_w;
+    DevBuf<unsigned> d_rows, d_off;
+    if (!d_msa.alloc((size_t)N * L) || !d_w.alloc((size_t)N) || !d_rows.alloc((size_t)L * N) ||
+        !d_off.alloc((size_t)L * (q + 1)) ||
+        cudaMemcpy(d_msa, h_msa, (size_t)N * L, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_w, h_w, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice) != cudaSuccess ||
+        mf_pairfreq_range(q, d_msa, d_w, d_rows, d_off, N, L, ld, d_F_home, site_lo, site_hi) != 0 ||
+        cudaDeviceSynchronize() != cudaSuccess) {
+        if (cudaPeekAtLastError() != cudaSuccess) set_error("mf: GPU %d: %s", dev, cudaGetErrorString(cudaGetLastError()));
+        err->store(1);
+    }
 }
 
 static int mf_prepare(MfWork &W, const uint8_t *msa, const double *w, long N, int L, int q)
@@ -519,7 +578,27 @@ static int mf_prepare(MfWork &W, const uint8_t *msa, const double *w, long N, in
         return -1;
     DCA_CUDA(cudaMemcpy(W.d_msa, msa, (size_t)N * L, cudaMemcpyHostToDevice));
     DCA_CUDA(cudaMemcpy(W.d_w, w, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice));
-    return (q == 21) ? mf_pairfreq_t<21>(W, N, L) : mf_pairfreq_t<5>(W, N, L);
+    // GPUs: DCA_B200_GPUS / dca_set_gpus (default all visible), worth it only for real work
+    int G = backend_gpu_count(L);
+    if ((double)N * L * L < 2.0e8) G = 1;
+    int home = 0;
+    DCA_CUDA(cudaGetDevice(&home));
+    if (G > 1 && home != 0) G = 1;                 // the helpers are devices 1..G-1
+    W.gpus = 1;
+    if (G > 1) {
+        const std::vector<int> b = mf_site_bounds(L, G);
+        std::atomic<int> err{0};
+        std::vector<std::thread> th;
+        for (int r = 1; r < G; ++r)
+            th.emplace_back(mf_pairfreq_worker, r, home, msa, w, N, L, q, W.ld, W.d_F, b[(size_t)r], b[(size_t)r + 1], &err);
+        const int rc0 = mf_pairfreq_range(q, W.d_msa, W.d_w, W.d_rows, W.d_off, N, L, W.ld, W.d_F, b[0], b[1]);
+        for (auto &t : th) t.join();
+        DCA_CUDA(cudaSetDevice(home));
+        if (rc0 != 0) return -1;
+        if (!err.load()) { W.gpus = G; return 0; }
+        // a helper failed (no peer access, out of memory ...): redo everything here
+    }
+    return mf_pairfreq_range(q, W.d_msa, W.d_w, W.d_rows, W.d_off, N, L, W.ld, W.d_F, 0, L);
 }
 
 int mf_freqs_host(const uint8_t *msa, const double *w, long N, int L, int q, double *fi, double *fij)

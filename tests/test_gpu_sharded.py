@@ -209,3 +209,27 @@ def test_plmdca_backend_drives_several_gpus(tmp_path):
             assert relmax(xg, x1) <= 5e-5, g
     finally:
         _lib.set_backend_gpus(0)
+
+
+def test_mean_field_pair_histograms_on_several_gpus():
+    """the pair-frequency histograms split by site ranges over the GPUs, every GPU
+    storing its columns straight into the solver GPU's matrix.  Each (site, tile) is computed by
+    the same code in the same order wherever it runs, so the results are bit-identical."""
+    from pydca_b200 import _lib, msa_numerics
+    from pydca_b200.synthetic import synthetic_msa
+    ngpu = _lib.lib().dca_device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    N, L, q = 6000, 130, 21
+    msa = synthetic_msa(N, L, q, seed=9)
+    w = 1.0 / _lib.sequence_counts(msa, 0.8, compare_f64=True).astype(np.float64)
+    try:
+        _lib.set_backend_gpus(1)
+        one = msa_numerics.mean_field_scores(msa, q, w, 0.5, want_couplings=True)
+        for g in sorted({2, ngpu}):
+            _lib.set_backend_gpus(g)
+            many = msa_numerics.mean_field_scores(msa, q, w, 0.5, want_couplings=True)
+            assert (many["fn"] == one["fn"]).all() and (many["couplings"] == one["couplings"]).all(), g
+            assert (many["reg_fi"] == one["reg_fi"]).all()
+    finally:
+        _lib.set_backend_gpus(0)
