@@ -128,7 +128,10 @@ struct SeqJob {
     int L;
 };
 int seqsum_prepare();        // once per device before the first launch (dynamic shared memory attribute)
-int seqsum_launch(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st);
+struct SeqPipe;              // device buffers of the producer / consumer pipeline (one per optimiser instance)
+SeqPipe *seqsum_pipe_create(long nmax);                  // null: the single-CTA kernel is used
+void seqsum_pipe_destroy(SeqPipe *p);
+int seqsum_launch(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st, SeqPipe *pipe = nullptr);
 int seqsum_host(const float *x, const float *y, long n, long n0, float lam0, float lam1, float *out);
 
 // ---- scoring.cu ---------------------------------------------------------------------------

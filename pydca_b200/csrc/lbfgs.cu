@@ -617,6 +617,7 @@ struct Driver {
     int evals = 0;
     bool fidelity = false;         // reference arithmetic: sequential float32 sums (seqsum.cu)
     float *fd = nullptr, *h_fd = nullptr;
+    SeqPipe *pipe = nullptr;
 
     int alloc()
     {
@@ -626,6 +627,7 @@ struct Driver {
             h_fd = static_cast<float *>(host_pinned_alloc(sizeof(float) * FD_FLOATS));
             if (!h_fd) return -1;
             if (seqsum_prepare() != 0) return -1;
+            pipe = seqsum_pipe_create(n);
         }
         float **v[] = {&xp, &g, &gp, &d};
         for (auto pp : v) if (!dev_alloc_t(pp, (size_t)n)) return -1;
@@ -649,6 +651,7 @@ struct Driver {
         dev_free(sc); dev_free(partial); dev_free(ticket); dev_free(gram); dev_free(coef); dev_free(gram_loc);
         dev_free(fd);
         if (h_fd) host_pinned_free(h_fd);
+        seqsum_pipe_destroy(pipe);
     }
 
     // objective at x -> g ; returns {fx, g.d, g.g, x.x} on the host
@@ -677,7 +680,7 @@ struct Driver {
         if (dir) jobs[nj++] = dot_job(g, dir, FD_DG);
         jobs[nj++] = dot_job(g, g, FD_GG);
         jobs[nj++] = dot_job(x, x, FD_XX);
-        if (seqsum_launch(jobs, nj, fd, st) != 0) return -1;
+        if (seqsum_launch(jobs, nj, fd, st, pipe) != 0) return -1;
         DCA_CUDA(cudaMemcpyAsync(h_fd, fd, sizeof(float) * FD_FLOATS, cudaMemcpyDeviceToHost, st));
         DCA_CUDA(cudaStreamSynchronize(st));
         h[PS_FX] = h_fd[FD_FX]; h[PS_DG] = dir ? h_fd[FD_DG] : 0.0; h[PS_GG] = h_fd[FD_GG]; h[PS_XX] = h_fd[FD_XX];
@@ -690,23 +693,23 @@ struct Driver {
     {
         DCA_LAUNCH(fid_diff_kernel, blocks, VEC_THREADS, 0, st, s[end], y[end], d, x, xp, g, gp, n);
         SeqJob two[2] = {dot_job(y[end], s[end], FD_YS + end), dot_job(y[end], y[end], FD_YY)};
-        if (seqsum_launch(two, 2, fd, st) != 0) return -1;
+        if (seqsum_launch(two, 2, fd, st, pipe) != 0) return -1;
         int j = (end + 1) % LB_M;
         for (int i = 0; i < bound; ++i) {
             j = (j + LB_M - 1) % LB_M;
             SeqJob a = dot_job(s[j], d, FD_DOT);
-            if (seqsum_launch(&a, 1, fd, st) != 0) return -1;
+            if (seqsum_launch(&a, 1, fd, st, pipe) != 0) return -1;
             DCA_LAUNCH(fid_axpy_kernel, blocks, VEC_THREADS, 0, st, d, y[j], fd, 0, j, n);
         }
         DCA_LAUNCH(fid_axpy_kernel, blocks, VEC_THREADS, 0, st, d, (const float *)nullptr, fd, 1, end, n);
         for (int i = 0; i < bound; ++i) {
             SeqJob b = dot_job(y[j], d, FD_DOT);
-            if (seqsum_launch(&b, 1, fd, st) != 0) return -1;
+            if (seqsum_launch(&b, 1, fd, st, pipe) != 0) return -1;
             DCA_LAUNCH(fid_axpy_kernel, blocks, VEC_THREADS, 0, st, d, s[j], fd, 2, j, n);
             j = (j + 1) % LB_M;
         }
         SeqJob dg = dot_job(g, d, FD_DGINIT);             // vecdot(&dginit, g, s, n), lbfgs.cpp:830
-        return seqsum_launch(&dg, 1, fd, st);
+        return seqsum_launch(&dg, 1, fd, st, pipe);
     }
 
     int evaluate(const float *dir, double *h, double *dginit = nullptr)

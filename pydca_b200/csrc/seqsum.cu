@@ -7,6 +7,18 @@
 // These run s = fl32(s + t_k) over all P parameters; the rounding bias of that chain (1.8 % of
 // |g|^2 at config 2) is part of the reference's results, so it is reproduced bit for bit.
 //
+// Two kernels.  seqsum_pipe_kernel (the one the optimiser uses) is a producer / consumer
+// pipeline per sum: P producer CTAs take the 4096-term chunks round-robin and reduce each to a
+// 32-byte record (total and prefix range, for both parities) for the THREE binades around the
+// exponent the consumer last published; one chain warp in the consumer CTA prefetches 32
+// records at a time and applies each in O(1) -- pick the candidate matching the running
+// value's exponent, check the prefix range against M, one integer addition.  A record that
+// does not fit (binade crossed twice since it was made, a prefix leaves the binade, a term
+// too large, running value 0) sends that one chunk through the exact in-CTA path below; a
+// bounded look-ahead keeps the producers from running far ahead of the exponent.  The
+// result is exact in every case; only the speed depends on the speculation.
+// seqsum_kernel is the single-CTA version (no speculation), kept as the fallback.
+//
 // One CTA per sum (the chain is serial; independent sums of one optimiser step run as
 // separate CTAs of one launch).  A CTA walks the vector in groups of 4096 terms staged by a
 // 4-deep cp.async ring.  Per group every thread rounds its 4 terms to integers in the
@@ -17,6 +29,8 @@
 #include "dca_common.cuh"
 #include "dca_internal.h"
 #include "seqsum_core.h"
+
+#include <algorithm>
 
 namespace dca {
 
@@ -268,6 +282,303 @@ seqsum_kernel(SeqLaunch jobs, float *__restrict__ out)
     if (tid == 0) out[J.out] = s;
 }
 
+// ---- producer / consumer pipeline -------------------------------------------------------------
+constexpr int PC_CHUNK = SQ_GROUP;             // 4096 terms: one row of 128 per warp
+struct SeqRec { int total[2], pmin[2], pmax[2]; int flags; int e_base; };      // 32 bytes
+static_assert(sizeof(SeqRec) == 32, "record layout");
+
+struct SeqPipeDev {
+    unsigned long long *state;                 // [jobs][2]: (launch << 32) | progress, (launch << 32) | exponent field
+    unsigned *ready;                           // [jobs][maxchunks] = launch id once the records are written
+    SeqRec *rec;                               // [jobs][maxchunks][3]
+    long maxchunks;
+};
+
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// the four terms of this thread at `base` (arithmetic_ansi.h:119 / plmdca_numerics.cpp:470, :482)
+__device__ __forceinline__ void load_terms(const SeqJob &J, long base, float *t)
+{
+    const long n = J.n;
+    const bool two = (J.kind == SEQ_DOT);
+    float xv[4], yv[4];
+    if (base + 4 <= n) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(J.x + base));
+        xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+        if (two) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(J.y + base));
+            yv[0] = b.x; yv[1] = b.y; yv[2] = b.z; yv[3] = b.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            xv[k] = (base + k < n) ? J.x[base + k] : 0.f;
+            yv[k] = (two && base + k < n) ? J.y[base + k] : 0.f;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (two) t[k] = __fmul_rn(xv[k], yv[k]);
+        else {
+            const float lam = (base + k < J.n0) ? J.lam0 : J.lam1;
+            t[k] = __fmul_rn(__fmul_rn(lam, xv[k]), xv[k]);
+        }
+        if (base + k >= n) t[k] = 0.f;
+    }
+}
+
+__device__ __forceinline__ int exp_field(float s)           // 0 when the integer picture does not apply
+{
+    const int ef = (int)((seq_bits(s) >> 23) & 0xffu);
+    return (ef < 40 || ef > 214) ? 0 : ef;
+}
+
+// warp 0 of the consumer: one chunk [0, 4096) of tbuf from running value s, exactly, using the
+// warp summaries computed for the exponent s had at the start of the chunk where they still apply
+__device__ float walk_chunk(float s, bool ctx_ok, const SeqSum *wsum, const int *wflag, const float *tbuf)
+{
+    const int lane = threadIdx.x & 31;
+    SeqCtx c0;
+    bool stale = !ctx_ok || !seq_ctx_make(s, &c0);
+    for (int w = 0; w < SQ_WARPS; ++w) {
+        bool done = false;
+        if (!stale) {
+            SeqCtx cc;
+            seq_ctx_make(s, &cc);                          // same binade as c0: every applied block keeps it
+            const int p = cc.M & 1;
+            const SeqSum v = wsum[w];
+            if (!(wflag[w] & 1) && seq_block_ok(cc, v.pmin[p], v.pmax[p])) { s = seq_apply(cc, v.total[p]); done = true; }
+        }
+        if (done) continue;
+        const float4 q = *reinterpret_cast<const float4 *>(tbuf + w * 128 + 4 * lane);
+        const float t4[4] = {q.x, q.y, q.z, q.w};
+        if (!try_warp<4>(s, t4)) {
+            for (int h = 0; h < 4; ++h) {
+                const float t1 = tbuf[w * 128 + h * 32 + lane];
+                if (try_warp<1>(s, &t1)) continue;
+#pragma unroll 8
+                for (int k = 0; k < 32; ++k) s = __fadd_rn(s, __shfl_sync(0xffffffffu, t1, k));
+            }
+        }
+        SeqCtx cn;
+        stale = !ctx_ok || !seq_ctx_make(s, &cn) || cn.scale != c0.scale;
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(SQ_THREADS, 1)
+seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P, unsigned launch_id)
+{
+    __shared__ __align__(16) float tbuf[PC_CHUNK];
+    __shared__ SeqSum wsum[2][3][SQ_WARPS];
+    __shared__ int wflag[2][3][SQ_WARPS];
+    __shared__ float s_sh;
+    __shared__ long c_sh;
+    __shared__ int e_sh, skip_sh;
+
+    const int job = blockIdx.x / (P + 1), role = blockIdx.x % (P + 1);
+    const SeqJob J = jobs.job[job];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long nchunks = (J.n + PC_CHUNK - 1) / PC_CHUNK;
+    unsigned long long *st_prog = pd.state + 2 * job, *st_exp = pd.state + 2 * job + 1;
+    unsigned *ready = pd.ready + (size_t)job * pd.maxchunks;
+    SeqRec *rec = pd.rec + (size_t)job * pd.maxchunks * 3;
+    const unsigned long long tag = (unsigned long long)launch_id << 32;
+    const long lookahead = 2L * P + 40;
+
+    if (role > 0) {
+        // ================= producer: chunks role-1, role-1+P, ... =================
+        int buf = 0;
+        for (long c = role - 1; c < nchunks; c += P, buf ^= 1) {
+            if (tid == 0) {
+                int skip = 0, e = 0;
+                for (;;) {
+                    const unsigned long long a = ld_acquire_u64(st_prog), b = ld_acquire_u64(st_exp);
+                    const long prog = ((a >> 32) == launch_id) ? (long)(a & 0xffffffffu) : 0;
+                    e = ((b >> 32) == launch_id) ? (int)(b & 0xffffffffu) : 0;
+                    if (prog > c) { skip = 1; break; }                     // the consumer did this chunk itself
+                    if (c <= prog + lookahead && e != 0) break;
+                    __nanosleep(200);
+                }
+                e_sh = e; skip_sh = skip;
+            }
+            __syncthreads();
+            const int e = e_sh;
+            const bool skip = skip_sh != 0;
+            if (!skip) {
+                float t[4];
+                load_terms(J, c * PC_CHUNK + warp * 128 + 4 * lane, t);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int ef = e - 1 + k;
+                    SeqCtx cx;
+                    cx.M = 0; cx.u = 0.f;
+                    const bool valid = (ef >= 40 && ef <= 214);
+                    cx.scale = seq_from_bits((uint32_t)(277 - (valid ? ef : 127)) << 23);      // 2^(23 - (ef - 127))
+                    bool bad = !valid, tie = false;
+                    SeqSum v = lane_summary<4>(cx, t, &bad, &tie);
+                    const bool wbad = __any_sync(0xffffffffu, bad), wtie = __any_sync(0xffffffffu, tie);
+                    v = warp_summary(v, wtie);
+                    if (lane == 31) { wsum[buf][k][warp] = v; wflag[buf][k][warp] = (wbad ? 1 : 0) | (wtie ? 2 : 0); }
+                }
+            }
+            __syncthreads();
+            if (!skip && warp < 3) {
+                SeqSum v = wsum[buf][warp][lane];
+                const int fl = wflag[buf][warp][lane];
+                const bool anybad = __any_sync(0xffffffffu, (fl & 1) != 0);
+                v = warp_scan(v, __any_sync(0xffffffffu, (fl & 2) != 0));
+                if (lane == 31) {
+                    SeqRec r;
+                    r.total[0] = v.total[0]; r.total[1] = v.total[1]; r.pmin[0] = v.pmin[0]; r.pmin[1] = v.pmin[1];
+                    r.pmax[0] = v.pmax[0]; r.pmax[1] = v.pmax[1]; r.flags = anybad ? 1 : 0; r.e_base = e - 1;
+                    int4 *dst = reinterpret_cast<int4 *>(rec + c * 3 + warp);
+                    dst[0] = make_int4(r.total[0], r.total[1], r.pmin[0], r.pmin[1]);
+                    dst[1] = make_int4(r.pmax[0], r.pmax[1], r.flags, r.e_base);
+                    __threadfence();
+                }
+            }
+            __syncthreads();
+            if (!skip && tid == 0) st_release_u32(ready + c, launch_id);
+        }
+        return;
+    }
+
+    // ================= consumer =================
+    if (tid == 0) { s_sh = 0.f; c_sh = 0; st_release_u64(st_prog, tag); st_release_u64(st_exp, tag); }
+    __syncthreads();
+    for (;;) {
+        if (warp == 0) {
+            // ---- fast-forward over the producers' records ----
+            float s = s_sh;
+            long c = c_sh;
+            bool stop = false;
+            while (c < nchunks && !stop) {
+                const long mine = c + lane;
+                bool have = false;
+                int4 q[3][2];
+                if (mine < nchunks && ld_acquire_u32(ready + mine) == launch_id) {
+                    have = true;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int4 *src = reinterpret_cast<const int4 *>(rec + mine * 3 + k);
+                        q[k][0] = __ldcg(src); q[k][1] = __ldcg(src + 1);
+                    }
+                }
+                int k = 0;
+                for (; k < 32 && c + k < nchunks; ++k) {
+                    SeqCtx cc;
+                    if (!seq_ctx_make(s, &cc)) { stop = true; break; }
+                    const int ef = exp_field(s);
+                    if (!__shfl_sync(0xffffffffu, (int)have, k)) {
+                        // not ready when the batch was fetched: wait for it, but never for long
+                        bool ok = false;
+                        const long long t0 = clock64();
+                        while (clock64() - t0 < 60000) {
+                            if (ld_acquire_u32(ready + c + k) == launch_id) { ok = true; break; }
+                        }
+                        if (!ok) { stop = true; break; }
+                        if (lane == k) {
+                            have = true;
+#pragma unroll
+                            for (int kk = 0; kk < 3; ++kk) {
+                                const int4 *src = reinterpret_cast<const int4 *>(rec + mine * 3 + kk);
+                                q[kk][0] = __ldcg(src); q[kk][1] = __ldcg(src + 1);
+                            }
+                        }
+                    }
+                    // every lane selects, for ITS chunk, the candidate made for the current exponent;
+                    // lane k's selection is the one that counts
+                    const int idx = have ? (ef - q[0][1].w) : -1;
+                    const int4 a = (idx == 0) ? q[0][0] : ((idx == 1) ? q[1][0] : q[2][0]);
+                    const int4 b = (idx == 0) ? q[0][1] : ((idx == 1) ? q[1][1] : q[2][1]);
+                    const int p = cc.M & 1;
+                    const int my_total = p ? a.y : a.x, my_pmin = p ? a.w : a.z, my_pmax = p ? b.y : b.x;
+                    const int my_bad = (idx < 0 || idx > 2) ? 1 : (b.z & 1);
+                    const int total = __shfl_sync(0xffffffffu, my_total, k);
+                    const int pmin = __shfl_sync(0xffffffffu, my_pmin, k);
+                    const int pmax = __shfl_sync(0xffffffffu, my_pmax, k);
+                    const int bad = __shfl_sync(0xffffffffu, my_bad, k);
+                    if (bad || !seq_block_ok(cc, pmin, pmax)) { stop = true; break; }
+                    s = seq_apply(cc, total);
+                }
+                c += k;
+                if (lane == 0) {
+                    st_release_u64(st_prog, tag | (unsigned long long)c);
+                    st_release_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s));
+                }
+            }
+            if (lane == 0) { s_sh = s; c_sh = c; }
+        }
+        __syncthreads();
+        const long c = c_sh;
+        const float s = s_sh;
+        if (c >= nchunks) break;
+        // ---- exact path for chunk c: the whole CTA summarises it for the true exponent ----
+        float t[4];
+        load_terms(J, c * PC_CHUNK + 4 * tid, t);
+        *reinterpret_cast<float4 *>(tbuf + 4 * tid) = make_float4(t[0], t[1], t[2], t[3]);
+        SeqCtx cx;
+        const bool ctx_ok = seq_ctx_make(s, &cx);
+        if (ctx_ok) {
+            bool bad = false, tie = false;
+            SeqSum v = lane_summary<4>(cx, t, &bad, &tie);
+            const bool wbad = __any_sync(0xffffffffu, bad), wtie = __any_sync(0xffffffffu, tie);
+            v = warp_summary(v, wtie);
+            if (lane == 31) { wsum[0][0][warp] = v; wflag[0][0][warp] = (wbad ? 1 : 0) | (wtie ? 2 : 0); }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const float s_new = walk_chunk(s, ctx_ok, wsum[0][0], wflag[0][0], tbuf);
+            if (lane == 0) {
+                s_sh = s_new; c_sh = c + 1;
+                st_release_u64(st_prog, tag | (unsigned long long)(c + 1));
+                st_release_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s_new));
+            }
+        }
+        __syncthreads();
+    }
+
+    float s = s_sh;
+    if (J.fxsite) {                                        // as in seqsum_kernel
+        for (int i0 = 0; i0 < J.L; i0 += PC_CHUNK) {
+            __syncthreads();
+            for (int i = i0 + tid; i < min(J.L, i0 + PC_CHUNK); i += SQ_THREADS) {
+                double a = 0.0;
+                for (long k = 0; k < J.nscan; ++k) a += J.fxsite[k * J.L + i];
+                tbuf[i - i0] = (float)a;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int i = i0; i < min(J.L, i0 + PC_CHUNK); ++i) s = __fadd_rn(s, tbuf[i - i0]);
+                s_sh = s;
+            }
+            __syncthreads();
+            s = s_sh;
+        }
+    }
+    if (tid == 0) out[J.out] = s;
+}
+
 }  // namespace
 
 int seqsum_prepare()
@@ -276,12 +587,56 @@ int seqsum_prepare()
     return 0;
 }
 
-int seqsum_launch(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st)
+struct SeqPipe {
+    SeqPipeDev dev{};
+    unsigned launch_id = 0;
+};
+
+SeqPipe *seqsum_pipe_create(long nmax)
+{
+    const char *e = getenv("DCA_B200_SEQSUM");
+    if (e && strcmp(e, "serial") == 0) return nullptr;       // single-CTA kernel only (measurements)
+    SeqPipe *p = new SeqPipe();
+    p->dev.maxchunks = (nmax + PC_CHUNK - 1) / PC_CHUNK;
+    const size_t nrec = (size_t)SEQ_MAX_JOBS * p->dev.maxchunks;
+    p->dev.state = static_cast<unsigned long long *>(dev_alloc(sizeof(unsigned long long) * 2 * SEQ_MAX_JOBS));
+    p->dev.ready = static_cast<unsigned *>(dev_alloc(sizeof(unsigned) * nrec));
+    p->dev.rec = static_cast<SeqRec *>(dev_alloc(sizeof(SeqRec) * 3 * nrec));
+    if (!p->dev.state || !p->dev.ready || !p->dev.rec ||
+        cudaMemset(p->dev.state, 0, sizeof(unsigned long long) * 2 * SEQ_MAX_JOBS) != cudaSuccess ||
+        cudaMemset(p->dev.ready, 0, sizeof(unsigned) * nrec) != cudaSuccess) {
+        seqsum_pipe_destroy(p);
+        return nullptr;
+    }
+    return p;
+}
+
+void seqsum_pipe_destroy(SeqPipe *p)
+{
+    if (!p) return;
+    dev_free(p->dev.state); dev_free(p->dev.ready); dev_free(p->dev.rec);
+    delete p;
+}
+
+int seqsum_launch(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st, SeqPipe *pipe)
 {
     if (njobs < 1 || njobs > SEQ_MAX_JOBS) { set_error("seqsum_launch: %d jobs (1..%d)", njobs, SEQ_MAX_JOBS); return -1; }
     SeqLaunch l{};
-    for (int k = 0; k < njobs; ++k) l.job[k] = jobs[k];
-    DCA_LAUNCH(seqsum_kernel, njobs, SQ_THREADS, SQ_SMEM, st, l, d_out);
+    long nmax = 0;
+    for (int k = 0; k < njobs; ++k) { l.job[k] = jobs[k]; nmax = std::max(nmax, jobs[k].n); }
+    const long chunks = (nmax + PC_CHUNK - 1) / PC_CHUNK;
+    if (!pipe || chunks > pipe->dev.maxchunks || chunks < 64) {
+        DCA_LAUNCH(seqsum_kernel, njobs, SQ_THREADS, SQ_SMEM, st, l, d_out);
+        return 0;
+    }
+    // every CTA of the grid must be resident (producers and consumer talk through memory):
+    // 1024-thread CTAs take one SM each, so (P + 1) * njobs <= SM count
+    int P = std::min(40, sm_count() / njobs - 1);
+    P = (int)std::min<long>(P, std::max<long>(1, chunks / 8));
+    if (P < 2) { DCA_LAUNCH(seqsum_kernel, njobs, SQ_THREADS, SQ_SMEM, st, l, d_out); return 0; }
+    ++pipe->launch_id;
+    if (pipe->launch_id == 0) ++pipe->launch_id;
+    DCA_LAUNCH(seqsum_pipe_kernel, njobs * (P + 1), SQ_THREADS, 0, st, l, d_out, pipe->dev, P, pipe->launch_id);
     return 0;
 }
 
@@ -293,6 +648,7 @@ int seqsum_host(const float *x, const float *y, long n, long n0, float lam0, flo
     if (!x || !out || n <= 0) { set_error("seqsum_host: bad arguments"); return -1; }
     if (seqsum_prepare() != 0) return -1;
     float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    SeqPipe *pipe = nullptr;
     int rc = -1;
     cudaStream_t st = nullptr;
     if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { set_error("seqsum_host: stream"); return -1; }
@@ -303,7 +659,8 @@ int seqsum_host(const float *x, const float *y, long n, long n0, float lam0, flo
         if (y && cudaMemcpyAsync(dy, y, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
         SeqJob j{};
         j.x = dx; j.y = dy; j.n = n; j.kind = y ? SEQ_DOT : SEQ_REG; j.n0 = n0; j.lam0 = lam0; j.lam1 = lam1; j.out = 0;
-        if (seqsum_launch(&j, 1, dout, st) != 0) break;
+        pipe = seqsum_pipe_create(n);
+        if (seqsum_launch(&j, 1, dout, st, pipe) != 0) break;
         if (cudaMemcpyAsync(out, dout, sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
         if (cudaStreamSynchronize(st) != cudaSuccess) break;
         rc = 0;
@@ -311,6 +668,7 @@ int seqsum_host(const float *x, const float *y, long n, long n0, float lam0, flo
     if (rc != 0 && cudaPeekAtLastError() != cudaSuccess) set_error("seqsum_host: %s", cudaGetErrorString(cudaGetLastError()));
     cudaStreamSynchronize(st);
     dev_free(dx); dev_free(dy); dev_free(dout);
+    seqsum_pipe_destroy(pipe);
     cudaStreamDestroy(st);
     return rc;
 }
