@@ -115,6 +115,11 @@ int dca_set_arithmetic(int mode);
  * dot product of x and y (y != NULL), or the sequential L2 accumulation of x with lambda0 on
  * the first n0 entries and lambda1 on the rest (y == NULL). */
 int dca_seq_sum(const float *x, const float *y, long n, long n0, float lambda0, float lambda1, float *out);
+/* the same with the CUDA-event time of one (warm) launch and the pipeline's counters: stats8 =
+ * {chunks applied from producer records, chunks done exactly by the consumer CTA, ready
+ * time-outs, stale / unusable records, failed prefix-range checks, 0, 0, 0} */
+int dca_seq_sum_stats(const float *x, const float *y, long n, long n0, float lambda0, float lambda1,
+                      float *out, unsigned *stats8, float *kernel_ms);
 /* initial point, PlmDCA::initFieldsAndCouplings (plmdca_numerics.cpp:207-249) */
 int dca_plm_init(dca_plm *p, float *x_out_host);
 /* objective + gradient with HOST buffers (x in, g out, *fx out): PlmDCA::gradient

@@ -97,6 +97,8 @@ def lib():
     L.dca_plm_set_carry.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.dca_plm_set_fidelity.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.dca_set_arithmetic.argtypes = [ctypes.c_int]
+    L.dca_seq_sum_stats.argtypes = [_f32p, _f32p, ctypes.c_long, ctypes.c_long, ctypes.c_float, ctypes.c_float, _f32p,
+                                    _u32p, _f32p]
     L.dca_set_gpus.argtypes = [ctypes.c_int]
     L.dca_seq_sum.argtypes = [_f32p, _f32p, ctypes.c_long, ctypes.c_long, ctypes.c_float, ctypes.c_float, _f32p]
     L.dca_plm_init.argtypes = [ctypes.c_void_p, _f32p]
@@ -359,6 +361,18 @@ def seq_dot(x, y):
     out = ctypes.c_float()
     check(lib().dca_seq_sum(ptr(x, _f32p), ptr(y, _f32p), x.size, 0, 0.0, 0.0, ctypes.byref(out)), "dca_seq_sum")
     return np.float32(out.value)
+
+
+def seq_dot_stats(x, y):
+    """(value, kernel ms of one warm launch, pipeline counters) of the sequential float32 dot."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    out, ms = ctypes.c_float(), ctypes.c_float()
+    st = np.zeros(8, dtype=np.uint32)
+    check(lib().dca_seq_sum_stats(ptr(x, _f32p), ptr(y, _f32p), x.size, 0, 0.0, 0.0, ctypes.byref(out),
+                                  ptr(st, _u32p), ctypes.byref(ms)), "dca_seq_sum_stats")
+    keys = ("from_records", "exact", "timeouts", "stale", "range")
+    return np.float32(out.value), ms.value, dict(zip(keys, st[:5].tolist()))
 
 
 def seq_reg(x, n0, lambda0, lambda1):

@@ -366,6 +366,12 @@ int dca_seq_sum(const float *x, const float *y, long n, long n0, float lambda0, 
     return seqsum_host(x, y, n, n0, lambda0, lambda1, out);
 }
 
+int dca_seq_sum_stats(const float *x, const float *y, long n, long n0, float lambda0, float lambda1, float *out,
+                      unsigned *stats8, float *kernel_ms)
+{
+    return seqsum_host(x, y, n, n0, lambda0, lambda1, out, stats8, kernel_ms);
+}
+
 int dca_plm_init(dca_plm *p, float *x_out_host)
 {
     if (!p || !x_out_host) { set_error("dca_plm_init: null argument"); return -1; }

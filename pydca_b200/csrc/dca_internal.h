@@ -131,8 +131,10 @@ int seqsum_prepare();        // once per device before the first launch (dynamic
 struct SeqPipe;              // device buffers of the producer / consumer pipeline (one per optimiser instance)
 SeqPipe *seqsum_pipe_create(long nmax);                  // null: the single-CTA kernel is used
 void seqsum_pipe_destroy(SeqPipe *p);
+int seqsum_pipe_stats(SeqPipe *p, unsigned *out_jobs_x8, cudaStream_t st);
 int seqsum_launch(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st, SeqPipe *pipe = nullptr);
-int seqsum_host(const float *x, const float *y, long n, long n0, float lam0, float lam1, float *out);
+int seqsum_host(const float *x, const float *y, long n, long n0, float lam0, float lam1, float *out,
+                unsigned *stats8 = nullptr, float *kernel_ms = nullptr);
 
 // ---- scoring.cu ---------------------------------------------------------------------------
 int plm_fn_apc_host(const float *h_x, int L, int q, double *fn, double *fn_apc);

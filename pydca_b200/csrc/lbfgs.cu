@@ -978,6 +978,13 @@ done:
 #undef LB_CHECK
     cudaEventRecord(ev1, st);
     cudaStreamSynchronize(st);
+    if (D.fidelity && D.pipe && getenv("DCA_B200_TRACE")) {
+        unsigned stt[8 * SEQ_MAX_JOBS] = {0};
+        if (seqsum_pipe_stats(D.pipe, stt, st) == 0)
+            for (int j = 0; j < SEQ_MAX_JOBS; ++j)
+                fprintf(stderr, "[dca trace] seqsum job slot %d: %u chunks from records, %u exact, %u time-outs, %u stale, %u range\n",
+                        j, stt[8 * j], stt[8 * j + 1], stt[8 * j + 2], stt[8 * j + 3], stt[8 * j + 4]);
+    }
     if (!warm_marked) { cudaEventRecord(evw, st); cudaStreamSynchronize(st); evals_at_warm = D.evals; }
     float ms_total = 0.f, ms_timed = 0.f;
     cudaEventElapsedTime(&ms_total, ev0, ev1);

@@ -145,6 +145,18 @@ __device__ __forceinline__ bool try_warp(float &s, const float *t)
     return true;
 }
 
+// the plain chain over 32 terms in shared memory: every lane runs it on the same (broadcast)
+// loads, so s stays warp-uniform; the loads do not depend on s and pipeline ahead of the adds
+__device__ __forceinline__ float serial32(float s, const float *t)
+{
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) {
+        const float4 q = *reinterpret_cast<const float4 *>(t + k);
+        s = __fadd_rn(s, q.x); s = __fadd_rn(s, q.y); s = __fadd_rn(s, q.z); s = __fadd_rn(s, q.w);
+    }
+    return s;
+}
+
 // the group [0, 4096) of tbuf, from running value s, exactly; executed by one full warp
 __device__ float fallback_group(float s, const float *tbuf)
 {
@@ -156,9 +168,7 @@ __device__ float fallback_group(float s, const float *tbuf)
         for (int h = 0; h < 4; ++h) {
             const float t1 = tbuf[b * 128 + h * 32 + lane];
             if (try_warp<1>(s, &t1)) continue;
-            // the plain chain: every lane runs it on broadcast terms, s stays warp-uniform
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) s = __fadd_rn(s, __shfl_sync(0xffffffffu, t1, k));
+            s = serial32(s, tbuf + b * 128 + h * 32);
         }
     }
     return s;
@@ -291,6 +301,10 @@ struct SeqPipeDev {
     unsigned long long *state;                 // [jobs][2]: (launch << 32) | progress, (launch << 32) | exponent field
     unsigned *ready;                           // [jobs][maxchunks] = launch id once the records are written
     SeqRec *rec;                               // [jobs][maxchunks][3]
+    double *csum;                              // [jobs][maxchunks] float64 sums of the chunks' terms (pre-pass)
+    int *epred;                                // [jobs][maxchunks] exponent field predicted for the running value entering chunk c (0: none)
+    unsigned *ticket;                          // [jobs] arrival counter of the pre-pass
+    unsigned *stats;                           // [jobs][8]: chunks applied from records, chunks done exactly, ready time-outs, stale records, failed range checks
     long maxchunks;
 };
 
@@ -352,37 +366,95 @@ __device__ __forceinline__ int exp_field(float s)           // 0 when the intege
     return (ef < 40 || ef > 214) ? 0 : ef;
 }
 
-// warp 0 of the consumer: one chunk [0, 4096) of tbuf from running value s, exactly, using the
-// warp summaries computed for the exponent s had at the start of the chunk where they still apply
-__device__ float walk_chunk(float s, bool ctx_ok, const SeqSum *wsum, const int *wflag, const float *tbuf)
+// warp 0 of the consumer: rows [w0, 32) of the chunk in tbuf from running value s, exactly.  The
+// warp summaries were made for the exponent s has on entry; a row whose summary does not fit is
+// done by the finer paths, and if that changed the exponent the walk returns the next row so that
+// the whole CTA can re-summarise the rest for the new exponent (returns 32 when the chunk is done).
+__device__ int walk_chunk(float &s, int w0, bool ctx_ok, const SeqSum *wsum, const int *wflag, const float *tbuf)
 {
     const int lane = threadIdx.x & 31;
     SeqCtx c0;
-    bool stale = !ctx_ok || !seq_ctx_make(s, &c0);
-    for (int w = 0; w < SQ_WARPS; ++w) {
-        bool done = false;
-        if (!stale) {
+    const bool usable = ctx_ok && seq_ctx_make(s, &c0);
+    for (int w = w0; w < SQ_WARPS; ++w) {
+        if (usable) {
             SeqCtx cc;
             seq_ctx_make(s, &cc);                          // same binade as c0: every applied block keeps it
             const int p = cc.M & 1;
             const SeqSum v = wsum[w];
-            if (!(wflag[w] & 1) && seq_block_ok(cc, v.pmin[p], v.pmax[p])) { s = seq_apply(cc, v.total[p]); done = true; }
+            if (!(wflag[w] & 1) && seq_block_ok(cc, v.pmin[p], v.pmax[p])) { s = seq_apply(cc, v.total[p]); continue; }
         }
-        if (done) continue;
         const float4 q = *reinterpret_cast<const float4 *>(tbuf + w * 128 + 4 * lane);
         const float t4[4] = {q.x, q.y, q.z, q.w};
         if (!try_warp<4>(s, t4)) {
             for (int h = 0; h < 4; ++h) {
                 const float t1 = tbuf[w * 128 + h * 32 + lane];
                 if (try_warp<1>(s, &t1)) continue;
-#pragma unroll 8
-                for (int k = 0; k < 32; ++k) s = __fadd_rn(s, __shfl_sync(0xffffffffu, t1, k));
+                s = serial32(s, tbuf + w * 128 + h * 32);
             }
         }
         SeqCtx cn;
-        stale = !ctx_ok || !seq_ctx_make(s, &cn) || cn.scale != c0.scale;
+        const bool same = usable && seq_ctx_make(s, &cn) && cn.scale == c0.scale;
+        if (!same && w + 1 < SQ_WARPS && seq_ctx_make(s, &cn)) return w + 1;      // re-summarise the rest
     }
-    return s;
+    return SQ_WARPS;
+}
+
+// Pre-pass: float64 sum of every chunk's terms; the last CTA of a job turns them into the
+// exponent the running value is EXPECTED to have when it enters each chunk (exclusive prefix,
+// rounded to float).  The sequential float32 value drifts away from this (stagnation), which
+// the producers correct with the drift the consumer has observed so far.
+__global__ void __launch_bounds__(256)
+seqsum_prepass_kernel(SeqLaunch jobs, SeqPipeDev pd)
+{
+    __shared__ double red[8];
+    __shared__ bool last;
+    const int job = blockIdx.y;
+    const SeqJob J = jobs.job[job];
+    const long nchunks = (J.n + PC_CHUNK - 1) / PC_CHUNK;
+    const long c = blockIdx.x;
+    if (c >= nchunks) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < PC_CHUNK / (4 * 256); ++r) {
+        float t[4];
+        load_terms(J, c * PC_CHUNK + (long)r * 1024 + 4 * tid, t);
+        acc += ((double)t[0] + (double)t[1]) + ((double)t[2] + (double)t[3]);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    double *csum = pd.csum + (size_t)job * pd.maxchunks;
+    int *epred = pd.epred + (size_t)job * pd.maxchunks;
+    if (tid == 0) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w];
+        csum[c] = v;
+        __threadfence();
+        last = (atomicInc(pd.ticket + job, (unsigned)nchunks - 1u) == (unsigned)nchunks - 1u);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // exclusive prefix over the chunk sums: each thread a contiguous run, then a scan of the runs
+    __shared__ double runs[256];
+    const long per = (nchunks + 255) / 256;
+    const long lo = min(nchunks, (long)tid * per), hi = min(nchunks, lo + per);
+    double run = 0.0;
+    for (long k = lo; k < hi; ++k) run += __ldcg(csum + k);
+    runs[tid] = run;
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0;
+        for (int k = 0; k < 256; ++k) { const double v = runs[k]; runs[k] = a; a += v; }
+    }
+    __syncthreads();
+    double pre = runs[tid];
+    for (long k = lo; k < hi; ++k) {
+        epred[k] = exp_field((float)pre);
+        pre += __ldcg(csum + k);
+    }
 }
 
 __global__ void __launch_bounds__(SQ_THREADS, 1)
@@ -403,36 +475,41 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
     unsigned *ready = pd.ready + (size_t)job * pd.maxchunks;
     SeqRec *rec = pd.rec + (size_t)job * pd.maxchunks * 3;
     const unsigned long long tag = (unsigned long long)launch_id << 32;
-    const long lookahead = 2L * P + 40;
 
     if (role > 0) {
         // ================= producer: chunks role-1, role-1+P, ... =================
+        // No flow control: the exponent of the running value at chunk c is predicted by the
+        // pre-pass (epred) and corrected by the drift the consumer has measured so far
+        // (published exponent minus prediction at the consumer's position).
+        const int *epred = pd.epred + (size_t)job * pd.maxchunks;
         int buf = 0;
-        for (long c = role - 1; c < nchunks; c += P, buf ^= 1) {
+        float tn[4];
+        long c = role - 1;
+        if (c < nchunks) load_terms(J, c * PC_CHUNK + warp * 128 + 4 * lane, tn);
+        for (; c < nchunks; c += P, buf ^= 1) {
+            float t[4] = {tn[0], tn[1], tn[2], tn[3]};
+            if (c + P < nchunks) load_terms(J, (c + P) * PC_CHUNK + warp * 128 + 4 * lane, tn);      // next chunk in flight
             if (tid == 0) {
-                int skip = 0, e = 0;
-                for (;;) {
-                    const unsigned long long a = ld_acquire_u64(st_prog), b = ld_acquire_u64(st_exp);
-                    const long prog = ((a >> 32) == launch_id) ? (long)(a & 0xffffffffu) : 0;
-                    e = ((b >> 32) == launch_id) ? (int)(b & 0xffffffffu) : 0;
-                    if (prog > c) { skip = 1; break; }                     // the consumer did this chunk itself
-                    if (c <= prog + lookahead && e != 0) break;
-                    __nanosleep(200);
+                const unsigned long long a = ld_acquire_u64(st_prog), b = ld_acquire_u64(st_exp);
+                const long prog = ((a >> 32) == launch_id) ? (long)(a & 0xffffffffu) : 0;
+                const int e_seen = ((b >> 32) == launch_id) ? (int)(b & 0xffffffffu) : 0;
+                int e = __ldcg(epred + c);
+                if (e != 0 && e_seen != 0 && prog > 0 && prog < nchunks) {
+                    const int e_there = __ldcg(epred + prog);
+                    if (e_there != 0) e += e_seen - e_there;
                 }
-                e_sh = e; skip_sh = skip;
+                e_sh = e; skip_sh = (prog > c) ? 1 : 0;                    // the consumer did this chunk itself
             }
             __syncthreads();
             const int e = e_sh;
             const bool skip = skip_sh != 0;
             if (!skip) {
-                float t[4];
-                load_terms(J, c * PC_CHUNK + warp * 128 + 4 * lane, t);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const int ef = e - 1 + k;
                     SeqCtx cx;
                     cx.M = 0; cx.u = 0.f;
-                    const bool valid = (ef >= 40 && ef <= 214);
+                    const bool valid = (e != 0 && ef >= 40 && ef <= 214);
                     cx.scale = seq_from_bits((uint32_t)(277 - (valid ? ef : 127)) << 23);      // 2^(23 - (ef - 127))
                     bool bad = !valid, tie = false;
                     SeqSum v = lane_summary<4>(cx, t, &bad, &tie);
@@ -448,12 +525,9 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                 const bool anybad = __any_sync(0xffffffffu, (fl & 1) != 0);
                 v = warp_scan(v, __any_sync(0xffffffffu, (fl & 2) != 0));
                 if (lane == 31) {
-                    SeqRec r;
-                    r.total[0] = v.total[0]; r.total[1] = v.total[1]; r.pmin[0] = v.pmin[0]; r.pmin[1] = v.pmin[1];
-                    r.pmax[0] = v.pmax[0]; r.pmax[1] = v.pmax[1]; r.flags = anybad ? 1 : 0; r.e_base = e - 1;
                     int4 *dst = reinterpret_cast<int4 *>(rec + c * 3 + warp);
-                    dst[0] = make_int4(r.total[0], r.total[1], r.pmin[0], r.pmin[1]);
-                    dst[1] = make_int4(r.pmax[0], r.pmax[1], r.flags, r.e_base);
+                    dst[0] = make_int4(v.total[0], v.total[1], v.pmin[0], v.pmin[1]);
+                    dst[1] = make_int4(v.pmax[0], v.pmax[1], anybad ? 1 : 0, e - 1);
                     __threadfence();
                 }
             }
@@ -468,92 +542,109 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
     __syncthreads();
     for (;;) {
         if (warp == 0) {
-            // ---- fast-forward over the producers' records ----
+            // ---- fast-forward over the producers' records, 32 chunks per step ----
+            // The records of a batch are composed by a warp scan (both parities); the range check of
+            // the composed prefix tells how many leading chunks can be applied at once, and as long
+            // as it holds the exponent -- hence the choice of candidate -- cannot change.
             float s = s_sh;
             long c = c_sh;
             bool stop = false;
+            unsigned n_fast = 0, n_timeout = 0, n_stale = 0, n_range = 0;
             while (c < nchunks && !stop) {
+                SeqCtx cc;
+                if (!seq_ctx_make(s, &cc)) break;
+                const int ef = exp_field(s);
                 const long mine = c + lane;
-                bool have = false;
-                int4 q[3][2];
-                if (mine < nchunks && ld_acquire_u32(ready + mine) == launch_id) {
-                    have = true;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int4 *src = reinterpret_cast<const int4 *>(rec + mine * 3 + k);
-                        q[k][0] = __ldcg(src); q[k][1] = __ldcg(src + 1);
+                const bool rdy = mine < nchunks && ld_acquire_u32(ready + mine) == launch_id;
+                const unsigned rmask = __ballot_sync(0xffffffffu, rdy);
+                const int nready = (rmask == 0xffffffffu) ? 32 : (__ffs(~rmask) - 1);
+                if (nready == 0) {
+                    bool ok = false;
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < 40000) {
+                        if (ld_acquire_u32(ready + c) == launch_id) { ok = true; break; }
+                    }
+                    if (!ok) { ++n_timeout; stop = true; }
+                    continue;
+                }
+                SeqSum v = seq_single(0, 0);
+                int bad = 1;
+                if (lane < nready) {
+                    const int4 *src = reinterpret_cast<const int4 *>(rec + mine * 3);
+                    const int e_base = __ldcg(src + 1).w;
+                    const int idx = ef - e_base;
+                    if (idx >= 0 && idx <= 2) {
+                        const int4 a = __ldcg(src + 2 * idx), b = __ldcg(src + 2 * idx + 1);
+                        v.total[0] = a.x; v.total[1] = a.y; v.pmin[0] = a.z; v.pmin[1] = a.w;
+                        v.pmax[0] = b.x; v.pmax[1] = b.y;
+                        bad = b.z & 1;
                     }
                 }
-                int k = 0;
-                for (; k < 32 && c + k < nchunks; ++k) {
-                    SeqCtx cc;
-                    if (!seq_ctx_make(s, &cc)) { stop = true; break; }
-                    const int ef = exp_field(s);
-                    if (!__shfl_sync(0xffffffffu, (int)have, k)) {
-                        // not ready when the batch was fetched: wait for it, but never for long
-                        bool ok = false;
-                        const long long t0 = clock64();
-                        while (clock64() - t0 < 60000) {
-                            if (ld_acquire_u32(ready + c + k) == launch_id) { ok = true; break; }
-                        }
-                        if (!ok) { stop = true; break; }
-                        if (lane == k) {
-                            have = true;
-#pragma unroll
-                            for (int kk = 0; kk < 3; ++kk) {
-                                const int4 *src = reinterpret_cast<const int4 *>(rec + mine * 3 + kk);
-                                q[kk][0] = __ldcg(src); q[kk][1] = __ldcg(src + 1);
-                            }
-                        }
-                    }
-                    // every lane selects, for ITS chunk, the candidate made for the current exponent;
-                    // lane k's selection is the one that counts
-                    const int idx = have ? (ef - q[0][1].w) : -1;
-                    const int4 a = (idx == 0) ? q[0][0] : ((idx == 1) ? q[1][0] : q[2][0]);
-                    const int4 b = (idx == 0) ? q[0][1] : ((idx == 1) ? q[1][1] : q[2][1]);
-                    const int p = cc.M & 1;
-                    const int my_total = p ? a.y : a.x, my_pmin = p ? a.w : a.z, my_pmax = p ? b.y : b.x;
-                    const int my_bad = (idx < 0 || idx > 2) ? 1 : (b.z & 1);
-                    const int total = __shfl_sync(0xffffffffu, my_total, k);
-                    const int pmin = __shfl_sync(0xffffffffu, my_pmin, k);
-                    const int pmax = __shfl_sync(0xffffffffu, my_pmax, k);
-                    const int bad = __shfl_sync(0xffffffffu, my_bad, k);
-                    if (bad || !seq_block_ok(cc, pmin, pmax)) { stop = true; break; }
+                const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);
+                const int nusable = (badmask == 0u) ? 32 : (__ffs(badmask) - 1);      // leading usable records
+                v = warp_scan(v, true);
+                const int p = cc.M & 1;
+                const bool okl = lane < nusable && seq_block_ok(cc, v.pmin[p], v.pmax[p]);
+                const unsigned okmask = __ballot_sync(0xffffffffu, okl);
+                const int nok = (okmask == 0xffffffffu) ? 32 : (__ffs(~okmask) - 1);
+                if (nok > 0) {
+                    const int total = __shfl_sync(0xffffffffu, v.total[p], nok - 1);
                     s = seq_apply(cc, total);
+                    c += nok;
+                    n_fast += (unsigned)nok;
                 }
-                c += k;
                 if (lane == 0) {
                     st_release_u64(st_prog, tag | (unsigned long long)c);
                     st_release_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s));
                 }
+                if (nok < nready) {                        // chunk c needs the exact path
+                    if (nok >= nusable) ++n_stale; else ++n_range;
+                    stop = true;
+                }
             }
-            if (lane == 0) { s_sh = s; c_sh = c; }
+            if (lane == 0) {
+                s_sh = s; c_sh = c;
+                unsigned *stt = pd.stats + 8 * job;
+                stt[0] += n_fast; stt[2] += n_timeout; stt[3] += n_stale; stt[4] += n_range;
+            }
         }
         __syncthreads();
         const long c = c_sh;
         const float s = s_sh;
         if (c >= nchunks) break;
-        // ---- exact path for chunk c: the whole CTA summarises it for the true exponent ----
+        // ---- exact path for chunk c: the whole CTA summarises it for the true exponent; if the
+        // exponent changes inside the chunk, the remaining rows are summarised again ----
         float t[4];
         load_terms(J, c * PC_CHUNK + 4 * tid, t);
         *reinterpret_cast<float4 *>(tbuf + 4 * tid) = make_float4(t[0], t[1], t[2], t[3]);
-        SeqCtx cx;
-        const bool ctx_ok = seq_ctx_make(s, &cx);
-        if (ctx_ok) {
-            bool bad = false, tie = false;
-            SeqSum v = lane_summary<4>(cx, t, &bad, &tie);
-            const bool wbad = __any_sync(0xffffffffu, bad), wtie = __any_sync(0xffffffffu, tie);
-            v = warp_summary(v, wtie);
-            if (lane == 31) { wsum[0][0][warp] = v; wflag[0][0][warp] = (wbad ? 1 : 0) | (wtie ? 2 : 0); }
-        }
-        __syncthreads();
-        if (warp == 0) {
-            const float s_new = walk_chunk(s, ctx_ok, wsum[0][0], wflag[0][0], tbuf);
-            if (lane == 0) {
-                s_sh = s_new; c_sh = c + 1;
-                st_release_u64(st_prog, tag | (unsigned long long)(c + 1));
-                st_release_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s_new));
+        int w0 = 0;
+        float sc = s;
+        for (;;) {
+            SeqCtx cx;
+            const bool ctx_ok = seq_ctx_make(sc, &cx);
+            if (ctx_ok && warp >= w0) {
+                bool bad = false, tie = false;
+                SeqSum v = lane_summary<4>(cx, t, &bad, &tie);
+                const bool wbad = __any_sync(0xffffffffu, bad), wtie = __any_sync(0xffffffffu, tie);
+                v = warp_summary(v, wtie);
+                if (lane == 31) { wsum[0][0][warp] = v; wflag[0][0][warp] = (wbad ? 1 : 0) | (wtie ? 2 : 0); }
             }
+            __syncthreads();
+            if (warp == 0) {
+                float s_new = sc;
+                const int next = walk_chunk(s_new, w0, ctx_ok, wsum[0][0], wflag[0][0], tbuf);
+                if (lane == 0) { s_sh = s_new; e_sh = next; }
+            }
+            __syncthreads();
+            sc = s_sh;
+            w0 = e_sh;
+            if (w0 >= SQ_WARPS) break;
+        }
+        if (tid == 0) {
+            c_sh = c + 1;
+            pd.stats[8 * job + 1] += 1u;
+            st_release_u64(st_prog, tag | (unsigned long long)(c + 1));
+            st_release_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(sc));
         }
         __syncthreads();
     }
@@ -602,7 +693,13 @@ SeqPipe *seqsum_pipe_create(long nmax)
     p->dev.state = static_cast<unsigned long long *>(dev_alloc(sizeof(unsigned long long) * 2 * SEQ_MAX_JOBS));
     p->dev.ready = static_cast<unsigned *>(dev_alloc(sizeof(unsigned) * nrec));
     p->dev.rec = static_cast<SeqRec *>(dev_alloc(sizeof(SeqRec) * 3 * nrec));
-    if (!p->dev.state || !p->dev.ready || !p->dev.rec ||
+    p->dev.stats = static_cast<unsigned *>(dev_alloc(sizeof(unsigned) * 8 * SEQ_MAX_JOBS));
+    p->dev.csum = static_cast<double *>(dev_alloc(sizeof(double) * nrec));
+    p->dev.epred = static_cast<int *>(dev_alloc(sizeof(int) * nrec));
+    p->dev.ticket = static_cast<unsigned *>(dev_alloc(sizeof(unsigned) * SEQ_MAX_JOBS));
+    if (!p->dev.state || !p->dev.ready || !p->dev.rec || !p->dev.stats || !p->dev.csum || !p->dev.epred || !p->dev.ticket ||
+        cudaMemset(p->dev.ticket, 0, sizeof(unsigned) * SEQ_MAX_JOBS) != cudaSuccess ||
+        cudaMemset(p->dev.stats, 0, sizeof(unsigned) * 8 * SEQ_MAX_JOBS) != cudaSuccess ||
         cudaMemset(p->dev.state, 0, sizeof(unsigned long long) * 2 * SEQ_MAX_JOBS) != cudaSuccess ||
         cudaMemset(p->dev.ready, 0, sizeof(unsigned) * nrec) != cudaSuccess) {
         seqsum_pipe_destroy(p);
@@ -611,10 +708,20 @@ SeqPipe *seqsum_pipe_create(long nmax)
     return p;
 }
 
+// accumulated counters of the pipeline since creation: out[jobs][8] (see SeqPipeDev::stats)
+int seqsum_pipe_stats(SeqPipe *p, unsigned *out, cudaStream_t st)
+{
+    if (!p) return -1;
+    DCA_CUDA(cudaMemcpyAsync(out, p->dev.stats, sizeof(unsigned) * 8 * SEQ_MAX_JOBS, cudaMemcpyDeviceToHost, st));
+    DCA_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 void seqsum_pipe_destroy(SeqPipe *p)
 {
     if (!p) return;
-    dev_free(p->dev.state); dev_free(p->dev.ready); dev_free(p->dev.rec);
+    dev_free(p->dev.state); dev_free(p->dev.ready); dev_free(p->dev.rec); dev_free(p->dev.stats);
+    dev_free(p->dev.csum); dev_free(p->dev.epred); dev_free(p->dev.ticket);
     delete p;
 }
 
@@ -631,18 +738,21 @@ int seqsum_launch(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st, 
     }
     // every CTA of the grid must be resident (producers and consumer talk through memory):
     // 1024-thread CTAs take one SM each, so (P + 1) * njobs <= SM count
-    int P = std::min(40, sm_count() / njobs - 1);
-    P = (int)std::min<long>(P, std::max<long>(1, chunks / 8));
+    int P = sm_count() / njobs - 1;
+    P = (int)std::min<long>(P, std::max<long>(1, chunks / 4));
     if (P < 2) { DCA_LAUNCH(seqsum_kernel, njobs, SQ_THREADS, SQ_SMEM, st, l, d_out); return 0; }
     ++pipe->launch_id;
     if (pipe->launch_id == 0) ++pipe->launch_id;
+    // the pre-pass needs equal chunk counts per job only for its grid; shorter jobs return early
+    DCA_LAUNCH(seqsum_prepass_kernel, dim3((unsigned)chunks, (unsigned)njobs), 256, 0, st, l, pipe->dev);
     DCA_LAUNCH(seqsum_pipe_kernel, njobs * (P + 1), SQ_THREADS, 0, st, l, d_out, pipe->dev, P, pipe->launch_id);
     return 0;
 }
 
 // host-buffer entry for the parity tests: out = sequential float32 dot(x, y) (y != null) or the
 // L2 accumulation of x with lam0 on the first n0 entries and lam1 on the rest (y == null)
-int seqsum_host(const float *x, const float *y, long n, long n0, float lam0, float lam1, float *out)
+int seqsum_host(const float *x, const float *y, long n, long n0, float lam0, float lam1, float *out,
+                unsigned *stats8, float *kernel_ms)
 {
     if (require_device() != 0) return -1;
     if (!x || !out || n <= 0) { set_error("seqsum_host: bad arguments"); return -1; }
@@ -660,7 +770,20 @@ int seqsum_host(const float *x, const float *y, long n, long n0, float lam0, flo
         SeqJob j{};
         j.x = dx; j.y = dy; j.n = n; j.kind = y ? SEQ_DOT : SEQ_REG; j.n0 = n0; j.lam0 = lam0; j.lam1 = lam1; j.out = 0;
         pipe = seqsum_pipe_create(n);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        if (seqsum_launch(&j, 1, dout, st, pipe) != 0) break;          // warm (module load)
+        if (pipe) cudaMemsetAsync(pipe->dev.stats, 0, sizeof(unsigned) * 8 * SEQ_MAX_JOBS, st);
+        cudaEventRecord(e0, st);
         if (seqsum_launch(&j, 1, dout, st, pipe) != 0) break;
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (stats8) {
+            memset(stats8, 0, sizeof(unsigned) * 8);
+            if (pipe) cudaMemcpyAsync(stats8, pipe->dev.stats, sizeof(unsigned) * 8, cudaMemcpyDeviceToHost, st);
+        }
         if (cudaMemcpyAsync(out, dout, sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
         if (cudaStreamSynchronize(st) != cudaSuccess) break;
         rc = 0;

@@ -87,9 +87,12 @@ SEQ_HD void seq_round_term(const SeqCtx &c, float t, int *r0, int *r1, bool *bad
 {
     const float z = t * c.scale;                      // exact (power of two), may overflow to inf
     if (!(fabsf(z) < (float)SEQ_R_MAX)) { *bad = true; *r0 = 0; *r1 = 0; return; }
-    const float r = rintf(z);
-    *r0 = (int)r;
-    *r1 = (fabsf(z - r) == 0.5f) ? 2 * (int)floorf(z) + 1 - (int)r : (int)r;
+    const float r = rintf(z);                         // round half to even, like the adder
+    const float d = z - r;                            // exact
+    const int ri = (int)r;
+    *r0 = ri;
+    // tie: z = m + 1/2; rintf took the even neighbour, the other one lies on d's side
+    *r1 = (fabsf(d) == 0.5f) ? (d > 0.f ? ri + 1 : ri - 1) : ri;
 }
 
 // can a block whose inclusive prefix sums span [pmin, pmax] be applied in one step?

@@ -43,8 +43,9 @@ def main():
     r = rng.standard_normal(n).astype(np.float32)
     for name, a, b in (("g.g", g, g), ("g.d", g, d), ("g.noise", g, r), ("noise.noise", r, rng.standard_normal(n).astype(np.float32))):
         t0 = time.time()
-        got = _lib.seq_dot(a, b)
+        got, kms, stats = _lib.seq_dot_stats(a, b)
         t1 = time.time()
+        print("   kernel %.3f ms, pipeline %s" % (kms, stats))
         want = np.float32(NL.seq_naive_dot(a.ctypes.data_as(f32p), b.ctypes.data_as(f32p), n))
         print("seq_dot %-12s gpu %.9g naive %.9g %s (%.1f ms incl. H2D)" %
               (name, got, want, "OK" if got.view(np.uint32) == want.view(np.uint32) else "MISMATCH", 1e3 * (t1 - t0)))
