@@ -299,7 +299,7 @@ static_assert(sizeof(SeqRec) == 32, "record layout");
 
 struct SeqPipeDev {
     unsigned long long *state;                 // [jobs][2]: (launch << 32) | progress, (launch << 32) | exponent field
-    unsigned *ready;                           // [jobs][maxchunks] = launch id once the records are written
+    unsigned *ready;                           // [jobs][maxchunks] = (launch id << 8) | middle candidate's exponent, once the records are written
     SeqRec *rec;                               // [jobs][maxchunks][3]
     double *csum;                              // [jobs][maxchunks] float64 sums of the chunks' terms (pre-pass)
     int *epred;                                // [jobs][maxchunks] exponent field predicted for the running value entering chunk c (0: none)
@@ -317,6 +317,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
 {
@@ -532,7 +536,7 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                 }
             }
             __syncthreads();
-            if (!skip && tid == 0) st_release_u32(ready + c, launch_id);
+            if (!skip && tid == 0) st_release_u32(ready + c, (launch_id << 8) | (unsigned)((e_sh) & 0xff));      // e_base + 1 = e
         }
         return;
     }
@@ -545,41 +549,58 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
             // ---- fast-forward over the producers' records, 32 chunks per step ----
             // The records of a batch are composed by a warp scan (both parities); the range check of
             // the composed prefix tells how many leading chunks can be applied at once, and as long
-            // as it holds the exponent -- hence the choice of candidate -- cannot change.
+            // as it holds the exponent -- hence the choice of candidate -- cannot change.  The loads
+            // are software-pipelined: while batch b is scanned, the records of batch b+1 (whose ready
+            // words arrived one step earlier and name the candidate) and the ready words of batch b+2
+            // are in flight; the ready word is (launch << 8) | exponent of the middle candidate.
             float s = s_sh;
             long c = c_sh;
             bool stop = false;
             unsigned n_fast = 0, n_timeout = 0, n_stale = 0, n_range = 0;
+            const unsigned want = launch_id << 8;
+            auto flag_at = [&](long k) -> unsigned { return (k < nchunks) ? ld_acquire_u32(ready + k) : 0u; };
+            // candidate of chunk k made for exponent ef, if its ready word fl says there is one
+            auto fetch = [&](long k, unsigned fl, int ef, int4 &A, int4 &B) -> bool {
+                if ((fl & 0xffffff00u) != want) return false;
+                const int idx = ef - ((int)(fl & 0xffu) - 1);
+                if (idx < 0 || idx > 2 || (fl & 0xffu) == 0u) { A = make_int4(0, 0, 0, 0); B = make_int4(0, 0, 1, 0); return true; }
+                const int4 *src = reinterpret_cast<const int4 *>(rec + k * 3 + idx);
+                A = __ldcg(src); B = __ldcg(src + 1);
+                return true;
+            };
+            bool pre_valid = false;
+            int pre_ef = 0;
+            int4 curA = make_int4(0, 0, 0, 0), curB = make_int4(0, 0, 1, 0);
+            bool cur_rdy = false;
+            unsigned fl_next = 0;
             while (c < nchunks && !stop) {
                 SeqCtx cc;
                 if (!seq_ctx_make(s, &cc)) break;
                 const int ef = exp_field(s);
-                const long mine = c + lane;
-                const bool rdy = mine < nchunks && ld_acquire_u32(ready + mine) == launch_id;
-                const unsigned rmask = __ballot_sync(0xffffffffu, rdy);
+                if (!pre_valid || pre_ef != ef) {          // (re)start the pipeline at c
+                    cur_rdy = fetch(c + lane, flag_at(c + lane), ef, curA, curB);
+                    fl_next = flag_at(c + 32 + lane);
+                    pre_valid = true; pre_ef = ef;
+                }
+                int4 nxtA = make_int4(0, 0, 0, 0), nxtB = make_int4(0, 0, 1, 0);
+                const bool nxt_rdy = fetch(c + 32 + lane, fl_next, ef, nxtA, nxtB);      // in flight during the scan
+                const unsigned fl_next2 = flag_at(c + 64 + lane);
+                const unsigned rmask = __ballot_sync(0xffffffffu, cur_rdy);
                 const int nready = (rmask == 0xffffffffu) ? 32 : (__ffs(~rmask) - 1);
                 if (nready == 0) {
                     bool ok = false;
                     const long long t0 = clock64();
                     while (clock64() - t0 < 40000) {
-                        if (ld_acquire_u32(ready + c) == launch_id) { ok = true; break; }
+                        if ((ld_acquire_u32(ready + c) & 0xffffff00u) == want) { ok = true; break; }
                     }
                     if (!ok) { ++n_timeout; stop = true; }
+                    pre_valid = false;
                     continue;
                 }
-                SeqSum v = seq_single(0, 0);
-                int bad = 1;
-                if (lane < nready) {
-                    const int4 *src = reinterpret_cast<const int4 *>(rec + mine * 3);
-                    const int e_base = __ldcg(src + 1).w;
-                    const int idx = ef - e_base;
-                    if (idx >= 0 && idx <= 2) {
-                        const int4 a = __ldcg(src + 2 * idx), b = __ldcg(src + 2 * idx + 1);
-                        v.total[0] = a.x; v.total[1] = a.y; v.pmin[0] = a.z; v.pmin[1] = a.w;
-                        v.pmax[0] = b.x; v.pmax[1] = b.y;
-                        bad = b.z & 1;
-                    }
-                }
+                SeqSum v;
+                v.total[0] = curA.x; v.total[1] = curA.y; v.pmin[0] = curA.z; v.pmin[1] = curA.w;
+                v.pmax[0] = curB.x; v.pmax[1] = curB.y;
+                const int bad = (lane < nready) ? (curB.z & 1) : 1;
                 const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);
                 const int nusable = (badmask == 0u) ? 32 : (__ffs(badmask) - 1);      // leading usable records
                 v = warp_scan(v, true);
@@ -593,10 +614,15 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                     c += nok;
                     n_fast += (unsigned)nok;
                 }
-                if (lane == 0) {
-                    st_release_u64(st_prog, tag | (unsigned long long)c);
-                    st_release_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s));
+                if (lane == 0) {                           // hints for the producers: no ordering needed
+                    st_relaxed_u64(st_prog, tag | (unsigned long long)c);
+                    st_relaxed_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s));
                 }
+                if (nok == 32) {                           // the prefetched batch is the next one, same exponent
+                    curA = nxtA; curB = nxtB; cur_rdy = nxt_rdy; fl_next = fl_next2;
+                    continue;
+                }
+                pre_valid = false;
                 if (nok < nready) {                        // chunk c needs the exact path
                     if (nok >= nusable) ++n_stale; else ++n_range;
                     stop = true;
@@ -742,7 +768,11 @@ int seqsum_launch(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st, 
     P = (int)std::min<long>(P, std::max<long>(1, chunks / 4));
     if (P < 2) { DCA_LAUNCH(seqsum_kernel, njobs, SQ_THREADS, SQ_SMEM, st, l, d_out); return 0; }
     ++pipe->launch_id;
-    if (pipe->launch_id == 0) ++pipe->launch_id;
+    if ((pipe->launch_id & 0xffffffu) == 0u) {
+        // the ready words carry 24 bits of the launch id: start a new era with clean flags
+        ++pipe->launch_id;
+        DCA_CUDA(cudaMemsetAsync(pipe->dev.ready, 0, sizeof(unsigned) * (size_t)SEQ_MAX_JOBS * pipe->dev.maxchunks, st));
+    }
     // the pre-pass needs equal chunk counts per job only for its grid; shorter jobs return early
     DCA_LAUNCH(seqsum_prepass_kernel, dim3((unsigned)chunks, (unsigned)njobs), 256, 0, st, l, pipe->dev);
     DCA_LAUNCH(seqsum_pipe_kernel, njobs * (P + 1), SQ_THREADS, 0, st, l, d_out, pipe->dev, P, pipe->launch_id);
