@@ -94,11 +94,14 @@ def full(path, tag, cmd):
             t = float(t.replace(",", "")) * {"ms": 1e3, "us": 1.0, "ns": 1e-3, "msecond": 1e3, "usecond": 1.0,
                                               "nsecond": 1e-3}.get(tu, 1.0)
             traffic["kernels"][k] = {"dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes": rd + wr, "gpu_time_us": t}
-    json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
+    if not os.environ.get("NCU_KEEP_TRAFFIC"):      # captures of other kernels must not replace the plmDCA table
+        json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
     return out
 
 
 if __name__ == "__main__":
     tag, lpath, fpath, cmd = sys.argv[1:5]
-    print(launches(lpath, tag, cmd))
-    print(full(fpath, tag, cmd))
+    if lpath != "-":
+        print(launches(lpath, tag, cmd))
+    if fpath != "-":
+        print(full(fpath, tag, cmd))
