@@ -240,6 +240,15 @@ int dca_fp64_mma_peak(int reps, double *tflops_out);
 int dca_mf_corr_from_freqs(const double *reg_fi, const double *reg_fij, int seqs_len,
                            int num_site_states, double *corr_out);
 
+/* ---- reference-sequence matching -----------------------------------------------------------
+ * scores_out[n] = Smith-Waterman / Gotoh local alignment score of the reference sequence
+ * (ref_codes: states 0..q-2, no gaps) against row n of the alignment with its gaps removed:
+ * the search loop of SequenceBackmapper.find_matching_seqs_from_alignment
+ * (sequence_backmapper.py:228-283; Biopython pairwise2.align.localds with BLOSUM62, -10/-1 for
+ * proteins and +5/-4, -8/0 for RNA, :207-214), one GPU thread per sequence.  Integers: exact. */
+int dca_sw_scores(const uint8_t *msa, long num_seqs, int seqs_len, int num_site_states,
+                  const uint8_t *ref_codes, int ref_len, int *scores_out);
+
 /* ---- direct information ------------------------------------------------------------
  * two-site-model fields (fixed point to 1e-4) + DI per pair:
  * msa_numerics.py:378-533 (mf: couplings = n x n matrix) and

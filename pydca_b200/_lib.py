@@ -123,6 +123,8 @@ def lib():
                                 _f64p, _f64p, _f64p, _f64p, _f64p, _f32p]
     L.dca_mf_corr_from_freqs.argtypes = [_f64p, _f64p, ctypes.c_int, ctypes.c_int, _f64p]
     L.dca_fp64_mma_peak.argtypes = [ctypes.c_int, _f64p]
+    L.dca_sw_scores.argtypes = [_u8p, ctypes.c_long, ctypes.c_int, ctypes.c_int, _u8p, ctypes.c_int,
+                                ctypes.POINTER(ctypes.c_int)]
     L.dca_mf_direct_info.argtypes = [_f64p, _f64p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
     L.dca_plm_direct_info.argtypes = [_f32p, _f64p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
     _lib = L
@@ -389,6 +391,18 @@ def lbfgs_vector_bench(n, stored_pairs=5, reps=20):
     ms = np.zeros(3, dtype=np.float32)
     check(lib().dca_lbfgs_vector_bench(int(n), int(stored_pairs), int(reps), ptr(ms, _f32p)), "dca_lbfgs_vector_bench")
     return dict(zip(("update_gram", "direction", "step"), ms.tolist()))
+
+
+def sw_scores(msa, num_site_states, ref_codes):
+    """Local alignment score of the reference (codes 0..q-2) against every row of the zero-based
+    alignment, gaps removed (int32[N])."""
+    msa = np.ascontiguousarray(msa, dtype=np.uint8)
+    ref = np.ascontiguousarray(ref_codes, dtype=np.uint8)
+    n, l = msa.shape
+    out = np.zeros(n, dtype=np.int32)
+    check(lib().dca_sw_scores(ptr(msa, _u8p), n, l, int(num_site_states), ptr(ref, _u8p), ref.size,
+                              out.ctypes.data_as(ctypes.POINTER(ctypes.c_int))), "dca_sw_scores")
+    return out
 
 
 def fp64_mma_peak(reps=5):

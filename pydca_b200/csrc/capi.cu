@@ -809,6 +809,12 @@ int dca_mf_scores(const uint8_t *msa, const double *weights, long num_seqs, int 
                           couplings_out, fn_out, fn_apc_out, di_out, stage_ms_out);
 }
 
+int dca_sw_scores(const uint8_t *msa, long num_seqs, int seqs_len, int num_site_states, const uint8_t *ref_codes,
+                  int ref_len, int *scores_out)
+{
+    return sw_scores_host(msa, num_seqs, seqs_len, num_site_states, ref_codes, ref_len, scores_out);
+}
+
 int dca_fp64_mma_peak(int reps, double *tflops_out) { return fp64_mma_peak(reps, tflops_out); }
 
 int dca_mf_corr_from_freqs(const double *reg_fi, const double *reg_fij, int seqs_len, int num_site_states,

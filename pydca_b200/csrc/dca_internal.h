@@ -136,6 +136,9 @@ int seqsum_launch(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st, 
 int seqsum_host(const float *x, const float *y, long n, long n0, float lam0, float lam1, float *out,
                 unsigned *stats8 = nullptr, float *kernel_ms = nullptr);
 
+// ---- align.cu -----------------------------------------------------------------------------
+int sw_scores_host(const uint8_t *msa, long N, int L, int q, const uint8_t *ref, int ref_len, int *scores_out);
+
 // ---- scoring.cu ---------------------------------------------------------------------------
 int plm_fn_apc_host(const float *h_x, int L, int q, double *fn, double *fn_apc);
 

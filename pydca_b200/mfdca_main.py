@@ -10,7 +10,7 @@ from argparse import ArgumentParser
 
 from . import dca_utilities
 from .meanfield_dca import MeanFieldDCA
-from .plmdca_main import _reject_refseq, configure_logging
+from .plmdca_main import _seqbackmapper, configure_logging
 
 logger = logging.getLogger(__name__)
 
@@ -26,7 +26,7 @@ def execute_from_command_line(msa_file=None, biomolecule=None, seqid=None, pseud
     if the_command is None or the_command.strip() not in DCA_COMPUTATION_SUBCOMMANDS:
         return None
     the_command = the_command.strip()
-    _reject_refseq(refseq_file)
+    mapper = _seqbackmapper(msa_file, refseq_file, biomolecule)
     inst = MeanFieldDCA(msa_file, biomolecule, seqid=seqid, pseudocount=pseudocount)
     meta = dca_utilities.mfdca_param_metadata(inst)
     if not output_dir:
@@ -40,21 +40,21 @@ def execute_from_command_line(msa_file=None, biomolecule=None, seqid=None, pseud
     if the_command == "compute_di":
         if apc:
             score_type = " MF DI average product corrected (APC)"
-            scores, path = inst.compute_sorted_DI_APC(), out("MFDCA_apc_di_scores_")
+            scores, path = inst.compute_sorted_DI_APC(seqbackmapper=mapper), out("MFDCA_apc_di_scores_")
         else:
             score_type = "raw DI"
-            scores, path = inst.compute_sorted_DI(), out("MFDCA_raw_di_scores_")
+            scores, path = inst.compute_sorted_DI(seqbackmapper=mapper), out("MFDCA_raw_di_scores_")
         dca_utilities.write_sorted_dca_scores(path, scores, metadata=meta, score_type=score_type)
     if the_command == "compute_fn":
         if apc:
             score_type = "MFDCA Frobenius norm, average product corrected (APC)"
-            scores, path = inst.compute_sorted_FN_APC(), out("MFDCA_apc_fn_scores_")
+            scores, path = inst.compute_sorted_FN_APC(seqbackmapper=mapper), out("MFDCA_apc_fn_scores_")
         else:
             score_type = "MFDCA raw Frobenius norm"
-            scores, path = inst.compute_sorted_FN(), out("MFDCA_raw_fn_scores_")
+            scores, path = inst.compute_sorted_FN(seqbackmapper=mapper), out("MFDCA_raw_fn_scores_")
         dca_utilities.write_sorted_dca_scores(path, scores, metadata=meta, score_type=score_type)
     if the_command == "compute_params":
-        fields, couplings = inst.compute_params(ranked_by=ranked_by, linear_dist=linear_dist,
+        fields, couplings = inst.compute_params(seqbackmapper=mapper, ranked_by=ranked_by, linear_dist=linear_dist,
                                                 num_site_pairs=num_site_pairs)
         meta.append("#\tTotal number of sites whose fields are extracted: {}".format(len(fields)))
         dca_utilities.write_fields_csv(out("fields_"), fields, metadata=meta)

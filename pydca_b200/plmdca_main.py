@@ -3,9 +3,9 @@ pydca/plmdca_main.py:259-352 (`plmdca {compute_fn,compute_di,compute_params}`).
 
     python -m pydca_b200.plmdca_main compute_fn protein msa.fa --max_iterations 500 --apc
 
---num_threads is accepted and ignored (the work runs on the GPU).  --refseq_file
-needs the reference's SequenceBackmapper (Biopython pairwise alignment, SURVEY 8f-4,
-out of scope): it is rejected with a clear message instead of silently ignored.
+--num_threads is accepted and ignored (the work runs on the GPU).  --refseq_file maps
+the scores to the positions of a reference sequence through pydca_b200.sequence_backmapper
+(Biopython-free; the search over the alignment runs on the GPU).
 """
 import logging
 import os
@@ -24,11 +24,12 @@ def configure_logging():
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(name)s %(levelname)s %(message)s")
 
 
-def _reject_refseq(refseq_file):
-    if refseq_file:
-        raise SystemExit("--refseq_file: reference-sequence back-mapping is outside the B200 hot path "
-                         "(pydca's SequenceBackmapper needs Biopython); pass a seqbackmapper object to the "
-                         "class API instead")
+def _seqbackmapper(msa_file, refseq_file, biomolecule):
+    """plmdca_main.py:185-192: back-mapping to a reference sequence when --refseq_file is given."""
+    if not refseq_file:
+        return None
+    from .sequence_backmapper import SequenceBackmapper
+    return SequenceBackmapper(msa_file=msa_file, refseq_file=refseq_file, biomolecule=biomolecule)
 
 
 def execute_from_command_line(biomolecule, msa_file, the_command=None, refseq_file=None, seqid=None,
@@ -38,11 +39,11 @@ def execute_from_command_line(biomolecule, msa_file, the_command=None, refseq_fi
     """pydca/plmdca_main.py:136-256."""
     if verbose:
         configure_logging()
-    _reject_refseq(refseq_file)
     inst = PlmDCA(msa_file, biomolecule, seqid=seqid, lambda_h=lambda_h, lambda_J=lambda_J,
                   max_iterations=max_iterations, num_threads=num_threads, verbose=verbose, arithmetic=arithmetic)
     if the_command not in DCA_COMPUTATION_SUBCOMMANDS:
         return None
+    mapper = _seqbackmapper(msa_file, refseq_file, biomolecule)
     meta = dca_utilities.plmdca_param_metadata(inst)
     if not output_dir:
         base, _ = os.path.splitext(os.path.basename(msa_file))
@@ -55,21 +56,21 @@ def execute_from_command_line(biomolecule, msa_file, the_command=None, refseq_fi
     if the_command == "compute_fn":
         if apc:
             score_type = "PLMDCA Frobenius norm, average product corrected (APC)"
-            scores, path = inst.compute_sorted_FN_APC(), out("PLMDCA_apc_fn_scores_")
+            scores, path = inst.compute_sorted_FN_APC(seqbackmapper=mapper), out("PLMDCA_apc_fn_scores_")
         else:
             score_type = "PLMDCA Frobenius norm, non-APC (not average product corrected)"
-            scores, path = inst.compute_sorted_FN(), out("PLMDCA_raw_fn_scores_")
+            scores, path = inst.compute_sorted_FN(seqbackmapper=mapper), out("PLMDCA_raw_fn_scores_")
         dca_utilities.write_sorted_dca_scores(path, scores, metadata=meta, score_type=score_type)
     if the_command == "compute_di":
         if apc:
             score_type = "PLMDCA  DI scores, average product corrected (APC)"
-            scores, path = inst.compute_sorted_DI_APC(), out("PLMDCA_apc_di_scores_")
+            scores, path = inst.compute_sorted_DI_APC(seqbackmapper=mapper), out("PLMDCA_apc_di_scores_")
         else:
             score_type = "PLMDCA DI scores, non-APC (not average product corrected)"
-            scores, path = inst.compute_sorted_DI(), out("PLMDCA_raw_di_scores_")
+            scores, path = inst.compute_sorted_DI(seqbackmapper=mapper), out("PLMDCA_raw_di_scores_")
         dca_utilities.write_sorted_dca_scores(path, scores, metadata=meta, score_type=score_type)
     if the_command == "compute_params":
-        fields, couplings = inst.compute_params(ranked_by=ranked_by, linear_dist=linear_dist,
+        fields, couplings = inst.compute_params(seqbackmapper=mapper, ranked_by=ranked_by, linear_dist=linear_dist,
                                                 num_site_pairs=num_site_pairs)
         meta.append("#\tTotal number of sites whose fields are extracted: {}".format(len(fields)))
         dca_utilities.write_fields_csv(out("fields_"), fields, metadata=meta)
