@@ -32,7 +32,7 @@ _f64p = ctypes.POINTER(ctypes.c_double)
 
 def build(ref=True):
     """Compile the checkers (building the checker is not using it)."""
-    targets = ["port"]
+    targets = ["port", "seqmodel"]
     if ref and os.path.isdir("/root/reference/pydca/plmdca"):
         targets.append("ref")
     subprocess.run(["make", "-s", "-C", _HERE] + targets, check=True)

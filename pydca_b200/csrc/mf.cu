@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstring>
 #include <thread>
 #include <vector>
 
@@ -290,7 +291,8 @@ dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, i
 // (0.33 ms per block); with the symmetric update halving the GEMM time that single-CTA kernel had
 // become the critical path of the whole inverse.
 __global__ void __launch_bounds__(512, 1)
-gj_diag_inv_kernel(const double *__restrict__ A, int ld, int k, double *__restrict__ Dinv, int *__restrict__ info)
+gj_diag_inv_kernel(const double *__restrict__ A, int ld, int k, double *__restrict__ Dinv, int *__restrict__ info,
+                   double pivot_tol)
 {
     __shared__ double prow[2][GJ_B], pcol[2][GJ_B];
     const int tid = threadIdx.x, tr = tid >> 5, tc = tid & 31;
@@ -326,7 +328,9 @@ gj_diag_inv_kernel(const double *__restrict__ A, int ld, int k, double *__restri
         }
         __syncthreads();
         const double d = prow[buf][p];
-        if (tid == 0 && !(fabs(d) > 0.0) && info) *info = k * GJ_B + p + 1;
+        // a symmetric positive definite matrix has positive pivots (Schur complements); anything at or
+        // below pivot_tol = 1e-14 * max diagonal is singular / indefinite to working precision (NaN included)
+        if (tid == 0 && !(d > pivot_tol) && info && *info == 0) *info = k * GJ_B + p + 1;
         const double piv = 1.0 / d;
         double rowv[4], colv[8];
 #pragma unroll
@@ -418,6 +422,19 @@ __global__ void negate_copy_kernel(const double *__restrict__ A, int ld, int n, 
 static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
 {
     const int nb = npad / GJ_B;
+    double pivot_tol = 0.0;
+    {   // scale of the problem: the largest diagonal entry (n doubles, strided copy)
+        std::vector<double> diag((size_t)npad);
+        DCA_CUDA(cudaMemcpy2DAsync(diag.data(), sizeof(double), d_A, sizeof(double) * (size_t)(npad + 1), sizeof(double),
+                                   (size_t)npad, cudaMemcpyDeviceToHost, st));
+        DCA_CUDA(cudaStreamSynchronize(st));
+        double mx = 0.0;
+        for (double v : diag) {
+            if (!(v > 0.0)) { set_error("mf_couplings: non-positive diagonal entry %g: the matrix is not positive definite", v); return -1; }
+            mx = std::max(mx, v);
+        }
+        pivot_tol = 1e-14 * mx;
+    }
     double *d_Dinv[2] = {nullptr, nullptr}, *d_Ck = nullptr, *d_Rk = nullptr, *d_Arow = nullptr;
     int *d_info = nullptr;
     if (!dev_alloc_t(&d_Dinv[0], (size_t)GJ_B * GJ_B) || !dev_alloc_t(&d_Dinv[1], (size_t)GJ_B * GJ_B) ||
@@ -437,7 +454,7 @@ static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
     const size_t smem_gemm = sizeof(double) * (2 * GJ_B * GM_AS + 2 * GM_KC * GM_BS);
     const size_t smem_diag = 0;          // the diagonal-block kernel keeps the block in registers
     DCA_CUDA(cudaFuncSetAttribute(dgemm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
-    DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, st, d_A, npad, 0, d_Dinv[0], d_info);
+    DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, st, d_A, npad, 0, d_Dinv[0], d_info, pivot_tol);
     for (int k = 0; k < nb; ++k) {
         double *Dk = d_Dinv[k & 1];
         if (k > 0) DCA_CUDA(cudaStreamWaitEvent(st, ev_diag, 0));          // Dinv_k from the side stream
@@ -456,7 +473,7 @@ static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
                        d_A + off * npad + off, npad, d_Ck + off * GJ_B, GJ_B, d_Rk + off, npad, -1.0, 1.0, -1, -1, -1, 0);
             DCA_CUDA(cudaEventRecord(ev_tile, st));
             DCA_CUDA(cudaStreamWaitEvent(side, ev_tile, 0));
-            DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, side, d_A, npad, k + 1, d_Dinv[(k + 1) & 1], d_info);
+            DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, side, d_A, npad, k + 1, d_Dinv[(k + 1) & 1], d_info, pivot_tol);
             DCA_CUDA(cudaEventRecord(ev_diag, side));
         }
         // A[i,j] -= Ck[i] * Rk[j] for the tiles j <= i of every row block i != k (tile (k+1,k+1) already done):
@@ -475,7 +492,11 @@ static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
     DCA_CUDA(cudaStreamSynchronize(side));
     cudaStreamDestroy(side); cudaEventDestroy(ev_tile); cudaEventDestroy(ev_diag);
     dev_free(d_Dinv[0]); dev_free(d_Dinv[1]); dev_free(d_Ck); dev_free(d_Rk); dev_free(d_Arow); dev_free(d_info);
-    if (info != 0) { set_error("mf_couplings: zero pivot at row %d: the correlation matrix is singular (increase the pseudocount)", info - 1); return -1; }
+    if (info != 0) {
+        set_error("mf_couplings: pivot at row %d is not positive: the correlation matrix is singular or indefinite to "
+                  "working precision (increase the pseudocount)", info - 1);
+        return -1;
+    }
     return 0;
 }
 
@@ -812,6 +833,29 @@ int fp64_mma_peak(int reps, double *tflops_out)
     return 0;
 }
 
+// largest |A[r][c] - A[c][r]| and largest |A[r][c]| (as ordered bit patterns of non-negative doubles)
+__global__ void asymmetry_kernel(const double *__restrict__ A, int ld, int n, unsigned long long *__restrict__ out2)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    double da = 0.0, mx = 0.0;
+    if (idx < (long)n * n) {
+        const int r = (int)(idx / n), c = (int)(idx - (long)r * n);
+        const double v = A[(size_t)r * ld + c];
+        mx = fabs(v);
+        if (c > r) da = fabs(v - A[(size_t)c * ld + r]);
+        if (v != v) da = __longlong_as_double(0x7ff0000000000000LL);       // NaN input: report as infinitely asymmetric
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        da = fmax(da, __shfl_xor_sync(0xffffffffu, da, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out2, (unsigned long long)__double_as_longlong(da));
+        atomicMax(out2 + 1, (unsigned long long)__double_as_longlong(mx));
+    }
+}
+
 int mf_couplings_host(const double *corr, int n, double *out)
 {
     if (require_device() != 0) return -1;
@@ -826,7 +870,31 @@ int mf_couplings_host(const double *corr, int n, double *out)
         DCA_CUDA(cudaMemcpy2D(d_A + (size_t)n * npad + n, sizeof(double) * (size_t)(npad + 1), ones.data(),
                               sizeof(double), sizeof(double), (size_t)(npad - n), cudaMemcpyHostToDevice));
     }
-    int rc = gj_invert_device(d_A, npad, 0);
+    // The reference inverts with a general, pivoted LU (np.linalg.inv, msa_numerics.py:340); the kernel
+    // here is a symmetric, non-pivoting elimination that reads the lower tiles only.  It is exact for what
+    // construct_corr_mat produces (symmetric positive definite for pseudocount > 0); anything else is
+    // refused instead of silently giving wrong couplings.
+    int rc = 0;
+    {
+        DevBuf<unsigned long long> d_chk;
+        unsigned long long h_chk[2] = {0, 0};
+        if (!d_chk.alloc(2)) rc = -1;
+        if (rc == 0) {
+            cudaMemset(d_chk, 0, sizeof h_chk);
+            DCA_LAUNCH(asymmetry_kernel, (unsigned)ceil_div<long>((long)n * n, 256), 256, 0, 0, d_A, npad, n, d_chk.p);
+            if (cudaMemcpy(h_chk, d_chk, sizeof h_chk, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("mf_couplings: symmetry check failed"); rc = -1; }
+        }
+        if (rc == 0) {
+            double asym, mx;
+            memcpy(&asym, &h_chk[0], 8); memcpy(&mx, &h_chk[1], 8);
+            if (!(asym <= 1e-12 * mx)) {
+                set_error("mf_couplings: corr_mat is not symmetric (max |C - C^T| = %g, max |C| = %g); only symmetric positive "
+                          "definite matrices (construct_corr_mat's output) can be inverted here", asym, mx);
+                rc = -1;
+            }
+        }
+    }
+    if (rc == 0) rc = gj_invert_device(d_A, npad, 0);
     if (rc == 0) {
         if (cudaMalloc(&d_out, sizeof(double) * (size_t)n * n) != cudaSuccess) { set_error("mf_couplings: out of device memory"); rc = -1; }
     }

@@ -440,3 +440,38 @@ def test_cli_config1_mfdca_and_plmdca(tmp_path, golden):
                              "--lambda_J", "2.0", "--output_dir", str(out_dir)])
     rows = [l for l in (out_dir / "PLMDCA_raw_fn_scores_toy.txt").read_text().splitlines() if not l.startswith("#")]
     assert len(rows) == 7 * 6 // 2
+
+
+def test_compute_couplings_refuses_what_it_cannot_invert():
+    """ADVICE (round 1): the reference inverts with a general pivoted LU (np.linalg.inv,
+    msa_numerics.py:340); the GPU kernel is a symmetric non-pivoting elimination on the lower
+    tiles.  Asymmetric, indefinite or numerically singular input must raise, never return wrong
+    couplings; a moderately ill-conditioned SPD matrix must still invert accurately."""
+    from pydca_b200 import msa_numerics
+    rng = np.random.default_rng(12)
+    n = 300
+    a = rng.standard_normal((n, n))
+    spd = a @ a.T / n + 0.5 * np.eye(n)
+    got = msa_numerics.compute_couplings(corr_mat=spd)
+    assert relmax(got, -np.linalg.inv(spd)) <= 1e-10
+    asym = spd.copy()
+    asym[3, 7] += 1e-3
+    with pytest.raises(lib().DcaBackendError, match="not symmetric"):
+        msa_numerics.compute_couplings(corr_mat=asym)
+    indef = spd.copy()
+    indef[5, 5] = -1.0
+    with pytest.raises(lib().DcaBackendError):
+        msa_numerics.compute_couplings(corr_mat=indef)
+    u = rng.standard_normal((n, 3))
+    singular = u @ u.T                                    # rank 3: Schur pivots collapse to round-off
+    with pytest.raises(lib().DcaBackendError, match="singular or indefinite|not positive"):
+        msa_numerics.compute_couplings(corr_mat=singular)
+    q_, _ = np.linalg.qr(a)
+    illc = (q_ * np.logspace(0, -8, n)) @ q_.T            # SPD, condition number 1e8
+    illc = (illc + illc.T) / 2
+    got = msa_numerics.compute_couplings(corr_mat=illc)
+    assert relmax(got @ illc, -np.eye(n)) <= 1e-6
+    nan = spd.copy()
+    nan[2, 2] = np.nan
+    with pytest.raises(lib().DcaBackendError):
+        msa_numerics.compute_couplings(corr_mat=nan)
