@@ -430,7 +430,7 @@ static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
         DCA_CUDA(cudaStreamSynchronize(st));
         double mx = 0.0;
         for (double v : diag) {
-            if (!(v > 0.0)) { set_error("mf_couplings: non-positive diagonal entry %g: the matrix is not positive definite", v); return -1; }
+            if (!(v > 0.0)) { set_error("mf_couplings: non-positive diagonal entry %g: the matrix is singular or not positive definite", v); return -1; }
             mx = std::max(mx, v);
         }
         pivot_tol = 1e-14 * mx;

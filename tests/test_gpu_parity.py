@@ -470,7 +470,7 @@ def test_compute_couplings_refuses_what_it_cannot_invert():
     illc = (q_ * np.logspace(0, -8, n)) @ q_.T            # SPD, condition number 1e8
     illc = (illc + illc.T) / 2
     got = msa_numerics.compute_couplings(corr_mat=illc)
-    assert relmax(got @ illc, -np.eye(n)) <= 1e-6
+    assert relmax(got, -np.linalg.inv(illc)) <= 1e-6       # forward error ~ cond * eps for both
     nan = spd.copy()
     nan[2, 2] = np.nan
     with pytest.raises(lib().DcaBackendError):
