@@ -69,6 +69,26 @@ def first_record_length(file_name):
     return n, length
 
 
+def first_sequence_length(file_name):
+    """Length of record 0 without walking the whole file (the C reader does the rest)."""
+    length, started = 0, False
+    with open(file_name) as fh:
+        for line in fh:
+            line = line.strip()
+            if not line:
+                continue
+            if line.startswith(">"):
+                if started and length:
+                    break
+                started = True
+            else:
+                started = True
+                length += len(line)
+    if not length:
+        raise ValueError("no sequences found in %s" % file_name)
+    return length
+
+
 def _num_states(biomolecule):
     b = biomolecule.strip().upper()
     if b not in ("PROTEIN", "RNA"):
@@ -79,8 +99,7 @@ def _num_states(biomolecule):
 def get_alignment_zero_based(file_name, biomolecule="protein"):
     """uint8[N, L], states 0..q-1, unique rows in first-occurrence order."""
     b, _ = _num_states(biomolecule)
-    _, length = first_record_length(file_name)
-    return _lib.read_fasta(file_name, b, length)
+    return _lib.read_fasta(file_name, b, first_sequence_length(file_name))
 
 
 def alignment_zero_based(alignment, biomolecule="protein"):

@@ -21,13 +21,39 @@ class PlmDCAException(Exception):
     """Implements exceptions related to PlmDCA computation"""
 
 
-def _sorted_pairs(scores, seqs_len):
+_PAIR_TUPLES = {}
+
+
+def _pair_tuples(seqs_len):
+    """[(i, j)] for i < j in pair order, built once per L."""
+    pt = _PAIR_TUPLES.get(seqs_len)
+    if pt is None:
+        iu, ju = np.triu_indices(seqs_len, k=1)
+        pt = _PAIR_TUPLES[seqs_len] = list(zip(iu.tolist(), ju.tolist()))
+    return pt
+
+
+class _ScoreList(list):
+    """A ranked [((i, j), score), ...] list that also carries its content as arrays (pair index in
+    pair order, score), so that the APC step does not have to parse 10^5 tuples back."""
+    __slots__ = ("pair_idx", "values", "seqs_len", "arrays_only")
+
+
+def _ranked(pair_idx, values, seqs_len, materialize=True):
+    """materialize=False: arrays only (an intermediate result handed straight to the APC step; building
+    4.5e4 tuples costs as much as the whole device pipeline at L = 300)."""
+    pt = _pair_tuples(seqs_len)
+    out = _ScoreList([(pt[k], v) for k, v in zip(pair_idx.tolist(), values.tolist())] if materialize else [])
+    out.pair_idx, out.values, out.seqs_len, out.arrays_only = pair_idx, values, seqs_len, not materialize
+    return out
+
+
+def _sorted_pairs(scores, seqs_len, materialize=True):
     """[((i, j), score), ...] sorted like ``sorted(..., reverse=True)``: descending,
     ties keep (i, j) order (plmdca.py:478)."""
-    scores = np.asarray(scores)
-    iu, ju = np.triu_indices(seqs_len, k=1)
+    scores = np.asarray(scores, dtype=np.float64)
     order = np.argsort(-scores, kind="stable")
-    return list(zip(zip(iu[order].tolist(), ju[order].tolist()), scores[order].tolist()))
+    return _ranked(order, scores[order], seqs_len, materialize)
 
 
 def average_product_correction(sorted_scores, seqs_len):
@@ -36,18 +62,29 @@ def average_product_correction(sorted_scores, seqs_len):
     unbuffered np.add.at below adds in exactly that order, with plain float64 additions as
     sum() did on the Pythons the reference ran on (3.12's sum() is compensated: <= 1 ulp apart)."""
     n = seqs_len
-    pairs = np.array([p for p, _ in sorted_scores], dtype=np.int64).reshape(-1, 2)
-    vals = np.array([s for _, s in sorted_scores], dtype=np.float64)
+    iu, ju = np.triu_indices(n, k=1)
+    if isinstance(sorted_scores, _ScoreList) and sorted_scores.seqs_len == n and (
+            sorted_scores.arrays_only or len(sorted_scores) == len(sorted_scores.values)):
+        idx, vals = sorted_scores.pair_idx, sorted_scores.values
+    else:                                   # a foreign list (e.g. back-mapped scores): parse it
+        first = np.full((n, n), -1, dtype=np.int64)
+        first[iu, ju] = np.arange(iu.size)
+        pairs = np.array([p for p, _ in sorted_scores], dtype=np.int64).reshape(-1, 2)
+        idx = first[pairs[:, 0], pairs[:, 1]]
+        vals = np.array([s for _, s in sorted_scores], dtype=np.float64)
+        if (idx < 0).any():
+            raise ValueError("average_product_correction expects site pairs (i, j) with i < j < %d" % n)
+    pi, pj = iu[idx], ju[idx]
     site_sum = np.zeros(n, dtype=np.float64)
-    np.add.at(site_sum, pairs.ravel(), np.repeat(vals, 2))
+    np.add.at(site_sum, np.stack([pi, pj], axis=1).ravel(), np.repeat(vals, 2))
     av = site_sum / float(n - 1)
     tot = 0.0
     for v in av.tolist():          # plain left-to-right float sum (the reference's Python 3.5-3.7 sum())
         tot += v
     av_all = tot / float(n)
-    corrected = vals - av[pairs[:, 0]] * (av[pairs[:, 1]] / av_all)
+    corrected = vals - av[pi] * (av[pj] / av_all)
     order = np.argsort(-corrected, kind="stable")
-    return [(sorted_scores[k][0], v) for k, v in zip(order.tolist(), corrected[order].tolist())]
+    return _ranked(idx[order], corrected[order], n)
 
 
 class PlmDCA:
