@@ -223,30 +223,35 @@ class MeanFieldDCA:
     def get_site_pair_di_score(self):
         """meanfield_dca.py:793-830 -> {(i, j): DI}."""
         logger.info("\n\tComputing direct information")
+        di = self._di_scores()
+        iu, ju = np.triu_indices(self.__sequences_len, k=1)
+        return {(int(i), int(j)): s for i, j, s in zip(iu, ju, di.tolist())}
+
+    def _di_scores(self):
         res = msa_numerics.mean_field_scores(self.__msa0, self.__num_site_states, self.__sequences_weight,
                                              self.__pseudocount, want_couplings=self.keep_couplings, want_di=True)
         self.__couplings = res.get("couplings")
         self.last_stage_ms = self._stage_dict(res["stage_ms"])
-        di = res["di"]
-        iu, ju = np.triu_indices(self.__sequences_len, k=1)
-        return {(int(i), int(j)): s for i, j, s in zip(iu, ju, di.tolist())}
+        return res["di"]
 
-    def compute_sorted_DI(self, seqbackmapper=None):
-        unsorted_di = self.get_site_pair_di_score()
-        sorted_di = sorted(unsorted_di.items(), key=lambda k: k[1], reverse=True)
+    def compute_sorted_DI(self, seqbackmapper=None, _materialize=True):
+        """meanfield_dca.py:833-868: the (i, j)-ordered dictionary sorted by score, descending, stable."""
+        logger.info("\n\tComputing direct information")
+        sorted_di = _sorted_pairs(self._di_scores(), self.__sequences_len,
+                                  _materialize or seqbackmapper is not None)
         if seqbackmapper is not None:
             sorted_di = self.get_mapped_site_pairs_dca_scores(sorted_di, seqbackmapper)
         return sorted_di
 
     def compute_sorted_DI_APC(self, seqbackmapper=None):
-        sorted_di = self.compute_sorted_DI()
+        sorted_di = self.compute_sorted_DI(_materialize=False)
         logger.info("\n\tPerforming average product correction (APC) of DI scores")
         out = average_product_correction(sorted_di, self.__sequences_len)
         if seqbackmapper is not None:
             out = self.get_mapped_site_pairs_dca_scores(out, seqbackmapper)
         return out
 
-    def compute_sorted_FN(self, seqbackmapper=None):
+    def compute_sorted_FN(self, seqbackmapper=None, _materialize=True):
         """meanfield_dca.py:902-943."""
         logger.info("\n\tComputing Frobenius norm of couplings")
         res = msa_numerics.mean_field_scores(self.__msa0, self.__num_site_states, self.__sequences_weight,
@@ -254,14 +259,14 @@ class MeanFieldDCA:
         self.__couplings = res.get("couplings")
         self.last_stage_ms = self._stage_dict(res["stage_ms"])
         fn = res["fn"]
-        fn_sorted = _sorted_pairs(fn, self.__sequences_len)
+        fn_sorted = _sorted_pairs(fn, self.__sequences_len, _materialize or seqbackmapper is not None)
         if seqbackmapper is not None:
             fn_sorted = self.get_mapped_site_pairs_dca_scores(fn_sorted, seqbackmapper)
         return fn_sorted
 
     def compute_sorted_FN_APC(self, seqbackmapper=None):
         """meanfield_dca.py:946-988."""
-        raw_fn = self.compute_sorted_FN()
+        raw_fn = self.compute_sorted_FN(_materialize=False)
         logger.info("\n\tPerforming average product correction (APC) to Frobenius norm of couplings.")
         out = average_product_correction(raw_fn, self.__sequences_len)
         if seqbackmapper is not None:
