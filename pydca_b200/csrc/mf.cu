@@ -196,12 +196,20 @@ __global__ void mf_corr_kernel(const double *__restrict__ F, size_t f_split_stri
 }
 
 // ------------------------------------------------------------------------------
-// FP64 tensor-core GEMM: C[128x128 tile] = beta*C + alpha * A[128xK] * B[Kx128],
-// K = 128.  grid = (N/128, M/128); CTA row-block `skip_rb` is skipped.
+// FP64 tensor-core GEMM: C[BM x 128 tile] = beta*C + alpha * A[BM x 128] * B[128 x 128], K = 128.
+// BM = 128 (8 warps) or 64 (4 warps, up to three CTAs per SM: with one 128 x 128 CTA per SM the
+// epilogue's read-modify-write of C -- 256 KB per tile at ~44 GB/s per SM, 20 % of the CTA's life --
+// overlapped with nothing).  Which tiles a launch touches is a `mode`:
+//   GM_ALL    grid (nb, rows/BM): every tile
+//   GM_PRIO   step k of the symmetric Gauss-Jordan, the tiles step k+1's pivot panel is built from:
+//             row block k+1 (tiles (k+1, j <= k+1)) and column block k+1 (tiles (i > k+1, k+1));
+//             grid (nb, 128/BM), blockIdx.x enumerates them
+//   GM_REST   the other tiles (i, j <= i) of every row block i != k (and not in the PRIO set)
 constexpr int GJ_B = 128;
 constexpr int GM_KC = 16;
 constexpr int GM_AS = 20;      // A smem row stride (doubles): 4 mod 16 -> conflict-free LDS.64
 constexpr int GM_BS = 132;     // B smem row stride (doubles)
+enum { GM_ALL = 0, GM_PRIO = 1, GM_REST = 2 };
 
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
 {
@@ -209,22 +217,33 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256, 1)
+template <int BM>
+__global__ void __launch_bounds__(BM * 2, (BM == 64) ? 3 : 1)
 dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, int lda,
-                const double *__restrict__ B, int ldb, double alpha, double beta, int skip_rb,
-                int skip_tr, int skip_tc, int lower_only)
+                const double *__restrict__ B, int ldb, double alpha, double beta, int mode, int k)
 {
-    if ((int)blockIdx.y == skip_rb) return;
-    if (lower_only && blockIdx.x > blockIdx.y) return;          // symmetric sweep: tiles (i, j <= i) only
-    if ((int)blockIdx.y == skip_tr && (int)blockIdx.x == skip_tc) return;
+    constexpr int NT = BM * 2;                 // threads: one warp per 32 x 64 patch
+    constexpr int SUB = GJ_B / BM;             // row sub-tiles per 128-row block
+    int tr, tc, sub;                           // 128-blocked tile coordinates + row sub-tile
+    if (mode == GM_ALL) {
+        tc = blockIdx.x; tr = blockIdx.y / SUB; sub = blockIdx.y % SUB;
+    } else if (mode == GM_PRIO) {
+        const int t = blockIdx.x;
+        sub = blockIdx.y;
+        if (t <= k + 1) { tr = k + 1; tc = t; } else { tr = t; tc = k + 1; }
+    } else {
+        tc = blockIdx.x; tr = blockIdx.y / SUB; sub = blockIdx.y % SUB;
+        if (tc > tr || tr == k || tr == k + 1 || (tc == k + 1 && tr > k + 1)) return;
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *As = reinterpret_cast<double *>(smem_raw);                 // [2][128][GM_AS]
-    double *Bs = As + 2 * GJ_B * GM_AS;                                // [2][GM_KC][GM_BS]
+    double *As = reinterpret_cast<double *>(smem_raw);                 // [2][BM][GM_AS]
+    double *Bs = As + 2 * BM * GM_AS;                                  // [2][GM_KC][GM_BS]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1;                           // 4 x 2 warps: 32 x 64 per warp
+    const int wm = warp >> 1, wn = warp & 1;                           // (BM/32) x 2 warps: 32 x 64 per warp
     const int g = lane >> 2, t4 = lane & 3;
-    const double *Ab = A + (size_t)blockIdx.y * GJ_B * lda;
-    const double *Bb = B + (size_t)blockIdx.x * GJ_B;
+    const size_t row0 = (size_t)tr * GJ_B + (size_t)sub * BM;
+    const double *Ab = A + row0 * lda;
+    const double *Bb = B + (size_t)tc * GJ_B;
 
     double acc[4][8][2];
 #pragma unroll
@@ -233,14 +252,14 @@ dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, i
         for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
 
     auto stage = [&](int buf, int kc) {
-        // A chunk: 128 rows x 16 doubles (8 x 16B per row)
-        for (int t = tid; t < GJ_B * 8; t += 256) {
+        // A chunk: BM rows x 16 doubles (8 x 16B per row)
+        for (int t = tid; t < BM * 8; t += NT) {
             const int row = t >> 3, seg = t & 7;
-            cp_async16(As + ((size_t)buf * GJ_B + row) * GM_AS + seg * 2,
+            cp_async16(As + ((size_t)buf * BM + row) * GM_AS + seg * 2,
                        Ab + (size_t)row * lda + kc * GM_KC + seg * 2);
         }
         // B chunk: 16 rows x 128 doubles (64 x 16B per row)
-        for (int t = tid; t < GM_KC * 64; t += 256) {
+        for (int t = tid; t < GM_KC * 64; t += NT) {
             const int row = t >> 6, seg = t & 63;
             cp_async16(Bs + ((size_t)buf * GM_KC + row) * GM_BS + seg * 2,
                        Bb + (size_t)(kc * GM_KC + row) * ldb + seg * 2);
@@ -255,7 +274,7 @@ dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, i
         if (kc + 1 < NK) { stage(buf ^ 1, kc + 1); cp_async_wait<1>(); }
         else             { cp_async_wait<0>(); }
         __syncthreads();
-        const double *Ap = As + (size_t)buf * GJ_B * GM_AS + (wm * 32 + g) * GM_AS + t4;
+        const double *Ap = As + (size_t)buf * BM * GM_AS + (wm * 32 + g) * GM_AS + t4;
         const double *Bp = Bs + (size_t)buf * GM_KC * GM_BS + t4 * GM_BS + wn * 64 + g;
 #pragma unroll
         for (int k4 = 0; k4 < GM_KC / 4; ++k4) {
@@ -271,7 +290,7 @@ dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, i
         }
         __syncthreads();
     }
-    double *Cb = C + (size_t)blockIdx.y * GJ_B * ldc + (size_t)blockIdx.x * GJ_B;
+    double *Cb = C + row0 * ldc + (size_t)tc * GJ_B;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -287,9 +306,13 @@ dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, i
 // The block lives in REGISTERS: thread (tr, tc) = (warp, lane) owns the 8 x 4 patch rows tr*8.., cols
 // tc*4..; per pivot the owners publish the old pivot row and column through two small shared arrays
 // (double-buffered: one barrier per pivot) and every thread updates its patch from 4 + 8 values.
-// The first version kept the block in shared memory and moved 2 x 128 KB through it per pivot
-// (0.33 ms per block); with the symmetric update halving the GEMM time that single-CTA kernel had
-// become the critical path of the whole inverse.
+// The update of a pivot step is  a'[i][j] = a[i][j] - col[i] * row[j]  everywhere except in the pivot
+// row (row[j], pivot element 1/d) and the pivot column (-col[i]/d).  Selecting those cases per element
+// cost three 64-bit selects per FMA and made this single-CTA kernel issue-bound (0.185 ms per block,
+// the critical path of the look-ahead).  Instead the owners patch their registers BEFORE the update --
+// pivot column := 0 with row[p] := 1/d, pivot row := 0 with col[p] := -1 -- after which the one
+// formula gives exactly the special values (0 - c * (1/d), 0 - (-1) * r, 0 - (-1) * (1/d)): the
+// update is 32 plain FMAs per thread, the patches are switch statements only the owners run.
 __global__ void __launch_bounds__(512, 1)
 gj_diag_inv_kernel(const double *__restrict__ A, int ld, int k, double *__restrict__ Dinv, int *__restrict__ info,
                    double pivot_tol)
@@ -304,52 +327,47 @@ gj_diag_inv_kernel(const double *__restrict__ A, int ld, int k, double *__restri
         const double2 hi = *reinterpret_cast<const double2 *>(Ak + (size_t)(tr * 8 + i) * ld + tc * 4 + 2);
         a[i][0] = lo.x; a[i][1] = lo.y; a[i][2] = hi.x; a[i][3] = hi.y;
     }
+#define GJ_ROW_CASE(I) case I: prow[buf][tc * 4 + 0] = a[I][0]; prow[buf][tc * 4 + 1] = a[I][1]; \
+                               prow[buf][tc * 4 + 2] = a[I][2]; prow[buf][tc * 4 + 3] = a[I][3]; \
+                               a[I][0] = 0.0; a[I][1] = 0.0; a[I][2] = 0.0; a[I][3] = 0.0; break;
+#define GJ_COL_CASE(J) case J: _Pragma("unroll") for (int i = 0; i < 8; ++i) { pcol[buf][tr * 8 + i] = a[i][J]; a[i][J] = 0.0; } break;
     for (int p = 0; p < GJ_B; ++p) {
         const int buf = p & 1;
-        if (tr == (p >> 3)) {                          // my warp owns pivot row p (register row p & 7)
-            const int i0 = p & 7;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                double v = a[0][j];
-#pragma unroll
-                for (int i = 1; i < 8; ++i) v = (i0 == i) ? a[i][j] : v;
-                prow[buf][tc * 4 + j] = v;
-            }
+        const bool own_row = (tr == (p >> 3)), own_col = (tc == (p >> 2));
+        // the element (p, p) belongs to both owners: publish the column first (it still holds d),
+        // then the row -- whose copy of d is read back below as prow[p] -- and zero both
+        if (own_col) {                                 // my lane owns pivot column p (register column p & 3)
+            switch (p & 3) { GJ_COL_CASE(0) GJ_COL_CASE(1) GJ_COL_CASE(2) GJ_COL_CASE(3) }
         }
-        if (tc == (p >> 2)) {                          // my lane owns pivot column p (register column p & 3)
-            const int j0 = p & 3;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                double v = a[i][0];
-#pragma unroll
-                for (int j = 1; j < 4; ++j) v = (j0 == j) ? a[i][j] : v;
-                pcol[buf][tr * 8 + i] = v;
-            }
+        if (own_row) {                                 // my warp owns pivot row p (register row p & 7)
+            switch (p & 7) { GJ_ROW_CASE(0) GJ_ROW_CASE(1) GJ_ROW_CASE(2) GJ_ROW_CASE(3)
+                             GJ_ROW_CASE(4) GJ_ROW_CASE(5) GJ_ROW_CASE(6) GJ_ROW_CASE(7) }
         }
         __syncthreads();
-        const double d = prow[buf][p];
+        // prow[p] was zeroed by the column owner before the row was published: d comes from pcol
+        const double d = pcol[buf][p];
         // a symmetric positive definite matrix has positive pivots (Schur complements); anything at or
         // below pivot_tol = 1e-14 * max diagonal is singular / indefinite to working precision (NaN included)
         if (tid == 0 && !(d > pivot_tol) && info && *info == 0) *info = k * GJ_B + p + 1;
         const double piv = 1.0 / d;
         double rowv[4], colv[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rowv[j] = prow[buf][tc * 4 + j] * piv;      // scaled pivot row
-#pragma unroll
-        for (int i = 0; i < 8; ++i) colv[i] = pcol[buf][tr * 8 + i];
+        for (int j = 0; j < 4; ++j) {
+            const double r = prow[buf][tc * 4 + j] * piv;                       // scaled pivot row
+            rowv[j] = (tc * 4 + j == p) ? piv : r;                              // (prow[p] is 0)
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const bool rp = (tr * 8 + i == p);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool cp = (tc * 4 + j == p);
-                double v;
-                if (rp) v = cp ? piv : rowv[j];
-                else v = cp ? (-colv[i] * piv) : (a[i][j] - colv[i] * rowv[j]);
-                a[i][j] = v;
-            }
+            const double c = pcol[buf][tr * 8 + i];
+            colv[i] = (tr * 8 + i == p) ? -1.0 : c;
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[i][j] = a[i][j] - colv[i] * rowv[j];
     }
+#undef GJ_ROW_CASE
+#undef GJ_COL_CASE
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         double *o = Dinv + (size_t)(tr * 8 + i) * GJ_B + tc * 4;
@@ -416,9 +434,16 @@ __global__ void negate_copy_kernel(const double *__restrict__ A, int ld, int n, 
 
 // d_A: npad x npad (row-major, ld = npad), SYMMETRIC positive definite, overwritten by its inverse.
 // Only the tiles on and below the diagonal are read and updated (see gj_gather_kernel).
-// Look-ahead schedule: the 128x128 diagonal inverse is a single-CTA, latency-bound kernel
-// (~0.33 ms); step k therefore updates tile (k+1,k+1) first, and a second stream inverts it
-// while the main stream finishes the rank-128 update of step k.
+// Look-ahead schedule.  Step k needs the pivot panel (Ck, Rk = Dinv_k * row block k), whose producers
+// -- the single-CTA diagonal inverse, the gather and a 128-row GEMM -- are latency-bound kernels
+// that leave the GPU empty (0.06 + 0.19 ms per step when they ran in line).  Everything they read
+// lives in row block k+1 and column block k+1, so step k updates those nb tiles first (GM_PRIO), and
+// a high-priority side stream builds panel k+1 (double-buffered Ck / Arow / Rk) while the main stream
+// finishes the rank-128 update of the remaining tiles (GM_REST) and stores row block k.
+//   main:  wait panel(k) | PRIO update(k) | record | REST update(k) | row block k := Rk
+//   side:                                   wait   | Dinv(k+1) | gather(k+1) | Rk(k+1) | record panel(k+1)
+// gather(k+1) resets column block k+1 of A, which REST(k) does not touch; REST(k+1) follows on the
+// main stream, after row block k has been stored.
 static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
 {
     const int nb = npad / GJ_B;
@@ -435,63 +460,68 @@ static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
         }
         pivot_tol = 1e-14 * mx;
     }
-    double *d_Dinv[2] = {nullptr, nullptr}, *d_Ck = nullptr, *d_Rk = nullptr, *d_Arow = nullptr;
-    int *d_info = nullptr;
-    if (!dev_alloc_t(&d_Dinv[0], (size_t)GJ_B * GJ_B) || !dev_alloc_t(&d_Dinv[1], (size_t)GJ_B * GJ_B) ||
-        !dev_alloc_t(&d_Ck, (size_t)npad * GJ_B) || !dev_alloc_t(&d_Rk, (size_t)npad * GJ_B) ||
-        !dev_alloc_t(&d_Arow, (size_t)npad * GJ_B) || !dev_alloc_t(&d_info, (size_t)1))
-        return -1;
+    DevBuf<double> Dinv, Ck[2], Rk[2], Arow[2];
+    DevBuf<int> info_buf;
+    if (!Dinv.alloc((size_t)GJ_B * GJ_B) || !info_buf.alloc(1)) return -1;
+    for (int b = 0; b < 2; ++b)
+        if (!Ck[b].alloc((size_t)npad * GJ_B) || !Rk[b].alloc((size_t)npad * GJ_B) || !Arow[b].alloc((size_t)npad * GJ_B))
+            return -1;
+    int *d_info = info_buf.p;
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_tile = nullptr, ev_diag = nullptr;
-    {   // highest priority: its single CTA must get an SM while the big update is still queued
+    cudaEvent_t ev_prio = nullptr, ev_panel = nullptr;
+    {   // highest priority: its small grids must get SMs while the big update is still queued
         int prio_lo = 0, prio_hi = 0;
         DCA_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         DCA_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
     }
-    DCA_CUDA(cudaEventCreateWithFlags(&ev_tile, cudaEventDisableTiming));
-    DCA_CUDA(cudaEventCreateWithFlags(&ev_diag, cudaEventDisableTiming));
+    DCA_CUDA(cudaEventCreateWithFlags(&ev_prio, cudaEventDisableTiming));
+    DCA_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
     DCA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
-    const size_t smem_gemm = sizeof(double) * (2 * GJ_B * GM_AS + 2 * GM_KC * GM_BS);
-    const size_t smem_diag = 0;          // the diagonal-block kernel keeps the block in registers
-    DCA_CUDA(cudaFuncSetAttribute(dgemm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
-    DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, st, d_A, npad, 0, d_Dinv[0], d_info, pivot_tol);
-    for (int k = 0; k < nb; ++k) {
-        double *Dk = d_Dinv[k & 1];
-        if (k > 0) DCA_CUDA(cudaStreamWaitEvent(st, ev_diag, 0));          // Dinv_k from the side stream
-        // column block k and row block k rebuilt from the lower tiles; column block k reset to unit columns
-        DCA_LAUNCH(gj_gather_kernel, (unsigned)ceil_div<long>((long)npad * GJ_B, 256), 256, 0, st, d_A, npad, npad, k,
-                   d_Ck, d_Arow);
-        // Rk (128 x npad) = Dinv (128x128) * A[kblock rows, :]
-        DCA_LAUNCH(dgemm128_kernel, dim3(nb, 1), 256, smem_gemm, st,
-                   d_Rk, npad, Dk, GJ_B, d_Arow, npad, 1.0, 0.0, -1, -1, -1, 0);
-        int skr = -1;
+    constexpr int BM = 64, SUB = GJ_B / BM;
+    const size_t smem_gemm = sizeof(double) * (2 * BM * GM_AS + 2 * GM_KC * GM_BS);
+    DCA_CUDA(cudaFuncSetAttribute(dgemm128_kernel<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
+    // panel of step kk on stream s: Dinv_kk, column / row block kk rebuilt from the lower tiles (column
+    // block kk reset to unit columns), Rk (128 x npad) = Dinv_kk * row block kk
+    auto panel = [&](int kk, cudaStream_t s) -> int {
+        const int b = kk & 1;
+        DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, 0, s, d_A, npad, kk, Dinv.p, d_info, pivot_tol);
+        DCA_LAUNCH(gj_gather_kernel, (unsigned)ceil_div<long>((long)npad * GJ_B, 256), 256, 0, s, d_A, npad, npad, kk,
+                   Ck[b].p, Arow[b].p);
+        DCA_LAUNCH(dgemm128_kernel<BM>, dim3(nb, SUB), BM * 2, smem_gemm, s,
+                   Rk[b].p, npad, Dinv.p, GJ_B, Arow[b].p, npad, 1.0, 0.0, (int)GM_ALL, 0);
+        return 0;
+    };
+    int rc = panel(0, st);
+    for (int k = 0; k < nb && rc == 0; ++k) {
+        const int b = k & 1;
+        if (k > 0) DCA_CUDA(cudaStreamWaitEvent(st, ev_panel, 0));          // panel k from the side stream
         if (k + 1 < nb) {
-            // tile (k+1,k+1) first, then its inverse on the side stream
-            skr = k + 1;
-            const size_t off = (size_t)(k + 1) * GJ_B;
-            DCA_LAUNCH(dgemm128_kernel, dim3(1, 1), 256, smem_gemm, st,
-                       d_A + off * npad + off, npad, d_Ck + off * GJ_B, GJ_B, d_Rk + off, npad, -1.0, 1.0, -1, -1, -1, 0);
-            DCA_CUDA(cudaEventRecord(ev_tile, st));
-            DCA_CUDA(cudaStreamWaitEvent(side, ev_tile, 0));
-            DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, smem_diag, side, d_A, npad, k + 1, d_Dinv[(k + 1) & 1], d_info, pivot_tol);
-            DCA_CUDA(cudaEventRecord(ev_diag, side));
+            // A[i,j] -= Ck[i] * Rk[j] on row block k+1 and column block k+1 first, then panel k+1 on the side stream
+            DCA_LAUNCH(dgemm128_kernel<BM>, dim3(nb, SUB), BM * 2, smem_gemm, st,
+                       d_A, npad, Ck[b].p, GJ_B, Rk[b].p, npad, -1.0, 1.0, (int)GM_PRIO, k);
+            DCA_CUDA(cudaEventRecord(ev_prio, st));
+            DCA_CUDA(cudaStreamWaitEvent(side, ev_prio, 0));
+            // (panel k+1 overwrites the buffers of panel k-1: REST(k-1) precedes PRIO(k) on the main stream)
+            rc = panel(k + 1, side);
+            if (rc != 0) break;
+            DCA_CUDA(cudaEventRecord(ev_panel, side));
         }
-        // A[i,j] -= Ck[i] * Rk[j] for the tiles j <= i of every row block i != k (tile (k+1,k+1) already done):
-        // half the rank-128 updates of the unsymmetric algorithm (n^3 instead of 2 n^3 flops)
-        DCA_LAUNCH(dgemm128_kernel, dim3(nb, nb), 256, smem_gemm, st,
-                   d_A, npad, d_Ck, GJ_B, d_Rk, npad, -1.0, 1.0, k, skr, skr, 1);
+        // the tiles j <= i of every other row block i != k: half the rank-128 updates of the unsymmetric
+        // algorithm (n^3 instead of 2 n^3 flops)
+        DCA_LAUNCH(dgemm128_kernel<BM>, dim3(nb, nb * SUB), BM * 2, smem_gemm, st,
+                   d_A, npad, Ck[b].p, GJ_B, Rk[b].p, npad, -1.0, 1.0, (int)GM_REST, k);
         // row block k, columns 0 .. (k+1)*128: the part below / on the diagonal
-        DCA_CUDA(cudaMemcpy2DAsync(d_A + (size_t)k * GJ_B * npad, sizeof(double) * (size_t)npad, d_Rk,
+        DCA_CUDA(cudaMemcpy2DAsync(d_A + (size_t)k * GJ_B * npad, sizeof(double) * (size_t)npad, Rk[b].p,
                                    sizeof(double) * (size_t)npad, sizeof(double) * (size_t)(k + 1) * GJ_B, GJ_B,
                                    cudaMemcpyDeviceToDevice, st));
     }
-    DCA_LAUNCH(gj_mirror_kernel, dim3(npad / 32, npad / 32), dim3(32, 8), 0, st, d_A, npad, npad);
+    if (rc == 0) DCA_LAUNCH(gj_mirror_kernel, dim3(npad / 32, npad / 32), dim3(32, 8), 0, st, d_A, npad, npad);
     int info = 0;
-    DCA_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
-    DCA_CUDA(cudaStreamSynchronize(st));
-    DCA_CUDA(cudaStreamSynchronize(side));
-    cudaStreamDestroy(side); cudaEventDestroy(ev_tile); cudaEventDestroy(ev_diag);
-    dev_free(d_Dinv[0]); dev_free(d_Dinv[1]); dev_free(d_Ck); dev_free(d_Rk); dev_free(d_Arow); dev_free(d_info);
+    if (rc == 0) DCA_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    cudaStreamSynchronize(side);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(side); cudaEventDestroy(ev_prio); cudaEventDestroy(ev_panel);
+    if (rc != 0) return -1;
     if (info != 0) {
         set_error("mf_couplings: pivot at row %d is not positive: the correlation matrix is singular or indefinite to "
                   "working precision (increase the pseudocount)", info - 1);
