@@ -204,7 +204,9 @@ __global__ void mf_corr_kernel(const double *__restrict__ F, size_t f_split_stri
 //   GM_PRIO   step k of the symmetric Gauss-Jordan, the tiles step k+1's pivot panel is built from:
 //             row block k+1 (tiles (k+1, j <= k+1)) and column block k+1 (tiles (i > k+1, k+1));
 //             grid (nb, 128/BM), blockIdx.x enumerates them
-//   GM_REST   the other tiles (i, j <= i) of every row block i != k (and not in the PRIO set)
+//   GM_REST   the other tiles (i, j <= i) of every row block i != k (and not in the PRIO set); row block k
+//             itself is the pivot row of the step: its tiles are copied from B (= Rk).  grid
+//             (nb (nb + 1) / 2, 128/BM), blockIdx.x enumerates the lower tiles
 constexpr int GJ_B = 128;
 constexpr int GM_KC = 16;
 constexpr int GM_AS = 20;      // A smem row stride (doubles): 4 mod 16 -> conflict-free LDS.64
@@ -232,8 +234,24 @@ dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, i
         sub = blockIdx.y;
         if (t <= k + 1) { tr = k + 1; tc = t; } else { tr = t; tc = k + 1; }
     } else {
-        tc = blockIdx.x; tr = blockIdx.y / SUB; sub = blockIdx.y % SUB;
-        if (tc > tr || tr == k || tr == k + 1 || (tc == k + 1 && tr > k + 1)) return;
+        // blockIdx.x enumerates the tiles (tr, tc <= tr) row by row
+        const int t = blockIdx.x;
+        sub = blockIdx.y;
+        tr = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
+        while (tr * (tr + 1) / 2 > t) --tr;
+        tc = t - tr * (tr + 1) / 2;
+        if (tr == k + 1 || (tc == k + 1 && tr > k + 1)) return;
+        if (tr == k) {
+            // row block k of the result is Rk itself (B): copy this CTA's BM x 128 piece
+            const double *src = B + (size_t)sub * BM * ldb + (size_t)tc * GJ_B;
+            double *dst = C + ((size_t)k * GJ_B + (size_t)sub * BM) * ldc + (size_t)tc * GJ_B;
+            for (int e = threadIdx.x; e < BM * (GJ_B / 2); e += NT) {
+                const int r = e / (GJ_B / 2), c2 = e - r * (GJ_B / 2);
+                reinterpret_cast<double2 *>(dst + (size_t)r * ldc)[c2] = reinterpret_cast<const double2 *>(src + (size_t)r * ldb)[c2];
+            }
+            return;
+        }
     }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *As = reinterpret_cast<double *>(smem_raw);                 // [2][BM][GM_AS]
@@ -439,7 +457,7 @@ __global__ void negate_copy_kernel(const double *__restrict__ A, int ld, int n, 
 // that leave the GPU empty (0.06 + 0.19 ms per step when they ran in line).  Everything they read
 // lives in row block k+1 and column block k+1, so step k updates those nb tiles first (GM_PRIO), and
 // a high-priority side stream builds panel k+1 (double-buffered Ck / Arow / Rk) while the main stream
-// finishes the rank-128 update of the remaining tiles (GM_REST) and stores row block k.
+// finishes the rank-128 update of the remaining tiles and stores row block k (GM_REST).
 //   main:  wait panel(k) | PRIO update(k) | record | REST update(k) | row block k := Rk
 //   side:                                   wait   | Dinv(k+1) | gather(k+1) | Rk(k+1) | record panel(k+1)
 // gather(k+1) resets column block k+1 of A, which REST(k) does not touch; REST(k+1) follows on the
@@ -508,12 +526,9 @@ static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
         }
         // the tiles j <= i of every other row block i != k: half the rank-128 updates of the unsymmetric
         // algorithm (n^3 instead of 2 n^3 flops)
-        DCA_LAUNCH(dgemm128_kernel<BM>, dim3(nb, nb * SUB), BM * 2, smem_gemm, st,
+        // (row block k, the part below / on the diagonal, is stored by the same launch)
+        DCA_LAUNCH(dgemm128_kernel<BM>, dim3(nb * (nb + 1) / 2, SUB), BM * 2, smem_gemm, st,
                    d_A, npad, Ck[b].p, GJ_B, Rk[b].p, npad, -1.0, 1.0, (int)GM_REST, k);
-        // row block k, columns 0 .. (k+1)*128: the part below / on the diagonal
-        DCA_CUDA(cudaMemcpy2DAsync(d_A + (size_t)k * GJ_B * npad, sizeof(double) * (size_t)npad, Rk[b].p,
-                                   sizeof(double) * (size_t)npad, sizeof(double) * (size_t)(k + 1) * GJ_B, GJ_B,
-                                   cudaMemcpyDeviceToDevice, st));
     }
     if (rc == 0) DCA_LAUNCH(gj_mirror_kernel, dim3(npad / 32, npad / 32), dim3(32, 8), 0, st, d_A, npad, npad);
     int info = 0;
