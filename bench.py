@@ -458,7 +458,7 @@ def reweight_block():
     return out
 
 
-def c4_block():
+def c4_block(hbm_peak=None):
     """BASELINE configs[3] on ONE GPU: N=50000, L=500 (P = 55 M): a 10-iteration fit."""
     from pydca_b200 import _lib
     from pydca_b200.synthetic import synthetic_msa
@@ -477,13 +477,23 @@ def c4_block():
         ms.pop("export", None)
         adds = float(N) * L * L * Q
         smem_peak = 148 * 32 * 1.965
-        return {"workload": "C4 on one GPU: plmdca N=%d L=%d q=%d, first 10 L-BFGS iterations" % (N, L, Q),
-                "evals_per_s": res.evaluations / (res.device_ms * 1e-3), "evaluations": res.evaluations,
-                "fit_ms": res.device_ms, "kernel_ms": ms,
-                "logits_frac_of_smem_roof": adds / (ms["logits"] * 1e-3) / 1e9 / smem_peak,
-                "scatter_frac_of_smem_roof": adds / (ms["scatter"] * 1e-3) / 1e9 / smem_peak}
+        out = {"workload": "C4 on one GPU: plmdca N=%d L=%d q=%d, first 10 L-BFGS iterations" % (N, L, Q),
+               "evals_per_s": res.evaluations / (res.device_ms * 1e-3), "evaluations": res.evaluations,
+               "fit_ms": res.device_ms, "kernel_ms": ms,
+               "logits_frac_of_smem_roof": adds / (ms["logits"] * 1e-3) / 1e9 / smem_peak,
+               "scatter_frac_of_smem_roof": adds / (ms["scatter"] * 1e-3) / 1e9 / smem_peak}
     finally:
         obj.close()
+    try:        # the HBM-bound L-BFGS passes at this size (220 MB vectors; C2's are 20 MB: ramp-dominated)
+        P = L * Q + L * (L - 1) // 2 * Q * Q
+        vm = _lib.lbfgs_vector_bench(P, 5, 5)
+        hbm = hbm_peak if hbm_peak else 6552.0
+        nbytes = {"update_gram": 4 * P * 14, "direction": 4 * P * 12, "step": 4 * P * 3}
+        out["hbm_bound_kernels"] = {k: {"ms": vm[k], "bytes": nbytes[k], "achieved_gbs": nbytes[k] / (vm[k] * 1e-3) / 1e9,
+                                        "frac": nbytes[k] / (vm[k] * 1e-3) / 1e9 / hbm} for k in nbytes}
+    except Exception as exc:
+        out["hbm_bound_kernels"] = {"error": repr(exc)}
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -659,7 +669,7 @@ def run_ours(args, rank, world, local_rank):
             line["roofline"] = roofline_block(obj, x0, peaks)
             if not args.no_extras:
                 for name, fn in (("parity", lambda: parity_block(msa, w, lam)), ("mfdca", lambda: mfdca_block(tmp, peaks)),
-                                 ("reweight", reweight_block), ("c4", c4_block)):
+                                 ("reweight", reweight_block), ("c4", lambda: c4_block(find_hbm_peak(peaks)[0]))):
                     try:
                         line[name] = fn()
                     except Exception as exc:          # an extra block never takes the headline down
