@@ -196,6 +196,38 @@ int dca_plm_connect_ipc(dca_plm *p, const unsigned char *handles /* world x 64 b
 int dca_plm_connect_ptrs(dca_plm *p, void *const *arena_ptrs /* world entries, by rank */);
 int dca_plm_disconnect(dca_plm *p);
 
+/* ---- asymmetric (per-site) estimator -- SURVEY 8e last row, what north_star words as "plmDCA's
+ * independent per-site subproblems": NOT the reference's estimator (the reference fits one symmetric
+ * J with all site conditionals coupled, plmdca_numerics.cpp:436-607); an opt-in fast mode.
+ * Site i keeps its own copy J^(i)_ij of its couplings, which only its own conditional sees:
+ *   f = sum_i [ -sum_n w_n log p_n(i, s_ni) + lambda_h |h_i|^2 + (lambda_J / 2) sum_{j != i} |J^(i)_ij|^2 ]
+ * (the relaxation of the joint objective: equal to it when J^(i)_ij = (J^(j)_ji)^T), the same
+ * conditional as the reference's including its carry (:492, :499).  The L problems share nothing,
+ * so site ranges go to different GPUs with no exchange; at the end J_ij = (J^(i)_ij + (J^(j)_ji)^T) / 2.
+ * A handle from dca_plm_create_asym covers the sites [site_lo, site_hi); its parameter vector
+ * (dca_plm_local_params floats; dca_plm_init / eval / fit / fit_from_init work on it) is
+ *   x = [ h : ld floats, column c = (i - site_lo) * q + a | W : L*q rows x ld ],  W[j*q + b][c] = J^(i)_ij(a, b)
+ * with ld = the column count padded to a multiple of 128 (pad columns and the blocks j == i stay 0). */
+dca_plm *dca_plm_create_asym(const uint8_t *msa, const float *weights, long num_seqs, int seqs_len,
+                             int num_site_states, float lambda_h, float lambda_J, int site_lo, int site_hi);
+/* copy the handle's columns (of x_local_host, or of the device-resident result when NULL) into host
+ * arrays that hold every site: W_full [L*q][ld_full] (column i*q + a), fields_full [L*q] */
+int dca_plm_asym_export(dca_plm *p, const float *x_local_host, float *W_full_host, int ld_full,
+                        float *fields_full_host);
+/* symmetrise: the reference's parameter vector (P floats, plmdca_numerics.cpp:226, :338-342) */
+int dca_plm_asym_pack(const float *W_full_host, int ld_full, const float *fields_full_host, int seqs_len,
+                      int num_site_states, float *x_out_host);
+/* all of it on `gpus` GPUs of this node (0 = DCA_B200_GPUS / all visible): one host thread per GPU, equal
+ * site ranges, independent L-BFGS runs (same parameters as plmdcaBackend.cpp:68-75), one gather through
+ * host memory, symmetrisation on the caller's GPU.  result: the slowest GPU's iterations /
+ * evaluations / device time, the sum of the objectives.  plmdcaBackend() takes this path when
+ * DCA_B200_ESTIMATOR=asymmetric or after dca_set_estimator(1). */
+int dca_plm_fit_asymmetric(const uint8_t *msa, const float *weights, long num_seqs, int seqs_len,
+                           int num_site_states, float lambda_h, float lambda_J, int max_iterations,
+                           int gpus, int verbose, float *x_out_host, dca_fit_result *result);
+/* process-wide estimator of plmdcaBackend(): 0 joint (the reference's), 1 asymmetric, -1 = environment */
+int dca_set_estimator(int mode);
+
 /* statistics of this thread's most recent plmdcaBackend() call (the reference's
  * entry point discards the L-BFGS return code, plmdcaBackend.cpp:197). */
 int dca_last_fit(dca_fit_result *result);

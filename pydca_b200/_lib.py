@@ -78,6 +78,14 @@ def lib():
     L.dca_plm_create_sharded.argtypes = [_u8p, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                          ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     L.dca_plm_create_sharded.restype = ctypes.c_void_p
+    L.dca_plm_create_asym.argtypes = L.dca_plm_create.argtypes
+    L.dca_plm_create_asym.restype = ctypes.c_void_p
+    L.dca_plm_asym_export.argtypes = [ctypes.c_void_p, _f32p, _f32p, ctypes.c_int, _f32p]
+    L.dca_plm_asym_pack.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int, ctypes.c_int, _f32p]
+    L.dca_plm_fit_asymmetric.argtypes = [_u8p, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                         ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p,
+                                         ctypes.POINTER(FitResult)]
+    L.dca_set_estimator.argtypes = [ctypes.c_int]
     L.dca_plm_local_params.argtypes = [ctypes.c_void_p]
     L.dca_plm_local_params.restype = ctypes.c_long
     L.dca_plm_local_layout.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_long)]
@@ -133,6 +141,42 @@ def lib():
 
 def last_error():
     return lib().dca_last_error().decode("utf-8", "replace")
+
+
+ESTIMATORS = {None: -1, "joint": 0, "asymmetric": 1}
+
+
+def set_estimator(mode):
+    """Estimator of plmdcaBackend(): 'joint' (the reference's), 'asymmetric' (independent per-site
+    fits, symmetrised at the end) or None = the DCA_B200_ESTIMATOR environment variable."""
+    if mode not in ESTIMATORS:
+        raise ValueError("estimator must be 'joint', 'asymmetric' or None, got %r" % (mode,))
+    check(lib().dca_set_estimator(ESTIMATORS[mode]), "dca_set_estimator")
+
+
+def asym_pack(W_full, h_full, seqs_len, num_site_states):
+    """Directed couplings of all sites -> the reference's parameter vector (symmetrised)."""
+    W_full = np.ascontiguousarray(W_full, dtype=np.float32)
+    h_full = np.ascontiguousarray(h_full, dtype=np.float32).ravel()
+    l, q = int(seqs_len), int(num_site_states)
+    x = np.empty(l * q + l * (l - 1) // 2 * q * q, dtype=np.float32)
+    check(lib().dca_plm_asym_pack(ptr(W_full, _f32p), int(W_full.shape[1]), ptr(h_full, _f32p), l, q, ptr(x, _f32p)),
+          "dca_plm_asym_pack")
+    return x
+
+
+def fit_asymmetric(msa, weights, num_site_states, lambda_h, lambda_J, max_iterations, gpus=0, verbose=False):
+    """Asymmetric plmDCA on `gpus` GPUs (0 = all visible / DCA_B200_GPUS) -> (x in the reference layout, FitResult)."""
+    msa = np.ascontiguousarray(msa, dtype=np.uint8)
+    weights = np.ascontiguousarray(weights, dtype=np.float32)
+    n, l = msa.shape
+    q = int(num_site_states)
+    x = np.empty(l * q + l * (l - 1) // 2 * q * q, dtype=np.float32)
+    res = FitResult()
+    check(lib().dca_plm_fit_asymmetric(ptr(msa, _u8p), ptr(weights, _f32p), n, l, q, float(lambda_h), float(lambda_J),
+                                       int(max_iterations), int(gpus), int(bool(verbose)), ptr(x, _f32p),
+                                       ctypes.byref(res)), "dca_plm_fit_asymmetric")
+    return x, res
 
 
 def check(rc, what):
@@ -199,13 +243,22 @@ class PlmObjective:
     ``shard=(rank, world, bounds)``: owner-sharded multi-GPU objective (include/dca_b200.h);
     init / eval / fit then work on the LOCAL slice of ``Ploc`` floats and are collective."""
 
-    def __init__(self, msa, weights, num_site_states, lambda_h, lambda_J, sites=None, shard=None):
+    def __init__(self, msa, weights, num_site_states, lambda_h, lambda_J, sites=None, shard=None, asymmetric=False):
         msa = np.ascontiguousarray(msa, dtype=np.uint8)
         weights = np.ascontiguousarray(weights, dtype=np.float32)
         n, l = msa.shape
         self.N, self.L, self.q = n, l, int(num_site_states)
         self.shard = None
-        if shard is not None:
+        self.asymmetric = bool(asymmetric)
+        if asymmetric:
+            # per-site estimator on the sites [lo, hi): x = [h (ld) | W (L*q rows x ld)], include/dca_b200.h
+            if shard is not None:
+                raise ValueError("the asymmetric estimator needs no owner-sharding: give every GPU its own sites=(lo, hi)")
+            lo, hi = (0, l) if sites is None else sites
+            self.sites = (int(lo), int(hi))
+            self._h = lib().dca_plm_create_asym(ptr(msa, _u8p), ptr(weights, _f32p), n, l, self.q,
+                                                float(lambda_h), float(lambda_J), int(lo), int(hi))
+        elif shard is not None:
             rank, world, bounds = shard
             b = (ctypes.c_int * (int(world) + 1))(*[int(v) for v in bounds])
             self.shard = (int(rank), int(world), tuple(int(v) for v in bounds))
@@ -219,6 +272,33 @@ class PlmObjective:
             raise DcaBackendError("dca_plm_create failed: %s" % last_error())
         self.P = int(lib().dca_plm_num_params(self._h))
         self.Ploc = int(lib().dca_plm_local_params(self._h))
+
+    # ---- asymmetric estimator ------------------------------------------------------------
+    def asym_shape(self):
+        """(ncol, ld): valid and padded column counts of the local matrix."""
+        ncol = (self.sites[1] - self.sites[0]) * self.q
+        ld = self.Ploc // (self.L * self.q + 1)
+        return ncol, ld
+
+    def asym_split(self, x):
+        """x -> (h [sites, q], W [L*q, sites*q]) views without the pad columns."""
+        ncol, ld = self.asym_shape()
+        return x[:ncol].reshape(-1, self.q), x[ld:].reshape(self.L * self.q, ld)[:, :ncol]
+
+    def asym_join(self, h, W):
+        ncol, ld = self.asym_shape()
+        x = np.zeros(self.Ploc, dtype=np.float32)
+        x[:ncol] = np.asarray(h, dtype=np.float32).ravel()
+        x[ld:].reshape(self.L * self.q, ld)[:, :ncol] = W
+        return x
+
+    def asym_export(self, W_full, h_full, x=None):
+        """Write my columns of x (default: the device-resident result of the last fit) into the
+        all-sites host arrays W_full [L*q, L*q] and h_full [L*q] (float32, C order)."""
+        assert W_full.dtype == np.float32 and W_full.flags.c_contiguous and h_full.dtype == np.float32
+        xp = None if x is None else ptr(np.ascontiguousarray(x, dtype=np.float32), _f32p)
+        check(lib().dca_plm_asym_export(self._h, xp, ptr(W_full, _f32p), int(W_full.shape[1]), ptr(h_full, _f32p)),
+              "dca_plm_asym_export")
 
     # ---- owner-sharded wiring -----------------------------------------------------------
     def local_layout(self):

@@ -108,6 +108,7 @@ extern "C" void dca_plm_destroy(dca_plm *p);
 // reference (the reference's sequential float32 sums bit for bit: its trajectory, FN ~1e-6)
 static std::atomic<int> g_arithmetic{-1};      // dca_set_arithmetic(): overrides the environment
 static std::atomic<int> g_gpus{0};             // dca_set_gpus(): overrides DCA_B200_GPUS (0 = environment)
+static std::atomic<int> g_estimator{-1};       // dca_set_estimator(): overrides DCA_B200_ESTIMATOR
 
 // how many GPUs plmdcaBackend() drives: dca_set_gpus() > DCA_B200_GPUS > all visible
 static int backend_gpus(int L);
@@ -131,6 +132,17 @@ static int backend_arithmetic()
     if (e && (strcmp(e, "accurate") == 0 || strcmp(e, "0") == 0)) return 0;
     if (e && (strcmp(e, "reference") == 0 || strcmp(e, "1") == 0)) return 1;
     return DCA_DEFAULT_ARITHMETIC;
+}
+
+// estimator of plmdcaBackend(): joint (0, the reference's: one symmetric J, default) or asymmetric (1:
+// every site fits its own copy of its couplings, independent problems, symmetrised at the end)
+static int backend_estimator()
+{
+    const int forced = g_estimator.load();
+    if (forced == 0 || forced == 1) return forced;
+    const char *e = getenv("DCA_B200_ESTIMATOR");
+    if (e && (strcmp(e, "asymmetric") == 0 || strcmp(e, "1") == 0)) return 1;
+    return 0;
 }
 
 static dca_plm *wrap_problem(PlmProblem *prob)
@@ -245,6 +257,33 @@ dca_plm *dca_plm_create_sharded(const uint8_t *msa, const float *weights, long n
     return wrap_problem(prob);
 }
 
+dca_plm *dca_plm_create_asym(const uint8_t *msa, const float *weights, long num_seqs, int seqs_len,
+                             int num_site_states, float lambda_h, float lambda_J, int site_lo, int site_hi)
+{
+    if (!msa || !weights) { set_error("dca_plm_create_asym: null input"); return nullptr; }
+    PlmProblem *prob = plm_create_asym(msa, weights, num_seqs, seqs_len, num_site_states, lambda_h, lambda_J,
+                                       site_lo, site_hi);
+    if (!prob) return nullptr;
+    return wrap_problem(prob);
+}
+
+int dca_plm_asym_export(dca_plm *p, const float *x_local_host, float *W_full_host, int ld_full, float *fields_full_host)
+{
+    if (!p || !W_full_host || !fields_full_host) { set_error("dca_plm_asym_export: null argument"); return -1; }
+    if (x_local_host)
+        DCA_CUDA(cudaMemcpyAsync(p->d_x, x_local_host, sizeof(float) * (size_t)plm_local_params(p->prob),
+                                 cudaMemcpyHostToDevice, plm_stream(p->prob)));
+    return plm_asym_export(p->prob, p->d_x, W_full_host, ld_full, fields_full_host);
+}
+
+int dca_plm_asym_pack(const float *W_full_host, int ld_full, const float *fields_full_host, int seqs_len,
+                      int num_site_states, float *x_out_host)
+{
+    if (!W_full_host || !fields_full_host || !x_out_host) { set_error("dca_plm_asym_pack: null argument"); return -1; }
+    if (ld_full < seqs_len * num_site_states) { set_error("dca_plm_asym_pack: ld_full %d < L*q", ld_full); return -1; }
+    return plm_asym_pack_host(W_full_host, ld_full, fields_full_host, seqs_len, num_site_states, x_out_host);
+}
+
 long dca_plm_local_params(const dca_plm *p) { return p ? plm_local_params(p->prob) : -1; }
 
 int dca_plm_local_layout(const dca_plm *p, long *out4)
@@ -345,6 +384,13 @@ int dca_set_arithmetic(int mode)
 {
     if (mode < -1 || mode > 1) { set_error("dca_set_arithmetic: mode must be -1 (environment), 0 (accurate) or 1 (reference)"); return -1; }
     g_arithmetic.store(mode);
+    return 0;
+}
+
+int dca_set_estimator(int mode)
+{
+    if (mode < -1 || mode > 1) { set_error("dca_set_estimator: mode %d (0 joint, 1 asymmetric, -1 environment)", mode); return -1; }
+    g_estimator.store(mode);
     return 0;
 }
 
@@ -662,6 +708,90 @@ static int backend_multi_gpu(int G, const std::vector<uint8_t> &msa, std::vector
     return 0;
 }
 
+// ---- asymmetric estimator over G GPUs: independent fits of contiguous site ranges (every site costs the
+// same: L - 1 blocks), no exchange at all during the fits; at the end every GPU copies its columns of
+// the directed couplings into one host matrix -- the single gather of north_star -- and the caller's
+// GPU symmetrises it into the reference's vector.
+struct AsymShared {
+    int G = 1, dev0 = 0;
+    const uint8_t *msa = nullptr;
+    const float *w = nullptr;
+    long N = 0;
+    int L = 0, q = 0, max_it = 0, verbose = 0, ld_full = 0;
+    float lh = 0.f, lJ = 0.f;
+    std::vector<int> bounds;
+    float *W_full = nullptr, *h_full = nullptr;
+    std::vector<LbfgsResult> res;
+    std::atomic<int> err{0};
+};
+
+static void asym_worker(AsymShared *S, int r)
+{
+    auto fail = [&](const char *what) {
+        S->err.store(1);
+        fprintf(stderr, "plmdca asymmetric: GPU %d: %s: %s\n", r, what, last_error());
+    };
+    if (S->G > 1 && cudaSetDevice(r) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", r); fail("device"); return; }
+    PlmProblem *prob = plm_create_asym(S->msa, S->w, S->N, S->L, S->q, S->lh, S->lJ, S->bounds[(size_t)r], S->bounds[(size_t)r + 1]);
+    if (!prob) { fail("create"); return; }
+    float *d_x = static_cast<float *>(dev_alloc(sizeof(float) * (size_t)plm_local_params(prob)));
+    if (!d_x) fail("allocation");
+    else if (plm_init_x_device(prob, d_x) != 0 ||
+             lbfgs_minimize(prob, d_x, S->max_it, (r == 0) ? S->verbose : 0, nullptr, nullptr, &S->res[(size_t)r], 0, nullptr, nullptr) != 0)
+        fail("fit");
+    else if (plm_asym_export(prob, d_x, S->W_full, S->ld_full, S->h_full) != 0)
+        fail("export");
+    cudaStreamSynchronize(plm_stream(prob));
+    dev_free(d_x);
+    plm_destroy(prob);
+}
+
+static int fit_asymmetric(const uint8_t *msa, const float *w, long N, int L, int q, float lh, float lJ, int max_it,
+                          int gpus, int verbose, float *x_out, dca_fit_result *result)
+{
+    if (require_device() != 0) return -1;
+    int visible = 1;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess) { cudaGetLastError(); visible = 1; }
+    AsymShared S;
+    S.G = std::max(1, std::min(std::min(gpus <= 0 ? backend_gpus(L) : gpus, visible), L));
+    cudaGetDevice(&S.dev0);
+    S.msa = msa; S.w = w; S.N = N; S.L = L; S.q = q; S.lh = lh; S.lJ = lJ; S.max_it = max_it; S.verbose = verbose;
+    S.bounds = even_bounds(L, S.G);
+    S.res.assign((size_t)S.G, LbfgsResult{});
+    const long Lq = (long)L * q;
+    S.ld_full = (int)((Lq + 3) & ~3L);
+    S.W_full = static_cast<float *>(host_pinned_alloc(sizeof(float) * (size_t)Lq * S.ld_full));
+    S.h_full = static_cast<float *>(host_pinned_alloc(sizeof(float) * (size_t)Lq));
+    int rc = (S.W_full && S.h_full) ? 0 : -1;
+    if (rc == 0) {
+        std::vector<std::thread> th;
+        for (int r = 1; r < S.G; ++r) th.emplace_back(asym_worker, &S, r);
+        asym_worker(&S, 0);
+        for (auto &t : th) t.join();
+        if (S.G > 1) cudaSetDevice(S.dev0);
+        if (S.err.load()) rc = -1;
+    }
+    if (rc == 0) rc = plm_asym_pack_host(S.W_full, S.ld_full, S.h_full, L, q, x_out);
+    if (S.W_full) host_pinned_free(S.W_full);
+    if (S.h_full) host_pinned_free(S.h_full);
+    if (rc == 0 && result) {
+        // the fits are independent: report the slowest one's counts, the sum of the objectives, and
+        // the first status that is neither success nor the float32 line-search floor (-1001)
+        dca_fit_result out{};
+        out.status = 0;
+        for (const LbfgsResult &r : S.res) {
+            out.iterations = std::max(out.iterations, r.iterations);
+            out.evaluations = std::max(out.evaluations, r.evaluations);
+            out.device_ms = std::max(out.device_ms, (double)r.device_ms);
+            out.fx += r.fx;
+            if (out.status == 0 || (out.status == -1001 && r.status != 0)) out.status = r.status;
+        }
+        out.timed_ms = out.device_ms; out.timed_evaluations = out.evaluations;
+        *result = out;
+    }
+    return rc;
+}
+
 }  // namespace
 
 // ---- the reference's own entry point -------------------------------------------
@@ -707,6 +837,28 @@ float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states,
         }
         for (long n = 0; n < N; ++n) w[n] = 1.f / (float)counts[n];                          // :669
         mark("reweight");
+    }
+    if (backend_estimator() == 1) {        // independent per-site fits (not the reference's estimator): opt-in
+        if (G > 1 && deep) {
+            std::vector<uint32_t> counts((size_t)N);
+            if (dca_weights(msa.data(), N, L, (double)seqid, 0, 0, N, counts.data()) != 0) {
+                fprintf(stderr, "plmdcaBackend: %s\n", last_error());
+                return nullptr;
+            }
+            for (long n = 0; n < N; ++n) w[n] = 1.f / (float)counts[n];
+        }
+        const size_t Pa = (size_t)L * q + (size_t)L * (L - 1) / 2 * q * q;
+        float *xa = (float *)host_pinned_alloc(sizeof(float) * Pa);
+        if (!xa) { fprintf(stderr, "ERROR: Failed to allocate a memory block for variables.\n"); return nullptr; }
+        dca_fit_result resa{};
+        if (fit_asymmetric(msa.data(), w.data(), N, L, q, lambda_h, lambda_J, (int)max_iteration, G, verbose ? 1 : 0, xa, &resa) != 0) {
+            fprintf(stderr, "plmdcaBackend: %s\n", last_error());
+            host_pinned_free(xa);
+            return nullptr;
+        }
+        mark("asymmetric");
+        t_last_fit = resa;
+        return xa;
     }
     if (G > 1) {
         const size_t Pm = (size_t)L * q + (size_t)L * (L - 1) / 2 * q * q;
@@ -759,6 +911,15 @@ float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states,
     if (rc != 0) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); host_pinned_free(x); return nullptr; }
     t_last_fit = res;
     return x;
+}
+
+int dca_plm_fit_asymmetric(const uint8_t *msa, const float *weights, long num_seqs, int seqs_len, int num_site_states,
+                           float lambda_h, float lambda_J, int max_iterations, int gpus, int verbose,
+                           float *x_out_host, dca_fit_result *result)
+{
+    if (!msa || !weights || !x_out_host) { set_error("dca_plm_fit_asymmetric: null argument"); return -1; }
+    return fit_asymmetric(msa, weights, num_seqs, seqs_len, num_site_states, lambda_h, lambda_J, max_iterations, gpus,
+                          verbose, x_out_host, result);
 }
 
 int dca_last_fit(dca_fit_result *result)

@@ -66,6 +66,11 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
 // [bounds[r], bounds[r+1]); x, g and the optimiser's vectors hold the local slice only
 PlmProblem *plm_create_sharded(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
                                float lambda_h, float lambda_J, int rank, int world, const int *bounds);
+PlmProblem *plm_create_asym(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
+                            float lambda_h, float lambda_J, int site_lo, int site_hi);
+bool plm_is_asym(const PlmProblem *p);
+int plm_asym_export(PlmProblem *p, const float *d_x, float *h_W_full, int ld_full, float *h_fields_full);
+int plm_asym_pack_host(const float *h_W_full, int ld_full, const float *h_fields_full, int L, int q, float *h_xref);
 int plm_connect(PlmProblem *p, void *const *arenas, bool shared_process);    // device pointers of every rank's arena
 void plm_disconnect(PlmProblem *p);
 void *plm_arena(const PlmProblem *p);

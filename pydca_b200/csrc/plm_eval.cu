@@ -116,6 +116,16 @@ struct PlmProblem {
     double *d_scal_loc = nullptr;
     int n_active_own = 0;
     int own_jg = AS_JG;      // sites j per CTA of the owner kernels: 8, or 2 when the shard is small
+    // ---- asymmetric (per-site) estimator: the sites [site_lo, site_hi) are independent problems, each
+    // with its OWN copy of the couplings J^(i)_ij.  The parameter vector IS the coupling matrix in the
+    // W layout, restricted to my columns:  x = [ h (ld floats: column (i - lo)*q + a) | W (Lq rows x ld) ],
+    // so the logits kernel reads x through a tensor map and the gradient is the scatter's G plus the
+    // regulariser: no unpack, no transposing assemble, no exchange between GPUs.
+    bool asym = false;
+    int ncol = 0;            // (site_hi - site_lo) * q valid columns (ld = padded to 128)
+    int fin_rows = 8;        // rows of x per finish CTA
+    struct { const float *base; CUtensorMap tm; } wmap[4];   // tensor maps over x's W part, by base pointer
+    int n_wmap = 0;
 };
 
 XrCall plm_xr_next(PlmProblem *p);
@@ -321,8 +331,11 @@ template <int Q, int SM_PF>
 __global__ void __launch_bounds__(128)
 plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, const uint8_t *__restrict__ msa,
                    const float *__restrict__ w, long N, int L, int site_lo, int site_hi,
-                   int chunk, int warm, int carry, double *__restrict__ fxpart, double *__restrict__ fxsite)
+                   int chunk, int warm, int carry, double *__restrict__ fxpart, double *__restrict__ fxsite,
+                   int col_shift)
 {   // fxsite (may be null): [scan chunk][L] per-site partials of fx, for the reference-order sum of seqsum.cu
+    // col_shift: column of S / Rz that holds state 0 of site 0 is -col_shift (asymmetric mode keeps only
+    // its own sites' columns: col_shift = site_lo * Q; 0 otherwise)
     __shared__ float sbuf[4][32 * Q];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long k = (long)blockIdx.y * 4 + wib;
@@ -335,7 +348,7 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
     const bool active = site < site_hi;
     const int ncols = min(32, site_hi - s0) * Q;
     float *buf = sbuf[wib];
-    const size_t cbase = (size_t)s0 * Q;
+    const size_t cbase = (size_t)s0 * Q - (size_t)col_shift;
 
     // The chain is serial in n and every step needs one row segment of S from L2/HBM.  SM_PF rows
     // are kept in flight (register ring, statically indexed by unrolling the step loop SM_PF
@@ -686,6 +699,110 @@ plm_assemble_kernel(const float *__restrict__ x, const float *__restrict__ G, si
     assemble_finish(s_reg, s_dg, s_gg, s_xx, red, fxpart, nfx, ticket, n_active, scal);
 }
 
+// ------------------------------------------------------------------------------
+// Asymmetric (per-site) estimator, SURVEY 8e last row: site i keeps its own couplings J^(i)_ij,
+// the conditional of site i is the only term they appear in, and the L problems are independent.
+// Objective of my sites (the relaxation of the joint one: each directed copy carries lambda_J / 2):
+//   f = sum_i [ -sum_n w_n log p_n(i, s_ni) + lambda_h |h_i|^2 + (lambda_J / 2) sum_{j != i} |J^(i)_ij|^2 ]
+// Parameters in the W layout (see PlmProblem::asym): x = [ h | W ],  W[(j,b)][(i,a)] = J^(i)_ij(a,b);
+// the gradient of the data term with respect to W is the scatter's G, element by element.
+//   g_W = sum_splits G + lambda_J * W      (diagonal blocks j == i and pad columns: 0)
+//   g_h[(i,a)] = sum_b G[(i,b)][(i,a)] + 2 lambda_h h     (sum_b [s_ni == b] = 1: any row block sums
+//                                                          r_n(i,a) over n; the diagonal one is used)
+// grid (ceil(ld / 1024), ceil((Lq + 1) / rows)); the CTA of the last row group also owns the field row.
+template <int Q>
+__global__ void __launch_bounds__(256)
+plm_asym_finish_kernel(const float *__restrict__ x, const float *__restrict__ G, size_t g_split_stride, int nsplit,
+                       int Lq, int ld, int ncol, int site_lo, float lh, float lJ, int rows_per_cta,
+                       const float *__restrict__ d, float *__restrict__ g, double *__restrict__ red,
+                       const double *__restrict__ fxpart, int nfx, unsigned *__restrict__ ticket,
+                       unsigned n_active, double *__restrict__ scal)
+{
+    const int c = ((int)blockIdx.x * 256 + (int)threadIdx.x) * 4;           // my 4 columns
+    const int r0 = (int)blockIdx.y * rows_per_cta;
+    double s_reg = 0.0, s_dg = 0.0, s_gg = 0.0, s_xx = 0.0;
+    if (c < ld) {
+        int site[4];
+        bool valid[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { valid[e] = (c + e) < ncol; site[e] = site_lo + (c + e) / Q; }
+        const float *xw = x + ld;
+        float *gw = g + ld;
+        const float *dw = d ? d + ld : nullptr;
+        for (int r = r0; r < min(r0 + rows_per_cta, Lq); ++r) {
+            const size_t o = (size_t)r * ld + c;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < nsplit; ++s) {
+                const float4 v = *reinterpret_cast<const float4 *>(G + (size_t)s * g_split_stride + o);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            const float4 xv = *reinterpret_cast<const float4 *>(xw + o);
+            const int rs = r / Q;
+            const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float ge[4] = {acc.x, acc.y, acc.z, acc.w};
+            float out[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool on = valid[e] && rs != site[e];
+                out[e] = on ? (ge[e] + lJ * xe[e]) : 0.f;
+                if (on) { s_reg += 0.5 * (double)lJ * xe[e] * xe[e]; s_xx += (double)xe[e] * xe[e]; }
+                s_gg += (double)out[e] * out[e];
+            }
+            *reinterpret_cast<float4 *>(gw + o) = make_float4(out[0], out[1], out[2], out[3]);
+            if (dw) {
+                const float4 dv = *reinterpret_cast<const float4 *>(dw + o);
+                s_dg += (double)out[0] * dv.x + (double)out[1] * dv.y + (double)out[2] * dv.z + (double)out[3] * dv.w;
+            }
+        }
+        if (blockIdx.y == gridDim.y - 1) {                                 // the field row
+            float out[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                out[e] = 0.f;
+                if (valid[e]) {
+                    const float h = x[c + e];
+                    float col = 0.f;
+                    for (int s = 0; s < nsplit; ++s) {
+                        const float *Gs = G + (size_t)s * g_split_stride;
+                        for (int b = 0; b < Q; ++b) col += Gs[((size_t)site[e] * Q + b) * ld + c + e];
+                    }
+                    out[e] = 2.f * lh * h + col;
+                    s_reg += (double)lh * h * h; s_xx += (double)h * h;
+                    s_gg += (double)out[e] * out[e];
+                    if (d) s_dg += (double)out[e] * d[c + e];
+                }
+            }
+            *reinterpret_cast<float4 *>(g + c) = make_float4(out[0], out[1], out[2], out[3]);
+        }
+    }
+    assemble_finish(s_reg, s_dg, s_gg, s_xx, red, fxpart, nfx, ticket, n_active, scal);
+}
+
+// reference layout from the directed copies: J_ij = (J^(i)_ij + (J^(j)_ji)^T) / 2, fields as they are.
+// W: [Lq][ldw] with ALL sites' columns (column (i,a) = i*Q + a), h: [Lq].  One thread per output element.
+template <int Q>
+__global__ void plm_asym_pack_kernel(const float *__restrict__ W, int ldw, const float *__restrict__ h, int L,
+                                     float *__restrict__ xref)
+{
+    constexpr int QQ = Q * Q;
+    const long Lq = (long)L * Q;
+    const long P = Lq + (long)L * (L - 1) / 2 * QQ;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    if (idx < Lq) { xref[idx] = h[idx]; return; }
+    const long k = idx - Lq;
+    const long pr = k / QQ;
+    const int e = (int)(k - pr * QQ), a = e / Q, b = e - a * Q;
+    // invert pair(i,j): rows of the strict upper triangle
+    int i = (int)((2.0 * L - 1.0 - sqrt((2.0 * L - 1.0) * (2.0 * L - 1.0) - 8.0 * (double)pr)) * 0.5);
+    while (pair_index(L, i + 1, i + 2) <= pr && i + 2 < L) ++i;
+    while (pair_index(L, i, i + 1) > pr) --i;
+    const int j = (int)(pr - pair_index(L, i, i + 1)) + i + 1;
+    const float mine = W[((size_t)j * Q + b) * ldw + (size_t)i * Q + a];      // J^(i)_ij(a,b)
+    const float theirs = W[((size_t)i * Q + a) * ldw + (size_t)j * Q + b];    // J^(j)_ji(b,a)
+    xref[idx] = 0.5f * (mine + theirs);
+}
+
 // ==============================================================================
 // Owner-sharded multi-GPU mode (xrank.cuh).  Rank r owns the
 // sites [lo, hi) and the LOCAL parameter slice
@@ -915,10 +1032,66 @@ static int plm_setup_t(PlmProblem *p)
     return 0;
 }
 
+// asymmetric mode: logits straight from x (tensor map over its W part), softmax, scatter, finish
+template <int Q>
+static int plm_eval_asym_t(PlmProblem *p, const float *d_x, float *d_g, const float *d_dir, cudaEvent_t *ev)
+{
+    cudaStream_t st = p->stream;
+    const int L = p->L, ld = p->ld, lo = p->site_lo, hi = p->site_hi, nsites = hi - lo;
+    int evi = 0;
+#define PLM_MARK() do { if (ev) cudaEventRecord(ev[evi++], st); } while (0)
+    const CUtensorMap *tm = nullptr;
+    for (int k = 0; k < p->n_wmap; ++k)
+        if (p->wmap[k].base == d_x) tm = &p->wmap[k].tm;
+    if (!tm) {
+        const int k = (p->n_wmap < 4) ? p->n_wmap++ : 3;          // the optimiser alternates between two buffers
+        const unsigned jb = (Q > 8) ? 4 : 16;
+        if (make_tensor_map_2d(&p->wmap[k].tm, 4, d_x + ld, (unsigned long long)ld, (unsigned long long)p->Lq,
+                               sizeof(float) * (unsigned long long)ld, (unsigned)p->lg_tc, jb * (unsigned)Q) != 0) return -1;
+        p->wmap[k].base = d_x;
+        tm = &p->wmap[k].tm;
+    }
+    PLM_MARK(); PLM_MARK();                                        // (no unpack)
+    const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * p->lg_tc + 2 * LgCfg<Q>::JB * LG_TN + 64 + 1024;
+    dim3 gridA(p->lg_tiles, (unsigned)(p->Npad / LG_TN));
+    const XrWait wt{nullptr, nullptr, 0, 0u};
+    if (p->lg_tc == 128)
+        DCA_LAUNCH((plm_logits_kernel<Q, 128>), gridA, LG_THREADS, smemA, st,
+                   *tm, p->tmM, ld, p->N, L, d_x, 0, p->ncol, p->d_S, 0, wt);
+    else
+        DCA_LAUNCH((plm_logits_kernel<Q, 64>), gridA, LG_THREADS, smemA, st,
+                   *tm, p->tmM, ld, p->N, L, d_x, 0, p->ncol, p->d_S, 0, wt);
+    PLM_MARK();
+    dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
+    if ((long)gridB.x * gridB.y > 2L * sm_count())
+        DCA_LAUNCH((plm_softmax_kernel<Q, 1>), gridB, 128, 0, st, p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
+                   p->chunk, p->warm, p->carry, p->d_fxpart, (double *)nullptr, lo * Q);
+    else
+        DCA_LAUNCH((plm_softmax_kernel<Q, 4>), gridB, 128, 0, st, p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
+                   p->chunk, p->warm, p->carry, p->d_fxpart, (double *)nullptr, lo * Q);
+    PLM_MARK();
+    const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
+    const size_t gstride = (size_t)p->Lq * ld;
+    dim3 gridC(p->col_tiles, p->site_tiles, p->nsplit);
+    DCA_LAUNCH((plm_scatter_kernel<Q>), gridC, SC_WARPS * 32, smemC, st,
+               p->tmS, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride, p->chunks_per_split, 0, p->sites_per_tile);
+    PLM_MARK(); PLM_MARK();                                        // (no export)
+    const int nfx = (int)(gridB.x * p->nscan);
+    dim3 gridF(ceil_div(ld, 1024), ceil_div(p->Lq + 1, p->fin_rows));
+    DCA_LAUNCH((plm_asym_finish_kernel<Q>), gridF, 256, 0, st, d_x, p->d_G, gstride, p->nsplit, p->Lq, ld, p->ncol, lo,
+               p->lh, p->lJ, p->fin_rows, d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket,
+               gridF.x * gridF.y, p->d_scal);
+    PLM_MARK();
+#undef PLM_MARK
+    DCA_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <int Q>
 static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *d_dir,
                       cudaEvent_t *ev = nullptr)
 {
+    if (p->asym) return plm_eval_asym_t<Q>(p, d_x, d_g, d_dir, ev);
     cudaStream_t st = p->stream;
     const int L = p->L, ld = p->ld;
     const int lo = p->site_lo, hi = p->site_hi, nsites = hi - lo;
@@ -956,14 +1129,15 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
     PLM_MARK();
 
     dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
+    const int col_shift = 0;
     if ((long)gridB.x * gridB.y > 2L * sm_count())
         DCA_LAUNCH((plm_softmax_kernel<Q, 1>), gridB, 128, 0, st,
                    p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr);
+                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift);
     else
         DCA_LAUNCH((plm_softmax_kernel<Q, 4>), gridB, 128, 0, st,
                    p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr);
+                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift);
     PLM_MARK();
 
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
@@ -1079,7 +1253,7 @@ static XrLayout xr_layout(int Lq, int ld, int max_sites, int q)
 
 static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
                                    float lambda_h, float lambda_J, int site_lo, int site_hi,
-                                   int rank, int world, const int *bounds)
+                                   int rank, int world, const int *bounds, bool asym = false)
 {
     if (require_device() != 0) return nullptr;
     if (q != 21 && q != 5) { set_error("plm: num_site_states must be 21 or 5 (got %d)", q); return nullptr; }
@@ -1103,27 +1277,31 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     PlmProblem *p = new PlmProblem();
     p->N = N; p->L = L; p->q = q; p->Lq = L * q;
     p->Npad = ceil_div<long>(N, LG_TN) * LG_TN;
-    p->ld = ceil_div(p->Lq, LG_TC) * LG_TC;
+    p->asym = asym;
+    p->ncol = (site_hi - site_lo) * q;
+    p->ld = asym ? ceil_div(p->ncol, LG_TC) * LG_TC : ceil_div(p->Lq, LG_TC) * LG_TC;
     p->P = (long)L * q + (long)L * (L - 1) / 2 * q * q;
     p->lh = lambda_h; p->lJ = lambda_J;
     p->site_lo = site_lo; p->site_hi = site_hi;
     p->nchunk = (int)ceil_div<long>(N, SC_CH);
-    p->col_tile0 = (site_lo * q) / SC_TC;
-    p->col_tiles = ceil_div(site_hi * q, SC_TC) - p->col_tile0;
+    // column space of S / Rz / G / W: all sites' columns, or (asymmetric) my sites' columns from 0
+    const int col_lo = asym ? 0 : site_lo * q, col_hi = asym ? p->ncol : site_hi * q;
+    p->col_tile0 = col_lo / SC_TC;
+    p->col_tiles = ceil_div(col_hi, SC_TC) - p->col_tile0;
     {   // logits tiling: every SM streams (CTAs it hosts) x (columns per CTA) through shared memory;
         // take the narrow 64-column CTAs only when they shorten that makespan (small grids)
         const long seq_tiles = p->Npad / LG_TN;
         const int sms = sm_count();
         long best = -1;
         for (int tc : {128, 64}) {
-            const int t0 = (site_lo * q) / tc, nt = ceil_div(site_hi * q, tc) - t0;
+            const int t0 = col_lo / tc, nt = ceil_div(col_hi, tc) - t0;
             const long cost = ceil_div<long>((long)nt * seq_tiles, sms) * tc;
             if (best < 0 || cost < best) { best = cost; p->lg_tc = tc; p->lg_tile0 = t0; p->lg_tiles = nt; }
         }
         if (const char *e = getenv("DCA_B200_LOGITS_TC")) {        // measurement override
             const int tc = atoi(e);
             if (tc == 64 || tc == 128) {
-                p->lg_tc = tc; p->lg_tile0 = (site_lo * q) / tc; p->lg_tiles = ceil_div(site_hi * q, tc) - p->lg_tile0;
+                p->lg_tc = tc; p->lg_tile0 = col_lo / tc; p->lg_tiles = ceil_div(col_hi, tc) - p->lg_tile0;
             }
         }
     }
@@ -1145,6 +1323,13 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     }
     p->red_blocks = std::max(p->red_blocks, ceil_div(L, 2) * (site_hi - site_lo));
     p->Ploc = p->P;
+    if (asym) {
+        p->Ploc = (long)p->ld * (p->Lq + 1);
+        // finish kernel: enough CTAs to fill the GPU a few times over
+        p->fin_rows = 8;
+        while (p->fin_rows > 1 && (long)ceil_div(p->ld, 1024) * ceil_div(p->Lq + 1, p->fin_rows) < 4L * sm_count()) p->fin_rows >>= 1;
+        p->red_blocks = std::max(p->red_blocks, ceil_div(p->ld, 1024) * ceil_div(p->Lq + 1, p->fin_rows));
+    }
     if (sharded) {
         p->sharded = true;
         p->peers.rank = rank; p->peers.world = world;
@@ -1215,7 +1400,7 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
         p->peers.arena[rank] = p->arena;
         p->connected = (world == 1);
         PLM_ALLOC(p->d_scal_loc, sizeof(double) * 8);
-    } else {
+    } else if (!asym) {
         PLM_ALLOC(p->d_W, sizeof(float) * (size_t)p->Lq * p->ld);
         PLM_TRY(cudaMemsetAsync(p->d_W, 0, sizeof(float) * (size_t)p->Lq * p->ld, p->stream));
     }
@@ -1241,8 +1426,8 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
                            sizeof(float) * (unsigned long long)p->ld, SC_TC, SC_CH) != 0) { plm_free(p); return nullptr; }
     {
         const unsigned jb = (q > 8) ? 4 : 16;         // LgCfg<Q>::JB
-        if (make_tensor_map_2d(&p->tmW, 4, p->d_W, (unsigned long long)p->ld, (unsigned long long)p->Lq,
-                               sizeof(float) * (unsigned long long)p->ld, (unsigned)p->lg_tc, jb * (unsigned)q) != 0 ||
+        if ((!asym && make_tensor_map_2d(&p->tmW, 4, p->d_W, (unsigned long long)p->ld, (unsigned long long)p->Lq,
+                                         sizeof(float) * (unsigned long long)p->ld, (unsigned)p->lg_tc, jb * (unsigned)q) != 0) ||
             make_tensor_map_2d(&p->tmM, 1, p->d_msaT, (unsigned long long)p->Npad, (unsigned long long)L,
                                (unsigned long long)p->Npad, LG_TN, jb) != 0) { plm_free(p); return nullptr; }
     }
@@ -1258,6 +1443,46 @@ PlmProblem *plm_create(const uint8_t *h_msa, const float *h_w, long N, int L, in
                        float lambda_h, float lambda_J, int site_lo, int site_hi)
 {
     return plm_create_impl(h_msa, h_w, N, L, q, lambda_h, lambda_J, site_lo, site_hi, 0, 1, nullptr);
+}
+
+// asymmetric (per-site) estimator on the sites [site_lo, site_hi): see plm_asym_finish_kernel
+PlmProblem *plm_create_asym(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
+                            float lambda_h, float lambda_J, int site_lo, int site_hi)
+{
+    return plm_create_impl(h_msa, h_w, N, L, q, lambda_h, lambda_J, site_lo, site_hi, 0, 1, nullptr, true);
+}
+
+bool plm_is_asym(const PlmProblem *p) { return p->asym; }
+
+// my columns of the directed couplings and my fields into host arrays that hold ALL sites:
+// W_full [Lq][ld_full] (column (i,a) = i*q + a), h_full [Lq]
+int plm_asym_export(PlmProblem *p, const float *d_x, float *h_W_full, int ld_full, float *h_fields_full)
+{
+    if (!p->asym) { set_error("plm_asym_export: not an asymmetric objective"); return -1; }
+    const size_t c0 = (size_t)p->site_lo * p->q;
+    DCA_CUDA(cudaMemcpy2DAsync(h_W_full + c0, sizeof(float) * (size_t)ld_full, d_x + p->ld, sizeof(float) * (size_t)p->ld,
+                               sizeof(float) * (size_t)p->ncol, (size_t)p->Lq, cudaMemcpyDeviceToHost, p->stream));
+    DCA_CUDA(cudaMemcpyAsync(h_fields_full + c0, d_x, sizeof(float) * (size_t)p->ncol, cudaMemcpyDeviceToHost, p->stream));
+    DCA_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// directed copies of all sites -> the reference's parameter vector (symmetrised couplings)
+int plm_asym_pack_host(const float *h_W_full, int ld_full, const float *h_fields_full, int L, int q, float *h_xref)
+{
+    if (require_device() != 0) return -1;
+    if (q != 21 && q != 5) { set_error("plm_asym_pack: num_site_states must be 21 or 5 (got %d)", q); return -1; }
+    const long Lq = (long)L * q, P = Lq + (long)L * (L - 1) / 2 * q * q;
+    DevBuf<float> W, h, x;
+    if (!W.alloc((size_t)Lq * ld_full) || !h.alloc((size_t)Lq) || !x.alloc((size_t)P)) return -1;
+    DCA_CUDA(cudaMemcpy(W, h_W_full, sizeof(float) * (size_t)Lq * ld_full, cudaMemcpyHostToDevice));
+    DCA_CUDA(cudaMemcpy(h, h_fields_full, sizeof(float) * (size_t)Lq, cudaMemcpyHostToDevice));
+    const unsigned blocks = (unsigned)ceil_div<long>(P, 256);
+    if (q == 21) DCA_LAUNCH((plm_asym_pack_kernel<21>), blocks, 256, 0, 0, W.p, ld_full, h.p, L, x.p);
+    else DCA_LAUNCH((plm_asym_pack_kernel<5>), blocks, 256, 0, 0, W.p, ld_full, h.p, L, x.p);
+    DCA_CUDA(cudaGetLastError());
+    DCA_CUDA(cudaMemcpy(h_xref, x, sizeof(float) * (size_t)P, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 PlmProblem *plm_create_sharded(const uint8_t *h_msa, const float *h_w, long N, int L, int q,
@@ -1340,6 +1565,7 @@ void plm_set_carry(PlmProblem *p, int carry, int chunk, int warm)
 int plm_set_fidelity(PlmProblem *p, int on)
 {
     if (on && p->sharded) { set_error("plm: the reference-arithmetic mode runs on one GPU (sequential sums span the whole vector)"); return -1; }
+    if (on && p->asym) { set_error("plm: the reference-arithmetic mode reproduces the reference's joint fit; the asymmetric estimator has no reference"); return -1; }
     if (on && !p->d_fxsite) {
         const size_t count = (size_t)(p->N / 8 + 1) * p->L;          // chunk >= 8
         if (!dev_alloc_t(&p->d_fxsite, count)) return -1;
@@ -1403,7 +1629,8 @@ int plm_read_scalars(PlmProblem *p, double *out, double *dginit)
 int plm_init_x_device(PlmProblem *p, float *d_x)
 {
     DCA_CUDA(cudaMemsetAsync(d_x, 0, sizeof(float) * (size_t)p->Ploc, p->stream));
-    const int lo = p->sharded ? p->site_lo : 0, hi = p->sharded ? p->site_hi : p->L;
+    const bool local = p->sharded || p->asym;
+    const int lo = local ? p->site_lo : 0, hi = local ? p->site_hi : p->L;
     if (p->q == 21)
         DCA_LAUNCH((plm_init_fields_kernel<21>), ceil_div(hi - lo, 64), 64, 0, p->stream,
                    p->d_msaT, p->d_w, p->N, p->Npad, lo, hi, p->h_meff, d_x);

@@ -128,7 +128,7 @@ class PlmDCA:
     """Pseudolikelihood-maximisation DCA on one B200 (plmdca.py:25)."""
 
     def __init__(self, msa_file, biomolecule, seqid=None, lambda_h=None, lambda_J=None,
-                 max_iterations=None, num_threads=None, verbose=False, arithmetic=None):
+                 max_iterations=None, num_threads=None, verbose=False, arithmetic=None, estimator=None):
         # arithmetic (not in the reference): 'accurate' (float64 reductions, fastest), 'reference' (the
         # reference's sequential float32 sums bit for bit -> its L-BFGS trajectory, FN within ~1e-6;
         # one GPU) or None = the DCA_B200_ARITHMETIC environment variable (default accurate)
@@ -136,6 +136,14 @@ class PlmDCA:
             logger.error("\n\tInvalid arithmetic mode {}".format(arithmetic))
             raise PlmDCAException
         self.__arithmetic = arithmetic
+        # estimator (not in the reference): 'joint' = the reference's fit of one symmetric J (default);
+        # 'asymmetric' = every site fits its own couplings independently (sites spread over the GPUs with
+        # no exchange), symmetrised at the end -- a different estimator, close scores, not the reference's;
+        # None = the DCA_B200_ESTIMATOR environment variable
+        if estimator not in _lib.ESTIMATORS:
+            logger.error("\n\tInvalid estimator {}".format(estimator))
+            raise PlmDCAException
+        self.__estimator = estimator
         self.__biomolecule = biomolecule.strip().upper()
         if self.__biomolecule not in ("PROTEIN", "RNA"):
             logger.error("\n\tInvalid biomolecule type {}".format(self.__biomolecule))
@@ -223,6 +231,7 @@ class PlmDCA:
         logger.info("\n\tComputing fields and couplings using gradient decent")
         lib = _lib.lib()
         _lib.set_backend_arithmetic(self.__arithmetic)
+        _lib.set_estimator(self.__estimator)
         h_j_ptr = lib.plmdcaBackend(
             self.__biomolecule_int, self.__num_site_states, self.__msa_file.encode("utf-8"),
             self.__seqs_len, self.__seqid, self.__lambda_h, self.__lambda_J, self.__max_iterations,

@@ -35,12 +35,13 @@ def _seqbackmapper(msa_file, refseq_file, biomolecule):
 def execute_from_command_line(biomolecule, msa_file, the_command=None, refseq_file=None, seqid=None,
                               lambda_h=None, lambda_J=None, max_iterations=None, apc=False, verbose=False,
                               output_dir=None, num_threads=None, ranked_by=None, linear_dist=None,
-                              num_site_pairs=None, arithmetic=None):
+                              num_site_pairs=None, arithmetic=None, estimator=None):
     """pydca/plmdca_main.py:136-256."""
     if verbose:
         configure_logging()
     inst = PlmDCA(msa_file, biomolecule, seqid=seqid, lambda_h=lambda_h, lambda_J=lambda_J,
-                  max_iterations=max_iterations, num_threads=num_threads, verbose=verbose, arithmetic=arithmetic)
+                  max_iterations=max_iterations, num_threads=num_threads, verbose=verbose, arithmetic=arithmetic,
+                  estimator=estimator)
     if the_command not in DCA_COMPUTATION_SUBCOMMANDS:
         return None
     mapper = _seqbackmapper(msa_file, refseq_file, biomolecule)
@@ -104,6 +105,10 @@ def build_parser():
         p.add_argument("--arithmetic", choices=("accurate", "reference"),
                        help="accurate: float64 reductions (default, fastest); reference: the reference's sequential "
                             "float32 sums bit for bit, i.e. its own L-BFGS trajectory (not a flag of the reference)")
+        p.add_argument("--estimator", choices=("joint", "asymmetric"),
+                       help="joint: the reference's fit of one symmetric coupling matrix (default); asymmetric: every "
+                            "site fits its own couplings independently, sites spread over the GPUs without any "
+                            "exchange, symmetrised at the end (a different estimator; not a flag of the reference)")
         if name != "compute_params":
             p.add_argument("--apc", action="store_true", help="Compute the average product corrected (APC) scores")
         else:
@@ -124,7 +129,8 @@ def run_plm_dca(argv=None):
                               max_iterations=args.get("max_iterations"), num_threads=args.get("num_threads"),
                               apc=args.get("apc"), output_dir=args.get("output_dir"), verbose=args.get("verbose"),
                               ranked_by=args.get("ranked_by"), linear_dist=args.get("linear_dist"),
-                              num_site_pairs=args.get("num_site_pairs"), arithmetic=args.get("arithmetic"))
+                              num_site_pairs=args.get("num_site_pairs"), arithmetic=args.get("arithmetic"),
+                              estimator=args.get("estimator"))
     return None
 
 
