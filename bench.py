@@ -634,6 +634,33 @@ def run_ours(args, rank, world, local_rank):
                            "per-GPU H2D + owner-sharded fit (one host thread per GPU, peer-memory exchange) + per-GPU "
                            "D2H of its slice into the returned host vector" % world}
 
+    # ---- the asymmetric (per-site) estimator on the same workload and the same N GPUs: independent site
+    # ranges, no exchange, one gather (SURVEY 8e last row; NOT the reference's estimator, reported beside it)
+    asym = None
+    if not args.no_extras:
+        cpu_barrier()
+        if rank == 0:
+            try:
+                _lib.fit_asymmetric(msa, w, Q, lam, lam, MAX_ITER, gpus=world)              # warm
+                t1 = time.perf_counter()
+                xa, ra = _lib.fit_asymmetric(msa, w, Q, lam, lam, MAX_ITER, gpus=world)
+                a_wall = time.perf_counter() - t1
+                xj = last_x[0] if world > 1 else _lib.plmdca_backend(path, "protein", SEQ_LEN, Q, SEQID, lam, lam, MAX_ITER)
+                top = SEQ_LEN
+                rank_a = np.argsort(-_lib.plm_fn_apc(xa, SEQ_LEN, Q)[1], kind="stable")[:top]
+                rank_j = np.argsort(-_lib.plm_fn_apc(xj, SEQ_LEN, Q)[1], kind="stable")[:top]
+                asym = {"workload": "C2, estimator = asymmetric: L independent per-site problems, contiguous site ranges on "
+                                    "%d GPU(s), no exchange during the fits, one gather + symmetrisation" % world,
+                        "call": "dca_plm_fit_asymmetric on host arrays (weights given): H2D + fits + gather + symmetrise + D2H",
+                        "wall_ms": 1e3 * a_wall, "device_ms_slowest_gpu": ra.device_ms,
+                        "evaluations_slowest_gpu": ra.evaluations, "iterations_slowest_gpu": ra.iterations,
+                        "status": ra.status, "evals_per_s_slowest_gpu": ra.evaluations / (ra.device_ms * 1e-3),
+                        "fn_apc_topL_overlap_with_joint_fit": int(len(set(rank_a.tolist()) & set(rank_j.tolist()))),
+                        "topL": top}
+            except Exception as exc:
+                asym = {"error": repr(exc)}
+        cpu_barrier()
+
     # ---- numerical check of the real multi-GPU run: the gathered parameters of the sharded fit
     # against a single-GPU fit of the same input on rank 0's GPU, in this run
     multi_check = None
@@ -665,6 +692,8 @@ def run_ours(args, rank, world, local_rank):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches)}
         if multi_check is not None:
             line["multi_gpu_check"] = multi_check
+        if asym is not None:
+            line["asymmetric"] = asym
         if world == 1:
             line["roofline"] = roofline_block(obj, x0, peaks)
             if not args.no_extras:

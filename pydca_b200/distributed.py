@@ -248,3 +248,79 @@ class ShardedPlm:
             dist.barrier(group=self.group)       # nobody frees an arena a peer still maps
             self.obj.close()
             self.obj = None
+
+
+# ---- asymmetric (per-site) estimator: independent site ranges, one all-gather ----------------------------
+def assemble_asym_slabs(slabs, bounds, seqs_len, num_site_states):
+    """slabs[r]: float32 [(L*q + 1), ld_max] of rank r (row 0 = fields, rows 1.. = its columns of the
+    directed couplings, first (bounds[r+1] - bounds[r]) * q columns valid) -> (W_full [L*q, L*q],
+    h_full [L*q]) holding every site's columns."""
+    lq = int(seqs_len) * int(num_site_states)
+    W = np.zeros((lq, lq), dtype=np.float32)
+    h = np.zeros(lq, dtype=np.float32)
+    for r, slab in enumerate(slabs):
+        c0, c1 = bounds[r] * num_site_states, bounds[r + 1] * num_site_states
+        h[c0:c1] = slab[0, :c1 - c0]
+        W[:, c0:c1] = slab[1:, :c1 - c0]
+    return W, h
+
+
+class AsymmetricPlm:
+    """One rank of the asymmetric estimator (include/dca_b200.h: dca_plm_create_asym): the rank fits the
+    sites [bounds[rank], bounds[rank+1]) on its GPU with NO communication, then ONE all-gather of the
+    column slabs gives every rank all directed couplings, which it symmetrises into the reference's
+    parameter vector -- north_star's "independent per-site subproblems ... a single NCCL all-gather
+    of the final J blocks".
+
+        ap = AsymmetricPlm(msa, w, q, lam_h, lam_J)      # inside an initialised process group
+        res = ap.fit(max_iterations)
+        x = ap.gather()                                   # reference layout, on every rank
+        ap.close()
+    """
+
+    def __init__(self, msa, weights, num_site_states, lambda_h, lambda_J, group=None, bounds=None):
+        import torch.distributed as dist
+        from . import _lib
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.L, self.q = int(msa.shape[1]), int(num_site_states)
+        if bounds is None:          # every site costs the same (L - 1 blocks): an even split is balanced
+            bounds = [shard_range(self.L, r, self.world)[0] for r in range(self.world)] + [self.L]
+        self.bounds = [int(b) for b in bounds]
+        self.obj = _lib.PlmObjective(msa, weights, num_site_states, lambda_h, lambda_J,
+                                     sites=(self.bounds[self.rank], self.bounds[self.rank + 1]), asymmetric=True)
+
+    def fit(self, max_iterations, verbose=False):
+        return self.obj.fit_from_init(max_iterations, verbose=verbose)
+
+    def _ld(self, r):
+        return -(-((self.bounds[r + 1] - self.bounds[r]) * self.q) // 128) * 128
+
+    def gather(self, x_local=None, device=None, pack=None):
+        """x_local: host copy of my vector (gloo / tests); None = the device-resident fit result (nccl).
+        pack: symmetrisation callable (tests substitute the oracle's); default the CUDA one."""
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        lq = self.L * self.q
+        ld, ld_max = self._ld(self.rank), max(self._ld(r) for r in range(self.world))
+        backend = dist.get_backend(self.group)
+        if backend == "nccl" and x_local is None:
+            dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+            src = torch.as_tensor(_CudaView(self.obj.x_device(), (lq + 1) * ld, "<f4"), device=dev).view(lq + 1, ld)
+            mine = torch.zeros((lq + 1, ld_max), dtype=torch.float32, device=dev)
+            mine[:, :ld].copy_(src)
+        else:
+            mine = torch.zeros((lq + 1, ld_max), dtype=torch.float32)
+            mine[:, :ld] = torch.from_numpy(np.ascontiguousarray(x_local, dtype=np.float32).reshape(lq + 1, ld))
+            if backend == "nccl":
+                mine = mine.cuda()
+        out = torch.empty(self.world * (lq + 1) * ld_max, dtype=torch.float32, device=mine.device)
+        dist.all_gather_into_tensor(out, mine.reshape(-1), group=self.group)
+        W, h = assemble_asym_slabs(out.cpu().numpy().reshape(self.world, lq + 1, ld_max), self.bounds, self.L, self.q)
+        return (pack or _lib.asym_pack)(W, h, self.L, self.q)
+
+    def close(self):
+        if self.obj is not None:
+            self.obj.close()
+            self.obj = None

@@ -280,6 +280,23 @@ def _worker(rank, world, port, out_dir):
     assert np.abs(got_slice - want).max() <= 1e-5 * np.abs(g_full).max()
     # the fields of my sites never leave the rank; blocks below my range got nothing from me twice
     assert all(float(t.abs().sum()) == 0.0 for r, t in enumerate(recvs) if r < rank)
+    # asymmetric estimator: every rank holds its sites' columns of the directed couplings; one
+    # all-gather + symmetrisation (the oracle's stands in for the CUDA kernel) gives the reference vector
+    from oracle import asym_oracle
+    from pydca_b200.distributed import AsymmetricPlm
+    rngA = np.random.default_rng(9)
+    W_all = rngA.normal(size=(L * q, L * q)).astype(np.float32)
+    h_all = rngA.normal(size=L * q).astype(np.float32)
+    ap = AsymmetricPlm.__new__(AsymmetricPlm)
+    ap.group, ap.rank, ap.world, ap.L, ap.q = None, rank, world, L, q
+    ap.bounds = [shard_range(L, r, world)[0] for r in range(world)] + [L]
+    alo, ahi = ap.bounds[rank], ap.bounds[rank + 1]
+    ld_a = ap._ld(rank)
+    mine_a = np.zeros((L * q + 1, ld_a), dtype=np.float32)
+    mine_a[0, :(ahi - alo) * q] = h_all[alo * q:ahi * q]
+    mine_a[1:, :(ahi - alo) * q] = W_all[:, alo * q:ahi * q]
+    got_a = ap.gather(mine_a.ravel(), pack=lambda W, h, l_, q_: asym_oracle.symmetrise(h, W, l_, q_))
+    assert np.abs(got_a - asym_oracle.symmetrise(h_all, W_all, L, q)).max() == 0.0
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
