@@ -422,62 +422,6 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
     if (lane == 0) fxpart[k * gridDim.x + blockIdx.x] = fx;
 }
 
-// The same scan for SMALL grids (a multi-GPU shard of ~20 sites): there the kernel above is a few
-// hundred warps, one or two per SM, each walking its chain at the latency of ~250 dependent
-// instructions per step (0.9 us; 45 us for the 48 steps -- as long as the shard's logits kernel).
-// Here a warp is ONE chain (site, chunk) and lane a holds state a: a step is one coalesced load, two
-// 5-step shuffle reductions (max, sum) and one exp per lane -- ~0.15 us -- and there are 32x more warps.
-template <int Q>
-__global__ void __launch_bounds__(128)
-plm_softmax_small_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, const uint8_t *__restrict__ msa,
-                         const float *__restrict__ w, long N, int L, int site_lo, int nsites,
-                         int chunk, int warm, int carry, double *__restrict__ fxpart, int col_shift)
-{
-    static_assert(Q <= 32, "one lane per state");
-    constexpr int PF = 8;                                   // rows of S in flight per lane
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long k = (long)blockIdx.y * 4 + wib;
-    const long nbeg = k * chunk;
-    if (nbeg >= N) return;
-    const long nend = min(N, nbeg + (long)chunk);
-    const long nstart = carry ? max(0L, nbeg - (long)warm) : nbeg;
-    const int site = site_lo + (int)blockIdx.x;
-    const bool on = lane < Q;
-    const size_t col = (size_t)site * Q - (size_t)col_shift + (on ? lane : 0);
-    float p = 0.f, fx = 0.f;
-    float nxt[PF];
-#pragma unroll
-    for (int u = 0; u < PF; ++u) nxt[u] = (on && nstart + u < nend) ? S[(size_t)(nstart + u) * ld + col] : 0.f;
-    double fxd = 0.0;
-    for (long n0 = nstart; n0 < nend; n0 += PF) {
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            const long n = n0 + u;
-            if (n >= nend) break;                            // warp-uniform
-            const float s = nxt[u];
-            if (on && n + PF < nend) nxt[u] = S[(size_t)(n + PF) * ld + col];
-            float l = on ? (carry ? p + s : s) : -INFINITY;
-            float m = l;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            const float e = on ? expf(l - m) : 0.f;
-            float z = e;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-            p = e * (1.f / z);
-            if (n >= nbeg) {
-                const int r = msa[(size_t)n * L + site];
-                const float wn = w[n];
-                if (on) Rz[(size_t)n * ld + col] = wn * p - ((lane == r) ? wn : 0.f);
-                if (lane == r) fxd -= (double)(wn * logf(p));
-            }
-        }
-    }
-    (void)fx;
-    fxd = warp_sum(fxd);
-    if (lane == 0) fxpart[k * nsites + blockIdx.x] = fxd;
-}
-
 // ------------------------------------------------------------------------------
 // scatter: G[(j,b)][col] = sum_{n : s_nj == b} r[n][col], warp = one site j,
 // 21 float4 accumulators per lane, sequences visited in residue-bucket order
@@ -1079,7 +1023,6 @@ static int plm_setup_t(PlmProblem *p)
         DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_logits_kernel<Q, 64>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_softmax_kernel<Q, 1>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_softmax_kernel<Q, 4>)));
-        DCA_CUDA(cudaFuncGetAttributes(&fa, plm_softmax_small_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_scatter_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_init_fields_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, xr_barrier_kernel));
@@ -1120,15 +1063,12 @@ static int plm_eval_asym_t(PlmProblem *p, const float *d_x, float *d_g, const fl
                    *tm, p->tmM, ld, p->N, L, d_x, 0, p->ncol, p->d_S, 0, wt);
     PLM_MARK();
     dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
-    int nfx = (int)(gridB.x * p->nscan);
-    if ((long)gridB.x * gridB.y > 2L * sm_count()) {
+    if ((long)gridB.x * gridB.y > 2L * sm_count())
         DCA_LAUNCH((plm_softmax_kernel<Q, 1>), gridB, 128, 0, st, p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
                    p->chunk, p->warm, p->carry, p->d_fxpart, (double *)nullptr, lo * Q);
-    } else {
-        DCA_LAUNCH((plm_softmax_small_kernel<Q>), dim3(nsites, gridB.y), 128, 0, st, p->d_S, p->d_Rz, ld, p->d_msa, p->d_w,
-                   p->N, L, lo, nsites, p->chunk, p->warm, p->carry, p->d_fxpart, lo * Q);
-        nfx = (int)(nsites * p->nscan);
-    }
+    else
+        DCA_LAUNCH((plm_softmax_kernel<Q, 4>), gridB, 128, 0, st, p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
+                   p->chunk, p->warm, p->carry, p->d_fxpart, (double *)nullptr, lo * Q);
     PLM_MARK();
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
     const size_t gstride = (size_t)p->Lq * ld;
@@ -1136,6 +1076,7 @@ static int plm_eval_asym_t(PlmProblem *p, const float *d_x, float *d_g, const fl
     DCA_LAUNCH((plm_scatter_kernel<Q>), gridC, SC_WARPS * 32, smemC, st,
                p->tmS, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride, p->chunks_per_split, 0, p->sites_per_tile);
     PLM_MARK(); PLM_MARK();                                        // (no export)
+    const int nfx = (int)(gridB.x * p->nscan);
     dim3 gridF(ceil_div(ld, 1024), ceil_div(p->Lq + 1, p->fin_rows));
     DCA_LAUNCH((plm_asym_finish_kernel<Q>), gridF, 256, 0, st, d_x, p->d_G, gstride, p->nsplit, p->Lq, ld, p->ncol, lo,
                p->lh, p->lJ, p->fin_rows, d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket,
@@ -1189,21 +1130,14 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
 
     dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
     const int col_shift = 0;
-    int nfx = (int)(gridB.x * p->nscan);
-    if ((long)gridB.x * gridB.y > 2L * sm_count()) {
+    if ((long)gridB.x * gridB.y > 2L * sm_count())
         DCA_LAUNCH((plm_softmax_kernel<Q, 1>), gridB, 128, 0, st,
                    p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
                    p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift);
-    } else if (p->fidelity) {
+    else
         DCA_LAUNCH((plm_softmax_kernel<Q, 4>), gridB, 128, 0, st,
                    p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, p->d_fxsite, col_shift);
-    } else {        // small grid (a multi-GPU shard): one warp per chain, one lane per state
-        DCA_LAUNCH((plm_softmax_small_kernel<Q>), dim3(nsites, gridB.y), 128, 0, st,
-                   p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, nsites,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, col_shift);
-        nfx = (int)(nsites * p->nscan);
-    }
+                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift);
     PLM_MARK();
 
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
@@ -1214,6 +1148,7 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
                p->chunks_per_split, p->col_tile0, p->sites_per_tile);
     PLM_MARK();
 
+    const int nfx = (int)(gridB.x * p->nscan);
     if (p->sharded) {
         // export (+ signal) -> assemble (waits; its last CTA sums the scalars over the ranks)
         DCA_LAUNCH((plm_export_kernel<Q>), std::max(1, lo * Q), 128, 0, st, p->d_G, gstride, p->nsplit, ld, lo, hi,

@@ -162,8 +162,7 @@ def test_sharded_world1_is_the_plain_objective(port):
     x = (ref.init() + 0.1).astype(np.float32)
     f1, g1 = ref.eval(x)
     f2, g2 = one.eval(x)
-    # (fx: the two assemble kernels group their float64 partial sums differently -- last-bit differences)
-    assert abs(f1 - f2) <= 1e-13 * abs(f1) and (g1 == g2).all()
+    assert f1 == f2 and (g1 == g2).all()
     ref.close()
     one.disconnect()
     one.close()
