@@ -296,9 +296,10 @@ class AsymmetricPlm:
     def _ld(self, r):
         return -(-((self.bounds[r + 1] - self.bounds[r]) * self.q) // 128) * 128
 
-    def gather(self, x_local=None, device=None, pack=None):
+    def gather(self, x_local=None, device=None, pack=None, only_rank=None):
         """x_local: host copy of my vector (gloo / tests); None = the device-resident fit result (nccl).
-        pack: symmetrisation callable (tests substitute the oracle's); default the CUDA one."""
+        pack: symmetrisation callable (tests substitute the oracle's); default the CUDA one.
+        only_rank: symmetrise on that rank only (the others return None)."""
         import torch
         import torch.distributed as dist
         from . import _lib
@@ -317,6 +318,8 @@ class AsymmetricPlm:
                 mine = mine.cuda()
         out = torch.empty(self.world * (lq + 1) * ld_max, dtype=torch.float32, device=mine.device)
         dist.all_gather_into_tensor(out, mine.reshape(-1), group=self.group)
+        if only_rank is not None and self.rank != only_rank:
+            return None
         W, h = assemble_asym_slabs(out.cpu().numpy().reshape(self.world, lq + 1, ld_max), self.bounds, self.L, self.q)
         return (pack or _lib.asym_pack)(W, h, self.L, self.q)
 

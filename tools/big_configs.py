@@ -10,6 +10,8 @@ CUDA-event time of a short fit (max over ranks) -> evaluations/s, per-kernel ms 
 evaluation on rank 0 and on the last rank, and a numerical check of the gathered parameters
 against a single-GPU fit of the same input made in the same run on rank 0's GPU.
 --e2e additionally times the reference's entry point plmdcaBackend(file) with DCA_B200_GPUS=G.
+--asym additionally runs the asymmetric (per-site) estimator on the same G GPUs: independent fits of equal
+site ranges (no exchange), one NCCL all-gather of the column slabs, symmetrisation on rank 0.
 """
 import json
 import os
@@ -35,6 +37,7 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "c4"
     iters = int(sys.argv[2]) if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else 10
     want_e2e = "--e2e" in sys.argv
+    want_asym = "--asym" in sys.argv
     N, L = CONFIGS[name]
     q = 21
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -113,6 +116,34 @@ def main():
     torch.cuda.synchronize()
     dist.barrier(group=cpu)
     sp.close()
+
+    if want_asym:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu)
+        ap = dd.AsymmetricPlm(msa, w, q, lam, lam)
+        ap.fit(2)                                                              # warm
+        ams = ap.obj.eval_timed(ap.obj.init())
+        dist.barrier()
+        ra = ap.fit(iters)
+        a_ms = tmax(ra.device_ms)
+        a_ev = int(tmax(float(ra.evaluations)))
+        t = time.perf_counter()
+        xa = ap.gather(only_rank=0)
+        torch.cuda.synchronize()
+        t_gather = time.perf_counter() - t
+        ap.close()
+        if rank == 0:
+            fn_a, _ = _lib.plm_fn_apc(xa, L, q)
+            fn_j, _ = _lib.plm_fn_apc(x, L, q)
+            top = L
+            ra_, rj_ = np.argsort(-fn_a, kind="stable")[:top], np.argsort(-fn_j, kind="stable")[:top]
+            line["asymmetric"] = {"iterations": ra.iterations, "evaluations_max_over_ranks": a_ev,
+                                  "fit_device_ms_max_over_ranks": a_ms, "evals_per_s": a_ev / (a_ms * 1e-3),
+                                  "gather_and_symmetrise_seconds_rank0": t_gather,
+                                  "kernel_ms_rank0": {k: round(v, 3) for k, v in ams.items()},
+                                  "fn_topL_overlap_with_joint_fit_after_%d_iterations" % iters:
+                                      int(len(set(ra_.tolist()) & set(rj_.tolist()))), "topL": top}
+        dist.barrier(group=cpu)
 
     if want_e2e:
         torch.cuda.synchronize()
