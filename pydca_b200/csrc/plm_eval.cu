@@ -709,70 +709,90 @@ plm_assemble_kernel(const float *__restrict__ x, const float *__restrict__ G, si
 //   g_W = sum_splits G + lambda_J * W      (diagonal blocks j == i and pad columns: 0)
 //   g_h[(i,a)] = sum_b G[(i,b)][(i,a)] + 2 lambda_h h     (sum_b [s_ni == b] = 1: any row block sums
 //                                                          r_n(i,a) over n; the diagonal one is used)
-// grid (ceil(ld / 1024), ceil((Lq + 1) / rows)); the CTA of the last row group also owns the field row.
+// grid (ceil(ld / 1024), row groups + field groups): CTAs with blockIdx.y < row_groups own `rows_per_cta` rows of
+// W x 1024 columns (thread = 4 columns, float4); the remaining CTAs own the field row, 128 columns each, the
+// Q x nsplit terms of a column spread over the 8 warps (as a tail of one row-group CTA that sum was a serial
+// chain of Q * nsplit loads per thread: 0.04 ms of a 0.06 ms kernel on a 19-site shard).
 template <int Q>
 __global__ void __launch_bounds__(256)
 plm_asym_finish_kernel(const float *__restrict__ x, const float *__restrict__ G, size_t g_split_stride, int nsplit,
-                       int Lq, int ld, int ncol, int site_lo, float lh, float lJ, int rows_per_cta,
+                       int Lq, int ld, int ncol, int site_lo, float lh, float lJ, int rows_per_cta, int row_groups,
                        const float *__restrict__ d, float *__restrict__ g, double *__restrict__ red,
                        const double *__restrict__ fxpart, int nfx, unsigned *__restrict__ ticket,
                        unsigned n_active, double *__restrict__ scal)
 {
-    const int c = ((int)blockIdx.x * 256 + (int)threadIdx.x) * 4;           // my 4 columns
-    const int r0 = (int)blockIdx.y * rows_per_cta;
     double s_reg = 0.0, s_dg = 0.0, s_gg = 0.0, s_xx = 0.0;
-    if (c < ld) {
-        int site[4];
-        bool valid[4];
+    if ((int)blockIdx.y < row_groups) {
+        const int c = ((int)blockIdx.x * 256 + (int)threadIdx.x) * 4;           // my 4 columns
+        const int r0 = (int)blockIdx.y * rows_per_cta;
+        if (c < ld) {
+            int site[4];
+            bool valid[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { valid[e] = (c + e) < ncol; site[e] = site_lo + (c + e) / Q; }
-        const float *xw = x + ld;
-        float *gw = g + ld;
-        const float *dw = d ? d + ld : nullptr;
-        for (int r = r0; r < min(r0 + rows_per_cta, Lq); ++r) {
-            const size_t o = (size_t)r * ld + c;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s = 0; s < nsplit; ++s) {
-                const float4 v = *reinterpret_cast<const float4 *>(G + (size_t)s * g_split_stride + o);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-            const float4 xv = *reinterpret_cast<const float4 *>(xw + o);
-            const int rs = r / Q;
-            const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
-            const float ge[4] = {acc.x, acc.y, acc.z, acc.w};
-            float out[4];
+            for (int e = 0; e < 4; ++e) { valid[e] = (c + e) < ncol; site[e] = site_lo + (c + e) / Q; }
+            const float *xw = x + ld;
+            float *gw = g + ld;
+            const float *dw = d ? d + ld : nullptr;
+            for (int r = r0; r < min(r0 + rows_per_cta, Lq); ++r) {
+                const size_t o = (size_t)r * ld + c;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s = 0; s < nsplit; ++s) {
+                    const float4 v = *reinterpret_cast<const float4 *>(G + (size_t)s * g_split_stride + o);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                const float4 xv = *reinterpret_cast<const float4 *>(xw + o);
+                const int rs = r / Q;
+                const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+                const float ge[4] = {acc.x, acc.y, acc.z, acc.w};
+                float out[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const bool on = valid[e] && rs != site[e];
-                out[e] = on ? (ge[e] + lJ * xe[e]) : 0.f;
-                if (on) { s_reg += 0.5 * (double)lJ * xe[e] * xe[e]; s_xx += (double)xe[e] * xe[e]; }
-                s_gg += (double)out[e] * out[e];
-            }
-            *reinterpret_cast<float4 *>(gw + o) = make_float4(out[0], out[1], out[2], out[3]);
-            if (dw) {
-                const float4 dv = *reinterpret_cast<const float4 *>(dw + o);
-                s_dg += (double)out[0] * dv.x + (double)out[1] * dv.y + (double)out[2] * dv.z + (double)out[3] * dv.w;
-            }
-        }
-        if (blockIdx.y == gridDim.y - 1) {                                 // the field row
-            float out[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                out[e] = 0.f;
-                if (valid[e]) {
-                    const float h = x[c + e];
-                    float col = 0.f;
-                    for (int s = 0; s < nsplit; ++s) {
-                        const float *Gs = G + (size_t)s * g_split_stride;
-                        for (int b = 0; b < Q; ++b) col += Gs[((size_t)site[e] * Q + b) * ld + c + e];
-                    }
-                    out[e] = 2.f * lh * h + col;
-                    s_reg += (double)lh * h * h; s_xx += (double)h * h;
+                for (int e = 0; e < 4; ++e) {
+                    const bool on = valid[e] && rs != site[e];
+                    out[e] = on ? (ge[e] + lJ * xe[e]) : 0.f;
+                    if (on) { s_reg += 0.5 * (double)lJ * xe[e] * xe[e]; s_xx += (double)xe[e] * xe[e]; }
                     s_gg += (double)out[e] * out[e];
-                    if (d) s_dg += (double)out[e] * d[c + e];
+                }
+                *reinterpret_cast<float4 *>(gw + o) = make_float4(out[0], out[1], out[2], out[3]);
+                if (dw) {
+                    const float4 dv = *reinterpret_cast<const float4 *>(dw + o);
+                    s_dg += (double)out[0] * dv.x + (double)out[1] * dv.y + (double)out[2] * dv.z + (double)out[3] * dv.w;
                 }
             }
-            *reinterpret_cast<float4 *>(g + c) = make_float4(out[0], out[1], out[2], out[3]);
+        }
+    } else {
+        // the field row: 128 columns per CTA, warp w takes the states b = w, w + 8, w + 16
+        __shared__ float fs[8][128];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const int c0 = (((int)blockIdx.y - row_groups) * (int)gridDim.x + (int)blockIdx.x) * 128;
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c0 < ld) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = c0 + 4 * lane + e;
+                if (c < ncol) {
+                    const size_t row0 = (size_t)(site_lo + c / Q) * Q;
+                    for (int b = wid; b < Q; b += 8)
+                        for (int s = 0; s < nsplit; ++s) part[e] += G[(size_t)s * g_split_stride + (row0 + b) * ld + c];
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) fs[wid][4 * lane + e] = part[e];
+        __syncthreads();
+        if (threadIdx.x < 128 && c0 < ld) {
+            const int c = c0 + (int)threadIdx.x;
+            float out = 0.f;
+            if (c < ncol) {
+                float col = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) col += fs[w8][threadIdx.x];
+                const float h = x[c];
+                out = 2.f * lh * h + col;
+                s_reg += (double)lh * h * h; s_xx += (double)h * h;
+                s_gg += (double)out * out;
+                if (d) s_dg += (double)out * d[c];
+            }
+            g[c] = out;
         }
     }
     assemble_finish(s_reg, s_dg, s_gg, s_xx, red, fxpart, nfx, ticket, n_active, scal);
@@ -1077,9 +1097,10 @@ static int plm_eval_asym_t(PlmProblem *p, const float *d_x, float *d_g, const fl
                p->tmS, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride, p->chunks_per_split, 0, p->sites_per_tile);
     PLM_MARK(); PLM_MARK();                                        // (no export)
     const int nfx = (int)(gridB.x * p->nscan);
-    dim3 gridF(ceil_div(ld, 1024), ceil_div(p->Lq + 1, p->fin_rows));
+    const int row_groups = ceil_div(p->Lq, p->fin_rows), field_groups = ceil_div(ceil_div(ld, 128), ceil_div(ld, 1024));
+    dim3 gridF(ceil_div(ld, 1024), row_groups + field_groups);
     DCA_LAUNCH((plm_asym_finish_kernel<Q>), gridF, 256, 0, st, d_x, p->d_G, gstride, p->nsplit, p->Lq, ld, p->ncol, lo,
-               p->lh, p->lJ, p->fin_rows, d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket,
+               p->lh, p->lJ, p->fin_rows, row_groups, d_dir, d_g, p->d_red, p->d_fxpart, nfx, p->d_ticket,
                gridF.x * gridF.y, p->d_scal);
     PLM_MARK();
 #undef PLM_MARK
@@ -1327,8 +1348,8 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
         p->Ploc = (long)p->ld * (p->Lq + 1);
         // finish kernel: enough CTAs to fill the GPU a few times over
         p->fin_rows = 8;
-        while (p->fin_rows > 1 && (long)ceil_div(p->ld, 1024) * ceil_div(p->Lq + 1, p->fin_rows) < 4L * sm_count()) p->fin_rows >>= 1;
-        p->red_blocks = std::max(p->red_blocks, ceil_div(p->ld, 1024) * ceil_div(p->Lq + 1, p->fin_rows));
+        while (p->fin_rows > 1 && (long)ceil_div(p->ld, 1024) * ceil_div(p->Lq, p->fin_rows) < 4L * sm_count()) p->fin_rows >>= 1;
+        p->red_blocks = std::max(p->red_blocks, ceil_div(p->ld, 1024) * (ceil_div(p->Lq, p->fin_rows) + 8));
     }
     if (sharded) {
         p->sharded = true;
