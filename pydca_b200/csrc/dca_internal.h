@@ -35,6 +35,19 @@ struct DevBuf {
 int make_tensor_map_2d(void *out_CUtensorMap, int elem_bytes, const void *base, unsigned long long dim0,
                        unsigned long long dim1, unsigned long long stride1_bytes, unsigned box0, unsigned box1);
 
+// index of the first residue code >= q, or -1.  The common case (none) is one branch-free max over the
+// bytes, which the host compiler vectorises; a loop with an early exit per byte cost 1.5 ms of the
+// 4 ms frequency stage at N = 20000, L = 300.
+static inline long first_bad_residue(const uint8_t *msa, long count, int q)
+{
+    uint8_t mx = 0;
+    for (long k = 0; k < count; ++k) mx = msa[k] > mx ? msa[k] : mx;
+    if ((int)mx < q) return -1;
+    for (long k = 0; k < count; ++k)
+        if (msa[k] >= q) return k;
+    return -1;
+}
+
 // ---- capi.cu ------------------------------------------------------------------
 // GPUs one call may drive: dca_set_gpus() > DCA_B200_GPUS > all visible, capped by `limit`
 int backend_gpu_count(int limit);

@@ -201,17 +201,18 @@ __global__ void mf_corr_kernel(const double *__restrict__ F, size_t f_split_stri
 // epilogue's read-modify-write of C -- 256 KB per tile at ~44 GB/s per SM, 20 % of the CTA's life --
 // overlapped with nothing).  Which tiles a launch touches is a `mode`:
 //   GM_ALL    grid (nb, rows/BM): every tile
-//   GM_PRIO   step k of the symmetric Gauss-Jordan, the tiles step k+1's pivot panel is built from:
-//             row block k+1 (tiles (k+1, j <= k+1)) and column block k+1 (tiles (i > k+1, k+1));
-//             grid (nb, 128/BM), blockIdx.x enumerates them
-//   GM_REST   the other tiles (i, j <= i) of every row block i != k (and not in the PRIO set); row block k
+//   GM_BLK    step k of the symmetric Gauss-Jordan, the tiles of "block m" = row block m (tiles (m, j <= m)) and
+//             column block m (tiles (i > m, m)); grid (nb, 128/BM), blockIdx.x enumerates them.  m = k + 1 is what
+//             the pivot panel of step k + 1 is built from, m = k + 2 what the step after needs first (the tile
+//             (k + 2, k + 1) belongs to block k + 1 and is skipped when m = k + 2)
+//   GM_REST   the other tiles (i, j <= i) of every row block i != k (not in blocks k + 1, k + 2); row block k
 //             itself is the pivot row of the step: its tiles are copied from B (= Rk).  grid
 //             (nb (nb + 1) / 2, 128/BM), blockIdx.x enumerates the lower tiles
 constexpr int GJ_B = 128;
 constexpr int GM_KC = 16;
 constexpr int GM_AS = 20;      // A smem row stride (doubles): 4 mod 16 -> conflict-free LDS.64
 constexpr int GM_BS = 132;     // B smem row stride (doubles)
-enum { GM_ALL = 0, GM_PRIO = 1, GM_REST = 2 };
+enum { GM_ALL = 0, GM_BLK = 1, GM_REST = 2 };
 
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
 {
@@ -222,17 +223,18 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 template <int BM>
 __global__ void __launch_bounds__(BM * 2, (BM == 64) ? 3 : 1)
 dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, int lda,
-                const double *__restrict__ B, int ldb, double alpha, double beta, int mode, int k)
+                const double *__restrict__ B, int ldb, double alpha, double beta, int mode, int k, int m)
 {
     constexpr int NT = BM * 2;                 // threads: one warp per 32 x 64 patch
     constexpr int SUB = GJ_B / BM;             // row sub-tiles per 128-row block
     int tr, tc, sub;                           // 128-blocked tile coordinates + row sub-tile
     if (mode == GM_ALL) {
         tc = blockIdx.x; tr = blockIdx.y / SUB; sub = blockIdx.y % SUB;
-    } else if (mode == GM_PRIO) {
+    } else if (mode == GM_BLK) {
         const int t = blockIdx.x;
         sub = blockIdx.y;
-        if (t <= k + 1) { tr = k + 1; tc = t; } else { tr = t; tc = k + 1; }
+        if (t <= m) { tr = m; tc = t; } else { tr = t; tc = m; }
+        if (m == k + 2 && tr == k + 2 && tc == k + 1) return;       // belongs to block k + 1
     } else {
         // blockIdx.x enumerates the tiles (tr, tc <= tr) row by row
         const int t = blockIdx.x;
@@ -241,7 +243,8 @@ dgemm128_kernel(double *__restrict__ C, int ldc, const double *__restrict__ A, i
         while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
         while (tr * (tr + 1) / 2 > t) --tr;
         tc = t - tr * (tr + 1) / 2;
-        if (tr == k + 1 || (tc == k + 1 && tr > k + 1)) return;
+        if (tr == k + 1 || (tc == k + 1 && tr > k + 1)) return;          // block k + 1
+        if (tr == k + 2 || (tc == k + 2 && tr > k + 2)) return;          // block k + 2
         if (tr == k) {
             // row block k of the result is Rk itself (B): copy this CTA's BM x 128 piece
             const double *src = B + (size_t)sub * BM * ldb + (size_t)tc * GJ_B;
@@ -455,13 +458,20 @@ __global__ void negate_copy_kernel(const double *__restrict__ A, int ld, int n, 
 // Look-ahead schedule.  Step k needs the pivot panel (Ck, Rk = Dinv_k * row block k), whose producers
 // -- the single-CTA diagonal inverse, the gather and a 128-row GEMM -- are latency-bound kernels
 // that leave the GPU empty (0.06 + 0.19 ms per step when they ran in line).  Everything they read
-// lives in row block k+1 and column block k+1, so step k updates those nb tiles first (GM_PRIO), and
-// a high-priority side stream builds panel k+1 (double-buffered Ck / Arow / Rk) while the main stream
-// finishes the rank-128 update of the remaining tiles and stores row block k (GM_REST).
-//   main:  wait panel(k) | PRIO update(k) | record | REST update(k) | row block k := Rk
-//   side:                                   wait   | Dinv(k+1) | gather(k+1) | Rk(k+1) | record panel(k+1)
-// gather(k+1) resets column block k+1 of A, which REST(k) does not touch; REST(k+1) follows on the
-// main stream, after row block k has been stored.
+// lives in "block k+1" (row block k+1 and column block k+1), so the rank-128 update of step k is cut in
+// three launches -- U1(k): block k+1, U2(k): block k+2, REST(k): everything else plus the store of row
+// block k -- and the small ones run on two high-priority side streams, up to two steps ahead of the
+// main stream, which only ever runs the big update:
+//   main:    wait panel(k)                  | REST(k)                          | record rest(k)
+//   side A:  wait u2(k)                     | U1(k+1) | panel(k+2) = Dinv, gather, Rk | record panel(k+2)
+//   side B:  wait rest(k), panel(k+1)       | U2(k+1)                          | record u2(k+1)
+// U1(k+1) needs panel(k+1) (side A order) and step k on block k+2, i.e. U2(k) (+ the tile (k+2,k+1), which
+// U1(k) updated: side A order).  U2(k+1) needs panel(k+1) and step k on block k+3: REST(k), U1(k) for the
+// tile (k+3,k+1) (before panel(k+1) on side A) and U2(k) for (k+3,k+2) (side B order).  REST(k) touches neither
+// block k+1 nor k+2, so everything on the side streams overlaps it and fills its last partial wave;
+// panel(k+2) resets column block k+2 of A, which REST(k), REST(k+1) skip.  Ck / Arow / Rk are
+// triple-buffered: panel(k+2) overwrites the buffers of panel(k-1), whose last readers REST(k-1) (main) and
+// U2(k-1) (side B) precede U2(k), which side A waits for.
 static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
 {
     const int nb = npad / GJ_B;
@@ -478,64 +488,94 @@ static int gj_invert_device(double *d_A, int npad, cudaStream_t st)
         }
         pivot_tol = 1e-14 * mx;
     }
-    DevBuf<double> Dinv, Ck[2], Rk[2], Arow[2];
+    DevBuf<double> Dinv, Ck[3], Rk[3], Arow[3];
     DevBuf<int> info_buf;
     if (!Dinv.alloc((size_t)GJ_B * GJ_B) || !info_buf.alloc(1)) return -1;
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < 3; ++b)
         if (!Ck[b].alloc((size_t)npad * GJ_B) || !Rk[b].alloc((size_t)npad * GJ_B) || !Arow[b].alloc((size_t)npad * GJ_B))
             return -1;
     int *d_info = info_buf.p;
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_prio = nullptr, ev_panel = nullptr;
-    {   // highest priority: its small grids must get SMs while the big update is still queued
+    std::vector<cudaEvent_t> ev_panel((size_t)nb, nullptr), ev_u2((size_t)nb, nullptr), ev_rest((size_t)nb, nullptr);
+    cudaEvent_t ev_start = nullptr;
+    cudaStream_t sideB = nullptr;
+    {   // highest priority: the small grids must get SMs while the big update is still queued
         int prio_lo = 0, prio_hi = 0;
         DCA_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         DCA_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
+        DCA_CUDA(cudaStreamCreateWithPriority(&sideB, cudaStreamNonBlocking, prio_hi));
     }
-    DCA_CUDA(cudaEventCreateWithFlags(&ev_prio, cudaEventDisableTiming));
-    DCA_CUDA(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
+    for (int k = 0; k < nb; ++k) {
+        DCA_CUDA(cudaEventCreateWithFlags(&ev_panel[(size_t)k], cudaEventDisableTiming));
+        DCA_CUDA(cudaEventCreateWithFlags(&ev_u2[(size_t)k], cudaEventDisableTiming));
+        DCA_CUDA(cudaEventCreateWithFlags(&ev_rest[(size_t)k], cudaEventDisableTiming));
+    }
+    DCA_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
     DCA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), st));
     constexpr int BM = 64, SUB = GJ_B / BM;
     const size_t smem_gemm = sizeof(double) * (2 * BM * GM_AS + 2 * GM_KC * GM_BS);
     DCA_CUDA(cudaFuncSetAttribute(dgemm128_kernel<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
-    // panel of step kk on stream s: Dinv_kk, column / row block kk rebuilt from the lower tiles (column
+    // panel of step kk on side stream A: Dinv_kk, column / row block kk rebuilt from the lower tiles (column
     // block kk reset to unit columns), Rk (128 x npad) = Dinv_kk * row block kk
-    auto panel = [&](int kk, cudaStream_t s) -> int {
-        const int b = kk & 1;
-        DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, 0, s, d_A, npad, kk, Dinv.p, d_info, pivot_tol);
-        DCA_LAUNCH(gj_gather_kernel, (unsigned)ceil_div<long>((long)npad * GJ_B, 256), 256, 0, s, d_A, npad, npad, kk,
+    auto panel = [&](int kk) -> int {
+        const int b = kk % 3;
+        DCA_LAUNCH(gj_diag_inv_kernel, 1, 512, 0, side, d_A, npad, kk, Dinv.p, d_info, pivot_tol);
+        DCA_LAUNCH(gj_gather_kernel, (unsigned)ceil_div<long>((long)npad * GJ_B, 256), 256, 0, side, d_A, npad, npad, kk,
                    Ck[b].p, Arow[b].p);
-        DCA_LAUNCH(dgemm128_kernel<BM>, dim3(nb, SUB), BM * 2, smem_gemm, s,
-                   Rk[b].p, npad, Dinv.p, GJ_B, Arow[b].p, npad, 1.0, 0.0, (int)GM_ALL, 0);
+        DCA_LAUNCH(dgemm128_kernel<BM>, dim3(nb, SUB), BM * 2, smem_gemm, side,
+                   Rk[b].p, npad, Dinv.p, GJ_B, Arow[b].p, npad, 1.0, 0.0, (int)GM_ALL, 0, 0);
+        DCA_CUDA(cudaEventRecord(ev_panel[(size_t)kk], side));
         return 0;
     };
-    int rc = panel(0, st);
+    // A[i,j] -= Ck[i] * Rk[j] of step kk on the tiles of block m
+    auto update_block = [&](int kk, int m, cudaStream_t s) -> int {
+        const int b = kk % 3;
+        DCA_LAUNCH(dgemm128_kernel<BM>, dim3(nb, SUB), BM * 2, smem_gemm, s,
+                   d_A, npad, Ck[b].p, GJ_B, Rk[b].p, npad, -1.0, 1.0, (int)GM_BLK, kk, m);
+        return 0;
+    };
+    DCA_CUDA(cudaEventRecord(ev_start, st));               // the matrix (and the memset) precede this point on st
+    DCA_CUDA(cudaStreamWaitEvent(side, ev_start, 0));
+    int rc = panel(0);
+    if (rc == 0 && nb > 1) { rc = update_block(0, 1, side); if (rc == 0) rc = panel(1); }
+    if (rc == 0 && nb > 2) {                                // U2(0)
+        DCA_CUDA(cudaStreamWaitEvent(sideB, ev_panel[0], 0));
+        rc = update_block(0, 2, sideB);
+        if (rc == 0) DCA_CUDA(cudaEventRecord(ev_u2[0], sideB));
+    }
     for (int k = 0; k < nb && rc == 0; ++k) {
-        const int b = k & 1;
-        if (k > 0) DCA_CUDA(cudaStreamWaitEvent(st, ev_panel, 0));          // panel k from the side stream
-        if (k + 1 < nb) {
-            // A[i,j] -= Ck[i] * Rk[j] on row block k+1 and column block k+1 first, then panel k+1 on the side stream
-            DCA_LAUNCH(dgemm128_kernel<BM>, dim3(nb, SUB), BM * 2, smem_gemm, st,
-                       d_A, npad, Ck[b].p, GJ_B, Rk[b].p, npad, -1.0, 1.0, (int)GM_PRIO, k);
-            DCA_CUDA(cudaEventRecord(ev_prio, st));
-            DCA_CUDA(cudaStreamWaitEvent(side, ev_prio, 0));
-            // (panel k+1 overwrites the buffers of panel k-1: REST(k-1) precedes PRIO(k) on the main stream)
-            rc = panel(k + 1, side);
-            if (rc != 0) break;
-            DCA_CUDA(cudaEventRecord(ev_panel, side));
-        }
-        // the tiles j <= i of every other row block i != k: half the rank-128 updates of the unsymmetric
-        // algorithm (n^3 instead of 2 n^3 flops)
-        // (row block k, the part below / on the diagonal, is stored by the same launch)
+        const int b = k % 3;
+        // the tiles j <= i of every row block i != k outside blocks k+1, k+2 (half the rank-128 updates of the
+        // unsymmetric algorithm: n^3 instead of 2 n^3 flops) and the store of row block k, below / on the diagonal
+        DCA_CUDA(cudaStreamWaitEvent(st, ev_panel[(size_t)k], 0));
         DCA_LAUNCH(dgemm128_kernel<BM>, dim3(nb * (nb + 1) / 2, SUB), BM * 2, smem_gemm, st,
-                   d_A, npad, Ck[b].p, GJ_B, Rk[b].p, npad, -1.0, 1.0, (int)GM_REST, k);
+                   d_A, npad, Ck[b].p, GJ_B, Rk[b].p, npad, -1.0, 1.0, (int)GM_REST, k, 0);
+        DCA_CUDA(cudaEventRecord(ev_rest[(size_t)k], st));
+        if (k + 2 < nb) {                                   // side A: U1(k+1), panel(k+2)
+            DCA_CUDA(cudaStreamWaitEvent(side, ev_u2[(size_t)k], 0));
+            rc = update_block(k + 1, k + 2, side);
+            if (rc == 0) rc = panel(k + 2);
+            if (rc != 0) break;
+        }
+        if (k + 3 < nb) {                                   // side B: U2(k+1)
+            DCA_CUDA(cudaStreamWaitEvent(sideB, ev_rest[(size_t)k], 0));
+            DCA_CUDA(cudaStreamWaitEvent(sideB, ev_panel[(size_t)k + 1], 0));
+            rc = update_block(k + 1, k + 3, sideB);
+            if (rc == 0) DCA_CUDA(cudaEventRecord(ev_u2[(size_t)k + 1], sideB));
+        }
     }
     if (rc == 0) DCA_LAUNCH(gj_mirror_kernel, dim3(npad / 32, npad / 32), dim3(32, 8), 0, st, d_A, npad, npad);
     int info = 0;
     if (rc == 0) DCA_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
     cudaStreamSynchronize(side);
+    cudaStreamSynchronize(sideB);
     cudaStreamSynchronize(st);
-    cudaStreamDestroy(side); cudaEventDestroy(ev_prio); cudaEventDestroy(ev_panel);
+    cudaStreamDestroy(side);
+    cudaStreamDestroy(sideB);
+    for (auto e : ev_panel) if (e) cudaEventDestroy(e);
+    for (auto e : ev_u2) if (e) cudaEventDestroy(e);
+    for (auto e : ev_rest) if (e) cudaEventDestroy(e);
+    cudaEventDestroy(ev_start);
     if (rc != 0) return -1;
     if (info != 0) {
         set_error("mf_couplings: pivot at row %d is not positive: the correlation matrix is singular or indefinite to "
@@ -628,8 +668,10 @@ static int mf_prepare(MfWork &W, const uint8_t *msa, const double *w, long N, in
     if (require_device() != 0) return -1;
     if (q != 21 && q != 5) { set_error("mf: num_site_states must be 21 or 5 (got %d)", q); return -1; }
     if (N <= 0 || L < 2) { set_error("mf: empty alignment (N=%ld L=%d)", N, L); return -1; }
-    for (long k = 0; k < N * (long)L; ++k)
-        if (msa[k] >= q) { set_error("mf: residue code %d >= q=%d at flat index %ld", msa[k], q, k); return -1; }
+    {
+        const long k = first_bad_residue(msa, N * (long)L, q);
+        if (k >= 0) { set_error("mf: residue code %d >= q=%d at flat index %ld", msa[k], q, k); return -1; }
+    }
     const int Lq = L * q;
     W.ld = ceil_div(Lq, MF_TC) * MF_TC;
     W.nsplit = 1;

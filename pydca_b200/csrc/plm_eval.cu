@@ -1292,8 +1292,10 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     if (site_lo < 0 || site_hi > L || site_lo >= site_hi) {
         set_error("plm: bad site shard [%d,%d) for L=%d", site_lo, site_hi, L); return nullptr;
     }
-    for (long k = 0; k < N * (long)L; ++k)
-        if (h_msa[k] >= q) { set_error("plm: residue code %d >= q=%d at flat index %ld", h_msa[k], q, k); return nullptr; }
+    {
+        const long k = first_bad_residue(h_msa, N * (long)L, q);
+        if (k >= 0) { set_error("plm: residue code %d >= q=%d at flat index %ld", h_msa[k], q, k); return nullptr; }
+    }
 
     PlmProblem *p = new PlmProblem();
     p->N = N; p->L = L; p->q = q; p->Lq = L * q;
