@@ -719,12 +719,11 @@ int mf_freqs_host(const uint8_t *msa, const double *w, long N, int L, int q, dou
     DCA_CUDA(cudaMemcpy(fi, W.d_fi, sizeof(double) * (size_t)Lq, cudaMemcpyDeviceToHost));
     if (fij) {
         const long total = (long)L * (L - 1) / 2 * (q - 1) * (q - 1);
-        double *d_fij = nullptr;
-        DCA_CUDA(cudaMalloc(&d_fij, sizeof(double) * (size_t)total));
+        DevBuf<double> d_fij;
+        if (!d_fij.alloc((size_t)total)) return -1;
         DCA_LAUNCH(mf_pack_fij_kernel, (unsigned)ceil_div<long>(total, 256), 256, 0, 0,
-                   W.d_F, W.fstride, W.nsplit, L, q, W.ld, W.meff, d_fij);
-        cudaError_t e = cudaMemcpy(fij, d_fij, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost);
-        cudaFree(d_fij);
+                   W.d_F, W.fstride, W.nsplit, L, q, W.ld, W.meff, d_fij.p);
+        cudaError_t e = cudaMemcpy(fij, d_fij.p, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { set_error("mf_freqs: D2H failed: %s", cudaGetErrorString(e)); return -1; }
     }
     return 0;
@@ -791,17 +790,14 @@ int mf_corr_from_freqs_host(const double *reg_fi, const double *reg_fij, int L, 
     if (L < 2 || q < 2) { set_error("construct_corr_mat: bad shape L=%d q=%d", L, q); return -1; }
     const int qm1 = q - 1, n = L * qm1;
     const size_t nfij = (size_t)L * (L - 1) / 2 * qm1 * qm1;
-    double *d_fi = nullptr, *d_fij = nullptr, *d_C = nullptr;
-    DCA_CUDA(cudaMalloc(&d_fi, sizeof(double) * (size_t)L * q));
-    DCA_CUDA(cudaMalloc(&d_fij, sizeof(double) * nfij));
-    DCA_CUDA(cudaMalloc(&d_C, sizeof(double) * (size_t)n * n));
-    DCA_CUDA(cudaMemcpy(d_fi, reg_fi, sizeof(double) * (size_t)L * q, cudaMemcpyHostToDevice));
-    DCA_CUDA(cudaMemcpy(d_fij, reg_fij, sizeof(double) * nfij, cudaMemcpyHostToDevice));
+    DevBuf<double> d_fi, d_fij, d_C;          // cached blocks, released on every return path
+    if (!d_fi.alloc((size_t)L * q) || !d_fij.alloc(nfij) || !d_C.alloc((size_t)n * n)) return -1;
+    DCA_CUDA(cudaMemcpy(d_fi.p, reg_fi, sizeof(double) * (size_t)L * q, cudaMemcpyHostToDevice));
+    DCA_CUDA(cudaMemcpy(d_fij.p, reg_fij, sizeof(double) * nfij, cudaMemcpyHostToDevice));
     dim3 grid(ceil_div(n, 256), n);
-    DCA_LAUNCH(mf_corr_from_freqs_kernel, grid, 256, 0, 0, d_fi, d_fij, L, q, n, d_C);
+    DCA_LAUNCH(mf_corr_from_freqs_kernel, grid, 256, 0, 0, d_fi.p, d_fij.p, L, q, n, d_C.p);
     DCA_CUDA(cudaGetLastError());
-    DCA_CUDA(cudaMemcpy(corr, d_C, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
-    cudaFree(d_fi); cudaFree(d_fij); cudaFree(d_C);
+    DCA_CUDA(cudaMemcpy(corr, d_C.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -947,8 +943,9 @@ int mf_couplings_host(const double *corr, int n, double *out)
 {
     if (require_device() != 0) return -1;
     const int npad = ceil_div(n, GJ_B) * GJ_B;
-    double *d_A = nullptr, *d_out = nullptr;
-    DCA_CUDA(cudaMalloc(&d_A, sizeof(double) * (size_t)npad * npad));
+    DevBuf<double> A_buf, out_buf;            // cached blocks, released on every return path
+    if (!A_buf.alloc((size_t)npad * npad)) return -1;
+    double *d_A = A_buf.p, *d_out = nullptr;
     DCA_CUDA(cudaMemset(d_A, 0, sizeof(double) * (size_t)npad * npad));
     DCA_CUDA(cudaMemcpy2D(d_A, sizeof(double) * (size_t)npad, corr, sizeof(double) * (size_t)n,
                           sizeof(double) * (size_t)n, (size_t)n, cudaMemcpyHostToDevice));
@@ -983,14 +980,15 @@ int mf_couplings_host(const double *corr, int n, double *out)
     }
     if (rc == 0) rc = gj_invert_device(d_A, npad, 0);
     if (rc == 0) {
-        if (cudaMalloc(&d_out, sizeof(double) * (size_t)n * n) != cudaSuccess) { set_error("mf_couplings: out of device memory"); rc = -1; }
+        if (!out_buf.alloc((size_t)n * n)) rc = -1;
+        d_out = out_buf.p;
     }
     if (rc == 0) {
         DCA_LAUNCH(negate_copy_kernel, (unsigned)ceil_div<long>((long)n * n, 256), 256, 0, 0, d_A, npad, n, d_out);
         cudaError_t e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { set_error("mf_couplings: D2H failed: %s", cudaGetErrorString(e)); rc = -1; }
     }
-    cudaFree(d_A); cudaFree(d_out);
+    cudaDeviceSynchronize();                  // nothing of this call is in flight when the blocks go back to the cache
     return rc;
 }
 

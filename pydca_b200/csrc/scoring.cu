@@ -91,10 +91,11 @@ static int fn_apc_impl(const SRC *h_src, size_t count, int L, int q, int is_matr
     if (require_device() != 0) return -1;
     if (L < 2 || q < 2) { set_error("fn_apc: bad shape L=%d q=%d", L, q); return -1; }
     const long npairs = (long)L * (L - 1) / 2;
-    SRC *d_src = nullptr;
-    double *d_fn = nullptr;
-    DCA_CUDA(cudaMalloc(&d_src, sizeof(SRC) * count));
-    DCA_CUDA(cudaMalloc(&d_fn, sizeof(double) * (size_t)npairs));
+    DevBuf<SRC> src_buf;                       // cached blocks, released on every return path
+    DevBuf<double> fn_buf;
+    if (!src_buf.alloc(count) || !fn_buf.alloc((size_t)npairs)) return -1;
+    SRC *d_src = src_buf.p;
+    double *d_fn = fn_buf.p;
     DCA_CUDA(cudaMemcpy(d_src, h_src, sizeof(SRC) * count, cudaMemcpyHostToDevice));
     const int qm1 = q - 1;
     const size_t smem = sizeof(double) * FN_WARPS * (size_t)(qm1 * qm1 + 2 * qm1);
@@ -102,7 +103,6 @@ static int fn_apc_impl(const SRC *h_src, size_t count, int L, int q, int is_matr
                d_src, L, q, is_matrix, (long)L * (q - 1), d_fn);
     DCA_CUDA(cudaGetLastError());
     DCA_CUDA(cudaMemcpy(fn, d_fn, sizeof(double) * (size_t)npairs, cudaMemcpyDeviceToHost));
-    cudaFree(d_src); cudaFree(d_fn);
     if (fn_apc) apc_host(fn, L, fn_apc);
     return 0;
 }
@@ -193,12 +193,13 @@ static int di_impl(const SRC *h_src, size_t count, const double *h_reg_fi, int L
     if (require_device() != 0) return -1;
     if (L < 2 || q < 2 || q > 32) { set_error("direct_info: bad shape L=%d q=%d", L, q); return -1; }
     const long npairs = (long)L * (L - 1) / 2;
-    SRC *d_src = nullptr;
-    double *d_rfi = nullptr, *d_di = nullptr, *d_fields = nullptr;
-    DCA_CUDA(cudaMalloc(&d_src, sizeof(SRC) * count));
-    DCA_CUDA(cudaMalloc(&d_rfi, sizeof(double) * (size_t)L * q));
-    DCA_CUDA(cudaMalloc(&d_di, sizeof(double) * (size_t)npairs));
-    if (fields) DCA_CUDA(cudaMalloc(&d_fields, sizeof(double) * (size_t)npairs * 2 * q));
+    DevBuf<SRC> src_buf;                       // cached blocks, released on every return path
+    DevBuf<double> rfi_buf, di_buf, fields_buf;
+    if (!src_buf.alloc(count) || !rfi_buf.alloc((size_t)L * q) || !di_buf.alloc((size_t)npairs) ||
+        (fields && !fields_buf.alloc((size_t)npairs * 2 * q)))
+        return -1;
+    SRC *d_src = src_buf.p;
+    double *d_rfi = rfi_buf.p, *d_di = di_buf.p, *d_fields = fields_buf.p;
     DCA_CUDA(cudaMemcpy(d_src, h_src, sizeof(SRC) * count, cudaMemcpyHostToDevice));
     DCA_CUDA(cudaMemcpy(d_rfi, h_reg_fi, sizeof(double) * (size_t)L * q, cudaMemcpyHostToDevice));
     const size_t smem = sizeof(double) * DI_WARPS * (size_t)(q * q + 2 * q);
@@ -207,7 +208,6 @@ static int di_impl(const SRC *h_src, size_t count, const double *h_reg_fi, int L
     DCA_CUDA(cudaGetLastError());
     DCA_CUDA(cudaMemcpy(di, d_di, sizeof(double) * (size_t)npairs, cudaMemcpyDeviceToHost));
     if (fields) DCA_CUDA(cudaMemcpy(fields, d_fields, sizeof(double) * (size_t)npairs * 2 * q, cudaMemcpyDeviceToHost));
-    cudaFree(d_src); cudaFree(d_rfi); cudaFree(d_di); cudaFree(d_fields);
     return 0;
 }
 

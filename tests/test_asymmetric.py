@@ -175,3 +175,35 @@ def test_asym_driver_and_class(port, tmp_path):
     with pytest.raises(Exception):
         PlmDCA(path, "protein", estimator="per-site")
     lib().set_estimator(None)
+
+
+@pytest.mark.gpu
+def test_asym_gradient_at_bench_size_vs_the_reference_port(port):
+    """C2 size (N=5000, L=150, q=21): at a symmetric point the data gradient of the conditionals of a site
+    range R, scattered into the reference layout -- J_ij(a,b) gets [i in R] D[(j,b),(i,a)] + [j in R] D[(i,a),(j,b)]
+    -- is what the reference's own gradient restricted to those sites computes (plmdca_numerics.cpp:488-602;
+    the C port is bit-exact against it and linear in sites)."""
+    from pydca_b200.synthetic import synthetic_msa
+    N, L, q = 5000, 150, 21
+    msa = synthetic_msa(N, L, q)
+    w = port.plm_weights(port.reweight_counts(msa, 0.8))
+    lam = 0.2 * (L - 1)
+    rng = np.random.default_rng(8)
+    nP = L * q + L * (L - 1) // 2 * q * q
+    x = (port.plm_init(msa, w, q) + rng.normal(0, 0.05, nP)).astype(np.float32)
+    h, W = A.from_reference_vector(x, L, q)
+    _, g_reg = port.plm_gradient(msa, w, q, lam, lam, x, sites=(0, 0))
+    for lo, hi in ((0, 19), (70, 75), (131, 150)):
+        obj = lib().PlmObjective(msa, w, q, lam, lam, sites=(lo, hi), asymmetric=True)
+        fx, g = obj.eval(obj.asym_join(h[lo:hi], W[:, lo * q:hi * q]))
+        g_h, g_W = obj.asym_split(g)
+        obj.close()
+        D = np.zeros((L * q, L * q))
+        D[:, lo * q:hi * q] = g_W.astype(np.float64) - lam * W[:, lo * q:hi * q]      # data part of my columns
+        got = A.symmetrise(np.zeros(L * q), D, L, q)[L * q:] * 2.0                     # the two halves added
+        _, g_port = port.plm_gradient(msa, w, q, lam, lam, x, sites=(lo, hi))
+        want = (g_port.astype(np.float64) - g_reg)[L * q:]
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+        want_h = (g_port.astype(np.float64) - g_reg)[lo * q:hi * q]
+        got_h = g_h.astype(np.float64).ravel() - 2.0 * lam * h[lo:hi].ravel()
+        assert np.abs(got_h - want_h).max() <= 1e-5 * max(np.abs(want_h).max(), 1e-30)
