@@ -44,7 +44,15 @@ mf_site_buckets_kernel(const uint8_t *__restrict__ msa, long N, int L, unsigned 
     if (i >= site_hi) return;
     if (lane <= Q) cnt[wib][lane] = 0;
     __syncwarp();
-    for (long n = lane; n < N; n += 32) atomicAdd(&cnt[wib][msa[n * L + i]], 1u);
+    // one warp walks N rows with a stride of L bytes: the loop is bound by the latency of its loads (two warps
+    // per SM), so eight of them are kept in flight per lane
+    for (long n0 = lane; n0 < N; n0 += 32 * 8) {
+        unsigned r8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const long n = n0 + 32 * u; r8[u] = (n < N) ? msa[n * L + i] : (unsigned)Q; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (r8[u] < (unsigned)Q) atomicAdd(&cnt[wib][r8[u]], 1u);
+    }
     __syncwarp();
     if (lane == 0) {
         unsigned run = 0;
@@ -53,18 +61,25 @@ mf_site_buckets_kernel(const uint8_t *__restrict__ msa, long N, int L, unsigned 
     }
     __syncwarp();
     const unsigned lt = (1u << lane) - 1u;
-    for (long n0 = 0; n0 < N; n0 += 32) {
-        const long n = n0 + lane;
-        const bool valid = n < N;
-        const unsigned r = valid ? msa[n * L + i] : (unsigned)Q;
-        const unsigned peers = __match_any_sync(0xffffffffu, r);
-        const unsigned base = cnt[wib][r];
-        __syncwarp();
-        if (valid) {
-            rows[(size_t)i * N + base + __popc(peers & lt)] = (unsigned)n;
-            if ((peers & lt) == 0u) cnt[wib][r] = base + __popc(peers);     // lowest lane of the group
+    for (long nb = 0; nb < N; nb += 32 * 8) {
+        unsigned r8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const long n = nb + 32 * u + lane; r8[u] = (n < N) ? msa[n * L + i] : (unsigned)Q; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long n = nb + 32 * u + lane;
+            if (nb + 32 * u >= N) break;                                     // warp-uniform
+            const bool valid = n < N;
+            const unsigned r = r8[u];
+            const unsigned peers = __match_any_sync(0xffffffffu, r);
+            const unsigned base = cnt[wib][r];
+            __syncwarp();
+            if (valid) {
+                rows[(size_t)i * N + base + __popc(peers & lt)] = (unsigned)n;
+                if ((peers & lt) == 0u) cnt[wib][r] = base + __popc(peers);     // lowest lane of the group
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
