@@ -49,6 +49,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -121,6 +122,12 @@ struct PlmProblem {
     // W layout, restricted to my columns:  x = [ h (ld floats: column (i - lo)*q + a) | W (Lq rows x ld) ],
     // so the logits kernel reads x through a tensor map and the gradient is the scatter's G plus the
     // regulariser: no unpack, no transposing assemble, no exchange between GPUs.
+    // ---- similarity-sorted layout (single-GPU joint objective): rows of S / Rz and the columns of msaTs are in an
+    // order that puts similar sequences next to each other, so that the logits kernel finds many groups of four
+    // rows with one residue at a site (one shared-memory row instead of four; see plm_logits_kernel)
+    bool sorted = false, want_sorted = false;
+    int *d_rowidx = nullptr;          // sorted row of sequence n (the carry scan runs in file order)
+    uint8_t *d_msaTs = nullptr;       // msaT in sorted order
     bool asym = false;
     int ncol = 0;            // (site_hi - site_lo) * q valid columns (ld = padded to 128)
     int fin_rows = 8;        // rows of x per finish CTA
@@ -139,6 +146,71 @@ __global__ void transpose_msa_kernel(const uint8_t *__restrict__ msa, long N, in
     const int j = (int)(idx / Npad);
     const long n = idx - (long)j * Npad;
     msaT[idx] = (n < N) ? msa[n * L + j] : (uint8_t)0;
+}
+
+// ---- similarity-sorted layout ----------------------------------------------------------------------------------
+// Sequences within the reweighting threshold of each other share most of their residues.  One pass groups them:
+// every 16th sequence of the file is a leader, each sequence joins the leader it is most identical to, and the rows
+// are sorted by leader (file order inside a leader's run).  Nothing downstream depends on the quality of the
+// grouping for correctness -- the logits kernel tests every group of four rows for equality itself.
+// thread = one sequence; leaders are staged through shared memory 8 at a time as packed words
+constexpr int NL_TILE = 8;
+__global__ void __launch_bounds__(128)
+nearest_leader_kernel(const uint8_t *__restrict__ msa, long N, int L, int nleaders, int *__restrict__ best_leader)
+{
+    extern __shared__ uint32_t lead[];                  // [NL_TILE][Lw]
+    const int Lw = (L + 3) / 4;
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint8_t *row = msa + (size_t)min(n, N - 1) * L;
+    int best = 0, best_id = -1;
+    for (int l0 = 0; l0 < nleaders; l0 += NL_TILE) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < NL_TILE * Lw; t += blockDim.x) {
+            const int k = t / Lw, wdx = t - k * Lw;
+            uint32_t v = 0xffffffffu;                   // a leader that does not exist matches nothing
+            if (l0 + k < nleaders) {
+                const uint8_t *lr = msa + (size_t)((long)(l0 + k) * 16) * L;
+                v = 0;
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 4 * wdx + e;
+                    v |= (uint32_t)(c < L ? lr[c] : 0xffu) << (8 * e);
+                }
+            }
+            lead[t] = v;
+        }
+        __syncthreads();
+        int ident[NL_TILE];
+#pragma unroll
+        for (int k = 0; k < NL_TILE; ++k) ident[k] = 0;
+        for (int wdx = 0; wdx < Lw; ++wdx) {
+            uint32_t a = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = 4 * wdx + e;
+                a |= (uint32_t)(c < L ? row[c] : 0xfeu) << (8 * e);     // padding: 0xfe here, 0xff in the leaders
+            }
+#pragma unroll
+            for (int k = 0; k < NL_TILE; ++k) {
+                const uint32_t x = a ^ lead[k * Lw + wdx];
+                ident[k] += 4 - __popc((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u);   // bytes of x that are 0
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NL_TILE; ++k)
+            if (l0 + k < nleaders && ident[k] > best_id) { best_id = ident[k]; best = l0 + k; }
+    }
+    if (n < N) best_leader[n] = best;
+}
+
+// msaTs[j][k] = residue of the sequence in sorted row k at site j (rows beyond N: 0)
+__global__ void sorted_transpose_kernel(const uint8_t *__restrict__ msa, const int *__restrict__ order, long N, int L,
+                                        long Npad, uint8_t *__restrict__ msaTs)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)L * Npad) return;
+    const int j = (int)(idx / Npad);
+    const long k = idx - (long)j * Npad;
+    msaTs[idx] = (k < N) ? msa[(size_t)order[k] * L + j] : (uint8_t)0;
 }
 
 // one thread per (site, chunk): bucket the chunk's local indices by residue
@@ -229,8 +301,9 @@ template <int Q, int TC>
 __global__ void __launch_bounds__(LG_THREADS, (TC == 128) ? 2 : 3)
 plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmM,
                   int ld, long N, int L, const float *__restrict__ xf, int col_lo, int col_hi,
-                  float *__restrict__ S, int col_tile0, XrWait wt)
-{   // wt: owner-sharded mode only -- wait until every rank's unpack_push has signalled (W complete)
+                  float *__restrict__ S, int col_tile0, XrWait wt, int quad)
+{   // quad: use the equal-residues fast path for groups of four rows (reassociates the sums: off in the
+    // reference-arithmetic mode, which keeps the order of every addition)   // wt: owner-sharded mode only -- wait until every rank's unpack_push has signalled (W complete)
     // xf[c - col_lo] = field of column c for col_lo <= c < col_hi (the columns this GPU owns)
     // TC = columns per CTA: 128 (lane = float4) or 64 (lane = float2).  The narrow variant moves
     // the same shared-memory bytes per add; it exists for small grids (multi-GPU shards), where
@@ -257,6 +330,11 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     xr_wait_all(wt);
 
     float acc[16][VEC];
+    float gacc[4][VEC];              // per group of four rows: what all four have in common (VEC == 4 only)
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) gacc[g4][v] = 0.f;
     {
         const int c = col0 + VEC * lane;
 #pragma unroll
@@ -292,14 +370,31 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const float *Wj = Wb + jj * Q * TC;
             const unsigned rr[4] = {r16.x, r16.y, r16.z, r16.w};
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const unsigned b = (rr[t >> 2] >> (8 * (t & 3))) & 0xffu;
+            for (int g4 = 0; g4 < 4; ++g4) {
+                const unsigned word = rr[g4];                       // the residues of rows 4 g4 .. 4 g4 + 3
                 if constexpr (VEC == 4) {
-                    const float4 v = *reinterpret_cast<const float4 *>(Wj + b * TC);
-                    acc[t][0] += v.x; acc[t][1] += v.y; acc[t][2] += v.z; acc[t][3] += v.w;
+                    // four rows with one residue (common on the similarity-sorted layout): ONE shared-memory row
+                    // into the group's accumulator instead of four -- the kernel is bound by those loads.  The
+                    // test is warp-uniform (lanes are columns).
+                    if (quad && word == __funnelshift_r(word, word, 8)) {
+                        const float4 v = *reinterpret_cast<const float4 *>(Wj + (word & 0xffu) * TC);
+                        gacc[g4][0] += v.x; gacc[g4][1] += v.y; gacc[g4][2] += v.z; gacc[g4][3] += v.w;
+                    } else {
+#pragma unroll
+                        for (int t4 = 0; t4 < 4; ++t4) {
+                            const unsigned b = (word >> (8 * t4)) & 0xffu;
+                            const float4 v = *reinterpret_cast<const float4 *>(Wj + b * TC);
+                            acc[4 * g4 + t4][0] += v.x; acc[4 * g4 + t4][1] += v.y;
+                            acc[4 * g4 + t4][2] += v.z; acc[4 * g4 + t4][3] += v.w;
+                        }
+                    }
                 } else {
-                    const float2 v = *reinterpret_cast<const float2 *>(Wj + b * TC);
-                    acc[t][0] += v.x; acc[t][1] += v.y;
+#pragma unroll
+                    for (int t4 = 0; t4 < 4; ++t4) {
+                        const unsigned b = (word >> (8 * t4)) & 0xffu;
+                        const float2 v = *reinterpret_cast<const float2 *>(Wj + b * TC);
+                        acc[4 * g4 + t4][0] += v.x; acc[4 * g4 + t4][1] += v.y;
+                    }
                 }
             }
         }
@@ -315,7 +410,9 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const long n = n0 + warp * 16 + t;
         if (n < N) {
             float *dst = S + (size_t)n * ld + col0 + VEC * lane;
-            if constexpr (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+            if constexpr (VEC == 4)
+                *reinterpret_cast<float4 *>(dst) = make_float4(acc[t][0] + gacc[t >> 2][0], acc[t][1] + gacc[t >> 2][1],
+                                                                acc[t][2] + gacc[t >> 2][2], acc[t][3] + gacc[t >> 2][3]);
             else *reinterpret_cast<float2 *>(dst) = make_float2(acc[t][0], acc[t][1]);
         }
     }
@@ -332,8 +429,9 @@ __global__ void __launch_bounds__(128)
 plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, const uint8_t *__restrict__ msa,
                    const float *__restrict__ w, long N, int L, int site_lo, int site_hi,
                    int chunk, int warm, int carry, double *__restrict__ fxpart, double *__restrict__ fxsite,
-                   int col_shift)
-{   // fxsite (may be null): [scan chunk][L] per-site partials of fx, for the reference-order sum of seqsum.cu
+                   int col_shift, const int *__restrict__ rowidx)
+{   // rowidx (may be null): row of S / Rz that belongs to sequence n (similarity-sorted layout); the chain itself
+    // always runs in file order   // fxsite (may be null): [scan chunk][L] per-site partials of fx, for the reference-order sum of seqsum.cu
     // col_shift: column of S / Rz that holds state 0 of site 0 is -col_shift (asymmetric mode keeps only
     // its own sites' columns: col_shift = site_lo * Q; 0 otherwise)
     __shared__ float sbuf[4][32 * Q];
@@ -365,7 +463,7 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
 #pragma unroll
         for (int t = 0; t < Q; ++t) {
             const int idx = lane + 32 * t;
-            nxt[u][t] = (nn < nend && idx < ncols) ? S[(size_t)nn * ld + cbase + idx] : 0.f;
+            nxt[u][t] = (nn < nend && idx < ncols) ? S[(size_t)(rowidx ? rowidx[nn] : nn) * ld + cbase + idx] : 0.f;
         }
     }
     for (long n0 = nstart; n0 < nend; n0 += SM_PF) {
@@ -376,10 +474,11 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
 #pragma unroll
             for (int t = 0; t < Q; ++t) buf[lane + 32 * t] = nxt[u][t];
             if (n + SM_PF < nend) {
+                const size_t rn = (size_t)(rowidx ? rowidx[n + SM_PF] : n + SM_PF) * ld + cbase;
 #pragma unroll
                 for (int t = 0; t < Q; ++t) {
                     const int idx = lane + 32 * t;
-                    nxt[u][t] = (idx < ncols) ? S[(size_t)(n + SM_PF) * ld + cbase + idx] : 0.f;
+                    nxt[u][t] = (idx < ncols) ? S[rn + idx] : 0.f;
                 }
             }
             __syncwarp();
@@ -408,10 +507,11 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
                     for (int a = 0; a < Q; ++a) buf[lane * Q + a] = wn * p[a] - ((a == r) ? wn : 0.f);
                 }
                 __syncwarp();
+                const size_t ro = (size_t)(rowidx ? rowidx[n] : n) * ld + cbase;
 #pragma unroll
                 for (int t = 0; t < Q; ++t) {
                     const int idx = lane + 32 * t;
-                    if (idx < ncols) Rz[(size_t)n * ld + cbase + idx] = buf[idx];
+                    if (idx < ncols) Rz[ro + idx] = buf[idx];
                 }
             }
             __syncwarp();
@@ -1022,21 +1122,65 @@ plm_init_fields_kernel(const uint8_t *__restrict__ msaT, const float *__restrict
 }
 
 // ------------------------------------------------------------------------------
+// (re)build everything that depends on the order of the rows of S / Rz: the transposed alignment the logits kernel
+// stages, the softmax's row table, the scatter's perm records and the tensor map over the alignment.
+// use_sorted = false: file order (reference-arithmetic mode, sharded and asymmetric objectives).
+template <int Q>
+static int plm_layout_t(PlmProblem *p, bool use_sorted)
+{
+    cudaStream_t st = p->stream;
+    const long N = p->N, Npad = p->Npad;
+    const int L = p->L;
+    {   // file-order transposed alignment: the initial point accumulates in file order
+        const long total = (long)L * Npad;
+        DCA_LAUNCH(transpose_msa_kernel, (unsigned)ceil_div<long>(total, 256), 256, 0, st, p->d_msa, N, L, Npad, p->d_msaT);
+    }
+    p->sorted = false;
+    if (use_sorted && p->d_msaTs && p->d_rowidx) {
+        const int nleaders = (int)ceil_div<long>(N, 16);
+        DevBuf<int> d_best, d_order;
+        if (!d_best.alloc((size_t)N) || !d_order.alloc((size_t)N)) return -1;
+        const size_t smem = sizeof(uint32_t) * NL_TILE * ((L + 3) / 4);
+        DCA_LAUNCH(nearest_leader_kernel, (unsigned)ceil_div<long>(N, 128), 128, smem, st, p->d_msa, N, L, nleaders, d_best.p);
+        std::vector<int> best((size_t)N), order((size_t)N), rowidx((size_t)N);
+        DCA_CUDA(cudaMemcpyAsync(best.data(), d_best.p, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
+        DCA_CUDA(cudaStreamSynchronize(st));
+        {   // counting sort by leader, file order inside a leader's run
+            std::vector<int> start((size_t)nleaders + 1, 0);
+            for (long n = 0; n < N; ++n) ++start[(size_t)best[(size_t)n] + 1];
+            for (int k = 0; k < nleaders; ++k) start[(size_t)k + 1] += start[(size_t)k];
+            for (long n = 0; n < N; ++n) {
+                const int k = start[(size_t)best[(size_t)n]]++;
+                order[(size_t)k] = (int)n;
+                rowidx[(size_t)n] = k;
+            }
+        }
+        DCA_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
+        DCA_CUDA(cudaMemcpyAsync(p->d_rowidx, rowidx.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
+        const long total = (long)L * Npad;
+        DCA_LAUNCH(sorted_transpose_kernel, (unsigned)ceil_div<long>(total, 256), 256, 0, st, p->d_msa, d_order.p, N, L, Npad,
+                   p->d_msaTs);
+        DCA_CUDA(cudaStreamSynchronize(st));          // the host vectors and the scratch blocks go out of scope
+        p->sorted = true;
+    }
+    const uint8_t *mT = p->sorted ? p->d_msaTs : p->d_msaT;
+    {
+        const long total = (long)L * p->nchunk;
+        DCA_CUDA(cudaMemsetAsync(p->d_perm, 0, (size_t)p->site_tiles * p->sites_per_tile * p->nchunk * PERM_REC, st));
+        DCA_LAUNCH((build_perm_kernel<Q>), (unsigned)ceil_div<long>(total, 128), 128, 0, st,
+                   mT, N, Npad, L, p->nchunk, p->sites_per_tile, p->d_perm);
+    }
+    if (make_tensor_map_2d(&p->tmM, 1, mT, (unsigned long long)Npad, (unsigned long long)L, (unsigned long long)Npad, LG_TN,
+                           (unsigned)LgCfg<Q>::JB) != 0)
+        return -1;
+    DCA_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <int Q>
 static int plm_setup_t(PlmProblem *p)
 {
-    cudaStream_t st = p->stream;
-    {
-        const long total = (long)p->L * p->Npad;
-        DCA_LAUNCH(transpose_msa_kernel, (unsigned)ceil_div<long>(total, 256), 256, 0, st,
-                   p->d_msa, p->N, p->L, p->Npad, p->d_msaT);
-    }
-    {
-        const long total = (long)p->L * p->nchunk;
-        DCA_CUDA(cudaMemsetAsync(p->d_perm, 0, (size_t)p->site_tiles * p->sites_per_tile * p->nchunk * PERM_REC, st));
-        DCA_LAUNCH((build_perm_kernel<Q>), (unsigned)ceil_div<long>(total, 128), 128, 0, st,
-                   p->d_msaT, p->N, p->Npad, p->L, p->nchunk, p->sites_per_tile, p->d_perm);
-    }
+    if (plm_layout_t<Q>(p, p->want_sorted) != 0) return -1;
     const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN + 64 + 1024;
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
     DCA_CUDA(cudaFuncSetAttribute((plm_logits_kernel<Q, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
@@ -1090,18 +1234,18 @@ static int plm_eval_asym_t(PlmProblem *p, const float *d_x, float *d_g, const fl
     const XrWait wt{nullptr, nullptr, 0, 0u};
     if (p->lg_tc == 128)
         DCA_LAUNCH((plm_logits_kernel<Q, 128>), gridA, LG_THREADS, smemA, st,
-                   *tm, p->tmM, ld, p->N, L, d_x, 0, p->ncol, p->d_S, 0, wt);
+                   *tm, p->tmM, ld, p->N, L, d_x, 0, p->ncol, p->d_S, 0, wt, 1);
     else
         DCA_LAUNCH((plm_logits_kernel<Q, 64>), gridA, LG_THREADS, smemA, st,
-                   *tm, p->tmM, ld, p->N, L, d_x, 0, p->ncol, p->d_S, 0, wt);
+                   *tm, p->tmM, ld, p->N, L, d_x, 0, p->ncol, p->d_S, 0, wt, 1);
     PLM_MARK();
     dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
     if ((long)gridB.x * gridB.y > 2L * sm_count())
         DCA_LAUNCH((plm_softmax_kernel<Q, 1>), gridB, 128, 0, st, p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, (double *)nullptr, lo * Q);
+                   p->chunk, p->warm, p->carry, p->d_fxpart, (double *)nullptr, lo * Q, (const int *)nullptr);
     else
         DCA_LAUNCH((plm_softmax_kernel<Q, 4>), gridB, 128, 0, st, p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, (double *)nullptr, lo * Q);
+                   p->chunk, p->warm, p->carry, p->d_fxpart, (double *)nullptr, lo * Q, (const int *)nullptr);
     PLM_MARK();
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
     const size_t gstride = (size_t)p->Lq * ld;
@@ -1156,10 +1300,10 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
         wt = XrWait{reinterpret_cast<const unsigned *>(p->arena + p->lay.off_flags), p->d_err, p->peers.world, p->epoch};
     if (p->lg_tc == 128)
         DCA_LAUNCH((plm_logits_kernel<Q, 128>), gridA, LG_THREADS, smemA, st,
-                   p->tmW, p->tmM, ld, p->N, L, d_x, col_lo, col_hi, p->d_S, p->lg_tile0, wt);
+                   p->tmW, p->tmM, ld, p->N, L, d_x, col_lo, col_hi, p->d_S, p->lg_tile0, wt, p->fidelity ? 0 : 1);
     else
         DCA_LAUNCH((plm_logits_kernel<Q, 64>), gridA, LG_THREADS, smemA, st,
-                   p->tmW, p->tmM, ld, p->N, L, d_x, col_lo, col_hi, p->d_S, p->lg_tile0, wt);
+                   p->tmW, p->tmM, ld, p->N, L, d_x, col_lo, col_hi, p->d_S, p->lg_tile0, wt, p->fidelity ? 0 : 1);
     PLM_MARK();
 
     dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
@@ -1167,11 +1311,11 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
     if ((long)gridB.x * gridB.y > 2L * sm_count())
         DCA_LAUNCH((plm_softmax_kernel<Q, 1>), gridB, 128, 0, st,
                    p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift);
+                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift, p->sorted ? p->d_rowidx : (const int *)nullptr);
     else
         DCA_LAUNCH((plm_softmax_kernel<Q, 4>), gridB, 128, 0, st,
                    p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift);
+                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift, p->sorted ? p->d_rowidx : (const int *)nullptr);
     PLM_MARK();
 
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
@@ -1257,6 +1401,7 @@ static void plm_free(PlmProblem *p)
     if (!p) return;
     if (p->stream) cudaStreamSynchronize(p->stream);
     dev_free(p->d_msa); dev_free(p->d_msaT); dev_free(p->d_perm); dev_free(p->d_w);
+    dev_free(p->d_msaTs); dev_free(p->d_rowidx);
     if (!p->sharded) dev_free(p->d_W);
     dev_free(p->d_G); dev_free(p->d_S); dev_free(p->d_Rz); dev_free(p->d_fxpart);
     dev_free(p->d_fxsite); dev_free(p->d_red); dev_free(p->d_scal); dev_free(p->d_ticket); dev_free(p->d_scal_loc);
@@ -1331,7 +1476,10 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
         long best = -1;
         for (int tc : {128, 64}) {
             const int t0 = col_lo / tc, nt = ceil_div(col_hi, tc) - t0;
-            const long cost = ceil_div<long>((long)nt * seq_tiles, sms) * tc;
+            long cost = ceil_div<long>((long)nt * seq_tiles, sms) * tc;
+            // grids of several waves: the wave model says little (the last partial wave spreads one CTA per SM), the
+            // 64-column kernel is ~7 % slower per add and has no equal-residue fast path: only small grids take it
+            if (tc == 64 && (long)ceil_div(col_hi, 128) * seq_tiles >= 4L * sms) cost = best + 1;
             if (best < 0 || cost < best) { best = cost; p->lg_tc = tc; p->lg_tile0 = t0; p->lg_tiles = nt; }
         }
         if (const char *e = getenv("DCA_B200_LOGITS_TC")) {        // measurement override
@@ -1422,6 +1570,14 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     PLM_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     PLM_ALLOC(p->d_msa, (size_t)N * L);
     PLM_ALLOC(p->d_msaT, (size_t)L * p->Npad);
+    {   // similarity-sorted layout: single-GPU joint objective with 128-column logits CTAs (the fast path of the kernel)
+        const char *e = getenv("DCA_B200_LAYOUT");           // file | sorted (default)
+        p->want_sorted = !sharded && !asym && p->lg_tc == 128 && N >= 256 && !(e && strcmp(e, "file") == 0);
+        if (p->want_sorted) {
+            PLM_ALLOC(p->d_msaTs, (size_t)L * p->Npad);
+            PLM_ALLOC(p->d_rowidx, sizeof(int) * (size_t)N);
+        }
+    }
     PLM_ALLOC(p->d_perm, (size_t)p->site_tiles * p->sites_per_tile * p->nchunk * PERM_REC);
     PLM_ALLOC(p->d_w, sizeof(float) * (size_t)N);
     if (sharded) {
@@ -1602,6 +1758,13 @@ int plm_set_fidelity(PlmProblem *p, int on)
 {
     if (on && p->sharded) { set_error("plm: the reference-arithmetic mode runs on one GPU (sequential sums span the whole vector)"); return -1; }
     if (on && p->asym) { set_error("plm: the reference-arithmetic mode reproduces the reference's joint fit; the asymmetric estimator has no reference"); return -1; }
+    if (on && p->sorted) {
+        // the reference-arithmetic fit reproduces the reference's trajectory: keep the order of the sums inside the
+        // scatter (rows of a chunk in file order), i.e. the file-order layout
+        p->want_sorted = false;
+        if (((p->q == 21) ? plm_layout_t<21>(p, false) : plm_layout_t<5>(p, false)) != 0) return -1;
+        DCA_CUDA(cudaStreamSynchronize(p->stream));
+    }
     if (on && !p->d_fxsite) {
         const size_t count = (size_t)(p->N / 8 + 1) * p->L;          // chunk >= 8
         if (!dev_alloc_t(&p->d_fxsite, count)) return -1;

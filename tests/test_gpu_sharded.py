@@ -87,7 +87,9 @@ def test_sharded_eval_matches_single_gpu_and_oracle(port, N, L, q, bounds):
         fxs = [o[0] for o in outs]
         assert all(f == fxs[0] for f in fxs), "ranks disagree on fx bits"
         g = scatter_full_vector([o[1] for o in outs], layouts, objs[0].P)
-        assert abs(fxs[0] - fx1) <= 1e-9 * abs(fx1)
+        # (the single-GPU objective may run the 128-column logits kernel with its equal-residue fast path where a
+        # shard runs the 64-column one: float32 sums in a different association, not bit-identical any more)
+        assert abs(fxs[0] - fx1) <= 2e-7 * abs(fx1)
         assert relmax(g, g1) <= 2e-6
     f64, g64 = port.plm_gradient_f64(msa, w, q, lam, lam, x)
     assert abs(fxs[0] - f64) <= 1e-5 * abs(f64) and relmax(g, g64) <= 1e-5
