@@ -424,13 +424,13 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 // Logits are read from S, residuals written to a SEPARATE buffer Rz: a chain's warm-up rows are
 // the rows other chains emit, so writing the residuals in place (the first version did) is a race
 // that only co-residency of all CTAs hid -- grids of more than one wave read residuals as logits.
-template <int Q, int SM_PF>
+template <int Q, int SM_PF, bool SORTED>
 __global__ void __launch_bounds__(128)
 plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, const uint8_t *__restrict__ msa,
                    const float *__restrict__ w, long N, int L, int site_lo, int site_hi,
                    int chunk, int warm, int carry, double *__restrict__ fxpart, double *__restrict__ fxsite,
                    int col_shift, const int *__restrict__ rowidx)
-{   // rowidx (may be null): row of S / Rz that belongs to sequence n (similarity-sorted layout); the chain itself
+{   // SORTED: rowidx[n] = row of S / Rz that belongs to sequence n (similarity-sorted layout); the chain itself
     // always runs in file order   // fxsite (may be null): [scan chunk][L] per-site partials of fx, for the reference-order sum of seqsum.cu
     // col_shift: column of S / Rz that holds state 0 of site 0 is -col_shift (asymmetric mode keeps only
     // its own sites' columns: col_shift = site_lo * Q; 0 otherwise)
@@ -463,7 +463,7 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
 #pragma unroll
         for (int t = 0; t < Q; ++t) {
             const int idx = lane + 32 * t;
-            nxt[u][t] = (nn < nend && idx < ncols) ? S[(size_t)(rowidx ? rowidx[nn] : nn) * ld + cbase + idx] : 0.f;
+            nxt[u][t] = (nn < nend && idx < ncols) ? S[(size_t)(SORTED ? rowidx[nn] : nn) * ld + cbase + idx] : 0.f;
         }
     }
     for (long n0 = nstart; n0 < nend; n0 += SM_PF) {
@@ -474,7 +474,7 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
 #pragma unroll
             for (int t = 0; t < Q; ++t) buf[lane + 32 * t] = nxt[u][t];
             if (n + SM_PF < nend) {
-                const size_t rn = (size_t)(rowidx ? rowidx[n + SM_PF] : n + SM_PF) * ld + cbase;
+                const size_t rn = (size_t)(SORTED ? rowidx[n + SM_PF] : n + SM_PF) * ld + cbase;
 #pragma unroll
                 for (int t = 0; t < Q; ++t) {
                     const int idx = lane + 32 * t;
@@ -507,7 +507,7 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
                     for (int a = 0; a < Q; ++a) buf[lane * Q + a] = wn * p[a] - ((a == r) ? wn : 0.f);
                 }
                 __syncwarp();
-                const size_t ro = (size_t)(rowidx ? rowidx[n] : n) * ld + cbase;
+                const size_t ro = (size_t)(SORTED ? rowidx[n] : n) * ld + cbase;
 #pragma unroll
                 for (int t = 0; t < Q; ++t) {
                     const int idx = lane + 32 * t;
@@ -1198,8 +1198,12 @@ static int plm_setup_t(PlmProblem *p)
         DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_assemble_owner_kernel<Q, 2>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_logits_kernel<Q, 128>)));
         DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_logits_kernel<Q, 64>)));
-        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_softmax_kernel<Q, 1>)));
-        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_softmax_kernel<Q, 4>)));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_softmax_kernel<Q, 1, false>)));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_softmax_kernel<Q, 4, false>)));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_softmax_kernel<Q, 1, true>)));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, (plm_softmax_kernel<Q, 4, true>)));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, nearest_leader_kernel));
+        DCA_CUDA(cudaFuncGetAttributes(&fa, sorted_transpose_kernel));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_scatter_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, plm_init_fields_kernel<Q>));
         DCA_CUDA(cudaFuncGetAttributes(&fa, xr_barrier_kernel));
@@ -1208,6 +1212,19 @@ static int plm_setup_t(PlmProblem *p)
     DCA_CUDA(cudaGetLastError());
     return 0;
 }
+
+// the carry scan: PF rows in flight; the sorted instantiation follows the row table
+#define SM_LAUNCH(PF, FXSITE, COLSHIFT)                                                                         \
+    do {                                                                                                        \
+        if (p->sorted)                                                                                          \
+            DCA_LAUNCH((plm_softmax_kernel<Q, PF, true>), gridB, 128, 0, st, p->d_S, p->d_Rz, ld, p->d_msa,    \
+                       p->d_w, p->N, L, lo, hi, p->chunk, p->warm, p->carry, p->d_fxpart, FXSITE, COLSHIFT,     \
+                       (const int *)p->d_rowidx);                                                               \
+        else                                                                                                    \
+            DCA_LAUNCH((plm_softmax_kernel<Q, PF, false>), gridB, 128, 0, st, p->d_S, p->d_Rz, ld, p->d_msa,   \
+                       p->d_w, p->N, L, lo, hi, p->chunk, p->warm, p->carry, p->d_fxpart, FXSITE, COLSHIFT,     \
+                       (const int *)nullptr);                                                                   \
+    } while (0)
 
 // asymmetric mode: logits straight from x (tensor map over its W part), softmax, scatter, finish
 template <int Q>
@@ -1241,11 +1258,9 @@ static int plm_eval_asym_t(PlmProblem *p, const float *d_x, float *d_g, const fl
     PLM_MARK();
     dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
     if ((long)gridB.x * gridB.y > 2L * sm_count())
-        DCA_LAUNCH((plm_softmax_kernel<Q, 1>), gridB, 128, 0, st, p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, (double *)nullptr, lo * Q, (const int *)nullptr);
+        SM_LAUNCH(1, (double *)nullptr, lo * Q);
     else
-        DCA_LAUNCH((plm_softmax_kernel<Q, 4>), gridB, 128, 0, st, p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, (double *)nullptr, lo * Q, (const int *)nullptr);
+        SM_LAUNCH(4, (double *)nullptr, lo * Q);
     PLM_MARK();
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
     const size_t gstride = (size_t)p->Lq * ld;
@@ -1309,13 +1324,9 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
     dim3 gridB(ceil_div(nsites, 32), (unsigned)ceil_div<long>(p->nscan, 4));
     const int col_shift = 0;
     if ((long)gridB.x * gridB.y > 2L * sm_count())
-        DCA_LAUNCH((plm_softmax_kernel<Q, 1>), gridB, 128, 0, st,
-                   p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift, p->sorted ? p->d_rowidx : (const int *)nullptr);
+        SM_LAUNCH(1, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift);
     else
-        DCA_LAUNCH((plm_softmax_kernel<Q, 4>), gridB, 128, 0, st,
-                   p->d_S, p->d_Rz, ld, p->d_msa, p->d_w, p->N, L, lo, hi,
-                   p->chunk, p->warm, p->carry, p->d_fxpart, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift, p->sorted ? p->d_rowidx : (const int *)nullptr);
+        SM_LAUNCH(4, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift);
     PLM_MARK();
 
     const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
@@ -1570,9 +1581,14 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     PLM_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     PLM_ALLOC(p->d_msa, (size_t)N * L);
     PLM_ALLOC(p->d_msaT, (size_t)L * p->Npad);
-    {   // similarity-sorted layout: single-GPU joint objective with 128-column logits CTAs (the fast path of the kernel)
+    {   // similarity-sorted layout: wherever the 128-column logits CTAs (the kernel with the fast path) run.  Every
+        // rank of a multi-GPU objective sorts for itself: the order only concerns its own S / Rz rows
         const char *e = getenv("DCA_B200_LAYOUT");           // file | sorted (default)
-        p->want_sorted = !sharded && !asym && p->lg_tc == 128 && N >= 256 && !(e && strcmp(e, "file") == 0);
+        // ... and where the carry scan is throughput-bound (large grids): on shard-sized grids it is bound by the latency
+        // of one row load per chain step, and the row table would put a second dependent load in front of it
+        // (measured on a 38-site shard: scan 0.051 -> 0.101 ms for 0.013 ms saved in the logits)
+        const bool big_scan = (long)ceil_div(site_hi - site_lo, 32) * ceil_div<long>(p->nscan, 4) > 2L * sm_count();
+        p->want_sorted = p->lg_tc == 128 && big_scan && N >= 256 && !(e && strcmp(e, "file") == 0);
         if (p->want_sorted) {
             PLM_ALLOC(p->d_msaTs, (size_t)L * p->Npad);
             PLM_ALLOC(p->d_rowidx, sizeof(int) * (size_t)N);
