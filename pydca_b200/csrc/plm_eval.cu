@@ -63,6 +63,7 @@ constexpr int LG_THREADS = 256;   // 2 CTAs per SM
 template <int Q> struct LgCfg { static constexpr int JB = (Q > 8) ? 4 : 16; };   // sites per stage
 
 constexpr int SC_CH = 128;        // sequences per scatter chunk
+constexpr int SC_G4 = SC_CH / 4;  // groups of four rows per chunk: their sums ride along as 32 extra tile rows
 constexpr int SC_TC = 128;
 constexpr int SC_WARPS = 16;      // one site per warp
 // perm record of one (site, chunk): 32 bytes of bucket sizes (u8[q]) followed by
@@ -128,6 +129,9 @@ struct PlmProblem {
     bool sorted = false, want_sorted = false;
     int *d_rowidx = nullptr;          // sorted row of sequence n (the carry scan runs in file order)
     uint8_t *d_msaTs = nullptr;       // msaT in sorted order
+    float *d_Rz4 = nullptr;           // [Npad / 4][ld]: sums of four consecutive sorted rows of Rz (scatter fast path)
+    CUtensorMap tmS4;                 // Rz4 as [Npad / 4][ld] f32, box 128 x 32
+    bool group4 = false;              // the perm records reference group sums where four rows share a residue
     bool asym = false;
     int ncol = 0;            // (site_hi - site_lo) * q valid columns (ld = padded to 128)
     int fin_rows = 8;        // rows of x per finish CTA
@@ -218,8 +222,9 @@ __global__ void sorted_transpose_kernel(const uint8_t *__restrict__ msa, const i
 // the sites one scatter CTA works on are one contiguous block per chunk (one bulk copy)
 template <int Q>
 __global__ void build_perm_kernel(const uint8_t *__restrict__ msaT, long N, long Npad, int L,
-                                  int nchunk, int sites_per_tile, uint8_t *__restrict__ perm)
-{
+                                  int nchunk, int sites_per_tile, uint8_t *__restrict__ perm, int group4)
+{   // group4: four consecutive rows (4g .. 4g+3) with ONE residue become a single entry that points at row
+    // SC_CH + g of the staged tile -- the sum of the four rows, which the scatter kernel loads next to them
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)L * nchunk) return;
     const int j = (int)(idx / nchunk);
@@ -231,10 +236,17 @@ __global__ void build_perm_kernel(const uint8_t *__restrict__ msaT, long N, long
     int cnt[Q], pos[Q];
 #pragma unroll
     for (int b = 0; b < Q; ++b) cnt[b] = 0;
-    for (int r = 0; r < rows; ++r) {
-        const int v = col[r];
+    auto uniform4 = [&](int r0) {
+        return group4 && r0 + 3 < rows && col[r0] == col[r0 + 1] && col[r0] == col[r0 + 2] && col[r0] == col[r0 + 3];
+    };
+    for (int r0 = 0; r0 < rows; r0 += 4) {
+        const bool u = uniform4(r0);
+        for (int r = r0; r < min(rows, r0 + 4); ++r) {
+            const int v = col[r];
+            if (u && r != r0) continue;
 #pragma unroll
-        for (int b = 0; b < Q; ++b) cnt[b] += (v == b);
+            for (int b = 0; b < Q; ++b) cnt[b] += (v == b);
+        }
     }
     int off = 0;
 #pragma unroll
@@ -243,14 +255,34 @@ __global__ void build_perm_kernel(const uint8_t *__restrict__ msaT, long N, long
         pos[b] = off;
         off += (cnt[b] + 3) & ~3;
     }
-    for (int r = 0; r < rows; ++r) {
-        const int v = col[r];
-        int where = 0;
+    for (int r0 = 0; r0 < rows; r0 += 4) {
+        const bool u = uniform4(r0);
+        for (int r = r0; r < min(rows, r0 + 4); ++r) {
+            if (u && r != r0) continue;
+            const int v = col[r];
+            int where = 0;
 #pragma unroll
-        for (int b = 0; b < Q; ++b)
-            if (v == b) { where = pos[b]; pos[b] = where + 1; }
-        reinterpret_cast<uint32_t *>(rec + PERM_CNT)[where] = (uint32_t)r * (SC_TC * 4);
+            for (int b = 0; b < Q; ++b)
+                if (v == b) { where = pos[b]; pos[b] = where + 1; }
+            const int src = u ? (SC_CH + (r0 >> 2)) : r;
+            reinterpret_cast<uint32_t *>(rec + PERM_CNT)[where] = (uint32_t)src * (SC_TC * 4);
+        }
     }
+}
+
+// Rz4[g][:] = Rz[4g][:] + Rz[4g+1][:] + Rz[4g+2][:] + Rz[4g+3][:]   (float4 per thread)
+__global__ void __launch_bounds__(256)
+rowsum4_kernel(const float *__restrict__ Rz, float *__restrict__ Rz4, long ngroups, int ld)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ld4 = ld / 4;
+    if (idx >= ngroups * ld4) return;
+    const long g = idx / ld4;
+    const int c4 = (int)(idx - g * ld4);
+    const float4 *r = reinterpret_cast<const float4 *>(Rz + (size_t)g * 4 * ld) + c4;
+    const float4 a = r[0], b = r[ld4], c = r[2 * (size_t)ld4], d = r[3 * (size_t)ld4];
+    reinterpret_cast<float4 *>(Rz4 + (size_t)g * ld)[c4] =
+        make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z), (a.w + b.w) + (c.w + d.w));
 }
 
 // ------------------------------------------------------------------------------
@@ -535,13 +567,16 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
 // chunk c+2.
 template <int Q>
 __global__ void __launch_bounds__(SC_WARPS * 32, 1)
-plm_scatter_kernel(const __grid_constant__ CUtensorMap tmS, int ld, const uint8_t *__restrict__ perm, int nchunk,
+plm_scatter_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmS4, int group4,
+                   int ld, const uint8_t *__restrict__ perm, int nchunk,
                    long N, int L, float *__restrict__ G, size_t g_split_stride,
                    int chunks_per_split, int col_tile0, int sites_per_tile)
-{
+{   // group4: the perm records also reference rows SC_CH .. SC_CH + SC_G4 - 1 of the staged tile = the sums of four
+    // consecutive rows (Rz4, a second tensor map): where four rows share a residue one load replaces four
+    constexpr int SC_ROWS = SC_CH + SC_G4;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    float *Rs = reinterpret_cast<float *>(smem_raw);                                    // [2][SC_CH][SC_TC]
-    uint8_t *recs = smem_raw + sizeof(float) * 2 * SC_CH * SC_TC;                       // [2][SC_WARPS][PERM_REC]
+    float *Rs = reinterpret_cast<float *>(smem_raw);                                    // [2][SC_ROWS][SC_TC]
+    uint8_t *recs = smem_raw + sizeof(float) * 2 * SC_ROWS * SC_TC;                     // [2][SC_WARPS][PERM_REC]
     uint64_t *bars = reinterpret_cast<uint64_t *>(recs + 2 * SC_WARPS * PERM_REC);      // full[2], empty[2]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -570,8 +605,9 @@ plm_scatter_kernel(const __grid_constant__ CUtensorMap tmS, int ld, const uint8_
     // the 128 x 128 residual tile (2-D tensor map over S) and this tile's perm records
     auto issue = [&](int buf, int c) {
         if (lane == 0) {
-            mbar_expect_tx(&bars[buf], (unsigned)(SC_CH * SC_TC * 4 + nactive * PERM_REC));
-            tma_load_2d(Rs + (size_t)buf * SC_CH * SC_TC, &tmS, col0, c * SC_CH, &bars[buf]);
+            mbar_expect_tx(&bars[buf], (unsigned)((SC_CH + (group4 ? SC_G4 : 0)) * SC_TC * 4 + nactive * PERM_REC));
+            tma_load_2d(Rs + (size_t)buf * SC_ROWS * SC_TC, &tmS, col0, c * SC_CH, &bars[buf]);
+            if (group4) tma_load_2d(Rs + ((size_t)buf * SC_ROWS + SC_CH) * SC_TC, &tmS4, col0, c * SC_G4, &bars[buf]);
             tma_bulk_g2s(recs + (size_t)buf * SC_WARPS * PERM_REC,
                          perm + (((size_t)blockIdx.y * nchunk + c) * sites_per_tile) * PERM_REC,
                          (unsigned)(nactive * PERM_REC), &bars[buf]);
@@ -589,7 +625,7 @@ plm_scatter_kernel(const __grid_constant__ CUtensorMap tmS, int ld, const uint8_
         {
             const uint8_t *rec = recs + ((size_t)buf * SC_WARPS + warp) * PERM_REC;
             const uint4 *qp = reinterpret_cast<const uint4 *>(rec + PERM_CNT);
-            const char *Rb = reinterpret_cast<const char *>(Rs + (size_t)buf * SC_CH * SC_TC + 4 * lane);
+            const char *Rb = reinterpret_cast<const char *>(Rs + (size_t)buf * SC_ROWS * SC_TC + 4 * lane);
             // bucket sizes: 32 bytes, broadcast once per chunk
             const uint4 h0 = *reinterpret_cast<const uint4 *>(rec);
             const uint4 h1 = *reinterpret_cast<const uint4 *>(rec + 16);
@@ -1167,8 +1203,9 @@ static int plm_layout_t(PlmProblem *p, bool use_sorted)
     {
         const long total = (long)L * p->nchunk;
         DCA_CUDA(cudaMemsetAsync(p->d_perm, 0, (size_t)p->site_tiles * p->sites_per_tile * p->nchunk * PERM_REC, st));
+        p->group4 = p->sorted && p->d_Rz4 != nullptr;
         DCA_LAUNCH((build_perm_kernel<Q>), (unsigned)ceil_div<long>(total, 128), 128, 0, st,
-                   mT, N, Npad, L, p->nchunk, p->sites_per_tile, p->d_perm);
+                   mT, N, Npad, L, p->nchunk, p->sites_per_tile, p->d_perm, p->group4 ? 1 : 0);
     }
     if (make_tensor_map_2d(&p->tmM, 1, mT, (unsigned long long)Npad, (unsigned long long)L, (unsigned long long)Npad, LG_TN,
                            (unsigned)LgCfg<Q>::JB) != 0)
@@ -1182,7 +1219,7 @@ static int plm_setup_t(PlmProblem *p)
 {
     if (plm_layout_t<Q>(p, p->want_sorted) != 0) return -1;
     const size_t smemA = sizeof(float) * 2 * LgCfg<Q>::JB * Q * LG_TC + 2 * LgCfg<Q>::JB * LG_TN + 64 + 1024;
-    const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
+    const size_t smemC = sizeof(float) * 2 * (SC_CH + SC_G4) * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
     DCA_CUDA(cudaFuncSetAttribute((plm_logits_kernel<Q, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     DCA_CUDA(cudaFuncSetAttribute((plm_logits_kernel<Q, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     DCA_CUDA(cudaFuncSetAttribute(plm_scatter_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
@@ -1262,11 +1299,15 @@ static int plm_eval_asym_t(PlmProblem *p, const float *d_x, float *d_g, const fl
     else
         SM_LAUNCH(4, (double *)nullptr, lo * Q);
     PLM_MARK();
-    const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
+    const size_t smemC = sizeof(float) * 2 * (SC_CH + SC_G4) * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
     const size_t gstride = (size_t)p->Lq * ld;
     dim3 gridC(p->col_tiles, p->site_tiles, p->nsplit);
+    if (p->group4)
+        DCA_LAUNCH(rowsum4_kernel, (unsigned)ceil_div<long>((p->Npad / 4) * (long)(ld / 4), 256), 256, 0, st, p->d_Rz, p->d_Rz4,
+                   p->Npad / 4, ld);
     DCA_LAUNCH((plm_scatter_kernel<Q>), gridC, SC_WARPS * 32, smemC, st,
-               p->tmS, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride, p->chunks_per_split, 0, p->sites_per_tile);
+               p->tmS, p->group4 ? p->tmS4 : p->tmS, p->group4 ? 1 : 0, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride,
+               p->chunks_per_split, 0, p->sites_per_tile);
     PLM_MARK(); PLM_MARK();                                        // (no export)
     const int nfx = (int)(gridB.x * p->nscan);
     const int row_groups = ceil_div(p->Lq, p->fin_rows), field_groups = ceil_div(ceil_div(ld, 128), ceil_div(ld, 1024));
@@ -1329,11 +1370,14 @@ static int plm_eval_t(PlmProblem *p, const float *d_x, float *d_g, const float *
         SM_LAUNCH(4, p->fidelity ? p->d_fxsite : (double *)nullptr, col_shift);
     PLM_MARK();
 
-    const size_t smemC = sizeof(float) * 2 * SC_CH * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
+    const size_t smemC = sizeof(float) * 2 * (SC_CH + SC_G4) * SC_TC + 2 * SC_WARPS * PERM_REC + 64 + 1024;
     const size_t gstride = (size_t)p->Lq * ld;
     dim3 gridC(p->col_tiles, p->site_tiles, p->nsplit);
+    if (p->group4)
+        DCA_LAUNCH(rowsum4_kernel, (unsigned)ceil_div<long>((p->Npad / 4) * (long)(ld / 4), 256), 256, 0, st, p->d_Rz, p->d_Rz4,
+                   p->Npad / 4, ld);
     DCA_LAUNCH((plm_scatter_kernel<Q>), gridC, SC_WARPS * 32, smemC, st,
-               p->tmS, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride,
+               p->tmS, p->group4 ? p->tmS4 : p->tmS, p->group4 ? 1 : 0, ld, p->d_perm, p->nchunk, p->N, L, p->d_G, gstride,
                p->chunks_per_split, p->col_tile0, p->sites_per_tile);
     PLM_MARK();
 
@@ -1412,7 +1456,7 @@ static void plm_free(PlmProblem *p)
     if (!p) return;
     if (p->stream) cudaStreamSynchronize(p->stream);
     dev_free(p->d_msa); dev_free(p->d_msaT); dev_free(p->d_perm); dev_free(p->d_w);
-    dev_free(p->d_msaTs); dev_free(p->d_rowidx);
+    dev_free(p->d_msaTs); dev_free(p->d_rowidx); dev_free(p->d_Rz4);
     if (!p->sharded) dev_free(p->d_W);
     dev_free(p->d_G); dev_free(p->d_S); dev_free(p->d_Rz); dev_free(p->d_fxpart);
     dev_free(p->d_fxsite); dev_free(p->d_red); dev_free(p->d_scal); dev_free(p->d_ticket); dev_free(p->d_scal_loc);
@@ -1592,6 +1636,12 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
         if (p->want_sorted) {
             PLM_ALLOC(p->d_msaTs, (size_t)L * p->Npad);
             PLM_ALLOC(p->d_rowidx, sizeof(int) * (size_t)N);
+            if (!(getenv("DCA_B200_GROUP4") && atoi(getenv("DCA_B200_GROUP4")) == 0)) {      // measurement switch
+                PLM_ALLOC(p->d_Rz4, sizeof(float) * (size_t)(p->Npad / 4) * p->ld);
+                PLM_TRY(cudaMemsetAsync(p->d_Rz4, 0, sizeof(float) * (size_t)(p->Npad / 4) * p->ld, p->stream));
+                if (make_tensor_map_2d(&p->tmS4, 4, p->d_Rz4, (unsigned long long)p->ld, (unsigned long long)(p->Npad / 4),
+                                       sizeof(float) * (unsigned long long)p->ld, SC_TC, SC_G4) != 0) { plm_free(p); return nullptr; }
+            }
         }
     }
     PLM_ALLOC(p->d_perm, (size_t)p->site_tiles * p->sites_per_tile * p->nchunk * PERM_REC);
