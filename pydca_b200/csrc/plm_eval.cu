@@ -1824,11 +1824,11 @@ int plm_set_fidelity(PlmProblem *p, int on)
 {
     if (on && p->sharded) { set_error("plm: the reference-arithmetic mode runs on one GPU (sequential sums span the whole vector)"); return -1; }
     if (on && p->asym) { set_error("plm: the reference-arithmetic mode reproduces the reference's joint fit; the asymmetric estimator has no reference"); return -1; }
-    if (on && p->sorted) {
+    if ((on != 0) == p->sorted && p->want_sorted) {
         // the reference-arithmetic fit reproduces the reference's trajectory: keep the order of the sums inside the
-        // scatter (rows of a chunk in file order), i.e. the file-order layout
-        p->want_sorted = false;
-        if (((p->q == 21) ? plm_layout_t<21>(p, false) : plm_layout_t<5>(p, false)) != 0) return -1;
+        // scatter (rows of a chunk in file order), i.e. the file-order layout; back to the sorted one when it is
+        // switched off again
+        if (((p->q == 21) ? plm_layout_t<21>(p, !on) : plm_layout_t<5>(p, !on)) != 0) return -1;
         DCA_CUDA(cudaStreamSynchronize(p->stream));
     }
     if (on && !p->d_fxsite) {
