@@ -362,7 +362,7 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     xr_wait_all(wt);
 
     float acc[16][VEC];
-    float gacc[4][VEC];              // per group of four rows: what all four have in common (VEC == 4 only)
+    float gacc[4][VEC];              // per group of four rows: what all four have in common
 #pragma unroll
     for (int g4 = 0; g4 < 4; ++g4)
 #pragma unroll
@@ -420,7 +420,7 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                             acc[4 * g4 + t4][2] += v.z; acc[4 * g4 + t4][3] += v.w;
                         }
                     }
-                } else {
+                } else {       // (64 columns: the fast path does not pay -- measured 0.060 -> 0.067 ms on a 19-site shard)
 #pragma unroll
                     for (int t4 = 0; t4 < 4; ++t4) {
                         const unsigned b = (word >> (8 * t4)) & 0xffu;
@@ -445,7 +445,7 @@ plm_logits_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             if constexpr (VEC == 4)
                 *reinterpret_cast<float4 *>(dst) = make_float4(acc[t][0] + gacc[t >> 2][0], acc[t][1] + gacc[t >> 2][1],
                                                                 acc[t][2] + gacc[t >> 2][2], acc[t][3] + gacc[t >> 2][3]);
-            else *reinterpret_cast<float2 *>(dst) = make_float2(acc[t][0], acc[t][1]);
+            else *reinterpret_cast<float2 *>(dst) = make_float2(acc[t][0] + gacc[t >> 2][0], acc[t][1] + gacc[t >> 2][1]);
         }
     }
 }
@@ -485,17 +485,22 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
     // times).  Large grids are issue-bound and want occupancy: SM_PF = 1 (96 registers).  Small
     // grids (multi-GPU shards) are bound by the memory round trip per step (~0.9 us x 48 steps
     // was the whole 45 us kernel): SM_PF = 4 (201 registers) hides it.
+    // SORTED: the row of step n is rowidx[n]; the indices run one ring ahead of the rows (rcur: rows held in nxt,
+    // rnxt: rows of the steps after those), so that no row load waits for its index
     float p[Q], nxt[SM_PF][Q];
+    int rcur[SM_PF], rnxt[SM_PF];
 #pragma unroll
     for (int a = 0; a < Q; ++a) p[a] = 0.f;
     double fx = 0.0;
 #pragma unroll
     for (int u = 0; u < SM_PF; ++u) {
         const long nn = nstart + u;
+        rcur[u] = SORTED ? ((nn < nend) ? rowidx[nn] : 0) : (int)nn;
+        rnxt[u] = SORTED ? ((nn + SM_PF < nend) ? rowidx[nn + SM_PF] : 0) : (int)(nn + SM_PF);
 #pragma unroll
         for (int t = 0; t < Q; ++t) {
             const int idx = lane + 32 * t;
-            nxt[u][t] = (nn < nend && idx < ncols) ? S[(size_t)(SORTED ? rowidx[nn] : nn) * ld + cbase + idx] : 0.f;
+            nxt[u][t] = (nn < nend && idx < ncols) ? S[(size_t)rcur[u] * ld + cbase + idx] : 0.f;
         }
     }
     for (long n0 = nstart; n0 < nend; n0 += SM_PF) {
@@ -505,13 +510,16 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
             if (n >= nend) break;                          // warp-uniform
 #pragma unroll
             for (int t = 0; t < Q; ++t) buf[lane + 32 * t] = nxt[u][t];
+            const int row_n = rcur[u];                     // row of this step (the residuals go there)
             if (n + SM_PF < nend) {
-                const size_t rn = (size_t)(SORTED ? rowidx[n + SM_PF] : n + SM_PF) * ld + cbase;
+                const size_t rn = (size_t)rnxt[u] * ld + cbase;
 #pragma unroll
                 for (int t = 0; t < Q; ++t) {
                     const int idx = lane + 32 * t;
                     nxt[u][t] = (idx < ncols) ? S[rn + idx] : 0.f;
                 }
+                rcur[u] = rnxt[u];
+                rnxt[u] = SORTED ? ((n + 2 * SM_PF < nend) ? rowidx[n + 2 * SM_PF] : 0) : (int)(n + 2 * SM_PF);
             }
             __syncwarp();
             float l[Q];
@@ -539,7 +547,7 @@ plm_softmax_kernel(const float *__restrict__ S, float *__restrict__ Rz, int ld, 
                     for (int a = 0; a < Q; ++a) buf[lane * Q + a] = wn * p[a] - ((a == r) ? wn : 0.f);
                 }
                 __syncwarp();
-                const size_t ro = (size_t)(SORTED ? rowidx[n] : n) * ld + cbase;
+                const size_t ro = (size_t)row_n * ld + cbase;
 #pragma unroll
                 for (int t = 0; t < Q; ++t) {
                     const int idx = lane + 32 * t;
@@ -1534,7 +1542,8 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
             long cost = ceil_div<long>((long)nt * seq_tiles, sms) * tc;
             // grids of several waves: the wave model says little (the last partial wave spreads one CTA per SM), the
             // 64-column kernel is ~7 % slower per add and has no equal-residue fast path: only small grids take it
-            if (tc == 64 && (long)ceil_div(col_hi, 128) * seq_tiles >= 4L * sms) cost = best + 1;
+            // (measured on the sorted layout, 75-site shard = 520 CTAs of 128 columns: 0.152 ms against 0.185 ms)
+            if (tc == 64 && (long)(ceil_div(col_hi, 128) - col_lo / 128) * seq_tiles >= 3L * sms) cost = best + 1;
             if (best < 0 || cost < best) { best = cost; p->lg_tc = tc; p->lg_tile0 = t0; p->lg_tiles = nt; }
         }
         if (const char *e = getenv("DCA_B200_LOGITS_TC")) {        // measurement override
@@ -1625,14 +1634,10 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     PLM_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     PLM_ALLOC(p->d_msa, (size_t)N * L);
     PLM_ALLOC(p->d_msaT, (size_t)L * p->Npad);
-    {   // similarity-sorted layout: wherever the 128-column logits CTAs (the kernel with the fast path) run.  Every
-        // rank of a multi-GPU objective sorts for itself: the order only concerns its own S / Rz rows
+    {   // similarity-sorted layout.  Every rank of a multi-GPU objective sorts for itself: the order only concerns
+        // its own S / Rz rows
         const char *e = getenv("DCA_B200_LAYOUT");           // file | sorted (default)
-        // ... and where the carry scan is throughput-bound (large grids): on shard-sized grids it is bound by the latency
-        // of one row load per chain step, and the row table would put a second dependent load in front of it
-        // (measured on a 38-site shard: scan 0.051 -> 0.101 ms for 0.013 ms saved in the logits)
-        const bool big_scan = (long)ceil_div(site_hi - site_lo, 32) * ceil_div<long>(p->nscan, 4) > 2L * sm_count();
-        p->want_sorted = p->lg_tc == 128 && big_scan && N >= 256 && !(e && strcmp(e, "file") == 0);
+        p->want_sorted = N >= 256 && !(e && strcmp(e, "file") == 0);
         if (p->want_sorted) {
             PLM_ALLOC(p->d_msaTs, (size_t)L * p->Npad);
             PLM_ALLOC(p->d_rowidx, sizeof(int) * (size_t)N);
