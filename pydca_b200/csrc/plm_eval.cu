@@ -159,13 +159,18 @@ __global__ void transpose_msa_kernel(const uint8_t *__restrict__ msa, long N, in
 // grouping for correctness -- the logits kernel tests every group of four rows for equality itself.
 // thread = one sequence; leaders are staged through shared memory 8 at a time as packed words
 constexpr int NL_TILE = 8;
+// rows classified: n * row_stride for n < nrows (row_stride 1: every sequence; 16: the leaders themselves).
+// first_at > 0: not the most identical leader but the FIRST one with at least first_at identical residues (leaders
+// classified against leaders: the first similar leader is the representative of a cluster of leaders)
 __global__ void __launch_bounds__(128)
-nearest_leader_kernel(const uint8_t *__restrict__ msa, long N, int L, int nleaders, int *__restrict__ best_leader)
+nearest_leader_kernel(const uint8_t *__restrict__ msa, long nrows, int row_stride, int L, int nleaders, int first_at,
+                      int *__restrict__ best_leader)
 {
     extern __shared__ uint32_t lead[];                  // [NL_TILE][Lw]
     const int Lw = (L + 3) / 4;
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint8_t *row = msa + (size_t)min(n, N - 1) * L;
+    const long N = nrows;
+    const uint8_t *row = msa + (size_t)(min(n, nrows - 1) * row_stride) * L;
     int best = 0, best_id = -1;
     for (int l0 = 0; l0 < nleaders; l0 += NL_TILE) {
         __syncthreads();
@@ -200,8 +205,11 @@ nearest_leader_kernel(const uint8_t *__restrict__ msa, long N, int L, int nleade
             }
         }
 #pragma unroll
-        for (int k = 0; k < NL_TILE; ++k)
-            if (l0 + k < nleaders && ident[k] > best_id) { best_id = ident[k]; best = l0 + k; }
+        for (int k = 0; k < NL_TILE; ++k) {
+            if (l0 + k >= nleaders) continue;
+            if (first_at > 0) { if (best_id < first_at && ident[k] >= first_at) { best_id = ident[k]; best = l0 + k; } }
+            else if (ident[k] > best_id) { best_id = ident[k]; best = l0 + k; }
+        }
     }
     if (n < N) best_leader[n] = best;
 }
@@ -1185,16 +1193,28 @@ static int plm_layout_t(PlmProblem *p, bool use_sorted)
         DevBuf<int> d_best, d_order;
         if (!d_best.alloc((size_t)N) || !d_order.alloc((size_t)N)) return -1;
         const size_t smem = sizeof(uint32_t) * NL_TILE * ((L + 3) / 4);
-        DCA_LAUNCH(nearest_leader_kernel, (unsigned)ceil_div<long>(N, 128), 128, smem, st, p->d_msa, N, L, nleaders, d_best.p);
-        std::vector<int> best((size_t)N), order((size_t)N), rowidx((size_t)N);
+        DevBuf<int> d_rep;
+        if (!d_rep.alloc((size_t)nleaders)) return -1;
+        DCA_LAUNCH(nearest_leader_kernel, (unsigned)ceil_div<long>(N, 128), 128, smem, st, p->d_msa, N, 1, L, nleaders, 0, d_best.p);
+        // leaders against leaders: the first leader sharing half of the residues represents a cluster of leaders, so that
+        // the runs of one true cluster end up next to each other (groups of four that straddle two runs stay similar)
+        DCA_LAUNCH(nearest_leader_kernel, (unsigned)ceil_div<long>(nleaders, 128), 128, smem, st, p->d_msa, (long)nleaders, 16, L,
+                   nleaders, (L + 1) / 2, d_rep.p);
+        std::vector<int> best((size_t)N), rep((size_t)nleaders), order((size_t)N), rowidx((size_t)N);
         DCA_CUDA(cudaMemcpyAsync(best.data(), d_best.p, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
+        DCA_CUDA(cudaMemcpyAsync(rep.data(), d_rep.p, sizeof(int) * (size_t)nleaders, cudaMemcpyDeviceToHost, st));
         DCA_CUDA(cudaStreamSynchronize(st));
-        {   // counting sort by leader, file order inside a leader's run
+        {   // rank of every leader in (representative, leader) order, then a counting sort of the sequences by that
+            // rank: file order inside a leader's run
+            std::vector<int> by_rep((size_t)nleaders), rank((size_t)nleaders);
+            for (int k = 0; k < nleaders; ++k) by_rep[(size_t)k] = k;
+            std::stable_sort(by_rep.begin(), by_rep.end(), [&](int a, int b) { return rep[(size_t)a] < rep[(size_t)b]; });
+            for (int r = 0; r < nleaders; ++r) rank[(size_t)by_rep[(size_t)r]] = r;
             std::vector<int> start((size_t)nleaders + 1, 0);
-            for (long n = 0; n < N; ++n) ++start[(size_t)best[(size_t)n] + 1];
+            for (long n = 0; n < N; ++n) ++start[(size_t)rank[(size_t)best[(size_t)n]] + 1];
             for (int k = 0; k < nleaders; ++k) start[(size_t)k + 1] += start[(size_t)k];
             for (long n = 0; n < N; ++n) {
-                const int k = start[(size_t)best[(size_t)n]]++;
+                const int k = start[(size_t)rank[(size_t)best[(size_t)n]]]++;
                 order[(size_t)k] = (int)n;
                 rowidx[(size_t)n] = k;
             }
