@@ -134,6 +134,10 @@ int dca_plm_eval_device(dca_plm *p, const float *x_dev, float *g_dev,
  * (owner-sharded handles only, else 0), assemble+finalize.  out10 = {N, L, q, ld, P, nsplit, nchunk, col_tiles, Npad, nscan}. */
 int dca_plm_eval_timed(dca_plm *p, const float *x_host, float *ms_out);
 int dca_plm_describe(const dca_plm *p, long *out10);
+/* out4 = {1 if the handle uses the similarity-sorted row layout, 1 if its scatter uses four-row group sums, the
+ * fraction of (site, group of four rows) pairs whose rows carry one residue -- what the equal-residue fast paths
+ * of the logits / scatter kernels save --, columns per logits CTA}.  Measurement only. */
+int dca_plm_layout_stats(const dca_plm *p, double *out4);
 /* measurement hook for the HBM-bound part of the path: CUDA-event ms of the two L-BFGS
  * passes of one iteration and of the trial-step kernel on n floats with `stored_pairs`
  * (1..5) history pairs: ms_out3 = {history update + inner products, direction, step}. */

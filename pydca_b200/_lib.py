@@ -120,6 +120,7 @@ def lib():
     L.dca_plm_cuda_stream.argtypes = [ctypes.c_void_p]
     L.dca_plm_cuda_stream.restype = ctypes.c_void_p
     L.dca_plm_describe.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_long)]
+    L.dca_plm_layout_stats.argtypes = [ctypes.c_void_p, _f64p]
     L.dca_last_fit.argtypes = [ctypes.POINTER(FitResult)]
     L.dca_plm_fn_apc.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
     L.dca_mf_freqs.argtypes = [_u8p, _f64p, ctypes.c_long, ctypes.c_int, ctypes.c_int, _f64p, _f64p]
@@ -378,6 +379,12 @@ class PlmObjective:
         ms = np.zeros(6, dtype=np.float32)
         check(lib().dca_plm_eval_timed(self._h, ptr(x, _f32p), ptr(ms, _f32p)), "dca_plm_eval_timed")
         return dict(zip(self.KERNELS, ms.tolist()))
+
+    def layout_stats(self):
+        """{'sorted', 'group_sums', 'uniform4', 'logits_columns'}: the row layout the gather kernels run on."""
+        out = np.zeros(4, dtype=np.float64)
+        check(lib().dca_plm_layout_stats(self._h, ptr(out, _f64p)), "dca_plm_layout_stats")
+        return {"sorted": bool(out[0]), "group_sums": bool(out[1]), "uniform4": float(out[2]), "logits_columns": int(out[3])}
 
     def cuda_stream(self):
         """Raw cudaStream_t (int) the handle's kernels run on."""

@@ -479,6 +479,13 @@ int dca_plm_describe(const dca_plm *p, long *out10)
     return 0;
 }
 
+int dca_plm_layout_stats(const dca_plm *p, double *out4)
+{
+    if (!p || !out4) { set_error("dca_plm_layout_stats: null argument"); return -1; }
+    plm_layout_stats(p->prob, out4);
+    return 0;
+}
+
 int dca_plm_fit(dca_plm *p, float *x_inout_host, int max_iterations, int verbose, int warmup_iterations,
                 dca_allreduce_fn allreduce, void *allreduce_ctx, dca_fit_result *result)
 {

@@ -112,6 +112,7 @@ double *plm_scalar_buffer(PlmProblem *p);
 constexpr int PLM_NUM_KERNEL_TIMES = 6;   // unpack, logits, softmax, scatter, export (sharded), assemble+finalize
 int plm_eval_timed(PlmProblem *p, const float *d_x, float *d_g, float *ms);
 void plm_describe(const PlmProblem *p, long *out);
+void plm_layout_stats(const PlmProblem *p, double *out4);
 
 // ---- lbfgs.cu --------------------------------------------------------------------------
 struct LbfgsResult {

@@ -132,6 +132,7 @@ struct PlmProblem {
     float *d_Rz4 = nullptr;           // [Npad / 4][ld]: sums of four consecutive sorted rows of Rz (scatter fast path)
     CUtensorMap tmS4;                 // Rz4 as [Npad / 4][ld] f32, box 128 x 32
     bool group4 = false;              // the perm records reference group sums where four rows share a residue
+    double uniform4 = 0.0;            // fraction of the (site, 4-row group) pairs whose rows share one residue
     bool asym = false;
     int ncol = 0;            // (site_hi - site_lo) * q valid columns (ld = padded to 128)
     int fin_rows = 8;        // rows of x per finish CTA
@@ -212,6 +213,19 @@ nearest_leader_kernel(const uint8_t *__restrict__ msa, long nrows, int row_strid
         }
     }
     if (n < N) best_leader[n] = best;
+}
+
+// how many (site, group of four rows) pairs carry ONE residue: what the fast paths of the logits and scatter kernels
+// save (measurement only: bench.py turns it into executed shared-memory words per add)
+__global__ void count_uniform4_kernel(const uint8_t *__restrict__ msaT, long N, int L, long Npad, unsigned long long *count)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long ngroups = N / 4;
+    if (idx >= (long)L * ngroups) return;
+    const int j = (int)(idx / ngroups);
+    const long g = idx - (long)j * ngroups;
+    const unsigned word = *reinterpret_cast<const unsigned *>(msaT + (size_t)j * Npad + 4 * g);
+    if (word == __funnelshift_r(word, word, 8)) atomicAdd(count, 1ull);
 }
 
 // msaTs[j][k] = residue of the sequence in sorted row k at site j (rows beyond N: 0)
@@ -1229,6 +1243,18 @@ static int plm_layout_t(PlmProblem *p, bool use_sorted)
     }
     const uint8_t *mT = p->sorted ? p->d_msaTs : p->d_msaT;
     {
+        DevBuf<unsigned long long> d_cnt;
+        unsigned long long h_cnt = 0;
+        const long total = (long)L * (N / 4);
+        if (total > 0 && d_cnt.alloc(1)) {
+            DCA_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), st));
+            DCA_LAUNCH(count_uniform4_kernel, (unsigned)ceil_div<long>(total, 256), 256, 0, st, mT, N, L, Npad, d_cnt.p);
+            DCA_CUDA(cudaMemcpyAsync(&h_cnt, d_cnt.p, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+            DCA_CUDA(cudaStreamSynchronize(st));
+            p->uniform4 = (double)h_cnt / (double)total;
+        }
+    }
+    {
         const long total = (long)L * p->nchunk;
         DCA_CUDA(cudaMemsetAsync(p->d_perm, 0, (size_t)p->site_tiles * p->sites_per_tile * p->nchunk * PERM_REC, st));
         p->group4 = p->sorted && p->d_Rz4 != nullptr;
@@ -1887,6 +1913,13 @@ int plm_eval_timed(PlmProblem *p, const float *d_x, float *d_g, float *ms)
     for (int k = 0; k < PLM_NUM_KERNEL_TIMES; ++k) cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]);
     for (auto &e : ev) cudaEventDestroy(e);
     return rc;
+}
+
+// layout statistics, for the bench's roofline arithmetic: {sorted layout in use, scatter uses group sums, fraction of
+// (site, 4-row group) pairs with one residue, logits kernel columns}
+void plm_layout_stats(const PlmProblem *p, double *out4)
+{
+    out4[0] = p->sorted ? 1.0 : 0.0; out4[1] = p->group4 ? 1.0 : 0.0; out4[2] = p->uniform4; out4[3] = (double)p->lg_tc;
 }
 
 // static launch geometry, for the bench's roofline arithmetic

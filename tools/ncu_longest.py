@@ -1,3 +1,7 @@
+"""Key metrics of an ncu report, one row per (kernel, grid): the longest captured launch.
+
+    python tools/ncu_longest.py <report.ncu-rep> <out.csv> "<note: the command that was profiled>"
+"""
 import csv, subprocess, sys, re, io
 rep, out, note = sys.argv[1], sys.argv[2], sys.argv[3]
 txt = subprocess.run(["ncu","-i",rep,"--page","raw","--csv"],capture_output=True,text=True).stdout
@@ -27,5 +31,5 @@ with open(out,"w") as f:
     f.write("kernel,grid,"+",".join(k for k in KEYS if k in idx)+"\n")
     f.write("unit,,"+",".join(units[idx[k]] for k in KEYS if k in idx)+"\n")
     for (k,g),(t,r) in best.items():
-        f.write('%s,"%s",'%(k,g)+",".join(r[idx[kk]].replace(",","") for kk in KEYS if kk in idx)+"\n")
+        f.write('"%s","%s",'%(k,g)+",".join(r[idx[kk]].replace(",","") for kk in KEYS if kk in idx)+"\n")
 print(open(out).read()[:6000])
