@@ -162,23 +162,27 @@ __global__ void transpose_msa_kernel(const uint8_t *__restrict__ msa, long N, in
 constexpr int NL_TILE = 8;
 // rows classified: n * row_stride for n < nrows (row_stride 1: every sequence; 16: the leaders themselves).
 // first_at > 0: not the most identical leader but the FIRST one with at least first_at identical residues (leaders
-// classified against leaders: the first similar leader is the representative of a cluster of leaders)
+// classified against leaders: the first similar leader is the representative of a cluster of leaders).
+// blockIdx.y takes a slice of the leaders (a grid of N / 128 CTAs alone leaves most SMs empty); the slices meet in
+// `key`: most identical -> atomicMax of (identical residues << 20 | 0xfffff - leader), lowest leader on ties;
+// first similar -> atomicMin of the leader index.  key is cleared to 0 / 0x7fffffff by the caller; L < 2048.
 __global__ void __launch_bounds__(128)
 nearest_leader_kernel(const uint8_t *__restrict__ msa, long nrows, int row_stride, int L, int nleaders, int first_at,
-                      int *__restrict__ best_leader)
+                      unsigned *__restrict__ key)
 {
     extern __shared__ uint32_t lead[];                  // [NL_TILE][Lw]
     const int Lw = (L + 3) / 4;
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long N = nrows;
     const uint8_t *row = msa + (size_t)(min(n, nrows - 1) * row_stride) * L;
+    const int per = (((nleaders + (int)gridDim.y - 1) / (int)gridDim.y + NL_TILE - 1) / NL_TILE) * NL_TILE;
+    const int lbeg = (int)blockIdx.y * per, lend = min(nleaders, lbeg + per);
     int best = 0, best_id = -1;
-    for (int l0 = 0; l0 < nleaders; l0 += NL_TILE) {
+    for (int l0 = lbeg; l0 < lend; l0 += NL_TILE) {
         __syncthreads();
         for (int t = threadIdx.x; t < NL_TILE * Lw; t += blockDim.x) {
             const int k = t / Lw, wdx = t - k * Lw;
             uint32_t v = 0xffffffffu;                   // a leader that does not exist matches nothing
-            if (l0 + k < nleaders) {
+            if (l0 + k < lend) {
                 const uint8_t *lr = msa + (size_t)((long)(l0 + k) * 16) * L;
                 v = 0;
                 for (int e = 0; e < 4; ++e) {
@@ -207,12 +211,15 @@ nearest_leader_kernel(const uint8_t *__restrict__ msa, long nrows, int row_strid
         }
 #pragma unroll
         for (int k = 0; k < NL_TILE; ++k) {
-            if (l0 + k >= nleaders) continue;
+            if (l0 + k >= lend) continue;
             if (first_at > 0) { if (best_id < first_at && ident[k] >= first_at) { best_id = ident[k]; best = l0 + k; } }
             else if (ident[k] > best_id) { best_id = ident[k]; best = l0 + k; }
         }
     }
-    if (n < N) best_leader[n] = best;
+    if (n < nrows && best_id >= 0) {
+        if (first_at > 0) { if (best_id >= first_at) atomicMin(key + n, (unsigned)best); }
+        else atomicMax(key + n, ((unsigned)best_id << 20) | (0xfffffu - (unsigned)best));
+    }
 }
 
 // how many (site, group of four rows) pairs carry ONE residue: what the fast paths of the logits and scatter kernels
@@ -1207,17 +1214,28 @@ static int plm_layout_t(PlmProblem *p, bool use_sorted)
         DevBuf<int> d_best, d_order;
         if (!d_best.alloc((size_t)N) || !d_order.alloc((size_t)N)) return -1;
         const size_t smem = sizeof(uint32_t) * NL_TILE * ((L + 3) / 4);
-        DevBuf<int> d_rep;
+        DevBuf<unsigned> d_rep;
         if (!d_rep.alloc((size_t)nleaders)) return -1;
-        DCA_LAUNCH(nearest_leader_kernel, (unsigned)ceil_div<long>(N, 128), 128, smem, st, p->d_msa, N, 1, L, nleaders, 0, d_best.p);
+        unsigned *d_key = reinterpret_cast<unsigned *>(d_best.p);
+        const int slices = std::max(1, std::min(32, (int)((4L * sm_count()) / std::max<long>(1, ceil_div<long>(N, 128)))));
+        DCA_CUDA(cudaMemsetAsync(d_key, 0, sizeof(unsigned) * (size_t)N, st));
+        DCA_CUDA(cudaMemsetAsync(d_rep.p, 0x7f, sizeof(unsigned) * (size_t)nleaders, st));
+        DCA_LAUNCH(nearest_leader_kernel, dim3((unsigned)ceil_div<long>(N, 128), (unsigned)slices), 128, smem, st, p->d_msa, N, 1, L,
+                   nleaders, 0, d_key);
         // leaders against leaders: the first leader sharing half of the residues represents a cluster of leaders, so that
         // the runs of one true cluster end up next to each other (groups of four that straddle two runs stay similar)
-        DCA_LAUNCH(nearest_leader_kernel, (unsigned)ceil_div<long>(nleaders, 128), 128, smem, st, p->d_msa, (long)nleaders, 16, L,
-                   nleaders, (L + 1) / 2, d_rep.p);
+        DCA_LAUNCH(nearest_leader_kernel, dim3((unsigned)ceil_div<long>(nleaders, 128), 32), 128, smem, st, p->d_msa, (long)nleaders,
+                   16, L, nleaders, (L + 1) / 2, d_rep.p);
         std::vector<int> best((size_t)N), rep((size_t)nleaders), order((size_t)N), rowidx((size_t)N);
-        DCA_CUDA(cudaMemcpyAsync(best.data(), d_best.p, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
+        DCA_CUDA(cudaMemcpyAsync(best.data(), d_key, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
         DCA_CUDA(cudaMemcpyAsync(rep.data(), d_rep.p, sizeof(int) * (size_t)nleaders, cudaMemcpyDeviceToHost, st));
         DCA_CUDA(cudaStreamSynchronize(st));
+        for (long n = 0; n < N; ++n) {
+            const unsigned l = 0xfffffu - ((unsigned)best[(size_t)n] & 0xfffffu);
+            best[(size_t)n] = (l < (unsigned)nleaders) ? (int)l : 0;
+        }
+        for (int k = 0; k < nleaders; ++k)              // a leader always finds itself
+            if (rep[(size_t)k] < 0 || rep[(size_t)k] > k) rep[(size_t)k] = k;
         {   // rank of every leader in (representative, leader) order, then a counting sort of the sequences by that
             // rank: file order inside a leader's run
             std::vector<int> by_rep((size_t)nleaders), rank((size_t)nleaders);
@@ -1683,7 +1701,7 @@ static PlmProblem *plm_create_impl(const uint8_t *h_msa, const float *h_w, long 
     {   // similarity-sorted layout.  Every rank of a multi-GPU objective sorts for itself: the order only concerns
         // its own S / Rz rows
         const char *e = getenv("DCA_B200_LAYOUT");           // file | sorted (default)
-        p->want_sorted = N >= 256 && !(e && strcmp(e, "file") == 0);
+        p->want_sorted = N >= 256 && N < (1L << 24) && L < 2048 && !(e && strcmp(e, "file") == 0);
         if (p->want_sorted) {
             PLM_ALLOC(p->d_msaTs, (size_t)L * p->Npad);
             PLM_ALLOC(p->d_rowidx, sizeof(int) * (size_t)N);
