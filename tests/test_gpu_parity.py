@@ -475,3 +475,34 @@ def test_compute_couplings_refuses_what_it_cannot_invert():
     nan[2, 2] = np.nan
     with pytest.raises(lib().DcaBackendError):
         msa_numerics.compute_couplings(corr_mat=nan)
+
+
+def test_sorted_layout_and_fast_paths_do_not_change_the_result(port, monkeypatch):
+    """the similarity-sorted row layout with the equal-residue fast paths (logits: one operand row for
+    four agreeing rows; scatter: four-row group sums) against the file-order layout with the dense kernels, on a
+    clustered alignment (many uniform groups) and on a random one (hardly any), and both against the oracle."""
+    from pydca_b200.synthetic import synthetic_msa
+    rng = np.random.default_rng(12)
+    N, L, q = 3000, 60, 21
+    clustered = synthetic_msa(N, L, q, seed=21)
+    random_msa = rng.integers(0, q, size=(N, L)).astype(np.uint8)
+    lam = 0.2 * (L - 1)
+    for msa, min_u, max_u in ((clustered, 0.3, 1.0), (random_msa, 0.0, 0.01)):
+        w = port.plm_weights(port.reweight_counts(msa, 0.8))
+        x = (port.plm_init(msa, w, q) + rng.normal(0, 0.1, L * q + L * (L - 1) // 2 * q * q)).astype(np.float32)
+        out = {}
+        for layout in ("sorted", "file"):
+            monkeypatch.setenv("DCA_B200_LAYOUT", layout)
+            obj = lib().PlmObjective(msa, w, q, lam, lam)
+            st = obj.layout_stats()
+            assert st["sorted"] == (layout == "sorted") and st["group_sums"] == (layout == "sorted")
+            if layout == "sorted":
+                assert min_u <= st["uniform4"] <= max_u
+            out[layout] = obj.eval(x)
+            obj.close()
+        monkeypatch.delenv("DCA_B200_LAYOUT")
+        (f_s, g_s), (f_f, g_f) = out["sorted"], out["file"]
+        assert abs(f_s - f_f) <= 1e-6 * abs(f_f)
+        assert relmax(g_s, g_f) <= 3e-6
+        f64, g64 = port.plm_gradient_f64(msa, w, q, lam, lam, x)
+        assert abs(f_s - f64) <= 1e-5 * abs(f64) and relmax(g_s, g64) <= 1e-5
