@@ -66,6 +66,8 @@ int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, in
                            int part = -1, int nparts = 1);
 
 // ---- plm_eval.cu -------------------------------------------------------------------
+// similarity order of the rows of a device alignment (u8 [N][L]): order[k] = file index of sorted row k
+int similarity_order(const uint8_t *d_msa, long N, int L, cudaStream_t st, std::vector<int> &order, std::vector<int> &rowidx);
 struct PlmProblem;   // device-resident state of one plmDCA objective
 
 // scalars every evaluation leaves on the device (double): see plm_eval.cu

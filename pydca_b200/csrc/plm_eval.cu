@@ -167,13 +167,15 @@ constexpr int NL_TILE = 8;
 // `key`: most identical -> atomicMax of (identical residues << 20 | 0xfffff - leader), lowest leader on ties;
 // first similar -> atomicMin of the leader index.  key is cleared to 0 / 0x7fffffff by the caller; L < 2048.
 __global__ void __launch_bounds__(128)
-nearest_leader_kernel(const uint8_t *__restrict__ msa, long nrows, int row_stride, int L, int nleaders, int first_at,
-                      unsigned *__restrict__ key)
-{
+nearest_leader_kernel(const uint8_t *__restrict__ msa, long nrows, int row_stride, int Lfull, int cstride, int nleaders,
+                      int first_at, unsigned *__restrict__ key)
+{   // the compare runs on every cstride-th column (L = sampled columns): identity on a 64-column sample separates
+    // "same cluster" from "unrelated" as well as the full rows do, at a fraction of the cost
     extern __shared__ uint32_t lead[];                  // [NL_TILE][Lw]
+    const int L = (Lfull + cstride - 1) / cstride;
     const int Lw = (L + 3) / 4;
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint8_t *row = msa + (size_t)(min(n, nrows - 1) * row_stride) * L;
+    const uint8_t *row = msa + (size_t)(min(n, nrows - 1) * row_stride) * Lfull;
     const int per = (((nleaders + (int)gridDim.y - 1) / (int)gridDim.y + NL_TILE - 1) / NL_TILE) * NL_TILE;
     const int lbeg = (int)blockIdx.y * per, lend = min(nleaders, lbeg + per);
     int best = 0, best_id = -1;
@@ -183,11 +185,11 @@ nearest_leader_kernel(const uint8_t *__restrict__ msa, long nrows, int row_strid
             const int k = t / Lw, wdx = t - k * Lw;
             uint32_t v = 0xffffffffu;                   // a leader that does not exist matches nothing
             if (l0 + k < lend) {
-                const uint8_t *lr = msa + (size_t)((long)(l0 + k) * 16) * L;
+                const uint8_t *lr = msa + (size_t)((long)(l0 + k) * 16) * Lfull;
                 v = 0;
                 for (int e = 0; e < 4; ++e) {
                     const int c = 4 * wdx + e;
-                    v |= (uint32_t)(c < L ? lr[c] : 0xffu) << (8 * e);
+                    v |= (uint32_t)(c < L ? lr[c * cstride] : 0xffu) << (8 * e);
                 }
             }
             lead[t] = v;
@@ -201,7 +203,7 @@ nearest_leader_kernel(const uint8_t *__restrict__ msa, long nrows, int row_strid
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int c = 4 * wdx + e;
-                a |= (uint32_t)(c < L ? row[c] : 0xfeu) << (8 * e);     // padding: 0xfe here, 0xff in the leaders
+                a |= (uint32_t)(c < L ? row[c * cstride] : 0xfeu) << (8 * e);     // padding: 0xfe here, 0xff in the leaders
             }
 #pragma unroll
             for (int k = 0; k < NL_TILE; ++k) {
@@ -220,6 +222,55 @@ nearest_leader_kernel(const uint8_t *__restrict__ msa, long nrows, int row_strid
         if (first_at > 0) { if (best_id >= first_at) atomicMin(key + n, (unsigned)best); }
         else atomicMax(key + n, ((unsigned)best_id << 20) | (0xfffffu - (unsigned)best));
     }
+}
+
+// Row order that puts similar sequences next to each other (used by the plmDCA gather kernels' fast paths and by
+// the reweighting kernel's early exit).  order[k] = file index of the sequence in sorted row k, rowidx = its inverse.
+// Leaders = every 16th sequence of the file; identities are taken on a sample of ~64 columns.
+int similarity_order(const uint8_t *d_msa, long N, int L, cudaStream_t st, std::vector<int> &order, std::vector<int> &rowidx)
+{
+    const int nleaders = (int)ceil_div<long>(N, 16);
+    const int cstride = std::max(1, L / 64);
+    const int Ls = ceil_div(L, cstride);
+    DevBuf<unsigned> d_key, d_rep;
+    if (!d_key.alloc((size_t)N) || !d_rep.alloc((size_t)nleaders)) return -1;
+    const size_t smem = sizeof(uint32_t) * NL_TILE * ((Ls + 3) / 4);
+    const int slices = std::max(1, std::min(32, (int)((4L * sm_count()) / std::max<long>(1, ceil_div<long>(N, 128)))));
+    DCA_CUDA(cudaMemsetAsync(d_key.p, 0, sizeof(unsigned) * (size_t)N, st));
+    DCA_CUDA(cudaMemsetAsync(d_rep.p, 0x7f, sizeof(unsigned) * (size_t)nleaders, st));
+    DCA_LAUNCH(nearest_leader_kernel, dim3((unsigned)ceil_div<long>(N, 128), (unsigned)slices), 128, smem, st, d_msa, N, 1, L,
+               cstride, nleaders, 0, d_key.p);
+    // leaders against leaders: the first leader sharing half of the residues represents a cluster of leaders, so that
+    // the runs of one true cluster end up next to each other (groups of four that straddle two runs stay similar)
+    DCA_LAUNCH(nearest_leader_kernel, dim3((unsigned)ceil_div<long>(nleaders, 128), 32), 128, smem, st, d_msa, (long)nleaders,
+               16, L, cstride, nleaders, (Ls + 1) / 2, d_rep.p);
+    std::vector<int> best((size_t)N), rep((size_t)nleaders);
+    order.assign((size_t)N, 0);
+    rowidx.assign((size_t)N, 0);
+    DCA_CUDA(cudaMemcpyAsync(best.data(), d_key.p, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
+    DCA_CUDA(cudaMemcpyAsync(rep.data(), d_rep.p, sizeof(int) * (size_t)nleaders, cudaMemcpyDeviceToHost, st));
+    DCA_CUDA(cudaStreamSynchronize(st));
+    for (long n = 0; n < N; ++n) {
+        const unsigned l = 0xfffffu - ((unsigned)best[(size_t)n] & 0xfffffu);
+        best[(size_t)n] = (l < (unsigned)nleaders) ? (int)l : 0;
+    }
+    for (int k = 0; k < nleaders; ++k)              // a leader always finds itself
+        if (rep[(size_t)k] < 0 || rep[(size_t)k] > k) rep[(size_t)k] = k;
+    // rank of every leader in (representative, leader) order, then a counting sort of the sequences by that
+    // rank: file order inside a leader's run
+    std::vector<int> by_rep((size_t)nleaders), rank((size_t)nleaders);
+    for (int k = 0; k < nleaders; ++k) by_rep[(size_t)k] = k;
+    std::stable_sort(by_rep.begin(), by_rep.end(), [&](int a, int b) { return rep[(size_t)a] < rep[(size_t)b]; });
+    for (int r = 0; r < nleaders; ++r) rank[(size_t)by_rep[(size_t)r]] = r;
+    std::vector<int> start((size_t)nleaders + 1, 0);
+    for (long n = 0; n < N; ++n) ++start[(size_t)rank[(size_t)best[(size_t)n]] + 1];
+    for (int k = 0; k < nleaders; ++k) start[(size_t)k + 1] += start[(size_t)k];
+    for (long n = 0; n < N; ++n) {
+        const int k = start[(size_t)rank[(size_t)best[(size_t)n]]]++;
+        order[(size_t)k] = (int)n;
+        rowidx[(size_t)n] = k;
+    }
+    return 0;
 }
 
 // how many (site, group of four rows) pairs carry ONE residue: what the fast paths of the logits and scatter kernels
@@ -1210,47 +1261,10 @@ static int plm_layout_t(PlmProblem *p, bool use_sorted)
     }
     p->sorted = false;
     if (use_sorted && p->d_msaTs && p->d_rowidx) {
-        const int nleaders = (int)ceil_div<long>(N, 16);
-        DevBuf<int> d_best, d_order;
-        if (!d_best.alloc((size_t)N) || !d_order.alloc((size_t)N)) return -1;
-        const size_t smem = sizeof(uint32_t) * NL_TILE * ((L + 3) / 4);
-        DevBuf<unsigned> d_rep;
-        if (!d_rep.alloc((size_t)nleaders)) return -1;
-        unsigned *d_key = reinterpret_cast<unsigned *>(d_best.p);
-        const int slices = std::max(1, std::min(32, (int)((4L * sm_count()) / std::max<long>(1, ceil_div<long>(N, 128)))));
-        DCA_CUDA(cudaMemsetAsync(d_key, 0, sizeof(unsigned) * (size_t)N, st));
-        DCA_CUDA(cudaMemsetAsync(d_rep.p, 0x7f, sizeof(unsigned) * (size_t)nleaders, st));
-        DCA_LAUNCH(nearest_leader_kernel, dim3((unsigned)ceil_div<long>(N, 128), (unsigned)slices), 128, smem, st, p->d_msa, N, 1, L,
-                   nleaders, 0, d_key);
-        // leaders against leaders: the first leader sharing half of the residues represents a cluster of leaders, so that
-        // the runs of one true cluster end up next to each other (groups of four that straddle two runs stay similar)
-        DCA_LAUNCH(nearest_leader_kernel, dim3((unsigned)ceil_div<long>(nleaders, 128), 32), 128, smem, st, p->d_msa, (long)nleaders,
-                   16, L, nleaders, (L + 1) / 2, d_rep.p);
-        std::vector<int> best((size_t)N), rep((size_t)nleaders), order((size_t)N), rowidx((size_t)N);
-        DCA_CUDA(cudaMemcpyAsync(best.data(), d_key, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, st));
-        DCA_CUDA(cudaMemcpyAsync(rep.data(), d_rep.p, sizeof(int) * (size_t)nleaders, cudaMemcpyDeviceToHost, st));
-        DCA_CUDA(cudaStreamSynchronize(st));
-        for (long n = 0; n < N; ++n) {
-            const unsigned l = 0xfffffu - ((unsigned)best[(size_t)n] & 0xfffffu);
-            best[(size_t)n] = (l < (unsigned)nleaders) ? (int)l : 0;
-        }
-        for (int k = 0; k < nleaders; ++k)              // a leader always finds itself
-            if (rep[(size_t)k] < 0 || rep[(size_t)k] > k) rep[(size_t)k] = k;
-        {   // rank of every leader in (representative, leader) order, then a counting sort of the sequences by that
-            // rank: file order inside a leader's run
-            std::vector<int> by_rep((size_t)nleaders), rank((size_t)nleaders);
-            for (int k = 0; k < nleaders; ++k) by_rep[(size_t)k] = k;
-            std::stable_sort(by_rep.begin(), by_rep.end(), [&](int a, int b) { return rep[(size_t)a] < rep[(size_t)b]; });
-            for (int r = 0; r < nleaders; ++r) rank[(size_t)by_rep[(size_t)r]] = r;
-            std::vector<int> start((size_t)nleaders + 1, 0);
-            for (long n = 0; n < N; ++n) ++start[(size_t)rank[(size_t)best[(size_t)n]] + 1];
-            for (int k = 0; k < nleaders; ++k) start[(size_t)k + 1] += start[(size_t)k];
-            for (long n = 0; n < N; ++n) {
-                const int k = start[(size_t)rank[(size_t)best[(size_t)n]]]++;
-                order[(size_t)k] = (int)n;
-                rowidx[(size_t)n] = k;
-            }
-        }
+        DevBuf<int> d_order;
+        if (!d_order.alloc((size_t)N)) return -1;
+        std::vector<int> order, rowidx;
+        if (similarity_order(p->d_msa, N, L, st, order, rowidx) != 0) return -1;
         DCA_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
         DCA_CUDA(cudaMemcpyAsync(p->d_rowidx, rowidx.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, st));
         const long total = (long)L * Npad;

@@ -29,6 +29,8 @@
 #include "dca_internal.h"
 
 #include <algorithm>
+#include <cstring>
+#include <vector>
 
 namespace dca {
 
@@ -94,10 +96,15 @@ reweight_kernel(const uint32_t *__restrict__ msa_w, long N, long i_lo, long i_hi
 
     for (long j0 = jbeg; j0 < jend; j0 += RW_TJ) {
         unsigned acc[8][4];
+        unsigned pair_valid = 0;                               // bit 4 r + s: pair (row r, column s) is inside the ranges
+        bool decided = false;
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int s = 0; s < 4; ++s) acc[r][s] = 0;
+            for (int s = 0; s < 4; ++s) {
+                acc[r][s] = 0;
+                if ((i0 + ty + 16 * r) < i_hi && (j0 + tx + 16 * s) < jend) pair_valid |= 1u << (4 * r + s);
+            }
 
         stage(0, j0, 0);
         for (int kc = 0; kc < nk; ++kc) {
@@ -107,7 +114,6 @@ reweight_kernel(const uint32_t *__restrict__ msa_w, long N, long i_lo, long i_hi
             __syncthreads();
             const uint32_t *Ib = Is + (size_t)buf * RW_TI * RW_STRIDE;
             const uint32_t *Jb = Js + (size_t)buf * RW_TJ * RW_STRIDE;
-#pragma unroll 2
             for (int k4 = 0; k4 < RW_KW / 4; ++k4) {
                 uint4 a[8], b[4];
 #pragma unroll
@@ -127,9 +133,24 @@ reweight_kernel(const uint32_t *__restrict__ msa_w, long N, long i_lo, long i_hi
                         c = __dp4a(((a[r].w ^ b[s].w) + 0x1f1f1f1fu) & 0x20202020u, 0x01010101u, c);
                         acc[r][s] = c;
                     }
+                // Early exit: mismatches only grow, so once EVERY pair of the tile is over the budget the tile is
+                // decided (no hit).  On a similarity-sorted alignment almost all tile pairs are cross-cluster and are
+                // decided after a fraction of the columns (budget 0.2 L at a mismatch rate of ~0.95).  One block
+                // vote per 32 residues; pairs outside the ranges compare zeros with zeros and are masked out.
+                if ((k4 & 1) == 1) {
+                    bool open = false;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int s2 = 0; s2 < 4; ++s2)
+                            open |= (acc[r][s2] <= max_mismatch32) && ((pair_valid >> (4 * r + s2)) & 1u);
+                    if (!__syncthreads_or(open)) { decided = true; break; }
+                }
             }
+            if (decided) break;
             __syncthreads();
         }
+        if (decided) { cp_async_wait<0>(); __syncthreads(); }        // the next chunk may already be in flight
         const bool mirror = sym && (j0 >= i0 + RW_TI);     // off the diagonal block: the hit counts for row j too
         unsigned colhit[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -193,8 +214,8 @@ int reweight_min_ident(int L, double seqid, int compare_f64)
 
 // pack a u8 [N][L] device MSA into zero-padded word rows
 __global__ void pack_rows_kernel(const uint8_t *__restrict__ msa, long N, int L, int Lw,
-                                 uint32_t *__restrict__ out, unsigned *__restrict__ bad)
-{   // *bad is raised for residue codes >= 32: the mismatch test of reweight_kernel (bit 5 of
+                                 uint32_t *__restrict__ out, unsigned *__restrict__ bad, const int *__restrict__ order)
+{   // order (may be null): packed row n holds sequence order[n] (similarity-sorted rows)   // *bad is raised for residue codes >= 32: the mismatch test of reweight_kernel (bit 5 of
     // (a ^ b) + 0x1f per byte) is exact only for 5-bit codes
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * Lw) return;
@@ -205,12 +226,20 @@ __global__ void pack_rows_kernel(const uint8_t *__restrict__ msa, long N, int L,
     for (int b = 0; b < 4; ++b) {
         const int s = kw * 4 + b;
         if (s < L) {
-            const uint32_t c = msa[n * L + s];
+            const uint32_t c = msa[(order ? (long)order[n] : n) * L + s];
             if (c >= 32u) atomicOr(bad, 1u);
             v |= c << (8 * b);
         }
     }
     out[idx] = v;
+}
+
+// counts[order[k]] = sorted_counts[k]
+__global__ void unsort_counts_kernel(const unsigned *__restrict__ sorted_counts, const int *__restrict__ order, long N,
+                                     unsigned *__restrict__ counts)
+{
+    const long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N) counts[order[k]] = sorted_counts[k];
 }
 
 // counts for rows [row_lo,row_hi) against all N rows (multi-GPU: row shards,
@@ -231,13 +260,28 @@ int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, in
     }
     const int Lw = (int)(ceil_div(L, 4) + 3) / 4 * 4;
     DevBuf<uint32_t> d_words;            // released on every return path
-    DevBuf<unsigned> d_bad;
+    DevBuf<unsigned> d_bad, d_sorted_counts;
+    DevBuf<int> d_order;
     if (!d_words.alloc((size_t)N * Lw) || !d_bad.alloc(1)) return -1;
+    // Deep alignments (symmetric mode): compare the rows in similarity order.  Almost every tile pair then holds
+    // unrelated sequences only, which the kernel's early exit decides after a fraction of the columns; the counts
+    // come back through the permutation.  The order costs N^2/16 sampled compares -- worth it from ~1e10 on.
+    const bool use_sorted = sym && (double)N * (double)N * (double)L >= 2.0e10 && N < (1L << 24) && L < 2048 &&
+                            !(getenv("DCA_B200_REWEIGHT_ORDER") && strcmp(getenv("DCA_B200_REWEIGHT_ORDER"), "file") == 0);
+    if (use_sorted) {
+        std::vector<int> order, rowidx;
+        if (!d_order.alloc((size_t)N) || !d_sorted_counts.alloc((size_t)N)) return -1;
+        if (similarity_order(d_msa, N, L, stream, order, rowidx) != 0) return -1;
+        DCA_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, stream));
+        DCA_CUDA(cudaStreamSynchronize(stream));           // `order` goes out of scope
+        DCA_CUDA(cudaMemsetAsync(d_sorted_counts.p, 0, sizeof(unsigned) * (size_t)N, stream));
+    }
+    unsigned *d_out = use_sorted ? d_sorted_counts.p : d_counts;
     DCA_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), stream));
     {
         const long total = N * Lw;
         DCA_LAUNCH(pack_rows_kernel, (unsigned)ceil_div<long>(total, 256), 256, 0, stream,
-                   d_msa, N, L, Lw, d_words, d_bad);
+                   d_msa, N, L, Lw, d_words, d_bad, use_sorted ? (const int *)d_order.p : (const int *)nullptr);
     }
     DCA_CUDA(cudaMemsetAsync(d_counts + row_lo, 0, sizeof(unsigned) * (size_t)(row_hi - row_lo), stream));
     const int T = reweight_min_ident(L, seqid, compare_f64);
@@ -262,8 +306,11 @@ int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, in
         dim3 grid(gx, (unsigned)js);
         if (gx > 0)
             DCA_LAUNCH(reweight_kernel, grid, 256, smem, stream,
-                       d_words, N, row_lo, row_hi, Lw, jper, max_mismatch32, d_counts,
+                       d_words, N, row_lo, row_hi, Lw, jper, max_mismatch32, d_out,
                        sym ? 1 : 0, sym ? part : 0, sym ? nparts : 1);
+        if (use_sorted)
+            DCA_LAUNCH(unsort_counts_kernel, (unsigned)ceil_div<long>(N, 256), 256, 0, stream, d_sorted_counts.p, d_order.p, N,
+                       d_counts);
     }
     DCA_CUDA(cudaGetLastError());
     unsigned h_bad = 0;
