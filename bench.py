@@ -479,7 +479,7 @@ def reweight_block():
         out[tag] = {"N": N, "L": L, "device_ms": ms, "byte_compares_per_s": compares / (ms * 1e-3),
                     "packed_lane_floor_ms": floor_ms, "frac_of_packed_lane_floor": floor_ms / ms,
                     "note": "floor = N^2 L / 4 packed lane-ops at 148 x 128 lanes x 1.965 GHz (SURVEY 8d); the kernel "
-                            "spends 4 integer ops per 4 residues (xor, add, and, dp4a) on HALF the pairs (symmetric tiles)"}
+                            "spends 4 integer ops per 4 residues (xor, add, and, dp4a) on HALF the pairs (symmetric tiles); deep alignments are compared in similarity order and a tile stops once every pair is over the mismatch budget, so the rate is algorithmic (N^2 L byte compares / time, ordering pass included)"}
     return out
 
 
