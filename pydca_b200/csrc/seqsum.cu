@@ -293,6 +293,9 @@ seqsum_kernel(SeqLaunch jobs, float *__restrict__ out)
 }
 
 // ---- producer / consumer pipeline -------------------------------------------------------------
+constexpr int SEQ_MAX_ROUNDS = 6;            // exponent changes inside one chunk before the rest of it goes through the plain chain
+constexpr int PC_RING = 128;                 // chunks in the consumer's shared-memory ring of records
+constexpr int PC_FETCH = 4;                  // fetch warps of the consumer CTA (PC_RING / 32 batches in flight)
 constexpr int PC_CHUNK = SQ_GROUP;             // 4096 terms: one row of 128 per warp
 struct SeqRec { int total[2], pmin[2], pmax[2]; int flags; int e_base; };      // 32 bytes
 static_assert(sizeof(SeqRec) == 32, "record layout");
@@ -371,34 +374,54 @@ __device__ __forceinline__ int exp_field(float s)           // 0 when the intege
 }
 
 // warp 0 of the consumer: rows [w0, 32) of the chunk in tbuf from running value s, exactly.  The
-// warp summaries were made for the exponent s has on entry; a row whose summary does not fit is
-// done by the finer paths, and if that changed the exponent the walk returns the next row so that
-// the whole CTA can re-summarise the rest for the new exponent (returns 32 when the chunk is done).
-__device__ int walk_chunk(float &s, int w0, bool ctx_ok, const SeqSum *wsum, const int *wflag, const float *tbuf)
+// warp summaries were made for the exponent s has on entry.  Lane l takes row w + l: the row
+// summaries are composed by a warp scan (both parities) and the range check of the composed
+// prefixes says how many leading rows can be applied in ONE integer addition -- as long as it
+// holds the exponent cannot change.  The first row that does not fit goes through the plain
+// chain (128 dependent adds: ~600 cycles, cheaper than any finer speculation); if that changed
+// the exponent the walk returns the next row so that the whole CTA can re-summarise the rest for
+// the new exponent (returns 32 when the chunk is done).  all_serial: the exponent has already
+// changed several times inside this chunk -- the rest is done by the plain chain.
+__device__ int walk_chunk(float &s, int w0, bool ctx_ok, bool all_serial, const SeqSum *wsum, const int *wflag,
+                          const float *tbuf)
 {
     const int lane = threadIdx.x & 31;
     SeqCtx c0;
-    const bool usable = ctx_ok && seq_ctx_make(s, &c0);
-    for (int w = w0; w < SQ_WARPS; ++w) {
+    const bool usable = !all_serial && ctx_ok && seq_ctx_make(s, &c0);
+    int w = w0;
+    while (w < SQ_WARPS) {
         if (usable) {
             SeqCtx cc;
-            seq_ctx_make(s, &cc);                          // same binade as c0: every applied block keeps it
+            seq_ctx_make(s, &cc);                              // same binade as c0: every applied block keeps it
+            const int row = w + lane;
+            const bool valid = row < SQ_WARPS;
+            SeqSum v;
+            v.total[0] = v.total[1] = v.pmin[0] = v.pmin[1] = v.pmax[0] = v.pmax[1] = 0;
+            int bad = 0;
+            if (valid) { v = wsum[row]; bad = wflag[row] & 1; }
+            const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);
+            const int nusable = (badmask == 0u) ? 32 : (__ffs(badmask) - 1);
+            v = warp_scan(v, true);
             const int p = cc.M & 1;
-            const SeqSum v = wsum[w];
-            if (!(wflag[w] & 1) && seq_block_ok(cc, v.pmin[p], v.pmax[p])) { s = seq_apply(cc, v.total[p]); continue; }
-        }
-        const float4 q = *reinterpret_cast<const float4 *>(tbuf + w * 128 + 4 * lane);
-        const float t4[4] = {q.x, q.y, q.z, q.w};
-        if (!try_warp<4>(s, t4)) {
-            for (int h = 0; h < 4; ++h) {
-                const float t1 = tbuf[w * 128 + h * 32 + lane];
-                if (try_warp<1>(s, &t1)) continue;
-                s = serial32(s, tbuf + w * 128 + h * 32);
+            const bool okl = !valid || (lane < nusable && seq_block_ok(cc, v.pmin[p], v.pmax[p]));
+            const unsigned okmask = __ballot_sync(0xffffffffu, okl);
+            int nok = (okmask == 0xffffffffu) ? 32 : (__ffs(~okmask) - 1);
+            nok = min(nok, SQ_WARPS - w);
+            if (nok > 0) {
+                const int total = __shfl_sync(0xffffffffu, v.total[p], nok - 1);
+                s = seq_apply(cc, total);
+                w += nok;
+                if (w >= SQ_WARPS) break;
             }
         }
+        // row w: the plain chain; every lane runs it on the same (broadcast) loads, s stays warp-uniform
+#pragma unroll
+        for (int h = 0; h < 4; ++h) s = serial32(s, tbuf + w * 128 + h * 32);
+        ++w;
+        if (all_serial) continue;
         SeqCtx cn;
         const bool same = usable && seq_ctx_make(s, &cn) && cn.scale == c0.scale;
-        if (!same && w + 1 < SQ_WARPS && seq_ctx_make(s, &cn)) return w + 1;      // re-summarise the rest
+        if (!same && w < SQ_WARPS && seq_ctx_make(s, &cn)) return w;      // re-summarise the rest
     }
     return SQ_WARPS;
 }
@@ -470,6 +493,12 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
     __shared__ float s_sh;
     __shared__ long c_sh;
     __shared__ int e_sh, skip_sh;
+    // consumer only: ring of fetched records (three candidates per chunk), filled by the fetch warps
+    __shared__ int4 ring[PC_RING][6];
+    __shared__ volatile int ring_tag[PC_RING];             // chunk index + 1 once the slot holds that chunk
+    __shared__ volatile int ring_e[PC_RING];               // exponent field of the chunk's middle candidate
+    __shared__ volatile long cpos_sh;                      // the chain warp's position
+    __shared__ volatile int stop_sh;                       // the chain warp has left the fast-forward loop
 
     const int job = blockIdx.x / (P + 1), role = blockIdx.x % (P + 1);
     const SeqJob J = jobs.job[job];
@@ -542,65 +571,57 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
     }
 
     // ================= consumer =================
-    if (tid == 0) { s_sh = 0.f; c_sh = 0; st_release_u64(st_prog, tag); st_release_u64(st_exp, tag); }
+    if (tid == 0) { s_sh = 0.f; c_sh = 0; cpos_sh = 0; stop_sh = 0; st_release_u64(st_prog, tag); st_release_u64(st_exp, tag); }
+    for (int i = tid; i < PC_RING; i += SQ_THREADS) ring_tag[i] = 0;
     __syncthreads();
+    const long long clk_begin = clock64();
+    long long clk_exact = 0, clk_wait = 0;
     for (;;) {
         if (warp == 0) {
             // ---- fast-forward over the producers' records, 32 chunks per step ----
+            // The chain warp reads nothing but shared memory: the fetch warps below copy the records
+            // into a ring as the producers publish them (decoupled access / execute -- a global round
+            // trip inside the chain, and two more after every exact chunk, was most of its time).
             // The records of a batch are composed by a warp scan (both parities); the range check of
             // the composed prefix tells how many leading chunks can be applied at once, and as long
-            // as it holds the exponent -- hence the choice of candidate -- cannot change.  The loads
-            // are software-pipelined: while batch b is scanned, the records of batch b+1 (whose ready
-            // words arrived one step earlier and name the candidate) and the ready words of batch b+2
-            // are in flight; the ready word is (launch << 8) | exponent of the middle candidate.
+            // as it holds the exponent -- hence the choice of candidate -- cannot change.
             float s = s_sh;
             long c = c_sh;
             bool stop = false;
             unsigned n_fast = 0, n_timeout = 0, n_stale = 0, n_range = 0;
-            const unsigned want = launch_id << 8;
-            auto flag_at = [&](long k) -> unsigned { return (k < nchunks) ? ld_acquire_u32(ready + k) : 0u; };
-            // candidate of chunk k made for exponent ef, if its ready word fl says there is one
-            auto fetch = [&](long k, unsigned fl, int ef, int4 &A, int4 &B) -> bool {
-                if ((fl & 0xffffff00u) != want) return false;
-                const int idx = ef - ((int)(fl & 0xffu) - 1);
-                if (idx < 0 || idx > 2 || (fl & 0xffu) == 0u) { A = make_int4(0, 0, 0, 0); B = make_int4(0, 0, 1, 0); return true; }
-                const int4 *src = reinterpret_cast<const int4 *>(rec + k * 3 + idx);
-                A = __ldcg(src); B = __ldcg(src + 1);
-                return true;
-            };
-            bool pre_valid = false;
-            int pre_ef = 0;
-            int4 curA = make_int4(0, 0, 0, 0), curB = make_int4(0, 0, 1, 0);
-            bool cur_rdy = false;
-            unsigned fl_next = 0;
             while (c < nchunks && !stop) {
                 SeqCtx cc;
                 if (!seq_ctx_make(s, &cc)) break;
                 const int ef = exp_field(s);
-                if (!pre_valid || pre_ef != ef) {          // (re)start the pipeline at c
-                    cur_rdy = fetch(c + lane, flag_at(c + lane), ef, curA, curB);
-                    fl_next = flag_at(c + 32 + lane);
-                    pre_valid = true; pre_ef = ef;
-                }
-                int4 nxtA = make_int4(0, 0, 0, 0), nxtB = make_int4(0, 0, 1, 0);
-                const bool nxt_rdy = fetch(c + 32 + lane, fl_next, ef, nxtA, nxtB);      // in flight during the scan
-                const unsigned fl_next2 = flag_at(c + 64 + lane);
-                const unsigned rmask = __ballot_sync(0xffffffffu, cur_rdy);
+                const long k = c + lane;
+                const int slot = (int)(k % PC_RING);
+                const bool rdy = k < nchunks && ring_tag[slot] == (int)(k + 1);
+                const unsigned rmask = __ballot_sync(0xffffffffu, rdy);
                 const int nready = (rmask == 0xffffffffu) ? 32 : (__ffs(~rmask) - 1);
                 if (nready == 0) {
                     bool ok = false;
                     const long long t0 = clock64();
                     while (clock64() - t0 < 40000) {
-                        if ((ld_acquire_u32(ready + c) & 0xffffff00u) == want) { ok = true; break; }
+                        if (ring_tag[(int)(c % PC_RING)] == (int)(c + 1)) { ok = true; break; }
                     }
+                    clk_wait += clock64() - t0;
                     if (!ok) { ++n_timeout; stop = true; }
-                    pre_valid = false;
                     continue;
                 }
+                __threadfence_block();                     // tag before data (the fetch warp fenced the other way round)
                 SeqSum v;
-                v.total[0] = curA.x; v.total[1] = curA.y; v.pmin[0] = curA.z; v.pmin[1] = curA.w;
-                v.pmax[0] = curB.x; v.pmax[1] = curB.y;
-                const int bad = (lane < nready) ? (curB.z & 1) : 1;
+                v.total[0] = v.total[1] = v.pmin[0] = v.pmin[1] = v.pmax[0] = v.pmax[1] = 0;
+                int bad = 1;
+                if (lane < nready) {
+                    const int e_mid = ring_e[slot];        // exponent field of the middle candidate (0: none)
+                    const int idx = ef - (e_mid - 1);
+                    if (e_mid != 0 && idx >= 0 && idx <= 2) {
+                        const int4 A = ring[slot][2 * idx], B = ring[slot][2 * idx + 1];
+                        v.total[0] = A.x; v.total[1] = A.y; v.pmin[0] = A.z; v.pmin[1] = A.w;
+                        v.pmax[0] = B.x; v.pmax[1] = B.y;
+                        bad = B.z & 1;
+                    }
+                }
                 const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);
                 const int nusable = (badmask == 0u) ? 32 : (__ffs(badmask) - 1);      // leading usable records
                 v = warp_scan(v, true);
@@ -613,42 +634,74 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                     s = seq_apply(cc, total);
                     c += nok;
                     n_fast += (unsigned)nok;
+                    if (lane == 0) {
+                        cpos_sh = c;                       // frees the ring slots behind c
+                        st_relaxed_u64(st_prog, tag | (unsigned long long)c);      // hints for the producers
+                        st_relaxed_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s));
+                    }
                 }
-                if (lane == 0) {                           // hints for the producers: no ordering needed
-                    st_relaxed_u64(st_prog, tag | (unsigned long long)c);
-                    st_relaxed_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s));
-                }
-                if (nok == 32) {                           // the prefetched batch is the next one, same exponent
-                    curA = nxtA; curB = nxtB; cur_rdy = nxt_rdy; fl_next = fl_next2;
-                    continue;
-                }
-                pre_valid = false;
                 if (nok < nready) {                        // chunk c needs the exact path
                     if (nok >= nusable) ++n_stale; else ++n_range;
                     stop = true;
                 }
             }
             if (lane == 0) {
+                stop_sh = 1;
                 s_sh = s; c_sh = c;
                 unsigned *stt = pd.stats + 8 * job;
                 stt[0] += n_fast; stt[2] += n_timeout; stt[3] += n_stale; stt[4] += n_range;
+                stt[7] += (unsigned)(clk_wait >> 10); clk_wait = 0;
+            }
+        } else if (warp <= PC_FETCH) {
+            // ---- fetch warp: batches b = warp - 1 (mod PC_FETCH) of 32 chunks; every lane polls the ready
+            // word of its chunk and copies the three candidate records into the ring slot.  Stateless:
+            // what is already in the ring is told by the tags, what is no longer wanted by cpos_sh. ----
+            const int fj = warp - 1;
+            const unsigned want = launch_id << 8;
+            long b = -1;
+            while (stop_sh == 0) {
+                const long cp = cpos_sh;
+                const long bmin = cp / 32;
+                if (b < bmin) b = bmin + (((long)fj - bmin) % PC_FETCH + PC_FETCH) % PC_FETCH;
+                if (b * 32 >= nchunks || b * 32 + 32 > cp + PC_RING) { __nanosleep(64); continue; }
+                const long k = b * 32 + lane;
+                const int slot = (int)(k % PC_RING);
+                bool have = k >= nchunks || k < cp || ring_tag[slot] == (int)(k + 1);
+                if (!have) {
+                    const unsigned fl = ld_acquire_u32(ready + k);
+                    if ((fl & 0xffffff00u) == want) {
+                        const int4 *src = reinterpret_cast<const int4 *>(rec + k * 3);
+                        int4 r[6];
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) r[i] = __ldcg(src + i);
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) ring[slot][i] = r[i];
+                        ring_e[slot] = (int)(fl & 0xffu);
+                        __threadfence_block();
+                        ring_tag[slot] = (int)(k + 1);
+                        have = true;
+                    }
+                }
+                if (__all_sync(0xffffffffu, have)) b += PC_FETCH;
             }
         }
         __syncthreads();
         const long c = c_sh;
         const float s = s_sh;
         if (c >= nchunks) break;
+        const long long clk_e0 = clock64();
         // ---- exact path for chunk c: the whole CTA summarises it for the true exponent; if the
         // exponent changes inside the chunk, the remaining rows are summarised again ----
         float t[4];
         load_terms(J, c * PC_CHUNK + 4 * tid, t);
         *reinterpret_cast<float4 *>(tbuf + 4 * tid) = make_float4(t[0], t[1], t[2], t[3]);
-        int w0 = 0;
+        int w0 = 0, rounds = 0;
         float sc = s;
         for (;;) {
             SeqCtx cx;
             const bool ctx_ok = seq_ctx_make(sc, &cx);
-            if (ctx_ok && warp >= w0) {
+            ++rounds;
+            if (ctx_ok && warp >= w0 && rounds <= SEQ_MAX_ROUNDS) {
                 bool bad = false, tie = false;
                 SeqSum v = lane_summary<4>(cx, t, &bad, &tie);
                 const bool wbad = __any_sync(0xffffffffu, bad), wtie = __any_sync(0xffffffffu, tie);
@@ -658,7 +711,7 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
             __syncthreads();
             if (warp == 0) {
                 float s_new = sc;
-                const int next = walk_chunk(s_new, w0, ctx_ok, wsum[0][0], wflag[0][0], tbuf);
+                const int next = walk_chunk(s_new, w0, ctx_ok, rounds > SEQ_MAX_ROUNDS, wsum[0][0], wflag[0][0], tbuf);
                 if (lane == 0) { s_sh = s_new; e_sh = next; }
             }
             __syncthreads();
@@ -668,6 +721,8 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
         }
         if (tid == 0) {
             c_sh = c + 1;
+            cpos_sh = c + 1; stop_sh = 0;                  // the fetch warps resume behind the next barrier
+            clk_exact += clock64() - clk_e0;
             pd.stats[8 * job + 1] += 1u;
             st_release_u64(st_prog, tag | (unsigned long long)(c + 1));
             st_release_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(sc));
@@ -675,6 +730,10 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
         __syncthreads();
     }
 
+    if (tid == 0) {
+        pd.stats[8 * job + 5] += (unsigned)((clock64() - clk_begin) >> 10);
+        pd.stats[8 * job + 6] += (unsigned)(clk_exact >> 10);
+    }
     float s = s_sh;
     if (J.fxsite) {                                        // as in seqsum_kernel
         for (int i0 = 0; i0 < J.L; i0 += PC_CHUNK) {
@@ -751,7 +810,39 @@ void seqsum_pipe_destroy(SeqPipe *p)
     delete p;
 }
 
+static int seqsum_launch_impl(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st, SeqPipe *pipe);
+
+// DCA_B200_SEQSUM_TIMING=1 (measurements only): every launch is bracketed by CUDA events and a
+// synchronisation; per (first output slot, job count) the accumulated time goes to stderr.
 int seqsum_launch(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st, SeqPipe *pipe)
+{
+    static const bool timing = getenv("DCA_B200_SEQSUM_TIMING") != nullptr;
+    if (!timing) return seqsum_launch_impl(jobs, njobs, d_out, st, pipe);
+    static double acc_ms[32][SEQ_MAX_JOBS + 1];
+    static long acc_n[32][SEQ_MAX_JOBS + 1];
+    static long calls = 0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    const int rc = seqsum_launch_impl(jobs, njobs, d_out, st, pipe);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const int slot = jobs[0].out & 31;
+    acc_ms[slot][njobs] += ms; acc_n[slot][njobs] += 1;
+    if (++calls % 100 == 0) {
+        fprintf(stderr, "[seqsum timing] after %ld launches:", calls);
+        for (int a = 0; a < 32; ++a)
+            for (int b = 1; b <= SEQ_MAX_JOBS; ++b)
+                if (acc_n[a][b]) fprintf(stderr, " out%d x%d: %ld x %.3f ms;", a, b, acc_n[a][b], acc_ms[a][b] / acc_n[a][b]);
+        fprintf(stderr, "\n");
+    }
+    return rc;
+}
+
+static int seqsum_launch_impl(const SeqJob *jobs, int njobs, float *d_out, cudaStream_t st, SeqPipe *pipe)
 {
     if (njobs < 1 || njobs > SEQ_MAX_JOBS) { set_error("seqsum_launch: %d jobs (1..%d)", njobs, SEQ_MAX_JOBS); return -1; }
     SeqLaunch l{};
