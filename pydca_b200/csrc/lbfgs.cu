@@ -1005,7 +1005,7 @@ done:
         unsigned stt[8 * SEQ_MAX_JOBS] = {0};
         if (seqsum_pipe_stats(D.pipe, stt, st) == 0)
             for (int j = 0; j < SEQ_MAX_JOBS; ++j)
-                fprintf(stderr, "[dca trace] seqsum job slot %d: %u chunks from records, %u exact, %u time-outs, %u stale, %u range; consumer kcycles %u total, %u exact path, %u waiting\n",
+                fprintf(stderr, "[dca trace] seqsum job slot %d: %u chunks from records, %u exact, %u time-outs, %u stale, %u range; consumer kcycles %u total, %u exact path; %u chunks by the row walk\n",
                         j, stt[8 * j], stt[8 * j + 1], stt[8 * j + 2], stt[8 * j + 3], stt[8 * j + 4], stt[8 * j + 5], stt[8 * j + 6], stt[8 * j + 7]);
     }
     if (!warm_marked) { cudaEventRecord(evw, st); cudaStreamSynchronize(st); evals_at_warm = D.evals; }

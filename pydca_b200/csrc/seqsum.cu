@@ -304,10 +304,11 @@ struct SeqPipeDev {
     unsigned long long *state;                 // [jobs][2]: (launch << 32) | progress, (launch << 32) | exponent field
     unsigned *ready;                           // [jobs][maxchunks] = (launch id << 8) | middle candidate's exponent, once the records are written
     SeqRec *rec;                               // [jobs][maxchunks][3]
+    int4 *rowrec;                              // [jobs][maxchunks][3][32 rows][2]: the row (128-term) summaries behind each record + flags
     double *csum;                              // [jobs][maxchunks] float64 sums of the chunks' terms (pre-pass)
     int *epred;                                // [jobs][maxchunks] exponent field predicted for the running value entering chunk c (0: none)
     unsigned *ticket;                          // [jobs] arrival counter of the pre-pass
-    unsigned *stats;                           // [jobs][8]: chunks applied from records, chunks done exactly, ready time-outs, stale records, failed range checks
+    unsigned *stats;                           // [jobs][8]: chunks applied from records, chunks done by the CTA's exact path, ready time-outs, stale records, failed range checks, consumer kcycles (total, exact path), chunks done by the row walk
     long maxchunks;
 };
 
@@ -315,10 +316,10 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
 {
     asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
 {
     unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
@@ -426,6 +427,68 @@ __device__ int walk_chunk(float &s, int w0, bool ctx_ok, bool all_serial, const 
     return SQ_WARPS;
 }
 
+// The chain warp's own way through a chunk whose record does not fit (typically: the running value
+// crosses a binade inside it), from the producers' ROW summaries: lane l holds row l for the candidate
+// of the current exponent; the rows from w on are composed by a warp scan and the leading ones that
+// fit are applied in one integer addition; the first row that does not fit goes through the plain
+// chain (its 128 terms are loaded here); then the same again from the next row with the candidate
+// of the exponent reached.  No barrier, no re-summarising.  false (s untouched): a candidate is
+// missing, the integer picture does not apply, or the exponent keeps changing -- the CTA's exact
+// path does the chunk.
+__device__ bool row_walk(float &s_io, const SeqJob &J, long c, int e_mid, const int4 *rows, float *scratch)
+{
+    const int lane = threadIdx.x & 31;
+    if (e_mid == 0) return false;
+    int4 A = make_int4(0, 0, 0, 0), B = make_int4(0, 0, 1, 0);
+    int have = -1;                                         // candidate held in A, B
+    float s = s_io;
+    int w = 0, changes = 0;
+    while (w < SQ_WARPS) {
+        SeqCtx cc;
+        if (!seq_ctx_make(s, &cc)) return false;
+        const int ef = exp_field(s);
+        const int idx = ef - (e_mid - 1);
+        if (idx < 0 || idx > 2) return false;
+        if (idx != have) {                                 // on entry and after a change of exponent
+            A = __ldcg(rows + (idx * 32 + lane) * 2);
+            B = __ldcg(rows + (idx * 32 + lane) * 2 + 1);
+            have = idx;
+        }
+        SeqSum v;
+        int bad = 0;
+        if (lane < w) {                                    // rows already done: neutral element of seq_compose
+            v.total[0] = v.total[1] = 0; v.pmin[0] = v.pmin[1] = SEQ_SAT; v.pmax[0] = v.pmax[1] = -SEQ_SAT;
+        } else {
+            v.total[0] = A.x; v.total[1] = A.y; v.pmin[0] = A.z; v.pmin[1] = A.w; v.pmax[0] = B.x; v.pmax[1] = B.y;
+            bad = B.z & 1;
+        }
+        const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);
+        const int nusable = (badmask == 0u) ? 32 : (__ffs(badmask) - 1);
+        v = warp_scan(v, true);
+        const int p = cc.M & 1;
+        const bool okl = lane < w || (lane < nusable && seq_block_ok(cc, v.pmin[p], v.pmax[p]));
+        const unsigned okmask = __ballot_sync(0xffffffffu, okl);
+        const int nok = (okmask == 0xffffffffu) ? 32 : (__ffs(~okmask) - 1);
+        if (nok > w) {
+            const int total = __shfl_sync(0xffffffffu, v.total[p], nok - 1);
+            s = seq_apply(cc, total);
+            w = nok;
+            if (w >= SQ_WARPS) break;
+        }
+        float t[4];
+        load_terms(J, c * PC_CHUNK + (long)w * 128 + 4 * lane, t);
+        __syncwarp();
+        *reinterpret_cast<float4 *>(scratch + 4 * lane) = make_float4(t[0], t[1], t[2], t[3]);
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 4; ++h) s = serial32(s, scratch + h * 32);
+        ++w;
+        if (exp_field(s) != ef && ++changes > SEQ_MAX_ROUNDS) return false;
+    }
+    s_io = s;
+    return true;
+}
+
 // Pre-pass: float64 sum of every chunk's terms; the last CTA of a job turns them into the
 // exponent the running value is EXPECTED to have when it enters each chunk (exclusive prefix,
 // rounded to float).  The sequential float32 value drifts away from this (stagnation), which
@@ -507,6 +570,7 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
     unsigned long long *st_prog = pd.state + 2 * job, *st_exp = pd.state + 2 * job + 1;
     unsigned *ready = pd.ready + (size_t)job * pd.maxchunks;
     SeqRec *rec = pd.rec + (size_t)job * pd.maxchunks * 3;
+    int4 *rowrec = pd.rowrec + (size_t)job * pd.maxchunks * 3 * 64;
     const unsigned long long tag = (unsigned long long)launch_id << 32;
 
     if (role > 0) {
@@ -519,19 +583,27 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
         float tn[4];
         long c = role - 1;
         if (c < nchunks) load_terms(J, c * PC_CHUNK + warp * 128 + 4 * lane, tn);
+        // The consumer's hints (relaxed loads: they are hints) and the predictions are read one chunk
+        // ahead by thread 0, so that none of these round trips sits between two barriers.
+        unsigned long long a_n = 0, b_n = 0;
+        int ep_n = 0, et_n = 0;
+        long prog_n = 0;
+        auto decode_prog = [&](unsigned long long a) -> long { return ((a >> 32) == launch_id) ? (long)(a & 0xffffffffu) : 0; };
+        if (tid == 0 && c < nchunks) {
+            a_n = ld_relaxed_u64(st_prog); b_n = ld_relaxed_u64(st_exp); ep_n = __ldcg(epred + c);
+            prog_n = decode_prog(a_n);
+            et_n = (prog_n > 0 && prog_n < nchunks) ? __ldcg(epred + prog_n) : 0;
+        }
         for (; c < nchunks; c += P, buf ^= 1) {
             float t[4] = {tn[0], tn[1], tn[2], tn[3]};
             if (c + P < nchunks) load_terms(J, (c + P) * PC_CHUNK + warp * 128 + 4 * lane, tn);      // next chunk in flight
             if (tid == 0) {
-                const unsigned long long a = ld_acquire_u64(st_prog), b = ld_acquire_u64(st_exp);
-                const long prog = ((a >> 32) == launch_id) ? (long)(a & 0xffffffffu) : 0;
-                const int e_seen = ((b >> 32) == launch_id) ? (int)(b & 0xffffffffu) : 0;
-                int e = __ldcg(epred + c);
-                if (e != 0 && e_seen != 0 && prog > 0 && prog < nchunks) {
-                    const int e_there = __ldcg(epred + prog);
-                    if (e_there != 0) e += e_seen - e_there;
-                }
+                const long prog = prog_n;
+                const int e_seen = ((b_n >> 32) == launch_id) ? (int)(b_n & 0xffffffffu) : 0;
+                int e = ep_n;
+                if (e != 0 && e_seen != 0 && prog > 0 && prog < nchunks && et_n != 0) e += e_seen - et_n;
                 e_sh = e; skip_sh = (prog > c) ? 1 : 0;                    // the consumer did this chunk itself
+                if (c + P < nchunks) { a_n = ld_relaxed_u64(st_prog); b_n = ld_relaxed_u64(st_exp); ep_n = __ldcg(epred + c + P); }
             }
             __syncthreads();
             const int e = e_sh;
@@ -552,9 +624,18 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                 }
             }
             __syncthreads();
+            if (tid == 0 && c + P < nchunks) {             // the hint words have arrived: prediction at the consumer's position
+                prog_n = decode_prog(a_n);
+                et_n = (prog_n > 0 && prog_n < nchunks) ? __ldcg(epred + prog_n) : 0;
+            }
             if (!skip && warp < 3) {
                 SeqSum v = wsum[buf][warp][lane];
                 const int fl = wflag[buf][warp][lane];
+                {   // the row summaries themselves, for the consumer's walk through a chunk whose record does not fit
+                    int4 *dst = rowrec + ((c * 3 + warp) * 32 + lane) * 2;
+                    dst[0] = make_int4(v.total[0], v.total[1], v.pmin[0], v.pmin[1]);
+                    dst[1] = make_int4(v.pmax[0], v.pmax[1], fl, 0);
+                }
                 const bool anybad = __any_sync(0xffffffffu, (fl & 1) != 0);
                 v = warp_scan(v, __any_sync(0xffffffffu, (fl & 2) != 0));
                 if (lane == 31) {
@@ -575,7 +656,7 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
     for (int i = tid; i < PC_RING; i += SQ_THREADS) ring_tag[i] = 0;
     __syncthreads();
     const long long clk_begin = clock64();
-    long long clk_exact = 0, clk_wait = 0;
+    long long clk_exact = 0;
     for (;;) {
         if (warp == 0) {
             // ---- fast-forward over the producers' records, 32 chunks per step ----
@@ -588,7 +669,7 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
             float s = s_sh;
             long c = c_sh;
             bool stop = false;
-            unsigned n_fast = 0, n_timeout = 0, n_stale = 0, n_range = 0;
+            unsigned n_fast = 0, n_timeout = 0, n_stale = 0, n_range = 0, n_rows = 0;
             while (c < nchunks && !stop) {
                 SeqCtx cc;
                 if (!seq_ctx_make(s, &cc)) break;
@@ -604,7 +685,6 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                     while (clock64() - t0 < 40000) {
                         if (ring_tag[(int)(c % PC_RING)] == (int)(c + 1)) { ok = true; break; }
                     }
-                    clk_wait += clock64() - t0;
                     if (!ok) { ++n_timeout; stop = true; }
                     continue;
                 }
@@ -640,9 +720,17 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                         st_relaxed_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s));
                     }
                 }
-                if (nok < nready) {                        // chunk c needs the exact path
+                if (nok < nready) {                        // the record of chunk c does not fit
                     if (nok >= nusable) ++n_stale; else ++n_range;
-                    stop = true;
+                    const int e_mid = ring_e[(int)(c % PC_RING)];
+                    if (row_walk(s, J, c, e_mid, rowrec + c * 3 * 64, tbuf)) {
+                        ++c; ++n_rows;
+                        if (lane == 0) {
+                            cpos_sh = c;
+                            st_relaxed_u64(st_prog, tag | (unsigned long long)c);
+                            st_relaxed_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s));
+                        }
+                    } else stop = true;                    // the CTA's exact path
                 }
             }
             if (lane == 0) {
@@ -650,7 +738,7 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                 s_sh = s; c_sh = c;
                 unsigned *stt = pd.stats + 8 * job;
                 stt[0] += n_fast; stt[2] += n_timeout; stt[3] += n_stale; stt[4] += n_range;
-                stt[7] += (unsigned)(clk_wait >> 10); clk_wait = 0;
+                stt[7] += n_rows;
             }
         } else if (warp <= PC_FETCH) {
             // ---- fetch warp: batches b = warp - 1 (mod PC_FETCH) of 32 chunks; every lane polls the ready
@@ -778,11 +866,12 @@ SeqPipe *seqsum_pipe_create(long nmax)
     p->dev.state = static_cast<unsigned long long *>(dev_alloc(sizeof(unsigned long long) * 2 * SEQ_MAX_JOBS));
     p->dev.ready = static_cast<unsigned *>(dev_alloc(sizeof(unsigned) * nrec));
     p->dev.rec = static_cast<SeqRec *>(dev_alloc(sizeof(SeqRec) * 3 * nrec));
+    p->dev.rowrec = static_cast<int4 *>(dev_alloc(sizeof(int4) * 3 * 64 * nrec));
     p->dev.stats = static_cast<unsigned *>(dev_alloc(sizeof(unsigned) * 8 * SEQ_MAX_JOBS));
     p->dev.csum = static_cast<double *>(dev_alloc(sizeof(double) * nrec));
     p->dev.epred = static_cast<int *>(dev_alloc(sizeof(int) * nrec));
     p->dev.ticket = static_cast<unsigned *>(dev_alloc(sizeof(unsigned) * SEQ_MAX_JOBS));
-    if (!p->dev.state || !p->dev.ready || !p->dev.rec || !p->dev.stats || !p->dev.csum || !p->dev.epred || !p->dev.ticket ||
+    if (!p->dev.state || !p->dev.ready || !p->dev.rec || !p->dev.rowrec || !p->dev.stats || !p->dev.csum || !p->dev.epred || !p->dev.ticket ||
         cudaMemset(p->dev.ticket, 0, sizeof(unsigned) * SEQ_MAX_JOBS) != cudaSuccess ||
         cudaMemset(p->dev.stats, 0, sizeof(unsigned) * 8 * SEQ_MAX_JOBS) != cudaSuccess ||
         cudaMemset(p->dev.state, 0, sizeof(unsigned long long) * 2 * SEQ_MAX_JOBS) != cudaSuccess ||
@@ -805,7 +894,7 @@ int seqsum_pipe_stats(SeqPipe *p, unsigned *out, cudaStream_t st)
 void seqsum_pipe_destroy(SeqPipe *p)
 {
     if (!p) return;
-    dev_free(p->dev.state); dev_free(p->dev.ready); dev_free(p->dev.rec); dev_free(p->dev.stats);
+    dev_free(p->dev.state); dev_free(p->dev.ready); dev_free(p->dev.rec); dev_free(p->dev.rowrec); dev_free(p->dev.stats);
     dev_free(p->dev.csum); dev_free(p->dev.epred); dev_free(p->dev.ticket);
     delete p;
 }
