@@ -116,8 +116,9 @@ int dca_set_arithmetic(int mode);
  * the first n0 entries and lambda1 on the rest (y == NULL). */
 int dca_seq_sum(const float *x, const float *y, long n, long n0, float lambda0, float lambda1, float *out);
 /* the same with the CUDA-event time of one (warm) launch and the pipeline's counters: stats8 =
- * {chunks applied from producer records, chunks done exactly by the consumer CTA, ready
- * time-outs, stale / unusable records, failed prefix-range checks, 0, 0, 0} */
+ * {chunks applied from producer records, chunks done by the consumer CTA's exact path, ready
+ * time-outs, stale / unusable records, failed prefix-range checks, consumer kilocycles (total,
+ * exact path), chunks walked by the chain warp from the producers' row summaries} */
 int dca_seq_sum_stats(const float *x, const float *y, long n, long n0, float lambda0, float lambda1,
                       float *out, unsigned *stats8, float *kernel_ms);
 /* initial point, PlmDCA::initFieldsAndCouplings (plmdca_numerics.cpp:207-249) */

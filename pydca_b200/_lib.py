@@ -460,8 +460,8 @@ def seq_dot_stats(x, y):
     st = np.zeros(8, dtype=np.uint32)
     check(lib().dca_seq_sum_stats(ptr(x, _f32p), ptr(y, _f32p), x.size, 0, 0.0, 0.0, ctypes.byref(out),
                                   ptr(st, _u32p), ctypes.byref(ms)), "dca_seq_sum_stats")
-    keys = ("from_records", "exact", "timeouts", "stale", "range")
-    return np.float32(out.value), ms.value, dict(zip(keys, st[:5].tolist()))
+    keys = ("from_records", "exact", "timeouts", "stale", "range", "kcycles", "kcycles_exact", "row_walks")
+    return np.float32(out.value), ms.value, dict(zip(keys, st.tolist()))
 
 
 def seq_reg(x, n0, lambda0, lambda1):

@@ -322,6 +322,16 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int lds_acquire_cta(const volatile int *p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];\n" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(const_cast<const int *>(p))) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_release_cta(volatile int *p, int v)
+{
+    asm volatile("st.release.cta.shared.s32 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(const_cast<int *>(p))), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
@@ -374,44 +384,46 @@ __device__ __forceinline__ int exp_field(float s)           // 0 when the intege
     return (ef < 40 || ef > 214) ? 0 : ef;
 }
 
-// warp 0 of the consumer: rows [w0, 32) of the chunk in tbuf from running value s, exactly.  The
-// warp summaries were made for the exponent s has on entry.  Lane l takes row w + l: the row
-// summaries are composed by a warp scan (both parities) and the range check of the composed
-// prefixes says how many leading rows can be applied in ONE integer addition -- as long as it
-// holds the exponent cannot change.  The first row that does not fit goes through the plain
-// chain (128 dependent adds: ~600 cycles, cheaper than any finer speculation); if that changed
-// the exponent the walk returns the next row so that the whole CTA can re-summarise the rest for
-// the new exponent (returns 32 when the chunk is done).  all_serial: the exponent has already
-// changed several times inside this chunk -- the rest is done by the plain chain.
-__device__ int walk_chunk(float &s, int w0, bool ctx_ok, bool all_serial, const SeqSum *wsum, const int *wflag,
+// warp 0 of the consumer CTA: the chunk in tbuf from running value s, exactly.  Every row (128
+// terms) was summarised for the three exponents around the one the running value is PREDICTED to
+// have on entering it (float64 prefix of the row sums).  Lane l takes row l; the rows from w on
+// that have a candidate for the current exponent are composed by a warp scan (both parities) and
+// the range check of the composed prefixes says how many leading rows can be applied in ONE
+// integer addition -- as long as it holds the exponent cannot change.  The first row that does not
+// fit goes through the plain chain (128 dependent adds: ~600 cycles, cheaper than any finer
+// speculation), then the same again from the next row with the exponent reached: one pass through
+// the chunk however often the running value changes its binade (a sum starts from 0 and crosses
+// half a dozen in its first chunk).
+__device__ __noinline__ void walk_rows(float &s, const SeqSum (*ws)[SQ_WARPS], const int (*wf)[SQ_WARPS], const int *erow,
                           const float *tbuf)
 {
     const int lane = threadIdx.x & 31;
-    SeqCtx c0;
-    const bool usable = !all_serial && ctx_ok && seq_ctx_make(s, &c0);
-    int w = w0;
+    int w = 0;
     while (w < SQ_WARPS) {
-        if (usable) {
-            SeqCtx cc;
-            seq_ctx_make(s, &cc);                              // same binade as c0: every applied block keeps it
-            const int row = w + lane;
-            const bool valid = row < SQ_WARPS;
+        SeqCtx cc;
+        if (seq_ctx_make(s, &cc)) {
+            const int ef = exp_field(s);
             SeqSum v;
-            v.total[0] = v.total[1] = v.pmin[0] = v.pmin[1] = v.pmax[0] = v.pmax[1] = 0;
             int bad = 0;
-            if (valid) { v = wsum[row]; bad = wflag[row] & 1; }
+            if (lane < w) {                                // rows already done: neutral element of seq_compose
+                v.total[0] = v.total[1] = 0; v.pmin[0] = v.pmin[1] = SEQ_SAT; v.pmax[0] = v.pmax[1] = -SEQ_SAT;
+            } else {
+                const int em = erow[lane];
+                const int idx = ef - (em - 1);
+                if (em != 0 && idx >= 0 && idx <= 2) { v = ws[idx][lane]; bad = wf[idx][lane] & 1; }
+                else { v.total[0] = v.total[1] = v.pmin[0] = v.pmin[1] = v.pmax[0] = v.pmax[1] = 0; bad = 1; }
+            }
             const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);
             const int nusable = (badmask == 0u) ? 32 : (__ffs(badmask) - 1);
             v = warp_scan(v, true);
             const int p = cc.M & 1;
-            const bool okl = !valid || (lane < nusable && seq_block_ok(cc, v.pmin[p], v.pmax[p]));
+            const bool okl = lane < w || (lane < nusable && seq_block_ok(cc, v.pmin[p], v.pmax[p]));
             const unsigned okmask = __ballot_sync(0xffffffffu, okl);
-            int nok = (okmask == 0xffffffffu) ? 32 : (__ffs(~okmask) - 1);
-            nok = min(nok, SQ_WARPS - w);
-            if (nok > 0) {
+            const int nok = (okmask == 0xffffffffu) ? 32 : (__ffs(~okmask) - 1);
+            if (nok > w) {
                 const int total = __shfl_sync(0xffffffffu, v.total[p], nok - 1);
                 s = seq_apply(cc, total);
-                w += nok;
+                w = nok;
                 if (w >= SQ_WARPS) break;
             }
         }
@@ -419,12 +431,26 @@ __device__ int walk_chunk(float &s, int w0, bool ctx_ok, bool all_serial, const 
 #pragma unroll
         for (int h = 0; h < 4; ++h) s = serial32(s, tbuf + w * 128 + h * 32);
         ++w;
-        if (all_serial) continue;
-        SeqCtx cn;
-        const bool same = usable && seq_ctx_make(s, &cn) && cn.scale == c0.scale;
-        if (!same && w < SQ_WARPS && seq_ctx_make(s, &cn)) return w;      // re-summarise the rest
     }
-    return SQ_WARPS;
+}
+
+// summaries of this warp's row (4 terms per lane) for the exponent fields e - 1, e, e + 1 (e = 0: none)
+__device__ __forceinline__ void summarise_row3(int e, const float *t, SeqSum (*ws)[SQ_WARPS], int (*wf)[SQ_WARPS])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int ef = e - 1 + k;
+        SeqCtx cx;
+        cx.M = 0; cx.u = 0.f;
+        const bool valid = (e != 0 && ef >= 40 && ef <= 214);
+        cx.scale = seq_from_bits((uint32_t)(277 - (valid ? ef : 127)) << 23);      // 2^(23 - (ef - 127))
+        bool bad = !valid, tie = false;
+        SeqSum v = lane_summary<4>(cx, t, &bad, &tie);
+        const bool wbad = __any_sync(0xffffffffu, bad), wtie = __any_sync(0xffffffffu, tie);
+        v = warp_summary(v, wtie);
+        if (lane == 31) { ws[k][warp] = v; wf[k][warp] = (wbad ? 1 : 0) | (wtie ? 2 : 0); }
+    }
 }
 
 // The chain warp's own way through a chunk whose record does not fit (typically: the running value
@@ -435,7 +461,7 @@ __device__ int walk_chunk(float &s, int w0, bool ctx_ok, bool all_serial, const 
 // of the exponent reached.  No barrier, no re-summarising.  false (s untouched): a candidate is
 // missing, the integer picture does not apply, or the exponent keeps changing -- the CTA's exact
 // path does the chunk.
-__device__ bool row_walk(float &s_io, const SeqJob &J, long c, int e_mid, const int4 *rows, float *scratch)
+__device__ __noinline__ bool row_walk(float &s_io, const SeqJob &J, long c, int e_mid, const int4 *rows, float *scratch)
 {
     const int lane = threadIdx.x & 31;
     if (e_mid == 0) return false;
@@ -556,11 +582,13 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
     __shared__ float s_sh;
     __shared__ long c_sh;
     __shared__ int e_sh, skip_sh;
+    __shared__ double rowsum_sh[SQ_WARPS];                 // consumer's exact path: float64 row sums and
+    __shared__ int erow_sh[SQ_WARPS];                      // the exponent field predicted on entering each row
     // consumer only: ring of fetched records (three candidates per chunk), filled by the fetch warps
     __shared__ int4 ring[PC_RING][6];
     __shared__ volatile int ring_tag[PC_RING];             // chunk index + 1 once the slot holds that chunk
     __shared__ volatile int ring_e[PC_RING];               // exponent field of the chunk's middle candidate
-    __shared__ volatile long cpos_sh;                      // the chain warp's position
+    __shared__ volatile unsigned long long posexp_sh;      // the chain warp's position (low word) and the exponent field of its running value (high word)
     __shared__ volatile int stop_sh;                       // the chain warp has left the fast-forward loop
 
     const int job = blockIdx.x / (P + 1), role = blockIdx.x % (P + 1);
@@ -608,21 +636,7 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
             __syncthreads();
             const int e = e_sh;
             const bool skip = skip_sh != 0;
-            if (!skip) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int ef = e - 1 + k;
-                    SeqCtx cx;
-                    cx.M = 0; cx.u = 0.f;
-                    const bool valid = (e != 0 && ef >= 40 && ef <= 214);
-                    cx.scale = seq_from_bits((uint32_t)(277 - (valid ? ef : 127)) << 23);      // 2^(23 - (ef - 127))
-                    bool bad = !valid, tie = false;
-                    SeqSum v = lane_summary<4>(cx, t, &bad, &tie);
-                    const bool wbad = __any_sync(0xffffffffu, bad), wtie = __any_sync(0xffffffffu, tie);
-                    v = warp_summary(v, wtie);
-                    if (lane == 31) { wsum[buf][k][warp] = v; wflag[buf][k][warp] = (wbad ? 1 : 0) | (wtie ? 2 : 0); }
-                }
-            }
+            if (!skip) summarise_row3(e, t, wsum[buf], wflag[buf]);
             __syncthreads();
             if (tid == 0 && c + P < nchunks) {             // the hint words have arrived: prediction at the consumer's position
                 prog_n = decode_prog(a_n);
@@ -652,7 +666,7 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
     }
 
     // ================= consumer =================
-    if (tid == 0) { s_sh = 0.f; c_sh = 0; cpos_sh = 0; stop_sh = 0; st_release_u64(st_prog, tag); st_release_u64(st_exp, tag); }
+    if (tid == 0) { s_sh = 0.f; c_sh = 0; posexp_sh = 0ull; stop_sh = 0; st_release_u64(st_prog, tag); st_release_u64(st_exp, tag); }
     for (int i = tid; i < PC_RING; i += SQ_THREADS) ring_tag[i] = 0;
     __syncthreads();
     const long long clk_begin = clock64();
@@ -676,19 +690,18 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                 const int ef = exp_field(s);
                 const long k = c + lane;
                 const int slot = (int)(k % PC_RING);
-                const bool rdy = k < nchunks && ring_tag[slot] == (int)(k + 1);
+                const bool rdy = k < nchunks && lds_acquire_cta(&ring_tag[slot]) == (int)(k + 1);      // tag before data
                 const unsigned rmask = __ballot_sync(0xffffffffu, rdy);
                 const int nready = (rmask == 0xffffffffu) ? 32 : (__ffs(~rmask) - 1);
                 if (nready == 0) {
                     bool ok = false;
                     const long long t0 = clock64();
                     while (clock64() - t0 < 40000) {
-                        if (ring_tag[(int)(c % PC_RING)] == (int)(c + 1)) { ok = true; break; }
+                        if (lds_acquire_cta(&ring_tag[(int)(c % PC_RING)]) == (int)(c + 1)) { ok = true; break; }
                     }
                     if (!ok) { ++n_timeout; stop = true; }
                     continue;
                 }
-                __threadfence_block();                     // tag before data (the fetch warp fenced the other way round)
                 SeqSum v;
                 v.total[0] = v.total[1] = v.pmin[0] = v.pmin[1] = v.pmax[0] = v.pmax[1] = 0;
                 int bad = 1;
@@ -714,22 +727,15 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                     s = seq_apply(cc, total);
                     c += nok;
                     n_fast += (unsigned)nok;
-                    if (lane == 0) {
-                        cpos_sh = c;                       // frees the ring slots behind c
-                        st_relaxed_u64(st_prog, tag | (unsigned long long)c);      // hints for the producers
-                        st_relaxed_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s));
-                    }
+                    // frees the ring slots behind c; fetch warp 0 forwards it to the producers as their hint
+                    if (lane == 0) posexp_sh = ((unsigned long long)(unsigned)exp_field(s) << 32) | (unsigned long long)c;
                 }
                 if (nok < nready) {                        // the record of chunk c does not fit
                     if (nok >= nusable) ++n_stale; else ++n_range;
                     const int e_mid = ring_e[(int)(c % PC_RING)];
                     if (row_walk(s, J, c, e_mid, rowrec + c * 3 * 64, tbuf)) {
                         ++c; ++n_rows;
-                        if (lane == 0) {
-                            cpos_sh = c;
-                            st_relaxed_u64(st_prog, tag | (unsigned long long)c);
-                            st_relaxed_u64(st_exp, tag | (unsigned long long)(unsigned)exp_field(s));
-                        }
+                        if (lane == 0) posexp_sh = ((unsigned long long)(unsigned)exp_field(s) << 32) | (unsigned long long)c;
                     } else stop = true;                    // the CTA's exact path
                 }
             }
@@ -743,12 +749,19 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
         } else if (warp <= PC_FETCH) {
             // ---- fetch warp: batches b = warp - 1 (mod PC_FETCH) of 32 chunks; every lane polls the ready
             // word of its chunk and copies the three candidate records into the ring slot.  Stateless:
-            // what is already in the ring is told by the tags, what is no longer wanted by cpos_sh. ----
+            // what is already in the ring is told by the tags, what is no longer wanted by posexp_sh. ----
             const int fj = warp - 1;
             const unsigned want = launch_id << 8;
             long b = -1;
+            unsigned long long pe_sent = ~0ull;
             while (stop_sh == 0) {
-                const long cp = cpos_sh;
+                const unsigned long long pe = posexp_sh;
+                const long cp = (long)(pe & 0xffffffffull);
+                if (fj == 0 && lane == 0 && pe != pe_sent) {       // hints for the producers: no ordering needed
+                    st_relaxed_u64(st_prog, tag | (pe & 0xffffffffull));
+                    st_relaxed_u64(st_exp, tag | (pe >> 32));
+                    pe_sent = pe;
+                }
                 const long bmin = cp / 32;
                 if (b < bmin) b = bmin + (((long)fj - bmin) % PC_FETCH + PC_FETCH) % PC_FETCH;
                 if (b * 32 >= nchunks || b * 32 + 32 > cp + PC_RING) { __nanosleep(64); continue; }
@@ -765,8 +778,7 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
 #pragma unroll
                         for (int i = 0; i < 6; ++i) ring[slot][i] = r[i];
                         ring_e[slot] = (int)(fl & 0xffu);
-                        __threadfence_block();
-                        ring_tag[slot] = (int)(k + 1);
+                        sts_release_cta(&ring_tag[slot], (int)(k + 1));      // data before tag
                         have = true;
                     }
                 }
@@ -778,38 +790,34 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
         const float s = s_sh;
         if (c >= nchunks) break;
         const long long clk_e0 = clock64();
-        // ---- exact path for chunk c: the whole CTA summarises it for the true exponent; if the
-        // exponent changes inside the chunk, the remaining rows are summarised again ----
+        // ---- exact path for chunk c: the whole CTA summarises its rows for the exponents the running
+        // value is predicted to have on entering each of them, warp 0 walks the rows ----
         float t[4];
         load_terms(J, c * PC_CHUNK + 4 * tid, t);
         *reinterpret_cast<float4 *>(tbuf + 4 * tid) = make_float4(t[0], t[1], t[2], t[3]);
-        int w0 = 0, rounds = 0;
-        float sc = s;
-        for (;;) {
-            SeqCtx cx;
-            const bool ctx_ok = seq_ctx_make(sc, &cx);
-            ++rounds;
-            if (ctx_ok && warp >= w0 && rounds <= SEQ_MAX_ROUNDS) {
-                bool bad = false, tie = false;
-                SeqSum v = lane_summary<4>(cx, t, &bad, &tie);
-                const bool wbad = __any_sync(0xffffffffu, bad), wtie = __any_sync(0xffffffffu, tie);
-                v = warp_summary(v, wtie);
-                if (lane == 31) { wsum[0][0][warp] = v; wflag[0][0][warp] = (wbad ? 1 : 0) | (wtie ? 2 : 0); }
-            }
-            __syncthreads();
-            if (warp == 0) {
-                float s_new = sc;
-                const int next = walk_chunk(s_new, w0, ctx_ok, rounds > SEQ_MAX_ROUNDS, wsum[0][0], wflag[0][0], tbuf);
-                if (lane == 0) { s_sh = s_new; e_sh = next; }
-            }
-            __syncthreads();
-            sc = s_sh;
-            w0 = e_sh;
-            if (w0 >= SQ_WARPS) break;
+        {
+            const double rs = warp_sum(((double)t[0] + (double)t[1]) + ((double)t[2] + (double)t[3]));
+            if (lane == 0) rowsum_sh[warp] = rs;
         }
+        __syncthreads();
+        {
+            const double pre = warp_sum((lane < warp) ? rowsum_sh[lane] : 0.0);
+            const int e_row = exp_field((float)((double)s + pre));
+            summarise_row3(e_row, t, wsum[0], wflag[0]);
+            if (lane == 0) erow_sh[warp] = e_row;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            float s_new = s;
+            walk_rows(s_new, wsum[0], wflag[0], erow_sh, tbuf);
+            if (lane == 0) s_sh = s_new;
+        }
+        __syncthreads();
+        const float sc = s_sh;
         if (tid == 0) {
             c_sh = c + 1;
-            cpos_sh = c + 1; stop_sh = 0;                  // the fetch warps resume behind the next barrier
+            posexp_sh = ((unsigned long long)(unsigned)exp_field(sc) << 32) | (unsigned long long)(c + 1);
+            stop_sh = 0;                                   // the fetch warps resume behind the next barrier
             clk_exact += clock64() - clk_e0;
             pd.stats[8 * job + 1] += 1u;
             st_release_u64(st_prog, tag | (unsigned long long)(c + 1));
