@@ -10,13 +10,16 @@
 // Two kernels.  seqsum_pipe_kernel (the one the optimiser uses) is a producer / consumer
 // pipeline per sum: P producer CTAs take the 4096-term chunks round-robin and reduce each to a
 // 32-byte record (total and prefix range, for both parities) for the THREE binades around the
-// exponent the consumer last published; one chain warp in the consumer CTA prefetches 32
-// records at a time and applies each in O(1) -- pick the candidate matching the running
-// value's exponent, check the prefix range against M, one integer addition.  A record that
-// does not fit (binade crossed twice since it was made, a prefix leaves the binade, a term
-// too large, running value 0) sends that one chunk through the exact in-CTA path below; a
-// bounded look-ahead keeps the producers from running far ahead of the exponent.  The
-// result is exact in every case; only the speed depends on the speculation.
+// exponent predicted for the running value there (pre-pass: float64 prefix of the chunk sums,
+// corrected by the drift the consumer publishes), and keep the 32 row summaries behind it.  In
+// the consumer CTA four fetch warps copy the records into a shared-memory ring as they become
+// ready; one chain warp applies 32 of them per step -- candidate matching the running value's
+// exponent, records composed by a warp scan, range check against M, one integer addition.  A
+// record that does not fit (binade crossed inside the chunk) is walked by the chain warp from
+// the row summaries, the one row that does not fit by the plain chain; what that cannot do (no
+// candidate for the exponent, running value 0: the first chunk of every sum) goes through the
+// exact in-CTA path below.  The result is exact in every case; only the speed depends on the
+// speculation.
 // seqsum_kernel is the single-CTA version (no speculation), kept as the fallback.
 //
 // One CTA per sum (the chain is serial; independent sums of one optimiser step run as
