@@ -193,6 +193,21 @@ def biomolecule_int(biomolecule):
     return 1 if biomolecule.strip().upper() == "PROTEIN" else 2
 
 
+class _HostBuffer:
+    """Owner of a host buffer handed out by the library (dca_free_host when the last user is gone)."""
+
+    def __init__(self, p):
+        self._p = p
+
+    def __del__(self):
+        if self._p:
+            try:
+                lib().dca_free_host(self._p)
+            except Exception:      # interpreter shutdown
+                pass
+            self._p = None
+
+
 # ---- thin array-level wrappers -----------------------------------------------
 def read_fasta(path, biomolecule, seqs_len):
     """uint8[N, L] unique sequences (states 0..q-1) in first-occurrence order."""
@@ -200,9 +215,11 @@ def read_fasta(path, biomolecule, seqs_len):
     n = lib().dca_read_fasta(os.fsencode(path), biomolecule_int(biomolecule), int(seqs_len), ctypes.byref(out))
     if n <= 0:
         raise DcaBackendError("reading %s failed: %s" % (path, last_error()))
-    arr = np.ctypeslib.as_array(out, shape=(n, int(seqs_len))).copy()
-    lib().dca_free_host(out)
-    return arr
+    # the library's buffer itself (no copy of the alignment), released with the last view of it
+    size = int(n) * int(seqs_len)
+    buf = (ctypes.c_uint8 * size).from_address(ctypes.addressof(out.contents))
+    buf._owner = _HostBuffer(ctypes.cast(out, ctypes.c_void_p))
+    return np.frombuffer(buf, dtype=np.uint8).reshape(int(n), int(seqs_len))
 
 
 def sequence_counts(msa, seqid, compare_f64=False, rows=None):

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <new>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #ifndef DCA_DEFAULT_ARITHMETIC
@@ -175,20 +176,34 @@ int dca_set_device(int device)
 
 unsigned long long dca_kernel_launches(void) { return g_launches.load(); }
 
+static std::mutex g_host_vec_mu;
+static std::unordered_map<void *, std::vector<uint8_t> *> g_host_vecs;      // buffers handed out by dca_read_fasta
+
 long dca_read_fasta(const char *msa_file, int biomolecule, int seqs_len, uint8_t **msa_out)
 {
     if (!msa_file || !msa_out || seqs_len <= 0) { set_error("dca_read_fasta: bad arguments"); return -1; }
-    std::vector<uint8_t> buf;
-    const long n = read_fasta_unique(msa_file, biomolecule, seqs_len, buf);
-    if (n <= 0) return n;
-    uint8_t *out = (uint8_t *)malloc(buf.size());
-    if (!out) { set_error("dca_read_fasta: out of memory"); return -1; }
-    memcpy(out, buf.data(), buf.size());
-    *msa_out = out;
+    // the reader's own buffer is handed out (no copy of the alignment); dca_free_host finds it again
+    auto *buf = new std::vector<uint8_t>();
+    const long n = read_fasta_unique(msa_file, biomolecule, seqs_len, *buf);
+    if (n <= 0) { delete buf; return n; }
+    {
+        std::lock_guard<std::mutex> lk(g_host_vec_mu);
+        g_host_vecs[buf->data()] = buf;
+    }
+    *msa_out = buf->data();
     return n;
 }
 
-void dca_free_host(void *p) { free(p); }
+void dca_free_host(void *p)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_host_vec_mu);
+        auto it = g_host_vecs.find(p);
+        if (it != g_host_vecs.end()) { delete it->second; g_host_vecs.erase(it); return; }
+    }
+    free(p);
+}
 
 int dca_weights(const uint8_t *msa, long num_seqs, int seqs_len, double seqid, int compare_f64,
                 long row_lo, long row_hi, uint32_t *counts_out)

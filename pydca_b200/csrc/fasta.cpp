@@ -19,7 +19,16 @@
 #include <cctype>
 #include <cstdio>
 #include <string>
+#include <algorithm>
+#include <chrono>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <thread>
 #include <vector>
 
 namespace dca {
@@ -54,65 +63,39 @@ static uint64_t record_hash(const uint8_t *p, size_t n)
     return h ^ (h >> 29);
 }
 
-long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uint8_t> &out)
+namespace {
+
+// one contiguous piece of the file, starting at the beginning of a line (piece 0: the file's first byte,
+// every other piece: a '>' header line), parsed on its own thread
+struct Piece {
+    const char *begin = nullptr, *end = nullptr;
+    std::vector<uint8_t> recs;         // the piece's records in file order, L bytes each (duplicates included)
+    std::vector<uint64_t> hashes;
+    long lines = 0;                    // lines in the piece
+    long bad_line = 0;                 // first malformed record: line (within the piece) where it ended, 0 = none
+    int bad_fill = 0;
+};
+
+void parse_piece(Piece &pc, const uint8_t *lut, int L)
 {
-    FILE *f = std::fopen(path, "rb");
-    if (!f) { set_error("Unable to open file %s", path); return -1; }
-    // one read of the whole file, then a single pass over the bytes (the first version went
-    // through fgets + std::string per line: 2.3 ms of the 44 ms end-to-end call at N = 5000)
-    std::vector<char> text;
-    {
-        std::fseek(f, 0, SEEK_END);
-        const long size = std::ftell(f);
-        std::fseek(f, 0, SEEK_SET);
-        if (size > 0) {
-            text.resize((size_t)size);
-            const size_t got = std::fread(text.data(), 1, (size_t)size, f);
-            text.resize(got);
-        } else {                                   // not seekable (pipe): read in pieces
-            char buf[1 << 16];
-            size_t got;
-            while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) text.insert(text.end(), buf, buf + got);
-        }
-        std::fclose(f);
-    }
-    uint8_t lut[256];                              // 255 = white space inside a line (skipped)
-    for (int c = 0; c < 256; ++c) lut[c] = (uint8_t)encode_residue(biomolecule, c);
-    lut[(unsigned char)'\r'] = lut[(unsigned char)' '] = lut[(unsigned char)'\t'] = 255;
-
-    out.clear();
-    out.reserve(text.size());
-    // open-addressing table of record indices keyed by the FNV-1a hash of the encoded record
-    size_t cap = 1024;
-    while (cap < text.size() / (size_t)(L > 0 ? L : 1) * 2 + 16) cap <<= 1;
-    std::vector<long> slot(cap, -1);
-    std::vector<uint64_t> slot_hash(cap, 0);
     std::vector<uint8_t> rec((size_t)L);
-    long n = 0;
-    int fill = -1;                 // -1: no record open yet
+    int fill = -1;                     // -1: no record open yet
     long line_no = 0;
-    bool bad = false;
-
+    pc.recs.reserve((size_t)(pc.end - pc.begin));
     auto flush = [&]() {
-        if (fill <= 0) return;     // empty record: skipped like the reference's empty lines
-        if (fill < L) { set_error("%s: record ending at line %ld has %d residues, expected %d", path, line_no, fill, L); bad = true; return; }
-        const uint64_t h = record_hash(rec.data(), (size_t)L);
-        size_t k = (size_t)h & (cap - 1);
-        while (slot[k] >= 0) {                     // first occurrence wins (plmdca_numerics.cpp:756)
-            if (slot_hash[k] == h && std::memcmp(out.data() + (size_t)slot[k] * L, rec.data(), (size_t)L) == 0) return;
-            k = (k + 1) & (cap - 1);
-        }
-        slot[k] = n; slot_hash[k] = h;
-        out.insert(out.end(), rec.begin(), rec.end());
-        ++n;
+        if (fill <= 0) return true;    // empty record: skipped like the reference's empty lines
+        if (fill < L) { pc.bad_line = line_no; pc.bad_fill = fill; return false; }
+        pc.hashes.push_back(record_hash(rec.data(), (size_t)L));
+        pc.recs.insert(pc.recs.end(), rec.begin(), rec.end());
+        return true;
     };
-
-    const char *p = text.data(), *end = p + text.size();
-    while (p < end && !bad) {
+    const char *p = pc.begin, *end = pc.end;
+    bool ok = true;
+    while (p < end && ok) {
         const char *eol = static_cast<const char *>(std::memchr(p, '\n', (size_t)(end - p)));
         const char *stop = eol ? eol : end;
         ++line_no;
-        if (p < stop && *p == '>') { flush(); fill = 0; }
+        if (p < stop && *p == '>') { ok = flush(); fill = 0; }
         else {
             if (fill < 0 && p < stop) fill = 0;     // headerless file: one record
             const size_t len = (size_t)(stop - p);
@@ -135,8 +118,123 @@ long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uin
         }
         p = eol ? eol + 1 : end;
     }
-    if (!bad) flush();
-    if (bad) return -2;
+    if (ok) flush();
+    pc.lines = line_no;
+}
+
+}  // namespace
+
+long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uint8_t> &out)
+{
+    const auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *w) { if (getenv("DCA_B200_READER_TRACE")) fprintf(stderr, "[reader] %s %.2f ms\n", w, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count()); };
+    // The whole file at once: mapped when it is a regular file (no copy, the parser threads fault
+    // the pages in), read in pieces otherwise (pipe).
+    std::vector<char> text;
+    const char *tb = nullptr;
+    size_t tsize = 0;
+    void *map = MAP_FAILED;
+    size_t map_len = 0;
+    {
+        const int fd = open(path, O_RDONLY);
+        if (fd < 0) { set_error("Unable to open file %s", path); return -1; }
+        struct stat sb;
+        if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+            map_len = (size_t)sb.st_size;
+            map = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fd, 0);
+        }
+        if (map != MAP_FAILED) { tb = static_cast<const char *>(map); tsize = map_len; }
+        else {
+            char buf[1 << 16];
+            ssize_t got;
+            while ((got = read(fd, buf, sizeof buf)) > 0) text.insert(text.end(), buf, buf + got);
+            tb = text.data(); tsize = text.size();
+        }
+        close(fd);
+    }
+    struct Unmap { void *m; size_t n; ~Unmap() { if (m != MAP_FAILED) munmap(m, n); } } unmap{map, map_len};
+    lap("read");
+    uint8_t lut[256];                              // 255 = white space inside a line (skipped)
+    for (int c = 0; c < 256; ++c) lut[c] = (uint8_t)encode_residue(biomolecule, c);
+    lut[(unsigned char)'\r'] = lut[(unsigned char)' '] = lut[(unsigned char)'\t'] = 255;
+
+    // Pieces of ~1 MB cut in front of header lines ("\n>"), one host thread each (translation and
+    // hashing are the reader's time: 15 ms of a 31 ms mfDCA call at N = 20 000, L = 300 on one
+    // thread); the first-occurrence de-duplication below walks the pieces in file order.
+    const char *te = tb + tsize;
+    size_t want = tsize / (1u << 20);
+    const unsigned hc = std::thread::hardware_concurrency();
+    want = std::min<size_t>(want, std::min<unsigned>(hc ? hc : 1u, 16u));
+    if (const char *e = getenv("DCA_B200_READER_THREADS")) want = (size_t)std::max(1, atoi(e));
+    want = std::max<size_t>(want, 1);
+    std::vector<Piece> pieces;
+    {
+        const char *start = tb;
+        for (size_t t = 1; t < want && start < te; ++t) {
+            const char *from = tb + tsize * t / want;
+            if (from <= start) continue;
+            const char *cut = nullptr;
+            for (const char *q = from; q + 1 < te; ) {
+                q = static_cast<const char *>(std::memchr(q, '\n', (size_t)(te - q - 1)));
+                if (!q) break;
+                if (q[1] == '>') { cut = q + 1; break; }
+                ++q;
+            }
+            if (!cut) break;
+            Piece pc; pc.begin = start; pc.end = cut;
+            pieces.push_back(std::move(pc));
+            start = cut;
+        }
+        Piece last; last.begin = start; last.end = te;
+        pieces.push_back(std::move(last));
+    }
+    if (pieces.size() == 1) parse_piece(pieces[0], lut, L);
+    else {
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < pieces.size(); ++t) th.emplace_back(parse_piece, std::ref(pieces[t]), lut, L);
+        parse_piece(pieces[0], lut, L);
+        for (auto &x : th) x.join();
+    }
+    lap("parsed");
+    {   // the first malformed record in file order is the one the single pass would have stopped at
+        long lines_before = 0;
+        for (const Piece &pc : pieces) {
+            if (pc.bad_line) {
+                set_error("%s: record ending at line %ld has %d residues, expected %d", path, lines_before + pc.bad_line,
+                          pc.bad_fill, L);
+                return -2;
+            }
+            lines_before += pc.lines;
+        }
+    }
+
+    size_t total = 0;
+    for (const Piece &pc : pieces) total += pc.hashes.size();
+    out.clear();
+    out.reserve(total * (size_t)L);
+    // open-addressing table of record indices keyed by the hash of the encoded record
+    size_t cap = 1024;
+    while (cap < total * 2 + 16) cap <<= 1;
+    std::vector<long> slot(cap, -1);
+    std::vector<uint64_t> slot_hash(cap, 0);
+    long n = 0;
+    for (const Piece &pc : pieces) {
+        for (size_t r = 0; r < pc.hashes.size(); ++r) {
+            const uint8_t *rec = pc.recs.data() + r * (size_t)L;
+            const uint64_t h = pc.hashes[r];
+            size_t k = (size_t)h & (cap - 1);
+            bool dup = false;
+            while (slot[k] >= 0) {                 // first occurrence wins (plmdca_numerics.cpp:756)
+                if (slot_hash[k] == h && std::memcmp(out.data() + (size_t)slot[k] * L, rec, (size_t)L) == 0) { dup = true; break; }
+                k = (k + 1) & (cap - 1);
+            }
+            if (dup) continue;
+            slot[k] = n; slot_hash[k] = h;
+            out.insert(out.end(), rec, rec + L);
+            ++n;
+        }
+    }
+    lap("merged");
     if (n == 0) { set_error("%s: no sequences found", path); return -3; }
     return n;
 }

@@ -131,6 +131,46 @@ def test_fasta_reader_line_endings_whitespace_and_many_duplicates(tmp_path, port
     assert (got == port.read_fasta(str(d), "protein", 17)).all()
 
 
+def test_fasta_reader_pieces_on_several_threads(tmp_path, port, monkeypatch):
+    """The reader cuts large files in front of header lines and parses the pieces on host threads
+    (csrc/fasta.cpp); first-occurrence order across pieces, wrapped / CRLF / lower-case records,
+    blank lines, and the line number of the first malformed record must not depend on the cut."""
+    from pydca_b200 import _lib
+    rng = np.random.default_rng(8)
+    L, N = 61, 6000
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY-", dtype=np.uint8)
+    msa = rng.integers(0, 21, size=(N, L), dtype=np.uint8)
+    msa[1500:2500] = msa[0:1000]                    # duplicates that straddle pieces
+    msa[5500:] = msa[700:1200]
+    f = tmp_path / "pieces.fa"
+    with open(f, "wb") as fh:
+        for i, row in enumerate(msa):
+            s = letters[row].tobytes()
+            fh.write(b">s%d\n" % i)
+            if i % 3 == 0:
+                fh.write(s[:40] + b"\n" + s[40:] + b"\n")
+            elif i % 7 == 0:
+                fh.write(s.lower() + b"\r\n")
+            else:
+                fh.write(s + b"\n")
+            if i % 500 == 0:
+                fh.write(b"\n")
+    want = port.read_fasta(str(f), "protein", L)
+    assert want.shape == (N - 1500, L)
+    for threads in ("1", "2", "5", "16"):
+        monkeypatch.setenv("DCA_B200_READER_THREADS", threads)
+        assert (_lib.read_fasta(str(f), "protein", L) == want).all(), threads
+    with open(f, "ab") as fh:
+        fh.write(b">short\nACD\n>fine\n" + b"A" * L + b"\n")
+    msgs = []
+    for threads in ("1", "5"):
+        monkeypatch.setenv("DCA_B200_READER_THREADS", threads)
+        with pytest.raises(Exception) as e:
+            _lib.read_fasta(str(f), "protein", L)
+        msgs.append(str(e.value))
+    assert msgs[0] == msgs[1] and "has 3 residues, expected 61" in msgs[0]
+
+
 def test_char_form_helpers_and_slice_couplings(tmp_path):
     """Host helpers of the reference surface: fasta_reader.res_to_char / sequences_to_char_form /
     get_alignment_char_form (fasta_reader.py:53-76, :191-249) and msa_numerics.slice_couplings
