@@ -76,6 +76,7 @@ constexpr int PERM_ENTRIES = SC_CH + 3 * 21 + 9;      // 200: worst-case padding
 constexpr int PERM_REC = PERM_CNT + 4 * PERM_ENTRIES; // 832 bytes (52 x 16 B)
 
 constexpr int AS_JG = 8;          // sites j per assemble / unpack CTA
+constexpr int AS_UN = 4;          // elements per thread and step of the assemble loops
 
 struct PlmProblem {
     long N = 0, Npad = 0, P = 0;
@@ -887,37 +888,78 @@ plm_assemble_kernel(const float *__restrict__ x, const float *__restrict__ G, si
         s_gg += (double)gv * gv;
     }
 
+    // Both loops take AS_UN elements per thread and step, all their loads issued before the first use
+    // (the kernel is bound by the latency of its strided reads, not by bandwidth); the summation
+    // order over the splits is unchanged.
+    const int nel = npair * QQ;
     // transposed part U[a][b] = G[(j,b)][(i,a)]: read with a fastest, park in smem
-    for (int t = threadIdx.x; t < npair * QQ; t += 256) {
-        const int jj = t / QQ, e = t - jj * QQ;
-        const int b = e / Q, a = e - b * Q;
-        const int j = jlo + jj;
-        float u = 0.f;
-        if (own_i)
-            for (int s = 0; s < nsplit; ++s)
-                u += G[(size_t)s * g_split_stride + ((long)j * Q + b) * ld + i * Q + a];
-        tile[jj * QQ + a * Q + b] = u;
+    if (own_i) {
+        for (int t0 = threadIdx.x; t0 < nel; t0 += 256 * AS_UN) {
+            float u[AS_UN];
+            size_t off[AS_UN];
+#pragma unroll
+            for (int k = 0; k < AS_UN; ++k) {
+                const int t = min(t0 + 256 * k, nel - 1);
+                const int jj = t / QQ, e = t - jj * QQ;
+                const int b = e / Q, a = e - b * Q;
+                off[k] = ((size_t)(jlo + jj) * Q + b) * ld + i * Q + a;
+                u[k] = 0.f;
+            }
+            for (int s = 0; s < nsplit; ++s) {
+                const float *Gs = G + (size_t)s * g_split_stride;
+#pragma unroll
+                for (int k = 0; k < AS_UN; ++k) u[k] += Gs[off[k]];
+            }
+#pragma unroll
+            for (int k = 0; k < AS_UN; ++k) {
+                const int t = t0 + 256 * k;
+                if (t < nel) {
+                    const int jj = t / QQ, e = t - jj * QQ;
+                    const int b = e / Q, a = e - b * Q;
+                    tile[jj * QQ + a * Q + b] = u[k];
+                }
+            }
+        }
+    } else {
+        for (int t = threadIdx.x; t < nel; t += 256) tile[t] = 0.f;
     }
     __syncthreads();
     // pairs (i, jlo..jhi-1) are consecutive blocks of x: one contiguous run
     const long base = Lq + pair_index(L, i, jlo) * QQ;
-    for (int t = threadIdx.x; t < npair * QQ; t += 256) {
-        const int jj = t / QQ, e = t - jj * QQ;
-        const int a = e / Q, b = e - a * Q;
-        const int j = jlo + jj;
-        const float xv = x[base + t];
-        float gv = own_i ? 2.f * lJ * xv : 0.f;
-        gv += tile[t];
-        if (j >= site_lo && j < site_hi) {
-            float v = 0.f;
-            for (int s = 0; s < nsplit; ++s)
-                v += G[(size_t)s * g_split_stride + ((long)i * Q + a) * ld + j * Q + b];
-            gv += v;
+    for (int t0 = threadIdx.x; t0 < nel; t0 += 256 * AS_UN) {
+        float xv[AS_UN], v[AS_UN], dv[AS_UN];
+        size_t off[AS_UN];
+        bool own_j[AS_UN];
+#pragma unroll
+        for (int k = 0; k < AS_UN; ++k) {
+            const int t = min(t0 + 256 * k, nel - 1);
+            const int jj = t / QQ, e = t - jj * QQ;
+            const int a = e / Q, b = e - a * Q;
+            const int j = jlo + jj;
+            own_j[k] = (j >= site_lo && j < site_hi);
+            off[k] = ((size_t)i * Q + a) * ld + (size_t)j * Q + b;
+            xv[k] = x[base + t];
+            dv[k] = d ? d[base + t] : 0.f;
+            v[k] = 0.f;
         }
-        g[base + t] = gv;
-        if (own_i) { s_reg += (double)lJ * xv * xv; s_xx += (double)xv * xv; }
-        if (d) s_dg += (double)gv * d[base + t];
-        s_gg += (double)gv * gv;
+        for (int s = 0; s < nsplit; ++s) {
+            const float *Gs = G + (size_t)s * g_split_stride;
+#pragma unroll
+            for (int k = 0; k < AS_UN; ++k) if (own_j[k]) v[k] += Gs[off[k]];
+        }
+#pragma unroll
+        for (int k = 0; k < AS_UN; ++k) {
+            const int t = t0 + 256 * k;
+            if (t < nel) {
+                float gv = own_i ? 2.f * lJ * xv[k] : 0.f;
+                gv += tile[t];
+                if (own_j[k]) gv += v[k];
+                g[base + t] = gv;
+                if (own_i) { s_reg += (double)lJ * xv[k] * xv[k]; s_xx += (double)xv[k] * xv[k]; }
+                if (d) s_dg += (double)gv * dv[k];
+                s_gg += (double)gv * gv;
+            }
+        }
     }
 
     assemble_finish(s_reg, s_dg, s_gg, s_xx, red, fxpart, nfx, ticket, n_active, scal);
