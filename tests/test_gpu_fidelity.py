@@ -82,6 +82,56 @@ def test_sequential_sum_kernel_is_bit_exact(naive):
         assert _bits(lib().seq_reg(x, 3150, lam0, lam1)) == _bits(want)
 
 
+def test_sequential_sum_pipeline_on_adversarial_inputs(naive):
+    """The same claim at lengths that take the producer / consumer pipeline (>= 64 chunks of 4096
+    terms): records that do not fit (chain warp's row walk), missing candidates and running value 0
+    (the consumer CTA's exact path), rows with terms too large for the integer picture, ties, inf / nan."""
+    rng = np.random.default_rng(23)
+    one = lambda t: (np.asarray(t, dtype=np.float32), np.ones(len(t), dtype=np.float32))
+    n = 700_001
+    # hovering at a binade boundary: +-0.37 around 1024, 2048 and back down through 512
+    hover = np.tile(np.concatenate([np.full(300, 0.37), np.full(300, -0.37)]), n // 600)
+    _dot_case(naive, *one(np.concatenate([[1024.0], hover])))
+    _dot_case(naive, *one(np.concatenate([[2048.0 - 30.0], hover + 1e-4, -hover - 3e-3])))
+    # random walk: the exponent wanders, many sign changes of the running value
+    _dot_case(naive, rng.standard_normal(n), rng.standard_normal(n))
+    _dot_case(naive, *one(rng.standard_normal(n) * 1e-3))
+    # running value exactly 0 for whole chunks, then again after complete cancellation
+    z = np.concatenate([np.zeros(3 * 4096 + 17), rng.standard_normal(200_000), [0.0]])
+    z = np.concatenate([z, -z[::-1], np.zeros(5000), rng.standard_normal(150_000)])
+    _dot_case(naive, *one(z))
+    _dot_case(naive, *one(np.concatenate([np.ones(2 ** 18), -np.ones(2 ** 18), np.full(300_000, 2.0 ** -30)])))
+    # exponents all over the place: terms far too large / too small for the running value's binade
+    _dot_case(naive, *one(rng.standard_normal(n) * np.exp(rng.uniform(-40, 40, n))))
+    wide = rng.standard_normal(n) * 0.01
+    wide[rng.integers(0, n, 200)] *= 1e9                              # bursts
+    _dot_case(naive, *one(wide))
+    # quantised terms: exact ties at every step
+    _dot_case(naive, *one(np.round(rng.standard_normal(n) * 64) / 4))
+    _dot_case(naive, *one(np.concatenate([[2.0 ** 24], np.tile([1.0, 1.0, 3.0, -1.0], n // 4)])))
+    # stagnation: terms below half an ulp of the running value, with a few that are not
+    st = np.full(n, 1e-4)
+    st[0] = 4096.0
+    st[rng.integers(1, n, 500)] = 0.5
+    _dot_case(naive, *one(st))
+    # inf / nan appear in the middle of the vector
+    for bad in (np.inf, -np.inf, np.nan):
+        v = rng.standard_normal(n) * 0.1
+        v[n // 2 + 77] = bad
+        _dot_case(naive, *one(v))
+    v = rng.standard_normal(n) * 0.1
+    v[123_456], v[600_000] = np.inf, -np.inf
+    _dot_case(naive, *one(v))
+    # products that overflow / underflow in float32 (the term is formed in float32 like the reference's)
+    _dot_case(naive, rng.standard_normal(n) * 1e25, rng.standard_normal(n) * 1e20)
+    _dot_case(naive, rng.standard_normal(n) * 1e-25, rng.standard_normal(n) * 1e-20)
+    # the L2 accumulation at a length that takes the pipeline, lambda changing inside a chunk
+    x = (rng.standard_normal(n) * 0.05).astype(np.float32)
+    for n0, lam0, lam1 in ((3150, 29.8, 29.8), (4096 * 70 + 5, 1.0, 20.0), (0, 0.0, 3.0)):
+        want = np.float32(naive.seq_naive_reg(x.ctypes.data_as(_f32p), x.size, n0, lam0, lam1))
+        assert _bits(lib().seq_reg(x, n0, lam0, lam1)) == _bits(want), (n0, lam0, lam1)
+
+
 def _fn(x, L, q):
     fn, _ = lib().plm_fn_apc(x, L, q)
     return fn
