@@ -161,62 +161,89 @@ __global__ void transpose_msa_kernel(const uint8_t *__restrict__ msa, long N, in
 // grouping for correctness -- the logits kernel tests every group of four rows for equality itself.
 // thread = one sequence; leaders are staged through shared memory 8 at a time as packed words
 constexpr int NL_TILE = 8;
+constexpr int NL_ROWS = 128;                            // sequences per CTA
+
+// packed[n][w] = residues at the sampled columns 4w .. 4w+3 of sequence n (column c -> site c * cstride), one byte
+// each; words and bytes beyond the sample are 0 in every row (they always match: the same constant for every pair)
+__global__ void pack_sampled_kernel(const uint8_t *__restrict__ msa, long N, int Lfull, int cstride, int Ls, int Lw,
+                                    uint32_t *__restrict__ packed)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * Lw) return;
+    const long n = idx / Lw;
+    const int w = (int)(idx - n * Lw);
+    const uint8_t *row = msa + (size_t)n * Lfull;
+    uint32_t v = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int c = 4 * w + e;
+        if (c < Ls) v |= (uint32_t)row[(size_t)c * cstride] << (8 * e);
+    }
+    packed[idx] = v;
+}
+
 // rows classified: n * row_stride for n < nrows (row_stride 1: every sequence; 16: the leaders themselves).
 // first_at > 0: not the most identical leader but the FIRST one with at least first_at identical residues (leaders
 // classified against leaders: the first similar leader is the representative of a cluster of leaders).
 // blockIdx.y takes a slice of the leaders (a grid of N / 128 CTAs alone leaves most SMs empty); the slices meet in
 // `key`: most identical -> atomicMax of (identical residues << 20 | 0xfffff - leader), lowest leader on ties;
 // first similar -> atomicMin of the leader index.  key is cleared to 0 / 0x7fffffff by the caller; L < 2048.
-__global__ void __launch_bounds__(128)
-nearest_leader_kernel(const uint8_t *__restrict__ msa, long nrows, int row_stride, int Lfull, int cstride, int nleaders,
+// Works on the packed sample (Lw words per sequence, a multiple of 4): the CTA's 128 rows sit in shared memory
+// word-major (conflict-free), the leaders are read as broadcast 16-byte loads, and per 4 residues the inner loop
+// is xor / add / shift / and / add -- mismatch flags (bit 5 of (a ^ b) + 0x1f per byte: residue codes are below 32)
+// accumulated in four byte lanes (at most 4 * Lw / 4 <= 127 per lane).  The first version gathered the row's bytes
+// from global memory again for every tile of leaders: 42 ms of a 111 ms reweighting at N = 200 000.
+__global__ void __launch_bounds__(NL_ROWS)
+nearest_leader_kernel(const uint32_t *__restrict__ packed, long nrows, int row_stride, int Lw, int nleaders,
                       int first_at, unsigned *__restrict__ key)
-{   // the compare runs on every cstride-th column (L = sampled columns): identity on a 64-column sample separates
-    // "same cluster" from "unrelated" as well as the full rows do, at a fraction of the cost
-    extern __shared__ uint32_t lead[];                  // [NL_TILE][Lw]
-    const int L = (Lfull + cstride - 1) / cstride;
-    const int Lw = (L + 3) / 4;
-    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint8_t *row = msa + (size_t)(min(n, nrows - 1) * row_stride) * Lfull;
+{
+    extern __shared__ __align__(16) uint32_t nl_smem[];
+    uint32_t *lead = nl_smem;                           // [NL_TILE][Lw]
+    uint32_t *rows = nl_smem + NL_TILE * Lw;            // [Lw][NL_ROWS]
+    const int tid = threadIdx.x;
+    const long n = (long)blockIdx.x * NL_ROWS + tid;
+    {
+        const uint32_t *src = packed + (size_t)(min(n, nrows - 1) * row_stride) * Lw;
+        for (int w = 0; w < Lw; w += 4) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(src + w);
+            rows[(w + 0) * NL_ROWS + tid] = v.x; rows[(w + 1) * NL_ROWS + tid] = v.y;
+            rows[(w + 2) * NL_ROWS + tid] = v.z; rows[(w + 3) * NL_ROWS + tid] = v.w;
+        }
+    }
     const int per = (((nleaders + (int)gridDim.y - 1) / (int)gridDim.y + NL_TILE - 1) / NL_TILE) * NL_TILE;
     const int lbeg = (int)blockIdx.y * per, lend = min(nleaders, lbeg + per);
+    const int total = 4 * Lw;                           // compared bytes, padding included
     int best = 0, best_id = -1;
     for (int l0 = lbeg; l0 < lend; l0 += NL_TILE) {
         __syncthreads();
-        for (int t = threadIdx.x; t < NL_TILE * Lw; t += blockDim.x) {
-            const int k = t / Lw, wdx = t - k * Lw;
-            uint32_t v = 0xffffffffu;                   // a leader that does not exist matches nothing
-            if (l0 + k < lend) {
-                const uint8_t *lr = msa + (size_t)((long)(l0 + k) * 16) * Lfull;
-                v = 0;
-                for (int e = 0; e < 4; ++e) {
-                    const int c = 4 * wdx + e;
-                    v |= (uint32_t)(c < L ? lr[c * cstride] : 0xffu) << (8 * e);
-                }
-            }
-            lead[t] = v;
+        for (int t = tid; t < NL_TILE * Lw; t += NL_ROWS) {
+            const int k = t / Lw, w = t - k * Lw;
+            lead[t] = (l0 + k < lend) ? packed[(size_t)((long)(l0 + k) * 16) * Lw + w] : 0u;
         }
         __syncthreads();
-        int ident[NL_TILE];
+        uint32_t mism[NL_TILE];
 #pragma unroll
-        for (int k = 0; k < NL_TILE; ++k) ident[k] = 0;
-        for (int wdx = 0; wdx < Lw; ++wdx) {
-            uint32_t a = 0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = 4 * wdx + e;
-                a |= (uint32_t)(c < L ? row[c * cstride] : 0xfeu) << (8 * e);     // padding: 0xfe here, 0xff in the leaders
-            }
+        for (int k = 0; k < NL_TILE; ++k) mism[k] = 0;
+        for (int w = 0; w < Lw; w += 4) {
+            const uint32_t a0 = rows[(w + 0) * NL_ROWS + tid], a1 = rows[(w + 1) * NL_ROWS + tid];
+            const uint32_t a2 = rows[(w + 2) * NL_ROWS + tid], a3 = rows[(w + 3) * NL_ROWS + tid];
 #pragma unroll
             for (int k = 0; k < NL_TILE; ++k) {
-                const uint32_t x = a ^ lead[k * Lw + wdx];
-                ident[k] += 4 - __popc((((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u);   // bytes of x that are 0
+                const uint4 b = *reinterpret_cast<const uint4 *>(lead + k * Lw + w);
+                uint32_t m = mism[k];
+                m += (((a0 ^ b.x) + 0x1f1f1f1fu) >> 5) & 0x01010101u;
+                m += (((a1 ^ b.y) + 0x1f1f1f1fu) >> 5) & 0x01010101u;
+                m += (((a2 ^ b.z) + 0x1f1f1f1fu) >> 5) & 0x01010101u;
+                m += (((a3 ^ b.w) + 0x1f1f1f1fu) >> 5) & 0x01010101u;
+                mism[k] = m;
             }
         }
 #pragma unroll
         for (int k = 0; k < NL_TILE; ++k) {
             if (l0 + k >= lend) continue;
-            if (first_at > 0) { if (best_id < first_at && ident[k] >= first_at) { best_id = ident[k]; best = l0 + k; } }
-            else if (ident[k] > best_id) { best_id = ident[k]; best = l0 + k; }
+            const int ident = total - (int)__dp4a(mism[k], 0x01010101u, 0u);
+            if (first_at > 0) { if (best_id < first_at && ident >= first_at) { best_id = ident; best = l0 + k; } }
+            else if (ident > best_id) { best_id = ident; best = l0 + k; }
         }
     }
     if (n < nrows && best_id >= 0) {
@@ -233,18 +260,22 @@ int similarity_order(const uint8_t *d_msa, long N, int L, cudaStream_t st, std::
     const int nleaders = (int)ceil_div<long>(N, 16);
     const int cstride = std::max(1, L / 64);
     const int Ls = ceil_div(L, cstride);
+    const int Lw = (ceil_div(Ls, 4) + 3) / 4 * 4;       // words per packed sample row: 16-byte groups
+    const int npad = 4 * Lw - Ls;                       // padding bytes: identical in every pair
     DevBuf<unsigned> d_key, d_rep;
-    if (!d_key.alloc((size_t)N) || !d_rep.alloc((size_t)nleaders)) return -1;
-    const size_t smem = sizeof(uint32_t) * NL_TILE * ((Ls + 3) / 4);
-    const int slices = std::max(1, std::min(32, (int)((4L * sm_count()) / std::max<long>(1, ceil_div<long>(N, 128)))));
+    DevBuf<uint32_t> d_packed;
+    if (!d_key.alloc((size_t)N) || !d_rep.alloc((size_t)nleaders) || !d_packed.alloc((size_t)N * Lw)) return -1;
+    const size_t smem = sizeof(uint32_t) * (size_t)(NL_TILE + NL_ROWS) * Lw;
+    const int slices = std::max(1, std::min(32, (int)((4L * sm_count()) / std::max<long>(1, ceil_div<long>(N, NL_ROWS)))));
     DCA_CUDA(cudaMemsetAsync(d_key.p, 0, sizeof(unsigned) * (size_t)N, st));
     DCA_CUDA(cudaMemsetAsync(d_rep.p, 0x7f, sizeof(unsigned) * (size_t)nleaders, st));
-    DCA_LAUNCH(nearest_leader_kernel, dim3((unsigned)ceil_div<long>(N, 128), (unsigned)slices), 128, smem, st, d_msa, N, 1, L,
-               cstride, nleaders, 0, d_key.p);
+    DCA_LAUNCH(pack_sampled_kernel, (unsigned)ceil_div<long>(N * Lw, 256), 256, 0, st, d_msa, N, L, cstride, Ls, Lw, d_packed.p);
+    DCA_LAUNCH(nearest_leader_kernel, dim3((unsigned)ceil_div<long>(N, NL_ROWS), (unsigned)slices), NL_ROWS, smem, st,
+               d_packed.p, N, 1, Lw, nleaders, 0, d_key.p);
     // leaders against leaders: the first leader sharing half of the residues represents a cluster of leaders, so that
     // the runs of one true cluster end up next to each other (groups of four that straddle two runs stay similar)
-    DCA_LAUNCH(nearest_leader_kernel, dim3((unsigned)ceil_div<long>(nleaders, 128), 32), 128, smem, st, d_msa, (long)nleaders,
-               16, L, cstride, nleaders, (Ls + 1) / 2, d_rep.p);
+    DCA_LAUNCH(nearest_leader_kernel, dim3((unsigned)ceil_div<long>(nleaders, NL_ROWS), 32), NL_ROWS, smem, st,
+               d_packed.p, (long)nleaders, 16, Lw, nleaders, (Ls + 1) / 2 + npad, d_rep.p);
     std::vector<int> best((size_t)N), rep((size_t)nleaders);
     order.assign((size_t)N, 0);
     rowidx.assign((size_t)N, 0);

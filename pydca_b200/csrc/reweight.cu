@@ -266,14 +266,15 @@ int reweight_counts_device(const uint8_t *d_msa, long N, int L, double seqid, in
     // Deep alignments (symmetric mode): compare the rows in similarity order.  Almost every tile pair then holds
     // unrelated sequences only, which the kernel's early exit decides after a fraction of the columns; the counts
     // come back through the permutation.  The order costs N^2/16 sampled compares -- worth it from ~1e10 on -- and
-    // every part computes all of it (the parts must agree on the order): at N = 200 000 it is ~45 ms next to
-    // 65 / nparts ms of compares against 167 / nparts ms in file order, so from three parts on the file order
-    // wins (DCA_B200_REWEIGHT_ORDER=sorted | file overrides).
+    // every part computes all of it (the parts must agree on the order): at N = 200 000 it is ~19 ms next to
+    // 69 / nparts ms of compares against 167 / nparts ms in file order (measured per part: 4 parts 36.8 vs 42.7 ms,
+    // 8 parts 28.1 vs 21.5 ms), so from five parts on the file order wins (DCA_B200_REWEIGHT_ORDER=sorted | file
+    // overrides).
     const char *order_env = getenv("DCA_B200_REWEIGHT_ORDER");
     const bool order_file = order_env && strcmp(order_env, "file") == 0;
     const bool order_sorted = order_env && strcmp(order_env, "sorted") == 0;
     const bool use_sorted = sym && (double)N * (double)N * (double)L >= 2.0e10 && N < (1L << 24) && L < 2048 &&
-                            !order_file && (nparts <= 2 || order_sorted);
+                            !order_file && (nparts <= 4 || order_sorted);
     if (use_sorted) {
         std::vector<int> order, rowidx;
         if (!d_order.alloc((size_t)N) || !d_sorted_counts.alloc((size_t)N)) return -1;
