@@ -652,6 +652,9 @@ def run_ours(args, rank, world, local_rank):
             per_call = []
             t0 = time.perf_counter()
             for _ in range(n_e2e):
+                # the previous result goes back to the library before the next call, as in the single-GPU loop
+                # above (holding it made every second call allocate a fresh 20 MB pinned buffer: +12 ms)
+                last_x[0] = None
                 t1 = time.perf_counter()
                 last_x[0] = _lib.plmdca_backend(path, "protein", SEQ_LEN, Q, SEQID, lam, lam, MAX_ITER)
                 e_evals += _lib.last_fit().evaluations
