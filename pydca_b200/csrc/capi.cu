@@ -183,15 +183,22 @@ long dca_read_fasta(const char *msa_file, int biomolecule, int seqs_len, uint8_t
 {
     if (!msa_file || !msa_out || seqs_len <= 0) { set_error("dca_read_fasta: bad arguments"); return -1; }
     // the reader's own buffer is handed out (no copy of the alignment); dca_free_host finds it again
-    auto *buf = new std::vector<uint8_t>();
-    const long n = read_fasta_unique(msa_file, biomolecule, seqs_len, *buf);
-    if (n <= 0) { delete buf; return n; }
-    {
-        std::lock_guard<std::mutex> lk(g_host_vec_mu);
-        g_host_vecs[buf->data()] = buf;
+    std::vector<uint8_t> *buf = nullptr;
+    try {
+        buf = new std::vector<uint8_t>();
+        const long n = read_fasta_unique(msa_file, biomolecule, seqs_len, *buf);
+        if (n <= 0) { delete buf; return n; }
+        {
+            std::lock_guard<std::mutex> lk(g_host_vec_mu);
+            g_host_vecs[buf->data()] = buf;
+        }
+        *msa_out = buf->data();
+        return n;
+    } catch (const std::exception &e) {                    // no exception crosses the C ABI
+        delete buf;
+        set_error("dca_read_fasta: %s", e.what());
+        return -1;
     }
-    *msa_out = buf->data();
-    return n;
 }
 
 void dca_free_host(void *p)

@@ -24,6 +24,7 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <system_error>
 #include <unistd.h>
 #include <cstdlib>
 #include <cstring>
@@ -191,8 +192,14 @@ long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uin
     if (pieces.size() == 1) parse_piece(pieces[0], lut, L);
     else {
         std::vector<std::thread> th;
-        for (size_t t = 1; t < pieces.size(); ++t) th.emplace_back(parse_piece, std::ref(pieces[t]), lut, L);
+        size_t started = 1;
+        try {
+            for (; started < pieces.size(); ++started) th.emplace_back(parse_piece, std::ref(pieces[started]), lut, L);
+        } catch (const std::system_error &) {
+            // no more threads to be had: this thread parses the rest
+        }
         parse_piece(pieces[0], lut, L);
+        for (size_t t = started; t < pieces.size(); ++t) parse_piece(pieces[t], lut, L);
         for (auto &x : th) x.join();
     }
     lap("parsed");
