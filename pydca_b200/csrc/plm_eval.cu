@@ -190,8 +190,8 @@ __global__ void pack_sampled_kernel(const uint8_t *__restrict__ msa, long N, int
 // first similar -> atomicMin of the leader index.  key is cleared to 0 / 0x7fffffff by the caller; L < 2048.
 // Works on the packed sample (Lw words per sequence, a multiple of 4): the CTA's 128 rows sit in shared memory
 // word-major (conflict-free), the leaders are read as broadcast 16-byte loads, and per 4 residues the inner loop
-// is xor / add / shift / and / add -- mismatch flags (bit 5 of (a ^ b) + 0x1f per byte: residue codes are below 32)
-// accumulated in four byte lanes (at most 4 * Lw / 4 <= 127 per lane).  The first version gathered the row's bytes
+// is xor / add / and / add -- mismatch flags (bit 5 of (a ^ b) + 0x1f per byte: residue codes are below 32), four
+// words of them added up unshifted in the byte lanes and folded by one dp4a.  The first version gathered the row's bytes
 // from global memory again for every tile of leaders: 42 ms of a 111 ms reweighting at N = 200 000.
 __global__ void __launch_bounds__(NL_ROWS)
 nearest_leader_kernel(const uint32_t *__restrict__ packed, long nrows, int row_stride, int Lw, int nleaders,
@@ -221,7 +221,7 @@ nearest_leader_kernel(const uint32_t *__restrict__ packed, long nrows, int row_s
             lead[t] = (l0 + k < lend) ? packed[(size_t)((long)(l0 + k) * 16) * Lw + w] : 0u;
         }
         __syncthreads();
-        uint32_t mism[NL_TILE];
+        uint32_t mism[NL_TILE];                         // 32 x mismatches (the flags are bit 5 of their byte)
 #pragma unroll
         for (int k = 0; k < NL_TILE; ++k) mism[k] = 0;
         for (int w = 0; w < Lw; w += 4) {
@@ -230,18 +230,18 @@ nearest_leader_kernel(const uint32_t *__restrict__ packed, long nrows, int row_s
 #pragma unroll
             for (int k = 0; k < NL_TILE; ++k) {
                 const uint4 b = *reinterpret_cast<const uint4 *>(lead + k * Lw + w);
-                uint32_t m = mism[k];
-                m += (((a0 ^ b.x) + 0x1f1f1f1fu) >> 5) & 0x01010101u;
-                m += (((a1 ^ b.y) + 0x1f1f1f1fu) >> 5) & 0x01010101u;
-                m += (((a2 ^ b.z) + 0x1f1f1f1fu) >> 5) & 0x01010101u;
-                m += (((a3 ^ b.w) + 0x1f1f1f1fu) >> 5) & 0x01010101u;
-                mism[k] = m;
+                // four words of flags fit a byte lane unshifted (4 x 0x20); one dp4a folds the lanes
+                uint32_t m = ((a0 ^ b.x) + 0x1f1f1f1fu) & 0x20202020u;
+                m += ((a1 ^ b.y) + 0x1f1f1f1fu) & 0x20202020u;
+                m += ((a2 ^ b.z) + 0x1f1f1f1fu) & 0x20202020u;
+                m += ((a3 ^ b.w) + 0x1f1f1f1fu) & 0x20202020u;
+                mism[k] = __dp4a(m, 0x01010101u, mism[k]);
             }
         }
 #pragma unroll
         for (int k = 0; k < NL_TILE; ++k) {
             if (l0 + k >= lend) continue;
-            const int ident = total - (int)__dp4a(mism[k], 0x01010101u, 0u);
+            const int ident = total - (int)(mism[k] >> 5);
             if (first_at > 0) { if (best_id < first_at && ident >= first_at) { best_id = ident; best = l0 + k; } }
             else if (ident > best_id) { best_id = ident; best = l0 + k; }
         }
