@@ -296,7 +296,7 @@ seqsum_kernel(SeqLaunch jobs, float *__restrict__ out)
 }
 
 // ---- producer / consumer pipeline -------------------------------------------------------------
-constexpr int SEQ_MAX_ROUNDS = 6;            // exponent changes inside one chunk before the rest of it goes through the plain chain
+constexpr int SEQ_MAX_ROUNDS = 6;            // exponent changes inside one chunk after which the row walk hands it to the CTA's exact path
 constexpr int PC_RING = 128;                 // chunks in the consumer's shared-memory ring of records
 constexpr int PC_FETCH = 4;                  // fetch warps of the consumer CTA (PC_RING / 32 batches in flight)
 constexpr int PC_CHUNK = SQ_GROUP;             // 4096 terms: one row of 128 per warp
