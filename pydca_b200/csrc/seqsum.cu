@@ -77,6 +77,46 @@ __device__ __forceinline__ SeqSum warp_scan(SeqSum v, bool ties)
     return v;
 }
 
+// The same scan for summaries that do not depend on the parity (no exact tie inside: 99.8 % of the rows of the
+// config-2 fit) and are small (|fields| < 2^24: 32 of them add up without overflow): an integer scan of the totals
+// and prefix minima / maxima of the absolute prefix ranges -- 15 shuffles and ~30 integer operations in three short
+// dependent chains instead of five rounds of seq_compose on both parities (the chain warp runs alone on its
+// scheduler: ~1.2 k of the ~1.7 k cycles of one of its steps were this scan).  `valid` = false: neutral element.
+// Equal to warp_scan wherever no field saturates; a saturated field only ever turns "fits" into "does not fit".
+__device__ __forceinline__ SeqSum warp_scan_plain(const SeqSum &v, bool valid)
+{
+    const int lane = threadIdx.x & 31;
+    const int tot = valid ? v.total[0] : 0;
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
+    }
+    const int exc = inc - tot;
+    int a = valid ? exc + v.pmin[0] : (1 << 30), b = valid ? exc + v.pmax[0] : -(1 << 30);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ua = __shfl_up_sync(0xffffffffu, a, o), ub = __shfl_up_sync(0xffffffffu, b, o);
+        if (lane >= o) { a = min(a, ua); b = max(b, ub); }
+    }
+    SeqSum r;
+    r.total[0] = r.total[1] = inc;
+    r.pmin[0] = r.pmin[1] = a;
+    r.pmax[0] = r.pmax[1] = b;
+    return r;
+}
+
+// warp-uniform: can warp_scan_plain take these summaries?  (lanes that are not valid do not count)
+__device__ __forceinline__ bool scan_is_plain(const SeqSum &v, bool valid)
+{
+    const int lim = 1 << 24;
+    const bool ok = !valid || (v.total[0] == v.total[1] && v.pmin[0] == v.pmin[1] && v.pmax[0] == v.pmax[1] &&
+                               v.total[0] > -lim && v.total[0] < lim && v.pmin[0] > -lim && v.pmin[0] < lim &&
+                               v.pmax[0] > -lim && v.pmax[0] < lim);
+    return __all_sync(0xffffffffu, ok);
+}
+
 // summary of NT consecutive terms held by one lane
 template <int NT>
 __device__ __forceinline__ SeqSum lane_summary(const SeqCtx &c, const float *t, bool *bad, bool *tie)
@@ -381,6 +421,41 @@ __device__ __forceinline__ void load_terms(const SeqJob &J, long base, float *t)
     }
 }
 
+// The same in two steps, for a prefetch that does not wait: issue the loads of the four terms at `base`
+// (raw operands in registers), form the products when they are needed.  load_terms multiplies at once --
+// a warp that calls it stalls until the loads are back.
+__device__ __forceinline__ void load_raw(const SeqJob &J, long base, float4 &xr, float4 &yr)
+{
+    xr = make_float4(0.f, 0.f, 0.f, 0.f);
+    yr = xr;
+    if (base + 4 <= J.n) {
+        xr = __ldg(reinterpret_cast<const float4 *>(J.x + base));
+        if (J.kind == SEQ_DOT) yr = __ldg(reinterpret_cast<const float4 *>(J.y + base));
+    } else {
+        float xv[4], yv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            xv[k] = (base + k < J.n) ? J.x[base + k] : 0.f;
+            yv[k] = (J.kind == SEQ_DOT && base + k < J.n) ? J.y[base + k] : 0.f;
+        }
+        xr = make_float4(xv[0], xv[1], xv[2], xv[3]);
+        yr = make_float4(yv[0], yv[1], yv[2], yv[3]);
+    }
+}
+__device__ __forceinline__ void terms_from_raw(const SeqJob &J, long base, const float4 &xr, const float4 &yr, float *t)
+{
+    const float xv[4] = {xr.x, xr.y, xr.z, xr.w}, yv[4] = {yr.x, yr.y, yr.z, yr.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (J.kind == SEQ_DOT) t[k] = __fmul_rn(xv[k], yv[k]);
+        else {
+            const float lam = (base + k < J.n0) ? J.lam0 : J.lam1;
+            t[k] = __fmul_rn(__fmul_rn(lam, xv[k]), xv[k]);
+        }
+        if (base + k >= J.n) t[k] = 0.f;
+    }
+}
+
 __device__ __forceinline__ int exp_field(float s)           // 0 when the integer picture does not apply
 {
     const int ef = (int)((seq_bits(s) >> 23) & 0xffu);
@@ -418,7 +493,10 @@ __device__ __noinline__ void walk_rows(float &s, const SeqSum (*ws)[SQ_WARPS], c
             }
             const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);
             const int nusable = (badmask == 0u) ? 32 : (__ffs(badmask) - 1);
-            v = warp_scan(v, true);
+            {
+                const bool valid = lane >= w && bad == 0;      // (bad rows hold zeros: harmless in either scan)
+                v = scan_is_plain(v, valid) ? warp_scan_plain(v, valid) : warp_scan(v, true);
+            }
             const int p = cc.M & 1;
             const bool okl = lane < w || (lane < nusable && seq_block_ok(cc, v.pmin[p], v.pmax[p]));
             const unsigned okmask = __ballot_sync(0xffffffffu, okl);
@@ -493,7 +571,10 @@ __device__ __noinline__ bool row_walk(float &s_io, const SeqJob &J, long c, int 
         }
         const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);
         const int nusable = (badmask == 0u) ? 32 : (__ffs(badmask) - 1);
-        v = warp_scan(v, true);
+        {
+            const bool valid = lane >= w;
+            v = scan_is_plain(v, valid) ? warp_scan_plain(v, valid) : warp_scan(v, true);
+        }
         const int p = cc.M & 1;
         const bool okl = lane < w || (lane < nusable && seq_block_ok(cc, v.pmin[p], v.pmax[p]));
         const unsigned okmask = __ballot_sync(0xffffffffu, okl);
@@ -584,7 +665,6 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
     __shared__ int wflag[2][3][SQ_WARPS];
     __shared__ float s_sh;
     __shared__ long c_sh;
-    __shared__ int e_sh, skip_sh;
     __shared__ double rowsum_sh[SQ_WARPS];                 // consumer's exact path: float64 row sums and
     __shared__ int erow_sh[SQ_WARPS];                      // the exponent field predicted on entering each row
     // consumer only: ring of fetched records (three candidates per chunk), filled by the fetch warps
@@ -609,41 +689,62 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
         // No flow control: the exponent of the running value at chunk c is predicted by the
         // pre-pass (epred) and corrected by the drift the consumer has measured so far
         // (published exponent minus prediction at the consumer's position).
+        // ONE barrier per chunk.  The exponent of the next chunk is worked out by thread 0 (from hints read two
+        // chunks ahead with relaxed loads: they are hints) while the warps summarise the current one; a chunk is
+        // published one barrier later, after the next chunk's summaries -- by then its records have been on their
+        // way for a whole chunk and the release does not wait; the operands of the next chunk are prefetched RAW
+        // (a product formed at the prefetch would stall the warp until the loads are back); and the chunk's record
+        // is a reduction of the 32 row summaries, not a scan.  ncu before (profiles/r2q_seqsum_pipe_*): 21 % of the
+        // samples at the barrier behind the fence, 10 % at the first product of the prefetched terms, 6 % at the
+        // barrier behind thread 0's hints.
         const int *epred = pd.epred + (size_t)job * pd.maxchunks;
+        __shared__ int e_next_sh[2], skip_next_sh[2];
         int buf = 0;
-        float tn[4];
         long c = role - 1;
-        if (c < nchunks) load_terms(J, c * PC_CHUNK + warp * 128 + 4 * lane, tn);
-        // The consumer's hints (relaxed loads: they are hints) and the predictions are read one chunk
-        // ahead by thread 0, so that none of these round trips sits between two barriers.
-        unsigned long long a_n = 0, b_n = 0;
-        int ep_n = 0, et_n = 0;
-        long prog_n = 0;
+        float4 xn, yn;
+        if (c < nchunks) load_raw(J, c * PC_CHUNK + warp * 128 + 4 * lane, xn, yn);
+        unsigned long long a_n = 0, b_n = 0;               // thread 0: hint words and prediction for the NEXT chunk
+        int ep_n = 0;
         auto decode_prog = [&](unsigned long long a) -> long { return ((a >> 32) == launch_id) ? (long)(a & 0xffffffffu) : 0; };
+        auto predicted = [&](int ep, unsigned long long b, long prog, int et) -> int {
+            const int e_seen = ((b >> 32) == launch_id) ? (int)(b & 0xffffffffu) : 0;
+            int e = ep;
+            if (e != 0 && e_seen != 0 && prog > 0 && prog < nchunks && et != 0) e += e_seen - et;
+            return e;
+        };
         if (tid == 0 && c < nchunks) {
-            a_n = ld_relaxed_u64(st_prog); b_n = ld_relaxed_u64(st_exp); ep_n = __ldcg(epred + c);
-            prog_n = decode_prog(a_n);
-            et_n = (prog_n > 0 && prog_n < nchunks) ? __ldcg(epred + prog_n) : 0;
+            const unsigned long long a = ld_relaxed_u64(st_prog), b = ld_relaxed_u64(st_exp);
+            const long prog = decode_prog(a);
+            const int et = (prog > 0 && prog < nchunks) ? __ldcg(epred + prog) : 0;
+            e_next_sh[0] = predicted(__ldcg(epred + c), b, prog, et);
+            skip_next_sh[0] = (prog > c) ? 1 : 0;
+            if (c + P < nchunks) { a_n = ld_relaxed_u64(st_prog); b_n = ld_relaxed_u64(st_exp); ep_n = __ldcg(epred + c + P); }
         }
+        __syncthreads();
+        long c_prev = -1;
+        int e_prev = 0;
         for (; c < nchunks; c += P, buf ^= 1) {
-            float t[4] = {tn[0], tn[1], tn[2], tn[3]};
-            if (c + P < nchunks) load_terms(J, (c + P) * PC_CHUNK + warp * 128 + 4 * lane, tn);      // next chunk in flight
-            if (tid == 0) {
-                const long prog = prog_n;
-                const int e_seen = ((b_n >> 32) == launch_id) ? (int)(b_n & 0xffffffffu) : 0;
-                int e = ep_n;
-                if (e != 0 && e_seen != 0 && prog > 0 && prog < nchunks && et_n != 0) e += e_seen - et_n;
-                e_sh = e; skip_sh = (prog > c) ? 1 : 0;                    // the consumer did this chunk itself
-                if (c + P < nchunks) { a_n = ld_relaxed_u64(st_prog); b_n = ld_relaxed_u64(st_exp); ep_n = __ldcg(epred + c + P); }
-            }
-            __syncthreads();
-            const int e = e_sh;
-            const bool skip = skip_sh != 0;
-            if (!skip) summarise_row3(e, t, wsum[buf], wflag[buf]);
-            __syncthreads();
-            if (tid == 0 && c + P < nchunks) {             // the hint words have arrived: prediction at the consumer's position
+            float t[4];
+            terms_from_raw(J, c * PC_CHUNK + warp * 128 + 4 * lane, xn, yn, t);
+            if (c + P < nchunks) load_raw(J, (c + P) * PC_CHUNK + warp * 128 + 4 * lane, xn, yn);      // next chunk in flight
+            const int e = e_next_sh[buf];
+            const bool skip = skip_next_sh[buf] != 0;       // the consumer did this chunk itself
+            int et_n = 0;
+            long prog_n = 0;
+            if (tid == 0 && c + P < nchunks) {              // the hint words have arrived: prediction at the consumer's position
                 prog_n = decode_prog(a_n);
                 et_n = (prog_n > 0 && prog_n < nchunks) ? __ldcg(epred + prog_n) : 0;
+            }
+            if (!skip) summarise_row3(e, t, wsum[buf], wflag[buf]);
+            if (tid == 0 && c + P < nchunks) {
+                e_next_sh[buf ^ 1] = predicted(ep_n, b_n, prog_n, et_n);
+                skip_next_sh[buf ^ 1] = (prog_n > c + P) ? 1 : 0;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                // the previous chunk's records were written before this barrier by the three record warps
+                if (c_prev >= 0) st_release_u32(ready + c_prev, (launch_id << 8) | (unsigned)(e_prev & 0xff));
+                if (c + 2 * P < nchunks) { a_n = ld_relaxed_u64(st_prog); b_n = ld_relaxed_u64(st_exp); ep_n = __ldcg(epred + c + 2 * P); }
             }
             if (!skip && warp < 3) {
                 SeqSum v = wsum[buf][warp][lane];
@@ -653,18 +754,25 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                     dst[0] = make_int4(v.total[0], v.total[1], v.pmin[0], v.pmin[1]);
                     dst[1] = make_int4(v.pmax[0], v.pmax[1], fl, 0);
                 }
-                const bool anybad = __any_sync(0xffffffffu, (fl & 1) != 0);
-                v = warp_scan(v, __any_sync(0xffffffffu, (fl & 2) != 0));
+                // A row that moves the running integer by 2^24 or more cannot be part of a record that fits, and
+                // the plain reduction below needs |row totals| < 2^24 (32 of them: no 32-bit overflow): such a
+                // chunk is marked unusable like one with a term too large.
+                const int lim = 1 << 24;
+                const bool big = v.total[0] >= lim || v.total[0] <= -lim || v.total[1] >= lim || v.total[1] <= -lim ||
+                                 v.pmax[0] >= lim || v.pmax[1] >= lim || v.pmin[0] <= -lim || v.pmin[1] <= -lim;
+                const bool anybad = __any_sync(0xffffffffu, (fl & 1) != 0 || big);
+                v = warp_summary(v, __any_sync(0xffffffffu, (fl & 2) != 0));        // valid in lane 31
                 if (lane == 31) {
                     int4 *dst = reinterpret_cast<int4 *>(rec + c * 3 + warp);
                     dst[0] = make_int4(v.total[0], v.total[1], v.pmin[0], v.pmin[1]);
                     dst[1] = make_int4(v.pmax[0], v.pmax[1], anybad ? 1 : 0, e - 1);
-                    __threadfence();
                 }
             }
-            __syncthreads();
-            if (!skip && tid == 0) st_release_u32(ready + c, (launch_id << 8) | (unsigned)((e_sh) & 0xff));      // e_base + 1 = e
+            c_prev = skip ? -1 : c;
+            e_prev = e;
         }
+        __syncthreads();                                   // the last chunk: published right away
+        if (tid == 0 && c_prev >= 0) st_release_u32(ready + c_prev, (launch_id << 8) | (unsigned)(e_prev & 0xff));
         return;
     }
 
@@ -720,7 +828,7 @@ seqsum_pipe_kernel(SeqLaunch jobs, float *__restrict__ out, SeqPipeDev pd, int P
                 }
                 const unsigned badmask = __ballot_sync(0xffffffffu, bad != 0);
                 const int nusable = (badmask == 0u) ? 32 : (__ffs(badmask) - 1);      // leading usable records
-                v = warp_scan(v, true);
+                v = scan_is_plain(v, true) ? warp_scan_plain(v, true) : warp_scan(v, true);
                 const int p = cc.M & 1;
                 const bool okl = lane < nusable && seq_block_ok(cc, v.pmin[p], v.pmax[p]);
                 const unsigned okmask = __ballot_sync(0xffffffffu, okl);
