@@ -166,7 +166,7 @@ long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uin
     size_t want = tsize / (1u << 20);
     const unsigned hc = std::thread::hardware_concurrency();
     want = std::min<size_t>(want, std::min<unsigned>(hc ? hc : 1u, 16u));
-    if (const char *e = getenv("DCA_B200_READER_THREADS")) want = (size_t)std::max(1, atoi(e));
+    if (const char *e = getenv("DCA_B200_READER_THREADS")) want = (size_t)std::min(256, std::max(1, atoi(e)));
     want = std::max<size_t>(want, 1);
     std::vector<Piece> pieces;
     {
