@@ -404,30 +404,29 @@ __global__ void __launch_bounds__(256)
 plm_unpack_kernel(const float *__restrict__ x, int L, int ld, float *__restrict__ W)
 {
     constexpr int QQ = Q * Q;
-    __shared__ float tile[AS_JG][QQ];
+    __shared__ float tile[AS_JG * QQ];
     const int i = blockIdx.y;
     const int j0 = blockIdx.x * AS_JG;
     if (j0 + AS_JG - 1 <= i) return;
-    const long Lq = (long)L * Q;
-    for (int jj = 0; jj < AS_JG; ++jj) {
-        const int j = j0 + jj;
-        if (j <= i || j >= L) continue;
-        const float *xb = x + Lq + pair_index(L, i, j) * QQ;
-        for (int t = threadIdx.x; t < QQ; t += 256) {
-            const float v = xb[t];
-            tile[jj][t] = v;
-            const int a = t / Q, b = t - a * Q;
-            W[((long)i * Q + a) * ld + j * Q + b] = v;
-        }
+    // pairs (i, jlo..jhi-1) are consecutive blocks of x: one contiguous run, one flat loop over its elements
+    // (a loop per pair left 185 of 256 threads idle in every second pass and paid its bookkeeping per pair)
+    const int jlo = max(j0, i + 1), jhi = min(j0 + AS_JG, L);
+    const int nel = (jhi - jlo) * QQ;
+    const float *xb = x + (long)L * Q + pair_index(L, i, jlo) * QQ;
+    float *Wi = W + (size_t)i * Q * ld + (size_t)jlo * Q;         // row (i, 0), column (jlo, 0)
+    for (int u = threadIdx.x; u < nel; u += 256) {
+        const float v = xb[u];
+        tile[u] = v;
+        const int jj = u / QQ, t = u - jj * QQ;
+        const int a = t / Q, b = t - a * Q;
+        Wi[(size_t)a * ld + jj * Q + b] = v;
     }
     __syncthreads();
-    for (int jj = 0; jj < AS_JG; ++jj) {
-        const int j = j0 + jj;
-        if (j <= i || j >= L) continue;
-        for (int t = threadIdx.x; t < QQ; t += 256) {
-            const int b = t / Q, a = t - b * Q;
-            W[((long)j * Q + b) * ld + i * Q + a] = tile[jj][a * Q + b];
-        }
+    float *Wj = W + (size_t)jlo * Q * ld + (size_t)i * Q;         // row (jlo, 0), column (i, 0)
+    for (int u = threadIdx.x; u < nel; u += 256) {
+        const int jj = u / QQ, t = u - jj * QQ;
+        const int b = t / Q, a = t - b * Q;
+        Wj[(size_t)(jj * Q + b) * ld + a] = tile[jj * QQ + a * Q + b];
     }
 }
 
