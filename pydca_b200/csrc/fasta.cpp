@@ -159,11 +159,11 @@ long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uin
     for (int c = 0; c < 256; ++c) lut[c] = (uint8_t)encode_residue(biomolecule, c);
     lut[(unsigned char)'\r'] = lut[(unsigned char)' '] = lut[(unsigned char)'\t'] = 255;
 
-    // Pieces of ~1 MB cut in front of header lines ("\n>"), one host thread each (translation and
+    // Pieces of >= 128 KB cut in front of header lines ("\n>"), one host thread each (translation and
     // hashing are the reader's time: 15 ms of a 31 ms mfDCA call at N = 20 000, L = 300 on one
     // thread); the first-occurrence de-duplication below walks the pieces in file order.
     const char *te = tb + tsize;
-    size_t want = tsize / (1u << 20);
+    size_t want = tsize / (1u << 17);               // 128 KB per piece and thread (a thread start costs ~50 us)
     const unsigned hc = std::thread::hardware_concurrency();
     want = std::min<size_t>(want, std::min<unsigned>(hc ? hc : 1u, 16u));
     if (const char *e = getenv("DCA_B200_READER_THREADS")) want = (size_t)std::min(256, std::max(1, atoi(e)));
