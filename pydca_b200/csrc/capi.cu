@@ -177,15 +177,15 @@ int dca_set_device(int device)
 unsigned long long dca_kernel_launches(void) { return g_launches.load(); }
 
 static std::mutex g_host_vec_mu;
-static std::unordered_map<void *, std::vector<uint8_t> *> g_host_vecs;      // buffers handed out by dca_read_fasta
+static std::unordered_map<void *, ByteVec *> g_host_vecs;      // buffers handed out by dca_read_fasta
 
 long dca_read_fasta(const char *msa_file, int biomolecule, int seqs_len, uint8_t **msa_out)
 {
     if (!msa_file || !msa_out || seqs_len <= 0) { set_error("dca_read_fasta: bad arguments"); return -1; }
     // the reader's own buffer is handed out (no copy of the alignment); dca_free_host finds it again
-    std::vector<uint8_t> *buf = nullptr;
+    ByteVec *buf = nullptr;
     try {
-        buf = new std::vector<uint8_t>();
+        buf = new ByteVec();
         const long n = read_fasta_unique(msa_file, biomolecule, seqs_len, *buf);
         if (n <= 0) { delete buf; return n; }
         {
@@ -704,7 +704,7 @@ static std::vector<int> even_bounds(int L, int G)
 }
 
 // returns 0 and fills x_host / res on success; -1 when the multi-GPU path could not run
-static int backend_multi_gpu(int G, const std::vector<uint8_t> &msa, std::vector<float> &w, bool have_w, long N, int L,
+static int backend_multi_gpu(int G, const ByteVec &msa, std::vector<float> &w, bool have_w, long N, int L,
                              int q, double seqid, float lh, float lJ, int max_it, int verbose, float *x_host,
                              dca_fit_result *res, bool trace)
 {
@@ -845,7 +845,7 @@ float *plmdcaBackend(unsigned short biomolecule, unsigned short num_site_states,
         fprintf(stderr, "plmdcaBackend: %s\n", last_error());
         return nullptr;
     }
-    std::vector<uint8_t> msa;
+    ByteVec msa;
     const long N = read_fasta_unique(msa_file, biomolecule == 1 ? 1 : 2, L, msa);       // plmdca_numerics.cpp:43
     if (N <= 0) { fprintf(stderr, "plmdcaBackend: %s\n", last_error()); return nullptr; }
     mark("read_fasta");

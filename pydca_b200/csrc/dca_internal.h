@@ -3,6 +3,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <memory>
+#include <new>
+#include <utility>
 #include <vector>
 
 #include "xrank.cuh"
@@ -54,7 +57,16 @@ int backend_gpu_count(int limit);
 
 // ---- fasta.cpp -----------------------------------------------------------------
 // FASTA -> u8 [N][L] (states 0..q-1, gap q-1), unique rows in first-occurrence order.
-long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uint8_t> &out);
+// bytes whose resize() does not zero-fill (the reader's threads write every byte themselves: a serial memset
+// and the page faults of a 25 MB alignment were most of the de-duplication pass)
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+    template <class U> struct rebind { using other = default_init_allocator<U>; };
+    template <class U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+using ByteVec = std::vector<uint8_t, default_init_allocator<uint8_t>>;
+long read_fasta_unique(const char *path, int biomolecule, int L, ByteVec &out);
 int encode_residue(int biomolecule, int c);
 
 // ---- reweight.cu -----------------------------------------------------------------

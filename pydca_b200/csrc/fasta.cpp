@@ -125,7 +125,7 @@ void parse_piece(Piece &pc, const uint8_t *lut, int L)
 
 }  // namespace
 
-long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uint8_t> &out)
+long read_fasta_unique(const char *path, int biomolecule, int L, ByteVec &out)
 {
     const auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *w) { if (getenv("DCA_B200_READER_TRACE")) fprintf(stderr, "[reader] %s %.2f ms\n", w, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count()); };
@@ -217,29 +217,51 @@ long read_fasta_unique(const char *path, int biomolecule, int L, std::vector<uin
 
     size_t total = 0;
     for (const Piece &pc : pieces) total += pc.hashes.size();
-    out.clear();
-    out.reserve(total * (size_t)L);
-    // open-addressing table of record indices keyed by the hash of the encoded record
+    // First occurrences in file order: a serial pass over the hashes only (open addressing, equality confirmed
+    // on the pieces' own bytes) gives every kept record its row; the bytes are then copied by one thread per
+    // piece into the output, which is sized without being zero-filled.
     size_t cap = 1024;
     while (cap < total * 2 + 16) cap <<= 1;
-    std::vector<long> slot(cap, -1);
+    std::vector<const uint8_t *> slot(cap, nullptr);
     std::vector<uint64_t> slot_hash(cap, 0);
+    std::vector<std::vector<long>> dest(pieces.size());    // per piece: output row of each record, -1 = duplicate
     long n = 0;
-    for (const Piece &pc : pieces) {
+    for (size_t t = 0; t < pieces.size(); ++t) {
+        const Piece &pc = pieces[t];
+        dest[t].resize(pc.hashes.size());
         for (size_t r = 0; r < pc.hashes.size(); ++r) {
             const uint8_t *rec = pc.recs.data() + r * (size_t)L;
             const uint64_t h = pc.hashes[r];
             size_t k = (size_t)h & (cap - 1);
             bool dup = false;
-            while (slot[k] >= 0) {                 // first occurrence wins (plmdca_numerics.cpp:756)
-                if (slot_hash[k] == h && std::memcmp(out.data() + (size_t)slot[k] * L, rec, (size_t)L) == 0) { dup = true; break; }
+            while (slot[k]) {                      // first occurrence wins (plmdca_numerics.cpp:756)
+                if (slot_hash[k] == h && std::memcmp(slot[k], rec, (size_t)L) == 0) { dup = true; break; }
                 k = (k + 1) & (cap - 1);
             }
-            if (dup) continue;
-            slot[k] = n; slot_hash[k] = h;
-            out.insert(out.end(), rec, rec + L);
-            ++n;
+            if (dup) { dest[t][r] = -1; continue; }
+            slot[k] = rec; slot_hash[k] = h;
+            dest[t][r] = n++;
         }
+    }
+    out.clear();
+    out.resize((size_t)n * (size_t)L);
+    auto copy_piece = [&](size_t t) {
+        const Piece &pc = pieces[t];
+        const std::vector<long> &d = dest[t];
+        for (size_t r = 0; r < d.size(); ++r)
+            if (d[r] >= 0) std::memcpy(out.data() + (size_t)d[r] * L, pc.recs.data() + r * (size_t)L, (size_t)L);
+    };
+    if (pieces.size() == 1) copy_piece(0);
+    else {
+        std::vector<std::thread> th;
+        size_t started = 1;
+        try {
+            for (; started < pieces.size(); ++started) th.emplace_back(copy_piece, started);
+        } catch (const std::system_error &) {
+        }
+        copy_piece(0);
+        for (size_t t = started; t < pieces.size(); ++t) copy_piece(t);
+        for (auto &x : th) x.join();
     }
     lap("merged");
     if (n == 0) { set_error("%s: no sequences found", path); return -3; }
