@@ -13,6 +13,9 @@
 //   * letters missing from the C++ map (e.g. 'T' in RNA) are gaps, as in the
 //     Python reader; the C++ reader aborts on them (:752).
 //   * de-duplication is hash-then-verify, O(N L) instead of O(N^2 L).
+// Large files are cut into pieces in front of header lines; the pieces are translated and hashed on host
+// threads, first occurrences are decided in one serial pass over the hashes in file order, and the kept
+// records are copied into the output by one thread per piece.
 #include "dca_common.cuh"
 #include "dca_internal.h"
 
