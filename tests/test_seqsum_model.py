@@ -126,3 +126,74 @@ def test_random_magnitude_profiles(model):
         if trial % 3 == 0:                       # quantised terms provoke exact ties
             t = np.round(t * 4) / 4
         _check_sum(model, t)
+
+
+# ---- the producer / consumer pipeline's decisions (seqsum_pipe_kernel), sequentially on the CPU ----
+@pytest.fixture(scope="module")
+def pipe(model):
+    for name, args in [("seq_pipe_model_sum", [_f32p, ctypes.c_long, _i64p]),
+                       ("seq_pipe_model_dot", [_f32p, _f32p, ctypes.c_long, _i64p])]:
+        f = getattr(model, name)
+        f.argtypes = args
+        f.restype = ctypes.c_float
+    return model
+
+
+def _check_pipe(pipe, t, y=None):
+    t = np.ascontiguousarray(t, dtype=np.float32)
+    stats = (ctypes.c_long * 4)()
+    if y is None:
+        a = pipe.seq_naive_sum(_p(t), t.size)
+        b = pipe.seq_pipe_model_sum(_p(t), t.size, stats)
+    else:
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        a = pipe.seq_naive_dot(_p(t), _p(y), t.size)
+        b = pipe.seq_pipe_model_dot(_p(t), _p(y), t.size, stats)
+    assert _bits(a) == _bits(b) or (np.isnan(a) and np.isnan(b)), (a, b, list(stats))
+    return dict(zip(("records", "row_walks", "exact", "plain_scans"), stats))
+
+
+def test_pipeline_model_gradient_like_and_cancelling(pipe):
+    """The pipeline's own sequence of decisions -- chunk records for the three exponents around a stale
+    prediction, steps over 32 records with the plain integer scan where it applies, the row walk, the
+    consumer CTA's exact path with per-row predictions -- equals the naive loop, and every path is taken."""
+    rng = np.random.default_rng(11)
+    n = 700_001
+    g = (rng.standard_normal(n) * 0.02).astype(np.float32)
+    g[:3150] = (rng.standard_normal(3150) * 40).astype(np.float32)
+    st = _check_pipe(pipe, g, g)
+    assert st["records"] > 0.9 * (n // 4096) and st["exact"] >= 1 and st["plain_scans"] > 0
+    d = (-g * rng.uniform(0.5, 1.5, n)).astype(np.float32)
+    _check_pipe(pipe, g, d)
+    s = (rng.standard_normal(n) * 1e-3).astype(np.float32)
+    _check_pipe(pipe, s, d)                              # an inner product like those of the two-loop recursion
+    st = _check_pipe(pipe, rng.standard_normal(n), rng.standard_normal(n))     # random signs: the exponent wanders
+    assert st["row_walks"] > 10 and st["records"] > 10
+
+
+def test_pipeline_model_adversarial(pipe):
+    rng = np.random.default_rng(12)
+    n = 300_017
+    hover = np.tile(np.concatenate([np.full(300, 0.37), np.full(300, -0.37)]), n // 600)
+    st = _check_pipe(pipe, np.concatenate([[1024.0], hover]))
+    assert st["row_walks"] + st["exact"] > 1             # the running value hovers at 2^10
+    _check_pipe(pipe, np.concatenate([[2048.0 - 30.0], hover + 1e-4, -hover - 3e-3]))
+    z = np.concatenate([np.zeros(3 * 4096 + 17), rng.standard_normal(100_000), [0.0]])
+    _check_pipe(pipe, np.concatenate([z, -z[::-1], np.zeros(5000), rng.standard_normal(90_000)]))
+    _check_pipe(pipe, np.concatenate([np.ones(2 ** 17), -np.ones(2 ** 17), np.full(100_000, 2.0 ** -30)]))
+    _check_pipe(pipe, rng.standard_normal(n) * np.exp(rng.uniform(-40, 40, n)))
+    wide = rng.standard_normal(n) * 0.01
+    wide[rng.integers(0, n, 100)] *= 1e9
+    _check_pipe(pipe, wide)
+    _check_pipe(pipe, np.round(rng.standard_normal(n) * 64) / 4)             # ties at every step: no plain scan
+    _check_pipe(pipe, np.concatenate([[2.0 ** 24], np.tile([1.0, 1.0, 3.0, -1.0], n // 4)]))
+    stag = np.full(n, 1e-4)
+    stag[0] = 4096.0
+    stag[rng.integers(1, n, 300)] = 0.5
+    _check_pipe(pipe, stag)
+    for bad in (np.inf, -np.inf, np.nan):
+        v = rng.standard_normal(n) * 0.1
+        v[n // 2 + 77] = bad
+        _check_pipe(pipe, v)
+    for m in (1, 4095, 4096, 4097, 70_001, 262_144, 262_145):              # ragged lengths
+        _check_pipe(pipe, rng.standard_normal(m))
