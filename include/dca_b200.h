@@ -55,8 +55,10 @@ int dca_set_gpus(int n);
 /* ---- FASTA ingest (host logic) ----------------------------------------------
  * plmdca_numerics.cpp:685-767 / fasta_reader.py:122-163: upper-case, encode to
  * 0..q-1 (gap and every unknown letter = q-1), keep the first occurrence of
- * each distinct sequence in file order.  *msa_out is malloc'd u8[N][seqs_len];
- * free with dca_free_host.  Returns N (>0) or a negative error. */
+ * each distinct sequence in file order.  *msa_out is a u8[N][seqs_len] buffer owned by
+ * the library (the reader's own output, no copy) until it is released with dca_free_host
+ * -- not with free().  Large files are parsed on host threads (DCA_B200_READER_THREADS).
+ * Returns N (>0) or a negative error. */
 long dca_read_fasta(const char *msa_file, int biomolecule, int seqs_len, uint8_t **msa_out);
 void dca_free_host(void *p);
 
